@@ -1,0 +1,259 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference estimators on CPU (build container only).
+
+    python -m oracle.gen_golden            # writes tests/golden/
+
+TEST INFRASTRUCTURE.  The reference (``/root/reference``) does not travel to the GPU box, so its outputs on seeded
+inputs are committed as fixtures.  Inputs and weights are regenerated from seeds by ``oracle/synth.py`` and
+``oracle/closed_form.make_params`` (numpy PCG64, version-stable); only the reference's OUTPUTS are stored.
+
+What is pinned (reference call sites in brackets):
+  logprob_*.npz   CoupledResidualFM.log_prob / FlowMatching.log_prob [pretrain.py:192-214, :112-134] with the
+                  probe injected through ``_rademacher`` / ``randint_like`` (ref_shim.injected_randomness), for the
+                  task dims of SURVEY section 8, n_steps 20 and 32, plus the exact trace built from a_dim runs of
+                  the reference with basis-vector probes.
+  vfield_*.npz    CoupledResidualFM.v_field / ConditionalVNet.forward [pretrain.py:156-158, networks.py:23-25,46-49]
+  fmloss_*.npz    fm_loss value and autograd gradients [pretrain.py:179-190, :94-109] with t / noise injected
+  train_*.npz     the update loop of flowril.py:311-335 (zero_grad, backward, clip_grad_norm_, Adam.step) for
+                  scrf (all params), scrf fine-tune (head_r only, flowril.py:52-63) and 2fs; loss curves + final
+                  parameters.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from oracle import closed_form as cf  # noqa: E402
+from oracle import ref_shim, synth  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def build_ref(P, spec: cf.NetSpec, flat: np.ndarray, eps=1e-3):
+    import torch
+
+    if spec.n_heads == 2:
+        model = P.CoupledResidualFM(spec.s_dim, spec.a_dim, spec.hidden, depth=spec.depth, eps=eps)
+    else:
+        model = P.FlowMatching(spec.s_dim, spec.a_dim, spec.hidden, depth=spec.depth, eps=eps)
+    sd = {k: torch.from_numpy(v.copy()) for k, v in cf.unpack(spec, flat).items()}
+    assert list(sd.keys()) == list(model.state_dict().keys()), (list(sd.keys()), list(model.state_dict().keys()))
+    model.load_state_dict(sd)
+    return model
+
+
+def ref_log_prob(P, model, spec, s, a, role, probe, n_steps):
+    """probe [B,a] shared by all steps, or [n_steps,B,a]."""
+    import torch
+
+    st, at = torch.from_numpy(s), torch.from_numpy(a)
+    probes = [torch.from_numpy(probe)] if probe.ndim == 2 else [torch.from_numpy(p) for p in probe]
+    with ref_shim.injected_randomness(P, probes=probes):
+        if spec.n_heads == 2:
+            with torch.enable_grad():
+                out = model.log_prob(st, at, role, n_steps=n_steps)
+        else:
+            out = model.log_prob(torch.cat([st, at], dim=-1), n_steps=n_steps)
+    return out.detach().numpy().astype(np.float32)
+
+
+def gen_logprob(P):
+    cases = []
+    for task in ("sine", "maze", "hopper", "halfcheetah", "ant", "hand", "pick"):
+        for n_heads in (2, 1):
+            for n_steps in ((20, 32) if task in ("maze", "sine") else (32,)):
+                cases.append((task, n_heads, n_steps, 256, 4, 2.0))
+    cases.append(("hopper", 2, 32, 128, 4, 1.0))
+    cases.append(("hopper", 2, 8, 128, 2, 2.0))
+    cases.append(("maze", 1, 32, 128, 3, 2.0))
+    for idx, (task, n_heads, n_steps, hidden, depth, gain) in enumerate(cases):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        spec = cf.NetSpec(s_dim, a_dim, hidden, depth, n_heads)
+        B = 96
+        seed = 1000 + idx
+        out = {"meta": np.array([s_dim, a_dim, hidden, depth, n_heads, n_steps, B, seed]), "gain": np.float32(gain)}
+        s, a = synth.states_actions(seed, B, s_dim, a_dim)
+        probe = synth.rademacher(seed + 1, (B, a_dim))
+        probe_steps = synth.rademacher(seed + 2, (n_steps, B, a_dim))
+        roles = ("expert", "agent")
+        for ri, role in enumerate(roles):
+            # scrf: one net, two roles.  2fs: two independent nets (flowril.py:88-99), role only picks the seed.
+            flat = cf.make_params(spec, seed + (10 * ri if n_heads == 1 else 0), gain)
+            model = build_ref(P, spec, flat)
+            out[f"logp_{role}"] = ref_log_prob(P, model, spec, s, a, role, probe, n_steps)
+            out[f"logp_{role}_stepprobe"] = ref_log_prob(P, model, spec, s, a, role, probe_steps, n_steps)
+            if a_dim <= 8:
+                # exact trace from the unmodified reference: probe e_i gives prior(a_1) - delta*sum_k J_ii, and
+                # the primal trajectory does not depend on the probe.
+                runs = []
+                for i in range(a_dim):
+                    e = np.zeros((B, a_dim), np.float32)
+                    e[:, i] = 1.0
+                    runs.append(ref_log_prob(P, model, spec, s, a, role, e, n_steps).astype(np.float64))
+                zero = ref_log_prob(P, model, spec, s, a, role, np.zeros((B, a_dim), np.float32), n_steps)
+                out[f"logp_{role}_exact"] = (sum(runs) - (a_dim - 1) * zero.astype(np.float64)).astype(np.float32)
+        name = f"logprob_{idx:02d}_{task}_{'scrf' if n_heads == 2 else '2fs'}_h{hidden}d{depth}_n{n_steps}.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print("wrote", name, out["logp_expert"][:3])
+
+
+def gen_vfield(P):
+    import torch
+
+    for idx, (task, n_heads) in enumerate((("hopper", 2), ("maze", 1), ("ant", 2), ("sine", 2))):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        spec = cf.NetSpec(s_dim, a_dim, 256, 4, n_heads)
+        seed, B = 2000 + idx, 80
+        flat = cf.make_params(spec, seed, 2.0)
+        model = build_ref(P, spec, flat)
+        s, a = synth.states_actions(seed, B, s_dim, a_dim)
+        t = synth.rng(seed + 1).random((B, 1), dtype=np.float32)
+        st, at, tt = map(torch.from_numpy, (s, a, t))
+        out = {"meta": np.array([s_dim, a_dim, 256, 4, n_heads, 0, B, seed]), "gain": np.float32(2.0)}
+        with torch.no_grad():
+            if n_heads == 2:
+                out["v_expert"] = model.v_field(at, st, tt, "expert").numpy()
+                out["v_agent"] = model.v_field(at, st, tt, "agent").numpy()
+                vc, r = model.net(at, st, tt)
+                out["v_c"], out["r"] = vc.numpy(), r.numpy()
+            else:
+                out["v"] = model.net(at, st, tt).numpy()
+        name = f"vfield_{idx:02d}_{task}_{'scrf' if n_heads == 2 else '2fs'}.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print("wrote", name)
+
+
+def ref_fm_loss(P, model, spec, s, a, role, u, noise, dequant=None):
+    """u is the raw U[0,1) draw: the reference maps it to t = u*(1-2eps)+eps itself (pretrain.py:99, :182)."""
+    import torch
+
+    st, at = torch.from_numpy(s), torch.from_numpy(a)
+    kw = dict(rand=[torch.from_numpy(u)], normal=[torch.from_numpy(noise)])
+    if dequant is not None:
+        # reference scales randn_like by dequant_std itself (pretrain.py:98): feed unit-scale noise
+        kw["randn_like"] = [torch.from_numpy(dequant)]
+    with ref_shim.injected_randomness(P, **kw):
+        if spec.n_heads == 2:
+            return model.fm_loss(st, at, role)
+        return model.fm_loss(st, at)
+
+
+def flat_grads(model):
+    return np.concatenate([
+        (p.grad if p.grad is not None else p.new_zeros(p.shape)).detach().numpy().ravel() for p in model.parameters()
+    ]).astype(np.float32)
+
+
+def gen_fmloss(P):
+    cases = [("hopper", 2, 128, True), ("maze", 1, 128, True), ("sine", 2, 128, True),
+             ("halfcheetah", 2, 256, False), ("ant", 2, 256, False), ("hand", 1, 256, False)]
+    for idx, (task, n_heads, hidden, store_grad) in enumerate(cases):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        spec = cf.NetSpec(s_dim, a_dim, hidden, 4, n_heads)
+        seed, B = 3000 + idx, 200
+        flat = cf.make_params(spec, seed, 2.0)
+        s, a = synth.states_actions(seed, B, s_dim, a_dim)
+        out = {"meta": np.array([s_dim, a_dim, hidden, 4, n_heads, 0, B, seed]), "gain": np.float32(2.0)}
+        for ri, role in enumerate(("expert", "agent")):
+            model = build_ref(P, spec, flat)
+            _, noise, u = synth.cfm_draws(seed + 1 + ri, B, a_dim, return_u=True)
+            dq = synth.rng(seed + 5 + ri).standard_normal((B, a_dim)).astype(np.float32) if n_heads == 1 else None
+            loss = ref_fm_loss(P, model, spec, s, a, role, u, noise, dq)
+            loss.backward()
+            g = flat_grads(model)
+            out[f"loss_{role}"] = np.float32(loss.item())
+            out[f"gradnorm_{role}"] = np.float32(np.sqrt((g.astype(np.float64) ** 2).sum()))
+            # per-tensor norms for every case; the full gradient only for the small nets
+            norms, off = [], 0
+            for _, shape in spec.shapes():
+                n = int(np.prod(shape))
+                norms.append(np.sqrt((g[off:off + n].astype(np.float64) ** 2).sum()))
+                off += n
+            out[f"tensor_gradnorms_{role}"] = np.array(norms, np.float32)
+            if store_grad:
+                out[f"grad_{role}"] = g
+        name = f"fmloss_{idx:02d}_{task}_{'scrf' if n_heads == 2 else '2fs'}_h{hidden}.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print("wrote", name, out["loss_expert"], out["loss_agent"])
+
+
+def gen_train(P):
+    """flowril.py:311-335 for scrf (no regularisers: configs/sine/flowril-no-as.yaml), scrf fine-tune with frozen
+    trunk + head_c (flowril.py:52-63) and 2fs both nets (flowril.py:108-109).  Role swap quirk
+    lives above fm_loss and is not part of this fixture: batch 'E' is fed to role expert, batch 'A' to role agent."""
+    import torch
+
+    for idx, (task, kind, hidden, steps, lr) in enumerate((
+            ("hopper", "scrf", 128, 1000, 1e-3),
+            ("hopper", "scrf_ft", 128, 50, 1e-3),
+            ("maze", "2fs", 128, 50, 1e-3),
+            ("sine", "scrf", 128, 200, 1e-3),
+    )):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        n_heads = 1 if kind == "2fs" else 2
+        spec = cf.NetSpec(s_dim, a_dim, hidden, 4, n_heads)
+        seed, B = 4000 + idx, 128
+        models = [build_ref(P, spec, cf.make_params(spec, seed, 1.0))]
+        if kind == "2fs":
+            models.append(build_ref(P, spec, cf.make_params(spec, seed + 10, 1.0)))
+        if kind == "scrf_ft":
+            for p in models[0].net.shared.parameters():
+                p.requires_grad = False
+            for p in models[0].net.head_c.parameters():
+                p.requires_grad = False
+        all_params = [p for m in models for p in m.parameters()]
+        opt = torch.optim.Adam([p for p in all_params if p.requires_grad], lr=lr)
+        pool_s, _ = synth.states_actions(seed + 1, 4096, s_dim, a_dim)
+        pool_aE = synth.expert_actions(seed + 2, pool_s, a_dim)
+        pool_aA = np.clip(synth.rng(seed + 3).standard_normal((4096, a_dim)), -1, 1).astype(np.float32)
+        curve = np.zeros((steps, 2), np.float32)
+        norms = np.zeros(steps, np.float32)
+        for it in range(steps):
+            g = synth.rng(seed + 100 + it)
+            iE, iA = g.integers(0, 4096, B), g.integers(0, 4096, B)
+            _, nE, tE = synth.cfm_draws(seed + 10000 + 2 * it, B, a_dim, return_u=True)  # tE/tA: raw uniforms
+            _, nA, tA = synth.cfm_draws(seed + 10001 + 2 * it, B, a_dim, return_u=True)
+            dqE = dqA = None
+            if kind == "2fs":
+                dqE = synth.rng(seed + 50000 + 2 * it).standard_normal((B, a_dim)).astype(np.float32)
+                dqA = synth.rng(seed + 50001 + 2 * it).standard_normal((B, a_dim)).astype(np.float32)
+            lE = ref_fm_loss(P, models[0], spec, pool_s[iE], pool_aE[iE], "expert", tE, nE, dqE)
+            lA = ref_fm_loss(P, models[-1], spec, pool_s[iA], pool_aA[iA], "agent", tA, nA, dqA)
+            loss = 1.0 * lE + 1.0 * lA  # flowril.py:253 with the default rates
+            opt.zero_grad()
+            loss.backward()
+            norms[it] = float(torch.nn.utils.clip_grad_norm_(all_params, 1.0))  # flowril.py:324-329, disc_grad_pen=1
+            opt.step()
+            curve[it] = (lE.item(), lA.item())
+        out = {"meta": np.array([s_dim, a_dim, hidden, 4, n_heads, steps, B, seed]), "lr": np.float32(lr),
+               "curve": curve, "gradnorm": norms}
+        for mi, m in enumerate(models):
+            out[f"final_params_{mi}"] = np.concatenate([p.detach().numpy().ravel() for p in m.parameters()])
+        name = f"train_{idx:02d}_{task}_{kind}_h{hidden}_{steps}steps.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print("wrote", name, curve[0], curve[-1])
+
+
+def main():
+    import torch
+
+    assert ref_shim.available(), "reference checkout not found"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    P = ref_shim.load()
+    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train"]
+    if "logprob" in which:
+        gen_logprob(P)
+    if "vfield" in which:
+        gen_vfield(P)
+    if "fmloss" in which:
+        gen_fmloss(P)
+    if "train" in which:
+        gen_train(P)
+
+
+if __name__ == "__main__":
+    main()
