@@ -1,0 +1,145 @@
+/*
+ * flowril_b200.h -- C ABI of libflowril_b200.so: the B200 (sm_100a) implementation of the FLOWRIL/MODRIL
+ * flow-matching occupancy-density hot path (velocity-field MLP, ODE log-density with divergence, coupled-residual
+ * reward, conditional-flow-matching gradient, grad-clip + Adam).
+ *
+ * The reference (hhhhzl/MODRIL) is pure Python/PyTorch and has no FFI of its own; the
+ * boundary it exposes for this path is a Python class contract.  Each entry point below is what a binding for
+ * that contract calls, and cites the reference interface it replaces (paths relative to the reference checkout).
+ * The reference-side binding (ctypes) is shown in INTEGRATION.md; modril_b200/_native.py is that binding.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types.  All "dev" pointers are CUDA device pointers on the
+ *     device the net was created on; "host" pointers are ordinary host memory.
+ *   - every function returns 0 on success, a negative frl_status otherwise; frl_last_error() gives the message
+ *     (thread-local).  Nothing throws, nothing calls exit().
+ *   - work is enqueued on the caller's `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *     with no hidden synchronisation, except the *_host entry points which return after their results are in
+ *     host memory.
+ *   - a frl_net is not thread-safe; distinct nets may be used from distinct threads.
+ *   - matrices are row-major float32: s [B, s_dim], a [B, a_dim], probe [B, a_dim], t [B] ...
+ *   - parameters travel as ONE flat float32 vector in the reference's state_dict order
+ *     (modril/flowril/networks.py:13-21 SharedVNet, :37-44 ConditionalVNet):
+ *        trunk layer l: weight [H, K_l] then bias [H]  (K_0 = a_dim + s_dim + 1, input columns = [a | s | t])
+ *        n_heads == 2:  head_c.weight [a,H], head_c.bias [a], head_r.weight [a,H], head_r.bias [a]
+ *        n_heads == 1:  out.weight [a,H], out.bias [a]
+ */
+#ifndef FLOWRIL_B200_H
+#define FLOWRIL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FRL_ABI_VERSION 1
+#define FRL_MAX_STEPS 256
+#define FRL_MAX_DEPTH 8
+
+typedef enum {
+    FRL_OK = 0,
+    FRL_ERR_INVALID = -1,     /* bad argument / unsupported dimensions */
+    FRL_ERR_CUDA = -2,        /* a CUDA runtime call failed            */
+    FRL_ERR_UNSUPPORTED = -3, /* valid request this build cannot serve */
+    FRL_ERR_NOMEM = -4
+} frl_status;
+
+/* arithmetic mode of the log-density / velocity kernels */
+typedef enum {
+    FRL_PREC_FP32 = 0,    /* FP32 FFMA on CUDA cores: the 1e-4 parity mode                               */
+    FRL_PREC_BF16 = 1,    /* tcgen05 tensor cores, bf16 operands, fp32 accumulate, fp32 ODE state/trace  */
+    FRL_PREC_BF16X3 = 2   /* tcgen05, 3-term bf16 split of both operands (fp32-grade products)           */
+} frl_precision;
+
+/* divergence estimator of the log-density (modril/flowril/pretrain.py:88-92, :163-177) */
+typedef enum {
+    FRL_PROBE_SHARED = 0,   /* probe [B,a] reused at every Euler step (scrf: _rademacher is shape-deterministic) */
+    FRL_PROBE_PER_STEP = 1, /* probe [n_steps,B,a], fresh per step (2fs: randint_like, pretrain.py:90)           */
+    FRL_PROBE_EXACT = 2     /* exact Jacobian trace: a_dim basis tangents, probe pointer ignored                  */
+} frl_probe_mode;
+
+/* reward transform, modril/flowril/flowril.py:191-207 (--reward-type) */
+typedef enum { FRL_REWARD_RAW = 0, FRL_REWARD_NORM = 1, FRL_REWARD_EXP = 2, FRL_REWARD_CLIP = 3,
+               FRL_REWARD_SMOOTH = 4 } frl_reward_type;
+
+typedef struct {
+    int s_dim;     /* state dimension                                                            */
+    int a_dim;     /* action dimension (the ODE state)                                           */
+    int hidden;    /* trunk width H: 128 or 256                                                  */
+    int depth;     /* number of hidden layers, 1..FRL_MAX_DEPTH (networks.py:12 max(1, depth))   */
+    int n_heads;   /* 2 = SharedVNet (head_c + tanh(head_r)), 1 = ConditionalVNet                */
+    int device;    /* CUDA device ordinal                                                        */
+} frl_net_config;
+
+typedef struct frl_net frl_net; /* opaque: packed device copies of one velocity net + workspaces */
+
+int frl_abi_version(void);
+const char* frl_last_error(void);
+
+/* Replaces SharedVNet.__init__ / ConditionalVNet.__init__ + .to(device) (networks.py:10-21, :34-44;
+ * constructed by CoupledResidualFM / FlowMatching at pretrain.py:80, :153 and flowril.py:42-46, :88-99). */
+int frl_net_create(const frl_net_config* cfg, frl_net** out);
+int frl_net_destroy(frl_net* net);
+long long frl_net_num_params(const frl_net* net);
+
+/* (Re)pack kernel-side weight layouts from the flat fp32 master copy (device pointer, state_dict order).
+ * Replaces what load_state_dict / optimizer.step leave implicit in the reference (flowril.py:48-49, :330):
+ * call after every change of the master weights. */
+int frl_net_set_params(frl_net* net, const float* params_dev, void* stream);
+
+/* SharedVNet.forward / ConditionalVNet.forward (networks.py:23-25, :46-49).
+ * out0 [B,a] = v_c (n_heads 2) or v (n_heads 1); out1 [B,a] = tanh(head_r) (n_heads 2; may be NULL).
+ * t_dev [B] per-row times. */
+int frl_vfield(const frl_net* net, const float* s_dev, const float* a_dev, const float* t_dev,
+               float* out0_dev, float* out1_dev, long long B, int precision, void* stream);
+
+/* CoupledResidualFM.log_prob (pretrain.py:192-214) / FlowMatching.log_prob (:112-134) for one role.
+ * role_sign: +1 expert (v_c + r), -1 agent (v_c - r) (pretrain.py:156-158); ignored when n_heads == 1.
+ * t_mid_host [n_steps]: midpoint times 0.5*(g_k+g_{k+1}) of the caller's fp32 linspace (pretrain.py:122, :206);
+ * delta = 1/n_steps.  out_logp_dev [B]. */
+int frl_logprob(const frl_net* net, float role_sign, const float* s_dev, const float* a_dev,
+                const float* probe_dev, int probe_mode, const float* t_mid_host, int n_steps,
+                float* out_logp_dev, long long B, int precision, void* stream);
+
+/* FlowMatchingEstimation._compute_flow_reward / _compute_disc_val (flowril.py:175-208, :352-365): both roles in
+ * one launch.  net_expert scores role expert, net_agent role agent; pass the same net twice for scrf.
+ * Any of out_logp_e / out_logp_a / out_reward may be NULL.  reward = transform(logp_e - logp_a). */
+int frl_score(const frl_net* net_expert, const frl_net* net_agent, const float* s_dev, const float* a_dev,
+              const float* probe_dev, int probe_mode, const float* t_mid_host, int n_steps, int reward_type,
+              float* out_logp_e_dev, float* out_logp_a_dev, float* out_reward_dev, long long B, int precision,
+              void* stream);
+
+/* Same as frl_score with HOST buffers: chunks the batch, overlaps H2D / kernel / D2H on internal streams and
+ * returns when the outputs are in host memory (the end-to-end call bench.py times as `e2e`). */
+int frl_score_host(frl_net* net_expert, frl_net* net_agent, const float* s_host, const float* a_host,
+                   const float* probe_host, int probe_mode, const float* t_mid_host, int n_steps, int reward_type,
+                   float* out_logp_e_host, float* out_logp_a_host, float* out_reward_host, long long B,
+                   int precision);
+
+/* CoupledResidualFM.fm_loss / FlowMatching.fm_loss followed by backward (pretrain.py:179-190, :94-109;
+ * flowril.py:317-322) with caller-supplied randomness: t_dev [B] in [eps, 1-eps], noise_dev [B,a] ~ N(0,1).
+ * Computes L = mean_b (1-t_b)^1.5 sum_j (v_role - (noise - a0))^2, writes it to loss_dev[0] and ADDS
+ * grad_scale * dL/dtheta into grad_dev (flat, state_dict order) when accumulate != 0, else overwrites.
+ * (For 2fs the caller adds the dequantisation noise to a0 first, pretrain.py:98.)
+ * Deterministic: fixed reduction order, no float atomics.  mean_divisor: the B of the mean (the global batch
+ * when the rows are one data-parallel shard); <= 0 means B. */
+int frl_cfm_loss_grad(frl_net* net, float role_sign, const float* s_dev, const float* a0_dev, const float* t_dev,
+                      const float* noise_dev, long long B, long long mean_divisor, float grad_scale,
+                      int accumulate, float* loss_dev, float* grad_dev, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step (flowril.py:324-330; Adam defaults betas (0.9,0.999),
+ * eps 1e-8, no weight decay) over up to 4 flat segments that share one global gradient norm.
+ * step = 1-based step count after increment.  norm_out_dev[0] receives the pre-clip total norm (may be NULL). */
+typedef struct {
+    float* params;      /* [n] master weights, updated in place */
+    const float* grad;  /* [n]                                  */
+    float* exp_avg;     /* [n] Adam m                           */
+    float* exp_avg_sq;  /* [n] Adam v                           */
+    long long n;
+} frl_adam_segment;
+int frl_clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double lr, double beta1, double beta2,
+                  double eps, double max_norm, float* norm_out_dev, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWRIL_B200_H */

@@ -1,0 +1,89 @@
+"""ctypes binding of libflowril_b200.so (the C ABI in include/flowril_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, this raises.  The library is built in-tree by
+``python -m modril_b200.build`` (``__graft_entry__.build()``), never JIT-compiled into a cache directory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libflowril_b200.so")
+
+ABI_VERSION = 1
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+PROBE_SHARED, PROBE_PER_STEP, PROBE_EXACT = 0, 1, 2
+REWARD_TYPES = {"raw": 0, "norm": 1, "exp": 2, "clip": 3, "smooth": 4}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
+
+# every symbol include/flowril_b200.h declares (tests/test_abi.py checks the header against this list)
+EXPORTS = (
+    "frl_abi_version", "frl_last_error", "frl_net_create", "frl_net_destroy", "frl_net_num_params",
+    "frl_net_set_params", "frl_vfield", "frl_logprob", "frl_score", "frl_score_host", "frl_cfm_loss_grad",
+    "frl_clip_adam",
+)
+
+
+class NetConfig(C.Structure):
+    _fields_ = [("s_dim", C.c_int), ("a_dim", C.c_int), ("hidden", C.c_int), ("depth", C.c_int),
+                ("n_heads", C.c_int), ("device", C.c_int)]
+
+
+class AdamSegment(C.Structure):
+    _fields_ = [("params", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("n", C.c_longlong)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} not found: build it with `python -m modril_b200.build` (there is no CPU/PyTorch fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, ll, i32, f32, f64 = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_double
+    L.frl_abi_version.restype = i32
+    L.frl_last_error.restype = C.c_char_p
+    L.frl_net_create.argtypes = [C.POINTER(NetConfig), C.POINTER(vp)]
+    L.frl_net_destroy.argtypes = [vp]
+    L.frl_net_num_params.argtypes = [vp]
+    L.frl_net_num_params.restype = ll
+    L.frl_net_set_params.argtypes = [vp, vp, vp]
+    L.frl_vfield.argtypes = [vp, vp, vp, vp, vp, vp, ll, i32, vp]
+    L.frl_logprob.argtypes = [vp, f32, vp, vp, vp, i32, C.POINTER(f32), i32, vp, ll, i32, vp]
+    L.frl_score.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(f32), i32, i32, vp, vp, vp, ll, i32, vp]
+    L.frl_score_host.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(f32), i32, i32, vp, vp, vp, ll, i32]
+    L.frl_cfm_loss_grad.argtypes = [vp, f32, vp, vp, vp, vp, ll, ll, f32, i32, vp, vp, vp]
+    L.frl_clip_adam.argtypes = [C.POINTER(AdamSegment), i32, ll, f64, f64, f64, f64, f64, vp, i32, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("frl_last_error", "frl_net_num_params"):
+            fn.restype = i32
+    if L.frl_abi_version() != ABI_VERSION:
+        raise NativeError(f"ABI mismatch: library {L.frl_abi_version()} != binding {ABI_VERSION}")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc == 0:
+        return
+    msg = lib().frl_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(f"{what}: {msg}")
+    raise NativeError(f"{what} failed (status {rc}): {msg}")
+
+
+def float_array(values):
+    arr = (C.c_float * len(values))(*[float(v) for v in values])
+    return arr

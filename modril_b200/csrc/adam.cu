@@ -1,0 +1,115 @@
+// Global grad-norm clip + Adam over flat fp32 segments, deterministic (fixed reduction order, no float atomics).
+// Replaces torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step as called at
+// modril/flowril/flowril.py:324-330 (and modril/flowril/pretrain.py:417-420).
+#include <cmath>
+
+#include "frl_internal.h"
+
+namespace frl {
+
+constexpr int kNormBlocks = 296;  // 2 per SM
+constexpr int kNormThreads = 256;
+
+struct Segs {
+    frl_adam_segment s[4];
+    long long first[5];
+    int n;
+};
+
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[kNormThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < kNormThreads / 32; ++i) t += sh[i];
+    return t;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kNormThreads) sumsq_kernel(Segs sg, double* __restrict__ partial) {
+    const long long total = sg.first[sg.n];
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    const long long lo = blockIdx.x * per, hi = min(total, lo + per);
+    double acc = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        int k = 0;
+        while (k + 1 < sg.n && sg.first[k + 1] <= i) ++k;
+        const float g = sg.s[k].grad[i - sg.first[k]];
+        acc += (double)g * (double)g;
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+struct AdamScalars {
+    float one_minus_b1, b2, one_minus_b2, sqrt_bc2, eps, neg_step_size, max_norm;
+};
+
+__global__ void __launch_bounds__(256) adam_kernel(Segs sg, const double* __restrict__ partial, int n_partial,
+                                                   AdamScalars sc, float* __restrict__ norm_out) {
+    __shared__ float s_coef;
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < n_partial; ++i) t += partial[i];  // same order in every block
+        const float norm = (float)sqrt(t);
+        float coef = sc.max_norm / (norm + 1e-6f);               // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
+        s_coef = coef < 1.f ? coef : 1.f;
+        if (blockIdx.x == 0 && norm_out) norm_out[0] = norm;
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const long long total = sg.first[sg.n];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int k = 0;
+        while (k + 1 < sg.n && sg.first[k + 1] <= i) ++k;
+        const long long j = i - sg.first[k];
+        const frl_adam_segment& s = sg.s[k];
+        const float g = s.grad[j] * coef;
+        float m = s.exp_avg[j];
+        float v = s.exp_avg_sq[j];
+        m = m + (g - m) * sc.one_minus_b1;                         // exp_avg.lerp_(grad, 1 - beta1)
+        v = v * sc.b2 + sc.one_minus_b2 * g * g;                   // mul_(beta2).addcmul_(g, g, 1 - beta2)
+        const float denom = sqrtf(v) / sc.sqrt_bc2 + sc.eps;  // sqrt(v)/sqrt(bc2) + eps
+        s.params[j] = s.params[j] + sc.neg_step_size * (m / denom);
+        s.exp_avg[j] = m;
+        s.exp_avg_sq[j] = v;
+    }
+}
+
+int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double lr, double beta1, double beta2,
+              double eps, double max_norm, float* norm_out, cudaStream_t stream) {
+    Segs sg{};
+    sg.n = n_segs;
+    long long total = 0;
+    for (int i = 0; i < n_segs; ++i) {
+        sg.s[i] = segs[i];
+        sg.first[i] = total;
+        total += segs[i].n;
+    }
+    sg.first[n_segs] = total;
+    if (total == 0) return FRL_OK;
+    double* partial = nullptr;
+    FRL_CUDA(cudaMallocAsync((void**)&partial, kNormBlocks * sizeof(double), stream));
+    sumsq_kernel<<<kNormBlocks, kNormThreads, 0, stream>>>(sg, partial);
+    FRL_CUDA(cudaGetLastError());
+    const double bc1 = 1.0 - std::pow(beta1, (double)step);
+    const double bc2 = 1.0 - std::pow(beta2, (double)step);
+    AdamScalars sc;
+    sc.one_minus_b1 = (float)(1.0 - beta1);
+    sc.b2 = (float)beta2;
+    sc.one_minus_b2 = (float)(1.0 - beta2);
+    sc.sqrt_bc2 = (float)std::sqrt(bc2);
+    sc.eps = (float)eps;
+    sc.neg_step_size = (float)(-lr / bc1);
+    sc.max_norm = (float)max_norm;
+    int blocks = (int)std::min<long long>((total + 255) / 256, 592);
+    adam_kernel<<<blocks, 256, 0, stream>>>(sg, partial, kNormBlocks, sc, norm_out);
+    FRL_CUDA(cudaGetLastError());
+    FRL_CUDA(cudaFreeAsync(partial, stream));
+    return FRL_OK;
+}
+
+}  // namespace frl

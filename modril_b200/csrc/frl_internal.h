@@ -1,0 +1,106 @@
+// Internal declarations shared by the translation units of libflowril_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/flowril_b200.h"
+
+namespace frl {
+
+constexpr int kMaxDepth = FRL_MAX_DEPTH;
+constexpr int kMaxSteps = FRL_MAX_STEPS;
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define FRL_CUDA(expr)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return ::frl::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define FRL_REQUIRE(cond, msg)                         \
+    do {                                               \
+        if (!(cond)) {                                 \
+            ::frl::set_error(std::string("invalid argument: ") + (msg)); \
+            return FRL_ERR_INVALID;                    \
+        }                                              \
+    } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Device-side view of one packed net for the FP32 (FFMA) kernels.
+struct NetF32 {
+    const float* Wt[kMaxDepth];  // trunk layer l, K-major (transposed): [Kp_l][H], Kp_0 = round_up(d_in,16) zero padded
+    const float* W[kMaxDepth];   // trunk layer l, reference layout padded: [H][Kp_l]
+    const float* b[kMaxDepth];   // [H]
+    const float* Wh;             // heads, reference layout, rows padded: [NOp][H], NOp = round_up(n_heads*a_dim,16)
+    const float* Wht;            // heads, K-major: [H][NOp]
+    const float* bh;             // [NOp]
+};
+
+}  // namespace frl
+
+// Opaque handle of the C ABI.
+struct frl_net {
+    frl_net_config cfg;
+    int d_in, d_in_p, n_out, n_out_p;   // a+s+1, padded; n_heads*a_dim, padded
+    long long n_params;
+    long long off_w[frl::kMaxDepth], off_b[frl::kMaxDepth];  // offsets into the flat vector
+    long long off_wh[2], off_bh[2];
+    float* pack_f32 = nullptr;          // one allocation holding every NetF32 array
+    size_t pack_f32_floats = 0;
+    frl::NetF32 f32;
+    // tensor-core packing (bf16 hi/mid/lo canonical UMMA tiles), see logprob_tc.cu
+    void* pack_tc = nullptr;
+    size_t pack_tc_bytes = 0;
+    bool has_params = false;
+    // training workspace (grown on demand)
+    float* ws = nullptr;
+    size_t ws_floats = 0;
+    // host-staging state for frl_score_host
+    void* host_stage = nullptr;
+};
+
+void frl_host_stage_free(frl_net* net);  // api.cu
+
+namespace frl {
+
+// logprob_f32.cu
+struct ScoreArgs {
+    const frl_net* net[2];  // role slots (expert, agent); net[1] may be null when n_roles == 1
+    float sign[2];
+    int n_roles;
+    const float* s;
+    const float* a;
+    const float* probe;
+    int probe_mode;
+    const float* t_mid_host;
+    int n_steps;
+    int reward_type;        // -1: no reward output
+    float* out_logp[2];
+    float* out_reward;
+    long long B;
+};
+int launch_logprob_f32(const ScoreArgs& args, cudaStream_t stream);
+int launch_vfield_f32(const frl_net* net, const float* s, const float* a, const float* t, float* out0, float* out1,
+                      long long B, cudaStream_t stream);
+int launch_reward(const float* logp_e, const float* logp_a, float* reward, long long B, int reward_type,
+                  cudaStream_t stream);
+
+// logprob_tc.cu
+int tc_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
+int launch_logprob_tc(const ScoreArgs& args, int precision, cudaStream_t stream);
+
+// train_f32.cu
+int cfm_loss_grad_f32(frl_net* net, float role_sign, const float* s, const float* a0, const float* t,
+                      const float* noise, long long B, long long mean_divisor, float grad_scale, int accumulate,
+                      float* loss, float* grad, cudaStream_t stream);
+
+// adam.cu
+int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double lr, double beta1, double beta2,
+              double eps, double max_norm, float* norm_out, cudaStream_t stream);
+
+}  // namespace frl

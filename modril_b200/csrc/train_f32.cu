@@ -1,0 +1,368 @@
+// FP32 conditional-flow-matching loss + gradient (forward, backward) for one role batch.
+// Replaces  fm_loss(...) ; loss.backward()  of the reference (modril/flowril/pretrain.py:179-190, :94-109;
+// modril/flowril/flowril.py:317-322) with hand-written SGEMM-class kernels:
+//   forward  : X0 = [a_t | s | t],  H_l = relu(H_{l-1} W_l^T + b_l),  V = H_L Wh^T + bh
+//   loss     : L = (1/Bdiv) sum_b (1-t_b)^1.5 sum_j (v_bj - (noise - a0)_bj)^2 ;  dV in place of V
+//   backward : dWh = dV^T H_L, dbh = colsum dV, dH_L = dV Wh ; per layer dZ = dH * (H>0),
+//              dW_l = dZ^T H_{l-1} (split over the batch, partials reduced in fixed order), db_l = colsum dZ,
+//              dH_{l-1} = dZ W_l
+// Everything is deterministic: no float atomics, fixed split counts for a given (B, net).
+#include <algorithm>
+#include <cmath>
+
+#include "frl_internal.h"
+
+namespace frl {
+
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_MASK = 3 };
+constexpr int BK = 16;
+
+// C[M][N] (+ split offset) = op(A) * B.   A_TRANS=false: A is [M][lda] (k contiguous); true: A is [K][lda]
+// (m contiguous).  B is [K][ldb].  M guarded per row, N per float4, K per row (zero fill).
+template <int BM, int BN, int TM, int TN, bool A_TRANS, int EPI>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B,
+                                                    int ldb, float* __restrict__ C, int ldc, int M, int N, int K,
+                                                    const float* __restrict__ bias, const float* __restrict__ mask,
+                                                    int ldmask, int k_split_len) {
+    static_assert((BM / TM) * (BN / TN) == 256, "thread tiling must cover the block tile with 256 threads");
+    constexpr int AP = 4, BP = 4;
+    __shared__ __align__(16) float As[BK][BM + AP];
+    __shared__ __align__(16) float Bs[BK][BN + BP];
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int k_lo = blockIdx.z * k_split_len;
+    const int k_hi = min(K, k_lo + k_split_len);
+    C += (size_t)blockIdx.z * M * ldc;
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
+        if (A_TRANS) {
+            for (int idx = tid; idx < BK * BM / 4; idx += 256) {
+                const int kk = idx / (BM / 4), mq = idx % (BM / 4);
+                const int k = k0 + kk, m = m0 + mq * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < k_hi && m < M) v = *reinterpret_cast<const float4*>(A + (size_t)k * lda + m);
+                *reinterpret_cast<float4*>(&As[kk][mq * 4]) = v;
+            }
+        } else {
+            for (int idx = tid; idx < BM * BK / 4; idx += 256) {
+                const int mm = idx / (BK / 4), kq = idx % (BK / 4);
+                const int m = m0 + mm, k = k0 + kq * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < M && k < k_hi) v = *reinterpret_cast<const float4*>(A + (size_t)m * lda + k);
+                As[kq * 4 + 0][mm] = v.x;
+                As[kq * 4 + 1][mm] = v.y;
+                As[kq * 4 + 2][mm] = v.z;
+                As[kq * 4 + 3][mm] = v.w;
+            }
+        }
+        for (int idx = tid; idx < BK * BN / 4; idx += 256) {
+            const int kk = idx / (BN / 4), nq = idx % (BN / 4);
+            const int k = k0 + kk, n = n0 + nq * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < k_hi && n < N) v = *reinterpret_cast<const float4*>(B + (size_t)k * ldb + n);
+            *reinterpret_cast<float4*>(&Bs[kk][nq * 4]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) v += __ldg(bias + n);
+            if (EPI == EPI_BIAS_RELU) v = v > 0.f ? v : 0.f;
+            if (EPI == EPI_MASK) v = mask[(size_t)m * ldmask + n] > 0.f ? v : 0.f;
+            C[(size_t)m * ldc + n] = v;
+        }
+    }
+}
+
+template <bool A_TRANS, int EPI>
+static int run_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                    const float* bias, const float* mask, int ldmask, int splits, int k_split_len,
+                    cudaStream_t st) {
+    // pick a tile shape by the narrow dimension
+    if (N <= 16) {
+        dim3 grid((N + 15) / 16, (M + 127) / 128, splits);
+        sgemm_kernel<128, 16, 4, 2, A_TRANS, EPI><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, mask,
+                                                                         ldmask, k_split_len);
+    } else if (M <= 16) {
+        dim3 grid((N + 127) / 128, (M + 15) / 16, splits);
+        sgemm_kernel<16, 128, 1, 8, A_TRANS, EPI><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, mask,
+                                                                         ldmask, k_split_len);
+    } else if (N <= 64) {
+        dim3 grid((N + 63) / 64, (M + 127) / 128, splits);
+        sgemm_kernel<128, 64, 8, 4, A_TRANS, EPI><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, mask,
+                                                                         ldmask, k_split_len);
+    } else if (M <= 64) {
+        dim3 grid((N + 127) / 128, (M + 63) / 64, splits);
+        sgemm_kernel<64, 128, 4, 8, A_TRANS, EPI><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, mask,
+                                                                         ldmask, k_split_len);
+    } else {
+        dim3 grid((N + 127) / 128, (M + 127) / 128, splits);
+        sgemm_kernel<128, 128, 8, 8, A_TRANS, EPI><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, mask,
+                                                                          ldmask, k_split_len);
+    }
+    FRL_CUDA(cudaGetLastError());
+    return FRL_OK;
+}
+
+// X0[row] = [ (1-t) a0 + t noise | s | t | 0 ... ]   (pretrain.py:184 / :102; column order networks.py:24)
+__global__ void cfm_prepare_kernel(const float* __restrict__ s, const float* __restrict__ a0,
+                                   const float* __restrict__ t, const float* __restrict__ noise,
+                                   float* __restrict__ X0, long long B, int s_dim, int a_dim, int ld) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= B * ld) return;
+    const long long row = i / ld;
+    const int k = (int)(i % ld);
+    float v = 0.f;
+    const float tt = t[row];
+    if (k < a_dim) {
+        v = __fadd_rn(__fmul_rn(1.f - tt, a0[row * a_dim + k]), __fmul_rn(tt, noise[row * a_dim + k]));
+    } else if (k < a_dim + s_dim) {
+        v = s[row * s_dim + (k - a_dim)];
+    } else if (k == a_dim + s_dim) {
+        v = tt;
+    }
+    X0[i] = v;
+}
+
+// Per row: loss term and dL/d(head pre-activations), written over V in place.
+__global__ void __launch_bounds__(256) cfm_loss_kernel(float* __restrict__ V, int ldv, const float* __restrict__ a0,
+                                                       const float* __restrict__ noise, const float* __restrict__ t,
+                                                       long long B, int a_dim, int n_heads, float sign, float dscale,
+                                                       double* __restrict__ partial) {
+    const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double term = 0.0;
+    if (row < B) {
+        const float w = powf(1.f - t[row], 1.5f);  // pretrain.py:188 / :105
+        float* v = V + row * ldv;
+        float acc = 0.f;
+        for (int j = 0; j < a_dim; ++j) {
+            float pred = v[j];
+            float th = 0.f;
+            if (n_heads == 2) {
+                th = tanhf(v[a_dim + j]);
+                pred += sign * th;
+            }
+            const float diff = pred - (noise[row * a_dim + j] - a0[row * a_dim + j]);
+            acc += diff * diff;
+            const float d = dscale * w * diff;  // dscale = grad_scale * 2 / Bdiv
+            v[j] = d;
+            if (n_heads == 2) v[a_dim + j] = d * sign * (1.f - th * th);
+        }
+        term = (double)(w * acc);
+    }
+    __shared__ double sh[8];
+    for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = term;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tsum = 0.0;
+        for (int i = 0; i < 8; ++i) tsum += sh[i];
+        partial[blockIdx.x] = tsum;
+    }
+}
+
+__global__ void loss_final_kernel(const double* __restrict__ partial, int n, double inv_div, float* __restrict__ loss) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (float)(sh[0] * inv_div);
+}
+
+// grad[n*K + k] (+)= sum_s partial[s*split_stride + n*ldp + k]  for n < n_rows, k < K  (ldp >= K)
+__global__ void reduce_wgrad_kernel(const float* __restrict__ partial, int splits, size_t split_stride, int ldp,
+                                    int n_rows, int K, float* __restrict__ grad, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * K) return;
+    const int n = i / K, k = i % K;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[(size_t)s * split_stride + (size_t)n * ldp + k];
+    grad[i] = accumulate ? grad[i] + acc : acc;
+}
+
+// column sums of D [B][ld] over rows, split into chunks; partial[chunk][col]
+__global__ void colsum_partial_kernel(const float* __restrict__ D, int ld, long long B, int cols, int rows_per_chunk,
+                                      float* __restrict__ partial) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    const long long lo = (long long)blockIdx.y * rows_per_chunk;
+    const long long hi = min(B, lo + rows_per_chunk);
+    float acc = 0.f;
+    for (long long r = lo; r < hi; ++r) acc += D[r * ld + col];
+    partial[(size_t)blockIdx.y * cols + col] = acc;
+}
+
+__global__ void reduce_bias_kernel(const float* __restrict__ partial, int chunks, int ldp, int col0, int n,
+                                   float* __restrict__ grad, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int c = 0; c < chunks; ++c) acc += partial[(size_t)c * ldp + col0 + i];
+    grad[i] = accumulate ? grad[i] + acc : acc;
+}
+
+static int ensure_ws(frl_net* net, size_t floats) {
+    if (net->ws_floats >= floats) return FRL_OK;
+    if (net->ws) FRL_CUDA(cudaFree(net->ws));  // synchronises the device: earlier work has finished using it
+    net->ws = nullptr;
+    net->ws_floats = 0;
+    FRL_CUDA(cudaMalloc(&net->ws, floats * sizeof(float)));
+    net->ws_floats = floats;
+    return FRL_OK;
+}
+
+int cfm_loss_grad_f32(frl_net* net, float role_sign, const float* s, const float* a0, const float* t,
+                      const float* noise, long long B, long long mean_divisor, float grad_scale, int accumulate,
+                      float* loss, float* grad, cudaStream_t st) {
+    const int H = net->cfg.hidden, A = net->cfg.a_dim, depth = net->cfg.depth;
+    const int K0p = net->d_in_p, NOp = net->n_out_p;
+    FRL_REQUIRE(B > 0 && B < (1ll << 31) / std::max(H, K0p), "batch size out of range");
+    const int Bi = (int)B;
+    const double div = (double)(mean_divisor > 0 ? mean_divisor : B);
+
+    // split plan for the batch-reduction GEMMs (deterministic for a given B)
+    const int k_chunk_min = 64;
+    auto plan_splits = [&](int tiles) {
+        int want = std::max(1, 296 / std::max(1, tiles));
+        int maxs = std::max(1, (Bi + k_chunk_min - 1) / k_chunk_min);
+        return std::min(want, maxs);
+    };
+    const int splits_hh = plan_splits(((H + 127) / 128) * ((H + 127) / 128));
+    const int splits_small = plan_splits(2);
+    const int max_splits = std::max(splits_hh, splits_small);
+    const int cs_chunks = std::max(1, std::min(148, (Bi + 255) / 256));
+    const int cs_rows = (Bi + cs_chunks - 1) / cs_chunks;
+    const int loss_blocks = (Bi + 255) / 256;
+
+    // workspace carve-up (floats)
+    size_t off = 0;
+    auto take = [&](size_t n) { size_t o = off; off += (n + 3) / 4 * 4; return o; };
+    const size_t o_x0 = take((size_t)B * K0p);
+    size_t o_h[kMaxDepth];
+    for (int l = 0; l < depth; ++l) o_h[l] = take((size_t)B * H);
+    const size_t o_v = take((size_t)B * NOp);
+    const size_t o_dz0 = take((size_t)B * H);
+    const size_t o_dz1 = take((size_t)B * H);
+    const size_t o_part = take((size_t)max_splits * H * std::max(H, std::max(K0p, NOp)));
+    const size_t o_cs = take((size_t)cs_chunks * std::max(H, NOp));
+    const size_t o_lp = take((size_t)loss_blocks * 2 + 4);  // doubles
+    int rc = ensure_ws(net, off);
+    if (rc != FRL_OK) return rc;
+    float* ws = net->ws;
+    float* X0 = ws + o_x0;
+    float* V = ws + o_v;
+    float* dZ[2] = {ws + o_dz0, ws + o_dz1};
+    float* part = ws + o_part;
+    float* cs = ws + o_cs;
+    double* lpart = reinterpret_cast<double*>(ws + o_lp);
+    const NetF32& w = net->f32;
+
+    // ---- forward ----
+    {
+        long long n = B * K0p;
+        cfm_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, a0, t, noise, X0, B, net->cfg.s_dim, A, K0p);
+        FRL_CUDA(cudaGetLastError());
+    }
+    const float* in = X0;
+    int Kin = K0p;
+    for (int l = 0; l < depth; ++l) {
+        float* out = ws + o_h[l];
+        rc = run_gemm<false, EPI_BIAS_RELU>(in, Kin, w.Wt[l], H, out, H, Bi, H, Kin, w.b[l], nullptr, 0, 1, Kin, st);
+        if (rc != FRL_OK) return rc;
+        in = out;
+        Kin = H;
+    }
+    const float* Hlast = in;
+    rc = run_gemm<false, EPI_BIAS>(Hlast, H, w.Wht, NOp, V, NOp, Bi, NOp, H, w.bh, nullptr, 0, 1, H, st);
+    if (rc != FRL_OK) return rc;
+
+    // ---- loss + dV (in place) ----
+    cfm_loss_kernel<<<loss_blocks, 256, 0, st>>>(V, NOp, a0, noise, t, B, A, net->cfg.n_heads, role_sign,
+                                                 (float)((double)grad_scale * 2.0 / div), lpart);
+    FRL_CUDA(cudaGetLastError());
+    if (loss) {
+        loss_final_kernel<<<1, 256, 0, st>>>(lpart, loss_blocks, 1.0 / div, loss);
+        FRL_CUDA(cudaGetLastError());
+    }
+    if (!grad) return FRL_OK;
+
+    auto ksplit = [&](int splits) { return round_up((Bi + splits - 1) / splits, BK); };
+
+    // ---- heads backward ----
+    {
+        // dWh [NOp][H] = dV^T [NOp x B] * Hlast [B][H]
+        const int sp = splits_small;
+        rc = run_gemm<true, EPI_NONE>(V, NOp, Hlast, H, part, H, NOp, H, Bi, nullptr, nullptr, 0, sp, ksplit(sp), st);
+        if (rc != FRL_OK) return rc;
+        for (int h = 0; h < net->cfg.n_heads; ++h) {
+            // partial layout [split][NOp][H]; head h's rows start at h*A
+            reduce_wgrad_kernel<<<(A * H + 255) / 256, 256, 0, st>>>(part + (size_t)h * A * H, sp, (size_t)NOp * H, H,
+                                                                     A, H, grad + net->off_wh[h], accumulate);
+        }
+        FRL_CUDA(cudaGetLastError());
+        colsum_partial_kernel<<<dim3((NOp + 63) / 64, cs_chunks), 64, 0, st>>>(V, NOp, B, NOp, cs_rows, cs);
+        for (int h = 0; h < net->cfg.n_heads; ++h)
+            reduce_bias_kernel<<<1, 64, 0, st>>>(cs, cs_chunks, NOp, h * A, A, grad + net->off_bh[h], accumulate);
+        FRL_CUDA(cudaGetLastError());
+        // dZ_L = (dV [B][NOp] * Wh [NOp][H]) masked by H_L > 0
+        rc = run_gemm<false, EPI_MASK>(V, NOp, w.Wh, H, dZ[0], H, Bi, H, NOp, nullptr, Hlast, H, 1, NOp, st);
+        if (rc != FRL_OK) return rc;
+    }
+    // ---- trunk backward ----
+    int cur = 0;
+    for (int l = depth - 1; l >= 0; --l) {
+        const float* Xin = l == 0 ? X0 : ws + o_h[l - 1];
+        const int Kp = l == 0 ? K0p : H;
+        const int K = l == 0 ? net->d_in : H;
+        const int sp = (Kp == H) ? splits_hh : splits_small;
+        // dW_l [H][Kp] = dZ^T [H x B] * Xin [B][Kp]
+        rc = run_gemm<true, EPI_NONE>(dZ[cur], H, Xin, Kp, part, Kp, H, Kp, Bi, nullptr, nullptr, 0, sp, ksplit(sp), st);
+        if (rc != FRL_OK) return rc;
+        reduce_wgrad_kernel<<<(H * K + 255) / 256, 256, 0, st>>>(part, sp, (size_t)H * Kp, Kp, H, K,
+                                                                 grad + net->off_w[l], accumulate);
+        colsum_partial_kernel<<<dim3((H + 127) / 128, cs_chunks), 128, 0, st>>>(dZ[cur], H, B, H, cs_rows, cs);
+        reduce_bias_kernel<<<(H + 127) / 128, 128, 0, st>>>(cs, cs_chunks, H, 0, H, grad + net->off_b[l], accumulate);
+        FRL_CUDA(cudaGetLastError());
+        if (l > 0) {
+            // dZ_{l-1} = (dZ_l [B][H] * W_l [H][H]) masked by H_{l-1} > 0
+            rc = run_gemm<false, EPI_MASK>(dZ[cur], H, w.W[l], H, dZ[cur ^ 1], H, Bi, H, H, nullptr, Xin, H, 1, H, st);
+            if (rc != FRL_OK) return rc;
+            cur ^= 1;
+        }
+    }
+    return FRL_OK;
+}
+
+}  // namespace frl

@@ -1,0 +1,210 @@
+"""Velocity-field MLPs of the FLOWRIL density model, backed by the sm_100a kernels.
+
+Drop-in for the reference's ``modril/flowril/networks.py``: same class names, constructor arguments, attribute
+names (``.shared``, ``.head_c``, ``.head_r``, ``.net``) and ``state_dict`` keys, so
+pre-trained ``*_fm.pt`` files load unchanged and ``flowril.py``'s freezing code (``net.shared.parameters()`` ...,
+reference flowril.py:52-58) keeps working.
+
+Differences in mechanism (not in behaviour):
+  * all parameters of one net are views into ONE flat float32 buffer in ``state_dict`` order; the C library packs
+    its kernel-side layouts (transposed / padded / bf16) from that buffer (``frl_net_set_params``) whenever a
+    parameter's version counter shows it changed;
+  * ``forward`` calls ``frl_vfield``; there is no PyTorch implementation of the arithmetic in this package and no
+    CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from .. import _native
+
+
+def _current_stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def as_f32_cuda(x: torch.Tensor, device, what: str) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"{what} must be a torch.Tensor")
+    if x.device != device:
+        raise RuntimeError(f"{what} is on {x.device}, the flow net is on {device}")
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.detach().contiguous()
+
+
+class _FlatVNet(nn.Module):
+    """Common machinery: flat parameter storage + native handle."""
+
+    n_heads = 0
+
+    def _finish_init(self, s_dim: int, a_dim: int, hidden: int):
+        self.s_dim, self.a_dim, self.hidden = int(s_dim), int(a_dim), int(hidden)
+        self._flat = None
+        self._flat_grad = None
+        self._handle = None
+        self._packed_key = None
+        self._flatten()
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st.update(_handle=None, _packed_key=None, _flat=None, _flat_grad=None)  # native handle is per-object
+        return st
+
+    def __setstate__(self, st):
+        super().__setstate__(st)
+        self._flatten()
+
+    # ---- flat storage -------------------------------------------------------------------------------------
+    def _ordered_params(self):
+        return list(self.parameters())  # registration order == state_dict order
+
+    def _flatten(self):
+        params = self._ordered_params()
+        dev = params[0].device
+        if any(p.dtype != torch.float32 for p in params):
+            raise TypeError("flow nets are float32 only")
+        flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = flat[off:off + n].view(p.shape)
+                off += n
+        self._flat = flat
+        self._flat_grad = None
+        self._packed_key = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._release()
+        self._flatten()  # .to()/.cuda() re-allocates every parameter: gather them into one buffer again
+        return out
+
+    def flat_params(self) -> torch.Tensor:
+        self._check_views()
+        return self._flat
+
+    def flat_grad(self) -> torch.Tensor:
+        if self._flat_grad is None or self._flat_grad.device != self._flat.device:
+            self._flat_grad = torch.zeros_like(self._flat)
+        return self._flat_grad
+
+    def param_slices(self):
+        """[(parameter, offset, numel)] in flat order."""
+        out, off = [], 0
+        for p in self._ordered_params():
+            out.append((p, off, p.numel()))
+            off += p.numel()
+        return out
+
+    def _check_views(self):
+        base = self._flat.data_ptr()
+        off = 0
+        for p in self._ordered_params():
+            if p.data_ptr() != base + 4 * off or p.device != self._flat.device:
+                self._flatten()  # someone re-pointed a parameter (e.g. p.data = ...): re-gather
+                return
+            off += p.numel()
+
+    # ---- native handle ------------------------------------------------------------------------------------
+    def _release(self):
+        if getattr(self, "_handle", None):
+            _native.lib().frl_net_destroy(self._handle)
+        self._handle = None
+        self._packed_key = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def native(self) -> C.c_void_p:
+        """Handle with up-to-date packed weights (re-packs iff a parameter changed since the last call)."""
+        self._check_views()
+        dev = self._flat.device
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "modril_b200 flow nets compute only on CUDA (sm_100a) devices; there is no CPU fallback. "
+                "Move the module with .to('cuda').")
+        L = _native.lib()
+        if self._handle is None:
+            depth = self.depth
+            cfg = _native.NetConfig(self.s_dim, self.a_dim, self.hidden, depth, self.n_heads, dev.index or 0)
+            h = C.c_void_p()
+            _native.check(L.frl_net_create(C.byref(cfg), C.byref(h)), "frl_net_create")
+            self._handle = h
+        key = (self._flat.data_ptr(), tuple(p._version for p in self._ordered_params()))
+        if key != self._packed_key:
+            _native.check(L.frl_net_set_params(self._handle, _ptr(self._flat), _current_stream(dev)),
+                          "frl_net_set_params")
+            self._packed_key = key
+        return self._handle
+
+    def mark_dirty(self):
+        """Force a re-pack on next use (needed only after writing weights through ``.data`` or raw pointers)."""
+        self._packed_key = None
+
+    def _vfield(self, a, s, t):
+        dev = self._flat.device
+        h = self.native()
+        a = as_f32_cuda(a, dev, "a")
+        s = as_f32_cuda(s, dev, "s")
+        t = as_f32_cuda(t, dev, "t").reshape(-1)
+        B = a.shape[0]
+        if a.shape != (B, self.a_dim) or s.shape != (B, self.s_dim) or t.numel() != B:
+            raise ValueError(f"expected a [B,{self.a_dim}], s [B,{self.s_dim}], t [B,1]; got {tuple(a.shape)}, "
+                             f"{tuple(s.shape)}, {tuple(t.shape)}")
+        out0 = torch.empty(B, self.a_dim, device=dev)
+        out1 = torch.empty(B, self.a_dim, device=dev) if self.n_heads == 2 else None
+        _native.check(_native.lib().frl_vfield(h, _ptr(s), _ptr(a), _ptr(t), _ptr(out0), _ptr(out1), B,
+                                               _native.PREC_FP32, _current_stream(dev)), "frl_vfield")
+        return out0, out1
+
+
+class SharedVNet(_FlatVNet):
+    """Shared trunk with two heads: returns (v_c, tanh(r))  -- reference networks.py:5-25."""
+
+    n_heads = 2
+
+    def __init__(self, s_dim, a_dim, hidden=256, depth=4):
+        super().__init__()
+        self.depth = max(1, depth)
+        layers = [nn.Linear(s_dim + a_dim + 1, hidden), nn.ReLU()]
+        for _ in range(self.depth - 1):
+            layers += [nn.Linear(hidden, hidden), nn.ReLU()]
+        self.shared = nn.Sequential(*layers)
+        self.head_c = nn.Linear(hidden, a_dim)
+        self.head_r = nn.Linear(hidden, a_dim)
+        self._finish_init(s_dim, a_dim, hidden)
+
+    def forward(self, a, s, t):
+        return self._vfield(a, s, t)
+
+
+class ConditionalVNet(_FlatVNet):
+    """Time-conditioned vector field v(a_t, s, t) -- reference networks.py:28-49."""
+
+    n_heads = 1
+
+    def __init__(self, s_dim, a_dim, hidden=128, depth=4):
+        super().__init__()
+        self.depth = max(1, depth)
+        layers = [nn.Linear(a_dim + s_dim + 1, hidden), nn.ReLU()]
+        for _ in range(self.depth - 1):
+            layers += [nn.Linear(hidden, hidden), nn.ReLU()]
+        layers.append(nn.Linear(hidden, a_dim))
+        self.net = nn.Sequential(*layers)
+        self._finish_init(s_dim, a_dim, hidden)
+
+    def forward(self, a_t, s, t):
+        return self._vfield(a_t, s, t)[0]

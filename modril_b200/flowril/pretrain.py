@@ -1,0 +1,403 @@
+"""Flow-matching density estimators of FLOWRIL on B200 kernels.
+
+Drop-in for the estimator classes of the reference's ``modril/flowril/pretrain.py`` (level-1 boundary of SURVEY.md
+section 8b): ``CoupledResidualFM`` (:137-214) and ``FlowMatching`` (:62-134) with the same constructor arguments,
+attributes (``.net``, ``.prior``, ``.eps``), methods (``v_field``, ``fm_loss``, ``log_prob``, ``_hutch_div``) and
+``state_dict`` keys; module-level ``_rademacher`` (:42-52).
+
+Mechanism: ``log_prob`` is ONE launch of the fused Euler integrator (``frl_logprob`` / ``frl_score``) that carries
+the action state, a forward-mode tangent and the divergence accumulator through all ``n_steps`` on chip;
+``fm_loss`` is a fused forward+backward (``frl_cfm_loss_grad``) exposed to autograd through a custom Function, so
+``loss.backward()``, ``clip_grad_norm_`` and any torch optimizer keep working; ``FusedAdam`` and
+``train_step`` are the all-native route (grad-clip + Adam in one kernel on the flat parameter buffer).
+
+Randomness is drawn on the host side exactly where the reference draws it (same torch calls in the same order),
+and every method also accepts the draws explicitly (``probe=``, ``t=``, ``noise=``) -- the kernels themselves are
+deterministic functions of their inputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import _native
+from .networks import ConditionalVNet, SharedVNet, _current_stream, _ptr, as_f32_cuda
+
+CMAP = 'viridis'
+PLOT_KW = dict(density=1.2, linewidth=1, arrowstyle='-|>')
+ALPHA_BG = 0.85
+
+_DEFAULT_PRECISION = "fp32"
+
+
+def set_default_precision(name: str):
+    """'fp32' (FFMA, 1e-4 parity), 'bf16' or 'bf16x3' (tcgen05 tensor cores) for log_prob calls that do not
+    pass ``precision=`` explicitly."""
+    global _DEFAULT_PRECISION
+    if name not in _native.PRECISIONS:
+        raise ValueError(f"unknown precision {name!r}; choose from {sorted(_native.PRECISIONS)}")
+    _DEFAULT_PRECISION = name
+
+
+def _rademacher(shape_or_tensor, device=None):
+    """+-1 probe matching a shape or tensor.  Like the reference (pretrain.py:42-52) it draws from a FRESH,
+    unseeded ``torch.Generator`` on every call, so the probe is a deterministic function of (shape, device)."""
+    if isinstance(shape_or_tensor, torch.Tensor):
+        device = shape_or_tensor.device if device is None else device
+        shape = tuple(shape_or_tensor.shape)
+    else:
+        shape = shape_or_tensor
+        assert device is not None, "device must be specified when passing shape"
+    rng = torch.Generator(device=device)
+    return torch.randint(0, 2, shape, device=device, generator=rng).float().mul_(2).sub_(1)
+
+
+@functools.lru_cache(maxsize=64)
+def _t_mid(n_steps: int):
+    """Midpoints of torch.linspace(0, 1, n+1) in float32, as the reference forms them (pretrain.py:200, :206)."""
+    g = torch.linspace(0.0, 1.0, n_steps + 1)
+    tm = 0.5 * (g[:-1] + g[1:])
+    return _native.float_array(tm.tolist())
+
+
+def _precision_code(precision):
+    name = _DEFAULT_PRECISION if precision is None else precision
+    if name not in _native.PRECISIONS:
+        raise ValueError(f"unknown precision {name!r}")
+    return _native.PRECISIONS[name]
+
+
+def _probe_args(probe, exact, B, a_dim, n_steps, device):
+    if exact:
+        return None, _native.PROBE_EXACT
+    probe = as_f32_cuda(probe, device, "probe")
+    if probe.shape == (B, a_dim):
+        return probe, _native.PROBE_SHARED
+    if probe.shape == (n_steps, B, a_dim):
+        return probe, _native.PROBE_PER_STEP
+    raise ValueError(f"probe must be [B,{a_dim}] or [{n_steps},B,{a_dim}], got {tuple(probe.shape)}")
+
+
+def _log_prob_native(net, sign, s, a0, probe, exact, n_steps, precision):
+    dev = net.flat_params().device
+    h = net.native()
+    s = as_f32_cuda(s, dev, "s")
+    a0 = as_f32_cuda(a0, dev, "a0")
+    B = a0.shape[0]
+    if a0.shape != (B, net.a_dim) or s.shape != (B, net.s_dim):
+        raise ValueError(f"expected s [B,{net.s_dim}], a0 [B,{net.a_dim}]; got {tuple(s.shape)}, {tuple(a0.shape)}")
+    if not (1 <= n_steps <= 256):
+        raise ValueError("n_steps must be in 1..256")
+    probe, mode = _probe_args(probe, exact, B, net.a_dim, n_steps, dev)
+    out = torch.empty(B, device=dev)
+    _native.check(_native.lib().frl_logprob(h, float(sign), _ptr(s), _ptr(a0), _ptr(probe), mode, _t_mid(n_steps),
+                                            n_steps, _ptr(out), B, _precision_code(precision),
+                                            _current_stream(dev)), "frl_logprob")
+    return out
+
+
+def score_pair(net_e, net_a, s, a, probe=None, exact=False, n_steps=32, reward_type="raw", precision=None):
+    """Both roles in one launch: returns (logp_E, logp_A, reward).  For scrf pass the same net twice
+    (reference flowril.py:183-191); for 2fs the expert and agent nets (flowril.py:187-189)."""
+    dev = net_e.flat_params().device
+    he, ha = net_e.native(), net_a.native()
+    s = as_f32_cuda(s, dev, "s")
+    a = as_f32_cuda(a, dev, "a")
+    B = a.shape[0]
+    if a.shape != (B, net_e.a_dim) or s.shape != (B, net_e.s_dim):
+        raise ValueError(f"expected s [B,{net_e.s_dim}], a [B,{net_e.a_dim}]; got {tuple(s.shape)}, {tuple(a.shape)}")
+    if reward_type not in _native.REWARD_TYPES:
+        raise ValueError(f"Unrecognized reward type {reward_type}")  # reference flowril.py:207
+    probe, mode = _probe_args(probe, exact, B, net_e.a_dim, n_steps, dev)
+    le, la, rw = (torch.empty(B, device=dev) for _ in range(3))
+    _native.check(_native.lib().frl_score(he, ha, _ptr(s), _ptr(a), _ptr(probe), mode, _t_mid(n_steps), n_steps,
+                                          _native.REWARD_TYPES[reward_type], _ptr(le), _ptr(la), _ptr(rw), B,
+                                          _precision_code(precision), _current_stream(dev)), "frl_score")
+    return le, la, rw
+
+
+class _FMLoss(torch.autograd.Function):
+    """loss = frl_cfm_loss_grad(...): the fused kernel produces the loss AND dL/dtheta in forward; backward hands
+    the stored gradient (scaled by grad_output) to autograd so that ``loss.backward()`` fills ``p.grad``."""
+
+    @staticmethod
+    def forward(ctx, net, sign, s, a0, t, noise, *params):
+        dev = net.flat_params().device
+        h = net.native()
+        B = a0.shape[0]
+        loss = torch.empty(1, device=dev)
+        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        grad = torch.empty_like(net.flat_params()) if need_grad else None
+        _native.check(_native.lib().frl_cfm_loss_grad(h, float(sign), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B, 0,
+                                                      1.0, 0, _ptr(loss), _ptr(grad), _current_stream(dev)),
+                      "frl_cfm_loss_grad")
+        ctx.net = net
+        ctx.flat_grad = grad
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        outs = [None] * 6
+        flat = ctx.flat_grad
+        for p, off, n in ctx.net.param_slices():
+            if flat is None or not p.requires_grad:
+                outs.append(None)
+            else:
+                outs.append(flat[off:off + n].view(p.shape) * grad_out)
+        return tuple(outs)
+
+
+def _fm_loss_native(net, sign, s, a0, t, noise):
+    dev = net.flat_params().device
+    net.native()
+    s = as_f32_cuda(s, dev, "s")
+    a0 = as_f32_cuda(a0, dev, "a0")
+    t = as_f32_cuda(t, dev, "t").reshape(-1)
+    noise = as_f32_cuda(noise, dev, "noise")
+    B = a0.shape[0]
+    if a0.shape != (B, net.a_dim) or s.shape != (B, net.s_dim) or t.numel() != B or noise.shape != a0.shape:
+        raise ValueError("fm_loss: inconsistent batch shapes")
+    params = [p for p, _, _ in net.param_slices()]
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return _FMLoss.apply(net, sign, s, a0, t, noise, *params)
+    with torch.no_grad():
+        return _FMLoss.apply(net, sign, s, a0, t, noise, *params)
+
+
+class FlowMatching(nn.Module):
+    """One conditional flow net (the '2fs' option uses two of these) -- reference pretrain.py:62-134."""
+
+    def __init__(self, state_dim: int, action_dim: int, hidden_dim: int, depth: int = 4, eps: float = 1e-3):
+        super().__init__()
+        self.state_dim, self.action_dim = state_dim, action_dim
+        self.net = ConditionalVNet(self.state_dim, self.action_dim, hidden_dim, depth)
+        self.dim = self.state_dim + self.action_dim
+        self.prior = torch.distributions.Normal(0, 1)
+        self.eps = eps
+        self.T = 1.0
+
+    def _v_star(self, a_t, a0, t, noise):
+        return noise - a0
+
+    def fm_loss(self, s, a0, dequant_std=0.02, *, dequant=None, t=None, noise=None):
+        """CFM loss (reference pretrain.py:94-109).  Draw order when not supplied: dequantisation noise
+        (randn_like), t (rand), prior sample -- the reference's order."""
+        B = s.size(0)
+        dev = a0.device
+        if dequant is None:
+            dequant = torch.randn_like(a0)
+        a0 = a0 + dequant * dequant_std
+        if t is None:
+            t = torch.rand(B, 1, device=dev) * (1 - 2 * self.eps) + self.eps
+        if noise is None:
+            noise = self.prior.sample((B, self.action_dim)).to(a0)
+        return _fm_loss_native(self.net, 1.0, s, a0, t, noise)
+
+    def log_prob(self, x: torch.Tensor, n_steps: int = 32, *, probe=None, exact=False, precision=None):
+        """log p(a|s) for x = cat[s, a] (reference pretrain.py:112-134).  Without ``probe`` a fresh Rademacher
+        probe is drawn from the global RNG at every Euler step like ``_hutch_div`` does (pretrain.py:90)."""
+        s, a0 = x.split([self.state_dim, x.size(-1) - self.state_dim], dim=-1)
+        if probe is None and not exact:
+            probe = torch.stack([torch.randint_like(a0, 0, 2).float().mul_(2).sub_(1) for _ in range(n_steps)])
+        return _log_prob_native(self.net, 1.0, s, a0, probe, exact, n_steps, precision)
+
+
+class CoupledResidualFM(nn.Module):
+    """v_E = v_c + r, v_pi = v_c - r with r = tanh(head_r)  -- reference pretrain.py:137-214."""
+
+    def __init__(self, state_dim: int, action_dim: int, hidden_dim: int, depth: int = 4, eps: float = 1e-3):
+        super().__init__()
+        self.s_dim, self.a_dim, self.eps = state_dim, action_dim, eps
+        self.net = SharedVNet(state_dim, action_dim, hidden=hidden_dim, depth=depth)
+        self.prior = torch.distributions.Normal(0., 1.)
+
+    def v_field(self, a_t, s, t, role: str):
+        v_c, r = self.net(a_t, s, t)
+        return v_c + r if role == "expert" else v_c - r
+
+    def _v_star(self, a_t, a0, t, noise):
+        return noise - a0
+
+    def fm_loss(self, s, a0, role, *, t=None, noise=None):
+        """CFM loss for one role (reference pretrain.py:179-190); t then noise are drawn like the reference when
+        not supplied."""
+        B = a0.size(0)
+        dev = a0.device
+        if t is None:
+            t = torch.rand(B, 1, device=dev) * (1 - 2 * self.eps) + self.eps
+        if noise is None:
+            noise = self.prior.sample((B, self.a_dim)).to(dev)
+        return _fm_loss_native(self.net, 1.0 if role == "expert" else -1.0, s, a0, t, noise)
+
+    def log_prob(self, s, a0, role: str, n_steps: int = 32, *, probe=None, exact=False, precision=None):
+        """log p_role(a|s) (reference pretrain.py:192-214).  Default probe = ``_rademacher((B, a_dim))``, the same
+        matrix at every step and for both roles, as in the reference."""
+        if probe is None and not exact:
+            probe = _rademacher((a0.size(0), self.a_dim), device=a0.device)
+        return _log_prob_native(self.net, 1.0 if role == "expert" else -1.0, s, a0, probe, exact, n_steps, precision)
+
+    def score(self, s, a, n_steps: int = 32, reward_type: str = "raw", *, probe=None, exact=False, precision=None):
+        """(logp_E, logp_A, reward) in one launch -- what flowril.py:183-207 computes with two log_prob calls."""
+        if probe is None and not exact:
+            probe = _rademacher((a.size(0), self.a_dim), device=a.device)
+        return score_pair(self.net, self.net, s, a, probe, exact, n_steps, reward_type, precision)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# optimiser: torch.optim.Adam semantics on the flat buffers, one fused clip+Adam kernel
+# ------------------------------------------------------------------------------------------------------------
+class FusedAdam(torch.optim.Optimizer):
+    """Adam (torch defaults: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad) whose ``step`` is the
+    fused ``frl_clip_adam`` kernel.  ``state_dict()`` / ``load_state_dict()`` use ``torch.optim.Adam``'s layout
+    (per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``), so reference checkpoints (``flow_<option>_opt``,
+    reference flowril.py:581-597) round-trip.
+
+    ``nets`` are the ``_FlatVNet`` modules whose parameters are optimised; parameters with
+    ``requires_grad == False`` at construction are frozen (excluded from the norm and the update, like params with
+    ``grad is None`` in ``clip_grad_norm_`` / Adam).
+    """
+
+    def __init__(self, nets, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.nets = list(nets)
+        params = [p for net in self.nets for p, _, _ in net.param_slices() if p.requires_grad]
+        if not params:
+            raise ValueError("optimizer got an empty parameter list")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False,
+                                      foreach=None, capturable=False, differentiable=False, fused=None))
+        self._step = 0
+        self._m = [torch.zeros_like(net.flat_params()) for net in self.nets]
+        self._v = [torch.zeros_like(net.flat_params()) for net in self.nets]
+        self._norm = None
+        self._bind_state()
+
+    def _bind_state(self):
+        for net, m, v in zip(self.nets, self._m, self._v):
+            for p, off, n in net.param_slices():
+                if p.requires_grad:
+                    self.state[p] = {"step": torch.tensor(float(self._step)),
+                                     "exp_avg": m[off:off + n].view(p.shape),
+                                     "exp_avg_sq": v[off:off + n].view(p.shape)}
+
+    def _segments(self, grads):
+        """Contiguous runs of trainable parameters per net -> frl_adam_segment array."""
+        segs = []
+        for net, m, v, g in zip(self.nets, self._m, self._v, grads):
+            flat = net.flat_params()
+            run = None
+            for p, off, n in net.param_slices() + [(None, None, None)]:
+                if p is not None and p.requires_grad:
+                    run = [run[0], off + n] if run else [off, off + n]
+                elif run:
+                    segs.append((flat, g, m, v, run[0], run[1] - run[0]))
+                    run = None
+        if len(segs) > 4:
+            raise NotImplementedError("more than 4 disjoint trainable parameter ranges")
+        arr = (_native.AdamSegment * len(segs))()
+        for i, (flat, g, m, v, off, n) in enumerate(segs):
+            arr[i].params = flat.data_ptr() + 4 * off
+            arr[i].grad = g.data_ptr() + 4 * off
+            arr[i].exp_avg = m.data_ptr() + 4 * off
+            arr[i].exp_avg_sq = v.data_ptr() + 4 * off
+            arr[i].n = n
+        return arr, len(segs)
+
+    @torch.no_grad()
+    def step_flat(self, grads, max_norm: float = float("inf")):
+        """Clip (global norm over all trainable segments) + Adam on flat gradient buffers, one kernel pair."""
+        dev = self.nets[0].flat_params().device
+        group = self.param_groups[0]
+        self._step += 1
+        arr, n = self._segments(grads)
+        if self._norm is None or self._norm.device != dev:
+            self._norm = torch.zeros(1, device=dev)
+        b1, b2 = group["betas"]
+        mx = float(max_norm) if math.isfinite(max_norm) else 3.0e38
+        _native.check(_native.lib().frl_clip_adam(arr, n, self._step, float(group["lr"]), float(b1), float(b2),
+                                                  float(group["eps"]), mx, _ptr(self._norm), dev.index or 0,
+                                                  _current_stream(dev)), "frl_clip_adam")
+        for net in self.nets:
+            net.mark_dirty()
+        for st in self.state.values():
+            st["step"].fill_(float(self._step))
+        return self._norm
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        """torch-style step: consumes ``p.grad`` (already clipped by the caller, if at all)."""
+        loss = closure() if closure is not None else None
+        grads = []
+        for net in self.nets:
+            g = net.flat_grad()
+            g.zero_()
+            for p, off, n in net.param_slices():
+                if p.requires_grad and p.grad is not None:
+                    g[off:off + n].copy_(p.grad.reshape(-1))
+            grads.append(g)
+        self.step_flat(grads)
+        return loss
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        # torch replaced the state tensors by copies: move them back into the flat buffers
+        steps = []
+        for net, m, v in zip(self.nets, self._m, self._v):
+            for p, off, n in net.param_slices():
+                st = self.state.get(p)
+                if st:
+                    m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+                    v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.append(int(float(st["step"])))
+        self._step = max(steps) if steps else 0
+        self._bind_state()
+
+
+def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None):
+    """One reward-model update on the all-native route (reference flowril.py:311-330 without regularisers):
+    zero grads; for each term accumulate rate * d fm_loss / d theta; [all-reduce]; clip_grad_norm_(max_norm); Adam.
+
+    terms: list of dicts {net, sign, s, a0, t, noise, rate}; several terms may share a net (scrf: expert + agent).
+    world: optional (process_group, world_size) for data-parallel training: each rank passes its shard, the mean
+           divisor becomes the global batch and the flat gradients are all-reduced (sum) before the clip.
+    Returns the per-term loss tensors (device scalars; under DP the local shard's contribution summed over ranks).
+    """
+    L = _native.lib()
+    seen = []
+    losses = []
+    ws = 1 if world is None else world[1]
+    for term in terms:
+        net = term["net"]
+        dev = net.flat_params().device
+        h = net.native()
+        g = net.flat_grad()
+        first = all(net is not n for n in seen)
+        if first:
+            seen.append(net)
+        s = as_f32_cuda(term["s"], dev, "s")
+        a0 = as_f32_cuda(term["a0"], dev, "a0")
+        t = as_f32_cuda(term["t"], dev, "t").reshape(-1)
+        noise = as_f32_cuda(term["noise"], dev, "noise")
+        B = a0.shape[0]
+        loss = torch.empty(1, device=dev)
+        _native.check(L.frl_cfm_loss_grad(h, float(term["sign"]), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B, B * ws,
+                                          float(term.get("rate", 1.0)), 0 if first else 1, _ptr(loss), _ptr(g),
+                                          _current_stream(dev)), "frl_cfm_loss_grad")
+        losses.append(loss)
+    grads = []
+    for net in opt.nets:
+        g = net.flat_grad()
+        if all(net is not n for n in seen):
+            g.zero_()
+        grads.append(g)
+    if world is not None and ws > 1:
+        import torch.distributed as dist
+
+        for g in grads:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=world[0])
+        for l in losses:
+            dist.all_reduce(l, op=dist.ReduceOp.SUM, group=world[0])
+    opt.step_flat(grads, max_norm)
+    return [l.reshape(()) for l in losses]

@@ -1,0 +1,186 @@
+"""GPU parity of the fused log-density integrator / velocity field / reward (through the C ABI).
+
+Bars: FP32 mode 1e-4 * max(1,|ref|) per sample against (i) the committed outputs of the reference code and
+(ii) the float64 oracle; tensor-core modes 2e-3.  A small fraction of samples may sit on a ReLU kink (see
+gpu_common.assert_close)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as cf
+from oracle import synth
+from tests.gpu_common import assert_close, build_model, dev, spec_of
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+MODES = [("fp32", 1e-4, 0.011)]
+TC_MODES = [("bf16x3", 1e-4, 0.03), ("bf16", 2e-3, 0.05)]
+
+
+def _tc_available():
+    from modril_b200 import _native
+    return bool(getattr(_native, "HAS_TC", False))
+
+
+def _modes():
+    return MODES + (TC_MODES if _tc_available() else [])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "logprob_*.npz"))), ids=os.path.basename)
+def test_logprob_vs_reference_goldens(path):
+    g = np.load(path)
+    spec = spec_of(g["meta"])
+    n_steps, B, seed = (int(x) for x in g["meta"][5:8])
+    gain = float(g["gain"])
+    s, a = synth.states_actions(seed, B, spec.s_dim, spec.a_dim)
+    probe = synth.rademacher(seed + 1, (B, spec.a_dim))
+    probe_steps = synth.rademacher(seed + 2, (n_steps, B, spec.a_dim))
+    st, at, pt, pst = dev(s), dev(a), dev(probe), dev(probe_steps)
+    for mode, tol, kink in _modes():
+        outs = {}
+        for ri, role in enumerate(("expert", "agent")):
+            flat = cf.make_params(spec, seed + (10 * ri if spec.n_heads == 1 else 0), gain)
+            m = build_model(spec, flat)
+            if spec.n_heads == 2:
+                call = lambda **kw: m.log_prob(st, at, role, n_steps=n_steps, precision=mode, **kw)
+            else:
+                call = lambda **kw: m.log_prob(torch.cat([st, at], dim=-1), n_steps=n_steps, precision=mode, **kw)
+            got = call(probe=pt).cpu().numpy()
+            assert_close(got, g[f"logp_{role}"], tol, f"{mode} {role} shared probe", kink)
+            outs[role] = got
+            got = call(probe=pst).cpu().numpy()
+            assert_close(got, g[f"logp_{role}_stepprobe"], tol, f"{mode} {role} per-step probe", kink)
+            if f"logp_{role}_exact" in g:
+                got = call(exact=True).cpu().numpy()
+                assert_close(got, g[f"logp_{role}_exact"], 2 * tol, f"{mode} {role} exact trace", 2 * kink)
+        if spec.n_heads == 2:  # fused two-role launch == two single-role launches, bit for bit
+            le, la, rw = m.score(st, at, n_steps=n_steps, probe=pt, precision=mode)
+            assert np.array_equal(le.cpu().numpy(), outs["expert"])
+            assert np.array_equal(la.cpu().numpy(), outs["agent"])
+            assert np.array_equal(rw.cpu().numpy(), outs["expert"] - outs["agent"])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "vfield_*.npz"))), ids=os.path.basename)
+def test_vfield_vs_reference_goldens(path):
+    g = np.load(path)
+    spec = spec_of(g["meta"])
+    B, seed = int(g["meta"][6]), int(g["meta"][7])
+    flat = cf.make_params(spec, seed, float(g["gain"]))
+    s, a = synth.states_actions(seed, B, spec.s_dim, spec.a_dim)
+    t = synth.rng(seed + 1).random((B, 1), dtype=np.float32)
+    m = build_model(spec, flat)
+    st, at, tt = dev(s), dev(a), dev(t)
+    if spec.n_heads == 2:
+        vc, r = m.net(at, st, tt)
+        assert_close(vc.cpu().numpy(), g["v_c"], 1e-5, "v_c")
+        assert_close(r.cpu().numpy(), g["r"], 1e-5, "tanh(r)")
+        for role in ("expert", "agent"):
+            assert_close(m.v_field(at, st, tt, role).cpu().numpy(), g[f"v_{role}"], 1e-5, role)
+    else:
+        assert_close(m.net(at, st, tt).cpu().numpy(), g["v"], 1e-5, "v")
+
+
+@pytest.mark.parametrize("B", [1, 31, 32, 33, 127, 129, 1000])
+def test_ragged_batches_vs_oracle(B):
+    spec = cf.NetSpec(11, 3, 256, 4, 2)
+    flat = cf.make_params(spec, 77, 2.0)
+    m = build_model(spec, flat)
+    s, a = synth.states_actions(100 + B, B, 11, 3)
+    probe = synth.rademacher(200 + B, (B, 3))
+    for mode, tol, kink in _modes():
+        le, la, rw = m.score(dev(s), dev(a), n_steps=16, probe=dev(probe), precision=mode)
+        for role, got in (("expert", le), ("agent", la)):
+            ref = cf.log_prob(spec, flat, s, a, role, probe, 16)
+            assert_close(got.cpu().numpy(), ref, tol, f"{mode} B={B} {role}", max(kink, 1.5 / B))
+
+
+def test_empty_batch():
+    spec = cf.NetSpec(6, 2, 128, 4, 2)
+    m = build_model(spec, cf.make_params(spec, 5, 1.0))
+    le, la, rw = m.score(torch.zeros(0, 6, device="cuda"), torch.zeros(0, 2, device="cuda"),
+                         probe=torch.zeros(0, 2, device="cuda"))
+    assert le.shape == (0,) and la.shape == (0,) and rw.shape == (0,)
+
+
+@pytest.mark.parametrize("reward_type", ["raw", "norm", "exp", "clip", "smooth"])
+def test_reward_types(reward_type):
+    spec = cf.NetSpec(6, 2, 128, 4, 2)
+    flat = cf.make_params(spec, 9, 3.0)
+    m = build_model(spec, flat)
+    B = 256
+    s, a = synth.states_actions(31, B, 6, 2)
+    probe = synth.rademacher(32, (B, 2))
+    le, la, rw = m.score(dev(s), dev(a), n_steps=8, probe=dev(probe), reward_type=reward_type)
+    r32 = (le - la).cpu().numpy()
+    ref = cf.reward_transform(r32.astype(np.float32), reward_type)
+    assert_close(rw.cpu().numpy(), ref, 2e-6, reward_type)
+
+
+def test_bad_reward_type_raises():
+    spec = cf.NetSpec(6, 2, 128, 4, 2)
+    m = build_model(spec, cf.make_params(spec, 9, 1.0))
+    with pytest.raises(ValueError):
+        m.score(torch.zeros(4, 6, device="cuda"), torch.zeros(4, 2, device="cuda"), reward_type="bogus")
+
+
+def test_default_probe_matches_reference_generator():
+    """Without an explicit probe, scrf uses _rademacher((B,a)): identical on every call."""
+    from modril_b200.flowril import _rademacher
+    p1 = _rademacher((64, 3), device="cuda")
+    p2 = _rademacher((64, 3), device="cuda")
+    assert torch.equal(p1, p2) and set(p1.unique().tolist()) == {-1.0, 1.0}
+    spec = cf.NetSpec(11, 3, 128, 4, 2)
+    m = build_model(spec, cf.make_params(spec, 3, 2.0))
+    s, a = synth.states_actions(1, 64, 11, 3)
+    a1 = m.log_prob(dev(s), dev(a), "expert")
+    a2 = m.log_prob(dev(s), dev(a), "expert", probe=p1)
+    assert torch.equal(a1, a2)
+
+
+def test_score_host_matches_device():
+    import ctypes as C
+    from modril_b200 import _native
+    from modril_b200.flowril.pretrain import _t_mid
+    spec = cf.NetSpec(17, 6, 256, 4, 2)
+    flat = cf.make_params(spec, 21, 2.0)
+    m = build_model(spec, flat)
+    B, n = 3000, 12
+    s, a = synth.states_actions(41, B, 17, 6)
+    probe = synth.rademacher(42, (B, 6))
+    le, la, rw = m.score(dev(s), dev(a), n_steps=n, probe=dev(probe), reward_type="smooth")
+    h = m.net.native()
+    outs = [np.empty(B, np.float32) for _ in range(3)]
+    ptr = lambda x: C.c_void_p(x.ctypes.data)
+    rc = _native.lib().frl_score_host(h, h, ptr(s), ptr(a), ptr(probe), 0, _t_mid(n), n, 4, ptr(outs[0]),
+                                      ptr(outs[1]), ptr(outs[2]), B, 0)
+    _native.check(rc, "frl_score_host")
+    assert np.array_equal(outs[0], le.cpu().numpy())
+    assert np.array_equal(outs[1], la.cpu().numpy())
+    assert np.array_equal(outs[2], rw.cpu().numpy())
+
+
+def test_full_size_properties():
+    """BASELINE config 'maze, batch 64k, 20-step': properties that need no oracle at this size --
+    (i) determinism, (ii) permutation equivariance over rows, (iii) agreement of a 4096-row slice with the oracle,
+    (iv) exact trace == mean over many Hutchinson probes within its standard error."""
+    spec = cf.NetSpec(6, 2, 256, 4, 2)
+    flat = cf.make_params(spec, 50, 2.0)
+    m = build_model(spec, flat)
+    B, n = 65536, 20
+    s, a = synth.states_actions(51, B, 6, 2)
+    probe = synth.rademacher(52, (B, 2))
+    st, at, pt = dev(s), dev(a), dev(probe)
+    le, la, rw = m.score(st, at, n_steps=n, probe=pt)
+    le2, la2, _ = m.score(st, at, n_steps=n, probe=pt)
+    assert torch.equal(le, le2) and torch.equal(la, la2)
+    perm = torch.randperm(B, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    lep, lap, _ = m.score(st[perm], at[perm], n_steps=n, probe=pt[perm])
+    assert torch.equal(lep, le[perm]) and torch.equal(lap, la[perm])
+    idx = slice(30000, 30000 + 1024)
+    ref = cf.log_prob(spec, flat, s[idx], a[idx], "expert", probe[idx], n)
+    assert_close(le[idx].cpu().numpy(), ref, 1e-4, "64k slice vs oracle", 0.011)
+    assert torch.isfinite(rw).all()
