@@ -26,12 +26,12 @@ int check_pair(const frl_net* e, const frl_net* a) {
 }
 
 int dispatch_score(const ScoreArgs& args, int precision, cudaStream_t st) {
+    if (args.B <= 0) return FRL_OK;  // empty batch: nothing to do (pointers may legitimately be null)
     FRL_REQUIRE(args.n_steps >= 1 && args.n_steps <= kMaxSteps, "n_steps must be in 1..256");
     FRL_REQUIRE(args.t_mid_host != nullptr, "null t_mid");
     FRL_REQUIRE(args.s && args.a, "null s/a");
     FRL_REQUIRE(args.probe_mode == FRL_PROBE_EXACT || args.probe != nullptr, "null probe");
     FRL_REQUIRE(args.probe_mode >= 0 && args.probe_mode <= 2, "bad probe_mode");
-    if (args.B <= 0) return FRL_OK;
     int rc;
     if (precision == FRL_PREC_FP32) {
         rc = launch_logprob_f32(args, st);

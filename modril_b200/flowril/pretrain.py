@@ -125,12 +125,11 @@ class _FMLoss(torch.autograd.Function):
     the stored gradient (scaled by grad_output) to autograd so that ``loss.backward()`` fills ``p.grad``."""
 
     @staticmethod
-    def forward(ctx, net, sign, s, a0, t, noise, *params):
+    def forward(ctx, net, sign, need_grad, s, a0, t, noise, *params):
         dev = net.flat_params().device
         h = net.native()
         B = a0.shape[0]
         loss = torch.empty(1, device=dev)
-        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
         grad = torch.empty_like(net.flat_params()) if need_grad else None
         _native.check(_native.lib().frl_cfm_loss_grad(h, float(sign), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B, 0,
                                                       1.0, 0, _ptr(loss), _ptr(grad), _current_stream(dev)),
@@ -141,7 +140,7 @@ class _FMLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        outs = [None] * 6
+        outs = [None] * 7
         flat = ctx.flat_grad
         for p, off, n in ctx.net.param_slices():
             if flat is None or not p.requires_grad:
@@ -162,10 +161,9 @@ def _fm_loss_native(net, sign, s, a0, t, noise):
     if a0.shape != (B, net.a_dim) or s.shape != (B, net.s_dim) or t.numel() != B or noise.shape != a0.shape:
         raise ValueError("fm_loss: inconsistent batch shapes")
     params = [p for p, _, _ in net.param_slices()]
-    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-        return _FMLoss.apply(net, sign, s, a0, t, noise, *params)
-    with torch.no_grad():
-        return _FMLoss.apply(net, sign, s, a0, t, noise, *params)
+    # (grad mode is always off inside Function.forward, so decide here whether dL/dtheta is wanted)
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _FMLoss.apply(net, sign, need_grad, s, a0, t, noise, *params)
 
 
 class FlowMatching(nn.Module):
