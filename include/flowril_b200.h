@@ -47,7 +47,8 @@ typedef enum {
 typedef enum {
     FRL_PREC_FP32 = 0,    /* FP32 FFMA on CUDA cores: the 1e-4 parity mode                               */
     FRL_PREC_BF16 = 1,    /* tcgen05 tensor cores, bf16 operands, fp32 accumulate, fp32 ODE state/trace  */
-    FRL_PREC_BF16X3 = 2   /* tcgen05, 3-term bf16 split of both operands (fp32-grade products)           */
+    FRL_PREC_BF16X3 = 2,  /* tcgen05, 3-term split of both operands (fp32-grade products)                */
+    FRL_PREC_FP16 = 3     /* tcgen05 tensor cores, fp16 operands (11-bit significand), fp32 accumulate   */
 } frl_precision;
 
 /* divergence estimator of the log-density (modril/flowril/pretrain.py:88-92, :163-177) */

@@ -12,10 +12,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libflowril_b200.so")
 
 ABI_VERSION = 1
-PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3
+HAS_TC = True  # tensor-core (tcgen05) log-density kernels are built in
 PROBE_SHARED, PROBE_PER_STEP, PROBE_EXACT = 0, 1, 2
 REWARD_TYPES = {"raw": 0, "norm": 1, "exp": 2, "clip": 3, "smooth": 4}
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
 
 # every symbol include/flowril_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = (

@@ -35,7 +35,7 @@ int dispatch_score(const ScoreArgs& args, int precision, cudaStream_t st) {
     int rc;
     if (precision == FRL_PREC_FP32) {
         rc = launch_logprob_f32(args, st);
-    } else if (precision == FRL_PREC_BF16 || precision == FRL_PREC_BF16X3) {
+    } else if (precision == FRL_PREC_BF16 || precision == FRL_PREC_BF16X3 || precision == FRL_PREC_FP16) {
         rc = launch_logprob_tc(args, precision, st);
     } else {
         set_error("invalid argument: unknown precision");
