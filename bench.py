@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""Benchmark of the FLOWRIL density hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload maze] [--precision fp16]
+
+A "step" is one pass of the hot path over one synthetic batch: log p_E, log p_A and the reward for B (s, a) rows
+(two n_steps-step Euler integrations with the Hutchinson divergence; reference modril/flowril/flowril.py:175-208).
+Default workload = BASELINE.json configs[1]: maze (s 6 + a 2), batch 65536, 20-step ODE, scrf net H=256 depth 4.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (task dims key, batch per GPU, n_steps)
+    "sine": ("sine", 65536, 32),
+    "maze": ("maze", 65536, 20),
+    "hopper": ("hopper", 262144, 32),
+    "halfcheetah": ("halfcheetah", 262144, 32),
+    "ant": ("ant", 1048576, 32),
+    "hand": ("hand", 1048576, 32),
+}
+HIDDEN, DEPTH = 256, 4
+
+
+def algorithmic_flops_per_sample(s_dim, a_dim, n_steps, n_heads=2, H=HIDDEN, depth=DEPTH):
+    """SURVEY 8(d) / BASELINE.md: GEMM multiply-adds of the reference formulation, 2 FLOP per MAC, no hoisting
+    credit; Hutchinson with one probe: 2 roles * n_steps * (F_fwd + F_tan)."""
+    d_in = a_dim + s_dim + 1
+    f_fwd = 2 * (d_in * H + (depth - 1) * H * H + n_heads * H * a_dim)
+    f_tan = 2 * (a_dim * H + (depth - 1) * H * H + n_heads * H * a_dim)
+    return 2 * n_steps * (f_fwd + f_tan)
+
+
+def measured_peak_tflops():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops"]), "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone, L2 flushed between steps)"
+    except Exception:
+        return 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_inputs(task, B, n_steps, seed=0):
+    import numpy as np
+
+    from oracle import synth
+
+    s_dim, a_dim = synth.TASK_DIMS[task]
+    s, a = synth.states_actions(1000 + seed, B, s_dim, a_dim)
+    probe = synth.rademacher(1234, (B, a_dim))  # same probe at every step and for both roles (scrf semantics)
+    return s_dim, a_dim, s, a, probe
+
+
+def make_trained_model(task, device, steps=200):
+    """Default nn.Linear init under torch.manual_seed(0) + 200 CFM Adam steps (lr 1e-3) on the synthetic expert
+    a = tanh(s[:, :a_dim]) + 0.1 N(0,1) so that the fields are non-trivial."""
+    import numpy as np
+    import torch
+
+    from modril_b200.flowril import CoupledResidualFM, FusedAdam, train_step
+    from oracle import synth
+
+    s_dim, a_dim = synth.TASK_DIMS[task]
+    torch.manual_seed(0)
+    model = CoupledResidualFM(s_dim, a_dim, HIDDEN, depth=DEPTH).to(device)
+    opt = FusedAdam([model.net], lr=1e-3)
+    pool_s, pool_a = synth.states_actions(77, 8192, s_dim, a_dim)
+    pool_e = synth.expert_actions(78, pool_s, a_dim)
+    d_s, d_e, d_a = (torch.from_numpy(x).to(device) for x in (pool_s, pool_e, pool_a))
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for it in range(steps):
+        idx = torch.randint(0, 8192, (2, 256), generator=g).to(device)
+        t = (torch.rand(2, 256, 1, generator=g) * (1 - 2e-3) + 1e-3).to(device)
+        z = torch.randn(2, 256, a_dim, generator=g).to(device)
+        train_step([dict(net=model.net, sign=1.0, s=d_s[idx[0]], a0=d_e[idx[0]], t=t[0], noise=z[0]),
+                    dict(net=model.net, sign=-1.0, s=d_s[idx[1]], a0=d_a[idx[1]], t=t[1], noise=z[1])], opt, 1.0)
+    torch.cuda.synchronize(device)
+    return model
+
+
+def cpu_port_rate(task, B_sample, n_steps, flat, threads, reps=1):
+    """Scored samples/s of the torch-CPU port of the reference path (oracle/torch_port.py) on B_sample rows."""
+    import torch
+
+    from oracle import closed_form as cf
+    from oracle import synth, torch_port
+
+    torch.set_num_threads(threads)
+    s_dim, a_dim = synth.TASK_DIMS[task]
+    spec = cf.NetSpec(s_dim, a_dim, HIDDEN, DEPTH, 2)
+    _, _, s, a, probe = make_inputs(task, B_sample, n_steps)
+    st, at, pt = (torch.from_numpy(x) for x in (s, a, probe))
+    ft = torch.from_numpy(flat).clone()
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        torch_port.score(spec, ft, ft, st, at, pt, n_steps)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return B_sample / best, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (torch port, all host threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+
+    from oracle import closed_form as cf
+    from oracle import synth
+
+    task, B, n_steps = WORKLOADS[args.workload]
+    s_dim, a_dim = synth.TASK_DIMS[task]
+    spec = cf.NetSpec(s_dim, a_dim, HIDDEN, DEPTH, 2)
+    flat = cf.make_params(spec, 0, 1.0)
+    threads = os.cpu_count() or 1
+    rate, _ = cpu_port_rate(task, 1024, n_steps, flat, threads, reps=2)  # calibration (first pass warms up)
+    Bs = int(min(B, max(1024, rate * 4.0)))                               # ~4 s of CPU work per step
+    Bs = Bs // 1024 * 1024
+    times = []
+    for i in range(args.warmup + args.steps):
+        _, dt = cpu_port_rate(task, Bs, n_steps, flat, threads)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = Bs / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "scored_samples_per_sec", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{task}: s {s_dim} + a {a_dim}, {n_steps}-step ODE log-density, both roles + reward, "
+                               f"scrf H={HIDDEN} depth={DEPTH}", "batch_per_step_sample": Bs, "batch_full": B,
+                   "n_steps": n_steps},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{Bs} of {B} rows per step; torch-CPU port of the reference op sequence "
+                                   f"(oracle/torch_port.py), torch {torch.__version__}"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from modril_b200.flowril import FusedAdam, score_pair_host, train_step
+    from oracle import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    task, B, n_steps = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    s_dim, a_dim, s, a, probe = make_inputs(task, B, n_steps, seed=rank)
+    model = make_trained_model(task, device)
+    st, at, pt = (torch.from_numpy(x).to(device) for x in (s, a, probe))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+    prec = args.precision
+
+    def step():
+        return model.score(st, at, n_steps=n_steps, probe=pt, precision=prec)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(args.warmup):
+        step()
+        flush.zero_()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(local) as clocks:
+        for e0, e1 in ev:
+            e0.record()
+            out = step()
+            e1.record()
+            flush.zero_()
+        barrier()
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    tt = torch.tensor([total_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    value = world * B / (ms_per_step / 1e3)
+
+    # ---- end to end through the host-buffer entry point (pinned host memory -> device -> pinned host) ----
+    hs, ha, hp = (torch.from_numpy(x).pin_memory() for x in (s, a, probe))
+    houts = tuple(torch.empty(B).pin_memory() for _ in range(3))
+
+    def e2e_step():
+        return score_pair_host(model.net, model.net, hs, ha, hp, n_steps=n_steps, precision=prec, out=houts)
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()  # returns after the results are in host memory
+        flush.zero_()
+    torch.cuda.synchronize(device)
+    e2e_s = time.perf_counter() - t0
+    # subtract nothing: the L2 flush (~0.1 ms) stays inside, so this is a slight under-estimate of throughput
+    te = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(te.item())
+    e2e_check = float((houts[2] - out[2].cpu()).abs().max())
+
+    # ---- parity spot check inside the bench: this mode vs the fp32 kernel on the first 4096 rows ----
+    n_chk = min(4096, B)
+    ref = model.score(st[:n_chk], at[:n_chk], n_steps=n_steps, probe=pt[:n_chk], precision="fp32")
+    got = model.score(st[:n_chk], at[:n_chk], n_steps=n_steps, probe=pt[:n_chk], precision=prec)
+    rel = ((got[0] - ref[0]).abs() / ref[0].abs().clamp_min(1.0)).cpu().numpy()
+    parity = {"vs": "fp32 kernel, first %d rows, log p_E" % n_chk, "median_rel": float(np.median(rel)),
+              "p99_rel": float(np.quantile(rel, 0.99)), "max_rel": float(rel.max())}
+
+    # ---- other modes (kernel-only, 3 steps each) and the CFM train step, for context ----
+    extra = {}
+    for mode in ("fp32", "bf16", "fp16"):
+        if mode == prec:
+            continue
+        model.score(st, at, n_steps=n_steps, probe=pt, precision=mode)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 2 if mode == "fp32" else 5
+        e0.record()
+        for _ in range(reps):
+            model.score(st, at, n_steps=n_steps, probe=pt, precision=mode)
+        e1.record()
+        torch.cuda.synchronize(device)
+        extra[mode] = world * B / (e0.elapsed_time(e1) / reps / 1e3)
+
+    Bt = 65536
+    ts, ta = st[:Bt] if B >= Bt else st, at[:Bt] if B >= Bt else at
+    Bt = ts.shape[0]
+    g = torch.Generator(device="cpu").manual_seed(9 + rank)
+    tt_ = (torch.rand(2, Bt, 1, generator=g) * (1 - 2e-3) + 1e-3).to(device)
+    zz = torch.randn(2, Bt, a_dim, generator=g).to(device)
+    opt = FusedAdam([model.net], lr=1e-4)
+    grp = (dist.group.WORLD, world) if world > 1 else None
+
+    def tstep():
+        return train_step([dict(net=model.net, sign=1.0, s=ts, a0=ta, t=tt_[0], noise=zz[0]),
+                           dict(net=model.net, sign=-1.0, s=ts, a0=ta, t=tt_[1], noise=zz[1])], opt, 1.0, world=grp)
+
+    for _ in range(3):
+        tstep()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_t = 10
+    e0.record()
+    for _ in range(n_t):
+        tstep()
+    e1.record()
+    barrier()
+    tms = torch.tensor([e0.elapsed_time(e1) / n_t], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    train_rate = world * 2 * Bt / (float(tms.item()) / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the fused integrator; the reward kernel is ~0.1 % of the step) ----
+    flops = algorithmic_flops_per_sample(s_dim, a_dim, n_steps) * B
+    peak, peak_src = measured_peak_tflops()
+    achieved = flops / (ms_per_step / 1e3) / 1e12
+    if prec == "fp32":
+        peak, peak_src = 2 * 128 * 148 * 1.965e9 / 1e12, "FP32 FFMA peak 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)"
+    roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src,
+            "kernel": "logprob_tc_kernel" if prec != "fp32" else "logprob_f32_kernel",
+            "algorithmic_flops_per_sample": algorithmic_flops_per_sample(s_dim, a_dim, n_steps)}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import closed_form as cf
+
+        flat = model.net.flat_params().detach().cpu().numpy().copy()
+        threads = os.cpu_count() or 1
+        rate, _ = cpu_port_rate(task, 1024, n_steps, flat, threads, reps=2)
+        Bs = int(min(4 * B, max(2048, rate * 12.0))) // 1024 * 1024  # ~12 s of CPU work
+        rate, dt = cpu_port_rate(task, Bs, n_steps, flat, threads)
+        cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"{Bs} of {B} rows, one pass ({dt:.1f} s), torch-CPU port of the reference op sequence "
+                         f"(oracle/torch_port.py) with {threads} threads"}
+
+    line = {
+        "metric": "scored_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": prec, "data": "synthetic",
+        "config": {"workload": f"{task}: s {s_dim} + a {a_dim}, {n_steps}-step ODE log-density (Hutchinson, caller "
+                               f"probe), both roles + reward, scrf H={HIDDEN} depth={DEPTH}",
+                   "batch_per_gpu": B, "n_steps": n_steps, "parallelism": f"row-sharded x{world}, no collective",
+                   "l2": "256 MiB buffer rewritten between timed steps (inputs are smaller than L2)",
+                   "weights": "default init seed 0 + 200 CFM Adam steps on a synthetic expert"},
+        "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(world * B * (s_dim + 2 * a_dim) * 4),
+                "d2h_bytes_per_step": int(world * B * 3 * 4), "api": "frl_score_host via score_pair_host, pinned host buffers",
+                "max_abs_diff_vs_device_path": e2e_check},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clocks.summary(),
+        "parity": parity,
+        "other_modes_samples_per_sec": extra,
+        "train": {"metric": "cfm_train_samples_per_sec", "value": train_rate, "unit": "samples/s",
+                  "rows_per_step_per_gpu": 2 * Bt, "dtype": "fp32", "collective": "NCCL all-reduce of the flat grad"
+                  if world > 1 else "none"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="maze", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp16", choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--batch", type=int, default=0, help="override rows per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

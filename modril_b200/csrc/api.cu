@@ -141,6 +141,7 @@ extern "C" int frl_score_host(frl_net* ne, frl_net* na, const float* s_h, const 
     FRL_REQUIRE(n_steps >= 1 && n_steps <= kMaxSteps, "n_steps must be in 1..256");
     if (B <= 0) return FRL_OK;
     FRL_CUDA(cudaSetDevice(ne->cfg.device));
+    FRL_CUDA(cudaDeviceSynchronize());  // weight packs may still be in flight on the caller's streams
     const int S = ne->cfg.s_dim, A = ne->cfg.a_dim;
     const long long chunk = std::min<long long>(B, 262144);
     const int probe_rows = probe_mode == FRL_PROBE_PER_STEP ? n_steps : (probe_mode == FRL_PROBE_SHARED ? 1 : 0);

@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "frl_internal.h"
@@ -31,7 +32,7 @@ namespace frl {
 
 namespace tc {
 
-constexpr int kThreads = 320;          // 10 warps
+constexpr int kThreads = 384;          // 12 warps: producer, MMA-primal, MMA-tangent, TMEM owner, 8 epilogue
 constexpr int kEpiWarps = 8;
 constexpr int kStageBytes = 16384;
 constexpr int kMaxBlocks = 72;
@@ -44,9 +45,9 @@ struct Blk {
     uint16_t a_koff;    // first k-chunk (of 8) of the A operand this block multiplies
     uint8_t n_k16;      // K=16 MMAs per tile for the primal
     uint8_t n_k16_t;    // ... for the tangent (layer 0: only the action columns carry a tangent)
-    uint8_t src_x0;     // 1: A operand is the layer-0 input buffer, 0: the activation buffer
+    uint8_t src;        // A operand: 0 activation buffer, 1 layer-0 input buffer, 2 the constant "ones" tile (bias)
     uint8_t h;          // accumulator half
-    uint8_t first;      // first block of its accumulator (overwrite instead of accumulate)
+    uint8_t first;      // bit0: first primal MMA overwrites the accumulator, bit1: same for the tangent
     uint8_t commit;     // 0: none, 1: commit d_full[0], 2: commit d_full[1]
     uint8_t wait;       // bit0: wait a_ready[0], bit1: wait a_ready[1] before issuing
     uint8_t pad;
@@ -64,9 +65,11 @@ struct Params {
     long long B;
     int n_roles, n_heads, depth, s_dim, a_dim, d_in, K0p, KT, NOp, H;
     int n_steps, basis, accumulate, n_blocks, n_stages;
+    unsigned long long* trace;  // FRL_TC_TRACE: [role][8192] clock stamps of CTA 0 (timing experiments only)
+    int debug;  // FRL_TC_DEBUG env: bit0 skip trunk-epilogue work, bit1 skip MMA issue (timing experiments only)
     float delta;
     // shared-memory byte offsets
-    uint32_t off_a, off_x0p, off_x0t, off_bias, off_state, off_ring;
+    uint32_t off_a, off_x0p, off_x0t, off_ones, off_bias, off_state, off_rec, off_ring;
     Blk blk[kMaxBlocks];
     float t_mid[kMaxSteps];
 };
@@ -139,11 +142,56 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that also names the destination registers, so the compiler cannot hoist their uses above the wait
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&a)[32], uint32_t (&b)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
+                   "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]),
+                   "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31]),
+                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                   "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]),
+                   "+r"(b[16]), "+r"(b[17]), "+r"(b[18]), "+r"(b[19]), "+r"(b[20]), "+r"(b[21]), "+r"(b[22]), "+r"(b[23]),
+                   "+r"(b[24]), "+r"(b[25]), "+r"(b[26]), "+r"(b[27]), "+r"(b[28]), "+r"(b[29]), "+r"(b[30]), "+r"(b[31])
+                 :
+                 : "memory");
+}
+// 0xFFFF in each half whose source float has its sign bit set (z < 0 or -0): PRMT with sign replication
+__device__ __forceinline__ uint32_t neg_mask16x2(uint32_t z_lo, uint32_t z_hi) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(d) : "r"(z_lo), "r"(z_hi));
+    return d;
+}
+
+struct Tracer {
+    unsigned long long* buf;
+    int n;
+    __device__ __forceinline__ void init(unsigned long long* base, int role) {
+        buf = (base != nullptr && blockIdx.x == 0) ? base + (size_t)role * 8192 : nullptr;
+        n = 0;
+    }
+    __device__ __forceinline__ void mark(unsigned tag) {
+        if (buf && n < 8190) {
+            buf[n++] = ((unsigned long long)tag << 48) | (clock64() & 0xFFFFFFFFFFFFull);
+        }
+    }
+};
 
 // 16-bit operand types
 template <typename T> struct Cvt;
 template <> struct Cvt<__half> {
     static constexpr uint32_t kFmt = 0;  // F16
+    // relu + round + saturate + pack in ONE instruction (F2FP.SATFINITE.RELU.F16.F32.PACK_AB)
+    __device__ static __forceinline__ uint32_t pack2_relu(uint32_t lo, uint32_t hi) {
+        uint32_t d;
+        asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+        return d;
+    }
+    __device__ static __forceinline__ uint32_t pack2_sat(uint32_t lo, uint32_t hi) {
+        uint32_t d;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+        return d;
+    }
     __device__ static __forceinline__ uint32_t pack2(float lo, float hi) {
         lo = fminf(fmaxf(lo, -65504.f), 65504.f);
         hi = fminf(fmaxf(hi, -65504.f), 65504.f);
@@ -158,6 +206,16 @@ template <> struct Cvt<__half> {
 };
 template <> struct Cvt<__nv_bfloat16> {
     static constexpr uint32_t kFmt = 1;  // BF16
+    __device__ static __forceinline__ uint32_t pack2_relu(uint32_t lo, uint32_t hi) {
+        uint32_t d;
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+        return d;
+    }
+    __device__ static __forceinline__ uint32_t pack2_sat(uint32_t lo, uint32_t hi) {
+        uint32_t d;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+        return d;
+    }
     __device__ static __forceinline__ uint32_t pack2(float lo, float hi) {
         __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
         return *reinterpret_cast<uint32_t*>(&h);
@@ -171,7 +229,7 @@ template <> struct Cvt<__nv_bfloat16> {
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T16>
+template <typename T16, int H>
 __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // header: barriers
@@ -191,22 +249,23 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
     uint8_t* sRing = smem + p.off_ring;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int H = p.H, NH = H / 2;
-    const uint32_t a_tile_bytes = (uint32_t)H * kRows * 2;  // one activation tile
+    constexpr int NH = H / 2;
+    constexpr uint32_t a_tile_bytes = (uint32_t)H * kRows * 2;  // one activation tile
+    uint8_t* sOnes = smem + p.off_ones;  // [2][128][8]: columns 0..2 are 1.0 (multiplies the bias hi/mid/lo rows)
     const int nbias = p.depth * H + p.NOp;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(w_full(s), 1);
-            mbar_init(w_empty(s), 1);
+            mbar_init(w_empty(s), 2);   // one arrival per MMA-issuing warp
         }
         mbar_init(a_ready(0), kEpiWarps);
         mbar_init(a_ready(1), kEpiWarps);
-        mbar_init(d_full(0), 1);
-        mbar_init(d_full(1), 1);
+        mbar_init(d_full(0), 2);
+        mbar_init(d_full(1), 2);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == 3) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(512)
                      : "memory");
@@ -217,6 +276,27 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
         sBias[i] = p.bias[i / nbias][i % nbias];
     for (int i = threadIdx.x; i < (p.K0p + p.KT) * kRows * 2 / 16; i += kThreads)
         reinterpret_cast<uint4*>(sX0p)[i] = make_uint4(0, 0, 0, 0);  // X0t follows X0p contiguously
+    for (int i = threadIdx.x; i < 2 * kRows; i += kThreads) {
+        const uint32_t one = Cvt<T16>::one(1.f);
+        reinterpret_cast<uint4*>(sOnes)[i] = i < kRows ? make_uint4(one | (one << 16), one, 0, 0) : make_uint4(0, 0, 0, 0);
+    }
+    // per-block issue records for the two MMA warps (one 16-byte shared-memory load per block in the hot loop)
+    uint4* sRec = reinterpret_cast<uint4*>(smem + p.off_rec);  // [2 tiles][n_blocks]
+    for (int i = threadIdx.x; i < 2 * p.n_blocks; i += kThreads) {
+        const int x = i / p.n_blocks, b = i % p.n_blocks;
+        const Blk& k = p.blk[b];
+        const uint32_t src = k.src == 0 ? smem_u32(smem + p.off_a) + x * a_tile_bytes
+                             : (k.src == 1 ? smem_u32(x == 0 ? sX0p : sX0t) : smem_u32(sOnes));
+        const uint32_t a_lo = (((src + (uint32_t)k.a_koff * (kRows * 16)) >> 4) & 0x3FFF) | ((uint32_t)(kRows * 16 >> 4) << 16);
+        const uint32_t idesc = (1u << 4) | (Cvt<T16>::kFmt << 7) | (Cvt<T16>::kFmt << 10) | ((uint32_t)(kRows >> 4) << 24) |
+                               ((uint32_t)(k.nrows >> 3) << 17);
+        const uint32_t nk = x == 0 ? k.n_k16 : k.n_k16_t;
+        const uint32_t first = (k.first >> x) & 1;
+        // .z: nrows (B k-chunk stride in 16-byte units) | d column offset << 16 ; .w: nk | first<<8 | commit<<16 | wait<<24
+        sRec[i] = make_uint4(a_lo, idesc, (uint32_t)k.nrows | (((uint32_t)k.h * 256 + (uint32_t)x * 128) << 16),
+                             nk | (first << 8) | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24));
+    }
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -230,68 +310,89 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            Tracer tr; tr.init(p.trace, 0);
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const uint8_t* wbase = p.wpack[tile % p.n_roles];
                 for (int step = 0; step < p.n_steps; ++step) {
                     for (int b = 0; b < p.n_blocks; ++b) {
                         mbar_wait(w_empty(stage), phase ^ 1);
-                        mbar_expect_tx(w_full(stage), p.blk[b].bytes);
-                        bulk_g2s(smem_u32(sRing + (size_t)stage * kStageBytes), wbase + p.blk[b].goff, p.blk[b].bytes,
-                                 w_full(stage));
+                        tr.mark(b);
+                        if (p.debug & 4) {
+                            mbar_arrive(w_full(stage));  // timing experiment: no weight traffic
+                        } else {
+                            mbar_expect_tx(w_full(stage), p.blk[b].bytes);
+                            bulk_g2s(smem_u32(sRing + (size_t)stage * kStageBytes), wbase + p.blk[b].goff,
+                                     p.blk[b].bytes, w_full(stage));
+                        }
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer ----------------------------------------------
+    } else if (warp == 1 || warp == 2) {
+        // ------------------------------ MMA issuers: warp 1 = primal tile, warp 2 = tangent tile ------------------
+        // (two issuing threads: descriptor building + tcgen05.mma/commit issue of ONE thread is slower than the
+        //  tensor pipe at N=128; the tiles write different accumulators, so they need no mutual ordering)
         if (lane == 0) {
+            const int x = warp - 1;
             int stage = 0;
             uint32_t phase = 0, par_a0 = 0, par_a1 = 0;
-            const uint32_t idesc_base = (1u << 4) | (Cvt<T16>::kFmt << 7) | (Cvt<T16>::kFmt << 10) | ((uint32_t)(kRows >> 4) << 24);
-            const uint32_t a_base = smem_u32(sA), x0p_base = smem_u32(sX0p), x0t_base = smem_u32(sX0t);
+            const uint4* rec = sRec + x * p.n_blocks;
+            const uint32_t ring_lo = (smem_u32(sRing) >> 4);
+            constexpr uint32_t kDescHi = (uint32_t)(128 >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+            Tracer tr; tr.init(p.trace, 1 + x);
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int step = 0; step < p.n_steps; ++step) {
                     for (int b = 0; b < p.n_blocks; ++b) {
-                        const Blk& k = p.blk[b];
-                        if (k.wait & 1) { mbar_wait(a_ready(0), par_a0); par_a0 ^= 1; }
-                        if (k.wait & 2) { mbar_wait(a_ready(1), par_a1); par_a1 ^= 1; }
+                        const uint4 r = rec[b];
+                        tr.mark(0x100 + b);
+                        if (r.w & (1u << 24)) { mbar_wait(a_ready(0), par_a0); par_a0 ^= 1; }
+                        if (r.w & (2u << 24)) { mbar_wait(a_ready(1), par_a1); par_a1 ^= 1; }
                         mbar_wait(w_full(stage), phase);
                         tc_fence_after();
-                        const uint32_t idesc = idesc_base | ((uint32_t)(k.nrows >> 3) << 17);
-                        const uint32_t w_base = smem_u32(sRing + (size_t)stage * kStageBytes);
-                        const uint32_t w_lbo = (uint32_t)k.nrows * 16;
-#pragma unroll 1
-                        for (int x = 0; x < 2; ++x) {
-                            const int nk = x == 0 ? k.n_k16 : k.n_k16_t;
-                            const uint32_t src = k.src_x0 ? (x == 0 ? x0p_base : x0t_base) : a_base + x * a_tile_bytes;
-                            const uint32_t d = tmem + (uint32_t)k.h * 256 + (uint32_t)x * 128;
-                            for (int u = 0; u < nk; ++u) {
-                                const uint64_t da = make_desc(src + (uint32_t)(k.a_koff + 2 * u) * (kRows * 16), kRows * 16);
-                                const uint64_t db = make_desc(w_base + (uint32_t)(2 * u) * w_lbo, w_lbo);
-                                umma(d, da, db, idesc, (k.first && u == 0) ? 0u : 1u);
+                        tr.mark(0x300 + b);
+                        const uint32_t nk = (p.debug & 2) ? 0 : (r.w & 0xFF);
+                        if (nk) {
+                            const uint32_t nrows = r.z & 0xFFFF;
+                            const uint32_t d = tmem + (r.z >> 16);
+                            uint32_t a_lo = r.x;
+                            uint32_t b_lo = ((ring_lo + (uint32_t)stage * (kStageBytes >> 4)) & 0x3FFF) | (nrows << 16);
+                            uint32_t acc = ((r.w >> 8) & 1) ? 0u : 1u;
+                            for (uint32_t u = 0; u < nk; ++u) {
+                                const uint64_t da = ((uint64_t)kDescHi << 32) | a_lo;
+                                const uint64_t db = ((uint64_t)kDescHi << 32) | b_lo;
+                                umma(d, da, db, r.y, acc);
+                                acc = 1u;
+                                a_lo += 2 * (kRows * 16 >> 4);   // two k-chunks of 8 per K=16 MMA
+                                b_lo += 2 * nrows;
                             }
+                            umma_commit(w_empty(stage));
+                        } else {
+                            mbar_arrive(w_empty(stage));  // nothing issued by this warp for the block
                         }
-                        umma_commit(w_empty(stage));
-                        if (k.commit) umma_commit(d_full(k.commit - 1));
+                        const uint32_t cm = (r.w >> 16) & 0xFF;
+                        if (cm) umma_commit(d_full(cm - 1));
+                        tr.mark(0x400 + b);
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
+    } else if (warp == 3) {
+        // TMEM owner: nothing to do until teardown
     } else {
         // ------------------------------------------------ epilogue ------------------------------------------------
-        const int ew = warp - 2;            // 0..7
+        const int ew = warp - 4;            // 0..7
         const int q = warp & 3;             // TMEM lane quarter this warp may access
         const int ch = ew >> 2;             // which half of the N-half's columns
         const int row = q * 32 + lane;      // tile row == TMEM lane
         const int et = ew * 32 + lane;      // 0..255 epilogue thread id
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        const int cols_per_warp = NH / 2;   // 64 (H=256) or 32 (H=128)
         float* sA_state = sState;
         float* sP_state = sState + p.a_dim * kRows;
         const int t_col = p.a_dim + p.s_dim;
         uint32_t par_d0 = 0, par_d1 = 0;
+        Tracer tr; tr.init((lane == 0 && ew == 0) ? p.trace : nullptr, 3);
 
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int role = (int)(tile % p.n_roles);
@@ -330,47 +431,60 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
             for (int step = 0; step < p.n_steps; ++step) {
                 // ---- trunk layers ----
                 for (int l = 0; l < p.depth; ++l) {
-                    const float* bl = bias + l * H;
                     for (int h = 0; h < 2; ++h) {
+                        tr.mark(0x100 + l * 2 + h);
                         if (h == 0) { mbar_wait(d_full(0), par_d0); par_d0 ^= 1; }
                         else        { mbar_wait(d_full(1), par_d1); par_d1 ^= 1; }
                         tc_fence_after();
-                        for (int c0 = ch * cols_per_warp; c0 < (ch + 1) * cols_per_warp; c0 += 32) {
-                            uint32_t zp[32], zt[32];
-                            tmem_ld32(lane_addr + (uint32_t)h * 256 + (uint32_t)c0, zp);
-                            tmem_ld32(lane_addr + (uint32_t)h * 256 + 128 + (uint32_t)c0, zt);
-                            tmem_ld_wait();
-                            const int n0 = h * NH + c0;  // first output column == next layer's k index
-                            uint32_t op[16], ot[16];
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float2 bb = *reinterpret_cast<const float2*>(bl + n0 + 2 * j);
-                                const float z0 = __uint_as_float(zp[2 * j]) + bb.x;
-                                const float z1 = __uint_as_float(zp[2 * j + 1]) + bb.y;
-                                const float t0 = z0 > 0.f ? __uint_as_float(zt[2 * j]) : 0.f;
-                                const float t1 = z1 > 0.f ? __uint_as_float(zt[2 * j + 1]) : 0.f;
-                                op[j] = Cvt<T16>::pack2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
-                                ot[j] = Cvt<T16>::pack2(t0, t1);
+                        tr.mark(0x200 + l * 2 + h);
+                        if (!(p.debug & 1)) {
+                            // this warp's CPW columns of the half: all TMEM loads are issued up front, one wait
+                            constexpr int CPW = NH / 2, NCH = CPW / 32;
+                            uint32_t zp[NCH][32], zt[NCH][32];
+                            const uint32_t tb = lane_addr + (uint32_t)h * 256 + (uint32_t)(ch * CPW);
+                            tmem_ld32(tb, zp[0]);
+                            tmem_ld32(tb + 128, zt[0]);
+                            if (NCH == 2) {
+                                tmem_ld32(tb + 32, zp[NCH - 1]);
+                                tmem_ld32(tb + 128 + 32, zt[NCH - 1]);
                             }
-                            uint8_t* dp = sA + (size_t)(n0 >> 3) * (kRows * 16) + row * 16;
-                            uint8_t* dt = dp + a_tile_bytes;
+                            tmem_ld_wait_dep(zp[0], zt[0]);
+                            if (NCH == 2) tmem_ld_wait_dep(zp[NCH - 1], zt[NCH - 1]);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                *reinterpret_cast<uint4*>(dp + (size_t)i * (kRows * 16)) =
-                                    make_uint4(op[4 * i], op[4 * i + 1], op[4 * i + 2], op[4 * i + 3]);
-                                *reinterpret_cast<uint4*>(dt + (size_t)i * (kRows * 16)) =
-                                    make_uint4(ot[4 * i], ot[4 * i + 1], ot[4 * i + 2], ot[4 * i + 3]);
+                            for (int c = 0; c < NCH; ++c) {
+                                const int n0 = h * NH + ch * CPW + c * 32;  // output column == next layer's k index
+                                uint32_t op[16], ot[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    // bias is already in the accumulator (folded into the MMA); relu+round+pack is one
+                                    // F2FP; the tangent is masked by the primal's sign bits
+                                    op[j] = Cvt<T16>::pack2_relu(zp[c][2 * j], zp[c][2 * j + 1]);
+                                    ot[j] = Cvt<T16>::pack2_sat(zt[c][2 * j], zt[c][2 * j + 1]) &
+                                            ~neg_mask16x2(zp[c][2 * j], zp[c][2 * j + 1]);
+                                }
+                                uint8_t* dp = sA + (size_t)(n0 >> 3) * (kRows * 16) + row * 16;
+                                uint8_t* dt = dp + a_tile_bytes;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    *reinterpret_cast<uint4*>(dp + (size_t)i * (kRows * 16)) =
+                                        make_uint4(op[4 * i], op[4 * i + 1], op[4 * i + 2], op[4 * i + 3]);
+                                    *reinterpret_cast<uint4*>(dt + (size_t)i * (kRows * 16)) =
+                                        make_uint4(ot[4 * i], ot[4 * i + 1], ot[4 * i + 2], ot[4 * i + 3]);
+                                }
                             }
                         }
                         tc_fence_before();
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(a_ready(h));
+                        tr.mark(0x300 + l * 2 + h);
                     }
                 }
+                tr.mark(0x1FF);
                 // ---- heads: tanh, divergence, Euler update (pretrain.py:205-211) ----
                 mbar_wait(d_full(0), par_d0); par_d0 ^= 1;
                 tc_fence_after();
+                tr.mark(0x2FF);
                 const long long g = row0 + row;
                 if (ch == 0) {
                     const float* bh = bias + p.depth * H;
@@ -444,6 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(a_ready(0)); mbar_arrive(a_ready(1)); }
+                    tr.mark(0x3FF);
                 } else {
                     // the next tile's init rewrites X0 / state: every warp must be done with this tile first
                     tc_fence_before();
@@ -455,7 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 3) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
     }
@@ -466,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
 // ---------------------------------------------------------------------------------------------------------------
 struct PackBlk {
     uint32_t goff;          // bytes
-    int nrows, klen, n0, k0, layer;  // layer == depth -> heads
+    int nrows, klen, n0, k0, layer;  // layer == depth -> heads;  k0 < 0 -> bias block (rows k=0..2 = hi/mid/lo split)
 };
 struct PackParams {
     PackBlk blk[kMaxBlocks];
@@ -504,6 +619,26 @@ __global__ void tc_pack_kernel(const float* __restrict__ flat, uint8_t* __restri
         for (int e = 0; e < 8; ++e) {
             const int kg = k.k0 + j * 8 + e, ng = k.n0 + n;
             float v = 0.f;
+            if (k.k0 < 0) {
+                // bias block: column e of k-chunk 0 holds the e-th term of the 16-bit split of bias[n]
+                hv[e] = __float2half_rn(0.f);
+                bv[e] = __float2bfloat16_rn(0.f);
+                if (j == 0 && e < 3) {
+                    const float b = flat[pp.off_b[k.layer] + ng];
+                    float rh = b, rb = b;
+                    __half th = __float2half_rn(0.f);
+                    __nv_bfloat16 tb = __float2bfloat16_rn(0.f);
+                    for (int term = 0; term <= e; ++term) {
+                        th = __float2half_rn(fminf(fmaxf(rh, -65504.f), 65504.f));
+                        tb = __float2bfloat16_rn(rb);
+                        rh -= __half2float(th);
+                        rb -= __bfloat162float(tb);
+                    }
+                    hv[e] = th;
+                    bv[e] = tb;
+                }
+                continue;
+            }
             if (k.layer < pp.depth) {
                 const int K = k.layer == 0 ? pp.d_in : pp.H;
                 if (kg < K) v = flat[pp.off_w[k.layer] + (long long)ng * K + kg];
@@ -533,43 +668,45 @@ static Schedule make_schedule(const frl_net* net) {
     const int H = net->cfg.hidden, NH = H / 2, depth = net->cfg.depth, K0p = net->d_in_p, NOp = net->n_out_p;
     sc.KT = round_up(net->cfg.a_dim, 16);
     uint32_t goff = 0;
-    auto add = [&](int layer, int n0, int nrows, int k0, int klen, int a_koff, bool x0, int h, bool first, int commit,
+    auto add = [&](int layer, int n0, int nrows, int k0, int klen, int a_koff, int src, int h, int first, int commit,
                    int wait, int nk_t) {
         Blk b{};
         b.goff = goff; b.bytes = (uint32_t)nrows * klen * 2; b.nrows = (uint16_t)nrows; b.a_koff = (uint16_t)a_koff;
-        b.n_k16 = (uint8_t)(klen / 16); b.n_k16_t = (uint8_t)nk_t; b.src_x0 = x0; b.h = (uint8_t)h;
-        b.first = first; b.commit = (uint8_t)commit; b.wait = (uint8_t)wait;
+        b.n_k16 = (uint8_t)(klen / 16); b.n_k16_t = (uint8_t)nk_t; b.src = (uint8_t)src; b.h = (uint8_t)h;
+        b.first = (uint8_t)first; b.commit = (uint8_t)commit; b.wait = (uint8_t)wait;
         sc.blk.push_back(b);
         sc.pack.push_back(PackBlk{goff, nrows, klen, n0, k0, layer});
         goff += b.bytes;
     };
+    // bias block of (layer, half): ones[128 x 16] * [bias_hi; bias_mid; bias_lo; 0...]^T starts the primal accumulator
+    auto add_bias = [&](int layer, int h, int wait) { add(layer, h * NH, NH, -1, 16, 0, 2, h, 1, 0, wait, 0); };
     // layer 0: A operand = X0 (K0p columns); the tangent only has the first KT columns
     for (int h = 0; h < 2; ++h) {
+        add_bias(0, h, h == 0 ? 3 : 0);
         for (int k0 = 0; k0 < K0p; k0 += 64) {
             const int klen = std::min(64, K0p - k0);
             const int nk_t = std::max(0, std::min(klen, sc.KT - k0)) / 16;
-            add(0, h * NH, NH, k0, klen, k0 / 8, true, h, k0 == 0, (k0 + 64 >= K0p) ? h + 1 : 0,
-                (h == 0 && k0 == 0) ? 3 : 0, nk_t);
+            add(0, h * NH, NH, k0, klen, k0 / 8, 1, h, k0 == 0 ? 2 : 0, (k0 + 64 >= K0p) ? h + 1 : 0, 0, nk_t);
         }
     }
-    // trunk layers 1..depth-1: (h0,K-lo) (h1,K-lo) (h0,K-hi) (h1,K-hi)
+    // trunk layers 1..depth-1: (h0,K-lo) (h1,K-lo) (h0,K-hi) (h1,K-hi); the K-lo half of the in-place activation
+    // buffer is dead once (h1,K-lo) has been issued, i.e. before d_full[0] can complete
     const int nkq = H / 64;
     for (int l = 1; l < depth; ++l) {
         for (int khalf = 0; khalf < 2; ++khalf) {
             for (int h = 0; h < 2; ++h) {
+                if (khalf == 0) add_bias(l, h, h == 0 ? 1 : 2);  // h0: A k-lo ready & D[h0] free; h1: D[h1] free
                 for (int kq = khalf * nkq / 2; kq < (khalf + 1) * nkq / 2; ++kq) {
-                    int wait = 0;
-                    if (khalf == 0 && kq == 0) wait = (h == 0) ? 1 : 2;  // h0: A k-lo ready & D[h0] free; h1: D[h1] free
                     const bool last = khalf == 1 && kq == nkq - 1;
-                    add(l, h * NH, NH, kq * 64, 64, kq * 8, false, h, khalf == 0 && kq == 0, last ? h + 1 : 0, wait, 4);
+                    add(l, h * NH, NH, kq * 64, 64, kq * 8, 0, h, (khalf == 0 && kq == 0) ? 2 : 0, last ? h + 1 : 0, 0, 4);
                 }
             }
         }
     }
-    // heads: N = NOp, all K
+    // heads: N = NOp, all K (bias added in the epilogue in fp32)
     for (int kq = 0; kq < nkq; ++kq) {
         int wait = kq == 0 ? 1 : (kq == nkq / 2 ? 2 : 0);
-        add(depth, 0, NOp, kq * 64, 64, kq * 8, false, 0, kq == 0, kq == nkq - 1 ? 1 : 0, wait, 4);
+        add(depth, 0, NOp, kq * 64, 64, kq * 8, 0, 0, kq == 0 ? 3 : 0, kq == nkq - 1 ? 1 : 0, wait, 4);
     }
     sc.image_bytes = goff;
     return sc;
@@ -608,9 +745,9 @@ int tc_pack(frl_net* net, const float* params_dev, cudaStream_t stream) {
     return FRL_OK;
 }
 
-template <typename T16>
+template <typename T16, int H>
 static int launch_tc(const tc::Params& p, size_t smem_bytes, int grid, cudaStream_t stream) {
-    auto kern = tc::logprob_tc_kernel<T16>;
+    auto kern = tc::logprob_tc_kernel<T16, H>;
     FRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     kern<<<grid, tc::kThreads, smem_bytes, stream>>>(p);
     FRL_CUDA(cudaGetLastError());
@@ -647,6 +784,7 @@ int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
     p.s_dim = n0->cfg.s_dim; p.a_dim = n0->cfg.a_dim; p.d_in = n0->d_in; p.K0p = n0->d_in_p; p.KT = sc.KT;
     p.NOp = n0->n_out_p; p.H = H;
     p.n_steps = a.n_steps;
+    if (const char* dbg = getenv("FRL_TC_DEBUG")) p.debug = atoi(dbg);
     p.delta = (float)(1.0 / a.n_steps);
     for (int k = 0; k < a.n_steps; ++k) p.t_mid[k] = a.t_mid_host[k];
     p.probe_step_stride = a.probe_mode == FRL_PROBE_PER_STEP ? a.B * (long long)p.a_dim : 0;
@@ -658,9 +796,11 @@ int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
     p.off_a = off; off += 2u * H * kRows * 2;
     p.off_x0p = off; off += (uint32_t)p.K0p * kRows * 2;
     p.off_x0t = off; off += (uint32_t)p.KT * kRows * 2;
+    p.off_ones = off; off += 2u * kRows * 16;
     p.off_bias = off; off += (uint32_t)(a.n_roles * nb) * 4;
     off = (off + 15) / 16 * 16;
     p.off_state = off; off += 2u * p.a_dim * kRows * 4;
+    p.off_rec = off; off += 2u * (uint32_t)p.n_blocks * 16;
     off = (off + 1023) / 1024 * 1024;
     p.off_ring = off;
     int max_smem = 0;
@@ -680,8 +820,33 @@ int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
     const int grid = (int)std::min<long long>(n_tiles, sms);
 
     auto run = [&](const Params& q) {
-        return f16 ? launch_tc<__half>(q, smem_bytes, grid, stream) : launch_tc<__nv_bfloat16>(q, smem_bytes, grid, stream);
+        if (H == 256)
+            return f16 ? launch_tc<__half, 256>(q, smem_bytes, grid, stream)
+                       : launch_tc<__nv_bfloat16, 256>(q, smem_bytes, grid, stream);
+        return f16 ? launch_tc<__half, 128>(q, smem_bytes, grid, stream)
+                   : launch_tc<__nv_bfloat16, 128>(q, smem_bytes, grid, stream);
     };
+    if (const char* tp = getenv("FRL_TC_TRACE")) {
+        // timing experiment: stamp CTA 0's roles with clock64 and dump them (synchronises!)
+        unsigned long long* d = nullptr;
+        FRL_CUDA(cudaMalloc(&d, 4 * 8192 * sizeof(unsigned long long)));
+        FRL_CUDA(cudaMemset(d, 0, 4 * 8192 * sizeof(unsigned long long)));
+        p.trace = d;
+        p.basis = -1;
+        int rc = run(p);
+        if (rc != FRL_OK) return rc;
+        FRL_CUDA(cudaDeviceSynchronize());
+        std::vector<unsigned long long> h(4 * 8192);
+        FRL_CUDA(cudaMemcpy(h.data(), d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        if (FILE* f = fopen(tp, "w")) {
+            for (int r = 0; r < 4; ++r)
+                for (int i = 0; i < 8192 && h[(size_t)r * 8192 + i]; ++i)
+                    fprintf(f, "%d %llx %llu\n", r, h[(size_t)r * 8192 + i] >> 48, h[(size_t)r * 8192 + i] & 0xFFFFFFFFFFFFull);
+            fclose(f);
+        }
+        return FRL_OK;
+    }
     if (a.probe_mode == FRL_PROBE_EXACT) {
         for (int i = 0; i < p.a_dim; ++i) {
             p.basis = i;

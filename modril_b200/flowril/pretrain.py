@@ -120,6 +120,45 @@ def score_pair(net_e, net_a, s, a, probe=None, exact=False, n_steps=32, reward_t
     return le, la, rw
 
 
+def score_pair_host(net_e, net_a, s, a, probe=None, exact=False, n_steps=32, reward_type="raw", precision=None,
+                    out=None):
+    """End-to-end scoring of HOST tensors (``frl_score_host``): the library stages the batch through the device in
+    chunks (H2D, fused integrator, D2H overlapped on its own streams) and returns CPU tensors
+    (logp_E, logp_A, reward).  Pinned inputs/outputs (``tensor.pin_memory()``) make the copies asynchronous.
+    ``out``: optional tuple of three preallocated CPU float32 tensors [B]."""
+    dev = net_e.flat_params().device
+    torch.cuda.current_stream(dev).synchronize()  # pending weight packs run on the caller's stream
+    he, ha = net_e.native(), net_a.native()
+    torch.cuda.current_stream(dev).synchronize()
+
+    def host(x, what):
+        if x.device.type != "cpu":
+            raise RuntimeError(f"{what} must be a CPU tensor for the host entry point")
+        return x.detach().float().contiguous()
+
+    s, a = host(s, "s"), host(a, "a")
+    B = a.shape[0]
+    if a.shape != (B, net_e.a_dim) or s.shape != (B, net_e.s_dim):
+        raise ValueError(f"expected s [B,{net_e.s_dim}], a [B,{net_e.a_dim}]; got {tuple(s.shape)}, {tuple(a.shape)}")
+    if reward_type not in _native.REWARD_TYPES:
+        raise ValueError(f"Unrecognized reward type {reward_type}")
+    if exact:
+        probe, mode = None, _native.PROBE_EXACT
+    else:
+        probe = host(probe, "probe")
+        if probe.shape == (B, net_e.a_dim):
+            mode = _native.PROBE_SHARED
+        elif probe.shape == (n_steps, B, net_e.a_dim):
+            mode = _native.PROBE_PER_STEP
+        else:
+            raise ValueError(f"bad probe shape {tuple(probe.shape)}")
+    le, la, rw = out if out is not None else (torch.empty(B) for _ in range(3))
+    _native.check(_native.lib().frl_score_host(he, ha, _ptr(s), _ptr(a), _ptr(probe), mode, _t_mid(n_steps), n_steps,
+                                               _native.REWARD_TYPES[reward_type], _ptr(le), _ptr(la), _ptr(rw), B,
+                                               _precision_code(precision)), "frl_score_host")
+    return le, la, rw
+
+
 class _FMLoss(torch.autograd.Function):
     """loss = frl_cfm_loss_grad(...): the fused kernel produces the loss AND dL/dtheta in forward; backward hands
     the stored gradient (scaled by grad_output) to autograd so that ``loss.backward()`` fills ``p.grad``."""

@@ -1,0 +1,137 @@
+"""Host-side logic that needs no GPU: drop-in surface (state_dict keys, flat views, freezing), oracle helpers vs torch,
+and the torch-CPU port (bench baseline) vs the numpy oracle."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as cf
+from oracle import synth, torch_port
+
+
+def test_state_dict_keys_match_reference_layout():
+    from modril_b200.flowril import CoupledResidualFM, FlowMatching
+    m = CoupledResidualFM(11, 3, 256)
+    spec = cf.NetSpec(11, 3, 256, 4, 2)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == spec.shapes()
+    m2 = FlowMatching(6, 2, 128, depth=3)
+    spec2 = cf.NetSpec(6, 2, 128, 3, 1)
+    assert [(k, tuple(v.shape)) for k, v in m2.state_dict().items()] == spec2.shapes()
+    assert m.net.flat_params().numel() == spec.n_params()
+
+
+def test_parameters_are_views_of_one_flat_buffer_and_survive_load_and_copy():
+    from modril_b200.flowril import CoupledResidualFM
+    m = CoupledResidualFM(6, 2, 128)
+    flat = m.net.flat_params()
+    off = 0
+    for p in m.parameters():
+        assert p.data_ptr() == flat.data_ptr() + 4 * off
+        off += p.numel()
+    spec = cf.NetSpec(6, 2, 128, 4, 2)
+    new = cf.make_params(spec, 3, 1.0)
+    m.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in cf.unpack(spec, new).items()})
+    assert np.array_equal(m.net.flat_params().numpy(), new)
+    m2 = copy.deepcopy(m)
+    assert np.array_equal(m2.net.flat_params().numpy(), new)
+    assert m2.net.flat_params().data_ptr() != m.net.flat_params().data_ptr()
+    with torch.no_grad():
+        m.net.head_r.weight.mul_(2.0)   # in-place edits through the Parameter are edits of the flat buffer
+    assert np.allclose(m.net.flat_params().numpy()[-(2 * 128 + 2):-2], 2 * new[-(2 * 128 + 2):-2])
+
+
+def test_cpu_tensors_raise_no_fallback():
+    from modril_b200.flowril import CoupledResidualFM
+    m = CoupledResidualFM(6, 2, 128)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.log_prob(torch.zeros(4, 6), torch.zeros(4, 2), "expert")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.fm_loss(torch.zeros(4, 6), torch.zeros(4, 2), "expert")
+
+
+def test_fused_adam_state_dict_layout_and_freezing():
+    from modril_b200.flowril import CoupledResidualFM, FusedAdam
+    m = CoupledResidualFM(6, 2, 128)
+    for p in m.net.shared.parameters():      # reference flowril.py:52-58
+        p.requires_grad = False
+    for p in m.net.head_c.parameters():
+        p.requires_grad = False
+    opt = FusedAdam([m.net], lr=1e-3)
+    sd = opt.state_dict()
+    assert len(sd["param_groups"][0]["params"]) == 2          # head_r.weight, head_r.bias
+    ref = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-3)
+    assert set(sd["param_groups"][0].keys()) >= {"lr", "betas", "eps", "weight_decay", "amsgrad"}
+    assert sd["param_groups"][0]["betas"] == ref.state_dict()["param_groups"][0]["betas"]
+    arr, n = opt._segments([m.net.flat_grad()])
+    assert n == 1 and arr[0].n == 2 * 128 + 2                  # one contiguous trainable run at the tail
+
+
+def test_oracle_linspace_matches_torch():
+    for n in (1, 2, 7, 20, 32, 33, 100, 256):
+        g = torch.linspace(0.0, 1.0, n + 1)
+        assert np.array_equal(cf.torch_linspace_f32(n), g.numpy()), n
+        tm = (0.5 * (g[:-1] + g[1:])).numpy()
+        assert np.array_equal(cf.t_mid_grid(n), tm), n
+
+
+def test_t_mid_binding_matches_oracle():
+    from modril_b200.flowril.pretrain import _t_mid
+    for n in (20, 32):
+        assert np.array_equal(np.array(list(_t_mid(n)), np.float32), cf.t_mid_grid(n))
+
+
+def test_reward_transform_matches_torch_formulas():
+    r = torch.linspace(-30, 30, 121)
+    s = torch.sigmoid(r)
+    ref = {"raw": r, "norm": (s + 1e-20).log() - (1 - s + 1e-20).log(), "exp": -torch.exp(r) / (1 + torch.exp(r)),
+           "clip": torch.clamp(r, -20.0, 20.0), "smooth": -torch.log1p(torch.exp(-r))}   # reference flowril.py:195-205
+    for k, v in ref.items():
+        got = cf.reward_transform(r.numpy(), k)
+        assert np.allclose(got, v.numpy(), rtol=2e-6, atol=1e-6, equal_nan=True), k
+    with pytest.raises(ValueError):
+        cf.reward_transform(r.numpy(), "bogus")
+
+
+def test_torch_port_matches_numpy_oracle():
+    spec = cf.NetSpec(11, 3, 128, 4, 2)
+    flat = cf.make_params(spec, 4, 2.0)
+    B, n = 64, 8
+    s, a = synth.states_actions(1, B, 11, 3)
+    probe = synth.rademacher(2, (B, 3))
+    ft = torch.from_numpy(flat)
+    le, la, rw = torch_port.score(spec, ft, ft, torch.from_numpy(s), torch.from_numpy(a), torch.from_numpy(probe), n)
+    for role, got in (("expert", le), ("agent", la)):
+        ref = cf.log_prob(spec, flat, s, a, role, probe, n)
+        assert np.abs(got.numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+    t, noise = synth.cfm_draws(3, B, 3)
+    loss = torch_port.fm_loss(spec, ft.clone().requires_grad_(True), torch.from_numpy(s), torch.from_numpy(a), "agent",
+                              torch.from_numpy(t), torch.from_numpy(noise))
+    ref_loss, _ = cf.fm_loss_and_grad(spec, flat, s, a, "agent", t, noise)
+    assert abs(float(loss) - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+
+
+def test_oracle_training_curve_vs_reference_golden(golden_dir):
+    """The numpy oracle's hand-written backward + clip + Adam reproduces the reference's 50-step fine-tune run."""
+    import os
+    g = np.load(os.path.join(golden_dir, "train_01_hopper_scrf_ft_h128_50steps.npz"))
+    s_dim, a_dim, hidden, depth, n_heads, steps, B, seed = (int(x) for x in g["meta"])
+    spec = cf.NetSpec(s_dim, a_dim, hidden, depth, n_heads)
+    flat = cf.make_params(spec, seed, 1.0).astype(np.float64)
+    trainable = np.zeros(flat.size, bool)
+    n_frozen = sum(int(np.prod(sh)) for name, sh in spec.shapes() if "head_r" not in name)
+    trainable[n_frozen:] = True
+    m, v = np.zeros_like(flat), np.zeros_like(flat)
+    pool_s, _ = synth.states_actions(seed + 1, 4096, s_dim, a_dim)
+    pool_aE = synth.expert_actions(seed + 2, pool_s, a_dim)
+    pool_aA = np.clip(synth.rng(seed + 3).standard_normal((4096, a_dim)), -1, 1).astype(np.float32)
+    for it in range(20):
+        r = synth.rng(seed + 100 + it)
+        iE, iA = r.integers(0, 4096, B), r.integers(0, 4096, B)
+        tE, nE = synth.cfm_draws(seed + 10000 + 2 * it, B, a_dim)
+        tA, nA = synth.cfm_draws(seed + 10001 + 2 * it, B, a_dim)
+        flat, m, v, losses, norm = cf.train_step(
+            spec, flat, m, v, it + 1,
+            [("expert", pool_s[iE], pool_aE[iE], tE, nE), ("agent", pool_s[iA], pool_aA[iA], tA, nA)],
+            lr=float(g["lr"]), max_norm=1.0, trainable=trainable)
+        assert np.allclose(losses, g["curve"][it], rtol=2e-4), (it, losses, g["curve"][it])
