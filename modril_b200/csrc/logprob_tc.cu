@@ -280,21 +280,31 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
         const uint32_t one = Cvt<T16>::one(1.f);
         reinterpret_cast<uint4*>(sOnes)[i] = i < kRows ? make_uint4(one | (one << 16), one, 0, 0) : make_uint4(0, 0, 0, 0);
     }
-    // per-block issue records for the two MMA warps (one 16-byte shared-memory load per block in the hot loop)
-    uint4* sRec = reinterpret_cast<uint4*>(smem + p.off_rec);  // [2 tiles][n_blocks]
+    // per-block issue records for the two MMA warps (two 16-byte shared-memory loads per block in the hot loop).
+    // Work split: MMA warp j owns accumulator half h == j of the trunk / layer-0 / bias blocks and issues BOTH tiles
+    // there; in the heads blocks warp 0 issues the primal tile and warp 1 the tangent tile.  (One thread pays ~60
+    // cycles per tcgen05.mma and ~230 per tcgen05.commit -- tests/umma_bench.cu -- so a single issuer is slower
+    // than the tensor pipe at N = 128; two issuers working on different accumulators are not.)
+    uint4* sRec = reinterpret_cast<uint4*>(smem + p.off_rec);  // [2 warps][n_blocks][2]
     for (int i = threadIdx.x; i < 2 * p.n_blocks; i += kThreads) {
-        const int x = i / p.n_blocks, b = i % p.n_blocks;
+        const int j = i / p.n_blocks, b = i % p.n_blocks;
         const Blk& k = p.blk[b];
-        const uint32_t src = k.src == 0 ? smem_u32(smem + p.off_a) + x * a_tile_bytes
-                             : (k.src == 1 ? smem_u32(x == 0 ? sX0p : sX0t) : smem_u32(sOnes));
-        const uint32_t a_lo = (((src + (uint32_t)k.a_koff * (kRows * 16)) >> 4) & 0x3FFF) | ((uint32_t)(kRows * 16 >> 4) << 16);
+        const bool heads = k.nrows != NH;  // only the heads blocks have N != H/2 (NOp <= 64 < H/2)
+        uint32_t a_lo[2] = {0, 0}, dcol[2] = {0, 0}, nk[2] = {0, 0}, first[2] = {0, 0};
+        for (int x = 0; x < 2; ++x) {
+            const bool mine = heads ? (x == j) : (k.h == j);
+            if (!mine) continue;
+            const uint32_t src = k.src == 0 ? smem_u32(smem + p.off_a) + x * a_tile_bytes
+                                 : (k.src == 1 ? smem_u32(x == 0 ? sX0p : sX0t) : smem_u32(sOnes));
+            a_lo[x] = (((src + (uint32_t)k.a_koff * (kRows * 16)) >> 4) & 0x3FFF) | ((uint32_t)(kRows * 16 >> 4) << 16);
+            dcol[x] = (uint32_t)k.h * 256 + (uint32_t)x * 128;
+            nk[x] = x == 0 ? k.n_k16 : k.n_k16_t;
+            first[x] = (k.first >> x) & 1;
+        }
         const uint32_t idesc = (1u << 4) | (Cvt<T16>::kFmt << 7) | (Cvt<T16>::kFmt << 10) | ((uint32_t)(kRows >> 4) << 24) |
                                ((uint32_t)(k.nrows >> 3) << 17);
-        const uint32_t nk = x == 0 ? k.n_k16 : k.n_k16_t;
-        const uint32_t first = (k.first >> x) & 1;
-        // .z: nrows (B k-chunk stride in 16-byte units) | d column offset << 16 ; .w: nk | first<<8 | commit<<16 | wait<<24
-        sRec[i] = make_uint4(a_lo, idesc, (uint32_t)k.nrows | (((uint32_t)k.h * 256 + (uint32_t)x * 128) << 16),
-                             nk | (first << 8) | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24));
+        sRec[2 * i] = make_uint4(a_lo[0], a_lo[1], idesc, (uint32_t)k.nrows | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24));
+        sRec[2 * i + 1] = make_uint4(dcol[0], dcol[1], nk[0] | (first[0] << 8) | (nk[1] << 16) | (first[1] << 24), 0);
     }
     fence_async_smem();
     tc_fence_before();
@@ -330,48 +340,57 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
             }
         }
     } else if (warp == 1 || warp == 2) {
-        // ------------------------------ MMA issuers: warp 1 = primal tile, warp 2 = tangent tile ------------------
-        // (two issuing threads: descriptor building + tcgen05.mma/commit issue of ONE thread is slower than the
-        //  tensor pipe at N=128; the tiles write different accumulators, so they need no mutual ordering)
+        // ------------------------------ MMA issuers (see the record table above for the work split) ----------------
         if (lane == 0) {
-            const int x = warp - 1;
+            const int j = warp - 1;
             int stage = 0;
             uint32_t phase = 0, par_a0 = 0, par_a1 = 0;
-            const uint4* rec = sRec + x * p.n_blocks;
+            const uint4* rec = sRec + (size_t)j * p.n_blocks * 2;
             const uint32_t ring_lo = (smem_u32(sRing) >> 4);
             constexpr uint32_t kDescHi = (uint32_t)(128 >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
-            Tracer tr; tr.init(p.trace, 1 + x);
+            Tracer tr; tr.init(p.trace, 1 + j);
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int step = 0; step < p.n_steps; ++step) {
                     for (int b = 0; b < p.n_blocks; ++b) {
-                        const uint4 r = rec[b];
+                        const uint4 r0 = rec[2 * b], r1 = rec[2 * b + 1];
                         tr.mark(0x100 + b);
-                        if (r.w & (1u << 24)) { mbar_wait(a_ready(0), par_a0); par_a0 ^= 1; }
-                        if (r.w & (2u << 24)) { mbar_wait(a_ready(1), par_a1); par_a1 ^= 1; }
+                        if (r0.w & (1u << 24)) { mbar_wait(a_ready(0), par_a0); par_a0 ^= 1; }
+                        if (r0.w & (2u << 24)) { mbar_wait(a_ready(1), par_a1); par_a1 ^= 1; }
+                        const uint32_t nk0 = (p.debug & 2) ? 0 : (r1.z & 0xFF), nk1 = (p.debug & 2) ? 0 : ((r1.z >> 16) & 0xFF);
+                        const uint32_t cm = (r0.w >> 16) & 0xFF;
+                        // every issuer observes every fill of the ring (a warp that ran ahead through blocks it does
+                        // not own could otherwise arrive twice on one w_empty phase and release a stage too early)
                         mbar_wait(w_full(stage), phase);
-                        tc_fence_after();
-                        tr.mark(0x300 + b);
-                        const uint32_t nk = (p.debug & 2) ? 0 : (r.w & 0xFF);
-                        if (nk) {
-                            const uint32_t nrows = r.z & 0xFFFF;
-                            const uint32_t d = tmem + (r.z >> 16);
-                            uint32_t a_lo = r.x;
-                            uint32_t b_lo = ((ring_lo + (uint32_t)stage * (kStageBytes >> 4)) & 0x3FFF) | (nrows << 16);
-                            uint32_t acc = ((r.w >> 8) & 1) ? 0u : 1u;
-                            for (uint32_t u = 0; u < nk; ++u) {
-                                const uint64_t da = ((uint64_t)kDescHi << 32) | a_lo;
-                                const uint64_t db = ((uint64_t)kDescHi << 32) | b_lo;
-                                umma(d, da, db, r.y, acc);
-                                acc = 1u;
-                                a_lo += 2 * (kRows * 16 >> 4);   // two k-chunks of 8 per K=16 MMA
-                                b_lo += 2 * nrows;
+                        if (nk0 | nk1) {
+                            tc_fence_after();
+                            tr.mark(0x300 + b);
+                            const uint32_t nrows = r0.w & 0xFFFF;
+                            const uint32_t b_lo0 = ((ring_lo + (uint32_t)stage * (kStageBytes >> 4)) & 0x3FFF) | (nrows << 16);
+                            {
+                                uint32_t a_lo = r0.x, b_lo = b_lo0, acc = ((r1.z >> 8) & 1) ? 0u : 1u;
+                                for (uint32_t u = 0; u < nk0; ++u) {
+                                    umma(tmem + r1.x, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, r0.z, acc);
+                                    acc = 1u;
+                                    a_lo += 2 * (kRows * 16 >> 4);   // two k-chunks of 8 per K=16 MMA
+                                    b_lo += 2 * nrows;
+                                }
+                            }
+                            {
+                                uint32_t a_lo = r0.y, b_lo = b_lo0, acc = ((r1.z >> 24) & 1) ? 0u : 1u;
+                                for (uint32_t u = 0; u < nk1; ++u) {
+                                    umma(tmem + r1.y, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, r0.z, acc);
+                                    acc = 1u;
+                                    a_lo += 2 * (kRows * 16 >> 4);
+                                    b_lo += 2 * nrows;
+                                }
                             }
                             umma_commit(w_empty(stage));
+                            if (cm) umma_commit(d_full(cm - 1));
                         } else {
-                            mbar_arrive(w_empty(stage));  // nothing issued by this warp for the block
+                            // not this warp's block: release the stage / accumulator slot without touching the pipe
+                            mbar_arrive(w_empty(stage));
+                            if (cm) mbar_arrive(d_full(cm - 1));
                         }
-                        const uint32_t cm = (r.w >> 16) & 0xFF;
-                        if (cm) umma_commit(d_full(cm - 1));
                         tr.mark(0x400 + b);
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
@@ -800,7 +819,7 @@ int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
     p.off_bias = off; off += (uint32_t)(a.n_roles * nb) * 4;
     off = (off + 15) / 16 * 16;
     p.off_state = off; off += 2u * p.a_dim * kRows * 4;
-    p.off_rec = off; off += 2u * (uint32_t)p.n_blocks * 16;
+    p.off_rec = off; off += 4u * (uint32_t)p.n_blocks * 16;
     off = (off + 1023) / 1024 * 1024;
     p.off_ring = off;
     int max_smem = 0;
