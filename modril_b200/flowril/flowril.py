@@ -1,0 +1,435 @@
+"""The FLOWRIL reward module (plugin for the rl-toolkit PPO updater) on the B200 kernels.
+
+Mirror of the reference's ``modril/flowril/flowril.py`` as far as its hooks touch the hot path (SURVEY.md section 8:
+rows a7-a12): same class names (``FLOWRIL``, ``FlowMatchingEstimation``), hook names (``init``,
+``_create_flow_net``, ``_update_reward_func``, ``_get_reward``, ``_compute_flow_reward``, ``_compute_flow_loss``,
+``_compute_disc_val``, ``get_add_args``, ``save`` / ``load_resume``), CLI flags / YAML keys (flowril.py:545-579) and
+checkpoint keys (``flow_<option>``, ``flow_<option>_opt``; flowril.py:581-597).  Plotting / animation code
+(flowril.py:367-543) is out of scope.
+
+When rl-toolkit (``rlf``) is importable the classes derive from its ``BaseIRLAlgo`` / ``NestedAlgo`` and plug into
+``deps/baselines/main.py --alg flowril`` unchanged.  rl-toolkit needs gym + mujoco at import time, so for the tests
+and for stand-alone use a minimal stand-in base class reproduces the part of ``BaseIRLAlgo.update``
+(deps/rl-toolkit/rlf/algos/il/base_irl.py:37-72) that drives the hooks.
+
+Differences in mechanism, not in results:
+  * ``_get_reward(step, ...)`` is served from ONE fused launch over the whole rollout (T*N rows, both roles) made at
+    the first step of an update; the log-density is a pure function of (s, a, weights, probe) and the weights do not
+    change between the steps of one update, so the rows are bit-identical to per-step scoring.  Only the return
+    normalisation stays a sequential scan (flowril.py:221-228).
+  * ``_update_reward_func`` runs the all-native route (fused CFM gradient kernels + clip+Adam kernel) on the flat
+    parameter buffer.
+  * Reference quirk kept on purpose: ``_update_reward_func`` passes
+    ``(expert_batch, agent_batch)`` to ``_compute_flow_loss(agent_batch, expert_batch, ...)`` (flowril.py:314 vs :232),
+    so role "expert" is trained on the ROLLOUT batch and role "agent" on the DEMONSTRATION batch.
+  * The anti-divergence / Jacobian-stability regularisers and GradNorm2D (flowril.py:255-290) are row f1 of the
+    scope table and are not implemented yet: the module raises if they are enabled
+    (``--enable-loss-anti false --enable-loss-stable false``, i.e. configs/sine/flowril-no-as.yaml, or option 2fs).
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from .pretrain import CoupledResidualFM, FlowMatching, FusedAdam, _rademacher, score_pair, train_step
+
+try:  # the real plugin API, when rl-toolkit and its simulators are installed
+    import rlf.rl.utils as rutils
+    from rlf.algos.il.base_irl import BaseIRLAlgo
+    from rlf.algos.nested_algo import NestedAlgo
+    from rlf.algos.on_policy.ppo import PPO
+    from rlf.baselines.common.running_mean_std import RunningMeanStd
+
+    HAVE_RLF = True
+except Exception:  # pragma: no cover - exercised in this repo's tests
+    HAVE_RLF = False
+
+    class RunningMeanStd(object):
+        """float32 running moments (rlf/baselines/common/running_mean_std.py:3-35)."""
+
+        def __init__(self, epsilon=1e-4, shape=()):
+            self.mean = np.zeros(shape, "float32")
+            self.var = np.ones(shape, "float32")
+            self.count = epsilon
+
+        def update(self, x):
+            bm = np.mean(x, axis=0, dtype="float32")
+            bv = np.var(x, axis=0, dtype="float32")
+            n = x.shape[0]
+            delta = bm - self.mean
+            tot = self.count + n
+            m2 = self.var * self.count + bv * n + np.square(delta, dtype="float32") * self.count * n / tot
+            self.mean, self.var, self.count = self.mean + delta * n / tot, m2 / tot, tot
+
+    class _Utils:
+        @staticmethod
+        def get_obs_shape(space):
+            return tuple(space.shape)
+
+        @staticmethod
+        def get_ac_dim(space):
+            return int(space.shape[0])
+
+        @staticmethod
+        def get_ac_repr(space, action):
+            return action  # identity for Box spaces (rlf/rl/utils.py:392-404)
+
+        @staticmethod
+        def get_def_obs(obs):
+            return obs["observation"] if isinstance(obs, dict) and "observation" in obs else obs
+
+    rutils = _Utils()
+
+    class BaseIRLAlgo(object):
+        """The slice of rl-toolkit's BaseIRLAlgo / BaseILAlgo this module relies on
+        (base_irl.py:37-72, base_il.py:63-104): expert loader + the update loop that calls the two hooks."""
+
+        def __init__(self):
+            self.expert_train_loader = None
+
+        def init(self, policy, args):
+            self.policy, self.args = policy, args
+            loader = getattr(args, "expert_loader", None)
+            if loader is None and getattr(args, "expert_dataset", None) is not None:
+                ds = args.expert_dataset
+                n = ds["obs"].shape[0]
+
+                class _DS(torch.utils.data.Dataset):
+                    def __len__(self):
+                        return n
+
+                    def __getitem__(self, i):
+                        return {"state": ds["obs"][i], "actions": ds["actions"][i]}
+
+                loader = torch.utils.data.DataLoader(_DS(), batch_size=args.traj_batch_size, shuffle=True, drop_last=True)
+            self.expert_train_loader = loader
+
+        def get_env_ob_filt(self):
+            return None
+
+        def get_env_settings(self, args):
+            return type("Settings", (), {})()
+
+        def get_add_args(self, parser):
+            pass
+
+        def _adjust_action(self, x):
+            return x
+
+        def update(self, storage, gradient_clip=False, t=1):
+            for step in range(self.args.num_steps):
+                storage.rewards[step] = 0
+            log_vals = self._update_reward_func(storage)
+            for step in range(self.args.num_steps):
+                rewards, _ = self._get_reward(step, storage, {})
+                storage.rewards[step] = rewards
+            return log_vals
+
+        def save(self, checkpointer):
+            pass
+
+        def load_resume(self, checkpointer):
+            pass
+
+    NestedAlgo = None
+    PPO = None
+
+
+def str2bool(v):
+    return v.lower() == "true"
+
+
+class FlowMatchingEstimation(BaseIRLAlgo):
+    def __init__(self):
+        super().__init__()
+        self.step = 0
+        self._rollout_cache = None
+
+    # ---- construction (reference flowril.py:34-121) -------------------------------------------------------------
+    def _create_flow_net(self):
+        ob_shape = rutils.get_obs_shape(self.policy.obs_space)
+        self.state_dim = ob_shape[0]
+        self.action_dim = rutils.get_ac_dim(self.action_space)
+        dev = self.args.device
+        lr = self.args.disc_lr
+        if self.args.option == "scrf":
+            # NB: like the reference (flowril.py:42-46) scrf does not pass --flow-depth (class default 4)
+            self.flow_net = CoupledResidualFM(state_dim=self.state_dim, action_dim=self.action_dim,
+                                              hidden_dim=self.args.hidden_dim).to(dev)
+            if self.args.flow_path:
+                self.flow_net.load_state_dict(torch.load(self.args.flow_path, map_location=dev))
+                for p in self.flow_net.net.shared.parameters():   # freeze the common field, train the residual
+                    p.requires_grad = False
+                for p in self.flow_net.net.head_c.parameters():
+                    p.requires_grad = False
+                for p in self.flow_net.net.head_r.parameters():
+                    p.requires_grad = True
+            self.opt = FusedAdam([self.flow_net.net], lr=lr)
+            self.params = list(self.flow_net.parameters())
+            if not self.args.enable_loss_anti:
+                self.args.loss_anti = 0
+            if not self.args.enable_loss_stable:
+                self.args.loss_stable = 0
+            if self.args.loss_anti > 0 or self.args.loss_stable > 0:
+                raise NotImplementedError(
+                    "the anti-divergence / Jacobian-stability regularisers and GradNorm2D (reference "
+                    "flowril.py:255-290) are not implemented on the B200 path yet; run with "
+                    "--enable-loss-anti false --enable-loss-stable false or --option 2fs")
+        else:
+            mk = lambda: FlowMatching(state_dim=self.state_dim, action_dim=self.action_dim,
+                                      hidden_dim=self.args.hidden_dim, depth=self.args.flow_depth).to(dev)
+            self.flow_net_e, self.flow_net_a = mk(), mk()
+            if self.args.flow_path and not self.args.finetune_ve:
+                self.flow_net_e.load_state_dict(torch.load(self.args.flow_path, map_location=dev))
+                for p in self.flow_net_e.parameters():
+                    p.requires_grad = False
+                self.opt = FusedAdam([self.flow_net_a.net], lr=lr)
+            else:
+                self.opt = FusedAdam([self.flow_net_e.net, self.flow_net_a.net], lr=lr)
+
+    def init(self, policy, args):
+        super().init(policy, args)
+        self.policy = policy
+        self.args = args
+        self.action_space = self.policy.action_space
+        self._create_flow_net()
+        self.returns = None
+        self.ret_rms = RunningMeanStd(shape=())
+        self.eps = 1e-8
+        self.global_scale = 1e-3
+        self.precision = getattr(args, "flowril_precision", None)
+
+    def _get_sampler(self, storage):
+        agent_experience = storage.get_generator(None, mini_batch_size=self.expert_train_loader.batch_size)
+        return self.expert_train_loader, agent_experience
+
+    def _trans_batches(self, expert_batch, agent_batch):
+        return expert_batch, agent_batch
+
+    def get_env_settings(self, args):
+        settings = super().get_env_settings(args)
+        if not args.flowril_state_norm:
+            settings.ret_raw_obs = True
+        return settings
+
+    def _norm_expert_state(self, state, obsfilt):
+        if not self.args.flowril_state_norm:
+            return state
+        state = state.cpu().numpy()
+        if obsfilt is not None:
+            state = obsfilt(state, update=False)
+        return torch.tensor(state).to(self.args.device)
+
+    def _trans_agent_state(self, state, other_state=None):
+        if not self.args.flowril_state_norm:
+            if isinstance(state, dict):
+                return state["raw_obs"] if other_state is None else other_state["raw_obs"]
+            return state
+        return rutils.get_def_obs(state)
+
+    # ---- scoring (reference flowril.py:175-230, :352-365) ---------------------------------------------------------
+    def _nets(self):
+        if self.args.option == "scrf":
+            return self.flow_net.net, self.flow_net.net
+        return self.flow_net_e.net, self.flow_net_a.net
+
+    def _probe(self, n_rows, n_steps=32):
+        """The probes the reference would draw for a batch of n_rows (scrf: shape-deterministic `_rademacher`,
+        pretrain.py:51-52; 2fs: global-RNG `randint_like` per step and per net, pretrain.py:90 -- expert net first)."""
+        dev = self.args.device
+        if self.args.option == "scrf":
+            return _rademacher((n_rows, self.action_dim), device=dev)
+        like = torch.empty(n_rows, self.action_dim, device=dev)
+        return torch.stack([torch.randint_like(like, 0, 2).float().mul_(2).sub_(1) for _ in range(n_steps)])
+
+    def _score(self, state, action, reward_type):
+        ne, na = self._nets()
+        if self.args.option == "scrf":
+            probe = self._probe(state.shape[0])
+            return score_pair(ne, na, state, action, probe, n_steps=32, reward_type=reward_type,
+                              precision=self.precision)
+        # 2fs: each net draws its own per-step probes from the global RNG, expert first (flowril.py:187-189)
+        x = torch.cat([state, action], dim=-1)
+        le = self.flow_net_e.log_prob(x, precision=self.precision)
+        la = self.flow_net_a.log_prob(x, precision=self.precision)
+        return le, la, None
+
+    def _reward_from(self, le, la, rw):
+        if rw is not None:
+            return rw.unsqueeze(-1)
+        r = (le - la).unsqueeze(-1)
+        s = torch.sigmoid(r)
+        eps = 1e-20
+        rt = self.args.reward_type
+        if rt == "norm":
+            return (s + eps).log() - (1 - s + eps).log()
+        if rt == "exp":
+            e = torch.exp(r)
+            return -e / (1 + e)
+        if rt == "raw":
+            return r
+        if rt == "clip":
+            return torch.clamp(r, min=-20.0, max=20.0)
+        if rt == "smooth":
+            return -torch.log1p(torch.exp(-r))
+        raise ValueError(f"Unrecognized reward type {rt}")
+
+    def _compute_flow_reward(self, storage, step, add_info):
+        if self.args.reward_type not in ("raw", "norm", "exp", "clip", "smooth"):
+            raise ValueError(f"Unrecognized reward type {self.args.reward_type}")
+        batched = getattr(self.args, "flowril_batched_scoring", True) and self.args.option == "scrf"
+        if not batched:
+            state = self._trans_agent_state(storage.get_obs(step)).to(self.args.device)
+            action = rutils.get_ac_repr(self.action_space, storage.actions[step].to(self.args.device))
+            return self._reward_from(*self._score(state, action, self.args.reward_type))
+        if step == 0 or self._rollout_cache is None:
+            T = self.args.num_steps
+            states = torch.stack([self._trans_agent_state(storage.get_obs(t)).to(self.args.device) for t in range(T)])
+            actions = torch.stack([rutils.get_ac_repr(self.action_space, storage.actions[t].to(self.args.device))
+                                   for t in range(T)])
+            N = states.shape[1]
+            ne, na = self._nets()
+            probe = self._probe(N).repeat(T, 1)  # the same [N, a] probe at every rollout step, like the reference
+            le, la, rw = score_pair(ne, na, states.reshape(T * N, -1), actions.reshape(T * N, -1), probe, n_steps=32,
+                                    reward_type=self.args.reward_type, precision=self.precision)
+            self._rollout_cache = rw.reshape(T, N, 1)
+        return self._rollout_cache[step]
+
+    def _get_reward(self, step, storage, add_info):
+        masks = storage.masks[step]
+        with torch.no_grad():
+            for m in ((self.flow_net,) if self.args.option == "scrf" else (self.flow_net_e, self.flow_net_a)):
+                m.eval()
+            reward = self._compute_flow_reward(storage, step, add_info)
+            if self.args.flowril_reward_norm:
+                if self.returns is None:
+                    self.returns = reward.clone()
+                self.returns = self.returns * masks * self.args.gamma + reward
+                self.ret_rms.update(self.returns.cpu().numpy())
+                return reward / np.sqrt(self.ret_rms.var[0] + 1e-8), {}
+            return reward, {}
+
+    def _compute_disc_val(self, state, action):
+        state, action = state.to(self.args.device), action.to(self.args.device)
+        le, la, _ = self._score(state, action, "raw")
+        return (le - la).detach()
+
+    # ---- training (reference flowril.py:232-350) ---------------------------------------------------------------------
+    def _compute_flow_loss(self, agent_batch, expert_batch, obsfilt):
+        """Builds the two (s, a) batches exactly like the reference (incl. its argument-order quirk, see the module
+        docstring) and returns the CFM terms for ``train_step``: [(net, sign, s, a0, rate), ...]."""
+        expert_states = self._norm_expert_state(expert_batch["state"], obsfilt)
+        expert_actions = self._adjust_action(expert_batch["action"].to(self.args.device))
+        expert_actions = rutils.get_ac_repr(self.action_space, expert_actions)
+        agent_states = self._trans_agent_state(agent_batch["state"],
+                                               agent_batch["other_state"] if "other_state" in agent_batch else None)
+        agent_actions = rutils.get_ac_repr(self.action_space, agent_batch["actions"].to(self.args.device))
+        s_E, a_E = expert_states.to(self.args.device).float(), expert_actions.float()
+        s_A, a_A = agent_states.to(self.args.device).float(), agent_actions.float()
+        ne, na = self._nets()
+        only_a = bool(self.args.flow_path) and not self.args.finetune_ve and self.args.option == "2fs"
+        return [dict(net=ne, sign=1.0, s=s_E, a0=a_E, rate=0.0 if only_a else self.args.expert_loss_rate),
+                dict(net=na, sign=-1.0, s=s_A, a0=a_A, rate=1.0 if only_a else self.args.agent_loss_rate)]
+
+    def _draw(self, term):
+        """t / noise (and 2fs dequantisation) in the reference's draw order (pretrain.py:98-101, :182-183)."""
+        a0, dev = term["a0"], self.args.device
+        B = a0.shape[0]
+        eps = self.flow_net.eps if self.args.option == "scrf" else self.flow_net_e.eps
+        if self.args.option != "scrf":
+            a0 = a0 + torch.randn_like(a0) * 0.02
+        t = torch.rand(B, 1, device=dev) * (1 - 2 * eps) + eps
+        noise = torch.distributions.Normal(0., 1.).sample((B, self.action_dim)).to(dev)
+        return dict(term, a0=a0, t=t, noise=noise)
+
+    def _update_reward_func(self, storage):
+        for m in ((self.flow_net,) if self.args.option == "scrf" else (self.flow_net_e, self.flow_net_a)):
+            m.train()
+        self._rollout_cache = None
+        log_vals = defaultdict(float)
+        obsfilt = self.get_env_ob_filt()
+        expert_sampler, agent_sampler = self._get_sampler(storage)
+        if agent_sampler is None:
+            return {}
+        count = 0
+        sums = None
+        for _ in range(self.args.n_flowril_epochs):
+            for expert_batch, agent_batch in zip(expert_sampler, agent_sampler):
+                expert_batch, agent_batch = self._trans_batches(expert_batch, agent_batch)
+                terms = [self._draw(t) for t in self._compute_flow_loss(expert_batch, agent_batch, obsfilt)]  # sic
+                losses = train_step(terms, self.opt, max_norm=self.args.disc_grad_pen)
+                stacked = torch.stack(losses)
+                sums = stacked if sums is None else sums + stacked   # no host sync inside the loop
+                self.step += 1
+                count += 1
+        if sums is not None:
+            e_loss, a_loss = (float(x) for x in sums.cpu())
+            log_vals["flow_loss"] = e_loss / max(count, 1)
+            log_vals["agent_loss"] = a_loss / max(count, 1)
+        return log_vals
+
+    # ---- flags / checkpoints (reference flowril.py:545-597) ---------------------------------------------------------------
+    def get_add_args(self, parser):
+        super().get_add_args(parser)
+        parser.add_argument('--n-flowril-epochs', type=int, default=1)
+        parser.add_argument('--flowril-state-norm', type=str2bool, default=True)
+        parser.add_argument('--flowril-reward-norm', type=str2bool, default=True)
+        parser.add_argument('--flow-path', type=str, default=None)
+        parser.add_argument('--flow-depth', type=int, default=4)
+        parser.add_argument('--disc-lr', type=float, default=1e-4)
+        parser.add_argument('--disc-grad-pen', type=float, default=1.0)
+        parser.add_argument('--expert-loss-rate', type=float, default=1.0)
+        parser.add_argument('--agent-loss-rate', type=float, default=1.0)
+        parser.add_argument('--option', type=str, default='scrf', choices=['scrf', '2fs'])
+        parser.add_argument('--hidden-dim', type=int, default=256)
+        parser.add_argument('--enable-loss-anti', type=str2bool, default=True)
+        parser.add_argument('--enable-loss-stable', type=str2bool, default=True)
+        parser.add_argument('--params_autotune', type=str2bool, default=True)
+        parser.add_argument('--loss-anti', type=float, default=1e-4)
+        parser.add_argument('--loss-stable', type=float, default=1e-6)
+        parser.add_argument('--flow-loss-rate', type=float, default=0.2)
+        parser.add_argument('--finetune-ve', type=str2bool, default=False)
+        parser.add_argument('--reward-type', type=str, default='raw')
+        parser.add_argument('--plot-during-train', type=bool, default=True)
+        parser.add_argument('--save-animation', type=bool, default=True)
+        parser.add_argument('--save-interval', type=int, default=10)
+        parser.add_argument('--animation-type', type=str, default='gif')
+        parser.add_argument('--animation-fps', type=int, default=20)
+        # B200-only knobs (not in the reference)
+        parser.add_argument('--flowril-precision', type=str, default=None, choices=[None, 'fp32', 'fp16', 'bf16'])
+        parser.add_argument('--flowril-batched-scoring', type=str2bool, default=True)
+
+    def load_resume(self, checkpointer):
+        super().load_resume(checkpointer)
+        self.opt.load_state_dict(checkpointer.get_key(f'flow_{self.args.option}_opt'))
+        if self.args.option == "scrf":
+            self.flow_net.load_state_dict(checkpointer.get_key(f'flow_{self.args.option}'))
+        else:
+            self.flow_net_e.load_state_dict(checkpointer.get_key(f'flow_{self.args.option}_e'))
+            self.flow_net_a.load_state_dict(checkpointer.get_key(f'flow_{self.args.option}_a'))
+
+    def save(self, checkpointer):
+        super().save(checkpointer)
+        checkpointer.save_key(f'flow_{self.args.option}_opt', self.opt.state_dict())
+        if self.args.option == "scrf":
+            checkpointer.save_key(f'flow_{self.args.option}', self.flow_net.state_dict())
+        else:
+            # the reference LOADS here instead of saving (flowril.py:596-597); saving is what a
+            # resume needs, so this deliberately departs from the bug
+            checkpointer.save_key(f'flow_{self.args.option}_e', self.flow_net_e.state_dict())
+            checkpointer.save_key(f'flow_{self.args.option}_a', self.flow_net_a.state_dict())
+
+
+if HAVE_RLF:
+    class FLOWRIL(NestedAlgo):
+        def __init__(self, agent_updater=None):
+            super().__init__([FlowMatchingEstimation(), agent_updater or PPO()], 1)
+else:
+    class FLOWRIL(object):
+        """``NestedAlgo([FlowMatchingEstimation(), PPO()], 1)`` needs rl-toolkit (reference flowril.py:21-23)."""
+
+        def __init__(self, *a, **k):
+            raise ImportError("FLOWRIL (the NestedAlgo wrapper) needs rl-toolkit (rlf); "
+                              "FlowMatchingEstimation works stand-alone")

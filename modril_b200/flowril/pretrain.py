@@ -430,11 +430,8 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None):
             g.zero_()
         grads.append(g)
     if world is not None and ws > 1:
-        import torch.distributed as dist
+        from ..dist import allreduce_flat
 
-        for g in grads:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=world[0])
-        for l in losses:
-            dist.all_reduce(l, op=dist.ReduceOp.SUM, group=world[0])
+        allreduce_flat(grads, losses, world[0])
     opt.step_flat(grads, max_norm)
     return [l.reshape(()) for l in losses]

@@ -1,0 +1,213 @@
+"""The reward-module mirror (FlowMatchingEstimation hooks) on the GPU against the oracle, with a fake rollout storage.
+Reference call sites: flowril.py:175-230 (_get_reward), :232-350 (_update_reward_func), base_irl.py:37-72 (update)."""
+import argparse
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as cf
+from oracle import synth
+from tests.gpu_common import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+class Space:
+    def __init__(self, n):
+        self.shape = (n,)
+
+
+class Policy:
+    def __init__(self, s_dim, a_dim):
+        self.obs_space, self.action_space = Space(s_dim), Space(a_dim)
+
+
+class FakeStorage:
+    """The slice of rlf RolloutStorage the module touches (rollout_storage.py:243-323)."""
+
+    def __init__(self, T, N, s_dim, a_dim, seed, device):
+        g = synth.rng(seed)
+        self.obs = torch.from_numpy(g.standard_normal((T + 1, N, s_dim)).astype(np.float32)).to(device)
+        self.actions = torch.from_numpy(np.clip(g.standard_normal((T, N, a_dim)), -1, 1).astype(np.float32)).to(device)
+        m = (g.random((T + 1, N, 1)) > 0.1).astype(np.float32)
+        self.masks = torch.from_numpy(m).to(device)
+        self.rewards = torch.zeros(T, N, 1, device=device)
+        self.T, self.N = T, N
+
+    def get_obs(self, step):
+        return self.obs[step]
+
+    def get_generator(self, advantages=None, num_mini_batch=None, mini_batch_size=None, **kw):
+        B = self.T * self.N
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+        flat_s = self.obs[:-1].reshape(B, -1)
+        flat_a = self.actions.reshape(B, -1)
+        for i in range(0, B - mini_batch_size + 1, mini_batch_size):
+            idx = perm[i:i + mini_batch_size].to(flat_s.device)
+            yield {"state": flat_s[idx], "other_state": {}, "action": flat_a[idx]}
+
+
+def make_args(**kw):
+    d = dict(option="scrf", hidden_dim=128, flow_depth=4, flow_path=None, disc_lr=1e-3, disc_grad_pen=1.0,
+             expert_loss_rate=1.0, agent_loss_rate=1.0, enable_loss_anti=False, enable_loss_stable=False,
+             params_autotune=False, loss_anti=1e-4, loss_stable=1e-6, finetune_ve=False, reward_type="raw",
+             flowril_state_norm=False, flowril_reward_norm=True, n_flowril_epochs=1, gamma=0.99, num_steps=6,
+             num_processes=8, traj_batch_size=16, device=torch.device("cuda:0"), flowril_precision="fp32",
+             flowril_batched_scoring=True, env_name="Hopper-v3")
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def make_module(args, s_dim=11, a_dim=3, seed=0):
+    from modril_b200.flowril.flowril import FlowMatchingEstimation
+    torch.manual_seed(seed)
+    g = synth.rng(99)
+    obs = torch.from_numpy(g.standard_normal((64, s_dim)).astype(np.float32))
+    args.expert_dataset = {"obs": obs, "actions": torch.from_numpy(synth.expert_actions(5, obs.numpy(), a_dim))}
+    mod = FlowMatchingEstimation()
+    mod.init(Policy(s_dim, a_dim), args)
+    return mod
+
+
+def test_get_reward_matches_oracle_with_return_normalisation():
+    from modril_b200.flowril import _rademacher
+    args = make_args()
+    mod = make_module(args)
+    T, N = args.num_steps, args.num_processes
+    storage = FakeStorage(T, N, 11, 3, 7, args.device)
+    spec = cf.NetSpec(11, 3, 128, 4, 2)
+    flat = mod.flow_net.net.flat_params().cpu().numpy().astype(np.float64)
+    probe = _rademacher((N, 3), device=args.device).cpu().numpy()
+    raw = np.zeros((T, N, 1), np.float32)
+    for t in range(T):
+        s, a = storage.obs[t].cpu().numpy(), storage.actions[t].cpu().numpy()
+        le = cf.log_prob(spec, flat, s, a, "expert", probe, 32)
+        la = cf.log_prob(spec, flat, s, a, "agent", probe, 32)
+        raw[t, :, 0] = (le - la).astype(np.float32)
+    ref, _, _ = cf.normalise_rewards(raw, storage.masks.cpu().numpy(), args.gamma)
+    got = np.stack([mod._get_reward(t, storage, {})[0].cpu().numpy() for t in range(T)])
+    assert_close(got, ref, 2e-4, "normalised rewards", 0.03)
+    # per-step (reference call shape) and batched scoring are the same numbers, bit for bit
+    args2 = make_args(flowril_batched_scoring=False)
+    mod2 = make_module(args2)
+    got2 = np.stack([mod2._get_reward(t, storage, {})[0].cpu().numpy() for t in range(T)])
+    assert np.array_equal(got, got2)
+    # disc value (flowril.py:352-365)
+    dv = mod._compute_disc_val(storage.obs[0], storage.actions[0]).cpu().numpy()
+    assert_close(dv, raw[0, :, 0], 1e-4, "disc val", 0.13)
+
+
+@pytest.mark.parametrize("reward_type", ["norm", "exp", "clip", "smooth"])
+def test_reward_types_through_the_module(reward_type):
+    args = make_args(reward_type=reward_type, flowril_reward_norm=False)
+    mod = make_module(args)
+    storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 8, args.device)
+    raw_args = make_args(reward_type="raw", flowril_reward_norm=False)
+    raw_mod = make_module(raw_args)
+    for t in range(2):
+        got = mod._get_reward(t, storage, {})[0].cpu().numpy()
+        raw = raw_mod._get_reward(t, storage, {})[0].cpu().numpy()
+        assert_close(got, cf.reward_transform(raw, reward_type), 2e-6, reward_type)
+
+
+def test_bad_reward_type():
+    args = make_args(reward_type="bogus")
+    mod = make_module(args)
+    storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 8, args.device)
+    with pytest.raises(ValueError):
+        mod._get_reward(0, storage, {})
+
+
+def test_update_matches_oracle_including_role_swap():
+    """One _update_reward_func pass: replay the module's random draws (same torch seeds, same order) through the
+    float64 oracle.  Role 'expert' is trained on the ROLLOUT batch and role 'agent' on the DEMO batch."""
+    args = make_args(num_steps=4, num_processes=8, traj_batch_size=16)
+    mod = make_module(args)
+    storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 9, args.device)
+    spec = cf.NetSpec(11, 3, 128, 4, 2)
+    flat = mod.flow_net.net.flat_params().cpu().numpy().astype(np.float64)
+    m, v = np.zeros_like(flat), np.zeros_like(flat)
+    # replay: the DataLoader shuffle and the t/noise draws come from torch's global generators
+    state_cpu, state_cuda = torch.get_rng_state(), torch.cuda.get_rng_state()
+    log_vals = mod._update_reward_func(storage)
+    torch.set_rng_state(state_cpu)
+    torch.cuda.set_rng_state(state_cuda)
+    losses_ref = []
+    step = 0
+    for demo, roll in zip(mod.expert_train_loader, storage.get_generator(None, mini_batch_size=16)):
+        batches = []
+        for role, s, a in (("expert", roll["state"], roll["action"]), ("agent", demo["state"], demo["actions"])):
+            B = a.shape[0]
+            t = torch.rand(B, 1, device=args.device) * (1 - 2e-3) + 1e-3
+            noise = torch.distributions.Normal(0., 1.).sample((B, 3))
+            batches.append((role, s.cpu().numpy(), a.cpu().numpy(), t.cpu().numpy(), noise.numpy()))
+        step += 1
+        flat, m, v, losses, _ = cf.train_step(spec, flat, m, v, step, batches, lr=args.disc_lr, max_norm=1.0)
+        losses_ref.append(losses)
+    assert step == 2
+    ref = np.mean(np.array(losses_ref), axis=0)
+    assert abs(log_vals["flow_loss"] - ref[0]) <= 1e-4 * max(1, abs(ref[0]))
+    assert abs(log_vals["agent_loss"] - ref[1]) <= 1e-4 * max(1, abs(ref[1]))
+    got = mod.flow_net.net.flat_params().cpu().numpy()
+    assert np.abs(got - flat).max() <= 5e-6
+
+
+def test_full_update_loop_and_checkpoint_roundtrip():
+    args = make_args()
+    mod = make_module(args)
+    storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 11, args.device)
+    logs = mod.update(storage)
+    assert set(logs) >= {"flow_loss", "agent_loss"}
+    assert torch.isfinite(storage.rewards).all() and storage.rewards.abs().sum() > 0
+
+    class Ckpt:
+        def __init__(self):
+            self.d = {}
+
+        def save_key(self, k, v):
+            self.d[k] = copy.deepcopy(v)
+
+        def get_key(self, k):
+            return self.d[k]
+
+    ck = Ckpt()
+    mod.save(ck)
+    assert set(ck.d) == {"flow_scrf_opt", "flow_scrf"}
+    assert list(ck.d["flow_scrf"].keys())[0] == "net.shared.0.weight"
+    args2 = make_args()
+    mod2 = make_module(args2, seed=123)
+    mod2.load_resume(ck)
+    assert torch.equal(mod2.flow_net.net.flat_params(), mod.flow_net.net.flat_params())
+    # resumed optimiser continues identically
+    l1 = mod._update_reward_func(storage)
+    torch.manual_seed(5); s1 = torch.get_rng_state(); c1 = torch.cuda.get_rng_state()
+    for mm in (mod, mod2):
+        torch.set_rng_state(s1); torch.cuda.set_rng_state(c1)
+        mm.flow_net.load_state_dict(ck.d["flow_scrf"]); mm.opt.load_state_dict(ck.d["flow_scrf_opt"])
+        mm._update_reward_func(storage)
+    assert torch.equal(mod2.flow_net.net.flat_params(), mod.flow_net.net.flat_params())
+
+
+def test_regularisers_raise_until_implemented():
+    args = make_args(enable_loss_anti=True, enable_loss_stable=True)
+    with pytest.raises(NotImplementedError):
+        make_module(args)
+
+
+def test_2fs_option_runs_and_freezes_expert_net(tmp_path):
+    from modril_b200.flowril import FlowMatching
+    pre = FlowMatching(11, 3, 128, depth=4)
+    path = str(tmp_path / "hopper_fm.pt")
+    torch.save(pre.state_dict(), path)
+    args = make_args(option="2fs", flow_path=path, flowril_reward_norm=False)
+    mod = make_module(args)
+    storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 12, args.device)
+    before_e = mod.flow_net_e.net.flat_params().clone()
+    before_a = mod.flow_net_a.net.flat_params().clone()
+    logs = mod.update(storage)
+    assert torch.equal(mod.flow_net_e.net.flat_params(), before_e)          # frozen (flowril.py:101-106)
+    assert not torch.equal(mod.flow_net_a.net.flat_params(), before_a)
+    assert np.isfinite(logs["flow_loss"]) and np.isfinite(logs["agent_loss"])
+    assert torch.isfinite(storage.rewards).all()
