@@ -56,12 +56,14 @@ def _rademacher(shape_or_tensor, device=None):
     return torch.randint(0, 2, shape, device=device, generator=rng).float().mul_(2).sub_(1)
 
 
-@functools.lru_cache(maxsize=64)
-def _t_mid(n_steps: int):
-    """Midpoints of torch.linspace(0, 1, n+1) in float32, as the reference forms them (pretrain.py:200, :206)."""
-    g = torch.linspace(0.0, 1.0, n_steps + 1)
+@functools.lru_cache(maxsize=128)
+def _t_mid(n_steps: int, device_type: str = "cuda"):
+    """Midpoints of torch.linspace(0, 1, n+1) in float32, formed with torch on the device type the model lives on --
+    exactly what the reference does (pretrain.py:200, :206; the CPU and CUDA linspace kernels can differ in the last
+    bit).  Cached per (n_steps, device type): one tiny launch + copy the first time only."""
+    g = torch.linspace(0.0, 1.0, n_steps + 1, device=device_type)
     tm = 0.5 * (g[:-1] + g[1:])
-    return _native.float_array(tm.tolist())
+    return _native.float_array(tm.cpu().tolist())
 
 
 def _precision_code(precision):

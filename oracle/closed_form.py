@@ -152,18 +152,17 @@ def v_field(spec: NetSpec, flat, a, s, t, role: str, tangent=None):
 
 
 def torch_linspace_f32(n_steps: int) -> np.ndarray:
-    """torch.linspace(0, 1, n+1) in float32 as torch's CPU/CUDA kernels compute it: step = (end-start)/steps in
-    float32; first half start + i*step, second half end - (steps-i)*step  (ATen RangeFactories; the reference
-    calls it at pretrain.py:114, :200).  Checked against torch in tests/test_oracle_host.py."""
+    """torch.linspace(0, 1, n+1) in float32 as torch's CPU kernel computes it: the step is a float32, the first half
+    is start + step*i, the second half end - step*(steps-1-i), each evaluated as ONE fused multiply-add (a single
+    rounding; emulated here in float64, which is exact for these operands).  The reference calls it at
+    pretrain.py:114, :200.  Checked bit-for-bit against torch in tests/test_host_logic.py.  (The product computes
+    its grid with torch on the model's device, like the reference does.)"""
     steps = n_steps + 1
-    step = np.float32(np.float32(1.0) / np.float32(steps - 1))
+    step = float(np.float32(1.0) / np.float32(steps - 1))
     half = steps // 2
     out = np.empty(steps, dtype=np.float32)
     for i in range(steps):
-        if i < half:
-            out[i] = np.float32(0.0) + step * np.float32(i)
-        else:
-            out[i] = np.float32(1.0) - step * np.float32(steps - i - 1)
+        out[i] = np.float32(0.0 + step * i) if i < half else np.float32(1.0 - step * (steps - i - 1))
     return out
 
 

@@ -78,7 +78,7 @@ def test_oracle_linspace_matches_torch():
 def test_t_mid_binding_matches_oracle():
     from modril_b200.flowril.pretrain import _t_mid
     for n in (20, 32):
-        assert np.array_equal(np.array(list(_t_mid(n)), np.float32), cf.t_mid_grid(n))
+        assert np.array_equal(np.array(list(_t_mid(n, 'cpu')), np.float32), cf.t_mid_grid(n))
 
 
 def test_reward_transform_matches_torch_formulas():
@@ -103,7 +103,7 @@ def test_torch_port_matches_numpy_oracle():
     le, la, rw = torch_port.score(spec, ft, ft, torch.from_numpy(s), torch.from_numpy(a), torch.from_numpy(probe), n)
     for role, got in (("expert", le), ("agent", la)):
         ref = cf.log_prob(spec, flat, s, a, role, probe, n)
-        assert np.abs(got.numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+        assert np.abs(got.detach().numpy() - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
     t, noise = synth.cfm_draws(3, B, 3)
     loss = torch_port.fm_loss(spec, ft.clone().requires_grad_(True), torch.from_numpy(s), torch.from_numpy(a), "agent",
                               torch.from_numpy(t), torch.from_numpy(noise))
