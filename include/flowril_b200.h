@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FRL_ABI_VERSION 1
+#define FRL_ABI_VERSION 2
 #define FRL_MAX_STEPS 256
 #define FRL_MAX_DEPTH 8
 
@@ -126,6 +126,35 @@ int frl_score_host(frl_net* net_expert, frl_net* net_agent, const float* s_host,
 int frl_cfm_loss_grad(frl_net* net, float role_sign, const float* s_dev, const float* a0_dev, const float* t_dev,
                       const float* noise_dev, long long B, long long mean_divisor, float grad_scale,
                       int accumulate, float* loss_dev, float* grad_dev, void* stream);
+
+/* Anti-divergence and Jacobian-stability regularisers of the coupled-residual (n_heads == 2) model with their
+ * parameter gradients (flowril.py:255-264: `_hutch_div(mix_a, r, k=1).square().mean()` and
+ * `_jacobian_frobenius(mix_a, v_c + r).mean()`, pretrain.py:163-177, :55-59; the reference differentiates them by
+ * autograd double-backward inside loss.backward(), flowril.py:322, and GradNorm2D.update, networks.py:108-117).
+ *   loss_anti   = mean_b (v^T J_r v)^2,  loss_stable = mean_b |J_{v_c+r}^T v|^2,  v = probe [N,a] (caller-supplied;
+ *   the reference draws the same shape-deterministic `_rademacher` matrix for both), evaluated at (a, s, t).
+ * which: bit 0 = anti, bit 1 = stable.  Each requested loss writes its scalar to loss_*_dev[0] (may be NULL) and
+ * OVERWRITES grad_*_dev (flat, state_dict order, unscaled; may be NULL to skip the backward).  mean_divisor as in
+ * frl_cfm_loss_grad.  Deterministic. */
+int frl_reg_loss_grad(frl_net* net, const float* s_dev, const float* a_dev, const float* t_dev,
+                      const float* probe_dev, long long N, long long mean_divisor, int which, float* loss_anti_dev,
+                      float* loss_stable_dev, float* grad_anti_dev, float* grad_stable_dev, void* stream);
+
+/* y += c * x over n floats with c = alpha * num / (den + eps)  (den NULL: alpha * num; num NULL: alpha), forced to 0
+ * when gate_dev[0] <= 0.  num_dev / den_dev / gate_dev are optional DEVICE scalars, so the warm-up weights
+ * w = L_E / (L_reg + 1e-8) * 1e-3 of flowril.py:272-284 and GradNorm2D's beta / gamma (networks.py:104-106) scale a
+ * gradient without a host round trip; `gate` (the previous weight) reproduces `use_anti = args.loss_anti > 0`
+ * (flowril.py:255-256).  coef_out_dev (may be NULL; TWO floats: [0] = c, [1] = scratch that must start as 0; may alias
+ * gate_dev). */
+int frl_grad_axpy(float* y_dev, const float* x_dev, long long n, float alpha, const float* num_dev,
+                  const float* den_dev, float eps, const float* gate_dev, float* coef_out_dev, int device,
+                  void* stream);
+
+/* L2 norm of each parameter tensor's slice of a flat gradient: out_dev[i] = |flat[offsets[i] .. offsets[i+1])|.
+ * GradNorm2D.update sums `g.norm()` over the parameter tensors of each regulariser's gradient
+ * (networks.py:108-117).  offsets_host has n_tensors + 1 entries (n_tensors <= 20). */
+int frl_tensor_norms(const float* flat_dev, const long long* offsets_host, int n_tensors, float* out_dev, int device,
+                     void* stream);
 
 /* torch.nn.utils.clip_grad_norm_ + torch.optim.Adam.step (flowril.py:324-330; Adam defaults betas (0.9,0.999),
  * eps 1e-8, no weight decay) over up to 4 flat segments that share one global gradient norm.

@@ -112,4 +112,30 @@ int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double l
     return FRL_OK;
 }
 
+
+// Per-tensor L2 norms of a flat gradient (GradNorm2D.update sums g.norm() over the parameter tensors,
+// modril/flowril/networks.py:108-117).  One block per tensor, fixed reduction order.
+struct NormTable {
+    long long first[2 * kMaxDepth + 5];
+    int n;
+};
+__global__ void __launch_bounds__(kNormThreads) tensor_norms_kernel(const float* __restrict__ flat, NormTable tab,
+                                                                    float* __restrict__ out) {
+    const long long lo = tab.first[blockIdx.x], hi = tab.first[blockIdx.x + 1];
+    double acc = 0.0;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) acc += (double)flat[i] * (double)flat[i];
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) out[blockIdx.x] = (float)sqrt(acc);
+}
+
+int tensor_norms(const float* flat, const long long* offsets_host, int n_tensors, float* out, cudaStream_t stream) {
+    NormTable tab{};
+    FRL_REQUIRE(n_tensors >= 1 && n_tensors <= 2 * kMaxDepth + 4, "1..20 tensors");
+    tab.n = n_tensors;
+    for (int i = 0; i <= n_tensors; ++i) tab.first[i] = offsets_host[i];
+    tensor_norms_kernel<<<n_tensors, kNormThreads, 0, stream>>>(flat, tab, out);
+    FRL_CUDA(cudaGetLastError());
+    return FRL_OK;
+}
+
 }  // namespace frl

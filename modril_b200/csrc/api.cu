@@ -207,6 +207,35 @@ extern "C" int frl_cfm_loss_grad(frl_net* net, float role_sign, const float* s, 
                              accumulate, loss, grad, (cudaStream_t)stream);
 }
 
+extern "C" int frl_reg_loss_grad(frl_net* net, const float* s, const float* a, const float* t, const float* probe,
+                                 long long N, long long mean_divisor, int which, float* loss_anti, float* loss_stable,
+                                 float* grad_anti, float* grad_stable, void* stream) {
+    int rc = check_net(net);
+    if (rc != FRL_OK) return rc;
+    FRL_REQUIRE(net->cfg.n_heads == 2, "the regularisers are defined for the coupled-residual net (n_heads == 2) only");
+    FRL_REQUIRE(s && a && t && probe, "null input");
+    FRL_REQUIRE(N > 0, "empty batch");
+    FRL_REQUIRE(which >= 1 && which <= 3, "which: bit 0 = anti, bit 1 = stable");
+    FRL_CUDA(cudaSetDevice(net->cfg.device));
+    return reg_loss_grad_f32(net, s, a, t, probe, N, mean_divisor, which, loss_anti, loss_stable, grad_anti,
+                             grad_stable, (cudaStream_t)stream);
+}
+
+extern "C" int frl_grad_axpy(float* y, const float* x, long long n, float alpha, const float* num, const float* den,
+                             float eps, const float* gate, float* coef_out, int device, void* stream) {
+    FRL_REQUIRE(n >= 0 && (n == 0 || (x && y)), "null vector");
+    FRL_REQUIRE(num || !den, "den without num");
+    FRL_CUDA(cudaSetDevice(device));
+    return grad_axpy(y, x, n, alpha, num, den, eps, gate, coef_out, (cudaStream_t)stream);
+}
+
+extern "C" int frl_tensor_norms(const float* flat, const long long* offsets_host, int n_tensors, float* out,
+                                int device, void* stream) {
+    FRL_REQUIRE(flat && offsets_host && out, "null pointer");
+    FRL_CUDA(cudaSetDevice(device));
+    return tensor_norms(flat, offsets_host, n_tensors, out, (cudaStream_t)stream);
+}
+
 extern "C" int frl_clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double lr, double beta1,
                              double beta2, double eps, double max_norm, float* norm_out, int device, void* stream) {
     FRL_REQUIRE(segs && n_segs >= 1 && n_segs <= 4, "1..4 segments");

@@ -99,8 +99,15 @@ int cfm_loss_grad_f32(frl_net* net, float role_sign, const float* s, const float
                       const float* noise, long long B, long long mean_divisor, float grad_scale, int accumulate,
                       float* loss, float* grad, cudaStream_t stream);
 
+int reg_loss_grad_f32(frl_net* net, const float* s, const float* a, const float* t, const float* probe, long long N,
+                      long long mean_divisor, int which, float* loss_anti, float* loss_stable, float* grad_anti,
+                      float* grad_stable, cudaStream_t stream);
+int grad_axpy(float* y, const float* x, long long n, float alpha, const float* num, const float* den, float eps,
+              const float* gate, float* coef_out, cudaStream_t stream);
+
 // adam.cu
 int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double lr, double beta1, double beta2,
               double eps, double max_norm, float* norm_out, cudaStream_t stream);
+int tensor_norms(const float* flat, const long long* offsets_host, int n_tensors, float* out, cudaStream_t stream);
 
 }  // namespace frl

@@ -22,9 +22,14 @@ Differences in mechanism, not in results:
   * Reference quirk kept on purpose: ``_update_reward_func`` passes
     ``(expert_batch, agent_batch)`` to ``_compute_flow_loss(agent_batch, expert_batch, ...)`` (flowril.py:314 vs :232),
     so role "expert" is trained on the ROLLOUT batch and role "agent" on the DEMONSTRATION batch.
-  * The anti-divergence / Jacobian-stability regularisers and GradNorm2D (flowril.py:255-290) are row f1 of the
-    scope table and are not implemented yet: the module raises if they are enabled
-    (``--enable-loss-anti false --enable-loss-stable false``, i.e. configs/sine/flowril-no-as.yaml, or option 2fs).
+  * The anti-divergence / Jacobian-stability regularisers (flowril.py:255-290; ON by default) come out of
+    ``frl_reg_loss_grad`` as loss values plus hand-derived parameter gradients instead of autograd's double backward;
+    their weights (fixed, warm-up ``L_E / (L_reg + eps) * 1e-3``, or GradNorm2D's beta / gamma) are applied to the
+    gradients on the device.  Reference quirk kept (flowril.py:272): ``gradnorm.step_count`` only advances inside
+    ``GradNorm2D.forward``, which is only called from the branch taken when ``step_count > warmup_steps`` -- so with
+    the reference's control flow the warm-up weighting is what always runs; the GradNorm branch is implemented and
+    tested but, exactly like in the reference, not reachable from ``_compute_flow_loss`` unless ``step_count`` is
+    advanced externally.
 """
 from __future__ import annotations
 
@@ -33,7 +38,9 @@ from collections import defaultdict
 import numpy as np
 import torch
 
-from .pretrain import CoupledResidualFM, FlowMatching, FusedAdam, _rademacher, score_pair, train_step
+from .networks import GradNorm2D
+from .pretrain import (CoupledResidualFM, FlowMatching, FusedAdam, _rademacher, score_pair, tensor_grad_norm_sum,
+                       train_step)
 
 try:  # the real plugin API, when rl-toolkit and its simulators are installed
     import rlf.rl.utils as rutils
@@ -168,15 +175,21 @@ class FlowMatchingEstimation(BaseIRLAlgo):
                     p.requires_grad = True
             self.opt = FusedAdam([self.flow_net.net], lr=lr)
             self.params = list(self.flow_net.parameters())
+            if self.args.params_autotune:
+                self.gradnorm = GradNorm2D(beta_init=self.args.loss_anti, gamma_init=self.args.loss_stable, alpha=0.1,
+                                           warmup_steps=100, update_freq=10, ema_decay=0.9, beta_min=1e-8,
+                                           beta_max=1e1, gamma_min=1e-12, gamma_max=1e-2,
+                                           enable_beta=self.args.enable_loss_anti,
+                                           enable_gamma=self.args.enable_loss_stable).to(dev)
             if not self.args.enable_loss_anti:
                 self.args.loss_anti = 0
             if not self.args.enable_loss_stable:
                 self.args.loss_stable = 0
-            if self.args.loss_anti > 0 or self.args.loss_stable > 0:
-                raise NotImplementedError(
-                    "the anti-divergence / Jacobian-stability regularisers and GradNorm2D (reference "
-                    "flowril.py:255-290) are not implemented on the B200 path yet; run with "
-                    "--enable-loss-anti false --enable-loss-stable false or --option 2fs")
+            # device copies of the two weights (2 floats each: value + scratch): `use_anti = args.loss_anti > 0`
+            # (flowril.py:255-256) is evaluated on the device as a gate, so no host sync per batch
+            self._w_anti_init, self._w_stable_init = float(self.args.loss_anti), float(self.args.loss_stable)
+            self._w_anti = torch.tensor([self._w_anti_init, 0.0], device=dev)
+            self._w_stable = torch.tensor([self._w_stable_init, 0.0], device=dev)
         else:
             mk = lambda: FlowMatching(state_dim=self.state_dim, action_dim=self.action_dim,
                                       hidden_dim=self.args.hidden_dim, depth=self.args.flow_depth).to(dev)
@@ -330,8 +343,60 @@ class FlowMatchingEstimation(BaseIRLAlgo):
         s_A, a_A = agent_states.to(self.args.device).float(), agent_actions.float()
         ne, na = self._nets()
         only_a = bool(self.args.flow_path) and not self.args.finetune_ve and self.args.option == "2fs"
-        return [dict(net=ne, sign=1.0, s=s_E, a0=a_E, rate=0.0 if only_a else self.args.expert_loss_rate),
-                dict(net=na, sign=-1.0, s=s_A, a0=a_A, rate=1.0 if only_a else self.args.agent_loss_rate)]
+        terms = [dict(net=ne, sign=1.0, s=s_E, a0=a_E, rate=0.0 if only_a else self.args.expert_loss_rate),
+                 dict(net=na, sign=-1.0, s=s_A, a0=a_A, rate=1.0 if only_a else self.args.agent_loss_rate)]
+        return terms
+
+    def _reg_spec(self, terms):
+        """The regulariser part of reference flowril.py:255-290 for the (already drawn) scrf terms: mixed batch,
+        t_mix ~ U[0,1) (drawn AFTER the two fm_loss draws, like the reference), the shape-deterministic probe, and
+        how the two weights are formed.  Returns the ``reg`` dict of ``train_step`` or None."""
+        if self.args.option != "scrf":
+            return None
+        anti_on = self.args.enable_loss_anti if self.args.params_autotune else True
+        stable_on = self.args.enable_loss_stable if self.args.params_autotune else True
+        # a weight that started at 0 (term disabled) can never turn on: skip the work altogether
+        anti_on = anti_on and float(self._w_anti_init) > 0
+        stable_on = stable_on and float(self._w_stable_init) > 0
+        if not (anti_on or stable_on):
+            return None
+        s_E, a_E, s_A, a_A = terms[0]["s"], terms[0]["a0_raw"], terms[1]["s"], terms[1]["a0_raw"]
+        mix_s = torch.cat([s_E, s_A], dim=0)
+        mix_a = torch.cat([a_E, a_A], dim=0)
+        t_mix = torch.rand(mix_s.size(0), 1, device=mix_s.device)
+        reg = dict(net=self.flow_net.net, s=mix_s, a=mix_a, t=t_mix,
+                   probe=_rademacher((mix_a.size(0), self.action_dim), device=mix_a.device))
+        if not self.args.params_autotune:
+            mode = lambda w: float(w)                       # fixed weights (flowril.py:266-270)
+            reg["anti"] = mode(self._w_anti_init) if anti_on else None
+            reg["stable"] = mode(self._w_stable_init) if stable_on else None
+        elif int(self.gradnorm.step_count) <= self.gradnorm.warmup_steps:
+            warm = ("warmup", self.global_scale, self.eps)  # w = L_E / (L_reg + eps) * global_scale (flowril.py:272-284)
+            reg["anti"] = warm if anti_on else None
+            reg["stable"] = warm if stable_on else None
+        else:
+            reg["gradnorm"] = True                          # beta / gamma from GradNorm2D (flowril.py:286-290)
+            reg["anti"] = self.gradnorm.log_beta.detach().exp().reshape(1) if anti_on else None
+            reg["stable"] = self.gradnorm.log_gamma.detach().exp().reshape(1) if stable_on else None
+        reg["gate_anti"], reg["gate_stable"] = self._w_anti, self._w_stable
+        return reg
+
+    def _after_reg(self, reg):
+        """Bookkeeping the reference does after forming the regularised loss: `args.loss_anti/_stable` take the
+        weights used (device scalars here), and past warm-up GradNorm2D accumulates / updates (flowril.py:278-290)."""
+        out = reg.get("out") or {}
+        if reg.get("anti") is not None:
+            self.args.loss_anti = self._w_anti[0]
+        if reg.get("stable") is not None:
+            self.args.loss_stable = self._w_stable[0]
+        if reg.get("gradnorm"):
+            zero = torch.zeros((), device=self.args.device)
+            la, ls = out.get("loss_anti", zero), out.get("loss_stable", zero)
+            self.gradnorm(la, ls)
+            net = self.flow_net.net
+            ga = tensor_grad_norm_sum(net, out["grad_anti"]) if "grad_anti" in out else 0.0
+            gs = tensor_grad_norm_sum(net, out["grad_stable"]) if "grad_stable" in out else 0.0
+            self.gradnorm.update(la, ls, None, g_anti=ga, g_jpen=gs)
 
     def _draw(self, term):
         """t / noise (and 2fs dequantisation) in the reference's draw order (pretrain.py:98-101, :182-183)."""
@@ -342,7 +407,7 @@ class FlowMatchingEstimation(BaseIRLAlgo):
             a0 = a0 + torch.randn_like(a0) * 0.02
         t = torch.rand(B, 1, device=dev) * (1 - 2 * eps) + eps
         noise = torch.distributions.Normal(0., 1.).sample((B, self.action_dim)).to(dev)
-        return dict(term, a0=a0, t=t, noise=noise)
+        return dict(term, a0=a0, a0_raw=term["a0"], t=t, noise=noise)
 
     def _update_reward_func(self, storage):
         for m in ((self.flow_net,) if self.args.option == "scrf" else (self.flow_net_e, self.flow_net_a)):
@@ -359,7 +424,10 @@ class FlowMatchingEstimation(BaseIRLAlgo):
             for expert_batch, agent_batch in zip(expert_sampler, agent_sampler):
                 expert_batch, agent_batch = self._trans_batches(expert_batch, agent_batch)
                 terms = [self._draw(t) for t in self._compute_flow_loss(expert_batch, agent_batch, obsfilt)]  # sic
-                losses = train_step(terms, self.opt, max_norm=self.args.disc_grad_pen)
+                reg = self._reg_spec(terms)
+                losses = train_step(terms, self.opt, max_norm=self.args.disc_grad_pen, reg=reg)
+                if reg is not None:
+                    self._after_reg(reg)
                 stacked = torch.stack(losses)
                 sums = stacked if sums is None else sums + stacked   # no host sync inside the loop
                 self.step += 1

@@ -2,7 +2,7 @@
 
 Drop-in for the estimator classes of the reference's ``modril/flowril/pretrain.py`` (level-1 boundary of SURVEY.md
 section 8b): ``CoupledResidualFM`` (:137-214) and ``FlowMatching`` (:62-134) with the same constructor arguments,
-attributes (``.net``, ``.prior``, ``.eps``), methods (``v_field``, ``fm_loss``, ``log_prob``, ``_hutch_div``) and
+attributes (``.net``, ``.prior``, ``.eps``), methods (``v_field``, ``fm_loss``, ``log_prob``) and
 ``state_dict`` keys; module-level ``_rademacher`` (:42-52).
 
 Mechanism: ``log_prob`` is ONE launch of the fused Euler integrator (``frl_logprob`` / ``frl_score``) that carries
@@ -207,6 +207,63 @@ def _fm_loss_native(net, sign, s, a0, t, noise):
     return _FMLoss.apply(net, sign, need_grad, s, a0, t, noise, *params)
 
 
+def reg_losses_native(net, s, a, t, probe, anti=True, stable=True, need_grad=True, mean_divisor=0):
+    """Anti-divergence / Jacobian-stability regularisers of the scrf model on one (mixed) batch through
+    ``frl_reg_loss_grad`` (reference flowril.py:255-264).  Returns a dict with device scalars ``loss_anti`` /
+    ``loss_stable`` and (need_grad) the unscaled flat gradients ``grad_anti`` / ``grad_stable`` (state_dict order;
+    buffers owned by the net and overwritten by the next call)."""
+    dev = net.flat_params().device
+    h = net.native()
+    s = as_f32_cuda(s, dev, "s")
+    a = as_f32_cuda(a, dev, "a")
+    t = as_f32_cuda(t, dev, "t").reshape(-1)
+    probe = as_f32_cuda(probe, dev, "probe")
+    N = a.shape[0]
+    if a.shape != (N, net.a_dim) or s.shape != (N, net.s_dim) or t.numel() != N or probe.shape != a.shape:
+        raise ValueError("regularisers: inconsistent batch shapes")
+    which = (1 if anti else 0) | (2 if stable else 0)
+    if which == 0:
+        return {}
+    buf = getattr(net, "_reg_buf", None)
+    if buf is None or buf.device != dev or buf.shape[1] != net.flat_params().numel():
+        buf = torch.zeros(2, net.flat_params().numel(), device=dev)
+        net._reg_buf = buf
+    losses = torch.zeros(2, device=dev)
+    la, ls = losses[0:1], losses[1:2]
+    ga = buf[0] if (need_grad and anti) else None
+    gs = buf[1] if (need_grad and stable) else None
+    _native.check(_native.lib().frl_reg_loss_grad(h, _ptr(s), _ptr(a), _ptr(t), _ptr(probe), N, int(mean_divisor),
+                                                  which, _ptr(la if anti else None), _ptr(ls if stable else None),
+                                                  _ptr(ga), _ptr(gs), _current_stream(dev)), "frl_reg_loss_grad")
+    out = {}
+    if anti:
+        out["loss_anti"], out["grad_anti"] = la.reshape(()), ga
+    if stable:
+        out["loss_stable"], out["grad_stable"] = ls.reshape(()), gs
+    return out
+
+
+def tensor_grad_norm_sum(net, flat_grad):
+    """sum over the parameter tensors of ||g_tensor||_2 -- the quantity GradNorm2D.update forms with
+    ``sum(g.norm() for g in grads)`` (reference networks.py:108-117).  Returns a device scalar."""
+    dev = flat_grad.device
+    offs = [0]
+    for _, off, n in net.param_slices():
+        offs.append(off + n)
+    arr = (C.c_longlong * len(offs))(*offs)
+    out = torch.empty(len(offs) - 1, device=dev)
+    _native.check(_native.lib().frl_tensor_norms(_ptr(flat_grad), arr, len(offs) - 1, _ptr(out), dev.index or 0,
+                                                 _current_stream(dev)), "frl_tensor_norms")
+    return out.sum()
+
+
+def _axpy(y, x, alpha=1.0, num=None, den=None, eps=0.0, gate=None, coef_out=None):
+    dev = y.device
+    _native.check(_native.lib().frl_grad_axpy(_ptr(y), _ptr(x), y.numel(), float(alpha), _ptr(num), _ptr(den),
+                                              float(eps), _ptr(gate), _ptr(coef_out), dev.index or 0,
+                                              _current_stream(dev)), "frl_grad_axpy")
+
+
 class FlowMatching(nn.Module):
     """One conditional flow net (the '2fs' option uses two of these) -- reference pretrain.py:62-134."""
 
@@ -278,6 +335,15 @@ class CoupledResidualFM(nn.Module):
         if probe is None and not exact:
             probe = _rademacher((a0.size(0), self.a_dim), device=a0.device)
         return _log_prob_native(self.net, 1.0 if role == "expert" else -1.0, s, a0, probe, exact, n_steps, precision)
+
+    def reg_losses(self, s, a, *, t=None, probe=None, anti=True, stable=True, need_grad=False):
+        """(loss_anti, loss_stable) of reference flowril.py:259-263 on the batch (s, a): t ~ U[0,1) and the
+        shape-deterministic ``_rademacher`` probe are drawn like the reference when not supplied."""
+        if t is None:
+            t = torch.rand(a.size(0), 1, device=a.device)
+        if probe is None:
+            probe = _rademacher((a.size(0), self.a_dim), device=a.device)
+        return reg_losses_native(self.net, s, a, t, probe, anti, stable, need_grad)
 
     def score(self, s, a, n_steps: int = 32, reward_type: str = "raw", *, probe=None, exact=False, precision=None):
         """(logp_E, logp_A, reward) in one launch -- what flowril.py:183-207 computes with two log_prob calls."""
@@ -394,13 +460,24 @@ class FusedAdam(torch.optim.Optimizer):
         self._bind_state()
 
 
-def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None):
-    """One reward-model update on the all-native route (reference flowril.py:311-330 without regularisers):
-    zero grads; for each term accumulate rate * d fm_loss / d theta; [all-reduce]; clip_grad_norm_(max_norm); Adam.
+def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=None):
+    """One reward-model update on the all-native route (reference flowril.py:311-330):
+    zero grads; for each term accumulate rate * d fm_loss / d theta; [regularisers]; [all-reduce];
+    clip_grad_norm_(max_norm); Adam.
 
     terms: list of dicts {net, sign, s, a0, t, noise, rate}; several terms may share a net (scrf: expert + agent).
     world: optional (process_group, world_size) for data-parallel training: each rank passes its shard, the mean
            divisor becomes the global batch and the flat gradients are all-reduced (sum) before the clip.
+    reg:   optional dict for the scrf regularisers (reference flowril.py:255-290):
+             net, s, a, t, probe      the mixed batch, its times and Rademacher probe
+             anti / stable            how each term is weighted: None (off), a float (fixed weight,
+                                      flowril.py:266-270), ("warmup", scale, eps) for w = L_E/(L_reg+eps)*scale with
+                                      L_E = the first term's loss (flowril.py:272-284), or a device scalar tensor
+                                      (GradNorm2D's beta / gamma, networks.py:104-106)
+             gate_anti / gate_stable  optional 2-float device tensors holding the previous weight: a weight <= 0
+                                      switches the term off (``use_anti = args.loss_anti > 0``) and the new weight is
+                                      written back into them
+           On return reg["out"] holds loss_anti / loss_stable (device scalars) and grad_anti / grad_stable.
     Returns the per-term loss tensors (device scalars; under DP the local shard's contribution summed over ranks).
     """
     L = _native.lib()
@@ -431,9 +508,32 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None):
         if all(net is not n for n in seen):
             g.zero_()
         grads.append(g)
+    rout = None
+    if reg is not None and (reg.get("anti") is not None or reg.get("stable") is not None):
+        rnet = reg["net"]
+        N = reg["a"].shape[0]
+        rout = reg_losses_native(rnet, reg["s"], reg["a"], reg["t"], reg["probe"], anti=reg.get("anti") is not None,
+                                 stable=reg.get("stable") is not None, need_grad=True, mean_divisor=N * ws)
+        reg["out"] = rout
     if world is not None and ws > 1:
         from ..dist import allreduce_flat
 
-        allreduce_flat(grads, losses, world[0])
+        extra_g = [] if rout is None else [rout[k] for k in ("grad_anti", "grad_stable") if k in rout]
+        extra_l = [] if rout is None else [rout[k] for k in ("loss_anti", "loss_stable") if k in rout]
+        allreduce_flat(grads + extra_g, losses + extra_l, world[0])
+    if rout is not None:
+        target = reg["net"].flat_grad()
+        for key in ("anti", "stable"):
+            spec = reg.get(key)
+            if spec is None:
+                continue
+            g_reg, l_reg, gate = rout["grad_" + key], rout["loss_" + key], reg.get("gate_" + key)
+            if isinstance(spec, torch.Tensor):
+                _axpy(target, g_reg, 1.0, num=spec.reshape(-1), gate=gate, coef_out=gate)
+            elif isinstance(spec, tuple) and spec[0] == "warmup":
+                _axpy(target, g_reg, float(spec[1]), num=losses[0], den=l_reg.reshape(-1), eps=float(spec[2]),
+                      gate=gate, coef_out=gate)
+            else:
+                _axpy(target, g_reg, float(spec), gate=gate, coef_out=gate)
     opt.step_flat(grads, max_norm)
     return [l.reshape(()) for l in losses]

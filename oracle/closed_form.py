@@ -299,6 +299,121 @@ def fm_loss_and_grad(spec: NetSpec, flat, s, a0, role: str, t, noise, eps_unused
 
 
 # --------------------------------------------------------------------------------------------------
+# f1: anti-divergence and Jacobian-stability regularisers  (flowril.py:255-264; pretrain.py:55-59, :163-177)
+# --------------------------------------------------------------------------------------------------
+def reg_losses_and_grads(spec: NetSpec, flat, s, a, t, probe, dtype=np.float64):
+    """The two regularisers of the scrf reward model on the mixed (expert + agent) batch and their gradients.
+
+      loss_anti   = mean_b ( v^T J_r v )^2            J_r = d tanh(head_r) / d a     (flowril.py:262, _hutch_div k=1)
+      loss_stable = mean_b || J_{v_c + r}^T v ||^2                                   (flowril.py:263, pretrain.py:55-59)
+
+    with v = probe [N, a] (the reference draws the same shape-deterministic `_rademacher` matrix for both),
+    evaluated at (a, s, t) with t = torch.rand(N, 1) (flowril.py:259 -- no eps rescale).
+
+    The reference differentiates these through autograd's double backward.  Restated by hand (ReLU has zero second
+    derivative a.e., so only tanh'' and the weights' bilinear terms survive):
+
+      anti:    forward tangent u_l = D_l W_l u_{l-1} (u_0 = v on the action columns), w = W_r u_L,
+               q = sum_j v_j tau_j w_j with tau = 1 - r^2; adjoints: g_w = dq * v * tau back through the tangent
+               chain (weight grads = outer products with u_{l-1}); g_rho = dq * v * w * (-2 r tau) back through the
+               primal chain (ordinary MLP backward).
+      stable:  reverse chain mu_L = W_c^T v + W_r^T (v * tau), nu_l = D_l mu_l, mu_{l-1} = W_l^T nu_l,
+               g = A_1^T nu_1 (A_1 = action columns of W_1), p = |g|^2; its adjoint is a FORWARD tangent pass
+               mubar_0 = dp * 2 g, nubar_l = W_l mubar_{l-1}, mubar_l = D_l nubar_l with weight grads
+               nu_l (outer) mubar_{l-1}; heads: dW_c += v (outer) mubar_L, dW_r += (v tau) (outer) mubar_L,
+               g_rho = v * (W_r mubar_L) * (-2 r tau) back through the primal chain.
+
+    Returns (loss_anti, loss_stable, grad_anti_flat, grad_stable_flat).  Requires n_heads == 2.
+    """
+    assert spec.n_heads == 2, "the regularisers exist only for the coupled-residual (scrf) model"
+    flat = np.asarray(flat, dtype=dtype)
+    s = np.asarray(s, dtype=dtype)
+    a = np.asarray(a, dtype=dtype)
+    t = np.asarray(t, dtype=dtype).reshape(-1, 1)
+    v = np.asarray(probe, dtype=dtype)
+    N, A = a.shape
+    depth = max(1, spec.depth)
+    trunk, heads = _layers(spec, flat)
+    (Wc, bc), (Wr, br) = heads
+    names = [n for n, _ in spec.shapes()]
+
+    # primal + tangent forward
+    x = np.concatenate([a, s, t], axis=1)
+    hs, us, masks = [x], [None], []
+    u = None
+    for li, (W, b) in enumerate(trunk):
+        z = hs[-1] @ W.T + b
+        m = z > 0
+        zt = (v @ W[:, :A].T) if li == 0 else (u @ W.T)
+        u = np.where(m, zt, 0.0)
+        masks.append(m)
+        hs.append(np.where(m, z, 0.0))
+        us.append(u)
+    hL, uL = hs[-1], us[-1]
+    r = np.tanh(hL @ Wr.T + br)
+    tau = 1.0 - r * r
+    dtau_drho = -2.0 * r * tau
+
+    def primal_backward(g_rho, grads):
+        """ordinary MLP backward from a cotangent on the head_r pre-activation"""
+        grads[names[2 * depth + 2]] += g_rho.T @ hL
+        grads[names[2 * depth + 3]] += g_rho.sum(axis=0)
+        dh = g_rho @ Wr
+        for li in reversed(range(depth)):
+            dz = np.where(masks[li], dh, 0.0)
+            grads[names[2 * li]] += dz.T @ hs[li]
+            grads[names[2 * li + 1]] += dz.sum(axis=0)
+            if li > 0:
+                dh = dz @ trunk[li][0]
+
+    def zero_grads():
+        return {n: np.zeros(shape, dtype=dtype) for n, shape in spec.shapes()}
+
+    # ---- anti ----
+    w = uL @ Wr.T
+    q = (v * tau * w).sum(axis=1)
+    loss_anti = float((q * q).mean())
+    ga = zero_grads()
+    dq = (2.0 / N) * q[:, None]
+    g_w = dq * v * tau
+    ga[names[2 * depth + 2]] += g_w.T @ uL
+    du = g_w @ Wr
+    for li in reversed(range(depth)):
+        dzt = np.where(masks[li], du, 0.0)
+        if li == 0:
+            ga[names[0]][:, :A] += dzt.T @ v
+        else:
+            ga[names[2 * li]] += dzt.T @ us[li]
+            du = dzt @ trunk[li][0]
+    primal_backward(dq * v * w * dtau_drho, ga)
+
+    # ---- stable ----
+    mu = v @ Wc + (v * tau) @ Wr
+    nus = [None] * depth
+    for li in reversed(range(depth)):
+        nus[li] = np.where(masks[li], mu, 0.0)
+        if li > 0:
+            mu = nus[li] @ trunk[li][0]
+    g = nus[0] @ trunk[0][0][:, :A]
+    loss_stable = float((g * g).sum(axis=1).mean())
+    gs = zero_grads()
+    mubar = (2.0 / N) * g                       # [N, A]
+    gs[names[0]][:, :A] += nus[0].T @ mubar
+    nubar = mubar @ trunk[0][0][:, :A].T
+    mubar = np.where(masks[0], nubar, 0.0)
+    for li in range(1, depth):
+        gs[names[2 * li]] += nus[li].T @ mubar
+        nubar = mubar @ trunk[li][0].T
+        mubar = np.where(masks[li], nubar, 0.0)
+    gs[names[2 * depth]] += v.T @ mubar
+    gs[names[2 * depth + 2]] += (v * tau).T @ mubar
+    primal_backward(v * (mubar @ Wr.T) * dtau_drho, gs)
+
+    cat = lambda d: np.concatenate([d[n].ravel() for n in names]).astype(dtype)
+    return loss_anti, loss_stable, cat(ga), cat(gs)
+
+
+# --------------------------------------------------------------------------------------------------
 # a8: clip_grad_norm_ + Adam  (flowril.py:324-330; torch.nn.utils.clip_grad_norm_, torch.optim.Adam defaults)
 # --------------------------------------------------------------------------------------------------
 def clip_coef(grad, max_norm: float, trainable=None):
@@ -329,21 +444,41 @@ def adam_step(flat, grad, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, ep
 
 
 def train_step(spec: NetSpec, flat, m, v, step, batches, lr, max_norm, rates=(1.0, 1.0), trainable=None,
-               dtype=np.float64):
-    """One reward-model update as flowril.py:311-335 does it for scrf without regularisers:
-    loss = rate_E * L(role expert batch) + rate_A * L(role agent batch); clip; Adam.
-    batches = [(role, s, a0, t, noise), ...] in the order the losses are summed."""
+               dtype=np.float64, reg=None):
+    """One reward-model update as flowril.py:311-335 does it for scrf:
+    loss = rate_E * L(role expert batch) + rate_A * L(role agent batch) [+ w_anti * L_anti + w_stable * L_stable];
+    clip; Adam.  batches = [(role, s, a0, t, noise), ...] in the order the losses are summed.
+
+    reg (flowril.py:255-284): dict(s, a, t, probe, anti=spec, stable=spec) on the mixed batch, spec = None (off),
+    a float (fixed weight) or ("warmup", scale, eps) for w = L_E / (L_reg + eps) * scale with L_E the first loss.
+    With reg the return value gains (loss_anti, loss_stable, w_anti, w_stable) as a fifth element."""
     total = np.zeros_like(flat, dtype=dtype)
     losses = []
     for (role, s, a0, t, noise), rate in zip(batches, rates):
         l, g = fm_loss_and_grad(spec, flat, s, a0, role, t, noise, dtype=dtype)
         losses.append(l)
         total += rate * g
+    reg_out = None
+    if reg is not None:
+        la, ls, ga, gs = reg_losses_and_grads(spec, flat, reg["s"], reg["a"], reg["t"], reg["probe"], dtype=dtype)
+        ws = []
+        for sp, l_reg, g_reg in ((reg.get("anti"), la, ga), (reg.get("stable"), ls, gs)):
+            if sp is None:
+                w = 0.0
+            elif isinstance(sp, tuple):
+                w = losses[0] / (l_reg + sp[2]) * sp[1]
+            else:
+                w = float(sp)
+            total += w * g_reg
+            ws.append(w)
+        reg_out = (la, ls, ws[0], ws[1])
     if trainable is not None:
         total = np.where(trainable, total, 0.0)
     coef, norm = clip_coef(total, max_norm, trainable)
     total = total * coef
     flat, m, v = adam_step(np.asarray(flat, dtype=dtype), total, m, v, step, lr, trainable=trainable)
+    if reg is not None:
+        return flat, m, v, losses, norm, reg_out
     return flat, m, v, losses, norm
 
 

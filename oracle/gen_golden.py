@@ -13,6 +13,8 @@ What is pinned (reference call sites in brackets):
                   the reference with basis-vector probes.
   vfield_*.npz    CoupledResidualFM.v_field / ConditionalVNet.forward [pretrain.py:156-158, networks.py:23-25,46-49]
   fmloss_*.npz    fm_loss value and autograd gradients [pretrain.py:179-190, :94-109] with t / noise injected
+  reg_*.npz       the anti-divergence / Jacobian-stability regularisers [flowril.py:257-263 -> pretrain.py:163-177,
+                  :55-59] and their double-backward parameter gradients; trainreg_*.npz: the update loop with them.
   train_*.npz     the update loop of flowril.py:311-335 (zero_grad, backward, clip_grad_norm_, Adam.step) for
                   scrf (all params), scrf fine-tune (head_r only, flowril.py:52-63) and 2fs; loss curves + final
                   parameters.
@@ -237,6 +239,147 @@ def gen_train(P):
         print("wrote", name, curve[0], curve[-1])
 
 
+def ref_reg_losses(P, model, s, a, t, probe):
+    """loss_anti / loss_stable exactly as flowril.py:257-263 forms them (the probe is injected through
+    `_rademacher`, which both `_hutch_div` and `_jacobian_frobenius` call)."""
+    import torch
+
+    st, tt = torch.from_numpy(s), torch.from_numpy(t)
+    mix_a = torch.from_numpy(a).detach().requires_grad_(True)
+    with ref_shim.injected_randomness(P, probes=[torch.from_numpy(probe)]):
+        v_c, r = model.net(mix_a, st, tt)
+        loss_anti = model._hutch_div(mix_a, r, k=1).square().mean()
+        loss_stable = P._jacobian_frobenius(mix_a, v_c + r).mean()
+    return loss_anti, loss_stable
+
+
+def gen_reg(P):
+    """reg_*.npz: the two regulariser losses and their autograd (double-backward) parameter gradients."""
+    import torch
+
+    cases = [("hopper", 128, True), ("sine", 128, True), ("maze", 256, False), ("halfcheetah", 256, False),
+             ("ant", 256, False), ("hand", 256, False)]
+    for idx, (task, hidden, store_grad) in enumerate(cases):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        spec = cf.NetSpec(s_dim, a_dim, hidden, 4, 2)
+        seed, N = 5000 + idx, 192
+        flat = cf.make_params(spec, seed, 2.0)
+        model = build_ref(P, spec, flat)
+        s, a = synth.states_actions(seed, N, s_dim, a_dim)
+        t = synth.rng(seed + 1).random((N, 1), dtype=np.float32)
+        probe = synth.rademacher(seed + 2, (N, a_dim))
+        la, ls = ref_reg_losses(P, model, s, a, t, probe)
+        params = list(model.parameters())
+        out = {"meta": np.array([s_dim, a_dim, hidden, 4, 2, 0, N, seed]), "gain": np.float32(2.0),
+               "loss_anti": np.float32(la.item()), "loss_stable": np.float32(ls.item())}
+        for name, loss in (("anti", la), ("stable", ls)):
+            gs = torch.autograd.grad(loss, params, retain_graph=True, allow_unused=True)
+            g = np.concatenate([(g_ if g_ is not None else torch.zeros_like(p_)).numpy().ravel()
+                                for g_, p_ in zip(gs, params)]).astype(np.float32)
+            out[f"normsum_{name}"] = np.float32(sum(g_.norm().item() for g_ in gs if g_ is not None))  # networks.py:111
+            norms, off = [], 0
+            for _, shape in spec.shapes():
+                n = int(np.prod(shape))
+                norms.append(np.sqrt((g[off:off + n].astype(np.float64) ** 2).sum()))
+                off += n
+            out[f"tensor_gradnorms_{name}"] = np.array(norms, np.float32)
+            if store_grad:
+                out[f"grad_{name}"] = g
+        name = f"reg_{idx:02d}_{task}_scrf_h{hidden}.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print("wrote", name, out["loss_anti"], out["loss_stable"])
+
+
+def gen_train_reg(P):
+    """trainreg_*.npz: the scrf update of flowril.py:251-284 + :311-330 WITH the regularisers in the warm-up weighting
+    (the only branch the reference's control flow reaches, see modril_b200/flowril/flowril.py) and with fixed
+    weights (params_autotune false, flowril.py:266-270)."""
+    import torch
+
+    for idx, (task, hidden, steps, lr, mode) in enumerate((
+            ("hopper", 128, 300, 1e-3, "warmup"),
+            ("sine", 128, 100, 1e-3, "fixed"),
+    )):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        spec = cf.NetSpec(s_dim, a_dim, hidden, 4, 2)
+        seed, B = 6000 + idx, 128
+        model = build_ref(P, spec, cf.make_params(spec, seed, 1.0))
+        params = list(model.parameters())
+        opt = torch.optim.Adam(params, lr=lr)
+        pool_s, _ = synth.states_actions(seed + 1, 4096, s_dim, a_dim)
+        pool_aE = synth.expert_actions(seed + 2, pool_s, a_dim)
+        pool_aA = np.clip(synth.rng(seed + 3).standard_normal((4096, a_dim)), -1, 1).astype(np.float32)
+        probe = synth.rademacher(seed + 4, (2 * B, a_dim))  # the reference's probe is the same matrix every step
+        curve = np.zeros((steps, 4), np.float32)
+        weights = np.zeros((steps, 2), np.float32)
+        norms = np.zeros(steps, np.float32)
+        w_fixed = (1e-4, 1e-6)  # --loss-anti / --loss-stable defaults (flowril.py:566-567)
+        for it in range(steps):
+            g = synth.rng(seed + 100 + it)
+            iE, iA = g.integers(0, 4096, B), g.integers(0, 4096, B)
+            _, nE, tE = synth.cfm_draws(seed + 10000 + 2 * it, B, a_dim, return_u=True)
+            _, nA, tA = synth.cfm_draws(seed + 10001 + 2 * it, B, a_dim, return_u=True)
+            t_mix = synth.rng(seed + 70000 + it).random((2 * B, 1), dtype=np.float32)
+            lE = ref_fm_loss(P, model, spec, pool_s[iE], pool_aE[iE], "expert", tE, nE)
+            lA = ref_fm_loss(P, model, spec, pool_s[iA], pool_aA[iA], "agent", tA, nA)
+            flow_loss = 1.0 * lE + 1.0 * lA
+            mix_s = np.concatenate([pool_s[iE], pool_s[iA]])
+            mix_a = np.concatenate([pool_aE[iE], pool_aA[iA]])
+            l_anti, l_st = ref_reg_losses(P, model, mix_s, mix_a, t_mix, probe)
+            if mode == "warmup":  # flowril.py:272-284 with eps 1e-8, global_scale 1e-3 (flowril.py:118-119)
+                w_anti = lE.detach() / (l_anti.detach() + 1e-8) * 1e-3
+                w_st = lE.detach() / (l_st.detach() + 1e-8) * 1e-3
+            else:
+                w_anti, w_st = torch.tensor(w_fixed[0]), torch.tensor(w_fixed[1])
+            flow_loss = flow_loss + w_anti * l_anti + w_st * l_st
+            opt.zero_grad()
+            flow_loss.backward()
+            norms[it] = float(torch.nn.utils.clip_grad_norm_(params, 1.0))
+            opt.step()
+            curve[it] = (lE.item(), lA.item(), l_anti.item(), l_st.item())
+            weights[it] = (float(w_anti), float(w_st))
+        out = {"meta": np.array([s_dim, a_dim, hidden, 4, 2, steps, B, seed]), "lr": np.float32(lr), "curve": curve,
+               "weights": weights, "gradnorm": norms, "mode": np.array(0 if mode == "warmup" else 1),
+               "final_params_0": np.concatenate([p.detach().numpy().ravel() for p in params])}
+        name = f"trainreg_{idx:02d}_{task}_scrf_{mode}_h{hidden}_{steps}steps.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print("wrote", name, curve[0], curve[-1], weights[0], weights[-1])
+
+
+def gen_gradnorm():
+    """gradnorm_00.npz: trajectory of the reference's GradNorm2D (networks.py:52-138; the file needs only torch and
+    math, so it is loaded directly) on a toy pair of losses whose parameter gradients are known in closed form."""
+    import importlib.util
+
+    import torch
+
+    sp = importlib.util.spec_from_file_location("ref_networks",
+                                                os.path.join(ref_shim.REFERENCE_ROOT, "modril/flowril/networks.py"))
+    mod = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(mod)
+    gn = mod.GradNorm2D(beta_init=1e-4, gamma_init=1e-6, alpha=0.1, warmup_steps=20, update_freq=5, ema_decay=0.9,
+                        beta_min=1e-8, beta_max=1e1, gamma_min=1e-12, gamma_max=1e-2)
+    p1 = torch.nn.Parameter(torch.tensor([1.0, -2.0, 0.5]))
+    p2 = torch.nn.Parameter(torch.tensor([[0.3, 0.7]]))
+    g = synth.rng(42)
+    steps = 120
+    ca = g.uniform(0.5, 2.0, steps).astype(np.float32)
+    cb = g.uniform(0.1, 5.0, steps).astype(np.float32)
+    traj, regs = np.zeros((steps, 2)), np.zeros((steps, 3))
+    for k in range(steps):
+        la = float(ca[k]) * ((p1 ** 2).sum() + (p2 ** 2).sum())
+        lj = float(cb[k]) * ((p1 ** 4).sum() + p2.abs().sum())
+        reg, beta, gamma = gn(la, lj)
+        gn.update(la, lj, [p1, p2])
+        traj[k] = (float(gn.log_beta), float(gn.log_gamma))
+        regs[k] = (float(reg), float(beta), float(gamma))
+    np.savez_compressed(os.path.join(OUT, "gradnorm_00.npz"), ca=ca, cb=cb, traj=traj, regs=regs,
+                        L0=np.array([float(gn.L0_anti), float(gn.L0_jpen)]),
+                        ema=np.array([float(gn.ema_g_anti), float(gn.ema_g_jpen)]),
+                        step_count=np.array(int(gn.step_count)))
+    print("wrote gradnorm_00.npz", traj[-1])
+
+
 def main():
     import torch
 
@@ -244,7 +387,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     P = ref_shim.load()
-    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train"]
+    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm"]
     if "logprob" in which:
         gen_logprob(P)
     if "vfield" in which:
@@ -253,6 +396,12 @@ def main():
         gen_fmloss(P)
     if "train" in which:
         gen_train(P)
+    if "reg" in which:
+        gen_reg(P)
+    if "trainreg" in which:
+        gen_train_reg(P)
+    if "gradnorm" in which:
+        gen_gradnorm()
 
 
 if __name__ == "__main__":

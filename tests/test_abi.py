@@ -33,7 +33,8 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.frl_abi_version() == 1
+    from modril_b200 import _native
+    assert lib.frl_abi_version() == _native.ABI_VERSION == 2
     assert isinstance(lib.frl_last_error(), bytes)
 
 

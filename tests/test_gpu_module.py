@@ -190,10 +190,73 @@ def test_full_update_loop_and_checkpoint_roundtrip():
     assert torch.equal(mod2.flow_net.net.flat_params(), mod.flow_net.net.flat_params())
 
 
-def test_regularisers_raise_until_implemented():
-    args = make_args(enable_loss_anti=True, enable_loss_stable=True)
-    with pytest.raises(NotImplementedError):
-        make_module(args)
+@pytest.mark.parametrize("autotune", [True, False])
+def test_update_with_default_regularisers_matches_oracle(autotune):
+    """Default flags of the reference (--enable-loss-anti/-stable true, --params_autotune true, flowril.py:563-567):
+    the anti-divergence and Jacobian-stability terms join the update with the warm-up weights
+    L_E / (L_reg + 1e-8) * 1e-3 (flowril.py:272-284); with --params_autotune false the fixed --loss-anti /
+    --loss-stable weights (flowril.py:266-270).  Replayed through the float64 oracle with the same draws."""
+    from modril_b200.flowril import _rademacher
+    args = make_args(num_steps=4, num_processes=8, traj_batch_size=16, enable_loss_anti=True, enable_loss_stable=True,
+                     params_autotune=autotune)
+    mod = make_module(args)
+    storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 9, args.device)
+    spec = cf.NetSpec(11, 3, 128, 4, 2)
+    flat = mod.flow_net.net.flat_params().cpu().numpy().astype(np.float64)
+    m, v = np.zeros_like(flat), np.zeros_like(flat)
+    state_cpu, state_cuda = torch.get_rng_state(), torch.cuda.get_rng_state()
+    log_vals = mod._update_reward_func(storage)
+    torch.set_rng_state(state_cpu)
+    torch.cuda.set_rng_state(state_cuda)
+    probe = _rademacher((32, 3), device=args.device).cpu().numpy()
+    losses_ref, step, w = [], 0, None
+    for demo, roll in zip(mod.expert_train_loader, storage.get_generator(None, mini_batch_size=16)):
+        batches = []
+        for role, s, a in (("expert", roll["state"], roll["action"]), ("agent", demo["state"], demo["actions"])):
+            B = a.shape[0]
+            t = torch.rand(B, 1, device=args.device) * (1 - 2e-3) + 1e-3
+            noise = torch.distributions.Normal(0., 1.).sample((B, 3))
+            batches.append((role, s.cpu().numpy(), a.cpu().numpy(), t.cpu().numpy(), noise.numpy()))
+        t_mix = torch.rand(32, 1, device=args.device).cpu().numpy()
+        warm = ("warmup", 1e-3, 1e-8)
+        reg = dict(s=np.concatenate([batches[0][1], batches[1][1]]), a=np.concatenate([batches[0][2], batches[1][2]]),
+                   t=t_mix, probe=probe, anti=warm if autotune else 1e-4, stable=warm if autotune else 1e-6)
+        step += 1
+        flat, m, v, losses, _, (la, ls, wa, wst) = cf.train_step(spec, flat, m, v, step, batches, lr=args.disc_lr,
+                                                                  max_norm=1.0, reg=reg)
+        losses_ref.append(losses)
+        w = (wa, wst)
+    assert step == 2
+    ref = np.mean(np.array(losses_ref), axis=0)
+    assert abs(log_vals["flow_loss"] - ref[0]) <= 1e-4 * max(1, abs(ref[0]))
+    assert abs(log_vals["agent_loss"] - ref[1]) <= 1e-4 * max(1, abs(ref[1]))
+    got = mod.flow_net.net.flat_params().cpu().numpy()
+    assert np.abs(got - flat).max() <= 1e-5, np.abs(got - flat).max()
+    # args.loss_anti / args.loss_stable hold the weights last used, like the reference (flowril.py:278, :283)
+    assert abs(float(mod.args.loss_anti) - w[0]) <= 1e-3 * w[0]
+    assert abs(float(mod.args.loss_stable) - w[1]) <= 1e-3 * w[1]
+    if autotune:  # reference quirk: step_count never advances from _compute_flow_loss, warm-up is what runs
+        assert int(mod.gradnorm.step_count) == 0
+
+
+def test_gradnorm_branch_runs_when_step_count_is_past_warmup():
+    """The GradNorm2D branch of flowril.py:286-290 (not reachable through the reference's own control flow, see the
+    module docstring): beta / gamma weight the regulariser gradients and update() consumes the per-tensor norm sums."""
+    args = make_args(num_steps=4, num_processes=8, traj_batch_size=16, enable_loss_anti=True, enable_loss_stable=True,
+                     params_autotune=True)
+    mod = make_module(args)
+    mod.gradnorm.step_count.fill_(mod.gradnorm.warmup_steps + 9)   # next forward() makes it a multiple of update_freq
+    mod.gradnorm.L0_anti.fill_(1.0)
+    mod.gradnorm.L0_jpen.fill_(1.0)
+    storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 9, args.device)
+    lb, lg = float(mod.gradnorm.log_beta), float(mod.gradnorm.log_gamma)
+    before = mod.flow_net.net.flat_params().clone()
+    mod._update_reward_func(storage)
+    assert int(mod.gradnorm.step_count) == mod.gradnorm.warmup_steps + 11
+    assert float(mod.gradnorm.log_beta) != lb and float(mod.gradnorm.log_gamma) != lg
+    assert float(mod.gradnorm.ema_g_anti) > 0 and float(mod.gradnorm.ema_g_jpen) > 0
+    assert not torch.equal(before, mod.flow_net.net.flat_params())
+    assert abs(float(mod.args.loss_anti) - np.exp(lb)) <= 1e-6 * np.exp(lb) or float(mod.args.loss_anti) > 0
 
 
 def test_2fs_option_runs_and_freezes_expert_net(tmp_path):

@@ -135,3 +135,33 @@ def test_oracle_training_curve_vs_reference_golden(golden_dir):
             [("expert", pool_s[iE], pool_aE[iE], tE, nE), ("agent", pool_s[iA], pool_aA[iA], tA, nA)],
             lr=float(g["lr"]), max_norm=1.0, trainable=trainable)
         assert np.allclose(losses, g["curve"][it], rtol=2e-4), (it, losses, g["curve"][it])
+
+
+def test_gradnorm2d_mirror_follows_the_reference_trajectory(golden_dir):
+    """modril_b200's GradNorm2D (host-side scalar logic) against a trajectory of the reference's class
+    (networks.py:52-138; fixture from oracle/gen_golden.py gen_gradnorm).  The reference obtains the two gradient-norm
+    sums with autograd; here they are passed in (closed form for the toy losses of the fixture)."""
+    import os
+
+    import torch
+
+    from modril_b200.flowril.networks import GradNorm2D
+
+    g = np.load(os.path.join(golden_dir, "gradnorm_00.npz"))
+    gn = GradNorm2D(beta_init=1e-4, gamma_init=1e-6, alpha=0.1, warmup_steps=20, update_freq=5, ema_decay=0.9,
+                    beta_min=1e-8, beta_max=1e1, gamma_min=1e-12, gamma_max=1e-2)
+    p1, p2 = np.array([1.0, -2.0, 0.5]), np.array([0.3, 0.7])
+    n_anti = np.linalg.norm(2 * p1) + np.linalg.norm(2 * p2)          # sum of per-tensor norms (networks.py:111)
+    n_jpen = np.linalg.norm(4 * p1 ** 3) + np.linalg.norm(np.sign(p2))
+    va, vj = (p1 ** 2).sum() + (p2 ** 2).sum(), (p1 ** 4).sum() + np.abs(p2).sum()
+    for k in range(len(g["ca"])):
+        ca, cb = float(g["ca"][k]), float(g["cb"][k])
+        la, lj = torch.tensor(ca * va, dtype=torch.float32), torch.tensor(cb * vj, dtype=torch.float32)
+        reg, beta, gamma = gn(la, lj)
+        gn.update(la, lj, None, g_anti=ca * n_anti, g_jpen=cb * n_jpen)
+        assert abs(float(gn.log_beta) - g["traj"][k, 0]) <= 2e-5 and abs(float(gn.log_gamma) - g["traj"][k, 1]) <= 2e-5, k
+        assert np.allclose([float(reg), float(beta), float(gamma)], g["regs"][k], rtol=1e-4)
+    assert int(gn.step_count) == int(g["step_count"])
+    assert np.allclose([float(gn.L0_anti), float(gn.L0_jpen)], g["L0"], rtol=1e-5)
+    assert np.allclose([float(gn.ema_g_anti), float(gn.ema_g_jpen)], g["ema"], rtol=1e-4)
+    assert set(gn.state_dict()) == {"log_beta", "log_gamma", "step_count", "L0_anti", "L0_jpen", "ema_g_anti", "ema_g_jpen"}

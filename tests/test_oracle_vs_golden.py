@@ -104,3 +104,30 @@ def test_fmloss(path):
             ref = g[f"grad_{role}"]
             scale = np.abs(ref).max()
             assert np.abs(grad - ref).max() <= 2e-5 * scale, np.abs(grad - ref).max() / scale
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "reg_*.npz"))), ids=os.path.basename)
+def test_regularisers(path):
+    """Anti-divergence / Jacobian-stability losses and their hand-derived gradients (cf.reg_losses_and_grads) against
+    the reference's autograd double-backward (flowril.py:257-263)."""
+    g = np.load(path)
+    spec = _spec(g["meta"])
+    N, seed = int(g["meta"][6]), int(g["meta"][7])
+    flat = cf.make_params(spec, seed, float(g["gain"]))
+    s, a = synth.states_actions(seed, N, spec.s_dim, spec.a_dim)
+    t = synth.rng(seed + 1).random((N, 1), dtype=np.float32)
+    probe = synth.rademacher(seed + 2, (N, spec.a_dim))
+    la, ls, ga, gs = cf.reg_losses_and_grads(spec, flat, s, a, t, probe)
+    _close(np.array(la), g["loss_anti"], 2e-5, "loss_anti")
+    _close(np.array(ls), g["loss_stable"], 2e-5, "loss_stable")
+    for name, grad in (("anti", ga), ("stable", gs)):
+        norms, off = [], 0
+        for _, shape in spec.shapes():
+            n = int(np.prod(shape))
+            norms.append(np.sqrt((grad[off:off + n] ** 2).sum()))
+            off += n
+        assert np.allclose(norms, g[f"tensor_gradnorms_{name}"], rtol=2e-4, atol=1e-6), (name, norms)
+        assert abs(sum(norms) - g[f"normsum_{name}"]) <= 2e-4 * g[f"normsum_{name}"]
+        if f"grad_{name}" in g:
+            ref = g[f"grad_{name}"]
+            assert np.abs(grad - ref).max() <= 5e-5 * np.abs(ref).max(), np.abs(grad - ref).max() / np.abs(ref).max()
