@@ -150,6 +150,17 @@ int frl_grad_axpy(float* y_dev, const float* x_dev, long long n, float alpha, co
                   const float* den_dev, float eps, const float* gate_dev, float* coef_out_dev, int device,
                   void* stream);
 
+/* Return normalisation of FlowMatchingEstimation._get_reward (flowril.py:221-228) for a whole rollout in one launch:
+ * for t in 0..T-1:  returns = returns * masks[t] * gamma + reward[t];  RunningMeanStd.update(returns)
+ * (float32 moments, rlf/baselines/common/running_mean_std.py:3-35);  out[t] = reward[t] / sqrt(var + 1e-8).
+ * reward_dev / masks_dev / out_dev are [T, N]; returns_io_dev [N] carries the discounted returns between calls
+ * (returns_valid == 0 on the very first call: returns starts as reward[0], flowril.py:222-223);
+ * rms_mean_var_dev [2] = {mean, var} (initially {0, 1}) and rms_count_dev [1] (double, initially 1e-4) carry the
+ * running moments.  Replaces T device->host syncs per update with none. */
+int frl_normalise_rewards(const float* reward_dev, const float* masks_dev, int T, int N, float gamma,
+                          float* returns_io_dev, int returns_valid, float* rms_mean_var_dev, double* rms_count_dev,
+                          float* out_dev, int device, void* stream);
+
 /* L2 norm of each parameter tensor's slice of a flat gradient: out_dev[i] = |flat[offsets[i] .. offsets[i+1])|.
  * GradNorm2D.update sums `g.norm()` over the parameter tensors of each regulariser's gradient
  * (networks.py:108-117).  offsets_host has n_tensors + 1 entries (n_tensors <= 20). */

@@ -229,6 +229,17 @@ extern "C" int frl_grad_axpy(float* y, const float* x, long long n, float alpha,
     return grad_axpy(y, x, n, alpha, num, den, eps, gate, coef_out, (cudaStream_t)stream);
 }
 
+extern "C" int frl_normalise_rewards(const float* reward, const float* masks, int T, int N, float gamma,
+                                     float* returns_io, int returns_valid, float* rms_mean_var, double* rms_count,
+                                     float* out, int device, void* stream) {
+    FRL_REQUIRE(reward && masks && returns_io && rms_mean_var && rms_count && out, "null pointer");
+    FRL_REQUIRE(T >= 0 && N >= 1, "T >= 0 and N >= 1");
+    if (T == 0) return FRL_OK;
+    FRL_CUDA(cudaSetDevice(device));
+    return normalise_returns(reward, masks, T, N, gamma, returns_io, returns_valid, rms_mean_var, rms_count, out,
+                             (cudaStream_t)stream);
+}
+
 extern "C" int frl_tensor_norms(const float* flat, const long long* offsets_host, int n_tensors, float* out,
                                 int device, void* stream) {
     FRL_REQUIRE(flat && offsets_host && out, "null pointer");

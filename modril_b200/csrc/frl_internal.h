@@ -110,4 +110,8 @@ int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double l
               double eps, double max_norm, float* norm_out, cudaStream_t stream);
 int tensor_norms(const float* flat, const long long* offsets_host, int n_tensors, float* out, cudaStream_t stream);
 
+// returns.cu
+int normalise_returns(const float* reward, const float* masks, int T, int N, float gamma, float* returns,
+                      int returns_valid, float* mean_var, double* count, float* out, cudaStream_t stream);
+
 }  // namespace frl

@@ -15,8 +15,10 @@ and for stand-alone use a minimal stand-in base class reproduces the part of ``B
 Differences in mechanism, not in results:
   * ``_get_reward(step, ...)`` is served from ONE fused launch over the whole rollout (T*N rows, both roles) made at
     the first step of an update; the log-density is a pure function of (s, a, weights, probe) and the weights do not
-    change between the steps of one update, so the rows are bit-identical to per-step scoring.  Only the return
-    normalisation stays a sequential scan (flowril.py:221-228).
+    change between the steps of one update, so the rows are bit-identical to per-step scoring.  The return
+    normalisation (flowril.py:221-228: discounted-return recursion, float32 RunningMeanStd, scaling) is a sequential
+    scan over the steps; it runs as ONE more launch (``frl_normalise_rewards``) with its state on the device, so an
+    update does no device->host copy for the rewards at all (the reference does one per step).
   * ``_update_reward_func`` runs the all-native route (fused CFM gradient kernels + clip+Adam kernel) on the flat
     parameter buffer.
   * Reference quirk kept on purpose: ``_update_reward_func`` passes
@@ -144,6 +146,48 @@ except Exception:  # pragma: no cover - exercised in this repo's tests
     PPO = None
 
 
+class DeviceRunningMeanStd(object):
+    """The float32 running moments of rlf's RunningMeanStd (running_mean_std.py:3-35) kept ON THE DEVICE and advanced
+    by ``frl_normalise_rewards`` together with the discounted-return recursion (reference flowril.py:221-228), so the
+    reward hook needs no device->host copy per rollout step.  ``mean`` / ``var`` / ``count`` read the state back
+    (one sync) with the shapes the numpy object has after its first update (``var[0]`` works)."""
+
+    def __init__(self, device, epsilon=1e-4):
+        self.device = torch.device(device)
+        self.mean_var = torch.tensor([0.0, 1.0], device=self.device)
+        self.count_t = torch.tensor([epsilon], dtype=torch.float64, device=self.device)
+
+    @property
+    def mean(self):
+        return self.mean_var[:1].cpu().numpy()
+
+    @property
+    def var(self):
+        return self.mean_var[1:].cpu().numpy()
+
+    @property
+    def count(self):
+        return float(self.count_t.item())
+
+    def normalise(self, reward, masks, gamma, returns):
+        """reward / masks [T, N, 1] device tensors; returns: [N, 1] carried state or None (first call).
+        Returns (normalised reward [T, N, 1], new returns [N, 1])."""
+        from .. import _native
+        from .networks import _current_stream, _ptr, as_f32_cuda
+
+        T, N = reward.shape[0], reward.shape[1]
+        r = as_f32_cuda(reward, self.device, "reward").reshape(T, N)
+        m = as_f32_cuda(masks, self.device, "masks").reshape(T, N)
+        valid = returns is not None
+        ret = returns.detach().float().reshape(N).clone() if valid else torch.empty(N, device=self.device)
+        out = torch.empty(T, N, device=self.device)
+        _native.check(_native.lib().frl_normalise_rewards(_ptr(r), _ptr(m), T, N, float(gamma), _ptr(ret),
+                                                          1 if valid else 0, _ptr(self.mean_var), _ptr(self.count_t),
+                                                          _ptr(out), self.device.index or 0,
+                                                          _current_stream(self.device)), "frl_normalise_rewards")
+        return out.reshape(T, N, 1), ret.reshape(N, 1)
+
+
 def str2bool(v):
     return v.lower() == "true"
 
@@ -153,6 +197,7 @@ class FlowMatchingEstimation(BaseIRLAlgo):
         super().__init__()
         self.step = 0
         self._rollout_cache = None
+        self._norm_cache = None
 
     # ---- construction (reference flowril.py:34-121) -------------------------------------------------------------
     def _create_flow_net(self):
@@ -209,7 +254,7 @@ class FlowMatchingEstimation(BaseIRLAlgo):
         self.action_space = self.policy.action_space
         self._create_flow_net()
         self.returns = None
-        self.ret_rms = RunningMeanStd(shape=())
+        self.ret_rms = DeviceRunningMeanStd(self.args.device)
         self.eps = 1e-8
         self.global_scale = 1e-3
         self.precision = getattr(args, "flowril_precision", None)
@@ -289,11 +334,13 @@ class FlowMatchingEstimation(BaseIRLAlgo):
             return -torch.log1p(torch.exp(-r))
         raise ValueError(f"Unrecognized reward type {rt}")
 
+    def _batched(self):
+        return getattr(self.args, "flowril_batched_scoring", True) and self.args.option == "scrf"
+
     def _compute_flow_reward(self, storage, step, add_info):
         if self.args.reward_type not in ("raw", "norm", "exp", "clip", "smooth"):
             raise ValueError(f"Unrecognized reward type {self.args.reward_type}")
-        batched = getattr(self.args, "flowril_batched_scoring", True) and self.args.option == "scrf"
-        if not batched:
+        if not self._batched():
             state = self._trans_agent_state(storage.get_obs(step)).to(self.args.device)
             action = rutils.get_ac_repr(self.action_space, storage.actions[step].to(self.args.device))
             return self._reward_from(*self._score(state, action, self.args.reward_type))
@@ -308,21 +355,27 @@ class FlowMatchingEstimation(BaseIRLAlgo):
             le, la, rw = score_pair(ne, na, states.reshape(T * N, -1), actions.reshape(T * N, -1), probe, n_steps=32,
                                     reward_type=self.args.reward_type, precision=self.precision)
             self._rollout_cache = rw.reshape(T, N, 1)
+            self._norm_cache = None
         return self._rollout_cache[step]
 
     def _get_reward(self, step, storage, add_info):
-        masks = storage.masks[step]
         with torch.no_grad():
             for m in ((self.flow_net,) if self.args.option == "scrf" else (self.flow_net_e, self.flow_net_a)):
                 m.eval()
             reward = self._compute_flow_reward(storage, step, add_info)
-            if self.args.flowril_reward_norm:
-                if self.returns is None:
-                    self.returns = reward.clone()
-                self.returns = self.returns * masks * self.args.gamma + reward
-                self.ret_rms.update(self.returns.cpu().numpy())
-                return reward / np.sqrt(self.ret_rms.var[0] + 1e-8), {}
-            return reward, {}
+            if not self.args.flowril_reward_norm:
+                return reward, {}
+            # discounted-return recursion + running moments + scaling (reference flowril.py:221-228) on the device
+            if self._batched():
+                if self._norm_cache is None:
+                    T = self.args.num_steps
+                    masks = torch.stack([storage.masks[t].to(self.args.device) for t in range(T)])
+                    self._norm_cache, self.returns = self.ret_rms.normalise(self._rollout_cache, masks,
+                                                                            self.args.gamma, self.returns)
+                return self._norm_cache[step], {}
+            out, self.returns = self.ret_rms.normalise(reward.unsqueeze(0), storage.masks[step].unsqueeze(0),
+                                                       self.args.gamma, self.returns)
+            return out[0], {}
 
     def _compute_disc_val(self, state, action):
         state, action = state.to(self.args.device), action.to(self.args.device)

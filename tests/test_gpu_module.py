@@ -249,7 +249,7 @@ def test_gradnorm_branch_runs_when_step_count_is_past_warmup():
     mod.gradnorm.L0_anti.fill_(1.0)
     mod.gradnorm.L0_jpen.fill_(1.0)
     storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 9, args.device)
-    lb, lg = float(mod.gradnorm.log_beta), float(mod.gradnorm.log_gamma)
+    lb, lg = float(mod.gradnorm.log_beta.detach()), float(mod.gradnorm.log_gamma.detach())
     before = mod.flow_net.net.flat_params().clone()
     mod._update_reward_func(storage)
     assert int(mod.gradnorm.step_count) == mod.gradnorm.warmup_steps + 11
@@ -274,3 +274,23 @@ def test_2fs_option_runs_and_freezes_expert_net(tmp_path):
     assert not torch.equal(mod.flow_net_a.net.flat_params(), before_a)
     assert np.isfinite(logs["flow_loss"]) and np.isfinite(logs["agent_loss"])
     assert torch.isfinite(storage.rewards).all()
+
+
+@pytest.mark.parametrize("T,N", [(128, 32), (5, 1), (16, 3000), (1, 7)])
+def test_device_return_normalisation_vs_oracle(T, N):
+    """frl_normalise_rewards (one launch per rollout, state on the device) against the oracle's step-by-step numpy
+    restatement of flowril.py:221-228 + RunningMeanStd (float32), over two consecutive rollouts (state carry-over)."""
+    from modril_b200.flowril.flowril import DeviceRunningMeanStd
+    g = synth.rng(T * 1000 + N)
+    rms_dev = DeviceRunningMeanStd("cuda:0")
+    rms_ref, ret_ref, ret_dev = None, None, None
+    for call in range(2):
+        rew = (g.standard_normal((T, N, 1)) * 3 + 0.5).astype(np.float32)
+        masks = (g.random((T, N, 1)) > 0.1).astype(np.float32)
+        ref, ret_ref, rms_ref = cf.normalise_rewards(rew, masks, 0.99, rms_ref, ret_ref)
+        got, ret_dev = rms_dev.normalise(torch.from_numpy(rew).cuda(), torch.from_numpy(masks).cuda(), 0.99, ret_dev)
+        assert np.abs(got.cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
+        assert np.abs(ret_dev.cpu().numpy() - ret_ref).max() <= 1e-6 * max(1.0, np.abs(ret_ref).max())
+        assert abs(rms_dev.var[0] - rms_ref.var[0]) <= 2e-6 * rms_ref.var[0]
+        assert abs(rms_dev.mean[0] - rms_ref.mean[0]) <= 2e-6 * max(1.0, abs(rms_ref.mean[0]))
+        assert rms_dev.count == rms_ref.count
