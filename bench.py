@@ -324,29 +324,36 @@ def run_ours(args):
     opt = FusedAdam([model.net], lr=1e-4)
     grp = (dist.group.WORLD, world) if world > 1 else None
 
-    def tstep():
+    def tstep(prec_t):
         return train_step([dict(net=model.net, sign=1.0, s=ts, a0=ta, t=tt_[0], noise=zz[0]),
-                           dict(net=model.net, sign=-1.0, s=ts, a0=ta, t=tt_[1], noise=zz[1])], opt, 1.0, world=grp)
+                           dict(net=model.net, sign=-1.0, s=ts, a0=ta, t=tt_[1], noise=zz[1])], opt, 1.0, world=grp,
+                          precision=prec_t)
 
-    for _ in range(3):
-        tstep()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n_t = 10
-    e0.record()
-    for _ in range(n_t):
-        tstep()
-    e1.record()
-    barrier()
-    tms = torch.tensor([e0.elapsed_time(e1) / n_t], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    train_rate = world * 2 * Bt / (float(tms.item()) / 1e3)
+    train_rates = {}
+    for prec_t in ("fp32", "fp16"):
+        for _ in range(3):
+            tstep(prec_t)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_t = 10
+        e0.record()
+        for _ in range(n_t):
+            tstep(prec_t)
+        e1.record()
+        barrier()
+        tms = torch.tensor([e0.elapsed_time(e1) / n_t], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        train_rates[prec_t] = world * 2 * Bt / (float(tms.item()) / 1e3)
+    train_rate = train_rates["fp16"]
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    d_in_t = a_dim + s_dim + 1
+    f_fwd_train = 2 * (d_in_t * HIDDEN + (DEPTH - 1) * HIDDEN * HIDDEN + 2 * HIDDEN * a_dim)  # 3 F_fwd per row
 
     # ---- roofline of the dominant kernel (the fused integrator; the reward kernel is ~0.1 % of the step) ----
     flops = algorithmic_flops_per_sample(s_dim, a_dim, n_steps) * B
@@ -391,8 +398,12 @@ def run_ours(args):
         "parity": parity,
         "other_modes_samples_per_sec": extra,
         "train": {"metric": "cfm_train_samples_per_sec", "value": train_rate, "unit": "samples/s",
-                  "rows_per_step_per_gpu": 2 * Bt, "dtype": "fp32", "collective": "NCCL all-reduce of the flat grad"
-                  if world > 1 else "none"},
+                  "rows_per_step_per_gpu": 2 * Bt, "dtype": "fp16 operands / fp32 accumulate (tcgen05); fp32 clip + Adam",
+                  "step": "2 x frl_cfm_loss_grad_p (fwd + dgrad + wgrad) + [all-reduce] + frl_clip_adam + weight re-pack",
+                  "fp32_ffma_samples_per_sec": train_rates["fp32"],
+                  "algorithmic_tflops": train_rate * 3 * f_fwd_train / 1e12,
+                  "frac_of_peak": train_rate * 3 * f_fwd_train / 1e12 / measured_peak_tflops()[0],
+                  "collective": "NCCL all-reduce of the flat grad" if world > 1 else "none"},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FRL_ABI_VERSION 2
+#define FRL_ABI_VERSION 3
 #define FRL_MAX_STEPS 256
 #define FRL_MAX_DEPTH 8
 
@@ -126,6 +126,14 @@ int frl_score_host(frl_net* net_expert, frl_net* net_agent, const float* s_host,
 int frl_cfm_loss_grad(frl_net* net, float role_sign, const float* s_dev, const float* a0_dev, const float* t_dev,
                       const float* noise_dev, long long B, long long mean_divisor, float grad_scale,
                       int accumulate, float* loss_dev, float* grad_dev, void* stream);
+
+/* frl_cfm_loss_grad with a choice of arithmetic: FRL_PREC_FP32 (the call above) or FRL_PREC_FP16 -- the tcgen05
+ * tensor-core path: fp16 operands (weights, activations and back-propagated gradients are rounded to fp16 between
+ * layers; dL/dV is carried unscaled by 1/B so it stays O(1)), fp32 accumulation in TMEM, fp32 loss and gradient
+ * reduction in a fixed order (deterministic).  Same arguments and semantics otherwise. */
+int frl_cfm_loss_grad_p(frl_net* net, float role_sign, const float* s_dev, const float* a0_dev, const float* t_dev,
+                        const float* noise_dev, long long B, long long mean_divisor, float grad_scale,
+                        int accumulate, float* loss_dev, float* grad_dev, int precision, void* stream);
 
 /* Anti-divergence and Jacobian-stability regularisers of the coupled-residual (n_heads == 2) model with their
  * parameter gradients (flowril.py:255-264: `_hutch_div(mix_a, r, k=1).square().mean()` and

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libflowril_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3
 HAS_TC = True  # tensor-core (tcgen05) log-density kernels are built in
 PROBE_SHARED, PROBE_PER_STEP, PROBE_EXACT = 0, 1, 2
@@ -22,7 +22,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16
 EXPORTS = (
     "frl_abi_version", "frl_last_error", "frl_net_create", "frl_net_destroy", "frl_net_num_params",
     "frl_net_set_params", "frl_vfield", "frl_logprob", "frl_score", "frl_score_host", "frl_cfm_loss_grad",
-    "frl_clip_adam", "frl_reg_loss_grad", "frl_grad_axpy", "frl_tensor_norms", "frl_normalise_rewards",
+    "frl_clip_adam", "frl_reg_loss_grad", "frl_grad_axpy", "frl_tensor_norms", "frl_normalise_rewards", "frl_cfm_loss_grad_p",
 )
 
 
@@ -65,6 +65,7 @@ def lib():
     L.frl_score.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(f32), i32, i32, vp, vp, vp, ll, i32, vp]
     L.frl_score_host.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(f32), i32, i32, vp, vp, vp, ll, i32]
     L.frl_cfm_loss_grad.argtypes = [vp, f32, vp, vp, vp, vp, ll, ll, f32, i32, vp, vp, vp]
+    L.frl_cfm_loss_grad_p.argtypes = [vp, f32, vp, vp, vp, vp, ll, ll, f32, i32, vp, vp, i32, vp]
     L.frl_reg_loss_grad.argtypes = [vp, vp, vp, vp, vp, ll, ll, i32, vp, vp, vp, vp, vp]
     L.frl_grad_axpy.argtypes = [vp, vp, ll, f32, vp, vp, f32, vp, vp, i32, vp]
     L.frl_normalise_rewards.argtypes = [vp, vp, i32, i32, f32, vp, i32, vp, vp, vp, i32, vp]

@@ -207,6 +207,28 @@ extern "C" int frl_cfm_loss_grad(frl_net* net, float role_sign, const float* s, 
                              accumulate, loss, grad, (cudaStream_t)stream);
 }
 
+extern "C" int frl_cfm_loss_grad_p(frl_net* net, float role_sign, const float* s, const float* a0, const float* t,
+                                   const float* noise, long long B, long long mean_divisor, float grad_scale,
+                                   int accumulate, float* loss, float* grad, int precision, void* stream) {
+    if (precision == FRL_PREC_FP32)
+        return frl_cfm_loss_grad(net, role_sign, s, a0, t, noise, B, mean_divisor, grad_scale, accumulate, loss, grad, stream);
+    int rc = check_net(net);
+    if (rc != FRL_OK) return rc;
+    FRL_REQUIRE(s && a0 && t && noise, "null input");
+    FRL_REQUIRE(B > 0, "empty batch");
+    if (precision != FRL_PREC_FP16) {
+        set_error("frl_cfm_loss_grad_p: the tensor-core training path computes with fp16 operands (FRL_PREC_FP16)");
+        return FRL_ERR_UNSUPPORTED;
+    }
+    if (!net->pack_train) {
+        set_error("tensor-core training is not available for this net (a_dim too large)");
+        return FRL_ERR_UNSUPPORTED;
+    }
+    FRL_CUDA(cudaSetDevice(net->cfg.device));
+    return cfm_loss_grad_tc(net, role_sign >= 0.f ? 1.f : -1.f, s, a0, t, noise, B, mean_divisor, grad_scale,
+                            accumulate, loss, grad, (cudaStream_t)stream);
+}
+
 extern "C" int frl_reg_loss_grad(frl_net* net, const float* s, const float* a, const float* t, const float* probe,
                                  long long N, long long mean_divisor, int which, float* loss_anti, float* loss_stable,
                                  float* grad_anti, float* grad_stable, void* stream) {

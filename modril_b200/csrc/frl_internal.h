@@ -57,6 +57,10 @@ struct frl_net {
     void* pack_tc = nullptr;
     size_t pack_tc_bytes = 0;
     bool has_params = false;
+    // tensor-core training: fp16 weight images (train_tc.cu) and workspace
+    void* pack_train = nullptr;
+    void* ws_tc = nullptr;
+    size_t ws_tc_bytes = 0;
     // training workspace (grown on demand)
     float* ws = nullptr;
     size_t ws_floats = 0;
@@ -104,6 +108,12 @@ int reg_loss_grad_f32(frl_net* net, const float* s, const float* a, const float*
                       float* grad_stable, cudaStream_t stream);
 int grad_axpy(float* y, const float* x, long long n, float alpha, const float* num, const float* den, float eps,
               const float* gate, float* coef_out, cudaStream_t stream);
+
+// train_tc.cu
+int tc_train_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
+int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float* a0, const float* t, const float* noise,
+                     long long B, long long mean_divisor, float grad_scale, int accumulate, float* loss, float* grad,
+                     cudaStream_t stream);
 
 // adam.cu
 int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double lr, double beta1, double beta2,

@@ -126,6 +126,8 @@ extern "C" int frl_net_destroy(frl_net* net) {
     if (net->pack_f32) cudaFree(net->pack_f32);
     if (net->pack_tc) cudaFree(net->pack_tc);
     if (net->ws) cudaFree(net->ws);
+    if (net->pack_train) cudaFree(net->pack_train);
+    if (net->ws_tc) cudaFree(net->ws_tc);
     frl_host_stage_free(net);
     delete net;
     return FRL_OK;
@@ -171,6 +173,10 @@ extern "C" int frl_net_set_params(frl_net* net, const float* params_dev, void* s
     FRL_CUDA(cudaGetLastError());
     int rc = tc_pack(net, params_dev, st);
     if (rc != FRL_OK) return rc;
+    if (net->n_out_p <= 64) {   // fp16 GEMM images of the tensor-core training path
+        rc = tc_train_pack(net, params_dev, st);
+        if (rc != FRL_OK) return rc;
+    }
     net->has_params = true;
     return FRL_OK;
 }

@@ -1,0 +1,749 @@
+// tcgen05 tensor-core path of the conditional-flow-matching loss + gradient (sm_100a).
+// Same contract as cfm_loss_grad_f32 (train_f32.cu): replaces  fm_loss(...) ; loss.backward()  of the reference
+// (modril/flowril/pretrain.py:179-190, :94-109; modril/flowril/flowril.py:317-322), with fp16 operands and fp32
+// accumulation in TMEM.
+//
+// Data layout.  Every activation / gradient matrix [B rows][F features] lives in HBM as 128-row tiles, each tile
+// already the shared-memory image of a UMMA operand:  [tile][F/8][128 rows][8 x fp16]  (no swizzle; 8-row x 16-byte
+// core matrices contiguous).  One such image serves
+//   * as the K-major A operand of the forward / dgrad GEMMs (contraction over the features), and
+//   * as the MN-major operand of the wgrad GEMMs (contraction over the 128 rows)
+// without any transposition (tests/umma_probe_mn.cu), and a tile or a 64-feature slice of it is ONE contiguous
+// cp.async.bulk copy.  Epilogues write tiles straight from registers: for a fixed 8-feature chunk the 32 rows of a
+// warp are 512 contiguous bytes.
+//
+// Kernels
+//   tc_prepare_kernel        X0 = [(1-t) a0 + t noise | s | t | 0] as fp16 tiles
+//   tc_layer_kernel<EPI>     persistent GEMM over row tiles: D[128][N] = A_tile[128][K] * W^T, weights resident in
+//                            shared memory, A streamed through a bulk-copy ring, two TMEM accumulator stages so the
+//                            epilogue of tile i overlaps the MMAs of tile i+1.
+//                              EPI_RELU  H_l  = relu(D + b)                         (forward)
+//                              EPI_MASK  dZ_l = D * (H_l > 0)                       (dgrad)
+//                              EPI_LOSS  V = D + b_heads -> loss term, dV           (heads forward + CFM loss)
+//   tc_wgrad_kernel          dW = dZ^T X over a range of row tiles (both operands MN-major), M = 128 output features
+//                            per CTA, plus a ones column that yields the bias gradient; partial sums per split
+//   tc_reduce_kernel(s)      fixed-order reduction of the partials into the flat fp32 gradient (deterministic)
+#include <algorithm>
+#include <vector>
+
+#include "frl_internal.h"
+#include "tc_common.cuh"
+
+namespace frl {
+
+namespace ttc {
+
+using namespace tcc;
+
+constexpr int kRows = 128;
+constexpr int kChunkBytes = 16384;  // 64 features x 128 rows x 2 B
+constexpr int kLayerThreads = 320;  // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue
+constexpr int kWgradThreads = 192;  // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue
+constexpr int kMaxStages = 8;
+enum { EPI_RELU = 0, EPI_MASK = 1, EPI_LOSS = 2 };
+
+struct LayerParams {
+    const uint8_t* a_tiles;     // [tile][K/8][128][8]
+    const uint8_t* w_img;       // [K/8][N][8]
+    const float* bias;          // [N] (EPI_RELU, EPI_LOSS)
+    uint8_t* out_tiles;         // [tile][N/8][128][8]
+    const uint8_t* mask_tiles;  // [tile][N/8][128][8] (EPI_MASK)
+    int K, N, n_tiles, n_stages;
+    // EPI_LOSS
+    const float* a0;
+    const float* noise;
+    const float* t;
+    float sign;
+    int a_dim, n_heads;
+    long long B;
+    double* loss_partial;   // [n_tiles * 4]
+    float* dvsum_partial;   // [n_tiles * 4][N]
+};
+
+// X0 tiles: [tile][K0p/8][128][8];  one thread per (tile, 8-feature chunk, row)
+__global__ void tc_prepare_kernel(const float* __restrict__ s, const float* __restrict__ a0, const float* __restrict__ t,
+                                  const float* __restrict__ noise, uint8_t* __restrict__ X0t, long long B, int n_tiles,
+                                  int s_dim, int a_dim, int K0p) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int chunks = K0p / 8;
+    if (i >= (long long)n_tiles * chunks * kRows) return;
+    const int r = (int)(i % kRows);
+    const int kc = (int)((i / kRows) % chunks);
+    const long long tile = i / ((long long)kRows * chunks);
+    const long long row = tile * kRows + r;
+    __half h[8];
+    float tt = 0.f;
+    if (row < B) tt = t[row];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = kc * 8 + e;
+        float v = 0.f;
+        if (row < B) {
+            if (k < a_dim)
+                v = __fadd_rn(__fmul_rn(1.f - tt, a0[row * a_dim + k]), __fmul_rn(tt, noise[row * a_dim + k]));
+            else if (k < a_dim + s_dim)
+                v = s[row * s_dim + (k - a_dim)];
+            else if (k == a_dim + s_dim)
+                v = tt;
+        }
+        h[e] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    }
+    *reinterpret_cast<uint4*>(X0t + (size_t)i * 16) = *reinterpret_cast<uint4*>(h);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid_constant__ LayerParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t bar0 = smem_u32(smem);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+    const uint32_t w_full = bar0 + 8u * (2 * kMaxStages);
+    auto tmem_full = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 1 + i); };
+    auto tmem_empty = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 3 + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+    float* sBias = reinterpret_cast<float*>(smem + 1024);   // [N <= 256]
+    uint8_t* sW = smem + 2048;
+    const uint32_t w_bytes = (uint32_t)p.K * p.N * 2;
+    uint8_t* sRing = smem + 2048 + ((w_bytes + 1023) / 1024) * 1024;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = (p.K + 63) / 64;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.n_stages; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(w_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tmem_full(i), 1);
+            mbar_init(tmem_empty(i), 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc512(smem_u32(tmem_slot));
+    if (EPI != EPI_MASK)
+        for (int i = threadIdx.x; i < p.N; i += kLayerThreads) sBias[i] = p.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ producer ------------------------------------------------
+        if (lane == 0) {
+            mbar_expect_tx(w_full, w_bytes);
+            for (uint32_t off = 0; off < w_bytes; off += kChunkBytes)
+                bulk_g2s(smem_u32(sW + off), p.w_img + off, min((uint32_t)kChunkBytes, w_bytes - off), w_full);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const uint8_t* src = p.a_tiles + (size_t)tile * p.K * (kRows * 2);
+                for (int c = 0; c < n_chunks; ++c) {
+                    const uint32_t bytes = (uint32_t)min(64, p.K - 64 * c) * (kRows * 2);
+                    mbar_wait(empty(stage), phase ^ 1);
+                    mbar_expect_tx(full(stage), bytes);
+                    bulk_g2s(smem_u32(sRing + (size_t)stage * kChunkBytes), src + (size_t)c * kChunkBytes, bytes, full(stage));
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer ----------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16((uint32_t)p.N, false, false);
+            const uint32_t w_addr = smem_u32(sW), ring_addr = smem_u32(sRing);
+            int stage = 0, as = 0;
+            uint32_t phase = 0, aphase = 0;
+            mbar_wait(w_full, 0);
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(tmem_empty(as), aphase ^ 1);
+                tc_fence_after();
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int nk = min(64, p.K - 64 * c) / 16;
+                    mbar_wait(full(stage), phase);
+                    tc_fence_after();
+                    for (int j = 0; j < nk; ++j) {
+                        const uint64_t da = make_desc(ring_addr + stage * kChunkBytes + j * (2 * kRows * 16), kRows * 16, 128);
+                        const uint64_t db = make_desc(w_addr + (uint32_t)(c * 8 + 2 * j) * (uint32_t)p.N * 16, (uint32_t)p.N * 16, 128);
+                        umma_f16(tmem + (uint32_t)as * 256, da, db, idesc, (c | j) != 0);
+                    }
+                    umma_commit(empty(stage));
+                    if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tmem_full(as));
+                as ^= 1;
+                if (as == 0) aphase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue ------------------------------------------------
+        const int ew = warp - 2;
+        const int q = warp & 3;      // TMEM lane quarter this warp may access
+        const int ch = ew >> 2;      // column half
+        const int row = q * 32 + lane;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(tmem_full(as), aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
+            if (EPI == EPI_RELU || EPI == EPI_MASK) {
+                const int half = p.N / 2;
+                uint8_t* out = p.out_tiles + (size_t)tile * p.N * (kRows * 2) + (size_t)row * 16;
+                const uint8_t* msk = EPI == EPI_MASK ? p.mask_tiles + (size_t)tile * p.N * (kRows * 2) + (size_t)row * 16 : nullptr;
+                for (int c0 = ch * half; c0 < (ch + 1) * half; c0 += 32) {
+                    uint32_t z[32];
+                    tmem_ld32(taddr + (uint32_t)c0, z);
+                    uint4 mk[4];
+                    if (EPI == EPI_MASK) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            mk[i] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)(c0 / 8 + i) * (kRows * 16)));
+                    }
+                    tmem_ld_wait_dep(z);
+                    uint32_t o[16];
+                    if (EPI == EPI_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            o[j] = pack2_f16_relu(__uint_as_float(z[2 * j]) + sBias[c0 + 2 * j],
+                                                  __uint_as_float(z[2 * j + 1]) + sBias[c0 + 2 * j + 1]);
+                    } else {
+                        const uint32_t* mw = reinterpret_cast<const uint32_t*>(mk);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)  // H >= 0 after ReLU, so H > 0  <=>  its fp16 bits are non-zero
+                            o[j] = pack2_f16(__uint_as_float(z[2 * j]), __uint_as_float(z[2 * j + 1])) & __vcmpne2(mw[j], 0u);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(out + (size_t)(c0 / 8 + i) * (kRows * 16)) =
+                            make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+            } else if (ch == 0) {
+                // heads: V = D + b;  loss term and dL/dV (scaled by 2 w only: 1/B and the caller's grad_scale are applied
+                // in the final reduction so that fp16 keeps the values at O(1))  -- pretrain.py:184-189
+                float v[64];
+                for (int g16 = 0; g16 < p.N; g16 += 16) {
+                    uint32_t r16[16];
+                    tmem_ld16(taddr + (uint32_t)g16, r16);
+                    tmem_ld_wait_dep16(r16);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[g16 + i] = __uint_as_float(r16[i]) + sBias[g16 + i];
+                }
+                const long long g = (long long)tile * kRows + row;
+                const int A = p.a_dim;
+                double term = 0.0;
+                if (g < p.B) {
+                    const float w = powf(1.f - p.t[g], 1.5f);
+                    float acc = 0.f;
+                    for (int j = 0; j < A; ++j) {
+                        float pred = v[j], th = 0.f;
+                        if (p.n_heads == 2) {
+                            th = tanhf(v[A + j]);
+                            pred += p.sign * th;
+                        }
+                        const float diff = pred - (p.noise[g * A + j] - p.a0[g * A + j]);
+                        acc += diff * diff;
+                        const float d = 2.f * w * diff;
+                        v[j] = d;
+                        if (p.n_heads == 2) v[A + j] = d * p.sign * (1.f - th * th);
+                    }
+                    for (int j = p.n_heads * A; j < p.N; ++j) v[j] = 0.f;
+                    term = (double)(w * acc);
+                } else {
+                    for (int j = 0; j < p.N; ++j) v[j] = 0.f;
+                }
+                uint8_t* out = p.out_tiles + (size_t)tile * p.N * (kRows * 2) + (size_t)row * 16;
+                for (int c8 = 0; c8 < p.N; c8 += 8) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) o[i] = pack2_f16(v[c8 + 2 * i], v[c8 + 2 * i + 1]);
+                    *reinterpret_cast<uint4*>(out + (size_t)(c8 / 8) * (kRows * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+                    // bias gradient of the heads: column sums of the (fp16-rounded) dV over the warp's 32 rows
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __half2 hv = *reinterpret_cast<const __half2*>(&o[i]);
+                        float lo = __low2float(hv), hi = __high2float(hv);
+                        for (int s = 16; s > 0; s >>= 1) {
+                            lo += __shfl_xor_sync(0xffffffffu, lo, s);
+                            hi += __shfl_xor_sync(0xffffffffu, hi, s);
+                        }
+                        if (lane == 0) {
+                            p.dvsum_partial[((size_t)tile * 4 + q) * p.N + c8 + 2 * i] = lo;
+                            p.dvsum_partial[((size_t)tile * 4 + q) * p.N + c8 + 2 * i + 1] = hi;
+                        }
+                    }
+                }
+                for (int s = 16; s > 0; s >>= 1) term += __shfl_xor_sync(0xffffffffu, term, s);
+                if (lane == 0) p.loss_partial[(size_t)tile * 4 + q] = term;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(as));
+            as ^= 1;
+            if (as == 0) aphase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc512(tmem);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad:  partial[split][m][0..FQ) = sum_{tiles of the split} sum_b P[b][m0+m] Q[b][.],  column FQ = sum_b P[b][m0+m]
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxJobs = 2 * kMaxDepth + 2;
+struct WgradJob {
+    const uint8_t* p_tiles;   // [tile][FP/8][128][8]
+    const uint8_t* q_tiles;   // [tile][FQ/8][128][8]
+    float* partial;           // [n_splits][128][FQ + 16]
+    uint32_t p_tile_bytes, p_off, q_tile_bytes;
+    int FQ;
+};
+struct WgradParams {
+    WgradJob job[kMaxJobs];
+    int n_jobs, n_tiles, n_splits;
+};
+constexpr uint32_t kWgStageBytes = 32768 + 65536;
+constexpr uint32_t kWgOnesOff = 1024, kWgRingOff = 8192;
+
+__global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t bar0 = smem_u32(smem);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (2 + s); };
+    const uint32_t acc_full = bar0 + 8u * 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+    uint8_t* sOnes = smem + kWgOnesOff;   // [2][128][8]: feature 0 is 1.0 for every row
+    uint8_t* sRing = smem + kWgRingOff;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WgradJob& jb = p.job[blockIdx.y];
+    const int split = blockIdx.x;
+    const int t0 = (int)((long long)split * p.n_tiles / p.n_splits), t1 = (int)((long long)(split + 1) * p.n_tiles / p.n_splits);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(full(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc512(smem_u32(tmem_slot));
+    for (int i = threadIdx.x; i < 2 * kRows; i += kWgradThreads)
+        reinterpret_cast<uint4*>(sOnes)[i] = i < kRows ? make_uint4(0x3C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = t0; tile < t1; ++tile) {
+                mbar_wait(empty(stage), phase ^ 1);
+                mbar_expect_tx(full(stage), 32768u + jb.q_tile_bytes);
+                uint8_t* dst = sRing + (size_t)stage * kWgStageBytes;
+                bulk_g2s(smem_u32(dst), jb.p_tiles + (size_t)tile * jb.p_tile_bytes + jb.p_off, 16384u, full(stage));
+                bulk_g2s(smem_u32(dst + 16384), jb.p_tiles + (size_t)tile * jb.p_tile_bytes + jb.p_off + 16384u, 16384u, full(stage));
+                for (uint32_t off = 0; off < jb.q_tile_bytes; off += kChunkBytes)
+                    bulk_g2s(smem_u32(dst + 32768 + off), jb.q_tiles + (size_t)tile * jb.q_tile_bytes + off,
+                             min((uint32_t)kChunkBytes, jb.q_tile_bytes - off), full(stage));
+                if (++stage == 2) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16((uint32_t)jb.FQ, true, true), idesc1 = make_idesc_f16(16u, true, true);
+            const uint32_t ones_addr = smem_u32(sOnes), ring_addr = smem_u32(sRing);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = t0; tile < t1; ++tile) {
+                mbar_wait(full(stage), phase);
+                tc_fence_after();
+                const uint32_t pa = ring_addr + stage * kWgStageBytes, qa = pa + 32768;
+                for (int kk = 0; kk < kRows / 16; ++kk) {
+                    // MN-major: 8-row groups are 128 B apart (LBO), 8-feature chunks 128*16 B apart (SBO)
+                    const uint64_t da = make_desc(pa + kk * 256, 128, kRows * 16);
+                    const uint64_t db = make_desc(qa + kk * 256, 128, kRows * 16);
+                    const uint64_t d1 = make_desc(ones_addr + kk * 256, 128, kRows * 16);
+                    const uint32_t acc = (tile != t0 || kk != 0);
+                    umma_f16(tmem, da, db, idesc, acc);
+                    umma_f16(tmem + (uint32_t)jb.FQ, da, d1, idesc1, acc);
+                }
+                umma_commit(empty(stage));
+                if (++stage == 2) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int ldp = jb.FQ + 16;
+        float* dst = jb.partial + ((size_t)split * kRows + m) * ldp;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < ldp; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)c0, r);
+            tmem_ld_wait_dep16(r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(dst + c0 + 4 * i) =
+                    make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                __uint_as_float(r[4 * i + 3]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc512(tmem);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reductions of the partials into the flat gradient (fixed order: deterministic)
+// ---------------------------------------------------------------------------------------------------------------
+struct RedParams {
+    const float* part[kMaxJobs];   // per wgrad job
+    int ldp[kMaxJobs];
+    long long off_w[kMaxDepth], off_b[kMaxDepth], off_wh[2], off_bh[2];
+    int depth, H, d_in, a_dim, n_heads, n_splits, jobs_per_layer;  // jobs_per_layer = H / 128
+    long long n_trunk;   // number of flat entries before the heads
+    long long n_params;
+    float scale;
+    int accumulate;
+};
+
+__global__ void tc_reduce_kernel(RedParams rp, float* __restrict__ grad) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= rp.n_params) return;
+    int job, m, col;
+    if (e < rp.n_trunk) {
+        int l = 0;
+        while (l + 1 < rp.depth && rp.off_w[l + 1] <= e) ++l;
+        const int K = l == 0 ? rp.d_in : rp.H;
+        int n;
+        if (e < rp.off_b[l]) {
+            const long long i = e - rp.off_w[l];
+            n = (int)(i / K);
+            col = (int)(i % K);
+        } else {
+            n = (int)(e - rp.off_b[l]);
+            col = rp.ldp[l * rp.jobs_per_layer] - 16;   // the ones column
+        }
+        job = l * rp.jobs_per_layer + n / kRows;
+        m = n % kRows;
+    } else {
+        int h = (rp.n_heads == 2 && e >= rp.off_wh[1]) ? 1 : 0;
+        if (e >= rp.off_bh[h]) return;   // head biases: tc_reduce_small_kernel
+        const long long i = e - rp.off_wh[h];
+        const int j = (int)(i / rp.H), k = (int)(i % rp.H);
+        job = rp.depth * rp.jobs_per_layer + k / kRows;
+        m = k % kRows;
+        col = h * rp.a_dim + j;
+    }
+    const float* P = rp.part[job];
+    const int ldp = rp.ldp[job];
+    float acc = 0.f;
+    for (int s = 0; s < rp.n_splits; ++s) acc += P[((size_t)s * kRows + m) * ldp + col];
+    acc *= rp.scale;
+    grad[e] = rp.accumulate ? grad[e] + acc : acc;
+}
+
+// block 0: loss;  block 1 + o: bias gradient of head output o
+__global__ void __launch_bounds__(256) tc_reduce_small_kernel(const double* __restrict__ lpart, const float* __restrict__ dvsum,
+                                                              int n_part, int NOp, RedParams rp, double inv_div,
+                                                              float* __restrict__ loss, float* __restrict__ grad) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < n_part; i += 256) acc += lpart[i];
+    } else {
+        const int o = blockIdx.x - 1;
+        for (int i = threadIdx.x; i < n_part; i += 256) acc += (double)dvsum[(size_t)i * NOp + o];
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    if (blockIdx.x == 0) {
+        if (loss) loss[0] = (float)(sh[0] * inv_div);
+    } else if (grad) {
+        const int o = blockIdx.x - 1;
+        const int h = o / rp.a_dim, j = o % rp.a_dim;
+        if (h < rp.n_heads) {
+            const float v = (float)sh[0] * rp.scale;
+            float* g = grad + rp.off_bh[h] + j;
+            *g = rp.accumulate ? *g + v : v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight images (fp16) for the GEMMs above, rebuilt by frl_net_set_params
+// ---------------------------------------------------------------------------------------------------------------
+struct ImgJob {
+    long long src_off;   // into the flat fp32 parameters
+    int rs, cs;          // source strides of (row, feature)
+    int R, F;            // valid rows / features of this job
+    int row0, feat0;     // placement inside the image
+    long long img_off;   // byte offset of the image
+    int img_rows;        // rows of the image (N of the GEMM)
+    long long first;     // prefix sum of R * F
+};
+struct ImgTable {
+    ImgJob job[4 * kMaxDepth + 8];
+    int n_jobs;
+    long long total;
+};
+__global__ void tc_image_kernel(const float* __restrict__ flat, uint8_t* __restrict__ img, ImgTable tab) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tab.total; i += (long long)gridDim.x * blockDim.x) {
+        int j = 0;
+        while (j + 1 < tab.n_jobs && tab.job[j + 1].first <= i) ++j;
+        const ImgJob& jb = tab.job[j];
+        const long long e = i - jb.first;
+        const int r = (int)(e / jb.F), f = (int)(e % jb.F);
+        const float v = flat[jb.src_off + (long long)r * jb.rs + (long long)f * jb.cs];
+        const int ri = jb.row0 + r, fi = jb.feat0 + f;
+        __half* dst = reinterpret_cast<__half*>(img + jb.img_off) + ((size_t)(fi / 8) * jb.img_rows + ri) * 8 + (fi % 8);
+        *dst = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    }
+}
+
+struct TrainPack {   // byte offsets into net->pack_train
+    size_t wf[kMaxDepth];   // forward  image of layer l: [Kp_l/8][H][8]      (N = H outputs,  K = Kp_l inputs)
+    size_t wd[kMaxDepth];   // dgrad    image of layer l: [H/8][H][8]         (N = H inputs,   K = H outputs), l >= 1
+    size_t whf, whd;        // heads forward [H/8][NOp][8], heads dgrad [NOp/8][H][8]
+    size_t total;
+};
+static TrainPack train_pack_layout(const frl_net* net) {
+    TrainPack tp{};
+    const int H = net->cfg.hidden, depth = net->cfg.depth;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+    for (int l = 0; l < depth; ++l) tp.wf[l] = take((size_t)(l == 0 ? net->d_in_p : H) * H * 2);
+    for (int l = 1; l < depth; ++l) tp.wd[l] = take((size_t)H * H * 2);
+    tp.whf = take((size_t)H * net->n_out_p * 2);
+    tp.whd = take((size_t)net->n_out_p * H * 2);
+    tp.total = off;
+    return tp;
+}
+
+}  // namespace ttc
+
+int tc_train_pack(frl_net* net, const float* params_dev, cudaStream_t st) {
+    using namespace ttc;
+    const TrainPack tp = train_pack_layout(net);
+    if (!net->pack_train) FRL_CUDA(cudaMalloc(&net->pack_train, tp.total));
+    FRL_CUDA(cudaMemsetAsync(net->pack_train, 0, tp.total, st));
+    const int H = net->cfg.hidden, depth = net->cfg.depth, A = net->cfg.a_dim;
+    ImgTable tab{};
+    long long total = 0;
+    auto add = [&](long long src_off, int rs, int cs, int R, int F, int row0, int feat0, size_t img_off, int img_rows) {
+        ImgJob& j = tab.job[tab.n_jobs++];
+        j = ImgJob{src_off, rs, cs, R, F, row0, feat0, (long long)img_off, img_rows, total};
+        total += (long long)R * F;
+    };
+    for (int l = 0; l < depth; ++l) {
+        const int K = l == 0 ? net->d_in : H;
+        add(net->off_w[l], K, 1, H, K, 0, 0, tp.wf[l], H);              // rows = outputs n, features = inputs k
+        if (l >= 1) add(net->off_w[l], 1, K, H, H, 0, 0, tp.wd[l], H);  // rows = inputs k, features = outputs n
+    }
+    for (int h = 0; h < net->cfg.n_heads; ++h) {
+        add(net->off_wh[h], H, 1, A, H, h * A, 0, tp.whf, net->n_out_p);   // rows = outputs o, features = k
+        add(net->off_wh[h], 1, H, H, A, 0, h * A, tp.whd, H);              // rows = k, features = outputs o
+    }
+    tab.total = total;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 1184);
+    tc_image_kernel<<<blocks, 256, 0, st>>>(params_dev, static_cast<uint8_t*>(net->pack_train), tab);
+    FRL_CUDA(cudaGetLastError());
+    return FRL_OK;
+}
+
+template <int EPI>
+static int launch_layer(const ttc::LayerParams& p0, int device, cudaStream_t st) {
+    using namespace ttc;
+    LayerParams p = p0;
+    int max_smem = 0, sms = 0;
+    FRL_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    FRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const size_t base = 2048 + ((size_t)p.K * p.N * 2 + 1023) / 1024 * 1024;
+    int stages = (int)(((size_t)max_smem - base) / kChunkBytes);
+    stages = std::min(stages, kMaxStages);
+    if (stages < 2) {
+        set_error("tensor-core training: layer does not fit in shared memory");
+        return FRL_ERR_UNSUPPORTED;
+    }
+    p.n_stages = stages;
+    // > half of the SM's shared memory, so exactly one CTA (and its 512 TMEM columns) lives on an SM
+    const size_t smem_bytes = std::max(base + (size_t)stages * kChunkBytes, (size_t)120 * 1024);
+    auto kern = tc_layer_kernel<EPI>;
+    FRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    kern<<<std::min(p.n_tiles, sms), kLayerThreads, smem_bytes, st>>>(p);
+    FRL_CUDA(cudaGetLastError());
+    return FRL_OK;
+}
+
+int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float* a0, const float* t, const float* noise,
+                     long long B, long long mean_divisor, float grad_scale, int accumulate, float* loss, float* grad,
+                     cudaStream_t st) {
+    using namespace ttc;
+    const int H = net->cfg.hidden, A = net->cfg.a_dim, depth = net->cfg.depth;
+    const int K0p = net->d_in_p, NOp = net->n_out_p;
+    FRL_REQUIRE(B > 0 && B < (1ll << 30), "batch size out of range");
+    FRL_REQUIRE(net->pack_train != nullptr, "tensor-core training weights missing");
+    FRL_REQUIRE(NOp <= 64, "a_dim too large for the tensor-core training path");
+    const double div = (double)(mean_divisor > 0 ? mean_divisor : B);
+    const int nt = (int)((B + kRows - 1) / kRows);
+    const int device = net->cfg.device;
+    const TrainPack tp = train_pack_layout(net);
+    const uint8_t* pk = static_cast<const uint8_t*>(net->pack_train);
+
+    int sms = 0;
+    FRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int jpl = H / kRows;                    // M halves per layer
+    const int n_jobs = (depth + 1) * jpl;         // trunk layers + heads
+    const int n_splits = std::max(1, std::min(nt, sms / n_jobs));
+
+    // ---- workspace (bytes) ----
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+    const size_t tileH = (size_t)H * kRows * 2, tileX = (size_t)K0p * kRows * 2, tileV = (size_t)NOp * kRows * 2;
+    const size_t o_x0 = take(tileX * nt);
+    size_t o_h[kMaxDepth], o_dz[kMaxDepth];
+    for (int l = 0; l < depth; ++l) o_h[l] = take(tileH * nt);
+    for (int l = 0; l < depth; ++l) o_dz[l] = take(tileH * nt);
+    const size_t o_dv = take(tileV * nt);
+    const size_t o_lp = take((size_t)nt * 4 * sizeof(double));
+    const size_t o_dvs = take((size_t)nt * 4 * NOp * sizeof(float));
+    size_t o_part[kMaxJobs];
+    int ldp[kMaxJobs];
+    for (int j = 0; j < n_jobs; ++j) {
+        const int l = j / jpl;
+        ldp[j] = (l == 0 ? K0p : (l == depth ? NOp : H)) + 16;
+        o_part[j] = take((size_t)n_splits * kRows * ldp[j] * sizeof(float));
+    }
+    if (net->ws_tc_bytes < off) {
+        if (net->ws_tc) FRL_CUDA(cudaFree(net->ws_tc));   // synchronises: earlier work is done with it
+        net->ws_tc = nullptr;
+        net->ws_tc_bytes = 0;
+        FRL_CUDA(cudaMalloc(&net->ws_tc, off));
+        net->ws_tc_bytes = off;
+    }
+    uint8_t* ws = static_cast<uint8_t*>(net->ws_tc);
+    double* lpart = reinterpret_cast<double*>(ws + o_lp);
+    float* dvsum = reinterpret_cast<float*>(ws + o_dvs);
+
+    // ---- forward ----
+    {
+        const long long n = (long long)nt * (K0p / 8) * kRows;
+        tc_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, a0, t, noise, ws + o_x0, B, nt, net->cfg.s_dim, A, K0p);
+        FRL_CUDA(cudaGetLastError());
+    }
+    int rc;
+    for (int l = 0; l < depth; ++l) {
+        LayerParams p{};
+        p.a_tiles = l == 0 ? ws + o_x0 : ws + o_h[l - 1];
+        p.w_img = pk + tp.wf[l];
+        p.bias = net->f32.b[l];
+        p.out_tiles = ws + o_h[l];
+        p.K = l == 0 ? K0p : H;
+        p.N = H;
+        p.n_tiles = nt;
+        rc = launch_layer<EPI_RELU>(p, device, st);
+        if (rc != FRL_OK) return rc;
+    }
+    {
+        LayerParams p{};
+        p.a_tiles = ws + o_h[depth - 1];
+        p.w_img = pk + tp.whf;
+        p.bias = net->f32.bh;
+        p.out_tiles = ws + o_dv;
+        p.K = H;
+        p.N = NOp;
+        p.n_tiles = nt;
+        p.a0 = a0; p.noise = noise; p.t = t; p.sign = role_sign; p.a_dim = A; p.n_heads = net->cfg.n_heads; p.B = B;
+        p.loss_partial = lpart;
+        p.dvsum_partial = dvsum;
+        rc = launch_layer<EPI_LOSS>(p, device, st);
+        if (rc != FRL_OK) return rc;
+    }
+    RedParams rp{};
+    rp.depth = depth; rp.H = H; rp.d_in = net->d_in; rp.a_dim = A; rp.n_heads = net->cfg.n_heads;
+    rp.n_splits = n_splits; rp.jobs_per_layer = jpl;
+    for (int l = 0; l < depth; ++l) { rp.off_w[l] = net->off_w[l]; rp.off_b[l] = net->off_b[l]; }
+    for (int h = 0; h < net->cfg.n_heads; ++h) { rp.off_wh[h] = net->off_wh[h]; rp.off_bh[h] = net->off_bh[h]; }
+    rp.n_trunk = net->off_wh[0];
+    rp.n_params = net->n_params;
+    rp.scale = (float)((double)grad_scale / div);
+    rp.accumulate = accumulate;
+    for (int j = 0; j < n_jobs; ++j) { rp.part[j] = reinterpret_cast<const float*>(ws + o_part[j]); rp.ldp[j] = ldp[j]; }
+    if (!grad) {
+        tc_reduce_small_kernel<<<1, 256, 0, st>>>(lpart, dvsum, nt * 4, NOp, rp, 1.0 / div, loss, nullptr);
+        FRL_CUDA(cudaGetLastError());
+        return FRL_OK;
+    }
+
+    // ---- backward: dgrad chain ----
+    {
+        LayerParams p{};
+        p.a_tiles = ws + o_dv;
+        p.w_img = pk + tp.whd;
+        p.out_tiles = ws + o_dz[depth - 1];
+        p.mask_tiles = ws + o_h[depth - 1];
+        p.K = NOp;
+        p.N = H;
+        p.n_tiles = nt;
+        rc = launch_layer<EPI_MASK>(p, device, st);
+        if (rc != FRL_OK) return rc;
+    }
+    for (int l = depth - 1; l >= 1; --l) {
+        LayerParams p{};
+        p.a_tiles = ws + o_dz[l];
+        p.w_img = pk + tp.wd[l];
+        p.out_tiles = ws + o_dz[l - 1];
+        p.mask_tiles = ws + o_h[l - 1];
+        p.K = H;
+        p.N = H;
+        p.n_tiles = nt;
+        rc = launch_layer<EPI_MASK>(p, device, st);
+        if (rc != FRL_OK) return rc;
+    }
+    // ---- wgrad ----
+    {
+        WgradParams wp{};
+        wp.n_jobs = n_jobs; wp.n_tiles = nt; wp.n_splits = n_splits;
+        for (int j = 0; j < n_jobs; ++j) {
+            const int l = j / jpl, mh = j % jpl;
+            WgradJob& jb = wp.job[j];
+            jb.p_tiles = l == depth ? ws + o_h[depth - 1] : ws + o_dz[l];
+            jb.p_tile_bytes = (uint32_t)tileH;
+            jb.p_off = (uint32_t)mh * (kRows / 8) * (kRows * 16);
+            if (l == 0) { jb.q_tiles = ws + o_x0; jb.q_tile_bytes = (uint32_t)tileX; jb.FQ = K0p; }
+            else if (l == depth) { jb.q_tiles = ws + o_dv; jb.q_tile_bytes = (uint32_t)tileV; jb.FQ = NOp; }
+            else { jb.q_tiles = ws + o_h[l - 1]; jb.q_tile_bytes = (uint32_t)tileH; jb.FQ = H; }
+            jb.partial = reinterpret_cast<float*>(ws + o_part[j]);
+        }
+        const size_t smem_bytes = kWgRingOff + 2 * (size_t)kWgStageBytes;
+        FRL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        tc_wgrad_kernel<<<dim3(n_splits, n_jobs), kWgradThreads, smem_bytes, st>>>(wp);
+        FRL_CUDA(cudaGetLastError());
+    }
+    tc_reduce_kernel<<<(unsigned)((net->n_params + 255) / 256), 256, 0, st>>>(rp, grad);
+    tc_reduce_small_kernel<<<1 + net->cfg.n_heads * A, 256, 0, st>>>(lpart, dvsum, nt * 4, NOp, rp, 1.0 / div, loss, grad);
+    FRL_CUDA(cudaGetLastError());
+    return FRL_OK;
+}
+
+}  // namespace frl

@@ -166,22 +166,22 @@ class _FMLoss(torch.autograd.Function):
     the stored gradient (scaled by grad_output) to autograd so that ``loss.backward()`` fills ``p.grad``."""
 
     @staticmethod
-    def forward(ctx, net, sign, need_grad, s, a0, t, noise, *params):
+    def forward(ctx, net, sign, need_grad, prec, s, a0, t, noise, *params):
         dev = net.flat_params().device
         h = net.native()
         B = a0.shape[0]
         loss = torch.empty(1, device=dev)
         grad = torch.empty_like(net.flat_params()) if need_grad else None
-        _native.check(_native.lib().frl_cfm_loss_grad(h, float(sign), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B, 0,
-                                                      1.0, 0, _ptr(loss), _ptr(grad), _current_stream(dev)),
-                      "frl_cfm_loss_grad")
+        _native.check(_native.lib().frl_cfm_loss_grad_p(h, float(sign), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B, 0,
+                                                        1.0, 0, _ptr(loss), _ptr(grad), prec, _current_stream(dev)),
+                      "frl_cfm_loss_grad_p")
         ctx.net = net
         ctx.flat_grad = grad
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
-        outs = [None] * 7
+        outs = [None] * 8
         flat = ctx.flat_grad
         for p, off, n in ctx.net.param_slices():
             if flat is None or not p.requires_grad:
@@ -191,7 +191,26 @@ class _FMLoss(torch.autograd.Function):
         return tuple(outs)
 
 
-def _fm_loss_native(net, sign, s, a0, t, noise):
+_TRAIN_PRECISION = "fp32"
+
+
+def set_train_precision(name: str):
+    """'fp32' (FFMA kernels, the 1e-4 parity mode) or 'fp16' (tcgen05 tensor cores, fp16 operands / fp32 accumulate)
+    for ``fm_loss`` / ``train_step`` calls that do not pass ``precision=`` explicitly."""
+    global _TRAIN_PRECISION
+    if name not in ("fp32", "fp16"):
+        raise ValueError("training precision must be 'fp32' or 'fp16'")
+    _TRAIN_PRECISION = name
+
+
+def _train_precision_code(precision):
+    name = _TRAIN_PRECISION if precision is None else precision
+    if name not in ("fp32", "fp16"):
+        raise ValueError("training precision must be 'fp32' or 'fp16'")
+    return _native.PRECISIONS[name]
+
+
+def _fm_loss_native(net, sign, s, a0, t, noise, precision=None):
     dev = net.flat_params().device
     net.native()
     s = as_f32_cuda(s, dev, "s")
@@ -204,7 +223,7 @@ def _fm_loss_native(net, sign, s, a0, t, noise):
     params = [p for p, _, _ in net.param_slices()]
     # (grad mode is always off inside Function.forward, so decide here whether dL/dtheta is wanted)
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-    return _FMLoss.apply(net, sign, need_grad, s, a0, t, noise, *params)
+    return _FMLoss.apply(net, sign, need_grad, _train_precision_code(precision), s, a0, t, noise, *params)
 
 
 def reg_losses_native(net, s, a, t, probe, anti=True, stable=True, need_grad=True, mean_divisor=0):
@@ -279,7 +298,7 @@ class FlowMatching(nn.Module):
     def _v_star(self, a_t, a0, t, noise):
         return noise - a0
 
-    def fm_loss(self, s, a0, dequant_std=0.02, *, dequant=None, t=None, noise=None):
+    def fm_loss(self, s, a0, dequant_std=0.02, *, dequant=None, t=None, noise=None, precision=None):
         """CFM loss (reference pretrain.py:94-109).  Draw order when not supplied: dequantisation noise
         (randn_like), t (rand), prior sample -- the reference's order."""
         B = s.size(0)
@@ -291,7 +310,7 @@ class FlowMatching(nn.Module):
             t = torch.rand(B, 1, device=dev) * (1 - 2 * self.eps) + self.eps
         if noise is None:
             noise = self.prior.sample((B, self.action_dim)).to(a0)
-        return _fm_loss_native(self.net, 1.0, s, a0, t, noise)
+        return _fm_loss_native(self.net, 1.0, s, a0, t, noise, precision)
 
     def log_prob(self, x: torch.Tensor, n_steps: int = 32, *, probe=None, exact=False, precision=None):
         """log p(a|s) for x = cat[s, a] (reference pretrain.py:112-134).  Without ``probe`` a fresh Rademacher
@@ -318,7 +337,7 @@ class CoupledResidualFM(nn.Module):
     def _v_star(self, a_t, a0, t, noise):
         return noise - a0
 
-    def fm_loss(self, s, a0, role, *, t=None, noise=None):
+    def fm_loss(self, s, a0, role, *, t=None, noise=None, precision=None):
         """CFM loss for one role (reference pretrain.py:179-190); t then noise are drawn like the reference when
         not supplied."""
         B = a0.size(0)
@@ -327,7 +346,7 @@ class CoupledResidualFM(nn.Module):
             t = torch.rand(B, 1, device=dev) * (1 - 2 * self.eps) + self.eps
         if noise is None:
             noise = self.prior.sample((B, self.a_dim)).to(dev)
-        return _fm_loss_native(self.net, 1.0 if role == "expert" else -1.0, s, a0, t, noise)
+        return _fm_loss_native(self.net, 1.0 if role == "expert" else -1.0, s, a0, t, noise, precision)
 
     def log_prob(self, s, a0, role: str, n_steps: int = 32, *, probe=None, exact=False, precision=None):
         """log p_role(a|s) (reference pretrain.py:192-214).  Default probe = ``_rademacher((B, a_dim))``, the same
@@ -460,7 +479,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._bind_state()
 
 
-def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=None):
+def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=None, precision=None):
     """One reward-model update on the all-native route (reference flowril.py:311-330):
     zero grads; for each term accumulate rate * d fm_loss / d theta; [regularisers]; [all-reduce];
     clip_grad_norm_(max_norm); Adam.
@@ -478,9 +497,11 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
                                       switches the term off (``use_anti = args.loss_anti > 0``) and the new weight is
                                       written back into them
            On return reg["out"] holds loss_anti / loss_stable (device scalars) and grad_anti / grad_stable.
+    precision: 'fp32' (FFMA) or 'fp16' (tcgen05 tensor cores) for the CFM terms; default: ``set_train_precision``.
     Returns the per-term loss tensors (device scalars; under DP the local shard's contribution summed over ranks).
     """
     L = _native.lib()
+    prec = _train_precision_code(precision)
     seen = []
     losses = []
     ws = 1 if world is None else world[1]
@@ -498,9 +519,9 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
         noise = as_f32_cuda(term["noise"], dev, "noise")
         B = a0.shape[0]
         loss = torch.empty(1, device=dev)
-        _native.check(L.frl_cfm_loss_grad(h, float(term["sign"]), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B, B * ws,
-                                          float(term.get("rate", 1.0)), 0 if first else 1, _ptr(loss), _ptr(g),
-                                          _current_stream(dev)), "frl_cfm_loss_grad")
+        _native.check(L.frl_cfm_loss_grad_p(h, float(term["sign"]), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B, B * ws,
+                                            float(term.get("rate", 1.0)), 0 if first else 1, _ptr(loss), _ptr(g), prec,
+                                            _current_stream(dev)), "frl_cfm_loss_grad_p")
         losses.append(loss)
     grads = []
     for net in opt.nets:

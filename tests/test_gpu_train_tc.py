@@ -1,0 +1,170 @@
+"""GPU parity of the tcgen05 tensor-core CFM loss/gradient path (frl_cfm_loss_grad_p, FRL_PREC_FP16) through the
+C ABI.  fp16 operands bound the accuracy (scripts/tc_train_err.py, B200): the loss is within 1e-4 of the float64
+oracle (bar 2e-3); the gradient's relative L2 error is 2e-3..7e-3 at B = 4096 and 3e-3..2e-2 at B = 200 -- operand
+rounding (2^-11) flips ReLU masks of units whose pre-activation is within rounding of 0, and with few rows a single
+flipped unit is a visible share of the mean.  Bars: 3e-2 overall / 6e-2 per tensor on the 200-row stress nets, 1e-2 on
+the ragged batches, and the 1000-step loss curve of the reference within the stated tolerance of the fp16 mode."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import closed_form as cf
+from oracle import synth
+from tests.gpu_common import assert_close, build_model, dev, spec_of
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _flat_grad(model):
+    return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+                      for p, _, _ in model.net.param_slices()]).cpu().numpy()
+
+
+def _rel_l2(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return np.sqrt(((got - ref) ** 2).sum()) / np.sqrt((ref ** 2).sum())
+
+
+def _tensor_rel_l2(spec, got, ref):
+    out, off = {}, 0
+    for name, shape in spec.shapes():
+        n = int(np.prod(shape))
+        out[name] = _rel_l2(got[off:off + n], ref[off:off + n])
+        off += n
+    return out
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "fmloss_*.npz"))), ids=os.path.basename)
+def test_tc_fmloss_and_grads_vs_reference_and_oracle(path):
+    g = np.load(path)
+    spec = spec_of(g["meta"])
+    if spec.n_heads * spec.a_dim > 64:
+        pytest.skip("a_dim too large for the tensor-core training path")
+    B, seed = int(g["meta"][6]), int(g["meta"][7])
+    flat = cf.make_params(spec, seed, float(g["gain"]))
+    s, a = synth.states_actions(seed, B, spec.s_dim, spec.a_dim)
+    for ri, role in enumerate(("expert", "agent")):
+        m = build_model(spec, flat)
+        t, noise = synth.cfm_draws(seed + 1 + ri, B, spec.a_dim)
+        if spec.n_heads == 2:
+            loss = m.fm_loss(dev(s), dev(a), role, t=dev(t), noise=dev(noise), precision="fp16")
+            dq64 = None
+        else:
+            dq = synth.rng(seed + 5 + ri).standard_normal((B, spec.a_dim)).astype(np.float32)
+            loss = m.fm_loss(dev(s), dev(a), dequant=dev(dq), t=dev(t), noise=dev(noise), precision="fp16")
+            dq64 = dq * np.float32(0.02)
+        loss.backward()
+        grad = _flat_grad(m)
+        assert_close(np.array(loss.item()), g[f"loss_{role}"], 2e-3, f"loss {role}")
+        ref_loss, ref_grad = cf.fm_loss_and_grad(spec, flat, s, a, role, t, noise, dequant=dq64)
+        assert _rel_l2(grad, ref_grad) <= 3e-2, _rel_l2(grad, ref_grad)
+        worst = max(_tensor_rel_l2(spec, grad, ref_grad).values())
+        assert worst <= 6e-2, _tensor_rel_l2(spec, grad, ref_grad)
+        if f"grad_{role}" in g:
+            assert _rel_l2(grad, g[f"grad_{role}"]) <= 3e-2
+
+
+@pytest.mark.parametrize("B", [1, 7, 128, 129, 1000, 5000, 40000])
+def test_tc_fmloss_ragged_vs_fp32_kernels(B):
+    spec = cf.NetSpec(17, 6, 256, 4, 2)
+    flat = cf.make_params(spec, 91, 2.0)
+    s, a = synth.states_actions(300 + B, B, 17, 6)
+    t, noise = synth.cfm_draws(400 + B, B, 6)
+    out = {}
+    for prec in ("fp32", "fp16"):
+        m = build_model(spec, flat)
+        loss = m.fm_loss(dev(s), dev(a), "agent", t=dev(t), noise=dev(noise), precision=prec)
+        loss.backward()
+        out[prec] = (loss.item(), _flat_grad(m))
+    assert abs(out["fp16"][0] - out["fp32"][0]) <= 2e-3 * max(1.0, abs(out["fp32"][0]))
+    assert _rel_l2(out["fp16"][1], out["fp32"][1]) <= 1e-2, _rel_l2(out["fp16"][1], out["fp32"][1])
+    worst = max(_tensor_rel_l2(spec, out["fp16"][1], out["fp32"][1]).values())
+    assert worst <= 6e-2, _tensor_rel_l2(spec, out["fp16"][1], out["fp32"][1])
+
+
+@pytest.mark.parametrize("dims", [(1, 1, 128, 4, 2), (6, 2, 128, 3, 1), (11, 3, 256, 2, 2), (132, 8, 256, 4, 2),
+                                  (68, 20, 256, 4, 2), (16, 4, 128, 1, 1)])
+def test_tc_other_shapes_deterministic(dims):
+    spec = cf.NetSpec(*dims)
+    flat = cf.make_params(spec, 3, 2.0)
+    B = 700
+    s, a = synth.states_actions(8, B, spec.s_dim, spec.a_dim)
+    t, noise = synth.cfm_draws(9, B, spec.a_dim)
+    grads = []
+    for rep in range(2):
+        m = build_model(spec, flat)
+        if spec.n_heads == 2:
+            loss = m.fm_loss(dev(s), dev(a), "expert", t=dev(t), noise=dev(noise), precision="fp16")
+        else:
+            loss = m.fm_loss(dev(s), dev(a), dequant=torch.zeros(B, spec.a_dim, device="cuda"), t=dev(t), noise=dev(noise),
+                             precision="fp16")
+        loss.backward()
+        grads.append(_flat_grad(m))
+    assert np.array_equal(grads[0], grads[1])
+    ref_loss, ref_grad = cf.fm_loss_and_grad(spec, flat, s, a, "expert", t, noise)
+    assert abs(loss.item() - ref_loss) <= 2e-3 * max(1.0, abs(ref_loss))
+    assert _rel_l2(grads[0], ref_grad) <= 3e-2, _rel_l2(grads[0], ref_grad)
+
+
+def test_tc_grad_scale_accumulate_and_mean_divisor():
+    """train_step semantics on the tensor-core path: rate-weighted accumulation of two terms into one flat gradient
+    equals the FP32 kernels' result to fp16 accuracy; loss-only call leaves no gradient."""
+    from modril_b200.flowril import FusedAdam, train_step
+    spec = cf.NetSpec(11, 3, 256, 4, 2)
+    flat = cf.make_params(spec, 12, 1.0)
+    B = 3000
+    s, a = synth.states_actions(5, B, 11, 3)
+    t, noise = synth.cfm_draws(6, B, 3)
+    t2, noise2 = synth.cfm_draws(7, B, 3)
+    res = {}
+    for prec in ("fp32", "fp16"):
+        m = build_model(spec, flat)
+        opt = FusedAdam([m.net], lr=1e-3)
+        terms = [dict(net=m.net, sign=1.0, s=dev(s), a0=dev(a), t=dev(t), noise=dev(noise), rate=1.0),
+                 dict(net=m.net, sign=-1.0, s=dev(s), a0=dev(a), t=dev(t2), noise=dev(noise2), rate=0.5)]
+        losses = train_step(terms, opt, max_norm=1e9, precision=prec)
+        res[prec] = ([float(l) for l in losses], m.net.flat_grad().cpu().numpy().copy())
+    for l16, l32 in zip(res["fp16"][0], res["fp32"][0]):
+        assert abs(l16 - l32) <= 2e-3 * max(1.0, abs(l32))
+    assert _rel_l2(res["fp16"][1], res["fp32"][1]) <= 1e-2
+    with torch.no_grad():
+        m = build_model(spec, flat)
+        l = m.fm_loss(dev(s), dev(a), "expert", t=dev(t), noise=dev(noise), precision="fp16")
+    assert abs(l.item() - res["fp32"][0][0]) <= 2e-3 * max(1.0, abs(res["fp32"][0][0]))
+
+
+def test_tc_training_curve_vs_reference():
+    """1000 regular update steps of flowril.py:311-335 with the tensor-core gradient kernels: the loss curve tracks
+    the reference's (tests/golden/train_00) -- per-step 1e-2 over the first 50 steps, 50-step moving average within
+    5 % to the end (stated tolerance of the fp16 mode)."""
+    from modril_b200.flowril import FusedAdam, train_step
+    path = sorted(glob.glob(os.path.join(GOLDEN, "train_00_*.npz")))[0]
+    g = np.load(path)
+    spec = spec_of(g["meta"])
+    steps, B, seed = (int(x) for x in g["meta"][5:8])
+    m = build_model(spec, cf.make_params(spec, seed, 1.0))
+    opt = FusedAdam([m.net], lr=float(g["lr"]))
+    pool_s, _ = synth.states_actions(seed + 1, 4096, spec.s_dim, spec.a_dim)
+    pool_aE = synth.expert_actions(seed + 2, pool_s, spec.a_dim)
+    pool_aA = np.clip(synth.rng(seed + 3).standard_normal((4096, spec.a_dim)), -1, 1).astype(np.float32)
+    d_s, d_aE, d_aA = dev(pool_s), dev(pool_aE), dev(pool_aA)
+    log = []
+    for it in range(steps):
+        r = synth.rng(seed + 100 + it)
+        iE, iA = dev(r.integers(0, 4096, B)), dev(r.integers(0, 4096, B))
+        tE, nE = synth.cfm_draws(seed + 10000 + 2 * it, B, spec.a_dim)
+        tA, nA = synth.cfm_draws(seed + 10001 + 2 * it, B, spec.a_dim)
+        terms = [dict(net=m.net, sign=1.0, s=d_s[iE], a0=d_aE[iE], t=dev(tE), noise=dev(nE), rate=1.0),
+                 dict(net=m.net, sign=-1.0, s=d_s[iA], a0=d_aA[iA], t=dev(tA), noise=dev(nA), rate=1.0)]
+        log.append(torch.stack(train_step(terms, opt, max_norm=1.0, precision="fp16")))
+    curve = torch.stack(log).cpu().numpy()
+    ref = g["curve"]
+    assert_close(curve[:50], ref[:50], 1e-2, "first steps")
+    k = 50
+    ma = lambda x: np.stack([np.convolve(x[:, j], np.ones(k) / k, mode="valid") for j in range(2)], 1)
+    rel = np.abs(ma(curve) - ma(ref)) / np.abs(ma(ref))
+    assert rel.max() <= 5e-2, rel.max()
