@@ -321,8 +321,9 @@ def run_ours(args):
     g = torch.Generator(device="cpu").manual_seed(9 + rank)
     tt_ = (torch.rand(2, Bt, 1, generator=g) * (1 - 2e-3) + 1e-3).to(device)
     zz = torch.randn(2, Bt, a_dim, generator=g).to(device)
-    opt = FusedAdam([model.net], lr=1e-4)
     grp = (dist.group.WORLD, world) if world > 1 else None
+    use_graph = world == 1   # one CUDA graph per update (all kernels of both roles + clip + Adam + weight re-pack)
+    opt = FusedAdam([model.net], lr=1e-4, capturable=use_graph)
 
     def tstep(prec_t):
         return train_step([dict(net=model.net, sign=1.0, s=ts, a0=ta, t=tt_[0], noise=zz[0]),
@@ -333,12 +334,20 @@ def run_ours(args):
     for prec_t in ("fp32", "fp16"):
         for _ in range(3):
             tstep(prec_t)
+        run = lambda: tstep(prec_t)
+        if use_graph:
+            torch.cuda.synchronize(device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                tstep(prec_t)
+            run = graph.replay
+            run()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_t = 10
         e0.record()
         for _ in range(n_t):
-            tstep(prec_t)
+            run()
         e1.record()
         barrier()
         tms = torch.tensor([e0.elapsed_time(e1) / n_t], device=device, dtype=torch.float64)
@@ -399,7 +408,8 @@ def run_ours(args):
         "other_modes_samples_per_sec": extra,
         "train": {"metric": "cfm_train_samples_per_sec", "value": train_rate, "unit": "samples/s",
                   "rows_per_step_per_gpu": 2 * Bt, "dtype": "fp16 operands / fp32 accumulate (tcgen05); fp32 clip + Adam",
-                  "step": "2 x frl_cfm_loss_grad_p (fwd + dgrad + wgrad) + [all-reduce] + frl_clip_adam + weight re-pack",
+                  "step": "2 x frl_cfm_loss_grad_p (fwd + dgrad + wgrad) + [all-reduce] + frl_clip_adam + weight re-pack"
+                          + ("; replayed as one CUDA graph" if use_graph else ""),
                   "fp32_ffma_samples_per_sec": train_rates["fp32"],
                   "algorithmic_tflops": train_rate * 3 * f_fwd_train / 1e12,
                   "frac_of_peak": train_rate * 3 * f_fwd_train / 1e12 / measured_peak_tflops()[0],

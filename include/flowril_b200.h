@@ -188,6 +188,12 @@ typedef struct {
 int frl_clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double lr, double beta1, double beta2,
                   double eps, double max_norm, float* norm_out_dev, int device, void* stream);
 
+/* frl_clip_adam with the step count held ON THE DEVICE (step_dev[0], int64; the number of completed steps on entry):
+ * the call increments it and derives the bias corrections from it inside the kernels, so a captured CUDA graph of a
+ * whole update (frl_cfm_loss_grad_p ... frl_clip_adam_dev, frl_net_set_params) replays correctly step after step. */
+int frl_clip_adam_dev(const frl_adam_segment* segs, int n_segs, long long* step_dev, double lr, double beta1,
+                      double beta2, double eps, double max_norm, float* norm_out_dev, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16
 EXPORTS = (
     "frl_abi_version", "frl_last_error", "frl_net_create", "frl_net_destroy", "frl_net_num_params",
     "frl_net_set_params", "frl_vfield", "frl_logprob", "frl_score", "frl_score_host", "frl_cfm_loss_grad",
-    "frl_clip_adam", "frl_reg_loss_grad", "frl_grad_axpy", "frl_tensor_norms", "frl_normalise_rewards", "frl_cfm_loss_grad_p",
+    "frl_clip_adam", "frl_reg_loss_grad", "frl_grad_axpy", "frl_tensor_norms", "frl_normalise_rewards", "frl_cfm_loss_grad_p", "frl_clip_adam_dev",
 )
 
 
@@ -69,6 +69,7 @@ def lib():
     L.frl_reg_loss_grad.argtypes = [vp, vp, vp, vp, vp, ll, ll, i32, vp, vp, vp, vp, vp]
     L.frl_grad_axpy.argtypes = [vp, vp, ll, f32, vp, vp, f32, vp, vp, i32, vp]
     L.frl_normalise_rewards.argtypes = [vp, vp, i32, i32, f32, vp, i32, vp, vp, vp, i32, vp]
+    L.frl_clip_adam_dev.argtypes = [C.POINTER(AdamSegment), i32, vp, f64, f64, f64, f64, f64, vp, i32, vp]
     L.frl_tensor_norms.argtypes = [vp, C.POINTER(ll), i32, vp, i32, vp]
     L.frl_clip_adam.argtypes = [C.POINTER(AdamSegment), i32, ll, f64, f64, f64, f64, f64, vp, i32, vp]
     for name in EXPORTS:

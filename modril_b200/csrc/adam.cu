@@ -28,7 +28,10 @@ __device__ __forceinline__ double block_sum(double v) {
     return t;  // valid in thread 0
 }
 
-__global__ void __launch_bounds__(kNormThreads) sumsq_kernel(Segs sg, double* __restrict__ partial) {
+__global__ void __launch_bounds__(kNormThreads) sumsq_kernel(Segs sg, double* __restrict__ partial,
+                                                             long long* __restrict__ step_dev) {
+    // device-resident step counter (CUDA-graph replay): advance it here, the Adam kernel that follows reads it
+    if (step_dev && blockIdx.x == 0 && threadIdx.x == 0) step_dev[0] += 1;
     const long long total = sg.first[sg.n];
     const long long per = (total + gridDim.x - 1) / gridDim.x;
     const long long lo = blockIdx.x * per, hi = min(total, lo + per);
@@ -45,12 +48,21 @@ __global__ void __launch_bounds__(kNormThreads) sumsq_kernel(Segs sg, double* __
 
 struct AdamScalars {
     float one_minus_b1, b2, one_minus_b2, sqrt_bc2, eps, neg_step_size, max_norm;
+    double lr, beta1, beta2;   // used only with a device-resident step counter
 };
 
 __global__ void __launch_bounds__(256) adam_kernel(Segs sg, const double* __restrict__ partial, int n_partial,
-                                                   AdamScalars sc, float* __restrict__ norm_out) {
-    __shared__ float s_coef;
+                                                   AdamScalars sc, float* __restrict__ norm_out,
+                                                   const long long* __restrict__ step_dev) {
+    __shared__ float s_coef, s_sqrt_bc2, s_neg_step;
     if (threadIdx.x == 0) {
+        s_sqrt_bc2 = sc.sqrt_bc2;
+        s_neg_step = sc.neg_step_size;
+        if (step_dev) {   // bias corrections from the device counter (same formulas as the host path below)
+            const double st = (double)step_dev[0];
+            s_sqrt_bc2 = (float)sqrt(1.0 - pow(sc.beta2, st));
+            s_neg_step = (float)(-sc.lr / (1.0 - pow(sc.beta1, st)));
+        }
         double t = 0.0;
         for (int i = 0; i < n_partial; ++i) t += partial[i];  // same order in every block
         const float norm = (float)sqrt(t);
@@ -60,6 +72,8 @@ __global__ void __launch_bounds__(256) adam_kernel(Segs sg, const double* __rest
     }
     __syncthreads();
     const float coef = s_coef;
+    sc.sqrt_bc2 = s_sqrt_bc2;
+    sc.neg_step_size = s_neg_step;
     const long long total = sg.first[sg.n];
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -79,8 +93,8 @@ __global__ void __launch_bounds__(256) adam_kernel(Segs sg, const double* __rest
     }
 }
 
-int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double lr, double beta1, double beta2,
-              double eps, double max_norm, float* norm_out, cudaStream_t stream) {
+int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, long long* step_dev, double lr, double beta1,
+              double beta2, double eps, double max_norm, float* norm_out, cudaStream_t stream) {
     Segs sg{};
     sg.n = n_segs;
     long long total = 0;
@@ -93,7 +107,7 @@ int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double l
     if (total == 0) return FRL_OK;
     double* partial = nullptr;
     FRL_CUDA(cudaMallocAsync((void**)&partial, kNormBlocks * sizeof(double), stream));
-    sumsq_kernel<<<kNormBlocks, kNormThreads, 0, stream>>>(sg, partial);
+    sumsq_kernel<<<kNormBlocks, kNormThreads, 0, stream>>>(sg, partial, step_dev);
     FRL_CUDA(cudaGetLastError());
     const double bc1 = 1.0 - std::pow(beta1, (double)step);
     const double bc2 = 1.0 - std::pow(beta2, (double)step);
@@ -105,8 +119,9 @@ int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double l
     sc.eps = (float)eps;
     sc.neg_step_size = (float)(-lr / bc1);
     sc.max_norm = (float)max_norm;
+    sc.lr = lr; sc.beta1 = beta1; sc.beta2 = beta2;
     int blocks = (int)std::min<long long>((total + 255) / 256, 592);
-    adam_kernel<<<blocks, 256, 0, stream>>>(sg, partial, kNormBlocks, sc, norm_out);
+    adam_kernel<<<blocks, 256, 0, stream>>>(sg, partial, kNormBlocks, sc, norm_out, step_dev);
     FRL_CUDA(cudaGetLastError());
     FRL_CUDA(cudaFreeAsync(partial, stream));
     return FRL_OK;

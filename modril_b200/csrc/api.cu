@@ -277,5 +277,16 @@ extern "C" int frl_clip_adam(const frl_adam_segment* segs, int n_segs, long long
         FRL_REQUIRE(segs[i].n >= 0 && (segs[i].n == 0 || (segs[i].params && segs[i].grad && segs[i].exp_avg &&
                                                           segs[i].exp_avg_sq)), "null segment pointer");
     FRL_CUDA(cudaSetDevice(device));
-    return clip_adam(segs, n_segs, step, lr, beta1, beta2, eps, max_norm, norm_out, (cudaStream_t)stream);
+    return clip_adam(segs, n_segs, step, nullptr, lr, beta1, beta2, eps, max_norm, norm_out, (cudaStream_t)stream);
+}
+
+extern "C" int frl_clip_adam_dev(const frl_adam_segment* segs, int n_segs, long long* step_dev, double lr, double beta1,
+                                 double beta2, double eps, double max_norm, float* norm_out, int device, void* stream) {
+    FRL_REQUIRE(segs && n_segs >= 1 && n_segs <= 4, "1..4 segments");
+    FRL_REQUIRE(step_dev != nullptr, "null step counter");
+    for (int i = 0; i < n_segs; ++i)
+        FRL_REQUIRE(segs[i].n >= 0 && (segs[i].n == 0 || (segs[i].params && segs[i].grad && segs[i].exp_avg &&
+                                                          segs[i].exp_avg_sq)), "null segment pointer");
+    FRL_CUDA(cudaSetDevice(device));
+    return clip_adam(segs, n_segs, 1, step_dev, lr, beta1, beta2, eps, max_norm, norm_out, (cudaStream_t)stream);
 }

@@ -116,8 +116,8 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
                      cudaStream_t stream);
 
 // adam.cu
-int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, double lr, double beta1, double beta2,
-              double eps, double max_norm, float* norm_out, cudaStream_t stream);
+int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, long long* step_dev, double lr, double beta1,
+              double beta2, double eps, double max_norm, float* norm_out, cudaStream_t stream);
 int tensor_norms(const float* flat, const long long* offsets_host, int n_tensors, float* out, cudaStream_t stream);
 
 // returns.cu

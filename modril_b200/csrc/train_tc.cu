@@ -20,10 +20,12 @@
 //                              EPI_RELU  H_l  = relu(D + b)                         (forward)
 //                              EPI_MASK  dZ_l = D * (H_l > 0)                       (dgrad)
 //                              EPI_LOSS  V = D + b_heads -> loss term, dV           (heads forward + CFM loss)
-//   tc_wgrad_kernel          dW = dZ^T X over a range of row tiles (both operands MN-major), M = 128 output features
-//                            per CTA, plus a ones column that yields the bias gradient; partial sums per split
+//   tc_wgrad_kernel          dW = dZ^T X over a range of row tiles (both operands MN-major), all output features in
+//                            one CTA (two M = 128 halves in TMEM); the otherwise idle epilogue warps form the bias
+//                            gradient (column sums of dZ) from the same shared-memory tiles; partial sums per split
 //   tc_reduce_kernel(s)      fixed-order reduction of the partials into the flat fp32 gradient (deterministic)
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "frl_internal.h"
@@ -293,49 +295,57 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// wgrad:  partial[split][m][0..FQ) = sum_{tiles of the split} sum_b P[b][m0+m] Q[b][.],  column FQ = sum_b P[b][m0+m]
+// wgrad:  partial[split][m][0..FQ) = sum_{tiles of the split} sum_b P[b][m] Q[b][.]   for all FP features m of P,
+//         partial[split][m][FQ]    = sum_b P[b][m]                                      (bias gradient)
+// One CTA owns all output features: two M = 128 halves accumulate in TMEM columns [0, FQ) and [256, 256 + FQ), so a
+// row tile costs one P tile + one Q tile of traffic.  P travels in 128-feature halves through a 2-slot ring, Q through
+// a 2-slot ring of whole tiles.  The four epilogue warps are idle until the end, so they form the bias column sums
+// from the P halves in shared memory while the tensor pipe works on them.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kMaxJobs = 2 * kMaxDepth + 2;
+constexpr int kMaxJobs = kMaxDepth + 1;
 struct WgradJob {
     const uint8_t* p_tiles;   // [tile][FP/8][128][8]
     const uint8_t* q_tiles;   // [tile][FQ/8][128][8]
-    float* partial;           // [n_splits][128][FQ + 16]
-    uint32_t p_tile_bytes, p_off, q_tile_bytes;
-    int FQ;
+    float* partial;           // [n_splits][FP][FQ + 16]
+    uint32_t p_tile_bytes, q_tile_bytes;
+    int FP, FQ;
 };
 struct WgradParams {
     WgradJob job[kMaxJobs];
     int n_jobs, n_tiles, n_splits;
 };
-constexpr uint32_t kWgStageBytes = 32768 + 65536;
-constexpr uint32_t kWgOnesOff = 1024, kWgRingOff = 8192;
+constexpr uint32_t kWgPSlot = 32768, kWgQSlot = 65536;
+constexpr uint32_t kWgPOff = 1024, kWgQOff = kWgPOff + 2 * kWgPSlot;
+constexpr uint32_t kWgSmemBytes = kWgQOff + 2 * kWgQSlot;
 
 __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem);
-    auto full = [&](int s) { return bar0 + 8u * s; };
-    auto empty = [&](int s) { return bar0 + 8u * (2 + s); };
-    const uint32_t acc_full = bar0 + 8u * 4;
+    auto p_full = [&](int s) { return bar0 + 8u * s; };
+    auto p_empty = [&](int s) { return bar0 + 8u * (2 + s); };
+    auto q_full = [&](int s) { return bar0 + 8u * (4 + s); };
+    auto q_empty = [&](int s) { return bar0 + 8u * (6 + s); };
+    const uint32_t acc_full = bar0 + 8u * 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
-    uint8_t* sOnes = smem + kWgOnesOff;   // [2][128][8]: feature 0 is 1.0 for every row
-    uint8_t* sRing = smem + kWgRingOff;
+    uint8_t* sP = smem + kWgPOff;
+    uint8_t* sQ = smem + kWgQOff;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const WgradJob& jb = p.job[blockIdx.y];
     const int split = blockIdx.x;
     const int t0 = (int)((long long)split * p.n_tiles / p.n_splits), t1 = (int)((long long)(split + 1) * p.n_tiles / p.n_splits);
+    const int n_halves = jb.FP / kRows;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(full(s), 1);
-            mbar_init(empty(s), 1);
+            mbar_init(p_full(s), 1);
+            mbar_init(p_empty(s), 1 + 4);   // MMA commit + the four column-sum warps
+            mbar_init(q_full(s), 1);
+            mbar_init(q_empty(s), 1);
         }
         mbar_init(acc_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc512(smem_u32(tmem_slot));
-    for (int i = threadIdx.x; i < 2 * kRows; i += kWgradThreads)
-        reinterpret_cast<uint4*>(sOnes)[i] = i < kRows ? make_uint4(0x3C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -343,61 +353,115 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
 
     if (warp == 0) {
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int ps = 0, qs = 0;
+            uint32_t pph = 0, qph = 0;
+            auto load_p = [&](int tile, int mh) {
+                mbar_wait(p_empty(ps), pph ^ 1);
+                mbar_expect_tx(p_full(ps), kWgPSlot);
+                const uint8_t* src = jb.p_tiles + (size_t)tile * jb.p_tile_bytes + (size_t)mh * kWgPSlot;
+                bulk_g2s(smem_u32(sP + ps * kWgPSlot), src, 16384u, p_full(ps));
+                bulk_g2s(smem_u32(sP + ps * kWgPSlot + 16384), src + 16384, 16384u, p_full(ps));
+                if (++ps == 2) { ps = 0; pph ^= 1; }
+            };
             for (int tile = t0; tile < t1; ++tile) {
-                mbar_wait(empty(stage), phase ^ 1);
-                mbar_expect_tx(full(stage), 32768u + jb.q_tile_bytes);
-                uint8_t* dst = sRing + (size_t)stage * kWgStageBytes;
-                bulk_g2s(smem_u32(dst), jb.p_tiles + (size_t)tile * jb.p_tile_bytes + jb.p_off, 16384u, full(stage));
-                bulk_g2s(smem_u32(dst + 16384), jb.p_tiles + (size_t)tile * jb.p_tile_bytes + jb.p_off + 16384u, 16384u, full(stage));
+                load_p(tile, 0);
+                mbar_wait(q_empty(qs), qph ^ 1);
+                mbar_expect_tx(q_full(qs), jb.q_tile_bytes);
                 for (uint32_t off = 0; off < jb.q_tile_bytes; off += kChunkBytes)
-                    bulk_g2s(smem_u32(dst + 32768 + off), jb.q_tiles + (size_t)tile * jb.q_tile_bytes + off,
-                             min((uint32_t)kChunkBytes, jb.q_tile_bytes - off), full(stage));
-                if (++stage == 2) { stage = 0; phase ^= 1; }
+                    bulk_g2s(smem_u32(sQ + qs * kWgQSlot + off), jb.q_tiles + (size_t)tile * jb.q_tile_bytes + off,
+                             min((uint32_t)kChunkBytes, jb.q_tile_bytes - off), q_full(qs));
+                if (++qs == 2) { qs = 0; qph ^= 1; }
+                for (int mh = 1; mh < n_halves; ++mh) load_p(tile, mh);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_f16((uint32_t)jb.FQ, true, true), idesc1 = make_idesc_f16(16u, true, true);
-            const uint32_t ones_addr = smem_u32(sOnes), ring_addr = smem_u32(sRing);
-            int stage = 0;
-            uint32_t phase = 0;
+            const uint32_t idesc = make_idesc_f16((uint32_t)jb.FQ, true, true);
+            const uint32_t p_addr = smem_u32(sP), q_addr = smem_u32(sQ);
+            int ps = 0, qs = 0;
+            uint32_t pph = 0, qph = 0;
             for (int tile = t0; tile < t1; ++tile) {
-                mbar_wait(full(stage), phase);
-                tc_fence_after();
-                const uint32_t pa = ring_addr + stage * kWgStageBytes, qa = pa + 32768;
-                for (int kk = 0; kk < kRows / 16; ++kk) {
-                    // MN-major: 8-row groups are 128 B apart (LBO), 8-feature chunks 128*16 B apart (SBO)
-                    const uint64_t da = make_desc(pa + kk * 256, 128, kRows * 16);
-                    const uint64_t db = make_desc(qa + kk * 256, 128, kRows * 16);
-                    const uint64_t d1 = make_desc(ones_addr + kk * 256, 128, kRows * 16);
-                    const uint32_t acc = (tile != t0 || kk != 0);
-                    umma_f16(tmem, da, db, idesc, acc);
-                    umma_f16(tmem + (uint32_t)jb.FQ, da, d1, idesc1, acc);
+                for (int mh = 0; mh < n_halves; ++mh) {
+                    mbar_wait(p_full(ps), pph);
+                    if (mh == 0) mbar_wait(q_full(qs), qph);
+                    tc_fence_after();
+                    for (int kk = 0; kk < kRows / 16; ++kk) {
+                        // MN-major: 8-row groups are 128 B apart (LBO), 8-feature chunks 128*16 B apart (SBO)
+                        const uint64_t da = make_desc(p_addr + ps * kWgPSlot + kk * 256, 128, kRows * 16);
+                        const uint64_t db = make_desc(q_addr + qs * kWgQSlot + kk * 256, 128, kRows * 16);
+                        umma_f16(tmem + (uint32_t)mh * 256, da, db, idesc, (tile != t0 || kk != 0));
+                    }
+                    umma_commit(p_empty(ps));
+                    if (++ps == 2) { ps = 0; pph ^= 1; }
                 }
-                umma_commit(empty(stage));
-                if (++stage == 2) { stage = 0; phase ^= 1; }
+                umma_commit(q_empty(qs));
+                if (++qs == 2) { qs = 0; qph ^= 1; }
             }
             umma_commit(acc_full);
         }
     } else {
         const int q = warp & 3;
-        const int m = q * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;     // 0..127
+        // column sums of P: thread (chunk = et / 8, g = et % 8) adds rows g, g + 8, ... of one 8-feature chunk
+        const int chunk = et >> 3, g = et & 7;
+        float bsum[2][8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bsum[h][e] = 0.f;
+        int ps = 0;
+        uint32_t pph = 0;
+        for (int tile = t0; tile < t1; ++tile) {
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh) {
+                if (mh < n_halves) {
+                    mbar_wait(p_full(ps), pph);
+                    const uint8_t* src = sP + ps * kWgPSlot + chunk * (kRows * 16) + g * 16;
+#pragma unroll 4
+                    for (int r = 0; r < kRows / 8; ++r) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(src + r * 128);
+                        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __half22float2(hv[e]);
+                            bsum[mh][2 * e] += f.x;
+                            bsum[mh][2 * e + 1] += f.y;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(p_empty(ps));
+                    if (++ps == 2) { ps = 0; pph ^= 1; }
+                }
+            }
+        }
+        const int ldp = jb.FQ + 16;
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float v = bsum[mh][e];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                if (g == 0 && mh < n_halves)
+                    jb.partial[((size_t)split * jb.FP + mh * kRows + chunk * 8 + e) * ldp + jb.FQ] = v;
+            }
         mbar_wait(acc_full, 0);
         tc_fence_after();
-        const int ldp = jb.FQ + 16;
-        float* dst = jb.partial + ((size_t)split * kRows + m) * ldp;
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < ldp; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(taddr + (uint32_t)c0, r);
-            tmem_ld_wait_dep16(r);
+        const int m = q * 32 + lane;
+        for (int mh = 0; mh < n_halves; ++mh) {
+            float* dst = jb.partial + ((size_t)split * jb.FP + mh * kRows + m) * ldp;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)mh * 256;
+            for (int c0 = 0; c0 < jb.FQ; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + (uint32_t)c0, r);
+                tmem_ld_wait_dep16(r);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<float4*>(dst + c0 + 4 * i) =
-                    make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                                __uint_as_float(r[4 * i + 3]));
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<float4*>(dst + c0 + 4 * i) =
+                        make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                    __uint_as_float(r[4 * i + 3]));
+            }
         }
     }
     tc_fence_before();
@@ -415,7 +479,7 @@ struct RedParams {
     const float* part[kMaxJobs];   // per wgrad job
     int ldp[kMaxJobs];
     long long off_w[kMaxDepth], off_b[kMaxDepth], off_wh[2], off_bh[2];
-    int depth, H, d_in, a_dim, n_heads, n_splits, jobs_per_layer;  // jobs_per_layer = H / 128
+    int depth, H, d_in, a_dim, n_heads, n_splits;
     long long n_trunk;   // number of flat entries before the heads
     long long n_params;
     float scale;
@@ -437,23 +501,23 @@ __global__ void tc_reduce_kernel(RedParams rp, float* __restrict__ grad) {
             col = (int)(i % K);
         } else {
             n = (int)(e - rp.off_b[l]);
-            col = rp.ldp[l * rp.jobs_per_layer] - 16;   // the ones column
+            col = rp.ldp[l] - 16;   // the column-sum column
         }
-        job = l * rp.jobs_per_layer + n / kRows;
-        m = n % kRows;
+        job = l;
+        m = n;
     } else {
         int h = (rp.n_heads == 2 && e >= rp.off_wh[1]) ? 1 : 0;
         if (e >= rp.off_bh[h]) return;   // head biases: tc_reduce_small_kernel
         const long long i = e - rp.off_wh[h];
         const int j = (int)(i / rp.H), k = (int)(i % rp.H);
-        job = rp.depth * rp.jobs_per_layer + k / kRows;
-        m = k % kRows;
+        job = rp.depth;
+        m = k;
         col = h * rp.a_dim + j;
     }
     const float* P = rp.part[job];
     const int ldp = rp.ldp[job];
     float acc = 0.f;
-    for (int s = 0; s < rp.n_splits; ++s) acc += P[((size_t)s * kRows + m) * ldp + col];
+    for (int s = 0; s < rp.n_splits; ++s) acc += P[((size_t)s * rp.H + m) * ldp + col];
     acc *= rp.scale;
     grad[e] = rp.accumulate ? grad[e] + acc : acc;
 }
@@ -571,13 +635,48 @@ int tc_train_pack(frl_net* net, const float* params_dev, cudaStream_t st) {
     return FRL_OK;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the opt-in maximum
+static cudaError_t set_smem_attr_impl(const void* kern, int device) {
+    struct Seen { const void* k; int dev; };
+    static Seen seen[64];
+    static int n_seen = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i].k == kern && seen[i].dev == device) return cudaSuccess;
+    int max_smem = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e == cudaSuccess && n_seen < 64) seen[n_seen++] = Seen{kern, device};
+    return e;
+}
+template <typename K>
+static cudaError_t set_smem_attr(K kern, int device, int /*bytes*/) {
+    return set_smem_attr_impl(reinterpret_cast<const void*>(kern), device);
+}
+
+struct DevInfo { int sms, max_smem; };
+static int dev_info(int device, DevInfo* out) {
+    static DevInfo cache[64];
+    static bool have[64] = {};
+    if (device >= 0 && device < 64 && have[device]) { *out = cache[device]; return FRL_OK; }
+    DevInfo d{};
+    FRL_CUDA(cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    FRL_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, device));
+    if (device >= 0 && device < 64) { cache[device] = d; have[device] = true; }
+    *out = d;
+    return FRL_OK;
+}
+
 template <int EPI>
 static int launch_layer(const ttc::LayerParams& p0, int device, cudaStream_t st) {
     using namespace ttc;
     LayerParams p = p0;
-    int max_smem = 0, sms = 0;
-    FRL_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    FRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    DevInfo di{};
+    int rc0 = dev_info(device, &di);
+    if (rc0 != FRL_OK) return rc0;
+    const int max_smem = di.max_smem, sms = di.sms;
     const size_t base = 2048 + ((size_t)p.K * p.N * 2 + 1023) / 1024 * 1024;
     int stages = (int)(((size_t)max_smem - base) / kChunkBytes);
     stages = std::min(stages, kMaxStages);
@@ -589,7 +688,7 @@ static int launch_layer(const ttc::LayerParams& p0, int device, cudaStream_t st)
     // > half of the SM's shared memory, so exactly one CTA (and its 512 TMEM columns) lives on an SM
     const size_t smem_bytes = std::max(base + (size_t)stages * kChunkBytes, (size_t)120 * 1024);
     auto kern = tc_layer_kernel<EPI>;
-    FRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FRL_CUDA(set_smem_attr(kern, device, (int)smem_bytes));
     kern<<<std::min(p.n_tiles, sms), kLayerThreads, smem_bytes, st>>>(p);
     FRL_CUDA(cudaGetLastError());
     return FRL_OK;
@@ -610,10 +709,11 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
     const TrainPack tp = train_pack_layout(net);
     const uint8_t* pk = static_cast<const uint8_t*>(net->pack_train);
 
-    int sms = 0;
-    FRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    const int jpl = H / kRows;                    // M halves per layer
-    const int n_jobs = (depth + 1) * jpl;         // trunk layers + heads
+    DevInfo di{};
+    int rc = dev_info(device, &di);
+    if (rc != FRL_OK) return rc;
+    const int sms = di.sms;
+    const int n_jobs = depth + 1;                 // trunk layers + heads
     const int n_splits = std::max(1, std::min(nt, sms / n_jobs));
 
     // ---- workspace (bytes) ----
@@ -630,9 +730,8 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
     size_t o_part[kMaxJobs];
     int ldp[kMaxJobs];
     for (int j = 0; j < n_jobs; ++j) {
-        const int l = j / jpl;
-        ldp[j] = (l == 0 ? K0p : (l == depth ? NOp : H)) + 16;
-        o_part[j] = take((size_t)n_splits * kRows * ldp[j] * sizeof(float));
+        ldp[j] = (j == 0 ? K0p : (j == depth ? NOp : H)) + 16;
+        o_part[j] = take((size_t)n_splits * H * ldp[j] * sizeof(float));
     }
     if (net->ws_tc_bytes < off) {
         if (net->ws_tc) FRL_CUDA(cudaFree(net->ws_tc));   // synchronises: earlier work is done with it
@@ -651,7 +750,6 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
         tc_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, a0, t, noise, ws + o_x0, B, nt, net->cfg.s_dim, A, K0p);
         FRL_CUDA(cudaGetLastError());
     }
-    int rc;
     for (int l = 0; l < depth; ++l) {
         LayerParams p{};
         p.a_tiles = l == 0 ? ws + o_x0 : ws + o_h[l - 1];
@@ -681,7 +779,7 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
     }
     RedParams rp{};
     rp.depth = depth; rp.H = H; rp.d_in = net->d_in; rp.a_dim = A; rp.n_heads = net->cfg.n_heads;
-    rp.n_splits = n_splits; rp.jobs_per_layer = jpl;
+    rp.n_splits = n_splits;
     for (int l = 0; l < depth; ++l) { rp.off_w[l] = net->off_w[l]; rp.off_b[l] = net->off_b[l]; }
     for (int h = 0; h < net->cfg.n_heads; ++h) { rp.off_wh[h] = net->off_wh[h]; rp.off_bh[h] = net->off_bh[h]; }
     rp.n_trunk = net->off_wh[0];
@@ -724,19 +822,18 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
     {
         WgradParams wp{};
         wp.n_jobs = n_jobs; wp.n_tiles = nt; wp.n_splits = n_splits;
-        for (int j = 0; j < n_jobs; ++j) {
-            const int l = j / jpl, mh = j % jpl;
-            WgradJob& jb = wp.job[j];
+        for (int l = 0; l < n_jobs; ++l) {
+            WgradJob& jb = wp.job[l];
             jb.p_tiles = l == depth ? ws + o_h[depth - 1] : ws + o_dz[l];
             jb.p_tile_bytes = (uint32_t)tileH;
-            jb.p_off = (uint32_t)mh * (kRows / 8) * (kRows * 16);
+            jb.FP = H;
             if (l == 0) { jb.q_tiles = ws + o_x0; jb.q_tile_bytes = (uint32_t)tileX; jb.FQ = K0p; }
             else if (l == depth) { jb.q_tiles = ws + o_dv; jb.q_tile_bytes = (uint32_t)tileV; jb.FQ = NOp; }
             else { jb.q_tiles = ws + o_h[l - 1]; jb.q_tile_bytes = (uint32_t)tileH; jb.FQ = H; }
-            jb.partial = reinterpret_cast<float*>(ws + o_part[j]);
+            jb.partial = reinterpret_cast<float*>(ws + o_part[l]);
         }
-        const size_t smem_bytes = kWgRingOff + 2 * (size_t)kWgStageBytes;
-        FRL_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        const size_t smem_bytes = kWgSmemBytes;
+        FRL_CUDA(set_smem_attr(tc_wgrad_kernel, device, (int)smem_bytes));
         tc_wgrad_kernel<<<dim3(n_splits, n_jobs), kWgradThreads, smem_bytes, st>>>(wp);
         FRL_CUDA(cudaGetLastError());
     }

@@ -385,18 +385,29 @@ class FusedAdam(torch.optim.Optimizer):
     ``grad is None`` in ``clip_grad_norm_`` / Adam).
     """
 
-    def __init__(self, nets, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, nets, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, capturable=False):
+        """capturable=True keeps the step count on the device (``frl_clip_adam_dev``), so a whole update
+        (``train_step``) can be captured into a CUDA graph (``torch.cuda.graph``) and replayed."""
         self.nets = list(nets)
         params = [p for net in self.nets for p, _, _ in net.param_slices() if p.requires_grad]
         if not params:
             raise ValueError("optimizer got an empty parameter list")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False,
-                                      foreach=None, capturable=False, differentiable=False, fused=None))
+                                      foreach=None, capturable=bool(capturable), differentiable=False, fused=None))
         self._step = 0
+        self._step_dev = None
+        if capturable:
+            self._step_dev = torch.zeros(1, dtype=torch.int64, device=self.nets[0].flat_params().device)
         self._m = [torch.zeros_like(net.flat_params()) for net in self.nets]
         self._v = [torch.zeros_like(net.flat_params()) for net in self.nets]
         self._norm = None
+        self._seg_cache = None
         self._bind_state()
+
+    def step_count(self) -> int:
+        if self._step_dev is not None:
+            self._step = int(self._step_dev.item())
+        return self._step
 
     def _bind_state(self):
         for net, m, v in zip(self.nets, self._m, self._v):
@@ -406,8 +417,20 @@ class FusedAdam(torch.optim.Optimizer):
                                      "exp_avg": m[off:off + n].view(p.shape),
                                      "exp_avg_sq": v[off:off + n].view(p.shape)}
 
+    def state_dict(self):
+        step = float(self.step_count())
+        for st in self.state.values():   # the per-parameter step tensors are refreshed lazily, not every step
+            st["step"].fill_(step)
+        return super().state_dict()
+
     def _segments(self, grads):
-        """Contiguous runs of trainable parameters per net -> frl_adam_segment array."""
+        """Contiguous runs of trainable parameters per net -> frl_adam_segment array (cached while the buffers and
+        the trainable pattern stay the same)."""
+        key = tuple((net.flat_params().data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+                     tuple(p.requires_grad for p, _, _ in net.param_slices()))
+                    for net, m, v, g in zip(self.nets, self._m, self._v, grads))
+        if self._seg_cache is not None and self._seg_cache[0] == key:
+            return self._seg_cache[1], self._seg_cache[2]
         segs = []
         for net, m, v, g in zip(self.nets, self._m, self._v, grads):
             flat = net.flat_params()
@@ -427,6 +450,7 @@ class FusedAdam(torch.optim.Optimizer):
             arr[i].exp_avg = m.data_ptr() + 4 * off
             arr[i].exp_avg_sq = v.data_ptr() + 4 * off
             arr[i].n = n
+        self._seg_cache = (key, arr, len(segs))
         return arr, len(segs)
 
     @torch.no_grad()
@@ -434,19 +458,23 @@ class FusedAdam(torch.optim.Optimizer):
         """Clip (global norm over all trainable segments) + Adam on flat gradient buffers, one kernel pair."""
         dev = self.nets[0].flat_params().device
         group = self.param_groups[0]
-        self._step += 1
         arr, n = self._segments(grads)
         if self._norm is None or self._norm.device != dev:
             self._norm = torch.zeros(1, device=dev)
         b1, b2 = group["betas"]
         mx = float(max_norm) if math.isfinite(max_norm) else 3.0e38
-        _native.check(_native.lib().frl_clip_adam(arr, n, self._step, float(group["lr"]), float(b1), float(b2),
-                                                  float(group["eps"]), mx, _ptr(self._norm), dev.index or 0,
-                                                  _current_stream(dev)), "frl_clip_adam")
+        L = _native.lib()
+        if self._step_dev is not None:
+            _native.check(L.frl_clip_adam_dev(arr, n, _ptr(self._step_dev), float(group["lr"]), float(b1), float(b2),
+                                              float(group["eps"]), mx, _ptr(self._norm), dev.index or 0,
+                                              _current_stream(dev)), "frl_clip_adam_dev")
+        else:
+            self._step += 1
+            _native.check(L.frl_clip_adam(arr, n, self._step, float(group["lr"]), float(b1), float(b2),
+                                          float(group["eps"]), mx, _ptr(self._norm), dev.index or 0,
+                                          _current_stream(dev)), "frl_clip_adam")
         for net in self.nets:
             net.mark_dirty()
-        for st in self.state.values():
-            st["step"].fill_(float(self._step))
         return self._norm
 
     @torch.no_grad()
@@ -476,6 +504,9 @@ class FusedAdam(torch.optim.Optimizer):
                     v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
                     steps.append(int(float(st["step"])))
         self._step = max(steps) if steps else 0
+        if self._step_dev is not None:
+            self._step_dev.fill_(self._step)
+        self._seg_cache = None
         self._bind_state()
 
 
