@@ -516,8 +516,9 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
     clip_grad_norm_(max_norm); Adam.
 
     terms: list of dicts {net, sign, s, a0, t, noise, rate}; several terms may share a net (scrf: expert + agent).
-    world: optional (process_group, world_size) for data-parallel training: each rank passes its shard, the mean
-           divisor becomes the global batch and the flat gradients are all-reduced (sum) before the clip.
+    world: optional (process_group, world_size[, global_rows]) for data-parallel training: each rank passes its shard,
+           the mean divisor becomes the global batch (``global_rows`` per term when the shards are ragged, else
+           local rows * world_size) and the flat gradients are all-reduced (sum) before the clip.
     reg:   optional dict for the scrf regularisers (reference flowril.py:255-290):
              net, s, a, t, probe      the mixed batch, its times and Rademacher probe
              anti / stable            how each term is weighted: None (off), a float (fixed weight,
@@ -536,6 +537,7 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
     seen = []
     losses = []
     ws = 1 if world is None else world[1]
+    global_rows = world[2] if (world is not None and len(world) > 2) else None
     for term in terms:
         net = term["net"]
         dev = net.flat_params().device
@@ -550,7 +552,8 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
         noise = as_f32_cuda(term["noise"], dev, "noise")
         B = a0.shape[0]
         loss = torch.empty(1, device=dev)
-        _native.check(L.frl_cfm_loss_grad_p(h, float(term["sign"]), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B, B * ws,
+        _native.check(L.frl_cfm_loss_grad_p(h, float(term["sign"]), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B,
+                                            int(global_rows) if global_rows else B * ws,
                                             float(term.get("rate", 1.0)), 0 if first else 1, _ptr(loss), _ptr(g), prec,
                                             _current_stream(dev)), "frl_cfm_loss_grad_p")
         losses.append(loss)
@@ -565,7 +568,8 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
         rnet = reg["net"]
         N = reg["a"].shape[0]
         rout = reg_losses_native(rnet, reg["s"], reg["a"], reg["t"], reg["probe"], anti=reg.get("anti") is not None,
-                                 stable=reg.get("stable") is not None, need_grad=True, mean_divisor=N * ws)
+                                 stable=reg.get("stable") is not None, need_grad=True,
+                                 mean_divisor=int(reg["global_rows"]) if reg.get("global_rows") else N * ws)
         reg["out"] = rout
     if world is not None and ws > 1:
         from ..dist import allreduce_flat
