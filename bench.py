@@ -253,6 +253,7 @@ def run_ours(args):
         flush.zero_()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    torch.cuda.profiler.start()   # `ncu --profile-from-start off` then lists exactly the timed region's launches
     with ClockSampler(local) as clocks:
         for e0, e1 in ev:
             e0.record()
@@ -260,6 +261,7 @@ def run_ours(args):
             e1.record()
             flush.zero_()
         barrier()
+    torch.cuda.profiler.stop()
     total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     tt = torch.tensor([total_ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -370,8 +372,17 @@ def run_ours(args):
     achieved = flops / (ms_per_step / 1e3) / 1e12
     if prec == "fp32":
         peak, peak_src = 2 * 128 * 148 * 1.965e9 / 1e12, "FP32 FFMA peak 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)"
+    traffic, traffic_src = None, None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            ent = json.load(f).get(f"{args.workload}:{prec}:{B}")
+        if ent:
+            traffic, traffic_src = ent["bytes_per_launch"], ent["source"]
+    except Exception:
+        pass
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": B * ((s_dim + 2 * a_dim) * 4 + 12), "peak_source": peak_src,
             "kernel": "logprob_tc_kernel" if prec != "fp32" else "logprob_f32_kernel",
             "algorithmic_flops_per_sample": algorithmic_flops_per_sample(s_dim, a_dim, n_steps)}
 
@@ -412,7 +423,7 @@ def run_ours(args):
                           + ("; replayed as one CUDA graph" if use_graph else ""),
                   "fp32_ffma_samples_per_sec": train_rates["fp32"],
                   "algorithmic_tflops": train_rate * 3 * f_fwd_train / 1e12,
-                  "frac_of_peak": train_rate * 3 * f_fwd_train / 1e12 / measured_peak_tflops()[0],
+                  "frac_of_peak": train_rate * 3 * f_fwd_train / 1e12 / measured_peak_tflops()[0] / world,
                   "collective": "NCCL all-reduce of the flat grad" if world > 1 else "none"},
     }
     print(json.dumps(line), flush=True)
