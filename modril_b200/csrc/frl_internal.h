@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/flowril_b200.h"
 
@@ -56,6 +57,7 @@ struct frl_net {
     // tensor-core packing (bf16 hi/mid/lo canonical UMMA tiles), see logprob_tc.cu
     void* pack_tc = nullptr;
     size_t pack_tc_bytes = 0;
+    void* pack_tc2 = nullptr;           // block stream of the 64+64-row / N = 256 integrator (logprob_tc2.cu)
     bool has_params = false;
     // tensor-core training: fp16 weight images (train_tc.cu) and workspace
     void* pack_train = nullptr;
@@ -95,8 +97,21 @@ int launch_reward(const float* logp_e, const float* logp_a, float* reward, long 
                   cudaStream_t stream);
 
 // logprob_tc.cu
+namespace tc {
+constexpr int kMaxBlocks = 72;
+struct PackBlk {
+    uint32_t goff;                   // bytes
+    int nrows, klen, n0, k0, layer;  // layer == depth -> heads;  k0 < 0 -> bias block (rows k=0..2 = hi/mid/lo split)
+};
+}  // namespace tc
 int tc_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
+int tc_pack_images(frl_net* net, const std::vector<tc::PackBlk>& pack, uint32_t image_bytes, void** dst,
+                   const float* params_dev, cudaStream_t stream);
 int launch_logprob_tc(const ScoreArgs& args, int precision, cudaStream_t stream);
+
+// logprob_tc2.cu
+int tc2_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
+int launch_logprob_tc2(const ScoreArgs& args, int precision, cudaStream_t stream);
 
 // train_f32.cu
 int cfm_loss_grad_f32(frl_net* net, float role_sign, const float* s, const float* a0, const float* t,

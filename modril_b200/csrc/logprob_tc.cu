@@ -35,7 +35,6 @@ namespace tc {
 constexpr int kThreads = 384;          // 12 warps: producer, MMA-primal, MMA-tangent, TMEM owner, 8 epilogue
 constexpr int kEpiWarps = 8;
 constexpr int kStageBytes = 16384;
-constexpr int kMaxBlocks = 72;
 constexpr int kRows = 128;
 
 struct Blk {
@@ -598,10 +597,6 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
 // ---------------------------------------------------------------------------------------------------------------
 // weight packing: fp32 flat parameters -> fp16 and bf16 block images + fp32 bias vector
 // ---------------------------------------------------------------------------------------------------------------
-struct PackBlk {
-    uint32_t goff;          // bytes
-    int nrows, klen, n0, k0, layer;  // layer == depth -> heads;  k0 < 0 -> bias block (rows k=0..2 = hi/mid/lo split)
-};
 struct PackParams {
     PackBlk blk[kMaxBlocks];
     int n_blocks;
@@ -739,29 +734,36 @@ struct TcPack {
 
 }  // namespace tc
 
-int tc_pack(frl_net* net, const float* params_dev, cudaStream_t stream) {
+// fp16 + bf16 images of a block list (+ the fp32 bias vector) into *dst (allocated on first use):
+// layout [fp16 image | bf16 image | bias], each image rounded up to 256 B
+int tc_pack_images(frl_net* net, const std::vector<tc::PackBlk>& pack, uint32_t image_bytes, void** dst,
+                   const float* params_dev, cudaStream_t stream) {
     using namespace tc;
-    Schedule sc = make_schedule(net);
-    if ((int)sc.blk.size() > kMaxBlocks) return FRL_OK;
     const int nb = net->cfg.depth * net->cfg.hidden + net->n_out_p;
-    const size_t img = (sc.image_bytes + 255) / 256 * 256;
+    const size_t img = ((size_t)image_bytes + 255) / 256 * 256;
     const size_t total = 2 * img + (size_t)nb * sizeof(float);
-    if (!net->pack_tc) {
-        FRL_CUDA(cudaMalloc(&net->pack_tc, total));
-        net->pack_tc_bytes = total;
-    }
+    if (!*dst) FRL_CUDA(cudaMalloc(dst, total));
     PackParams pp{};
-    pp.n_blocks = (int)sc.pack.size();
-    for (int i = 0; i < pp.n_blocks; ++i) pp.blk[i] = sc.pack[i];
+    pp.n_blocks = (int)pack.size();
+    for (int i = 0; i < pp.n_blocks; ++i) pp.blk[i] = pack[i];
     for (int l = 0; l < net->cfg.depth; ++l) { pp.off_w[l] = net->off_w[l]; pp.off_b[l] = net->off_b[l]; }
     for (int h = 0; h < net->cfg.n_heads; ++h) { pp.off_wh[h] = net->off_wh[h]; pp.off_bh[h] = net->off_bh[h]; }
     pp.depth = net->cfg.depth; pp.H = net->cfg.hidden; pp.d_in = net->d_in; pp.a_dim = net->cfg.a_dim;
-    pp.n_heads = net->cfg.n_heads; pp.NOp = net->n_out_p; pp.image_bytes = sc.image_bytes;
-    uint8_t* base = static_cast<uint8_t*>(net->pack_tc);
+    pp.n_heads = net->cfg.n_heads; pp.NOp = net->n_out_p; pp.image_bytes = image_bytes;
+    uint8_t* base = static_cast<uint8_t*>(*dst);
     tc_pack_kernel<<<dim3(4, pp.n_blocks + 1), 256, 0, stream>>>(params_dev, base, base + img,
                                                                  reinterpret_cast<float*>(base + 2 * img), pp);
     FRL_CUDA(cudaGetLastError());
     return FRL_OK;
+}
+
+int tc_pack(frl_net* net, const float* params_dev, cudaStream_t stream) {
+    using namespace tc;
+    Schedule sc = make_schedule(net);
+    if ((int)sc.blk.size() > kMaxBlocks) return FRL_OK;
+    int rc = tc_pack_images(net, sc.pack, sc.image_bytes, &net->pack_tc, params_dev, stream);
+    if (rc != FRL_OK) return rc;
+    return tc2_pack(net, params_dev, stream);
 }
 
 template <typename T16, int H>
@@ -779,6 +781,13 @@ int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
     if (precision == FRL_PREC_BF16X3) {
         set_error("FRL_PREC_BF16X3 is not implemented in this build");
         return FRL_ERR_UNSUPPORTED;
+    }
+    // FRL_TC_V2=1 selects the experimental 64-sample / N = 256 integrator (logprob_tc2.cu).  It is parity-green but on
+    // one CTA its two in-flight tiles outgrow the shared-memory weight ring (profiles/r01f_tc2_experiment.md), so the
+    // 128-sample kernel below stays the default until the cta_group::2 version halves the ring bytes per CTA.
+    if (n0->pack_tc2 && getenv("FRL_TC_V2")) {
+        const int rc2 = launch_logprob_tc2(a, precision, stream);
+        if (rc2 <= 0) return rc2;   // > 0: shapes that do not fit the 64-sample kernel's shared-memory plan
     }
     if (!n0->pack_tc) {
         set_error("tensor-core weight image missing (network too deep for the block table)");

@@ -230,3 +230,25 @@ def test_full_size_properties():
     ref = cf.log_prob(spec, flat, s[idx], a[idx], "expert", probe[idx], n)
     assert_close(le[idx].cpu().numpy(), ref, 1e-4, "64k slice vs oracle", 0.011)
     assert torch.isfinite(rw).all()
+
+
+@pytest.mark.parametrize("task", ["maze", "hopper", "sine", "pick"])
+def test_experimental_n256_integrator_matches_default_kernel(task, monkeypatch):
+    """The experimental 64-sample-tile / N = 256 tcgen05 integrator (FRL_TC_V2=1, csrc/logprob_tc2.cu) computes the same
+    fp16 arithmetic as the default 128-sample kernel up to fp32 bias rounding (it adds trunk biases in the epilogue
+    instead of folding a 3-term split into the MMA): agreement far inside the fp16 mode's own 2e-3 bar, ragged B."""
+    sd, ad = synth.TASK_DIMS[task]
+    spec = cf.NetSpec(sd, ad, 256, 4, 2)
+    m = build_model(spec, cf.make_params(spec, 21, 1.0))
+    B = 1000
+    s, a = synth.states_actions(31, B, sd, ad)
+    probe = synth.rademacher(32, (B, ad))
+    ref = m.score(dev(s), dev(a), n_steps=20, probe=dev(probe), precision="fp16")
+    monkeypatch.setenv("FRL_TC_V2", "1")
+    got = m.score(dev(s), dev(a), n_steps=20, probe=dev(probe), precision="fp16")
+    monkeypatch.delenv("FRL_TC_V2")
+    f32 = m.score(dev(s), dev(a), n_steps=20, probe=dev(probe), precision="fp32")
+    for g, r, f in zip(got, ref, f32):
+        assert_close(g.cpu().numpy(), f.cpu().numpy(), 2e-3, f"{task} v2 vs fp32", kink_frac=0.02)
+        d = (g - r).abs() / r.abs().clamp_min(1.0)
+        assert float(d.median()) <= 2e-4, float(d.median())
