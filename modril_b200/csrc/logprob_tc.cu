@@ -32,7 +32,8 @@ namespace frl {
 
 namespace tc {
 
-constexpr int kThreads = 384;          // 12 warps: producer, MMA-primal, MMA-tangent, TMEM owner, 8 epilogue
+constexpr int kThreads = 416;          // 13 warps: producer (+TMEM owner), 4 MMA issuers, 8 epilogue
+constexpr int kMmaWarps = 4;           // (accumulator half) x (primal | tangent)
 constexpr int kEpiWarps = 8;
 constexpr int kStageBytes = 16384;
 constexpr int kRows = 128;
@@ -256,15 +257,15 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(w_full(s), 1);
-            mbar_init(w_empty(s), 2);   // one arrival per MMA-issuing warp
+            mbar_init(w_empty(s), kMmaWarps);   // one arrival per MMA-issuing warp
         }
         mbar_init(a_ready(0), kEpiWarps);
         mbar_init(a_ready(1), kEpiWarps);
-        mbar_init(d_full(0), 2);
-        mbar_init(d_full(1), 2);
+        mbar_init(d_full(0), kMmaWarps);
+        mbar_init(d_full(1), kMmaWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 3) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "n"(512)
                      : "memory");
@@ -279,31 +280,32 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
         const uint32_t one = Cvt<T16>::one(1.f);
         reinterpret_cast<uint4*>(sOnes)[i] = i < kRows ? make_uint4(one | (one << 16), one, 0, 0) : make_uint4(0, 0, 0, 0);
     }
-    // per-block issue records for the two MMA warps (two 16-byte shared-memory loads per block in the hot loop).
-    // Work split: MMA warp j owns accumulator half h == j of the trunk / layer-0 / bias blocks and issues BOTH tiles
-    // there; in the heads blocks warp 0 issues the primal tile and warp 1 the tangent tile.  (One thread pays ~60
-    // cycles per tcgen05.mma and ~230 per tcgen05.commit -- tests/umma_bench.cu -- so a single issuer is slower
-    // than the tensor pipe at N = 128; two issuers working on different accumulators are not.)
-    uint4* sRec = reinterpret_cast<uint4*>(smem + p.off_rec);  // [2 warps][n_blocks][2]
-    for (int i = threadIdx.x; i < 2 * p.n_blocks; i += kThreads) {
-        const int j = i / p.n_blocks, b = i % p.n_blocks;
+    // per-block issue records of the four MMA warps (two 16-byte shared-memory loads per block in the hot loop).
+    // Work split: MMA warp w = 2*h + x issues tile x (0 primal, 1 tangent) of accumulator half h for the trunk /
+    // layer-0 / bias blocks; in the heads blocks warp 0 issues the primal tile and warp 1 the tangent tile.  One thread
+    // pays ~60 cycles per tcgen05.mma and ~230 per tcgen05.commit (tests/umma_bench.cu) while an N = 128 MMA holds the
+    // tensor pipe for 64, so the issue work is spread over four threads; primal and tangent go to different
+    // accumulators, so their relative order does not matter and the results stay deterministic.
+    uint4* sRec = reinterpret_cast<uint4*>(smem + p.off_rec);  // [4 warps][n_blocks][2]
+    for (int i = threadIdx.x; i < kMmaWarps * p.n_blocks; i += kThreads) {
+        const int w = i / p.n_blocks, b = i % p.n_blocks;
         const Blk& k = p.blk[b];
         const bool heads = k.nrows != NH;  // only the heads blocks have N != H/2 (NOp <= 64 < H/2)
-        uint32_t a_lo[2] = {0, 0}, dcol[2] = {0, 0}, nk[2] = {0, 0}, first[2] = {0, 0};
-        for (int x = 0; x < 2; ++x) {
-            const bool mine = heads ? (x == j) : (k.h == j);
-            if (!mine) continue;
+        const int x = w & 1;
+        const bool mine = heads ? (w < 2) : ((int)k.h == (w >> 1));
+        uint32_t a_lo = 0, dcol = 0, nk = 0, first = 0;
+        if (mine) {
             const uint32_t src = k.src == 0 ? smem_u32(smem + p.off_a) + x * a_tile_bytes
                                  : (k.src == 1 ? smem_u32(x == 0 ? sX0p : sX0t) : smem_u32(sOnes));
-            a_lo[x] = (((src + (uint32_t)k.a_koff * (kRows * 16)) >> 4) & 0x3FFF) | ((uint32_t)(kRows * 16 >> 4) << 16);
-            dcol[x] = (uint32_t)k.h * 256 + (uint32_t)x * 128;
-            nk[x] = x == 0 ? k.n_k16 : k.n_k16_t;
-            first[x] = (k.first >> x) & 1;
+            a_lo = (((src + (uint32_t)k.a_koff * (kRows * 16)) >> 4) & 0x3FFF) | ((uint32_t)(kRows * 16 >> 4) << 16);
+            dcol = (uint32_t)k.h * 256 + (uint32_t)x * 128;
+            nk = x == 0 ? k.n_k16 : k.n_k16_t;
+            first = (k.first >> x) & 1;
         }
         const uint32_t idesc = (1u << 4) | (Cvt<T16>::kFmt << 7) | (Cvt<T16>::kFmt << 10) | ((uint32_t)(kRows >> 4) << 24) |
                                ((uint32_t)(k.nrows >> 3) << 17);
-        sRec[2 * i] = make_uint4(a_lo[0], a_lo[1], idesc, (uint32_t)k.nrows | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24));
-        sRec[2 * i + 1] = make_uint4(dcol[0], dcol[1], nk[0] | (first[0] << 8) | (nk[1] << 16) | (first[1] << 24), 0);
+        sRec[2 * i] = make_uint4(a_lo, dcol, idesc, (uint32_t)k.nrows | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24));
+        sRec[2 * i + 1] = make_uint4(nk | (first << 8), 0, 0, 0);
     }
     fence_async_smem();
     tc_fence_before();
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
                 }
             }
         }
-    } else if (warp == 1 || warp == 2) {
+    } else if (warp >= 1 && warp <= kMmaWarps) {
         // ------------------------------ MMA issuers (see the record table above for the work split) ----------------
         if (lane == 0) {
             const int j = warp - 1;
@@ -347,41 +349,32 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
             const uint4* rec = sRec + (size_t)j * p.n_blocks * 2;
             const uint32_t ring_lo = (smem_u32(sRing) >> 4);
             constexpr uint32_t kDescHi = (uint32_t)(128 >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
-            Tracer tr; tr.init(p.trace, 1 + j);
+            Tracer tr; tr.init(j < 2 ? p.trace : nullptr, 1 + j);
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int step = 0; step < p.n_steps; ++step) {
                     for (int b = 0; b < p.n_blocks; ++b) {
                         const uint4 r0 = rec[2 * b], r1 = rec[2 * b + 1];
                         tr.mark(0x100 + b);
+                        // every issuer observes every readiness phase of the activations, whether or not it issues here
                         if (r0.w & (1u << 24)) { mbar_wait(a_ready(0), par_a0); par_a0 ^= 1; }
                         if (r0.w & (2u << 24)) { mbar_wait(a_ready(1), par_a1); par_a1 ^= 1; }
-                        const uint32_t nk0 = (p.debug & 2) ? 0 : (r1.z & 0xFF), nk1 = (p.debug & 2) ? 0 : ((r1.z >> 16) & 0xFF);
+                        const uint32_t nk = (p.debug & 2) ? 0 : (r1.x & 0xFF);
                         const uint32_t cm = (r0.w >> 16) & 0xFF;
                         // every issuer observes every fill of the ring (a warp that ran ahead through blocks it does
                         // not own could otherwise arrive twice on one w_empty phase and release a stage too early)
                         mbar_wait(w_full(stage), phase);
-                        if (nk0 | nk1) {
+                        if (nk) {
                             tc_fence_after();
                             tr.mark(0x300 + b);
                             const uint32_t nrows = r0.w & 0xFFFF;
-                            const uint32_t b_lo0 = ((ring_lo + (uint32_t)stage * (kStageBytes >> 4)) & 0x3FFF) | (nrows << 16);
-                            {
-                                uint32_t a_lo = r0.x, b_lo = b_lo0, acc = ((r1.z >> 8) & 1) ? 0u : 1u;
-                                for (uint32_t u = 0; u < nk0; ++u) {
-                                    umma(tmem + r1.x, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, r0.z, acc);
-                                    acc = 1u;
-                                    a_lo += 2 * (kRows * 16 >> 4);   // two k-chunks of 8 per K=16 MMA
-                                    b_lo += 2 * nrows;
-                                }
-                            }
-                            {
-                                uint32_t a_lo = r0.y, b_lo = b_lo0, acc = ((r1.z >> 24) & 1) ? 0u : 1u;
-                                for (uint32_t u = 0; u < nk1; ++u) {
-                                    umma(tmem + r1.y, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, r0.z, acc);
-                                    acc = 1u;
-                                    a_lo += 2 * (kRows * 16 >> 4);
-                                    b_lo += 2 * nrows;
-                                }
+                            uint32_t a_lo = r0.x;
+                            uint32_t b_lo = ((ring_lo + (uint32_t)stage * (kStageBytes >> 4)) & 0x3FFF) | (nrows << 16);
+                            uint32_t acc = ((r1.x >> 8) & 1) ? 0u : 1u;
+                            for (uint32_t u = 0; u < nk; ++u) {
+                                umma(tmem + r0.y, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, r0.z, acc);
+                                acc = 1u;
+                                a_lo += 2 * (kRows * 16 >> 4);   // two k-chunks of 8 per K=16 MMA
+                                b_lo += 2 * nrows;
                             }
                             umma_commit(w_empty(stage));
                             if (cm) umma_commit(d_full(cm - 1));
@@ -396,11 +389,9 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
                 }
             }
         }
-    } else if (warp == 3) {
-        // TMEM owner: nothing to do until teardown
-    } else {
+    } else if (warp > kMmaWarps) {
         // ------------------------------------------------ epilogue ------------------------------------------------
-        const int ew = warp - 4;            // 0..7
+        const int ew = warp - (kMmaWarps + 1);   // 0..7
         const int q = warp & 3;             // TMEM lane quarter this warp may access
         const int ch = ew >> 2;             // which half of the N-half's columns
         const int row = q * 32 + lane;      // tile row == TMEM lane
@@ -588,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 3) {
+    if (warp == 0) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
     }
@@ -828,7 +819,7 @@ int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
     p.off_bias = off; off += (uint32_t)(a.n_roles * nb) * 4;
     off = (off + 15) / 16 * 16;
     p.off_state = off; off += 2u * p.a_dim * kRows * 4;
-    p.off_rec = off; off += 4u * (uint32_t)p.n_blocks * 16;
+    p.off_rec = off; off += 2u * tc::kMmaWarps * (uint32_t)p.n_blocks * 16;
     off = (off + 1023) / 1024 * 1024;
     p.off_ring = off;
     int max_smem = 0;
