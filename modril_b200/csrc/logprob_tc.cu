@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
     uint8_t* sA = smem + p.off_a;        // [2 tiles][H/8][128][8] T16
     uint8_t* sX0p = smem + p.off_x0p;    // [K0p/8][128][8]
     uint8_t* sX0t = smem + p.off_x0t;    // [KT/8][128][8]
-    float* sBias = reinterpret_cast<float*>(smem + p.off_bias);    // [2 roles][depth*H + NOp]
+    float* sBias = reinterpret_cast<float*>(smem + p.off_bias);    // [2 roles][NOp]: head biases (trunk biases ride in the MMA)
     float* sState = reinterpret_cast<float*>(smem + p.off_state);  // a [a_dim][128], probe [a_dim][128]
     uint8_t* sRing = smem + p.off_ring;
 
@@ -252,7 +252,6 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
     constexpr int NH = H / 2;
     constexpr uint32_t a_tile_bytes = (uint32_t)H * kRows * 2;  // one activation tile
     uint8_t* sOnes = smem + p.off_ones;  // [2][128][8]: columns 0..2 are 1.0 (multiplies the bias hi/mid/lo rows)
-    const int nbias = p.depth * H + p.NOp;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
@@ -272,8 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // biases of both roles, zero the (padded) layer-0 input buffers
-    for (int i = threadIdx.x; i < nbias * p.n_roles; i += kThreads)
-        sBias[i] = p.bias[i / nbias][i % nbias];
+    for (int i = threadIdx.x; i < p.NOp * p.n_roles; i += kThreads)
+        sBias[i] = p.bias[i / p.NOp][p.depth * H + i % p.NOp];
     for (int i = threadIdx.x; i < (p.K0p + p.KT) * kRows * 2 / 16; i += kThreads)
         reinterpret_cast<uint4*>(sX0p)[i] = make_uint4(0, 0, 0, 0);  // X0t follows X0p contiguously
     for (int i = threadIdx.x; i < 2 * kRows; i += kThreads) {
@@ -407,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
             const int role = (int)(tile % p.n_roles);
             const long long row0 = (tile / p.n_roles) * kRows;
             const float sign = p.sign[role];
-            const float* bias = sBias + role * nbias;
+            const float* bias_heads = sBias + role * p.NOp;
 
             // ---- tile init: layer-0 inputs + fp32 state ----
             for (int idx = et; idx < kRows * p.s_dim; idx += kEpiWarps * 32) {
@@ -496,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) logprob_tc_kernel(const __grid_co
                 tr.mark(0x2FF);
                 const long long g = row0 + row;
                 if (ch == 0) {
-                    const float* bh = bias + p.depth * H;
+                    const float* bh = bias_heads;
                     float div = 0.f;
                     for (int g16 = 0; g16 < p.NOp; g16 += 16) {
                         uint32_t vp[16], vt[16];
@@ -816,7 +815,7 @@ int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
     p.off_x0p = off; off += (uint32_t)p.K0p * kRows * 2;
     p.off_x0t = off; off += (uint32_t)p.KT * kRows * 2;
     p.off_ones = off; off += 2u * kRows * 16;
-    p.off_bias = off; off += (uint32_t)(a.n_roles * nb) * 4;
+    p.off_bias = off; off += (uint32_t)(a.n_roles * n0->n_out_p) * 4;
     off = (off + 15) / 16 * 16;
     p.off_state = off; off += 2u * p.a_dim * kRows * 4;
     p.off_rec = off; off += 2u * tc::kMmaWarps * (uint32_t)p.n_blocks * 16;
