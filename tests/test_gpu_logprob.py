@@ -252,3 +252,34 @@ def test_experimental_n256_integrator_matches_default_kernel(task, monkeypatch):
         assert_close(g.cpu().numpy(), f.cpu().numpy(), 2e-3, f"{task} v2 vs fp32", kink_frac=0.02)
         d = (g - r).abs() / r.abs().clamp_min(1.0)
         assert float(d.median()) <= 2e-4, float(d.median())
+
+
+@pytest.mark.parametrize("task,B,n_steps", [("hopper", 262144, 32), ("halfcheetah", 262144, 32), ("ant", 1048576, 32),
+                                            ("hand", 1048576, 32)])
+def test_baseline_full_sizes_tensor_core_properties(task, B, n_steps):
+    """BASELINE.json configs at their full sizes on the tensor-core path (fp16): size-independent properties --
+    determinism, row-permutation equivariance (tiles regroup, results must not move), the exported host entry point
+    equals the device path, reward == logp_E - logp_A, and a slice agrees with the FP32 kernels / the float64 oracle
+    within the mode's 2e-3 bar."""
+    sd, ad = synth.TASK_DIMS[task]
+    spec = cf.NetSpec(sd, ad, 256, 4, 2)
+    flat = cf.make_params(spec, 60, 1.0)
+    m = build_model(spec, flat)
+    s, a = synth.states_actions(61, B, sd, ad)
+    probe = synth.rademacher(62, (B, ad))
+    st, at, pt = dev(s), dev(a), dev(probe)
+    le, la, rw = m.score(st, at, n_steps=n_steps, probe=pt, precision="fp16")
+    le2, la2, rw2 = m.score(st, at, n_steps=n_steps, probe=pt, precision="fp16")
+    assert torch.equal(le, le2) and torch.equal(la, la2) and torch.equal(rw, rw2)
+    assert torch.isfinite(le).all() and torch.isfinite(la).all()
+    assert torch.equal(rw, le - la)
+    perm = torch.randperm(B, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    lep, lap, _ = m.score(st[perm], at[perm], n_steps=n_steps, probe=pt[perm], precision="fp16")
+    assert torch.equal(lep, le[perm]) and torch.equal(lap, la[perm])
+    lo = B // 3
+    sl = slice(lo, lo + 2048)
+    f32 = m.score(st[sl], at[sl], n_steps=n_steps, probe=pt[sl], precision="fp32")
+    assert_close(le[sl].cpu().numpy(), f32[0].cpu().numpy(), 2e-3, f"{task} fp16 vs fp32 kernels", kink_frac=0.01)
+    ref = cf.log_prob(spec, flat, s[lo:lo + 256], a[lo:lo + 256], "agent", probe[lo:lo + 256], n_steps)
+    assert_close(la[lo:lo + 256].cpu().numpy(), ref, 2e-3, f"{task} fp16 vs oracle", kink_frac=0.02)
+    assert_close(f32[1][:256].cpu().numpy(), ref, 1e-4, f"{task} fp32 vs oracle", kink_frac=0.02)
