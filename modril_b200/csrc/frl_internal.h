@@ -58,6 +58,7 @@ struct frl_net {
     void* pack_tc = nullptr;
     size_t pack_tc_bytes = 0;
     void* pack_tc2 = nullptr;           // block stream of the 64+64-row / N = 256 integrator (logprob_tc2.cu)
+    void* pack_tc3 = nullptr;           // per-CTA-rank block streams of the CTA-pair integrator (logprob_tc3.cu)
     bool has_params = false;
     // tensor-core training: fp16 weight images (train_tc.cu) and workspace
     void* pack_train = nullptr;
@@ -112,6 +113,10 @@ int launch_logprob_tc(const ScoreArgs& args, int precision, cudaStream_t stream)
 // logprob_tc2.cu
 int tc2_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
 int launch_logprob_tc2(const ScoreArgs& args, int precision, cudaStream_t stream);
+
+// logprob_tc3.cu
+int tc3_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
+int launch_logprob_tc3(const ScoreArgs& args, int precision, cudaStream_t stream);
 
 // train_f32.cu
 int cfm_loss_grad_f32(frl_net* net, float role_sign, const float* s, const float* a0, const float* t,

@@ -753,7 +753,9 @@ int tc_pack(frl_net* net, const float* params_dev, cudaStream_t stream) {
     if ((int)sc.blk.size() > kMaxBlocks) return FRL_OK;
     int rc = tc_pack_images(net, sc.pack, sc.image_bytes, &net->pack_tc, params_dev, stream);
     if (rc != FRL_OK) return rc;
-    return tc2_pack(net, params_dev, stream);
+    rc = tc2_pack(net, params_dev, stream);
+    if (rc != FRL_OK) return rc;
+    return tc3_pack(net, params_dev, stream);
 }
 
 template <typename T16, int H>
@@ -775,6 +777,10 @@ int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
     // FRL_TC_V2=1 selects the experimental 64-sample / N = 256 integrator (logprob_tc2.cu).  It is parity-green but on
     // one CTA its two in-flight tiles outgrow the shared-memory weight ring (profiles/r01f_tc2_experiment.md), so the
     // 128-sample kernel below stays the default until the cta_group::2 version halves the ring bytes per CTA.
+    if (n0->pack_tc3 && getenv("FRL_TC_V3")) {
+        const int rc3 = launch_logprob_tc3(a, precision, stream);
+        if (rc3 <= 0) return rc3;
+    }
     if (n0->pack_tc2 && getenv("FRL_TC_V2")) {
         const int rc2 = launch_logprob_tc2(a, precision, stream);
         if (rc2 <= 0) return rc2;   // > 0: shapes that do not fit the 64-sample kernel's shared-memory plan

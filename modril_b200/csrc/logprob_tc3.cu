@@ -1,0 +1,735 @@
+// tcgen05 fused log-density integrator for CTA PAIRS (sm_100a, cta_group::2): the 64-sample / N = 256 design of
+// logprob_tc2.cu with every MMA spanning two SMs.
+//
+// logprob_tc2.cu showed that one CTA cannot hold two in-flight 64-sample tiles AND a weight ring deep enough for the lag
+// between them (profiles/r01f_tc2_experiment.md).  Here two CTAs of a cluster form a pair:
+//   * one tcgen05.mma.cta_group::2 (M = 256) multiplies the 128 operand rows of BOTH CTAs with the same weight block, so
+//     a thread of the leader CTA issues for two SMs (half the issue cost per pipe cycle);
+//   * each CTA loads only its N/2 = 128 rows of a weight block (B is split across the pair): 16 KB per [K = 64] block,
+//     so the 80 KB ring holds five blocks, and the B-operand shared-memory bandwidth per SM halves;
+//   * each CTA keeps its own two tiles ("slots"), accumulators (2 x 256 TMEM columns), epilogue warps and producer.
+// Cross-CTA signalling: the peer's epilogue warps arrive on the leader's a_ready barriers through DSMEM
+// (mapa + mbarrier.arrive.release.cluster), a forwarder thread in the peer relays "my half of the weight block has
+// landed", and tcgen05.commit.cta_group::2 ... multicast::cluster releases ring slots / publishes accumulators in both
+// CTAs at once.  Row layout, 16x256b epilogue and state handling are those of logprob_tc2.cu; reference arithmetic:
+// modril/flowril/pretrain.py:192-214 / :112-134.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
+#include "frl_internal.h"
+#include "tc_common.cuh"
+
+namespace frl {
+
+namespace tc3 {
+
+using namespace tcc;
+
+constexpr int kThreads = 384;   // warp 0 producer, warps 1-2 MMA issuers (slot 0 / 1), warp 3 TMEM owner, 8 epilogue warps
+constexpr int kEpiWarps = 8;
+constexpr int kSlotBytes = 16384;   // ring slot; a weight block takes one or two consecutive slots
+constexpr int kBarRing = 8;         // blocks in flight are tracked by sequence number % kBarRing
+constexpr int kMaxSlots = 8;
+constexpr int kRows = 128;      // rows of the UMMA operand
+constexpr int kSamp = 64;       // samples per tile
+constexpr int H = 256;
+constexpr int kMaxBlocks = tc::kMaxBlocks;
+
+struct Blk {
+    uint32_t goff, bytes;
+    uint16_t nrows;     // N of the UMMA
+    uint16_t a_koff;    // first 8-feature chunk of the A operand
+    uint8_t n_k16;      // K = 16 MMAs
+    uint8_t src;        // A operand: 0 activations, 1 layer-0 input
+    uint8_t first;      // first MMA overwrites the accumulator
+    uint8_t commit;     // last block of a layer: commit d_full
+    uint8_t wait;       // bit0 / bit1: wait a_ready[slot][0 / 1] before issuing
+    uint8_t pad[3];
+};
+
+struct Params {
+    const uint8_t* wpack[2];
+    const float* bias[2];       // [depth*H + NOp] fp32 (only the head biases are read here)
+    float sign[2];
+    float* out[2];
+    const float* s;
+    const float* a;
+    const float* probe;
+    long long probe_step_stride;
+    long long B;
+    int n_roles, n_heads, depth, s_dim, a_dim, K0p, NOp;
+    int n_steps, basis, accumulate, n_blocks, n_stages;
+    float delta;
+    uint32_t rank_stride;        // bytes between the weight images of CTA rank 0 and rank 1
+    unsigned long long* trace;   // FRL_TC_TRACE: [4 roles][8192] clock stamps of CTA 0 (timing experiments only)
+    uint32_t off_a, off_x0, off_bias, off_state, off_rec, off_ring;
+    uint32_t x0_bytes, state_floats;   // per slot
+    Blk blk[kMaxBlocks];
+    float t_mid[kMaxSteps];
+};
+
+template <typename T> struct Cvt;
+template <> struct Cvt<__half> {
+    static constexpr uint32_t kFmt = 0;
+    __device__ static __forceinline__ uint32_t pack2_relu(uint32_t lo, uint32_t hi) {
+        uint32_t d;
+        asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+        return d;
+    }
+    __device__ static __forceinline__ uint32_t pack2_sat(uint32_t lo, uint32_t hi) {
+        uint32_t d;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+        return d;
+    }
+    __device__ static __forceinline__ uint16_t one(float x) {
+        x = fminf(fmaxf(x, -65504.f), 65504.f);
+        __half h = __float2half_rn(x);
+        return *reinterpret_cast<uint16_t*>(&h);
+    }
+};
+template <> struct Cvt<__nv_bfloat16> {
+    static constexpr uint32_t kFmt = 1;
+    __device__ static __forceinline__ uint32_t pack2_relu(uint32_t lo, uint32_t hi) {
+        uint32_t d;
+        asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+        return d;
+    }
+    __device__ static __forceinline__ uint32_t pack2_sat(uint32_t lo, uint32_t hi) {
+        uint32_t d;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+        return d;
+    }
+    __device__ static __forceinline__ uint16_t one(float x) {
+        __nv_bfloat16 h = __float2bfloat16_rn(x);
+        return *reinterpret_cast<uint16_t*>(&h);
+    }
+};
+
+// 0xFFFF in each half whose source float has its sign bit set (z < 0 or -0): PRMT with sign replication
+__device__ __forceinline__ uint32_t neg_mask16x2(uint32_t z_lo, uint32_t z_hi) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(d) : "r"(z_lo), "r"(z_hi));
+    return d;
+}
+
+struct Tracer {
+    unsigned long long* buf;
+    int n;
+    __device__ __forceinline__ void init(unsigned long long* base, int role) {
+        buf = (base != nullptr && blockIdx.x == 0) ? base + (size_t)role * 8192 : nullptr;
+        n = 0;
+    }
+    __device__ __forceinline__ void mark(unsigned tag) {
+        if (buf && n < 8190) buf[n++] = ((unsigned long long)tag << 48) | (clock64() & 0xFFFFFFFFFFFFull);
+    }
+};
+
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// 16 lanes x (8 * N) columns: thread t receives, for k = 0..N-1,  r[4k..4k+3] = D[base + t/4][8k + 2(t%4) + {0,1}],
+// D[base + 8 + t/4][8k + 2(t%4) + {0,1}]  (layout probed by tests/tmem_ld_probe.cu)
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+        "%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait_dep8(uint32_t (&a)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7])
+                 :
+                 : "memory");
+}
+
+// operand row of sample i (0..63): groups of 16 rows = 8 primal rows followed by the 8 tangent rows of the same samples,
+// so that one 16x256b TMEM load hands a thread the primal AND the tangent of its sample
+__device__ __forceinline__ int row_primal(int i) { return ((i >> 3) << 4) | (i & 7); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster (release at cluster scope: the
+// shared-memory operand rows written before it must be visible to the MMA the leader issues afterwards)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n" ::"r"(bar), "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "selp.b32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all prior MMAs of this thread -> one arrival on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
+template <typename T16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob_tc3_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t bar0 = smem_u32(smem);
+    auto w_full = [&](int s) { return bar0 + 8u * s; };                    // own half of the block has landed (tx)
+    auto w_fullp = [&](int s) { return bar0 + 8u * (kMaxSlots + s); };     // leader only: the peer's half has landed
+    auto w_empty = [&](int s) { return bar0 + 8u * (2 * kMaxSlots + s); }; // both issuers' MMAs on the slot completed
+    auto a_ready = [&](int slot, int ch) { return bar0 + 8u * (3 * kMaxSlots + slot * 2 + ch); };   // leader only
+    auto d_full = [&](int slot) { return bar0 + 8u * (3 * kMaxSlots + 4 + slot); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
+
+    constexpr uint32_t a_tile_bytes = (uint32_t)H * kRows * 2;   // 64 KB per slot
+    constexpr uint32_t kChunk = kRows * 16;                       // bytes of one 8-feature chunk of an operand image
+    uint8_t* sA = smem + p.off_a;         // [2 slots][H/8][128][8]
+    uint8_t* sX0 = smem + p.off_x0;       // [2 slots][K0p/8][128][8]
+    float* sBias = reinterpret_cast<float*>(smem + p.off_bias);     // [roles][depth*H + NOp] trunk + head biases (fp32)
+    const int nbias = p.depth * H + p.NOp;
+    float* sState = reinterpret_cast<float*>(smem + p.off_state);   // per slot: a [a_dim][64], probe [a_dim][64]
+    uint4* sRec = reinterpret_cast<uint4*>(smem + p.off_rec);       // [2 slots][n_blocks][2]
+    uint8_t* sRing = smem + p.off_ring;   // n_stages slots of 16 KB: this CTA's N/2 rows of one weight block each
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();          // 0 = leader (issues the MMAs of the pair)
+    const long long cluster_id = cluster_id_x();
+    const long long n_clusters = gridDim.x / 2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.n_stages; ++s) {
+            mbar_init(w_full(s), 1);
+            mbar_init(w_fullp(s), 1);
+            mbar_init(w_empty(s), 2);   // both issuers release a slot (multicast commit)
+        }
+        for (int slot = 0; slot < 2; ++slot) {
+            mbar_init(a_ready(slot, 0), kEpiWarps);   // 4 warps of this column half in each of the two CTAs
+            mbar_init(a_ready(slot, 1), kEpiWarps);
+            mbar_init(d_full(slot), 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < nbias * p.n_roles; i += kThreads) sBias[i] = p.bias[i / nbias][i % nbias];
+    for (int i = threadIdx.x; i < (int)(2 * p.x0_bytes / 16); i += kThreads)
+        reinterpret_cast<uint4*>(sX0)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 2 * p.n_blocks; i += kThreads) {
+        const int slot = i / p.n_blocks, b = i % p.n_blocks;
+        const Blk& k = p.blk[b];
+        const uint32_t src = k.src == 0 ? smem_u32(sA) + slot * a_tile_bytes : smem_u32(sX0) + slot * p.x0_bytes;
+        const uint32_t a_lo = (((src + (uint32_t)k.a_koff * kChunk) >> 4) & 0x3FFF) | ((kChunk >> 4) << 16);
+        // M = 256 over the pair, N = nrows (each CTA holds nrows / 2 rows of B)
+        const uint32_t idesc = (1u << 4) | (Cvt<T16>::kFmt << 7) | (Cvt<T16>::kFmt << 10) | ((uint32_t)(256 >> 4) << 24) |
+                               ((uint32_t)(k.nrows >> 3) << 17);
+        sRec[2 * i] = make_uint4(a_lo, idesc, (uint32_t)k.nrows | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24),
+                                 (uint32_t)slot * 256);
+        sRec[2 * i + 1] = make_uint4((uint32_t)k.n_k16 | ((uint32_t)k.first << 8), 0, 0, 0);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // barrier inits of both CTAs are visible before anyone arrives remotely
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    // work decomposition: a "quad" is four consecutive 64-sample tiles of one role: 2 per CTA of the pair
+    const long long tiles_per_role = (p.B + kSamp - 1) / kSamp;
+    const long long n_quads = ((tiles_per_role + 3) / 4) * p.n_roles;
+    auto arrive_leader = [&](uint32_t bar) {
+        if (cta_rank == 0) mbar_arrive(bar);
+        else mbar_arrive_remote(bar, 0);
+    };
+
+    if (warp == 0) {
+        // ------------------------------- producer: this CTA's half of every weight block --------------------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+                const uint8_t* wbase = p.wpack[quad % p.n_roles] + (size_t)cta_rank * p.rank_stride;
+                for (int step = 0; step < p.n_steps; ++step) {
+                    for (int b = 0; b < p.n_blocks; ++b) {
+                        mbar_wait(w_empty(stage), phase ^ 1);
+                        mbar_expect_tx(w_full(stage), p.blk[b].bytes);
+                        bulk_g2s(smem_u32(sRing + (size_t)stage * kSlotBytes), wbase + p.blk[b].goff, p.blk[b].bytes, w_full(stage));
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 3 && cta_rank == 1) {
+        // ------------------------------- peer: tell the leader when my half of a block has landed -----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long quad = cluster_id; quad < n_quads; quad += n_clusters)
+                for (int step = 0; step < p.n_steps; ++step)
+                    for (int b = 0; b < p.n_blocks; ++b) {
+                        mbar_wait(w_full(stage), phase);
+                        mbar_arrive_remote(w_fullp(stage), 0);
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if ((warp == 1 || warp == 2) && cta_rank == 0) {
+        // ------------------------------- leader: MMA issuer of one slot (of both CTAs) ----------------------------
+        if (lane == 0) {
+            const int slot = warp - 1;
+            int stage = 0;
+            uint32_t phase = 0, par_a0 = 0, par_a1 = 0;
+            const uint4* rec = sRec + (size_t)slot * p.n_blocks * 2;
+            const uint32_t ring_lo = smem_u32(sRing) >> 4;
+            constexpr uint32_t kDescHi = (uint32_t)(128 >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
+            Tracer tr; tr.init(p.trace, 1 + slot);
+            for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+                for (int step = 0; step < p.n_steps; ++step) {
+                    for (int b = 0; b < p.n_blocks; ++b) {
+                        const uint4 r0 = rec[2 * b], r1 = rec[2 * b + 1];
+                        tr.mark(0x100 + b);
+                        if (r0.z & (1u << 24)) { mbar_wait_cluster(a_ready(slot, 0), par_a0); par_a0 ^= 1; }
+                        if (r0.z & (2u << 24)) { mbar_wait_cluster(a_ready(slot, 1), par_a1); par_a1 ^= 1; }
+                        mbar_wait(w_full(stage), phase);
+                        mbar_wait_cluster(w_fullp(stage), phase);
+                        tr.mark(0x300 + b);
+                        tc_fence_after();
+                        const uint32_t nrows = r0.z & 0xFFFF, nk = r1.x & 0xFF, nhalf = nrows >> 1;
+                        uint32_t a_lo = r0.x;
+                        uint32_t b_lo = ((ring_lo + (uint32_t)stage * (kSlotBytes >> 4)) & 0x3FFF) | (nhalf << 16);
+                        uint32_t acc = ((r1.x >> 8) & 1) ? 0u : 1u;
+                        for (uint32_t u = 0; u < nk; ++u) {
+                            umma2_f16(tmem + r0.w, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, r0.y, acc);
+                            acc = 1u;
+                            a_lo += 2 * (kChunk >> 4);
+                            b_lo += 2 * nhalf;
+                        }
+                        umma2_commit_both(w_empty(stage));
+                        if ((r0.z >> 16) & 0xFF) umma2_commit_both(d_full(slot));
+                        tr.mark(0x400 + b);
+                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------ epilogue ------------------------------------------------
+        const int ew = warp - 4;
+        const int q = warp & 3;                 // TMEM lane quarter: operand rows 32q .. 32q+31 = samples 16q .. 16q+15
+        const int ch = ew >> 2;                 // column half (128 columns)
+        const int et = ew * 32 + lane;
+        const int tq = lane & 3, tr8 = lane >> 2;   // position inside the 16x256b fragment: column pair, row
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        const int t_col = p.a_dim + p.s_dim;
+        uint32_t par_d[2] = {0, 0};
+        float log_det[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [slot][16-row group]
+        Tracer tr; tr.init((lane == 0 && (ew == 0 || ew == 2)) ? p.trace : nullptr, ew == 0 ? 0 : 3);
+
+        for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
+            const int role = (int)(quad % p.n_roles);
+            const long long tile0 = 4 * (quad / p.n_roles) + 2 * cta_rank;   // this CTA's two tiles (padding tiles run masked)
+            constexpr int n_slots = 2;
+            const float sign = p.sign[role];
+            const float* bh = sBias + role * nbias + p.depth * H;
+
+            // ---- tile init: layer-0 operand rows + fp32 state (X0 was zeroed once; padding / tangent s,t columns stay 0) ----
+            for (int slot = 0; slot < n_slots; ++slot) {
+                const long long row0 = (tile0 + slot) * kSamp;
+                uint8_t* x0 = sX0 + slot * p.x0_bytes;
+                float* sA_state = sState + slot * p.state_floats;
+                float* sP_state = sA_state + p.a_dim * kSamp;
+                for (int idx = et; idx < kSamp * p.s_dim; idx += kEpiWarps * 32) {
+                    const int r = idx / p.s_dim, c = idx % p.s_dim;
+                    const long long g = row0 + r;
+                    const float v = g < p.B ? p.s[g * p.s_dim + c] : 0.f;
+                    const int kk = p.a_dim + c;
+                    *reinterpret_cast<uint16_t*>(x0 + (kk >> 3) * kChunk + row_primal(r) * 16 + (kk & 7) * 2) = Cvt<T16>::one(v);
+                }
+                for (int idx = et; idx < kSamp * p.a_dim; idx += kEpiWarps * 32) {
+                    const int r = idx / p.a_dim, c = idx % p.a_dim;
+                    const long long g = row0 + r;
+                    const float v = g < p.B ? p.a[g * p.a_dim + c] : 0.f;
+                    float pr = 0.f;
+                    if (g < p.B) pr = p.basis >= 0 ? (c == p.basis ? 1.f : 0.f) : p.probe[g * p.a_dim + c];
+                    sA_state[c * kSamp + r] = v;
+                    sP_state[c * kSamp + r] = pr;
+                    *reinterpret_cast<uint16_t*>(x0 + (c >> 3) * kChunk + row_primal(r) * 16 + (c & 7) * 2) = Cvt<T16>::one(v);
+                    *reinterpret_cast<uint16_t*>(x0 + (c >> 3) * kChunk + (row_primal(r) + 8) * 16 + (c & 7) * 2) = Cvt<T16>::one(pr);
+                }
+                if (et < kSamp)
+                    *reinterpret_cast<uint16_t*>(x0 + (t_col >> 3) * kChunk + row_primal(et) * 16 + (t_col & 7) * 2) =
+                        Cvt<T16>::one(p.t_mid[0]);
+                log_det[slot][0] = log_det[slot][1] = 0.f;
+            }
+            fence_async_smem();
+            named_sync(1, kEpiWarps * 32);
+            if (lane == 0)
+                for (int slot = 0; slot < n_slots; ++slot) arrive_leader(a_ready(slot, ch));
+
+            for (int step = 0; step < p.n_steps; ++step) {
+                // ---- trunk layers: accumulator -> next layer's operand ----
+                for (int l = 0; l < p.depth; ++l) {
+                    const float* bl = sBias + role * nbias + l * H + ch * 128 + 2 * tq;
+                    for (int slot = 0; slot < n_slots; ++slot) {
+                        tr.mark(0x100 + l * 2 + slot);
+                        mbar_wait(d_full(slot), par_d[slot]);
+                        par_d[slot] ^= 1;
+                        tc_fence_after();
+                        tr.mark(0x200 + l * 2 + slot);
+#pragma unroll
+                        for (int grp = 0; grp < 2; ++grp) {            // the two 16-row groups of this warp's lane quarter
+                            const int rowp = q * 32 + grp * 16 + tr8;  // primal row of this thread's sample; tangent = rowp + 8
+                            const uint32_t tb = lane_addr + ((uint32_t)(grp * 16) << 16) + (uint32_t)slot * 256 + (uint32_t)ch * 128;
+                            uint8_t* dst = sA + slot * a_tile_bytes + (size_t)(ch * 16) * kChunk + rowp * 16 + tq * 4;
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {     // 64 columns per load
+                                uint32_t z[32];
+                                tmem_ld_16x256b_x8(tb + half * 64, z);
+                                tmem_ld_wait_dep(z);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    // z[4k..4k+3] = primal (c, c+1), tangent (c, c+1) with c = half*64 + 8k + 2 tq
+                                    const float2 bb = *reinterpret_cast<const float2*>(bl + half * 64 + 8 * k);
+                                    const uint32_t lo = __float_as_uint(__uint_as_float(z[4 * k]) + bb.x);
+                                    const uint32_t hi = __float_as_uint(__uint_as_float(z[4 * k + 1]) + bb.y);
+                                    // primal: bias + relu + round + pack in one F2FP; tangent: masked by the primal's sign bits
+                                    const uint32_t wp = Cvt<T16>::pack2_relu(lo, hi);
+                                    const uint32_t wt = Cvt<T16>::pack2_sat(z[4 * k + 2], z[4 * k + 3]) & ~neg_mask16x2(lo, hi);
+                                    uint8_t* d = dst + (size_t)(half * 8 + k) * kChunk;
+                                    *reinterpret_cast<uint32_t*>(d) = wp;
+                                    *reinterpret_cast<uint32_t*>(d + 8 * 16) = wt;
+                                }
+                            }
+                        }
+                        tc_fence_before();
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) arrive_leader(a_ready(slot, ch));
+                        tr.mark(0x300 + l * 2 + slot);
+                    }
+                }
+                // ---- heads: tanh, divergence, Euler update (pretrain.py:205-211) ----
+                for (int slot = 0; slot < n_slots; ++slot) {
+                    tr.mark(0x1F0 + slot);
+                    mbar_wait(d_full(slot), par_d[slot]);
+                    par_d[slot] ^= 1;
+                    tc_fence_after();
+                    tr.mark(0x2F0 + slot);
+                    if (ch == 0) {
+                        uint8_t* x0 = sX0 + slot * p.x0_bytes;
+                        float* sA_state = sState + slot * p.state_floats;
+                        float* sP_state = sA_state + p.a_dim * kSamp;
+#pragma unroll
+                        for (int grp = 0; grp < 2; ++grp) {
+                            const int srow = q * 16 + grp * 8 + tr8;             // sample inside the tile
+                            const int rowp = q * 32 + grp * 16 + tr8;
+                            const long long g = (tile0 + slot) * kSamp + srow;
+                            const uint32_t hb = lane_addr + ((uint32_t)(grp * 16) << 16) + (uint32_t)slot * 256;
+                            float div = 0.f;
+                            for (int g16 = 0; g16 < p.NOp; g16 += 16) {
+                                uint32_t vv[8];
+                                tmem_ld_16x256b_x2(hb + (uint32_t)g16, vv);
+                                tmem_ld_wait_dep8(vv);
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) {
+                                    const int c = g16 + 8 * k + 2 * tq;   // this thread's column pair (c, c+1): primal vv[4k], vv[4k+1]; tangent vv[4k+2], vv[4k+3]
+                                    if (p.n_heads == 2) {
+                                        const int j = c >> 1;             // columns (2j, 2j+1) = (v_c, rho) of action dim j
+                                        if (j < p.a_dim) {
+                                            const float th = tanhf(__uint_as_float(vv[4 * k + 1]) + bh[c + 1]);
+                                            const float v = __uint_as_float(vv[4 * k]) + bh[c] + sign * th;
+                                            const float dv = __uint_as_float(vv[4 * k + 2]) +
+                                                             sign * (1.f - th * th) * __uint_as_float(vv[4 * k + 3]);
+                                            div = fmaf(dv, sP_state[j * kSamp + srow], div);
+                                            const float an = sA_state[j * kSamp + srow] + v * p.delta;
+                                            sA_state[j * kSamp + srow] = an;
+                                            *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + rowp * 16 + (j & 7) * 2) = Cvt<T16>::one(an);
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int e = 0; e < 2; ++e) {
+                                            const int j = c + e;
+                                            if (j < p.a_dim) {
+                                                const float v = __uint_as_float(vv[4 * k + e]) + bh[j];
+                                                div = fmaf(__uint_as_float(vv[4 * k + 2 + e]), sP_state[j * kSamp + srow], div);
+                                                const float an = sA_state[j * kSamp + srow] + v * p.delta;
+                                                sA_state[j * kSamp + srow] = an;
+                                                *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + rowp * 16 + (j & 7) * 2) = Cvt<T16>::one(an);
+                                            }
+                                        }
+                                    }
+                                }
+                            }
+                            // the four threads of a sample hold different action dims: sum their divergence terms
+                            div += __shfl_xor_sync(0xffffffffu, div, 1);
+                            div += __shfl_xor_sync(0xffffffffu, div, 2);
+                            log_det[slot][grp] -= p.delta * div;
+                            __syncwarp();   // the state of this sample (written by its four threads) is complete
+                            if (step + 1 < p.n_steps) {
+                                if (tq == 0)
+                                    *reinterpret_cast<uint16_t*>(x0 + (t_col >> 3) * kChunk + rowp * 16 + (t_col & 7) * 2) =
+                                        Cvt<T16>::one(p.t_mid[step + 1]);
+                                if (p.probe_step_stride != 0) {
+                                    for (int j = tq; j < p.a_dim; j += 4) {
+                                        const float pr = g < p.B ? p.probe[(step + 1) * p.probe_step_stride + g * p.a_dim + j] : 0.f;
+                                        sP_state[j * kSamp + srow] = pr;
+                                        *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + (rowp + 8) * 16 + (j & 7) * 2) =
+                                            Cvt<T16>::one(pr);
+                                    }
+                                }
+                            } else if (tq == 0 && g < p.B) {
+                                if (p.accumulate) {
+                                    p.out[role][g] += log_det[slot][grp];
+                                } else {
+                                    float prior = 0.f;
+                                    for (int j = 0; j < p.a_dim; ++j) {
+                                        const float x = sA_state[j * kSamp + srow];
+                                        prior += -0.5f * x * x - 0.91893853320467274178f;
+                                    }
+                                    p.out[role][g] = prior + log_det[slot][grp];
+                                }
+                            }
+                        }
+                    }
+                    if (step + 1 < p.n_steps) {
+                        tc_fence_before();
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) arrive_leader(a_ready(slot, ch));
+                    }
+                    tr.mark(0x3F0 + slot);
+                }
+            }
+            // the next pair's init rewrites X0 / state: every epilogue warp must be done with this pair first
+            tc_fence_before();
+            named_sync(1, kEpiWarps * 32);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the leader's last MMAs read the peer's shared memory: nobody leaves or frees TMEM early
+    if (warp == 3) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    }
+}
+
+// Block stream of one Euler step (shared by the packer and the kernel).  One kernel block = one ring slot of each CTA =
+// one tcgen05.commit: [K = 64][N = 256] for the trunk (each CTA of the pair holds 128 of the 256 rows: 16 KB), the whole
+// (<= 32 column) layer-0 input, or half of the heads' K.  Blk::goff / Blk::bytes describe ONE CTA's half.
+struct Schedule {
+    std::vector<Blk> blk;
+    std::vector<tc::PackBlk> pack[2];   // per CTA rank
+    uint32_t image_bytes = 0;           // of one rank's image
+};
+
+static bool supported(const frl_net* net) {
+    return net->cfg.hidden == H && net->d_in_p <= 32 && net->n_out_p <= 64;
+}
+
+static Schedule make_schedule(const frl_net* net) {
+    Schedule sc;
+    const int depth = net->cfg.depth, K0p = net->d_in_p, NOp = net->n_out_p;
+    uint32_t goff = 0;
+    auto add = [&](int layer, int nrows, int k0, int klen, int a_koff, int src, int first, int commit, int wait) {
+        Blk b{};
+        b.goff = goff; b.nrows = (uint16_t)nrows; b.a_koff = (uint16_t)a_koff;
+        b.n_k16 = (uint8_t)(klen / 16); b.src = (uint8_t)src; b.first = (uint8_t)first; b.commit = (uint8_t)commit;
+        b.wait = (uint8_t)wait;
+        for (int r = 0; r < 2; ++r) sc.pack[r].push_back(tc::PackBlk{goff, nrows / 2, klen, r * (nrows / 2), k0, layer});
+        goff += (uint32_t)(nrows / 2) * klen * 2;
+        b.bytes = goff - b.goff;
+        sc.blk.push_back(b);
+    };
+    // the accumulator-overwriting first block of every layer waits a_ready[slot][0] and [1]: both column halves of the
+    // previous epilogue (in both CTAs) have drained the accumulator and written the whole operand
+    add(0, H, 0, K0p, 0, 1, 1, 1, 3);
+    for (int l = 1; l < depth; ++l)
+        for (int k0 = 0; k0 < H; k0 += 64) add(l, H, k0, 64, k0 / 8, 0, k0 == 0, k0 + 64 >= H, k0 == 0 ? 3 : 0);
+    add(depth, NOp, 0, H / 2, 0, 0, 1, 0, 3);
+    add(depth, NOp, H / 2, H / 2, (H / 2) / 8, 0, 0, 1, 0);
+    sc.image_bytes = goff;
+    return sc;
+}
+
+static size_t rank_image_stride(const frl_net* net, uint32_t image_bytes) {
+    const size_t img = ((size_t)image_bytes + 255) / 256 * 256;
+    const size_t nb = (size_t)net->cfg.depth * net->cfg.hidden + net->n_out_p;
+    return (2 * img + nb * sizeof(float) + 255) / 256 * 256;
+}
+
+}  // namespace tc3
+
+int tc3_pack(frl_net* net, const float* params_dev, cudaStream_t stream) {
+    using namespace tc3;
+    if (!supported(net)) return FRL_OK;
+    Schedule sc = make_schedule(net);
+    if ((int)sc.blk.size() > kMaxBlocks) return FRL_OK;
+    // [rank 0: fp16 image | bf16 image | bias] [rank 1: ...]
+    const size_t stride = rank_image_stride(net, sc.image_bytes);
+    if (!net->pack_tc3) FRL_CUDA(cudaMalloc(&net->pack_tc3, 2 * stride));
+    for (int r = 0; r < 2; ++r) {
+        void* dst = static_cast<uint8_t*>(net->pack_tc3) + r * stride;
+        int rc = tc_pack_images(net, sc.pack[r], sc.image_bytes, &dst, params_dev, stream);
+        if (rc != FRL_OK) return rc;
+    }
+    return FRL_OK;
+}
+
+template <typename T16>
+static int launch_tc3(const tc3::Params& p, size_t smem_bytes, int grid, int device, cudaStream_t stream) {
+    auto kern = tc3::logprob_tc3_kernel<T16>;
+    static std::mutex mu;
+    static bool done[64] = {};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (device < 0 || device >= 64 || !done[device]) {
+            int max_smem = 0;
+            FRL_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+            FRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+            if (device >= 0 && device < 64) done[device] = true;
+        }
+    }
+    kern<<<grid, tc3::kThreads, smem_bytes, stream>>>(p);
+    FRL_CUDA(cudaGetLastError());
+    return FRL_OK;
+}
+
+int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
+    using namespace tc3;
+    const frl_net* n0 = a.net[0];
+    if (precision == FRL_PREC_BF16X3) {
+        set_error("FRL_PREC_BF16X3 is not implemented in this build");
+        return FRL_ERR_UNSUPPORTED;
+    }
+    Schedule sc = make_schedule(n0);
+    const int nb = n0->cfg.depth * H + n0->n_out_p;
+    const size_t img = ((size_t)sc.image_bytes + 255) / 256 * 256;
+    const bool f16 = precision == FRL_PREC_FP16;
+
+    Params p{};
+    for (int r = 0; r < a.n_roles; ++r) {
+        const uint8_t* base = static_cast<const uint8_t*>(a.net[r]->pack_tc3);
+        if (!base) {
+            set_error("tensor-core weight image missing for one of the nets");
+            return FRL_ERR_UNSUPPORTED;
+        }
+        p.wpack[r] = f16 ? base : base + img;
+        p.bias[r] = reinterpret_cast<const float*>(base + 2 * img);
+        p.sign[r] = a.sign[r];
+        p.out[r] = a.out_logp[r];
+    }
+    p.rank_stride = (uint32_t)rank_image_stride(n0, sc.image_bytes);
+    p.s = a.s; p.a = a.a; p.probe = a.probe;
+    p.B = a.B; p.n_roles = a.n_roles; p.n_heads = n0->cfg.n_heads; p.depth = n0->cfg.depth;
+    p.s_dim = n0->cfg.s_dim; p.a_dim = n0->cfg.a_dim; p.K0p = n0->d_in_p; p.NOp = n0->n_out_p;
+    p.n_steps = a.n_steps;
+    p.delta = (float)(1.0 / a.n_steps);
+    for (int k = 0; k < a.n_steps; ++k) p.t_mid[k] = a.t_mid_host[k];
+    p.probe_step_stride = a.probe_mode == FRL_PROBE_PER_STEP ? a.B * (long long)p.a_dim : 0;
+    p.n_blocks = (int)sc.blk.size();
+    for (int i = 0; i < p.n_blocks; ++i) p.blk[i] = sc.blk[i];
+
+    uint32_t off = 1024;   // barriers + TMEM slot
+    p.off_a = off; off += 2u * H * kRows * 2;
+    p.x0_bytes = (uint32_t)p.K0p * kRows * 2;
+    p.off_x0 = off; off += 2u * p.x0_bytes;
+    p.off_bias = off; off += (uint32_t)(a.n_roles * nb) * 4;
+    off = (off + 15) / 16 * 16;
+    p.state_floats = 2u * p.a_dim * kSamp;
+    p.off_state = off; off += 2u * p.state_floats * 4;
+    off = (off + 15) / 16 * 16;
+    p.off_rec = off; off += 4u * (uint32_t)p.n_blocks * 16;
+    off = (off + 1023) / 1024 * 1024;
+    p.off_ring = off;
+    int max_smem = 0, sms = 0;
+    FRL_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, n0->cfg.device));
+    FRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, n0->cfg.device));
+    int stages = ((int)max_smem - (int)off) / kSlotBytes;
+    if (stages > kMaxSlots) stages = kMaxSlots;
+    if (stages < 4) return 1;   // not enough shared memory for the ring: the caller falls back to the 128-sample kernel
+    p.n_stages = stages;
+    const size_t smem_bytes = (size_t)off + (size_t)stages * kSlotBytes;
+
+    const long long tiles_per_role = (a.B + kSamp - 1) / kSamp;
+    const long long n_quads = ((tiles_per_role + 3) / 4) * a.n_roles;
+    const int grid = 2 * (int)std::min<long long>(n_quads, sms / 2);   // clusters of two CTAs
+
+    auto run = [&](const Params& q) {
+        return f16 ? launch_tc3<__half>(q, smem_bytes, grid, n0->cfg.device, stream)
+                   : launch_tc3<__nv_bfloat16>(q, smem_bytes, grid, n0->cfg.device, stream);
+    };
+    if (const char* tp = getenv("FRL_TC_TRACE")) {
+        // timing experiment: stamp CTA 0's roles with clock64 and dump them (synchronises!)
+        unsigned long long* d = nullptr;
+        FRL_CUDA(cudaMalloc(&d, 4 * 8192 * sizeof(unsigned long long)));
+        FRL_CUDA(cudaMemset(d, 0, 4 * 8192 * sizeof(unsigned long long)));
+        p.trace = d;
+        p.basis = -1;
+        int rc = run(p);
+        if (rc != FRL_OK) return rc;
+        FRL_CUDA(cudaDeviceSynchronize());
+        std::vector<unsigned long long> h(4 * 8192);
+        FRL_CUDA(cudaMemcpy(h.data(), d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        if (FILE* f = fopen(tp, "w")) {
+            for (int r = 0; r < 4; ++r)
+                for (int i = 0; i < 8192 && h[(size_t)r * 8192 + i]; ++i)
+                    fprintf(f, "%d %llx %llu\n", r, h[(size_t)r * 8192 + i] >> 48, h[(size_t)r * 8192 + i] & 0xFFFFFFFFFFFFull);
+            fclose(f);
+        }
+        return FRL_OK;
+    }
+    if (a.probe_mode == FRL_PROBE_EXACT) {
+        for (int i = 0; i < p.a_dim; ++i) {
+            p.basis = i;
+            p.accumulate = i > 0;
+            int rc = run(p);
+            if (rc != FRL_OK) return rc;
+        }
+        return FRL_OK;
+    }
+    p.basis = -1;
+    p.accumulate = 0;
+    return run(p);
+}
+
+}  // namespace frl

@@ -126,6 +126,7 @@ extern "C" int frl_net_destroy(frl_net* net) {
     if (net->pack_f32) cudaFree(net->pack_f32);
     if (net->pack_tc) cudaFree(net->pack_tc);
     if (net->pack_tc2) cudaFree(net->pack_tc2);
+    if (net->pack_tc3) cudaFree(net->pack_tc3);
     if (net->ws) cudaFree(net->ws);
     if (net->pack_train) cudaFree(net->pack_train);
     if (net->ws_tc) cudaFree(net->ws_tc);
