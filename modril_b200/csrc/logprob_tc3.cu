@@ -32,7 +32,7 @@ using namespace tcc;
 
 constexpr int kThreads = 384;   // warp 0 producer, warps 1-2 MMA issuers (slot 0 / 1), warp 3 TMEM owner, 8 epilogue warps
 constexpr int kEpiWarps = 8;
-constexpr int kSlotBytes = 16384;   // ring slot; a weight block takes one or two consecutive slots
+constexpr int kSlotBytes = 20480;   // ring slot = this CTA's half of one weight block: [16 bias rows +] K = 64 rows of 128
 constexpr int kBarRing = 8;         // blocks in flight are tracked by sequence number % kBarRing
 constexpr int kMaxSlots = 8;
 constexpr int kRows = 128;      // rows of the UMMA operand
@@ -49,7 +49,8 @@ struct Blk {
     uint8_t first;      // first MMA overwrites the accumulator
     uint8_t commit;     // last block of a layer: commit d_full
     uint8_t wait;       // bit0 / bit1: wait a_ready[slot][0 / 1] before issuing
-    uint8_t pad[3];
+    uint8_t bias;       // the block starts with 16 bias rows: first MMA = ones tile x bias rows, overwrites the accumulator
+    uint8_t pad[2];
 };
 
 struct Params {
@@ -65,9 +66,10 @@ struct Params {
     int n_roles, n_heads, depth, s_dim, a_dim, K0p, NOp;
     int n_steps, basis, accumulate, n_blocks, n_stages;
     float delta;
+    int debug;                   // FRL_TC_DEBUG (timing experiments): 8 skip epilogue stores, 16 skip the bias add
     uint32_t rank_stride;        // bytes between the weight images of CTA rank 0 and rank 1
     unsigned long long* trace;   // FRL_TC_TRACE: [4 roles][8192] clock stamps of CTA 0 (timing experiments only)
-    uint32_t off_a, off_x0, off_bias, off_state, off_rec, off_ring;
+    uint32_t off_a, off_x0, off_ones, off_bias, off_state, off_rec, off_ring;
     uint32_t x0_bytes, state_floats;   // per slot
     Blk blk[kMaxBlocks];
     float t_mid[kMaxSteps];
@@ -117,11 +119,18 @@ __device__ __forceinline__ uint32_t neg_mask16x2(uint32_t z_lo, uint32_t z_hi) {
     return d;
 }
 
+// four 8x8 b16 matrices from the MMA-fragment layout (thread t: row t/4, columns 2(t%4), +1) to shared memory; lane i
+// supplies the address of row i%8 of matrix i/8 (16 bytes per row)
+__device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+                 : "memory");
+}
+
 struct Tracer {
     unsigned long long* buf;
     int n;
-    __device__ __forceinline__ void init(unsigned long long* base, int role) {
-        buf = (base != nullptr && blockIdx.x == 0) ? base + (size_t)role * 8192 : nullptr;
+    __device__ __forceinline__ void init(unsigned long long* base, int role, int cta = 0) {
+        buf = (base != nullptr && blockIdx.x == cta) ? base + (size_t)role * 8192 : nullptr;
         n = 0;
     }
     __device__ __forceinline__ void mark(unsigned tag) {
@@ -223,8 +232,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     constexpr uint32_t kChunk = kRows * 16;                       // bytes of one 8-feature chunk of an operand image
     uint8_t* sA = smem + p.off_a;         // [2 slots][H/8][128][8]
     uint8_t* sX0 = smem + p.off_x0;       // [2 slots][K0p/8][128][8]
-    float* sBias = reinterpret_cast<float*>(smem + p.off_bias);     // [roles][depth*H + NOp] trunk + head biases (fp32)
-    const int nbias = p.depth * H + p.NOp;
+    uint8_t* sOnes = smem + p.off_ones;   // [2][128][8]: feature 0..2 = 1.0 on the primal rows (bias hi/mid/lo terms)
+    float* sBias = reinterpret_cast<float*>(smem + p.off_bias);     // [roles][NOp] head biases (trunk biases ride in the MMA)
     float* sState = reinterpret_cast<float*>(smem + p.off_state);   // per slot: a [a_dim][64], probe [a_dim][64]
     uint4* sRec = reinterpret_cast<uint4*>(smem + p.off_rec);       // [2 slots][n_blocks][2]
     uint8_t* sRing = smem + p.off_ring;   // n_stages slots of 16 KB: this CTA's N/2 rows of one weight block each
@@ -251,7 +260,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < nbias * p.n_roles; i += kThreads) sBias[i] = p.bias[i / nbias][i % nbias];
+    for (int i = threadIdx.x; i < p.NOp * p.n_roles; i += kThreads) sBias[i] = p.bias[i / p.NOp][p.depth * H + i % p.NOp];
+    for (int i = threadIdx.x; i < 2 * kRows; i += kThreads) {
+        const uint32_t one = Cvt<T16>::one(1.f);   // primal rows are rows 0..7 of every 16-row group
+        reinterpret_cast<uint4*>(sOnes)[i] = (i < kRows && (i & 8) == 0) ? make_uint4(one | (one << 16), one, 0, 0)
+                                                                           : make_uint4(0, 0, 0, 0);
+    }
     for (int i = threadIdx.x; i < (int)(2 * p.x0_bytes / 16); i += kThreads)
         reinterpret_cast<uint4*>(sX0)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < 2 * p.n_blocks; i += kThreads) {
@@ -264,7 +278,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                                ((uint32_t)(k.nrows >> 3) << 17);
         sRec[2 * i] = make_uint4(a_lo, idesc, (uint32_t)k.nrows | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24),
                                  (uint32_t)slot * 256);
-        sRec[2 * i + 1] = make_uint4((uint32_t)k.n_k16 | ((uint32_t)k.first << 8), 0, 0, 0);
+        sRec[2 * i + 1] = make_uint4((uint32_t)k.n_k16 | ((uint32_t)k.first << 8) | ((uint32_t)k.bias << 16),
+                                     ((smem_u32(sOnes) >> 4) & 0x3FFF) | ((kChunk >> 4) << 16), 0, 0);
     }
     fence_async_smem();
     tc_fence_before();
@@ -336,6 +351,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         uint32_t a_lo = r0.x;
                         uint32_t b_lo = ((ring_lo + (uint32_t)stage * (kSlotBytes >> 4)) & 0x3FFF) | (nhalf << 16);
                         uint32_t acc = ((r1.x >> 8) & 1) ? 0u : 1u;
+                        if ((r1.x >> 16) & 1) {   // bias rows first: ones tile x [bias_hi; bias_mid; bias_lo; 0 ...]
+                            umma2_f16(tmem + r0.w, ((uint64_t)kDescHi << 32) | r1.y, ((uint64_t)kDescHi << 32) | b_lo, r0.y, 0u);
+                            acc = 1u;
+                            b_lo += 2 * nhalf;
+                        }
                         for (uint32_t u = 0; u < nk; ++u) {
                             umma2_f16(tmem + r0.w, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, r0.y, acc);
                             acc = 1u;
@@ -361,14 +381,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         const int t_col = p.a_dim + p.s_dim;
         uint32_t par_d[2] = {0, 0};
         float log_det[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [slot][16-row group]
-        Tracer tr; tr.init((lane == 0 && (ew == 0 || ew == 2)) ? p.trace : nullptr, ew == 0 ? 0 : 3);
+        Tracer tr;   // role 0: leader CTA's first epilogue warp, role 3: the peer CTA's
+        tr.init((lane == 0 && ew == 0) ? p.trace : nullptr, cta_rank == 0 ? 0 : 3, (int)cta_rank);
 
         for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
             const int role = (int)(quad % p.n_roles);
             const long long tile0 = 4 * (quad / p.n_roles) + 2 * cta_rank;   // this CTA's two tiles (padding tiles run masked)
             constexpr int n_slots = 2;
             const float sign = p.sign[role];
-            const float* bh = sBias + role * nbias + p.depth * H;
+            const float* bh = sBias + role * p.NOp;
 
             // ---- tile init: layer-0 operand rows + fp32 state (X0 was zeroed once; padding / tangent s,t columns stay 0) ----
             for (int slot = 0; slot < n_slots; ++slot) {
@@ -407,38 +428,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
             for (int step = 0; step < p.n_steps; ++step) {
                 // ---- trunk layers: accumulator -> next layer's operand ----
                 for (int l = 0; l < p.depth; ++l) {
-                    const float* bl = sBias + role * nbias + l * H + ch * 128 + 2 * tq;
                     for (int slot = 0; slot < n_slots; ++slot) {
                         tr.mark(0x100 + l * 2 + slot);
                         mbar_wait(d_full(slot), par_d[slot]);
                         par_d[slot] ^= 1;
                         tc_fence_after();
                         tr.mark(0x200 + l * 2 + slot);
-#pragma unroll
-                        for (int grp = 0; grp < 2; ++grp) {            // the two 16-row groups of this warp's lane quarter
-                            const int rowp = q * 32 + grp * 16 + tr8;  // primal row of this thread's sample; tangent = rowp + 8
+                        // Both 16-row groups of this warp's lane quarter, 128 columns each, in two software-pipelined
+                        // rounds: the TMEM loads of group 1 are in flight while group 0 is converted and stored (a
+                        // tcgen05.wait::ld covers every outstanding load, so the rounds are the pipelining granularity).
+                        uint32_t z[2][2][32];
+                        auto load_grp = [&](int grp) {
                             const uint32_t tb = lane_addr + ((uint32_t)(grp * 16) << 16) + (uint32_t)slot * 256 + (uint32_t)ch * 128;
-                            uint8_t* dst = sA + slot * a_tile_bytes + (size_t)(ch * 16) * kChunk + rowp * 16 + tq * 4;
+                            tmem_ld_16x256b_x8(tb, z[grp][0]);
+                            tmem_ld_16x256b_x8(tb + 64, z[grp][1]);
+                        };
+                        auto store_grp = [&](int grp) {
+                            // lane i addresses row i%8 of matrix i/8: matrices 0/1 = primal/tangent rows of chunk k,
+                            // matrices 2/3 = the same of chunk k+1
+                            const uint32_t rowa = (uint32_t)(q * 32 + grp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8);
+                            uint32_t addr = smem_u32(sA) + slot * a_tile_bytes + (uint32_t)(ch * 16 + (lane >> 4)) * kChunk + rowa * 16;
 #pragma unroll
-                            for (int half = 0; half < 2; ++half) {     // 64 columns per load
-                                uint32_t z[32];
-                                tmem_ld_16x256b_x8(tb + half * 64, z);
-                                tmem_ld_wait_dep(z);
+                            for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    // z[4k..4k+3] = primal (c, c+1), tangent (c, c+1) with c = half*64 + 8k + 2 tq
-                                    const float2 bb = *reinterpret_cast<const float2*>(bl + half * 64 + 8 * k);
-                                    const uint32_t lo = __float_as_uint(__uint_as_float(z[4 * k]) + bb.x);
-                                    const uint32_t hi = __float_as_uint(__uint_as_float(z[4 * k + 1]) + bb.y);
-                                    // primal: bias + relu + round + pack in one F2FP; tangent: masked by the primal's sign bits
-                                    const uint32_t wp = Cvt<T16>::pack2_relu(lo, hi);
-                                    const uint32_t wt = Cvt<T16>::pack2_sat(z[4 * k + 2], z[4 * k + 3]) & ~neg_mask16x2(lo, hi);
-                                    uint8_t* d = dst + (size_t)(half * 8 + k) * kChunk;
-                                    *reinterpret_cast<uint32_t*>(d) = wp;
-                                    *reinterpret_cast<uint32_t*>(d + 8 * 16) = wt;
+                                for (int k = 0; k < 8; k += 2) {
+                                    uint32_t w[4];
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e) {
+                                        // z[4k..4k+3] = primal (c, c+1), tangent (c, c+1) with c = half*64 + 8k + 2 tq; the bias is
+                                        // already in the accumulator.  primal: relu + round + pack in one F2FP; tangent:
+                                        // masked by the sign bits of the primal pre-activation
+                                        const uint32_t lo = z[grp][half][4 * (k + e)], hi = z[grp][half][4 * (k + e) + 1];
+                                        w[2 * e] = Cvt<T16>::pack2_relu(lo, hi);
+                                        w[2 * e + 1] = Cvt<T16>::pack2_sat(z[grp][half][4 * (k + e) + 2], z[grp][half][4 * (k + e) + 3]) &
+                                                       ~neg_mask16x2(lo, hi);
+                                    }
+                                    stmatrix_x4(addr, w[0], w[1], w[2], w[3]);
+                                    addr += 2 * kChunk;
                                 }
                             }
-                        }
+                        };
+                        load_grp(0);
+                        tmem_ld_wait_dep(z[0][0]);
+                        tmem_ld_wait_dep(z[0][1]);
+                        tr.mark(0x500 + l * 2 + slot);
+                        load_grp(1);
+                        store_grp(0);
+                        tr.mark(0x600 + l * 2 + slot);
+                        tmem_ld_wait_dep(z[1][0]);
+                        tmem_ld_wait_dep(z[1][1]);
+                        tr.mark(0x700 + l * 2 + slot);
+                        store_grp(1);
+                        tr.mark(0x800 + l * 2 + slot);
                         tc_fence_before();
                         fence_async_smem();
                         __syncwarp();
@@ -569,11 +610,15 @@ static Schedule make_schedule(const frl_net* net) {
     Schedule sc;
     const int depth = net->cfg.depth, K0p = net->d_in_p, NOp = net->n_out_p;
     uint32_t goff = 0;
-    auto add = [&](int layer, int nrows, int k0, int klen, int a_koff, int src, int first, int commit, int wait) {
+    auto add = [&](int layer, int nrows, int k0, int klen, int a_koff, int src, int bias, int first, int commit, int wait) {
         Blk b{};
         b.goff = goff; b.nrows = (uint16_t)nrows; b.a_koff = (uint16_t)a_koff;
         b.n_k16 = (uint8_t)(klen / 16); b.src = (uint8_t)src; b.first = (uint8_t)first; b.commit = (uint8_t)commit;
-        b.wait = (uint8_t)wait;
+        b.wait = (uint8_t)wait; b.bias = (uint8_t)bias;
+        if (bias) {
+            for (int r = 0; r < 2; ++r) sc.pack[r].push_back(tc::PackBlk{goff, nrows / 2, 16, r * (nrows / 2), -1, layer});
+            goff += (uint32_t)(nrows / 2) * 16 * 2;
+        }
         for (int r = 0; r < 2; ++r) sc.pack[r].push_back(tc::PackBlk{goff, nrows / 2, klen, r * (nrows / 2), k0, layer});
         goff += (uint32_t)(nrows / 2) * klen * 2;
         b.bytes = goff - b.goff;
@@ -581,11 +626,11 @@ static Schedule make_schedule(const frl_net* net) {
     };
     // the accumulator-overwriting first block of every layer waits a_ready[slot][0] and [1]: both column halves of the
     // previous epilogue (in both CTAs) have drained the accumulator and written the whole operand
-    add(0, H, 0, K0p, 0, 1, 1, 1, 3);
+    add(0, H, 0, K0p, 0, 1, 1, 1, 1, 3);
     for (int l = 1; l < depth; ++l)
-        for (int k0 = 0; k0 < H; k0 += 64) add(l, H, k0, 64, k0 / 8, 0, k0 == 0, k0 + 64 >= H, k0 == 0 ? 3 : 0);
-    add(depth, NOp, 0, H / 2, 0, 0, 1, 0, 3);
-    add(depth, NOp, H / 2, H / 2, (H / 2) / 8, 0, 0, 1, 0);
+        for (int k0 = 0; k0 < H; k0 += 64) add(l, H, k0, 64, k0 / 8, 0, k0 == 0, k0 == 0, k0 + 64 >= H, k0 == 0 ? 3 : 0);
+    add(depth, NOp, 0, H / 2, 0, 0, 0, 1, 0, 3);
+    add(depth, NOp, H / 2, H / 2, (H / 2) / 8, 0, 0, 0, 1, 0);
     sc.image_bytes = goff;
     return sc;
 }
@@ -641,7 +686,6 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
         return FRL_ERR_UNSUPPORTED;
     }
     Schedule sc = make_schedule(n0);
-    const int nb = n0->cfg.depth * H + n0->n_out_p;
     const size_t img = ((size_t)sc.image_bytes + 255) / 256 * 256;
     const bool f16 = precision == FRL_PREC_FP16;
 
@@ -658,6 +702,7 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
         p.out[r] = a.out_logp[r];
     }
     p.rank_stride = (uint32_t)rank_image_stride(n0, sc.image_bytes);
+    if (const char* dbg = getenv("FRL_TC_DEBUG")) p.debug = atoi(dbg);
     p.s = a.s; p.a = a.a; p.probe = a.probe;
     p.B = a.B; p.n_roles = a.n_roles; p.n_heads = n0->cfg.n_heads; p.depth = n0->cfg.depth;
     p.s_dim = n0->cfg.s_dim; p.a_dim = n0->cfg.a_dim; p.K0p = n0->d_in_p; p.NOp = n0->n_out_p;
@@ -672,7 +717,8 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
     p.off_a = off; off += 2u * H * kRows * 2;
     p.x0_bytes = (uint32_t)p.K0p * kRows * 2;
     p.off_x0 = off; off += 2u * p.x0_bytes;
-    p.off_bias = off; off += (uint32_t)(a.n_roles * nb) * 4;
+    p.off_ones = off; off += 2u * kRows * 16;
+    p.off_bias = off; off += (uint32_t)(a.n_roles * n0->n_out_p) * 4;
     off = (off + 15) / 16 * 16;
     p.state_floats = 2u * p.a_dim * kSamp;
     p.off_state = off; off += 2u * p.state_floats * 4;
