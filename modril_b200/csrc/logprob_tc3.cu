@@ -30,7 +30,8 @@ namespace tc3 {
 
 using namespace tcc;
 
-constexpr int kThreads = 384;   // warp 0 producer, warps 1-2 MMA issuers (slot 0 / 1), warp 3 TMEM owner, 8 epilogue warps
+constexpr int kThreads = 448;   // warp 0 producer, warps 1-4 MMA issuers (2 per slot), warp 5 TMEM owner / peer relay, 8 epilogue warps
+constexpr int kEpiWarp0 = 6;
 constexpr int kEpiWarps = 8;
 constexpr int kSlotBytes = 20480;   // ring slot = this CTA's half of one weight block: [16 bias rows +] K = 64 rows of 128
 constexpr int kBarRing = 8;         // blocks in flight are tracked by sequence number % kBarRing
@@ -188,7 +189,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
     asm volatile(
         "{\n.reg .b32 ra;\nmapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}\n" ::"r"(bar), "r"(rank)
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n}\n" ::"r"(bar), "r"(rank)
         : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -222,10 +223,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem);
     auto w_full = [&](int s) { return bar0 + 8u * s; };                    // own half of the block has landed (tx)
-    auto w_fullp = [&](int s) { return bar0 + 8u * (kMaxSlots + s); };     // leader only: the peer's half has landed
     auto w_empty = [&](int s) { return bar0 + 8u * (2 * kMaxSlots + s); }; // both issuers' MMAs on the slot completed
     auto a_ready = [&](int slot, int ch) { return bar0 + 8u * (3 * kMaxSlots + slot * 2 + ch); };   // leader only
     auto d_full = [&](int slot) { return bar0 + 8u * (3 * kMaxSlots + 4 + slot); };
+    auto hand = [&](int slot, int x) { return bar0 + 8u * (3 * kMaxSlots + 6 + slot * 2 + x); };   // leader only
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
 
     constexpr uint32_t a_tile_bytes = (uint32_t)H * kRows * 2;   // 64 KB per slot
@@ -245,18 +246,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
-            mbar_init(w_full(s), 1);
-            mbar_init(w_fullp(s), 1);
+            // leader: own producer (arrive.expect_tx) + the peer's "my half has landed" relay; peer: own producer only
+            mbar_init(w_full(s), cta_rank == 0 ? 2 : 1);
             mbar_init(w_empty(s), 2);   // both issuers release a slot (multicast commit)
         }
         for (int slot = 0; slot < 2; ++slot) {
             mbar_init(a_ready(slot, 0), kEpiWarps);   // 4 warps of this column half in each of the two CTAs
             mbar_init(a_ready(slot, 1), kEpiWarps);
             mbar_init(d_full(slot), 1);
+            mbar_init(hand(slot, 0), 1);
+            mbar_init(hand(slot, 1), 1);
         }
         fence_barrier_init();
     }
-    if (warp == 3) {
+    if (warp == 5) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
@@ -313,7 +316,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                 }
             }
         }
-    } else if (warp == 3 && cta_rank == 1) {
+    } else if (warp == 5 && cta_rank == 1) {
         // ------------------------------- peer: tell the leader when my half of a block has landed -----------------
         if (lane == 0) {
             int stage = 0;
@@ -322,57 +325,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                 for (int step = 0; step < p.n_steps; ++step)
                     for (int b = 0; b < p.n_blocks; ++b) {
                         mbar_wait(w_full(stage), phase);
-                        mbar_arrive_remote(w_fullp(stage), 0);
+                        mbar_arrive_remote(w_full(stage), 0);
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
         }
-    } else if ((warp == 1 || warp == 2) && cta_rank == 0) {
-        // ------------------------------- leader: MMA issuer of one slot (of both CTAs) ----------------------------
+    } else if (warp >= 1 && warp <= 4 && cta_rank == 0) {
+        // ------------------------------- leader: the two MMA issuers of one slot (of both CTAs) -------------------
+        // A thread pays ~60 cycles per tcgen05.mma and ~230 per tcgen05.commit.  Two threads per slot alternate blocks:
+        // issuer x issues block b (b % 2 == x), hands the baton to its partner, and only then pays for its commits,
+        // which run in the shadow of the partner's MMAs.  The baton keeps the MMAs of a slot in block order (the
+        // accumulation order stays deterministic); the tensor pipe executes in issue order, so the commit of the
+        // last block of a layer also covers the partner's earlier blocks.  With an even number of ring slots a slot
+        // of the ring is always consumed by the same issuer, so no thread ever skips a phase of a barrier it waits on.
         if (lane == 0) {
-            const int slot = warp - 1;
+            const int slot = (warp - 1) >> 1, x = (warp - 1) & 1;
             int stage = 0;
-            uint32_t phase = 0, par_a0 = 0, par_a1 = 0;
+            uint32_t phase = 0, par_a0 = 0, par_a1 = 0, par_h = 0;
+            long long seq = 0;
             const uint4* rec = sRec + (size_t)slot * p.n_blocks * 2;
             const uint32_t ring_lo = smem_u32(sRing) >> 4;
             constexpr uint32_t kDescHi = (uint32_t)(128 >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
-            Tracer tr; tr.init(p.trace, 1 + slot);
+            Tracer tr; tr.init(x == 0 ? p.trace : nullptr, 1 + slot);
             for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
                 for (int step = 0; step < p.n_steps; ++step) {
-                    for (int b = 0; b < p.n_blocks; ++b) {
+                    for (int b = 0; b < p.n_blocks; ++b, ++seq) {
                         const uint4 r0 = rec[2 * b], r1 = rec[2 * b + 1];
-                        tr.mark(0x100 + b);
+                        // every issuer observes every readiness phase of the operand (a skipped phase would alias parities)
                         if (r0.z & (1u << 24)) { mbar_wait_cluster(a_ready(slot, 0), par_a0); par_a0 ^= 1; }
                         if (r0.z & (2u << 24)) { mbar_wait_cluster(a_ready(slot, 1), par_a1); par_a1 ^= 1; }
-                        mbar_wait(w_full(stage), phase);
-                        mbar_wait_cluster(w_fullp(stage), phase);
-                        tr.mark(0x300 + b);
-                        tc_fence_after();
-                        const uint32_t nrows = r0.z & 0xFFFF, nk = r1.x & 0xFF, nhalf = nrows >> 1;
-                        uint32_t a_lo = r0.x;
-                        uint32_t b_lo = ((ring_lo + (uint32_t)stage * (kSlotBytes >> 4)) & 0x3FFF) | (nhalf << 16);
-                        uint32_t acc = ((r1.x >> 8) & 1) ? 0u : 1u;
-                        if ((r1.x >> 16) & 1) {   // bias rows first: ones tile x [bias_hi; bias_mid; bias_lo; 0 ...]
-                            umma2_f16(tmem + r0.w, ((uint64_t)kDescHi << 32) | r1.y, ((uint64_t)kDescHi << 32) | b_lo, r0.y, 0u);
-                            acc = 1u;
-                            b_lo += 2 * nhalf;
+                        if ((int)(seq & 1) == x) {
+                            tr.mark(0x100 + b);
+                            if (seq > 0) { mbar_wait(hand(slot, x), par_h); par_h ^= 1; }
+                            mbar_wait(w_full(stage), phase);   // both halves of the block are in the two CTAs' rings
+                            tr.mark(0x300 + b);
+                            tc_fence_after();
+                            const uint32_t nrows = r0.z & 0xFFFF, nk = r1.x & 0xFF, nhalf = nrows >> 1;
+                            uint32_t a_lo = r0.x;
+                            uint32_t b_lo = ((ring_lo + (uint32_t)stage * (kSlotBytes >> 4)) & 0x3FFF) | (nhalf << 16);
+                            uint32_t acc = ((r1.x >> 8) & 1) ? 0u : 1u;
+                            if ((r1.x >> 16) & 1) {   // bias rows first: ones tile x [bias_hi; bias_mid; bias_lo; 0 ...]
+                                umma2_f16(tmem + r0.w, ((uint64_t)kDescHi << 32) | r1.y, ((uint64_t)kDescHi << 32) | b_lo, r0.y, 0u);
+                                acc = 1u;
+                                b_lo += 2 * nhalf;
+                            }
+                            for (uint32_t u = 0; u < nk; ++u) {
+                                umma2_f16(tmem + r0.w, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, r0.y, acc);
+                                acc = 1u;
+                                a_lo += 2 * (kChunk >> 4);
+                                b_lo += 2 * nhalf;
+                            }
+                            mbar_arrive(hand(slot, x ^ 1));
+                            umma2_commit_both(w_empty(stage));
+                            if ((r0.z >> 16) & 0xFF) umma2_commit_both(d_full(slot));
+                            tr.mark(0x400 + b);
                         }
-                        for (uint32_t u = 0; u < nk; ++u) {
-                            umma2_f16(tmem + r0.w, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, r0.y, acc);
-                            acc = 1u;
-                            a_lo += 2 * (kChunk >> 4);
-                            b_lo += 2 * nhalf;
-                        }
-                        umma2_commit_both(w_empty(stage));
-                        if ((r0.z >> 16) & 0xFF) umma2_commit_both(d_full(slot));
-                        tr.mark(0x400 + b);
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= kEpiWarp0) {
         // ------------------------------------------------ epilogue ------------------------------------------------
-        const int ew = warp - 4;
+        const int ew = warp - kEpiWarp0;
         const int q = warp & 3;                 // TMEM lane quarter: operand rows 32q .. 32q+31 = samples 16q .. 16q+15
         const int ch = ew >> 2;                 // column half (128 columns)
         const int et = ew * 32 + lane;
@@ -587,7 +601,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();   // the leader's last MMAs read the peer's shared memory: nobody leaves or frees TMEM early
-    if (warp == 3) {
+    if (warp == 5) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
     }
@@ -731,6 +745,7 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
     FRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, n0->cfg.device));
     int stages = ((int)max_smem - (int)off) / kSlotBytes;
     if (stages > kMaxSlots) stages = kMaxSlots;
+    stages &= ~1;   // even: a ring slot is then always consumed by the same one of a slot's two issuers
     if (stages < 4) return 1;   // not enough shared memory for the ring: the caller falls back to the 128-sample kernel
     p.n_stages = stages;
     const size_t smem_bytes = (size_t)off + (size_t)stages * kSlotBytes;

@@ -1,0 +1,25 @@
+"""Repeated bit-exact comparison of the CTA-pair integrator (FRL_TC_V3=1) with the default kernel (race detector)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from oracle import closed_form as cf, synth
+from tests.gpu_common import build_model, dev
+bad = 0
+for task, n_steps, B in (("maze", 20, 65536), ("hopper", 32, 100000), ("sine", 8, 777), ("pick", 32, 50000), ("halfcheetah", 32, 30001)):
+    sd, ad = synth.TASK_DIMS[task]
+    spec = cf.NetSpec(sd, ad, 256, 4, 2)
+    m = build_model(spec, cf.make_params(spec, 5, 1.0))
+    s, a = synth.states_actions(6, B, sd, ad); probe = synth.rademacher(7, (B, ad))
+    st, at, pt = dev(s), dev(a), dev(probe)
+    os.environ.pop("FRL_TC_V3", None)
+    ref = m.score(st, at, n_steps=n_steps, probe=pt, precision="fp16")
+    os.environ["FRL_TC_V3"] = "1"
+    for rep in range(20):
+        got = m.score(st, at, n_steps=n_steps, probe=pt, precision="fp16")
+        ok = all(torch.equal(g, r) for g, r in zip(got, ref))
+        if not ok:
+            bad += 1
+            d = max(((g - r).abs() / r.abs().clamp_min(1)).max().item() for g, r in zip(got, ref))
+            print(f"MISMATCH {task} rep {rep}: max rel {d:.3e}", flush=True)
+    print(f"{task} B={B} n={n_steps}: 20 reps done", flush=True)
+print("bad =", bad)
