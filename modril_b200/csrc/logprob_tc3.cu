@@ -197,7 +197,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     while (!ok) {
         asm volatile(
             "{\n.reg .pred p;\n"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
             "selp.b32 %0, 1, 0, p;\n}\n"
             : "=r"(ok)
             : "r"(bar), "r"(parity)
@@ -508,12 +508,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                     par_d[slot] ^= 1;
                     tc_fence_after();
                     tr.mark(0x2F0 + slot);
-                    if (ch == 0) {
+                    {
+                        // the heads have only NOp <= 64 columns: the two warps of a lane quarter split its two 16-row groups
                         uint8_t* x0 = sX0 + slot * p.x0_bytes;
                         float* sA_state = sState + slot * p.state_floats;
                         float* sP_state = sA_state + p.a_dim * kSamp;
-#pragma unroll
-                        for (int grp = 0; grp < 2; ++grp) {
+                        {
+                            const int grp = ch;
                             const int srow = q * 16 + grp * 8 + tr8;             // sample inside the tile
                             const int rowp = q * 32 + grp * 16 + tr8;
                             const long long g = (tile0 + slot) * kSamp + srow;
