@@ -774,16 +774,16 @@ int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
         set_error("FRL_PREC_BF16X3 is not implemented in this build");
         return FRL_ERR_UNSUPPORTED;
     }
-    // FRL_TC_V2=1 selects the experimental 64-sample / N = 256 integrator (logprob_tc2.cu).  It is parity-green but on
-    // one CTA its two in-flight tiles outgrow the shared-memory weight ring (profiles/r01f_tc2_experiment.md), so the
-    // 128-sample kernel below stays the default until the cta_group::2 version halves the ring bytes per CTA.
-    if (n0->pack_tc3 && getenv("FRL_TC_V3")) {
-        const int rc3 = launch_logprob_tc3(a, precision, stream);
-        if (rc3 <= 0) return rc3;
-    }
+    // Kernel selection.  Default: the CTA-pair integrator (logprob_tc3.cu, cta_group::2) whenever the net fits its plan
+    // (H = 256, padded input width <= 32, <= 64 head columns, >= 4 ring slots); otherwise -- or with FRL_TC_V1=1 -- the
+    // 128-sample single-CTA kernel below.  FRL_TC_V2=1 selects the single-CTA N = 256 experiment (logprob_tc2.cu).
     if (n0->pack_tc2 && getenv("FRL_TC_V2")) {
         const int rc2 = launch_logprob_tc2(a, precision, stream);
         if (rc2 <= 0) return rc2;   // > 0: shapes that do not fit the 64-sample kernel's shared-memory plan
+    }
+    if (n0->pack_tc3 && !getenv("FRL_TC_V1") && !getenv("FRL_TC_V2") && precision != FRL_PREC_BF16X3) {
+        const int rc3 = launch_logprob_tc3(a, precision, stream);
+        if (rc3 <= 0) return rc3;
     }
     if (!n0->pack_tc) {
         set_error("tensor-core weight image missing (network too deep for the block table)");

@@ -1,4 +1,4 @@
-"""Repeated bit-exact comparison of the CTA-pair integrator (FRL_TC_V3=1) with the default kernel (race detector)."""
+"""Repeated bit-exact comparison of the CTA-pair integrator (the default) with the default kernel (race detector)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,9 +11,9 @@ for task, n_steps, B in (("maze", 20, 65536), ("hopper", 32, 100000), ("sine", 8
     m = build_model(spec, cf.make_params(spec, 5, 1.0))
     s, a = synth.states_actions(6, B, sd, ad); probe = synth.rademacher(7, (B, ad))
     st, at, pt = dev(s), dev(a), dev(probe)
-    os.environ.pop("FRL_TC_V3", None)
+    os.environ["FRL_TC_V1"] = "1"
     ref = m.score(st, at, n_steps=n_steps, probe=pt, precision="fp16")
-    os.environ["FRL_TC_V3"] = "1"
+    os.environ.pop("FRL_TC_V1")
     for rep in range(20):
         got = m.score(st, at, n_steps=n_steps, probe=pt, precision="fp16")
         ok = all(torch.equal(g, r) for g, r in zip(got, ref))

@@ -283,3 +283,27 @@ def test_baseline_full_sizes_tensor_core_properties(task, B, n_steps):
     ref = cf.log_prob(spec, flat, s[lo:lo + 256], a[lo:lo + 256], "agent", probe[lo:lo + 256], n_steps)
     assert_close(la[lo:lo + 256].cpu().numpy(), ref, 2e-3, f"{task} fp16 vs oracle", kink_frac=0.02)
     assert_close(f32[1][:256].cpu().numpy(), ref, 1e-4, f"{task} fp32 vs oracle", kink_frac=0.02)
+
+
+@pytest.mark.parametrize("task,B,n_steps,mode", [("maze", 4097, 20, "fp16"), ("hopper", 20000, 32, "bf16"),
+                                                 ("sine", 130, 8, "fp16"), ("pick", 9000, 32, "fp16")])
+def test_cta_pair_integrator_is_bit_identical_to_single_cta_kernel(task, B, n_steps, mode, monkeypatch):
+    """The default tensor-core kernel (CTA pairs, tcgen05 cta_group::2, csrc/logprob_tc3.cu) performs exactly the
+    arithmetic of the 128-sample single-CTA kernel (FRL_TC_V1=1, csrc/logprob_tc.cu) -- same operand rounding, same
+    bias folding, same K order -- so the two must agree bit for bit, also with per-step probes and the exact trace.
+    (Any cross-CTA ordering bug would show up here as a mismatch.)"""
+    sd, ad = synth.TASK_DIMS[task]
+    spec = cf.NetSpec(sd, ad, 256, 4, 2)
+    m = build_model(spec, cf.make_params(spec, 22, 1.0))
+    s, a = synth.states_actions(33, B, sd, ad)
+    probe = synth.rademacher(34, (B, ad))
+    probe_steps = synth.rademacher(35, (n_steps, B, ad))
+    calls = [dict(probe=dev(probe)), dict(probe=dev(probe_steps))] + ([dict(exact=True)] if ad <= 4 else [])
+    for kw in calls:
+        monkeypatch.setenv("FRL_TC_V1", "1")
+        ref = m.score(dev(s), dev(a), n_steps=n_steps, precision=mode, **kw)
+        monkeypatch.delenv("FRL_TC_V1")
+        for _ in range(3):
+            got = m.score(dev(s), dev(a), n_steps=n_steps, precision=mode, **kw)
+            for g, r in zip(got, ref):
+                assert torch.equal(g, r)
