@@ -33,7 +33,8 @@ using namespace tcc;
 constexpr int kThreads = 448;   // warp 0 producer, warps 1-4 MMA issuers (2 per slot), warp 5 TMEM owner / peer relay, 8 epilogue warps
 constexpr int kEpiWarp0 = 6;
 constexpr int kEpiWarps = 8;
-constexpr int kSlotBytes = 20480;   // ring slot = this CTA's half of one weight block: [16 bias rows +] K = 64 rows of 128
+constexpr int kSlotBytesA = 20480;  // plan A ring slot = this CTA's half of one weight block: [16 bias rows +] K = 64 rows of 128
+constexpr int kSlotBytesB = 16384;  // plan B (wider layer-0 inputs leave less room): blocks of at most 64 rows
 constexpr int kBarRing = 8;         // blocks in flight are tracked by sequence number % kBarRing
 constexpr int kMaxSlots = 8;
 constexpr int kRows = 128;      // rows of the UMMA operand
@@ -67,6 +68,7 @@ struct Params {
     int n_roles, n_heads, depth, s_dim, a_dim, K0p, NOp;
     int n_steps, basis, accumulate, n_blocks, n_stages;
     float delta;
+    uint32_t slot_bytes;         // ring slot size of the plan in use
     int debug;                   // FRL_TC_DEBUG (timing experiments): 8 skip epilogue stores, 16 skip the bias add
     uint32_t rank_stride;        // bytes between the weight images of CTA rank 0 and rank 1
     unsigned long long* trace;   // FRL_TC_TRACE: [4 roles][8192] clock stamps of CTA 0 (timing experiments only)
@@ -310,7 +312,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                     for (int b = 0; b < p.n_blocks; ++b) {
                         mbar_wait(w_empty(stage), phase ^ 1);
                         mbar_expect_tx(w_full(stage), p.blk[b].bytes);
-                        bulk_g2s(smem_u32(sRing + (size_t)stage * kSlotBytes), wbase + p.blk[b].goff, p.blk[b].bytes, w_full(stage));
+                        bulk_g2s(smem_u32(sRing + (size_t)stage * p.slot_bytes), wbase + p.blk[b].goff, p.blk[b].bytes, w_full(stage));
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -361,7 +363,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                             tc_fence_after();
                             const uint32_t nrows = r0.z & 0xFFFF, nk = r1.x & 0xFF, nhalf = nrows >> 1;
                             uint32_t a_lo = r0.x;
-                            uint32_t b_lo = ((ring_lo + (uint32_t)stage * (kSlotBytes >> 4)) & 0x3FFF) | (nhalf << 16);
+                            uint32_t b_lo = ((ring_lo + (uint32_t)stage * (p.slot_bytes >> 4)) & 0x3FFF) | (nhalf << 16);
                             uint32_t acc = ((r1.x >> 8) & 1) ? 0u : 1u;
                             if ((r1.x >> 16) & 1) {   // bias rows first: ones tile x [bias_hi; bias_mid; bias_lo; 0 ...]
                                 umma2_f16(tmem + r0.w, ((uint64_t)kDescHi << 32) | r1.y, ((uint64_t)kDescHi << 32) | b_lo, r0.y, 0u);
@@ -621,9 +623,35 @@ static bool supported(const frl_net* net) {
     return net->cfg.hidden == H && net->d_in_p <= 32 && net->n_out_p <= 64;
 }
 
+// Shared-memory bytes in front of the ring (worst case: two roles), and the plan it leaves room for:
+//   plan A: four 20 KB slots, trunk layer = 4 blocks  [bias16 + K64] [K64] [K64] [K64]
+//   plan B: four 16 KB slots, trunk layer = 5 blocks  [bias16 + K48] [K64] [K64] [K64] [K16]
+// The choice depends only on the net's dimensions, so the packer and every launch agree.
+static uint32_t front_bytes(const frl_net* net, int n_roles) {
+    uint32_t off = 1024;
+    off += 2u * H * kRows * 2;
+    off += 2u * (uint32_t)net->d_in_p * kRows * 2;
+    off += 2u * kRows * 16;
+    off += (uint32_t)(n_roles * net->n_out_p) * 4;
+    off = (off + 15) / 16 * 16;
+    off += 2u * (2u * net->cfg.a_dim * kSamp) * 4;
+    off = (off + 15) / 16 * 16;
+    off += 4u * (uint32_t)(5 * net->cfg.depth + 3) * 16;   // issue records (upper bound on the block count)
+    return (off + 1023) / 1024 * 1024;
+}
+static int choose_plan(const frl_net* net) {
+    const uint32_t max_smem = 232448;   // sm_100a opt-in maximum of dynamic shared memory per CTA
+    const uint32_t front = front_bytes(net, 2);
+    if (const char* force = getenv("FRL_TC3_PLAN")) return atoi(force);   // experiments only
+    if (front + 4u * kSlotBytesA <= max_smem) return 0;
+    if (front + 4u * kSlotBytesB <= max_smem) return 1;
+    return -1;
+}
+
 static Schedule make_schedule(const frl_net* net) {
     Schedule sc;
     const int depth = net->cfg.depth, K0p = net->d_in_p, NOp = net->n_out_p;
+    const int plan = choose_plan(net);
     uint32_t goff = 0;
     auto add = [&](int layer, int nrows, int k0, int klen, int a_koff, int src, int bias, int first, int commit, int wait) {
         Blk b{};
@@ -642,8 +670,15 @@ static Schedule make_schedule(const frl_net* net) {
     // the accumulator-overwriting first block of every layer waits a_ready[slot][0] and [1]: both column halves of the
     // previous epilogue (in both CTAs) have drained the accumulator and written the whole operand
     add(0, H, 0, K0p, 0, 1, 1, 1, 1, 3);
-    for (int l = 1; l < depth; ++l)
-        for (int k0 = 0; k0 < H; k0 += 64) add(l, H, k0, 64, k0 / 8, 0, k0 == 0, k0 == 0, k0 + 64 >= H, k0 == 0 ? 3 : 0);
+    for (int l = 1; l < depth; ++l) {
+        if (plan == 0) {
+            for (int k0 = 0; k0 < H; k0 += 64) add(l, H, k0, 64, k0 / 8, 0, k0 == 0, k0 == 0, k0 + 64 >= H, k0 == 0 ? 3 : 0);
+        } else {
+            add(l, H, 0, 48, 0, 0, 1, 1, 0, 3);
+            for (int k0 = 48; k0 < 240; k0 += 64) add(l, H, k0, 64, k0 / 8, 0, 0, 0, 0, 0);
+            add(l, H, 240, 16, 240 / 8, 0, 0, 0, 1, 0);
+        }
+    }
     add(depth, NOp, 0, H / 2, 0, 0, 0, 1, 0, 3);
     add(depth, NOp, H / 2, H / 2, (H / 2) / 8, 0, 0, 0, 1, 0);
     sc.image_bytes = goff;
@@ -660,7 +695,7 @@ static size_t rank_image_stride(const frl_net* net, uint32_t image_bytes) {
 
 int tc3_pack(frl_net* net, const float* params_dev, cudaStream_t stream) {
     using namespace tc3;
-    if (!supported(net)) return FRL_OK;
+    if (!supported(net) || choose_plan(net) < 0) return FRL_OK;
     Schedule sc = make_schedule(net);
     if ((int)sc.blk.size() > kMaxBlocks) return FRL_OK;
     // [rank 0: fp16 image | bf16 image | bias] [rank 1: ...]
@@ -744,12 +779,13 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
     int max_smem = 0, sms = 0;
     FRL_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, n0->cfg.device));
     FRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, n0->cfg.device));
-    int stages = ((int)max_smem - (int)off) / kSlotBytes;
+    p.slot_bytes = choose_plan(n0) == 0 ? kSlotBytesA : kSlotBytesB;
+    int stages = ((int)max_smem - (int)off) / (int)p.slot_bytes;
     if (stages > kMaxSlots) stages = kMaxSlots;
     stages &= ~1;   // even: a ring slot is then always consumed by the same one of a slot's two issuers
     if (stages < 4) return 1;   // not enough shared memory for the ring: the caller falls back to the 128-sample kernel
     p.n_stages = stages;
-    const size_t smem_bytes = (size_t)off + (size_t)stages * kSlotBytes;
+    const size_t smem_bytes = (size_t)off + (size_t)stages * p.slot_bytes;
 
     const long long tiles_per_role = (a.B + kSamp - 1) / kSamp;
     const long long n_quads = ((tiles_per_role + 3) / 4) * a.n_roles;
