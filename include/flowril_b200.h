@@ -47,7 +47,7 @@ typedef enum {
 typedef enum {
     FRL_PREC_FP32 = 0,    /* FP32 FFMA on CUDA cores: the 1e-4 parity mode                               */
     FRL_PREC_BF16 = 1,    /* tcgen05 tensor cores, bf16 operands, fp32 accumulate, fp32 ODE state/trace  */
-    FRL_PREC_BF16X3 = 2,  /* tcgen05, 3-term split of both operands (fp32-grade products)                */
+    FRL_PREC_BF16X3 = 2,  /* reserved (3-term operand split, fp32-grade products): returns FRL_ERR_UNSUPPORTED   */
     FRL_PREC_FP16 = 3     /* tcgen05 tensor cores, fp16 operands (11-bit significand), fp32 accumulate   */
 } frl_precision;
 
@@ -82,9 +82,11 @@ int frl_net_create(const frl_net_config* cfg, frl_net** out);
 int frl_net_destroy(frl_net* net);
 long long frl_net_num_params(const frl_net* net);
 
-/* (Re)pack kernel-side weight layouts from the flat fp32 master copy (device pointer, state_dict order).
- * Replaces what load_state_dict / optimizer.step leave implicit in the reference (flowril.py:48-49, :330):
- * call after every change of the master weights. */
+/* Declare the flat fp32 master copy (device pointer, state_dict order) of the net's weights, or that its contents
+ * changed.  Replaces what load_state_dict / optimizer.step leave implicit in the reference (flowril.py:48-49, :330):
+ * call after every change of the master weights.  Packing is lazy: each kernel family rebuilds its own layout
+ * (transposed / padded fp32, 16-bit UMMA block streams, GEMM images) on its first use after this call, on the stream of
+ * that use, so the buffer must stay valid (and unchanged, or re-declared) until then.  `stream` is unused. */
 int frl_net_set_params(frl_net* net, const float* params_dev, void* stream);
 
 /* SharedVNet.forward / ConditionalVNet.forward (networks.py:23-25, :46-49).

@@ -16,7 +16,7 @@ PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3
 HAS_TC = True  # tensor-core (tcgen05) log-density kernels are built in
 PROBE_SHARED, PROBE_PER_STEP, PROBE_EXACT = 0, 1, 2
 REWARD_TYPES = {"raw": 0, "norm": 1, "exp": 2, "clip": 3, "smooth": 4}
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}   # PREC_BF16X3 (2) is reserved
 
 # every symbol include/flowril_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = (

@@ -220,7 +220,7 @@ extern "C" int frl_cfm_loss_grad_p(frl_net* net, float role_sign, const float* s
         set_error("frl_cfm_loss_grad_p: the tensor-core training path computes with fp16 operands (FRL_PREC_FP16)");
         return FRL_ERR_UNSUPPORTED;
     }
-    if (!net->pack_train) {
+    if (net->n_out_p > 64) {
         set_error("tensor-core training is not available for this net (a_dim too large)");
         return FRL_ERR_UNSUPPORTED;
     }

@@ -60,6 +60,13 @@ struct frl_net {
     void* pack_tc2 = nullptr;           // block stream of the 64+64-row / N = 256 integrator (logprob_tc2.cu)
     void* pack_tc3 = nullptr;           // per-CTA-rank block streams of the CTA-pair integrator (logprob_tc3.cu)
     bool has_params = false;
+    // Lazy packing: frl_net_set_params only records the master vector and bumps `version`; each kernel family
+    // (re)builds its own layout on first use after a change (frl::ensure_pack), on the consumer's stream.
+    const float* params_dev = nullptr;
+    unsigned long long version = 0;
+    unsigned long long packed[5] = {0, 0, 0, 0, 0};
+    cudaEvent_t pack_event[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t pack_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // tensor-core training: fp16 weight images (train_tc.cu) and workspace
     void* pack_train = nullptr;
     void* ws_tc = nullptr;
@@ -74,6 +81,11 @@ struct frl_net {
 void frl_host_stage_free(frl_net* net);  // api.cu
 
 namespace frl {
+
+// net.cu: weight layouts, built lazily
+enum PackKind { PACK_F32 = 0, PACK_TC1 = 1, PACK_TC2 = 2, PACK_TC3 = 3, PACK_TRAIN = 4 };
+int ensure_pack(const frl_net* net, int kind, cudaStream_t stream);
+int pack_f32(frl_net* net, const float* params_dev, cudaStream_t stream);
 
 // logprob_f32.cu
 struct ScoreArgs {

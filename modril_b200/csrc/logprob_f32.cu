@@ -338,6 +338,10 @@ int launch_reward(const float* le, const float* la, float* reward, long long B, 
 
 int launch_logprob_f32(const ScoreArgs& a, cudaStream_t stream) {
     const frl_net* n0 = a.net[0];
+    for (int r = 0; r < a.n_roles; ++r) {
+        int rcp = ensure_pack(a.net[r], PACK_F32, stream);
+        if (rcp != FRL_OK) return rcp;
+    }
     LogprobK p{};
     fill_common(p, n0);
     for (int r = 0; r < a.n_roles; ++r) {
@@ -372,6 +376,10 @@ int launch_logprob_f32(const ScoreArgs& a, cudaStream_t stream) {
 
 int launch_vfield_f32(const frl_net* net, const float* s, const float* a, const float* t, float* out0, float* out1,
                       long long B, cudaStream_t stream) {
+    {
+        int rcp = ensure_pack(net, PACK_F32, stream);
+        if (rcp != FRL_OK) return rcp;
+    }
     LogprobK p{};
     fill_common(p, net);
     p.net[0] = net->f32;

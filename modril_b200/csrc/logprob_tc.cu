@@ -751,11 +751,7 @@ int tc_pack(frl_net* net, const float* params_dev, cudaStream_t stream) {
     using namespace tc;
     Schedule sc = make_schedule(net);
     if ((int)sc.blk.size() > kMaxBlocks) return FRL_OK;
-    int rc = tc_pack_images(net, sc.pack, sc.image_bytes, &net->pack_tc, params_dev, stream);
-    if (rc != FRL_OK) return rc;
-    rc = tc2_pack(net, params_dev, stream);
-    if (rc != FRL_OK) return rc;
-    return tc3_pack(net, params_dev, stream);
+    return tc_pack_images(net, sc.pack, sc.image_bytes, &net->pack_tc, params_dev, stream);
 }
 
 template <typename T16, int H>
@@ -777,13 +773,29 @@ int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
     // Kernel selection.  Default: the CTA-pair integrator (logprob_tc3.cu, cta_group::2) whenever the net fits its plan
     // (H = 256, padded input width <= 32, <= 64 head columns, >= 4 ring slots); otherwise -- or with FRL_TC_V1=1 -- the
     // 128-sample single-CTA kernel below.  FRL_TC_V2=1 selects the single-CTA N = 256 experiment (logprob_tc2.cu).
-    if (n0->pack_tc2 && getenv("FRL_TC_V2")) {
-        const int rc2 = launch_logprob_tc2(a, precision, stream);
-        if (rc2 <= 0) return rc2;   // > 0: shapes that do not fit the 64-sample kernel's shared-memory plan
+    if (getenv("FRL_TC_V2")) {
+        for (int r = 0; r < a.n_roles; ++r) {
+            int rcp = ensure_pack(a.net[r], PACK_TC2, stream);
+            if (rcp != FRL_OK) return rcp;
+        }
+        if (n0->pack_tc2) {
+            const int rc2 = launch_logprob_tc2(a, precision, stream);
+            if (rc2 <= 0) return rc2;   // > 0: shapes that do not fit the 64-sample kernel's shared-memory plan
+        }
     }
-    if (n0->pack_tc3 && !getenv("FRL_TC_V1") && !getenv("FRL_TC_V2") && precision != FRL_PREC_BF16X3) {
-        const int rc3 = launch_logprob_tc3(a, precision, stream);
-        if (rc3 <= 0) return rc3;
+    if (!getenv("FRL_TC_V1") && !getenv("FRL_TC_V2") && precision != FRL_PREC_BF16X3) {
+        for (int r = 0; r < a.n_roles; ++r) {
+            int rcp = ensure_pack(a.net[r], PACK_TC3, stream);
+            if (rcp != FRL_OK) return rcp;
+        }
+        if (n0->pack_tc3) {
+            const int rc3 = launch_logprob_tc3(a, precision, stream);
+            if (rc3 <= 0) return rc3;
+        }
+    }
+    for (int r = 0; r < a.n_roles; ++r) {
+        int rcp = ensure_pack(a.net[r], PACK_TC1, stream);
+        if (rcp != FRL_OK) return rcp;
     }
     if (!n0->pack_tc) {
         set_error("tensor-core weight image missing (network too deep for the block table)");

@@ -129,6 +129,8 @@ extern "C" int frl_net_destroy(frl_net* net) {
     if (net->pack_tc3) cudaFree(net->pack_tc3);
     if (net->ws) cudaFree(net->ws);
     if (net->pack_train) cudaFree(net->pack_train);
+    for (int k = 0; k < 5; ++k)
+        if (net->pack_event[k]) cudaEventDestroy(net->pack_event[k]);
     if (net->ws_tc) cudaFree(net->ws_tc);
     frl_host_stage_free(net);
     delete net;
@@ -137,10 +139,9 @@ extern "C" int frl_net_destroy(frl_net* net) {
 
 extern "C" long long frl_net_num_params(const frl_net* net) { return net ? net->n_params : -1; }
 
-extern "C" int frl_net_set_params(frl_net* net, const float* params_dev, void* stream) {
-    FRL_REQUIRE(net && params_dev, "null net/params");
-    FRL_CUDA(cudaSetDevice(net->cfg.device));
-    cudaStream_t st = (cudaStream_t)stream;
+namespace frl {
+
+int pack_f32(frl_net* net, const float* params_dev, cudaStream_t st) {
     const int H = net->cfg.hidden, A = net->cfg.a_dim;
     PackTable tab;
     int nj = 0;
@@ -173,12 +174,42 @@ extern "C" int frl_net_set_params(frl_net* net, const float* params_dev, void* s
     if (blocks > 592) blocks = 592;
     pack_f32_kernel<<<blocks, threads, 0, st>>>(params_dev, net->pack_f32, tab);
     FRL_CUDA(cudaGetLastError());
-    int rc = tc_pack(net, params_dev, st);
-    if (rc != FRL_OK) return rc;
-    if (net->n_out_p <= 64) {   // fp16 GEMM images of the tensor-core training path
-        rc = tc_train_pack(net, params_dev, st);
-        if (rc != FRL_OK) return rc;
+    return FRL_OK;
+}
+
+// Build the layout `kind` from the current master weights if it is stale.  Runs on the consumer's stream, so the pack
+// is ordered before the kernel that needs it; a different stream that finds the layout up to date waits on the event
+// recorded after the pack.
+int ensure_pack(const frl_net* cnet, int kind, cudaStream_t st) {
+    frl_net* net = const_cast<frl_net*>(cnet);
+    if (net->packed[kind] == net->version) {
+        if (net->pack_stream[kind] != st && net->pack_event[kind])
+            FRL_CUDA(cudaStreamWaitEvent(st, net->pack_event[kind], 0));
+        return FRL_OK;
     }
+    int rc = FRL_OK;
+    switch (kind) {
+        case PACK_F32: rc = pack_f32(net, net->params_dev, st); break;
+        case PACK_TC1: rc = tc_pack(net, net->params_dev, st); break;
+        case PACK_TC2: rc = tc2_pack(net, net->params_dev, st); break;
+        case PACK_TC3: rc = tc3_pack(net, net->params_dev, st); break;
+        case PACK_TRAIN: rc = net->n_out_p <= 64 ? tc_train_pack(net, net->params_dev, st) : FRL_OK; break;
+        default: set_error("bad pack kind"); return FRL_ERR_INVALID;
+    }
+    if (rc != FRL_OK) return rc;
+    if (!net->pack_event[kind]) FRL_CUDA(cudaEventCreateWithFlags(&net->pack_event[kind], cudaEventDisableTiming));
+    FRL_CUDA(cudaEventRecord(net->pack_event[kind], st));
+    net->pack_stream[kind] = st;
+    net->packed[kind] = net->version;
+    return FRL_OK;
+}
+
+}  // namespace frl
+
+extern "C" int frl_net_set_params(frl_net* net, const float* params_dev, void* /*stream*/) {
+    FRL_REQUIRE(net && params_dev, "null net/params");
+    net->params_dev = params_dev;
+    net->version += 1;     // every kernel family re-packs its own layout on next use (frl::ensure_pack)
     net->has_params = true;
     return FRL_OK;
 }

@@ -251,6 +251,10 @@ int cfm_loss_grad_f32(frl_net* net, float role_sign, const float* s, const float
     const int H = net->cfg.hidden, A = net->cfg.a_dim, depth = net->cfg.depth;
     const int K0p = net->d_in_p, NOp = net->n_out_p;
     FRL_REQUIRE(B > 0 && B < (1ll << 31) / std::max(H, K0p), "batch size out of range");
+    {
+        int rcp = ensure_pack(net, PACK_F32, st);
+        if (rcp != FRL_OK) return rcp;
+    }
     const int Bi = (int)B;
     const double div = (double)(mean_divisor > 0 ? mean_divisor : B);
 
@@ -499,6 +503,10 @@ int reg_loss_grad_f32(frl_net* net, const float* s, const float* a, const float*
     const int H = net->cfg.hidden, A = net->cfg.a_dim, depth = net->cfg.depth;
     const int K0p = net->d_in_p, NOp = net->n_out_p;
     FRL_REQUIRE(N > 0 && 2 * N < (1ll << 31) / std::max(H, K0p), "batch size out of range");
+    {
+        int rcp = ensure_pack(net, PACK_F32, st);
+        if (rcp != FRL_OK) return rcp;
+    }
     const int Ni = (int)N, R2 = 2 * Ni;
     const double div = (double)(mean_divisor > 0 ? mean_divisor : N);
     const float dscale = (float)(2.0 / div);

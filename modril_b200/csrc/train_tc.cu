@@ -701,6 +701,12 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
     const int H = net->cfg.hidden, A = net->cfg.a_dim, depth = net->cfg.depth;
     const int K0p = net->d_in_p, NOp = net->n_out_p;
     FRL_REQUIRE(B > 0 && B < (1ll << 30), "batch size out of range");
+    {
+        int rcp = ensure_pack(net, PACK_TRAIN, st);   // fp16 GEMM images
+        if (rcp != FRL_OK) return rcp;
+        rcp = ensure_pack(net, PACK_F32, st);          // fp32 biases
+        if (rcp != FRL_OK) return rcp;
+    }
     FRL_REQUIRE(net->pack_train != nullptr, "tensor-core training weights missing");
     FRL_REQUIRE(NOp <= 64, "a_dim too large for the tensor-core training path");
     const double div = (double)(mean_divisor > 0 ? mean_divisor : B);

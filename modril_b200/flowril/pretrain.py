@@ -35,7 +35,7 @@ _DEFAULT_PRECISION = "fp32"
 
 
 def set_default_precision(name: str):
-    """'fp32' (FFMA, 1e-4 parity), 'bf16' or 'bf16x3' (tcgen05 tensor cores) for log_prob calls that do not
+    """'fp32' (FFMA, 1e-4 parity), 'fp16' or 'bf16' (tcgen05 tensor cores) for log_prob calls that do not
     pass ``precision=`` explicitly."""
     global _DEFAULT_PRECISION
     if name not in _native.PRECISIONS:
