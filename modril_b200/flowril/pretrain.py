@@ -129,9 +129,7 @@ def score_pair_host(net_e, net_a, s, a, probe=None, exact=False, n_steps=32, rew
     (logp_E, logp_A, reward).  Pinned inputs/outputs (``tensor.pin_memory()``) make the copies asynchronous.
     ``out``: optional tuple of three preallocated CPU float32 tensors [B]."""
     dev = net_e.flat_params().device
-    torch.cuda.current_stream(dev).synchronize()  # pending weight packs run on the caller's stream
-    he, ha = net_e.native(), net_a.native()
-    torch.cuda.current_stream(dev).synchronize()
+    he, ha = net_e.native(), net_a.native()   # (the library synchronises the device itself before it stages the batch)
 
     def host(x, what):
         if x.device.type != "cpu":
