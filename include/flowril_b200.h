@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FRL_ABI_VERSION 3
+#define FRL_ABI_VERSION 4
 #define FRL_MAX_STEPS 256
 #define FRL_MAX_DEPTH 8
 
@@ -195,6 +195,42 @@ int frl_clip_adam(const frl_adam_segment* segs, int n_segs, long long step, doub
  * whole update (frl_cfm_loss_grad_p ... frl_clip_adam_dev, frl_net_set_params) replays correctly step after step. */
 int frl_clip_adam_dev(const frl_adam_segment* segs, int n_segs, long long* step_dev, double lr, double beta1,
                       double beta2, double eps, double max_norm, float* norm_out_dev, int device, void* stream);
+
+/* ---- BCF flow-matching policy (behaviour cloning with a flow-matching actor; scope row f3) ------------------------
+ * VectorNetwork (deps/rl-toolkit/rlf/rl/model.py:391-432): three embeddings + a two-layer velocity head,
+ *   v(x, s, t) = W2 relu(W1 [relu(Ws s + bs) | relu(Wt2 relu(wt1 t + bt1) + bt2) | relu(Wa x + ba)] + b1) + b2.
+ * Parameters are ONE flat FP32 vector in state_dict() order: time_embed.0.{weight [T,1], bias}, time_embed.2.{weight
+ * [H,T], bias}, state_embed.0.{weight [H,S], bias}, action_embed.0.{weight [H,A], bias}, velocity_head.0.{weight
+ * [H,3H], bias}, velocity_head.2.{weight [A,H], bias}.  hidden and time_dim must be multiples of 16. */
+typedef struct {
+    int s_dim, a_dim, hidden, time_dim; /* model.py:392 (state_dim, action_dim, hidden_dim=256, time_embed_dim=128) */
+    int device;
+} frl_vnet_config;
+typedef struct frl_vnet frl_vnet;
+int frl_vnet_create(const frl_vnet_config* cfg, frl_vnet** out);
+int frl_vnet_destroy(frl_vnet* net);
+long long frl_vnet_num_params(const frl_vnet* net);
+/* Same contract as frl_net_set_params: params_dev stays owned by the caller, kernel-side layouts are rebuilt lazily. */
+int frl_vnet_set_params(frl_vnet* net, const float* params_dev, void* stream);
+
+/* VectorNetwork.forward(x, state, t) (model.py:422-432): x [B,A], s [B,S], t [B] -> v [B,A]. */
+int frl_vnet_forward(frl_vnet* net, const float* x_dev, const float* s_dev, const float* t_dev, float* v_dev,
+                     long long B, void* stream);
+
+/* FlowPolicy.get_action's Euler sampler (rlf/policies/flow_policy.py:49-63): x <- x0 (the caller's N(0,1) draw,
+ * flow_policy.py:53), then n_steps of x += v(x, s, i/n_steps) / n_steps; writes the action [B,A].  The state
+ * embedding is computed once.  action_dev may alias x0_dev. */
+int frl_vnet_sample(frl_vnet* net, const float* s_dev, const float* x0_dev, int n_steps, float* action_dev, long long B,
+                    void* stream);
+
+/* Loss and parameter gradient of BehaviorCloneFlowMatching._bc_step (rlf/algos/il/bcf.py:108-128):
+ *   x_t = (1-t) x0 + t a;  flow = mse(v(x_t, s, t), a - x0);  act = mse(x0 + v(a, s, 1), a);  loss = flow + bc_coef act.
+ * x0 [B,A] and t [B] are the caller's draws (bcf.py:109-110).  losses_dev (may be NULL) receives {loss, flow, act};
+ * grad_dev (flat, state_dict order; may be NULL) receives grad_scale * dloss/dparams, overwritten or accumulated.
+ * mean_divisor: rows the mean is taken over (0 = B; the global batch under data parallelism).  Deterministic. */
+int frl_bcf_loss_grad(frl_vnet* net, const float* s_dev, const float* actions_dev, const float* x0_dev,
+                      const float* t_dev, long long B, long long mean_divisor, float bc_coef, float grad_scale,
+                      int accumulate, float* losses_dev, float* grad_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libflowril_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3
 HAS_TC = True  # tensor-core (tcgen05) log-density kernels are built in
 PROBE_SHARED, PROBE_PER_STEP, PROBE_EXACT = 0, 1, 2
@@ -23,12 +23,18 @@ EXPORTS = (
     "frl_abi_version", "frl_last_error", "frl_net_create", "frl_net_destroy", "frl_net_num_params",
     "frl_net_set_params", "frl_vfield", "frl_logprob", "frl_score", "frl_score_host", "frl_cfm_loss_grad",
     "frl_clip_adam", "frl_reg_loss_grad", "frl_grad_axpy", "frl_tensor_norms", "frl_normalise_rewards", "frl_cfm_loss_grad_p", "frl_clip_adam_dev",
+    "frl_vnet_create", "frl_vnet_destroy", "frl_vnet_num_params", "frl_vnet_set_params", "frl_vnet_forward",
+    "frl_vnet_sample", "frl_bcf_loss_grad",
 )
 
 
 class NetConfig(C.Structure):
     _fields_ = [("s_dim", C.c_int), ("a_dim", C.c_int), ("hidden", C.c_int), ("depth", C.c_int),
                 ("n_heads", C.c_int), ("device", C.c_int)]
+
+
+class VNetConfig(C.Structure):
+    _fields_ = [("s_dim", C.c_int), ("a_dim", C.c_int), ("hidden", C.c_int), ("time_dim", C.c_int), ("device", C.c_int)]
 
 
 class AdamSegment(C.Structure):
@@ -72,9 +78,17 @@ def lib():
     L.frl_clip_adam_dev.argtypes = [C.POINTER(AdamSegment), i32, vp, f64, f64, f64, f64, f64, vp, i32, vp]
     L.frl_tensor_norms.argtypes = [vp, C.POINTER(ll), i32, vp, i32, vp]
     L.frl_clip_adam.argtypes = [C.POINTER(AdamSegment), i32, ll, f64, f64, f64, f64, f64, vp, i32, vp]
+    L.frl_vnet_create.argtypes = [C.POINTER(VNetConfig), C.POINTER(vp)]
+    L.frl_vnet_destroy.argtypes = [vp]
+    L.frl_vnet_num_params.argtypes = [vp]
+    L.frl_vnet_num_params.restype = ll
+    L.frl_vnet_set_params.argtypes = [vp, vp, vp]
+    L.frl_vnet_forward.argtypes = [vp, vp, vp, vp, vp, ll, vp]
+    L.frl_vnet_sample.argtypes = [vp, vp, vp, i32, vp, ll, vp]
+    L.frl_bcf_loss_grad.argtypes = [vp, vp, vp, vp, vp, ll, ll, f32, f32, i32, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("frl_last_error", "frl_net_num_params"):
+        if name not in ("frl_last_error", "frl_net_num_params", "frl_vnet_num_params"):
             fn.restype = i32
     if L.frl_abi_version() != ABI_VERSION:
         raise NativeError(f"ABI mismatch: library {L.frl_abi_version()} != binding {ABI_VERSION}")

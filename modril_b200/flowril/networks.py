@@ -116,9 +116,14 @@ class _FlatVNet(nn.Module):
             off += p.numel()
 
     # ---- native handle ------------------------------------------------------------------------------------
+    _ABI = ("frl_net_create", "frl_net_destroy", "frl_net_set_params")
+
+    def _native_config(self, device_index: int):
+        return _native.NetConfig(self.s_dim, self.a_dim, self.hidden, self.depth, self.n_heads, device_index)
+
     def _release(self):
         if getattr(self, "_handle", None):
-            _native.lib().frl_net_destroy(self._handle)
+            getattr(_native.lib(), self._ABI[1])(self._handle)
         self._handle = None
         self._packed_key = None
 
@@ -138,15 +143,14 @@ class _FlatVNet(nn.Module):
                 "Move the module with .to('cuda').")
         L = _native.lib()
         if self._handle is None:
-            depth = self.depth
-            cfg = _native.NetConfig(self.s_dim, self.a_dim, self.hidden, depth, self.n_heads, dev.index or 0)
+            cfg = self._native_config(dev.index or 0)
             h = C.c_void_p()
-            _native.check(L.frl_net_create(C.byref(cfg), C.byref(h)), "frl_net_create")
+            _native.check(getattr(L, self._ABI[0])(C.byref(cfg), C.byref(h)), self._ABI[0])
             self._handle = h
         key = (self._flat.data_ptr(), tuple(p._version for p in self._ordered_params()))
         if key != self._packed_key:
-            _native.check(L.frl_net_set_params(self._handle, _ptr(self._flat), _current_stream(dev)),
-                          "frl_net_set_params")
+            _native.check(getattr(L, self._ABI[2])(self._handle, _ptr(self._flat), _current_stream(dev)),
+                          self._ABI[2])
             self._packed_key = key
         return self._handle
 

@@ -15,6 +15,8 @@ What is pinned (reference call sites in brackets):
   fmloss_*.npz    fm_loss value and autograd gradients [pretrain.py:179-190, :94-109] with t / noise injected
   reg_*.npz       the anti-divergence / Jacobian-stability regularisers [flowril.py:257-263 -> pretrain.py:163-177,
                   :55-59] and their double-backward parameter gradients; trainreg_*.npz: the update loop with them.
+  bcf_*.npz       VectorNetwork.forward, the BCF loss + gradients and the Euler action sampler [rlf/rl/model.py:391-432,
+                  rlf/algos/il/bcf.py:108-128, rlf/policies/flow_policy.py:49-63]; bcftrain_*.npz: _bc_step updates.
   train_*.npz     the update loop of flowril.py:311-335 (zero_grad, backward, clip_grad_norm_, Adam.step) for
                   scrf (all params), scrf fine-tune (head_r only, flowril.py:52-63) and 2fs; loss curves + final
                   parameters.
@@ -380,6 +382,147 @@ def gen_gradnorm():
     print("wrote gradnorm_00.npz", traj[-1])
 
 
+def load_vector_network():
+    """The reference's ``VectorNetwork`` class object.  ``rlf.rl.model`` imports the whole toolkit (gym, ...), which is
+    not installed here, so the class and the two init helpers it uses are compiled from the reference source file as it
+    lies under /root/reference (nothing is copied into the repo)."""
+    import ast
+
+    import torch
+    import torch.nn as nn
+
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "deps", "rl-toolkit", "rlf", "rl", "model.py")
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body
+            if (isinstance(n, ast.ClassDef) and n.name == "VectorNetwork")
+            or (isinstance(n, ast.FunctionDef) and n.name in ("weight_init", "no_bias_weight_init"))]
+    assert len(keep) == 3, [getattr(n, "name", None) for n in keep]
+    ns = {"torch": torch, "nn": nn, "np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns["VectorNetwork"]
+
+
+def build_vnet(VN, spec, flat, dtype=None):
+    import torch
+
+    m = VN(spec.s_dim, spec.a_dim, spec.hidden, spec.time_dim)
+    sd = m.state_dict()
+    assert [k for k in sd] == [n for n, _ in spec.shapes()], list(sd)
+    off = 0
+    for (name, shape) in spec.shapes():
+        n = int(np.prod(shape))
+        sd[name].copy_(torch.from_numpy(np.asarray(flat[off:off + n], np.float32).reshape(shape)))
+        off += n
+    return m.double() if dtype == "f64" else m
+
+
+def ref_bcf_loss(model, s, a, x0, t, coef):
+    """bcf.py:108-128 with the draws (x0, t) injected."""
+    import torch
+    import torch.nn.functional as F
+
+    dt = next(model.parameters()).dtype
+    states, actions, x0, t = (torch.from_numpy(np.asarray(v)).to(dt) for v in (s, a, x0, t.reshape(-1, 1)))
+    x_t = (1 - t) * x0 + t * actions
+    v_pred = model(x_t, states, t)
+    flow_loss = F.mse_loss(v_pred, actions - x0)
+    v_end = model(actions, states, torch.ones_like(t))
+    action_loss = F.mse_loss(x0 + v_end, actions)
+    return flow_loss + coef * action_loss, flow_loss, action_loss
+
+
+def ref_sample(model, s, x0, n_steps):
+    """flow_policy.py:49-63 with the initial draw injected."""
+    import torch
+
+    dt_ = next(model.parameters()).dtype
+    state, x = torch.from_numpy(s).to(dt_), torch.from_numpy(x0).to(dt_)
+    dt = 1.0 / n_steps
+    with torch.no_grad():
+        for i in range(n_steps):
+            t = torch.full((x.shape[0], 1), fill_value=i * dt).to(dt_)
+            x = x + model(x, state, t) * dt
+    return x.numpy()
+
+
+BCF_CASES = (  # (task, hidden, time_dim, B, coef, n_steps)
+    ("maze", 256, 128, 128, 1.0, 32),
+    ("hopper", 128, 128, 128, 1.0, 32),
+    ("sine", 64, 32, 100, 0.5, 20),
+    ("ant", 128, 64, 37, 2.0, 7),
+    ("hand", 192, 48, 64, 1.0, 32),
+)
+
+
+def bcf_inputs(seed, B, s_dim, a_dim):
+    s, _ = synth.states_actions(seed + 1, B, s_dim, a_dim)
+    a = synth.expert_actions(seed + 2, s, a_dim)
+    g = synth.rng(seed + 3)
+    x0 = g.standard_normal((B, a_dim)).astype(np.float32)
+    t = g.random(B).astype(np.float32)
+    return s, a, x0, t
+
+
+def gen_bcf():
+    """bcf_*.npz: VectorNetwork.forward, the bcf loss + autograd gradients (fp32 as the reference runs, and an fp64
+    copy of the same module for a tight pin of the oracle) and the Euler sampler; bcftrain_*.npz: 200 updates of
+    _bc_step + _standard_step (clip 0.5, Adam eps 1e-12, lr 1e-3)."""
+    import torch
+
+    from oracle import bcf_closed_form as bcf
+
+    VN = load_vector_network()
+    for idx, (task, hidden, tdim, B, coef, n_steps) in enumerate(BCF_CASES):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        spec = bcf.VNetSpec(s_dim, a_dim, hidden, tdim)
+        seed = 7000 + idx
+        flat = bcf.make_params(spec, seed, 1.0)
+        s, a, x0, t = bcf_inputs(seed, B, s_dim, a_dim)
+        out = {"meta": np.array([s_dim, a_dim, hidden, tdim, B, n_steps, seed]), "coef": np.float32(coef)}
+        for tag in ("f32", "f64"):
+            m = build_vnet(VN, spec, flat, tag)
+            dt = next(m.parameters()).dtype
+            with torch.no_grad():
+                out[f"v_{tag}"] = m(torch.from_numpy(x0).to(dt), torch.from_numpy(s).to(dt),
+                                    torch.from_numpy(t).to(dt)).numpy()     # 1-D t: model.py:423-424
+            loss, fl, al = ref_bcf_loss(m, s, a, x0, t, coef)
+            loss.backward()
+            out[f"loss_{tag}"] = np.array([loss.item(), fl.item(), al.item()])
+            g = np.concatenate([p.grad.numpy().ravel() for p in m.parameters()])
+            out[f"grad_{tag}"] = g if g.size < 100_000 else g.astype(np.float32)   # keep the fixtures small
+            out[f"sample_{tag}"] = ref_sample(m, s, x0, n_steps)
+        name = f"bcf_{idx:02d}_{task}_h{hidden}.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print("wrote", name, out["loss_f32"])
+
+    for idx, (task, hidden, steps) in enumerate((("hopper", 128, 200), ("maze", 256, 100))):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        spec = bcf.VNetSpec(s_dim, a_dim, hidden, 128)
+        seed, B, lr = 7500 + idx, 128, 1e-3
+        m = build_vnet(VN, spec, bcf.make_params(spec, seed, 1.0))
+        opt = torch.optim.Adam(m.parameters(), lr=lr, eps=1e-12)
+        pool_s, _ = synth.states_actions(seed + 1, 4096, s_dim, a_dim)
+        pool_a = synth.expert_actions(seed + 2, pool_s, a_dim)
+        curve = np.zeros((steps, 3), np.float32)
+        norms = np.zeros(steps, np.float32)
+        for it in range(steps):
+            g = synth.rng(seed + 100 + it)
+            i = g.integers(0, 4096, B)
+            x0 = g.standard_normal((B, a_dim)).astype(np.float32)
+            t = g.random(B).astype(np.float32)
+            loss, fl, al = ref_bcf_loss(m, pool_s[i], pool_a[i], x0, t, 1.0)
+            opt.zero_grad()
+            loss.backward()
+            norms[it] = float(torch.nn.utils.clip_grad_norm_(m.parameters(), 0.5))
+            opt.step()
+            curve[it] = (loss.item(), fl.item(), al.item())
+        name = f"bcftrain_{idx:02d}_{task}_h{hidden}_{steps}steps.npz"
+        np.savez_compressed(os.path.join(OUT, name), meta=np.array([s_dim, a_dim, hidden, 128, steps, B, seed]),
+                            lr=np.float32(lr), curve=curve, gradnorm=norms,
+                            final_params=np.concatenate([p.detach().numpy().ravel() for p in m.parameters()]))
+        print("wrote", name, curve[0], curve[-1])
+
+
 def main():
     import torch
 
@@ -387,7 +530,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     P = ref_shim.load()
-    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm"]
+    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "bcf"]
     if "logprob" in which:
         gen_logprob(P)
     if "vfield" in which:
@@ -402,6 +545,8 @@ def main():
         gen_train_reg(P)
     if "gradnorm" in which:
         gen_gradnorm()
+    if "bcf" in which:
+        gen_bcf()
 
 
 if __name__ == "__main__":

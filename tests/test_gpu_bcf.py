@@ -1,0 +1,144 @@
+"""GPU parity of the BCF flow-matching policy kernels (frl_vnet_forward / frl_vnet_sample / frl_bcf_loss_grad through
+the C ABI) against the reference goldens (tests/golden/bcf_*.npz) and the CPU oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bcf_closed_form as bcf
+from oracle import synth
+from oracle.gen_golden import bcf_inputs
+from tests.gpu_common import dev
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def build_vnet(spec, flat):
+    from modril_b200.bcf import VectorNetwork
+
+    m = VectorNetwork(spec.s_dim, spec.a_dim, spec.hidden, spec.time_dim).to("cuda:0")
+    m.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in bcf.unpack(spec, flat).items()})
+    return m
+
+
+def _rel_l2(got, ref):
+    ref = np.asarray(ref, np.float64)
+    return np.sqrt(((np.asarray(got, np.float64) - ref) ** 2).sum()) / np.sqrt((ref ** 2).sum())
+
+
+def test_state_dict_keys_match_reference_module():
+    from modril_b200.bcf import VectorNetwork
+
+    spec = bcf.VNetSpec(11, 3)
+    m = VectorNetwork(11, 3)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(n, tuple(s)) for n, s in spec.shapes()]
+    assert all(float(b.abs().max()) == 0.0 for n, b in m.state_dict().items() if n.endswith("bias"))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 3), torch.zeros(2, 11), torch.zeros(2))   # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "bcf_*.npz"))), ids=os.path.basename)
+def test_forward_loss_grad_sampler_vs_reference(path):
+    g = np.load(path)
+    s_dim, a_dim, hidden, tdim, B, n_steps, seed = (int(x) for x in g["meta"])
+    spec = bcf.VNetSpec(s_dim, a_dim, hidden, tdim)
+    flat = bcf.make_params(spec, seed, 1.0)
+    s, a, x0, t = bcf_inputs(seed, B, s_dim, a_dim)
+    coef = float(g["coef"])
+    m = build_vnet(spec, flat)
+    v = m(dev(x0), dev(s), dev(t)).cpu().numpy()
+    assert np.abs(v - g["v_f64"]).max() <= 2e-5
+    v2 = m(dev(x0), dev(s), dev(t.reshape(-1, 1))).cpu().numpy()          # [B,1] times (model.py:423-424)
+    assert np.array_equal(v, v2)
+    losses = m.bcf_loss(dev(s), dev(a), x0=dev(x0), t=dev(t), bc_coef=coef).cpu().numpy()
+    assert np.allclose(losses, g["loss_f64"], rtol=1e-5), (losses, g["loss_f64"])
+    grad = m.flat_grad().cpu().numpy()
+    assert _rel_l2(grad, g["grad_f64"]) <= 1e-4
+    assert np.abs(grad - g["grad_f64"]).max() <= 5e-4 * np.abs(g["grad_f64"]).max()
+    off = 0
+    for name, shape in spec.shapes():
+        n = int(np.prod(shape))
+        ref = g["grad_f64"][off:off + n].astype(np.float64)
+        assert _rel_l2(grad[off:off + n], ref) <= 3e-4, name
+        off += n
+    # loss only (grad=False) leaves the gradient buffer alone; accumulate adds; grad_scale scales
+    before = m.flat_grad().clone()
+    l2 = m.bcf_loss(dev(s), dev(a), x0=dev(x0), t=dev(t), bc_coef=coef, grad=False)
+    assert torch.equal(before, m.flat_grad()) and torch.equal(l2.cpu(), torch.from_numpy(losses))
+    m.bcf_loss(dev(s), dev(a), x0=dev(x0), t=dev(t), bc_coef=coef, accumulate=True, grad_scale=0.5)
+    assert _rel_l2(m.flat_grad().cpu().numpy(), 1.5 * g["grad_f64"].astype(np.float64)) <= 1e-4
+    x = m.sample_actions(dev(s), n_steps, x0=dev(x0)).cpu().numpy()
+    assert np.abs(x - g["sample_f64"]).max() <= 1e-4 * max(1.0, np.abs(g["sample_f64"]).max())
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "bcftrain_*.npz"))), ids=os.path.basename)
+def test_bc_updates_follow_reference_curve(path):
+    from modril_b200.bcf import FlowPolicy, FusedAdam, bc_step
+
+    g = np.load(path)
+    s_dim, a_dim, hidden, tdim, steps, B, seed = (int(x) for x in g["meta"])
+    spec = bcf.VNetSpec(s_dim, a_dim, hidden, tdim)
+    net = build_vnet(spec, bcf.make_params(spec, seed, 1.0))
+    policy = FlowPolicy(net)
+    opt = FusedAdam([net], lr=float(g["lr"]), eps=1e-12)
+    pool_s, _ = synth.states_actions(seed + 1, 4096, s_dim, a_dim)
+    pool_a = synth.expert_actions(seed + 2, pool_s, a_dim)
+    pool_s_d, pool_a_d = dev(pool_s), dev(pool_a)
+    curve, norms = [], []
+    for it in range(steps):
+        r = synth.rng(seed + 100 + it)
+        i = torch.from_numpy(r.integers(0, 4096, B)).cuda()
+        x0 = r.standard_normal((B, a_dim)).astype(np.float32)
+        t = r.random(B).astype(np.float32)
+        curve.append(bc_step(policy, opt, pool_s_d[i], pool_a_d[i], x0=dev(x0), t=dev(t)))
+        norms.append(opt._norm.clone())
+    curve = torch.stack(curve).cpu().numpy()
+    norms = torch.cat(norms).cpu().numpy()
+    # fp32 training trajectories separate slowly (ReLU kinks + Adam's sign-like early steps): tight early, loose late
+    assert np.allclose(curve[:20], g["curve"][:20], rtol=2e-3), np.abs(curve[:20] / g["curve"][:20] - 1).max()
+    assert np.allclose(curve, g["curve"], rtol=5e-2), np.abs(curve / g["curve"] - 1).max()
+    assert np.allclose(norms[:20], g["gradnorm"][:20], rtol=5e-3)
+    final = net.flat_params().cpu().numpy()
+    assert _rel_l2(final, g["final_params"]) <= 2e-2
+    # the trained policy acts: sampler output stays finite and near the expert's action range
+    act = policy.get_action(pool_s_d[:256]).cpu().numpy()
+    assert np.isfinite(act).all() and np.abs(act).max() < 10.0
+
+
+def test_large_ragged_batch_matches_oracle_and_is_deterministic():
+    spec = bcf.VNetSpec(17, 6, 256, 128)
+    flat = bcf.make_params(spec, 99, 1.0)
+    B = 4099
+    s, a, x0, t = bcf_inputs(991, B, 17, 6)
+    m = build_vnet(spec, flat)
+    l1 = m.bcf_loss(dev(s), dev(a), x0=dev(x0), t=dev(t), bc_coef=0.7).cpu().numpy()
+    g1 = m.flat_grad().clone()
+    l2 = m.bcf_loss(dev(s), dev(a), x0=dev(x0), t=dev(t), bc_coef=0.7).cpu().numpy()
+    assert np.array_equal(l1, l2) and torch.equal(g1, m.flat_grad())
+    total, flow, act, grad = bcf.bcf_loss_and_grad(spec, flat, s, a, x0, t, 0.7)
+    assert np.allclose(l1, [total, flow, act], rtol=1e-5)
+    assert _rel_l2(g1.cpu().numpy(), grad) <= 1e-4
+    x = m.sample_actions(dev(s), 32, x0=dev(x0)).cpu().numpy()
+    ref = bcf.sample_actions(spec, flat, s, x0, 32)
+    assert np.abs(x - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+    # data-parallel halves: mean_divisor = global rows, gradients add up to the full-batch gradient
+    h = B // 2
+    m.bcf_loss(dev(s[:h]), dev(a[:h]), x0=dev(x0[:h]), t=dev(t[:h]), bc_coef=0.7, mean_divisor=B)
+    m.bcf_loss(dev(s[h:]), dev(a[h:]), x0=dev(x0[h:]), t=dev(t[h:]), bc_coef=0.7, mean_divisor=B, accumulate=True)
+    assert _rel_l2(m.flat_grad().cpu().numpy(), grad) <= 1e-4
+
+
+def test_bad_arguments_raise():
+    from modril_b200.bcf import VectorNetwork
+
+    with pytest.raises(ValueError):
+        VectorNetwork(4, 2, hidden_dim=100).to("cuda:0").native()         # hidden not a multiple of 16
+    m = VectorNetwork(4, 2, 64, 32).to("cuda:0")
+    with pytest.raises(ValueError):
+        m(torch.zeros(3, 3, device="cuda"), torch.zeros(3, 4, device="cuda"), torch.zeros(3, device="cuda"))
+    with pytest.raises(ValueError):
+        m.sample_actions(torch.zeros(3, 4, device="cuda"), 0)
+    assert m.sample_actions(torch.zeros(0, 4, device="cuda"), 8).shape == (0, 2)
