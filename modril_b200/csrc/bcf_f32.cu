@@ -9,7 +9,7 @@
 // The three embeddings are written straight into the column slices of one [R][3H] buffer (ldc = 3H), which is also the
 // ReLU mask of the backward pass.  The loss runs the net on 2B stacked rows (rows 0..B-1: (x_t, t), rows B..2B-1:
 // (a, 1)), so forward and backward are one pass each.  Batch reductions are split and reduced in a fixed order
-// (deterministic).  The sampler hoists the state embedding (constant over the Euler steps) out of the loop.
+// (deterministic).  The sampler is ONE kernel over all Euler steps (see vnet_sample_kernel).
 #include <algorithm>
 #include <cmath>
 #include <new>
@@ -207,17 +207,134 @@ __global__ void time_grad_reduce_kernel(const float* __restrict__ partial, int c
     gw[col] = accumulate ? gw[col] + aw : aw;
     gb[col] = accumulate ? gb[col] + ab : ab;
 }
-__global__ void euler_update_kernel(float* __restrict__ x, const float* __restrict__ V, int ldv, long long B, int A, float dt) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= B * A) return;
-    const long long r = i / A;
-    const int j = (int)(i % A);
-    x[i] = fmaf(V[r * ldv + j], dt, x[i]);
-}
 __global__ void copy_out_kernel(const float* __restrict__ V, int ldv, float* __restrict__ out, long long B, int A) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= B * A) return;
     out[i] = V[(i / A) * ldv + i % A];
+}
+
+
+// ---- Euler action sampler (flow_policy.py:49-63), fused over all steps ---------------------------------------------
+// The head's first layer is linear in the concatenated features, so per row and step only the action-embedding block
+// of W1 is recurrent:  h1 = relu(W1[:,0:H] s_feat  +  (W1[:,H:2H] t_feat_i + b1)  +  W1[:,2H:3H] x_feat).
+// The first term is constant over the steps (computed once per row), the second is the same for every row (one small
+// launch for all steps: step_bias_kernel), the third is a [H x H] mat-vec per row and step whose weights are streamed
+// from L2.  One CTA integrates R rows through all steps; thread (g, j) owns column j over the k-slice g of KS.
+__global__ void __launch_bounds__(1024) step_bias_kernel(const float* __restrict__ wt1, const float* __restrict__ bt1,
+                                                         const float* __restrict__ Wt2t, const float* __restrict__ bt2,
+                                                         const float* __restrict__ W1t, const float* __restrict__ b1,
+                                                         float* __restrict__ tb, int T, int H, double dt) {
+    extern __shared__ float sm_tb[];
+    float* T1 = sm_tb;
+    float* T2 = sm_tb + T;
+    const int i = blockIdx.x;
+    const float t = (float)(i * dt);   // python double i*dt -> fp32 tensor (flow_policy.py:58)
+    for (int k = threadIdx.x; k < T; k += blockDim.x) T1[k] = fmaxf(fmaf(t, wt1[k], bt1[k]), 0.f);
+    __syncthreads();
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float acc = bt2[j];
+        for (int k = 0; k < T; ++k) acc = fmaf(Wt2t[(size_t)k * H + j], T1[k], acc);
+        T2[j] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float acc = b1[j];
+        for (int k = 0; k < H; ++k) acc = fmaf(W1t[(size_t)(H + k) * H + j], T2[k], acc);
+        tb[(size_t)i * H + j] = acc;
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void slice_matvec(const float* __restrict__ W, const float* __restrict__ feat, float* __restrict__ part,
+                                             int H, int KS) {
+    const int g = threadIdx.x / H, j = threadIdx.x % H;
+    const int klen = H / KS, k0 = g * klen;
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 4
+    for (int k = k0; k < k0 + klen; k += 4) {
+        const float w0 = __ldg(W + (size_t)k * H + j), w1 = __ldg(W + (size_t)(k + 1) * H + j);
+        const float w2 = __ldg(W + (size_t)(k + 2) * H + j), w3 = __ldg(W + (size_t)(k + 3) * H + j);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float4 f = *reinterpret_cast<const float4*>(feat + r * H + k);
+            acc[r] = fmaf(w0, f.x, acc[r]);
+            acc[r] = fmaf(w1, f.y, acc[r]);
+            acc[r] = fmaf(w2, f.z, acc[r]);
+            acc[r] = fmaf(w3, f.w, acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) part[(g * R + r) * H + j] = acc[r];
+}
+
+template <int R>
+__global__ void __launch_bounds__(1024) vnet_sample_kernel(const float* __restrict__ s, const float* __restrict__ x0,
+                                                           float* __restrict__ action, const float* __restrict__ tb,
+                                                           const float* __restrict__ Wst, const float* __restrict__ bs,
+                                                           const float* __restrict__ Wat, const float* __restrict__ ba,
+                                                           const float* __restrict__ W1t, const float* __restrict__ W2,
+                                                           const float* __restrict__ b2, long long B, int S, int A, int H,
+                                                           int KS, int n_steps, float dt) {
+    extern __shared__ __align__(16) float sm_s[];
+    float* feat = sm_s;                    // [R][H]  s_feat, then x_feat / h1 per step
+    float* cs = feat + R * H;              // [R][H]  W1[:,0:H] s_feat
+    float* part = cs + R * H;              // [KS][R][H]
+    float* xs = part + KS * R * H;         // [R][A]
+    float* ss = xs + R * A;                // [R][S]
+    const long long row0 = (long long)blockIdx.x * R;
+    const int nt = blockDim.x, tid = threadIdx.x;
+    for (int i = tid; i < R * S; i += nt) { const long long r = row0 + i / S; ss[i] = r < B ? s[r * S + i % S] : 0.f; }
+    for (int i = tid; i < R * A; i += nt) { const long long r = row0 + i / A; xs[i] = r < B ? x0[r * A + i % A] : 0.f; }
+    __syncthreads();
+    for (int i = tid; i < R * H; i += nt) {
+        const int r = i / H, j = i % H;
+        float acc = bs[j];
+        for (int k = 0; k < S; ++k) acc = fmaf(__ldg(Wst + (size_t)k * H + j), ss[r * S + k], acc);
+        feat[i] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    slice_matvec<R>(W1t, feat, part, H, KS);
+    __syncthreads();
+    for (int i = tid; i < R * H; i += nt) {
+        float acc = part[i];
+        for (int g = 1; g < KS; ++g) acc += part[g * R * H + i];
+        cs[i] = acc;
+    }
+    const int n_warps = nt >> 5, warp = tid >> 5, lane = tid & 31;
+    const float* W1x = W1t + (size_t)2 * H * H;
+    for (int step = 0; step < n_steps; ++step) {
+        __syncthreads();   // xs of the previous step / cs complete; feat free
+        for (int i = tid; i < R * H; i += nt) {
+            const int r = i / H, j = i % H;
+            float acc = ba[j];
+            for (int k = 0; k < A; ++k) acc = fmaf(__ldg(Wat + (size_t)k * H + j), xs[r * A + k], acc);
+            feat[i] = fmaxf(acc, 0.f);
+        }
+        __syncthreads();
+        slice_matvec<R>(W1x, feat, part, H, KS);
+        __syncthreads();
+        const float* tbi = tb + (size_t)step * H;
+        for (int i = tid; i < R * H; i += nt) {
+            float acc = part[i];
+            for (int g = 1; g < KS; ++g) acc += part[g * R * H + i];
+            feat[i] = fmaxf(acc + (cs[i] + __ldg(tbi + i % H)), 0.f);
+        }
+        __syncthreads();
+        if (warp < n_warps) {   // full warps only: (row, action component) dot products with a shuffle reduction
+            for (int p = warp; p < R * A; p += n_warps) {
+                const int r = p / A, a = p % A;
+                float acc = 0.f;
+                for (int j = lane; j < H; j += 32) acc = fmaf(__ldg(W2 + (size_t)a * H + j), feat[r * H + j], acc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) xs[p] = fmaf(acc + b2[a], dt, xs[p]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < R * A; i += nt) { const long long r = row0 + i / A; if (r < B) action[r * A + i % A] = xs[i]; }
 }
 
 struct VBuf {
@@ -309,8 +426,8 @@ extern "C" int frl_vnet_set_params(frl_vnet* n, const float* params_dev, void* /
 
 extern "C" int frl_vnet_forward(frl_vnet* n, const float* x, const float* s, const float* t, float* v, long long B, void* stream) {
     FRL_REQUIRE(n && n->version > 0, "frl_vnet_set_params has not been called");
-    FRL_REQUIRE(x && s && t && v, "null pointer");
     if (B <= 0) return FRL_OK;
+    FRL_REQUIRE(x && s && t && v, "null pointer");
     FRL_REQUIRE(B < (1ll << 31) / (3 * n->cfg.hidden), "batch too large");
     FRL_CUDA(cudaSetDevice(n->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -335,34 +452,40 @@ extern "C" int frl_vnet_forward(frl_vnet* n, const float* x, const float* s, con
 
 extern "C" int frl_vnet_sample(frl_vnet* n, const float* s, const float* x0, int n_steps, float* action, long long B, void* stream) {
     FRL_REQUIRE(n && n->version > 0, "frl_vnet_set_params has not been called");
+    if (B <= 0) return FRL_OK;
     FRL_REQUIRE(s && x0 && action, "null pointer");
     FRL_REQUIRE(n_steps >= 1 && n_steps <= 4096, "n_steps must be in 1..4096");
-    if (B <= 0) return FRL_OK;
-    FRL_REQUIRE(B < (1ll << 31) / (3 * n->cfg.hidden), "batch too large");
     FRL_CUDA(cudaSetDevice(n->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc = vnet_ensure_pack(n, st);
     if (rc != FRL_OK) return rc;
-    size_t used = 0;
-    carve(n, nullptr, (size_t)B, &used);
-    rc = vnet_ws(n, used);
+    const int S = n->cfg.s_dim, A = n->cfg.a_dim, T = n->cfg.time_dim, H = n->cfg.hidden;
+    rc = vnet_ws(n, (size_t)n_steps * H);
     if (rc != FRL_OK) return rc;
-    VBuf b = carve(n, n->ws, (size_t)B, &used);
-    const int S = n->cfg.s_dim, A = n->cfg.a_dim, T = n->cfg.time_dim;
-    const long long W = n->Sp + n->Ap + T;
-    FRL_CUDA(cudaMemcpyAsync(action, x0, (size_t)B * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    float* tb = n->ws;
+    const float* pk = n->pack;
     const double dt = 1.0 / n_steps;   // python double, flow_policy.py:55
-    for (int i = 0; i < n_steps; ++i) {
-        // t = i * dt as a python double, cast to the fp32 tensor (flow_policy.py:58); the state embedding is hoisted
-        vnet_prepare_kernel<<<(unsigned)((B * W + 255) / 256), 256, 0, st>>>(s, action, nullptr, nullptr, (float)(i * dt),
-                                                                           n->pack + n->o_wt1, n->pack + n->o_bt1, b.Sp_in, b.Xp_in,
-                                                                           b.T1, nullptr, B, B, S, A, n->Sp, n->Ap, T, 0, i == 0);
-        FRL_CUDA(cudaGetLastError());
-        rc = vnet_trunk(n, b, (int)B, i == 0, st);
-        if (rc != FRL_OK) return rc;
-        euler_update_kernel<<<(unsigned)((B * A + 255) / 256), 256, 0, st>>>(action, b.V, n->Aop, B, A, (float)dt);
-        FRL_CUDA(cudaGetLastError());
+    step_bias_kernel<<<n_steps, std::min(1024, round_up(std::max(T, H), 32)), (size_t)(T + H) * sizeof(float), st>>>(
+        pk + n->o_wt1, pk + n->o_bt1, pk + n->o_Wt2t, pk + n->o_bt2, pk + n->o_W1t, pk + n->o_b1, tb, T, H, dt);
+    FRL_CUDA(cudaGetLastError());
+    int KS = 4;
+    while (KS > 1 && H * KS > 1024) KS >>= 1;
+    auto smem_for = [&](int R) { return (size_t)(R * H * (2 + KS) + R * (A + S)) * sizeof(float); };
+    // 16 rows per CTA once that still fills the SMs (weights are streamed from L2 once per CTA and step)
+    const bool wide = B >= 16ll * 296 && smem_for(16) <= 200 * 1024;
+    const int R = wide ? 16 : 4;
+    const size_t smem = smem_for(R);
+    FRL_REQUIRE(smem <= 227 * 1024, "state too wide for the fused sampler");
+    const unsigned grid = (unsigned)((B + R - 1) / R);
+    auto kern = wide ? vnet_sample_kernel<16> : vnet_sample_kernel<4>;
+    static bool attr_done[2][64] = {};
+    if (!attr_done[wide][n->cfg.device & 63]) {
+        FRL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done[wide][n->cfg.device & 63] = true;
     }
+    kern<<<grid, H * KS, smem, st>>>(s, x0, action, tb, pk + n->o_Wst, pk + n->o_bs, pk + n->o_Wat, pk + n->o_ba, pk + n->o_W1t,
+                                     pk + n->o_W2, pk + n->o_b2, B, S, A, H, KS, n_steps, (float)dt);
+    FRL_CUDA(cudaGetLastError());
     return FRL_OK;
 }
 

@@ -108,6 +108,11 @@ static int run_gemm(const float* A, int lda, const float* B, int ldb, float* C, 
         dim3 grid((N + 127) / 128, (M + 15) / 16, splits);
         sgemm_kernel<16, 128, 1, 8, A_TRANS, EPI><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, mask,
                                                                          ldmask, k_split_len, mask_rows);
+    } else if ((long long)((M + 63) / 64) * ((N + 127) / 128) * splits < 74) {
+        // small problems (the reference's 128-row updates): more, smaller CTAs; the k order per output is unchanged
+        dim3 grid((N + 31) / 32, (M + 31) / 32, splits);
+        sgemm_kernel<32, 32, 2, 2, A_TRANS, EPI><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, mask,
+                                                                        ldmask, k_split_len, mask_rows);
     } else if (N <= 64) {
         dim3 grid((N + 63) / 64, (M + 127) / 128, splits);
         sgemm_kernel<128, 64, 8, 4, A_TRANS, EPI><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, mask,
