@@ -360,6 +360,34 @@ def run_ours(args):
         train_rates[prec_t] = world * 2 * Bt / (float(tms.item()) / 1e3)
     train_rate = train_rates["fp16"]
 
+    # ---- BCF flow-matching policy (scope row f3), informational: acting latency and one behaviour-cloning update ----
+    bcf_info = None
+    if world == 1:
+        from modril_b200.bcf import FlowPolicy, VectorNetwork, bc_step
+
+        vnet = VectorNetwork(s_dim, a_dim).to(device)
+        pol, bopt = FlowPolicy(vnet), FusedAdam([vnet], lr=1e-3, eps=1e-12)
+
+        def timed(fn, n):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(device)
+            return e0.elapsed_time(e1) / n
+
+        bcf_info = {"net": f"VectorNetwork s {s_dim} a {a_dim} H 256 T 128, FP32"}
+        for Bb, n_it in ((32, 50), (128, 50), (65536, 5)):
+            if Bb > B:
+                continue
+            bs_, ba_ = st[:Bb], at[:Bb]
+            bx0, bt_ = torch.randn(Bb, a_dim, device=device), torch.rand(Bb, device=device)
+            bcf_info[f"sample32_ms_B{Bb}"] = timed(lambda: pol.get_action(bs_, x0=bx0), n_it)
+            bcf_info[f"bc_update_ms_B{Bb}"] = timed(lambda: bc_step(pol, bopt, bs_, ba_, x0=bx0, t=bt_), n_it)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -427,6 +455,7 @@ def run_ours(args):
                   "algorithmic_tflops": train_rate * 3 * f_fwd_train / 1e12,
                   "frac_of_peak": train_rate * 3 * f_fwd_train / 1e12 / measured_peak_tflops()[0] / world,
                   "collective": "NCCL all-reduce of the flat grad" if world > 1 else "none"},
+        "bcf": bcf_info,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
