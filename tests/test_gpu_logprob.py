@@ -209,6 +209,30 @@ def test_score_host_matches_device():
     assert np.array_equal(outs[2], rw.cpu().numpy())
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("per_step", [False, True])
+def test_score_host_pinned_and_pageable_buffers(precision, per_step):
+    """Host entry point with pinned and with pageable buffers: bit-identical to the device-resident path, for shared
+    and per-step probes and ragged sizes."""
+    from modril_b200.flowril import score_pair_host
+    spec = cf.NetSpec(11, 3, 256, 4, 2)
+    m = build_model(spec, cf.make_params(spec, 22, 1.0))
+    B, n = 5003, 8
+    s, a = synth.states_actions(43, B, 11, 3)
+    probe = synth.rademacher(44, (n, B, 3) if per_step else (B, 3))
+    ref = m.score(dev(s), dev(a), n_steps=n, probe=dev(probe), precision=precision)
+    hs, ha, hp = (torch.from_numpy(x).pin_memory() for x in (s, a, probe))
+    outs = tuple(torch.empty(B).pin_memory() for _ in range(3))
+    score_pair_host(m.net, m.net, hs, ha, hp, n_steps=n, precision=precision, out=outs)
+    for got, want in zip(outs, ref):
+        assert torch.equal(got, want.cpu())
+    outs2 = tuple(torch.empty(B) for _ in range(3))
+    score_pair_host(m.net, m.net, torch.from_numpy(s), torch.from_numpy(a), torch.from_numpy(probe), n_steps=n,
+                    precision=precision, out=outs2)
+    for got, want in zip(outs2, ref):
+        assert torch.equal(got, want.cpu())
+
+
 def test_full_size_properties():
     """BASELINE config 'maze, batch 64k, 20-step': properties that need no oracle at this size --
     (i) determinism, (ii) permutation equivariance over rows, (iii) agreement of a 4096-row slice with the oracle,
