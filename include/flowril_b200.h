@@ -232,6 +232,23 @@ int frl_bcf_loss_grad(frl_vnet* net, const float* s_dev, const float* actions_de
                       const float* t_dev, long long B, long long mean_divisor, float bc_coef, float grad_scale,
                       int accumulate, float* losses_dev, float* grad_dev, void* stream);
 
+/* ---- PPO consumer of the rewards: returns / GAE and advantage normalisation (scope row f4, first part) -------------
+ * RolloutStorage.compute_returns (deps/rl-toolkit/rlf/storage/rollout_storage.py:178-233) as ONE launch.
+ * rewards [T,N] (value_dim copies of one reward, :179), value_preds [T+1,N,D], masks / bad_masks [T+1,N],
+ * next_value [N,D], returns [T+1,N,D].  bad_masks == NULL <=> not args.use_proper_time_limits.  use_gae: writes
+ * value_preds[T] = next_value (:185) and returns[0..T-1]; otherwise writes returns[T] = next_value (:201) and the
+ * discounted sums.  Float32 operation order of the torch loop (gamma * gae_lambda formed in double like the python
+ * floats): bit-identical results. */
+int frl_compute_returns(const float* rewards_dev, float* value_preds_dev, const float* masks_dev,
+                        const float* bad_masks_dev, const float* next_value_dev, int T, int N, int D, double gamma,
+                        double gae_lambda, int use_gae, float* returns_dev, int device, void* stream);
+
+/* RolloutStorage.compute_advantages (rollout_storage.py:235-239): adv = returns[:-1] - value_preds[:-1] over the first
+ * n = T*N*D elements, then (adv - adv.mean()) / (adv.std() + eps) (unbiased std; the reference's eps is 1e-5).
+ * scratch_dev: 256 doubles.  stats_out_dev (may be NULL) receives {mean, std}. */
+int frl_normalise_advantages(const float* returns_dev, const float* value_preds_dev, long long n, float eps,
+                             float* adv_dev, double* scratch_dev, float* stats_out_dev, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ EXPORTS = (
     "frl_net_set_params", "frl_vfield", "frl_logprob", "frl_score", "frl_score_host", "frl_cfm_loss_grad",
     "frl_clip_adam", "frl_reg_loss_grad", "frl_grad_axpy", "frl_tensor_norms", "frl_normalise_rewards", "frl_cfm_loss_grad_p", "frl_clip_adam_dev",
     "frl_vnet_create", "frl_vnet_destroy", "frl_vnet_num_params", "frl_vnet_set_params", "frl_vnet_forward",
-    "frl_vnet_sample", "frl_bcf_loss_grad",
+    "frl_vnet_sample", "frl_bcf_loss_grad", "frl_compute_returns", "frl_normalise_advantages",
 )
 
 
@@ -86,6 +86,8 @@ def lib():
     L.frl_vnet_forward.argtypes = [vp, vp, vp, vp, vp, ll, vp]
     L.frl_vnet_sample.argtypes = [vp, vp, vp, i32, vp, ll, vp]
     L.frl_bcf_loss_grad.argtypes = [vp, vp, vp, vp, vp, ll, ll, f32, f32, i32, vp, vp, vp]
+    L.frl_compute_returns.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f64, f64, i32, vp, i32, vp]
+    L.frl_normalise_advantages.argtypes = [vp, vp, ll, f32, vp, vp, vp, i32, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("frl_last_error", "frl_net_num_params", "frl_vnet_num_params"):

@@ -17,6 +17,7 @@ What is pinned (reference call sites in brackets):
                   :55-59] and their double-backward parameter gradients; trainreg_*.npz: the update loop with them.
   bcf_*.npz       VectorNetwork.forward, the BCF loss + gradients and the Euler action sampler [rlf/rl/model.py:391-432,
                   rlf/algos/il/bcf.py:108-128, rlf/policies/flow_policy.py:49-63]; bcftrain_*.npz: _bc_step updates.
+  gae_*.npz       RolloutStorage.compute_returns / compute_advantages [rlf/storage/rollout_storage.py:178-239]
   train_*.npz     the update loop of flowril.py:311-335 (zero_grad, backward, clip_grad_norm_, Adam.step) for
                   scrf (all params), scrf fine-tune (head_r only, flowril.py:52-63) and 2fs; loss curves + final
                   parameters.
@@ -523,6 +524,58 @@ def gen_bcf():
         print("wrote", name, curve[0], curve[-1])
 
 
+GAE_CASES = (  # (T, N, D, gamma, lambda, use_gae, proper_time_limits)
+    (128, 32, 1, 0.99, 0.95, True, False),      # the reference's PPO defaults (num_steps 128, 32 processes)
+    (128, 32, 1, 0.99, 0.95, True, True),
+    (64, 7, 1, 0.97, 0.9, False, False),
+    (64, 7, 2, 0.97, 0.9, False, True),
+    (5, 3, 3, 0.9, 1.0, True, True),
+)
+
+
+def gae_inputs(seed, T, N, D):
+    g = synth.rng(seed)
+    rewards = g.standard_normal((T, N, 1)).astype(np.float32)
+    value_preds = g.standard_normal((T + 1, N, D)).astype(np.float32)
+    masks = (g.random((T + 1, N, 1)) > 0.05).astype(np.float32)       # ~5% episode ends
+    bad_masks = (g.random((T + 1, N, 1)) > 0.03).astype(np.float32)   # ~3% time-limit truncations
+    next_value = g.standard_normal((N, D)).astype(np.float32)
+    return rewards, value_preds, masks, bad_masks, next_value
+
+
+def gen_gae():
+    """gae_*.npz: RolloutStorage.compute_returns / compute_advantages [rollout_storage.py:178-239] run as they are
+    (the two methods are compiled from the reference file and bound to a stand-in object carrying the tensors; the
+    storage class itself needs gym and the whole toolkit)."""
+    import ast
+    import types
+
+    import torch
+
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "deps", "rl-toolkit", "rlf", "storage", "rollout_storage.py")
+    tree = ast.parse(open(path).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "RolloutStorage"][0]
+    keep = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ("compute_returns", "compute_advantages")]
+    assert len(keep) == 2
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    for idx, (T, N, D, gamma, lam, use_gae, proper) in enumerate(GAE_CASES):
+        seed = 8000 + idx
+        rewards, value_preds, masks, bad_masks, next_value = gae_inputs(seed, T, N, D)
+        st = types.SimpleNamespace(
+            rewards=torch.from_numpy(rewards), value_preds=torch.from_numpy(value_preds.copy()),
+            masks=torch.from_numpy(masks), bad_masks=torch.from_numpy(bad_masks), value_dim=D,
+            returns=torch.zeros(T + 1, N, D),
+            args=types.SimpleNamespace(gamma=gamma, gae_lambda=lam, use_gae=use_gae, use_proper_time_limits=proper))
+        ns["compute_returns"](st, torch.from_numpy(next_value))
+        adv = ns["compute_advantages"](st)
+        name = f"gae_{idx:02d}_T{T}_N{N}_D{D}_{'gae' if use_gae else 'disc'}{'_ptl' if proper else ''}.npz"
+        np.savez_compressed(os.path.join(OUT, name), meta=np.array([T, N, D, int(use_gae), int(proper), seed]),
+                            gamma=np.float64(gamma), gae_lambda=np.float64(lam), returns=st.returns.numpy(),
+                            value_preds_after=st.value_preds.numpy(), advantages=adv.numpy())
+        print("wrote", name, float(st.returns.abs().mean()))
+
+
 def main():
     import torch
 
@@ -530,7 +583,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     P = ref_shim.load()
-    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "bcf"]
+    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "bcf", "gae"]
     if "logprob" in which:
         gen_logprob(P)
     if "vfield" in which:
@@ -547,6 +600,8 @@ def main():
         gen_gradnorm()
     if "bcf" in which:
         gen_bcf()
+    if "gae" in which:
+        gen_gae()
 
 
 if __name__ == "__main__":
