@@ -31,7 +31,7 @@ def compute_returns(rewards, value_preds, masks, bad_masks, next_value, returns,
     dev = returns.device
     T = rewards.shape[0]
     N, D = value_preds.shape[1], value_preds.shape[2]
-    if rewards.shape != (T, N, 1) or value_preds.shape != (T + 1, N, D) or returns.shape != (T + 1, N, D) \\
+    if rewards.shape != (T, N, 1) or value_preds.shape != (T + 1, N, D) or returns.shape != (T + 1, N, D) \
             or masks.shape != (T + 1, N, 1) or next_value.shape != (N, D):
         raise ValueError("shape mismatch: rewards [T,N,1], value_preds/returns [T+1,N,D], masks [T+1,N,1], next_value [N,D]")
     bm = None

@@ -165,3 +165,27 @@ def test_gradnorm2d_mirror_follows_the_reference_trajectory(golden_dir):
     assert np.allclose([float(gn.L0_anti), float(gn.L0_jpen)], g["L0"], rtol=1e-5)
     assert np.allclose([float(gn.ema_g_anti), float(gn.ema_g_jpen)], g["ema"], rtol=1e-4)
     assert set(gn.state_dict()) == {"log_beta", "log_gamma", "step_count", "L0_anti", "L0_jpen", "ema_g_anti", "ema_g_jpen"}
+
+
+def test_every_package_module_imports_and_bcf_ppo_mirrors_refuse_cpu():
+    """All product modules import on a CPU-only box (syntax / dependency check); the BCF and PPO mirrors have the
+    reference's names and refuse CPU tensors instead of falling back."""
+    import importlib
+    import pkgutil
+
+    import modril_b200
+
+    for m in pkgutil.walk_packages(modril_b200.__path__, "modril_b200."):
+        importlib.import_module(m.name)
+    from modril_b200.bcf import FlowPolicy, VectorNetwork
+    from modril_b200.ppo import compute_advantages
+
+    net = VectorNetwork(11, 3, 64, 32)
+    assert list(net.state_dict()) == ["time_embed.0.weight", "time_embed.0.bias", "time_embed.2.weight", "time_embed.2.bias",
+                                      "state_embed.0.weight", "state_embed.0.bias", "action_embed.0.weight",
+                                      "action_embed.0.bias", "velocity_head.0.weight", "velocity_head.0.bias",
+                                      "velocity_head.2.weight", "velocity_head.2.bias"]
+    with pytest.raises(RuntimeError):
+        FlowPolicy(net).get_action(torch.zeros(2, 11))
+    with pytest.raises(RuntimeError):
+        compute_advantages(torch.zeros(3, 2, 1), torch.zeros(3, 2, 1))
