@@ -30,9 +30,13 @@ namespace tc3 {
 
 using namespace tcc;
 
-constexpr int kThreads = 448;   // warp 0 producer, warps 1-4 MMA issuers (2 per slot), warp 5 TMEM owner / peer relay, 8 epilogue warps
+#ifndef FRL_TC3_EPI_WARPS
+#define FRL_TC3_EPI_WARPS 8
+#endif
 constexpr int kEpiWarp0 = 6;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = FRL_TC3_EPI_WARPS;   // 8 or 16: four lane quarters x (2 or 4) column slices
+constexpr int kColW = 256 / (kEpiWarps / 4);    // accumulator columns per epilogue warp (128 or 64)
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // warp 0 producer, warps 1-4 MMA issuers (2 per slot), warp 5 TMEM owner / peer relay, epilogue warps
 constexpr int kSlotBytesA = 20480;  // plan A ring slot = this CTA's half of one weight block: [16 bias rows +] K = 64 rows of 128
 constexpr int kSlotBytesB = 16384;  // plan B (wider layer-0 inputs leave less room): blocks of at most 64 rows
 constexpr int kBarRing = 8;         // blocks in flight are tracked by sequence number % kBarRing
@@ -72,9 +76,16 @@ struct Params {
     int debug;                   // FRL_TC_DEBUG (timing experiments): 8 skip epilogue stores, 16 skip the bias add
     uint32_t rank_stride;        // bytes between the weight images of CTA rank 0 and rank 1
     unsigned long long* trace;   // FRL_TC_TRACE: [4 roles][8192] clock stamps of CTA 0 (timing experiments only)
-    uint32_t off_a, off_x0, off_ones, off_bias, off_state, off_rec, off_ring;
+    uint32_t off_a, off_x0, off_ones, off_bias, off_state, off_rec, off_rrec, off_ring;
     uint32_t x0_bytes, state_floats;   // per slot
     Blk blk[kMaxBlocks];
+    // Ring order of one Euler step.  Private streams (default): every layer's blocks are streamed twice, once per tile
+    // slot -- [layer l for slot 0][layer l for slot 1][layer l+1 for slot 0] ... -- so the two slots run half a period
+    // apart and the epilogue of one overlaps the MMAs of the other.  Shared stream (FRL_TC3_SHARED=1): every block is
+    // loaded once and consumed by both slots, which keeps the slots in phase.
+    int ring_len, w_consumers;
+    uint8_t ring_blk[2 * kMaxBlocks];      // ring position -> block
+    uint8_t ring_pos[2][kMaxBlocks];       // [slot][block] -> ring position
     float t_mid[kMaxSteps];
 };
 
@@ -239,6 +250,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     float* sBias = reinterpret_cast<float*>(smem + p.off_bias);     // [roles][NOp] head biases (trunk biases ride in the MMA)
     float* sState = reinterpret_cast<float*>(smem + p.off_state);   // per slot: a [a_dim][64], probe [a_dim][64]
     uint4* sRec = reinterpret_cast<uint4*>(smem + p.off_rec);       // [2 slots][n_blocks][2]
+    uint2* sRingRec = reinterpret_cast<uint2*>(smem + p.off_rrec);  // [ring_len] {offset, bytes} of the producer's loads
     uint8_t* sRing = smem + p.off_ring;   // n_stages slots of 16 KB: this CTA's N/2 rows of one weight block each
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -250,7 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         for (int s = 0; s < p.n_stages; ++s) {
             // leader: own producer (arrive.expect_tx) + the peer's "my half has landed" relay; peer: own producer only
             mbar_init(w_full(s), cta_rank == 0 ? 2 : 1);
-            mbar_init(w_empty(s), 2);   // both issuers release a slot (multicast commit)
+            mbar_init(w_empty(s), p.w_consumers);   // released by the (multicast) commits of the slots that read it
         }
         for (int slot = 0; slot < 2; ++slot) {
             mbar_init(a_ready(slot, 0), kEpiWarps);   // 4 warps of this column half in each of the two CTAs
@@ -283,8 +295,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                                ((uint32_t)(k.nrows >> 3) << 17);
         sRec[2 * i] = make_uint4(a_lo, idesc, (uint32_t)k.nrows | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24),
                                  (uint32_t)slot * 256);
+        const uint32_t pos = p.ring_pos[slot][b];   // ring position inside a step, as (wraps, stage) of the ring
         sRec[2 * i + 1] = make_uint4((uint32_t)k.n_k16 | ((uint32_t)k.first << 8) | ((uint32_t)k.bias << 16),
-                                     ((smem_u32(sOnes) >> 4) & 0x3FFF) | ((kChunk >> 4) << 16), 0, 0);
+                                     ((smem_u32(sOnes) >> 4) & 0x3FFF) | ((kChunk >> 4) << 16),
+                                     (pos % (uint32_t)p.n_stages) | ((pos / (uint32_t)p.n_stages) << 8), 0);
+    }
+    for (int i = threadIdx.x; i < p.ring_len; i += kThreads) {
+        const Blk& k = p.blk[p.ring_blk[i]];
+        sRingRec[i] = make_uint2(k.goff, k.bytes);
     }
     fence_async_smem();
     tc_fence_before();
@@ -306,13 +324,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            Tracer tr; tr.init(cta_rank == 0 ? p.trace : nullptr, 3, 0);   // role 3: the leader's weight producer
             for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
                 const uint8_t* wbase = p.wpack[quad % p.n_roles] + (size_t)cta_rank * p.rank_stride;
                 for (int step = 0; step < p.n_steps; ++step) {
-                    for (int b = 0; b < p.n_blocks; ++b) {
+                    for (int i = 0; i < p.ring_len; ++i) {
+                        const uint2 k = sRingRec[i];
+                        tr.mark(0x100 + i);
                         mbar_wait(w_empty(stage), phase ^ 1);
-                        mbar_expect_tx(w_full(stage), p.blk[b].bytes);
-                        bulk_g2s(smem_u32(sRing + (size_t)stage * p.slot_bytes), wbase + p.blk[b].goff, p.blk[b].bytes, w_full(stage));
+                        tr.mark(0x200 + i);
+                        mbar_expect_tx(w_full(stage), k.y);
+                        bulk_g2s(smem_u32(sRing + (size_t)stage * p.slot_bytes), wbase + k.x, k.y, w_full(stage));
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -325,7 +347,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
             uint32_t phase = 0;
             for (long long quad = cluster_id; quad < n_quads; quad += n_clusters)
                 for (int step = 0; step < p.n_steps; ++step)
-                    for (int b = 0; b < p.n_blocks; ++b) {
+                    for (int i = 0; i < p.ring_len; ++i) {
                         mbar_wait(w_full(stage), phase);
                         mbar_arrive_remote(w_full(stage), 0);
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
@@ -341,9 +363,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         // of the ring is always consumed by the same issuer, so no thread ever skips a phase of a barrier it waits on.
         if (lane == 0) {
             const int slot = (warp - 1) >> 1, x = (warp - 1) & 1;
-            int stage = 0;
-            uint32_t phase = 0, par_a0 = 0, par_a1 = 0, par_h = 0;
+            uint32_t par_a0 = 0, par_a1 = 0, par_h = 0;
             long long seq = 0;
+            // ring position of the current step's first block, as (stage, wraps); a step advances it by ring_len
+            uint32_t base_stage = 0, base_wraps = 0;
+            const uint32_t len_stage = (uint32_t)p.ring_len % (uint32_t)p.n_stages, len_wraps = (uint32_t)p.ring_len / (uint32_t)p.n_stages;
             const uint4* rec = sRec + (size_t)slot * p.n_blocks * 2;
             const uint32_t ring_lo = smem_u32(sRing) >> 4;
             constexpr uint32_t kDescHi = (uint32_t)(128 >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
@@ -358,6 +382,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         if ((int)(seq & 1) == x) {
                             tr.mark(0x100 + b);
                             if (seq > 0) { mbar_wait(hand(slot, x), par_h); par_h ^= 1; }
+                            uint32_t stage = base_stage + (r1.z & 0xFF), wraps = base_wraps + (r1.z >> 8);
+                            if (stage >= (uint32_t)p.n_stages) { stage -= p.n_stages; ++wraps; }
+                            const uint32_t phase = wraps & 1;
                             mbar_wait(w_full(stage), phase);   // both halves of the block are in the two CTAs' rings
                             tr.mark(0x300 + b);
                             tc_fence_after();
@@ -381,8 +408,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                             if ((r0.z >> 16) & 0xFF) umma2_commit_both(d_full(slot));
                             tr.mark(0x400 + b);
                         }
-                        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
+                    base_stage += len_stage;
+                    base_wraps += len_wraps;
+                    if (base_stage >= (uint32_t)p.n_stages) { base_stage -= p.n_stages; ++base_wraps; }
                 }
             }
         }
@@ -390,7 +419,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         // ------------------------------------------------ epilogue ------------------------------------------------
         const int ew = warp - kEpiWarp0;
         const int q = warp & 3;                 // TMEM lane quarter: operand rows 32q .. 32q+31 = samples 16q .. 16q+15
-        const int ch = ew >> 2;                 // column half (128 columns)
+        const int ch = ew >> 2;                 // column slice (kColW columns)
+        const int ah = (ch * kColW) >> 7;       // the 128-column half (a_ready barrier) the slice belongs to
         const int et = ew * 32 + lane;
         const int tq = lane & 3, tr8 = lane >> 2;   // position inside the 16x256b fragment: column pair, row
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
@@ -398,7 +428,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         uint32_t par_d[2] = {0, 0};
         float log_det[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [slot][16-row group]
         Tracer tr;   // role 0: leader CTA's first epilogue warp, role 3: the peer CTA's
-        tr.init((lane == 0 && ew == 0) ? p.trace : nullptr, cta_rank == 0 ? 0 : 3, (int)cta_rank);
+        tr.init((lane == 0 && ew == 0 && cta_rank == 0) ? p.trace : nullptr, 0, 0);
 
         for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
             const int role = (int)(quad % p.n_roles);
@@ -439,7 +469,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
             fence_async_smem();
             named_sync(1, kEpiWarps * 32);
             if (lane == 0)
-                for (int slot = 0; slot < n_slots; ++slot) arrive_leader(a_ready(slot, ch));
+                for (int slot = 0; slot < n_slots; ++slot) arrive_leader(a_ready(slot, ah));
 
             for (int step = 0; step < p.n_steps; ++step) {
                 // ---- trunk layers: accumulator -> next layer's operand ----
@@ -453,19 +483,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         // Both 16-row groups of this warp's lane quarter, 128 columns each, in two software-pipelined
                         // rounds: the TMEM loads of group 1 are in flight while group 0 is converted and stored (a
                         // tcgen05.wait::ld covers every outstanding load, so the rounds are the pipelining granularity).
-                        uint32_t z[2][2][32];
+                        constexpr int kHalves = kColW / 64;
+                        uint32_t z[2][kHalves][32];
                         auto load_grp = [&](int grp) {
-                            const uint32_t tb = lane_addr + ((uint32_t)(grp * 16) << 16) + (uint32_t)slot * 256 + (uint32_t)ch * 128;
-                            tmem_ld_16x256b_x8(tb, z[grp][0]);
-                            tmem_ld_16x256b_x8(tb + 64, z[grp][1]);
+                            const uint32_t tb = lane_addr + ((uint32_t)(grp * 16) << 16) + (uint32_t)slot * 256 + (uint32_t)ch * kColW;
+#pragma unroll
+                            for (int half = 0; half < kHalves; ++half) tmem_ld_16x256b_x8(tb + 64 * half, z[grp][half]);
                         };
                         auto store_grp = [&](int grp) {
                             // lane i addresses row i%8 of matrix i/8: matrices 0/1 = primal/tangent rows of chunk k,
                             // matrices 2/3 = the same of chunk k+1
                             const uint32_t rowa = (uint32_t)(q * 32 + grp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8);
-                            uint32_t addr = smem_u32(sA) + slot * a_tile_bytes + (uint32_t)(ch * 16 + (lane >> 4)) * kChunk + rowa * 16;
+                            uint32_t addr = smem_u32(sA) + slot * a_tile_bytes + (uint32_t)(ch * (kColW / 8) + (lane >> 4)) * kChunk + rowa * 16;
 #pragma unroll
-                            for (int half = 0; half < 2; ++half) {
+                            for (int half = 0; half < kHalves; ++half) {
 #pragma unroll
                                 for (int k = 0; k < 8; k += 2) {
                                     uint32_t w[4];
@@ -485,21 +516,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                             }
                         };
                         load_grp(0);
-                        tmem_ld_wait_dep(z[0][0]);
-                        tmem_ld_wait_dep(z[0][1]);
+#pragma unroll
+                        for (int half = 0; half < kHalves; ++half) tmem_ld_wait_dep(z[0][half]);
                         tr.mark(0x500 + l * 2 + slot);
                         load_grp(1);
                         store_grp(0);
                         tr.mark(0x600 + l * 2 + slot);
-                        tmem_ld_wait_dep(z[1][0]);
-                        tmem_ld_wait_dep(z[1][1]);
+#pragma unroll
+                        for (int half = 0; half < kHalves; ++half) tmem_ld_wait_dep(z[1][half]);
                         tr.mark(0x700 + l * 2 + slot);
                         store_grp(1);
                         tr.mark(0x800 + l * 2 + slot);
                         tc_fence_before();
                         fence_async_smem();
                         __syncwarp();
-                        if (lane == 0) arrive_leader(a_ready(slot, ch));
+                        if (lane == 0) arrive_leader(a_ready(slot, ah));
                         tr.mark(0x300 + l * 2 + slot);
                     }
                 }
@@ -515,8 +546,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         uint8_t* x0 = sX0 + slot * p.x0_bytes;
                         float* sA_state = sState + slot * p.state_floats;
                         float* sP_state = sA_state + p.a_dim * kSamp;
-                        {
-                            const int grp = ch;
+                        if (ch % (kEpiWarps / 8) == 0) {   // one warp per 16-row group works on the heads
+                            const int grp = ch / (kEpiWarps / 8);
                             const int srow = q * 16 + grp * 8 + tr8;             // sample inside the tile
                             const int rowp = q * 32 + grp * 16 + tr8;
                             const long long g = (tile0 + slot) * kSamp + srow;
@@ -591,7 +622,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         tc_fence_before();
                         fence_async_smem();
                         __syncwarp();
-                        if (lane == 0) arrive_leader(a_ready(slot, ch));
+                        if (lane == 0) arrive_leader(a_ready(slot, ah));
                     }
                     tr.mark(0x3F0 + slot);
                 }
@@ -636,7 +667,7 @@ static uint32_t front_bytes(const frl_net* net, int n_roles) {
     off = (off + 15) / 16 * 16;
     off += 2u * (2u * net->cfg.a_dim * kSamp) * 4;
     off = (off + 15) / 16 * 16;
-    off += 4u * (uint32_t)(5 * net->cfg.depth + 3) * 16;   // issue records (upper bound on the block count)
+    off += 5u * (uint32_t)(5 * net->cfg.depth + 3) * 16;   // issue + ring records (upper bound on the block count)
     return (off + 1023) / 1024 * 1024;
 }
 static int choose_plan(const frl_net* net) {
@@ -762,6 +793,26 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
     p.probe_step_stride = a.probe_mode == FRL_PROBE_PER_STEP ? a.B * (long long)p.a_dim : 0;
     p.n_blocks = (int)sc.blk.size();
     for (int i = 0; i < p.n_blocks; ++i) p.blk[i] = sc.blk[i];
+    const char* shared_env = getenv("FRL_TC3_SHARED");   // experiments / A-B tests only
+    const bool shared_stream = shared_env && shared_env[0] == '1';
+    if (shared_stream) {
+        p.ring_len = p.n_blocks;
+        p.w_consumers = 2;
+        for (int i = 0; i < p.n_blocks; ++i) p.ring_blk[i] = p.ring_pos[0][i] = p.ring_pos[1][i] = (uint8_t)i;
+    } else {
+        p.ring_len = 0;
+        p.w_consumers = 1;
+        for (int b0 = 0; b0 < p.n_blocks;) {
+            int b1 = b0;
+            while (!p.blk[b1].commit) ++b1;   // a layer ends with the block that commits the accumulator
+            for (int slot = 0; slot < 2; ++slot)
+                for (int b = b0; b <= b1; ++b) {
+                    p.ring_pos[slot][b] = (uint8_t)p.ring_len;
+                    p.ring_blk[p.ring_len++] = (uint8_t)b;
+                }
+            b0 = b1 + 1;
+        }
+    }
 
     uint32_t off = 1024;   // barriers + TMEM slot
     p.off_a = off; off += 2u * H * kRows * 2;
@@ -774,6 +825,7 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
     p.off_state = off; off += 2u * p.state_floats * 4;
     off = (off + 15) / 16 * 16;
     p.off_rec = off; off += 4u * (uint32_t)p.n_blocks * 16;
+    p.off_rrec = off; off += (uint32_t)p.ring_len * 8;
     off = (off + 1023) / 1024 * 1024;
     p.off_ring = off;
     int max_smem = 0, sms = 0;

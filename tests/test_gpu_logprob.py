@@ -335,3 +335,20 @@ def test_cta_pair_integrator_is_bit_identical_to_single_cta_kernel(task, B, n_st
                     assert torch.equal(g, r)
                 else:
                     assert float(((g - r).abs() / r.abs().clamp_min(1.0)).max()) <= 2e-6
+
+
+@pytest.mark.parametrize("task,B,n_steps", [("maze", 40000, 20), ("halfcheetah", 5000, 8)])
+def test_private_and_shared_weight_streams_agree_bit_for_bit(task, B, n_steps, monkeypatch):
+    """The CTA-pair kernel streams every layer's weight blocks once per tile slot (default) or once for both slots
+    (FRL_TC3_SHARED=1); the two schedules reorder only the issue of independent MMAs, never the accumulation order."""
+    sd, ad = synth.TASK_DIMS[task]
+    spec = cf.NetSpec(sd, ad, 256, 4, 2)
+    m = build_model(spec, cf.make_params(spec, 23, 1.0))
+    s, a = synth.states_actions(36, B, sd, ad)
+    probe = synth.rademacher(37, (B, ad))
+    got = m.score(dev(s), dev(a), n_steps=n_steps, probe=dev(probe), precision="fp16")
+    monkeypatch.setenv("FRL_TC3_SHARED", "1")
+    ref = m.score(dev(s), dev(a), n_steps=n_steps, probe=dev(probe), precision="fp16")
+    monkeypatch.delenv("FRL_TC3_SHARED")
+    for g, r in zip(got, ref):
+        assert torch.equal(g, r)
