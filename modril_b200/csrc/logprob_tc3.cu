@@ -39,8 +39,7 @@ constexpr int kColW = 256 / (kEpiWarps / 4);    // accumulator columns per epilo
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // warp 0 producer, warps 1-4 MMA issuers (2 per slot), warp 5 TMEM owner / peer relay, epilogue warps
 constexpr int kSlotBytesA = 20480;  // plan A ring slot = this CTA's half of one weight block: [16 bias rows +] K = 64 rows of 128
 constexpr int kSlotBytesB = 16384;  // plan B (wider layer-0 inputs leave less room): blocks of at most 64 rows
-constexpr int kBarRing = 8;         // blocks in flight are tracked by sequence number % kBarRing
-constexpr int kMaxSlots = 8;
+constexpr int kMaxSlots = 16;
 constexpr int kRows = 128;      // rows of the UMMA operand
 constexpr int kSamp = 64;       // samples per tile
 constexpr int H = 256;
