@@ -413,7 +413,7 @@ def run_ours(args):
     roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": B * ((s_dim + 2 * a_dim) * 4 + 12), "peak_source": peak_src,
-            "kernel": "logprob_tc_kernel" if prec != "fp32" else "logprob_f32_kernel",
+            "kernel": "tc3::logprob_tc3_kernel (CTA pairs, tcgen05 cta_group::2)" if prec != "fp32" else "logprob_f32_kernel",
             "algorithmic_flops_per_sample": algorithmic_flops_per_sample(s_dim, a_dim, n_steps)}
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----

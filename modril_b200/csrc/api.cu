@@ -1,5 +1,7 @@
 // C-ABI entry points (see include/flowril_b200.h for the contract and the reference interfaces replaced).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <vector>
 
 #include "frl_internal.h"
@@ -141,7 +143,10 @@ extern "C" int frl_score_host(frl_net* ne, frl_net* na, const float* s_h, const 
     FRL_REQUIRE(n_steps >= 1 && n_steps <= kMaxSteps, "n_steps must be in 1..256");
     if (B <= 0) return FRL_OK;
     FRL_CUDA(cudaSetDevice(ne->cfg.device));
+    static const bool timing = getenv("FRL_HOST_TIMING") != nullptr;   // prints a host-clock breakdown of the call
+    const auto t_entry = std::chrono::steady_clock::now();
     FRL_CUDA(cudaDeviceSynchronize());  // weight packs may still be in flight on the caller's streams
+    const auto t_synced = std::chrono::steady_clock::now();
     const int S = ne->cfg.s_dim, A = ne->cfg.a_dim;
     const long long chunk = std::min<long long>(B, 262144);
     const int probe_rows = probe_mode == FRL_PROBE_PER_STEP ? n_steps : (probe_mode == FRL_PROBE_SHARED ? 1 : 0);
@@ -191,7 +196,13 @@ extern "C" int frl_score_host(frl_net* ne, frl_net* na, const float* s_h, const 
         if (rw_h) FRL_CUDA(cudaMemcpyAsync(rw_h + r0, d_rw, n * sizeof(float), cudaMemcpyDeviceToHost, st));
         // a slot is reused two chunks later: its stream order already serialises copy-in after the previous D2H
     }
+    const auto t_enqueued = std::chrono::steady_clock::now();
     for (int i = 0; i < HostStage::kSlots; ++i) FRL_CUDA(cudaStreamSynchronize(hs->stream[i]));
+    if (timing) {
+        const auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "frl_score_host: device sync %.1f us, enqueue %.1f us, wait %.1f us\n", us(t_entry, t_synced),
+                us(t_synced, t_enqueued), us(t_enqueued, std::chrono::steady_clock::now()));
+    }
     return FRL_OK;
 }
 

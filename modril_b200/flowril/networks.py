@@ -55,7 +55,7 @@ class _FlatVNet(nn.Module):
 
     def __getstate__(self):
         st = self.__dict__.copy()
-        st.update(_handle=None, _packed_key=None, _flat=None, _flat_grad=None)  # native handle is per-object
+        st.update(_handle=None, _packed_key=None, _flat=None, _flat_grad=None, _plist=None)  # native handle is per-object
         return st
 
     def __setstate__(self, st):
@@ -64,9 +64,16 @@ class _FlatVNet(nn.Module):
 
     # ---- flat storage -------------------------------------------------------------------------------------
     def _ordered_params(self):
-        return list(self.parameters())  # registration order == state_dict order
+        # registration order == state_dict order.  The module tree is fixed after __init__, so the list is cached
+        # (walking nn.Module.parameters() costs ~30 us, paid several times per native() call otherwise).
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = list(self.parameters())
+            self.__dict__["_plist"] = plist
+        return plist
 
     def _flatten(self):
+        self.__dict__["_plist"] = None
         params = self._ordered_params()
         dev = params[0].device
         if any(p.dtype != torch.float32 for p in params):
