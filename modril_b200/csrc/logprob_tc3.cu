@@ -323,7 +323,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            Tracer tr; tr.init(cta_rank == 0 ? p.trace : nullptr, 3, 0);   // role 3: the leader's weight producer
+            Tracer tr; tr.init((cta_rank == 0 && p.debug == 0) ? p.trace : nullptr, 3, 0);   // role 3: the leader's weight producer
             for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
                 const uint8_t* wbase = p.wpack[quad % p.n_roles] + (size_t)cta_rank * p.rank_stride;
                 for (int step = 0; step < p.n_steps; ++step) {
@@ -370,14 +370,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
             const uint4* rec = sRec + (size_t)slot * p.n_blocks * 2;
             const uint32_t ring_lo = smem_u32(sRing) >> 4;
             constexpr uint32_t kDescHi = (uint32_t)(128 >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
-            Tracer tr; tr.init(x == 0 ? p.trace : nullptr, 1 + slot);
+            Tracer tr;   // roles 1 / 2: issuer x = 0 of slots 0 / 1  (FRL_TC_DEBUG=100: both issuers of slot 0)
+            if (p.debug == 100) tr.init(slot == 0 ? p.trace : nullptr, 1 + x);
+            else tr.init(x == 0 ? p.trace : nullptr, 1 + slot);
             for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
                 for (int step = 0; step < p.n_steps; ++step) {
                     for (int b = 0; b < p.n_blocks; ++b, ++seq) {
                         const uint4 r0 = rec[2 * b], r1 = rec[2 * b + 1];
                         // every issuer observes every readiness phase of the operand (a skipped phase would alias parities)
+                        if (r0.z >> 24) tr.mark(0x500 + b);
                         if (r0.z & (1u << 24)) { mbar_wait_cluster(a_ready(slot, 0), par_a0); par_a0 ^= 1; }
                         if (r0.z & (2u << 24)) { mbar_wait_cluster(a_ready(slot, 1), par_a1); par_a1 ^= 1; }
+                        if (r0.z >> 24) tr.mark(0x600 + b);
                         if ((int)(seq & 1) == x) {
                             tr.mark(0x100 + b);
                             if (seq > 0) { mbar_wait(hand(slot, x), par_h); par_h ^= 1; }
@@ -427,7 +431,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         uint32_t par_d[2] = {0, 0};
         float log_det[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [slot][16-row group]
         Tracer tr;   // role 0: leader CTA's first epilogue warp, role 3: the peer CTA's
-        tr.init((lane == 0 && ew == 0 && cta_rank == 0) ? p.trace : nullptr, 0, 0);
+        tr.init((lane == 0 && (ew == 0 || ew == p.debug) && cta_rank == 0) ? p.trace : nullptr, ew == 0 ? 0 : 3, 0);
 
         for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
             const int role = (int)(quad % p.n_roles);
@@ -833,7 +837,7 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
     p.slot_bytes = choose_plan(n0) == 0 ? kSlotBytesA : kSlotBytesB;
     int stages = ((int)max_smem - (int)off) / (int)p.slot_bytes;
     if (stages > kMaxSlots) stages = kMaxSlots;
-    stages &= ~1;   // even: a ring slot is then always consumed by the same one of a slot's two issuers
+    if (const char* cap = getenv("FRL_TC3_STAGES")) stages = std::min(stages, atoi(cap));   // experiments only
     if (stages < 4) return 1;   // not enough shared memory for the ring: the caller falls back to the 128-sample kernel
     p.n_stages = stages;
     const size_t smem_bytes = (size_t)off + (size_t)stages * p.slot_bytes;
