@@ -449,7 +449,7 @@ def run_ours(args):
         "other_modes_samples_per_sec": extra,
         "train": {"metric": "cfm_train_samples_per_sec", "value": train_rate, "unit": "samples/s",
                   "rows_per_step_per_gpu": 2 * Bt, "dtype": "fp16 operands / fp32 accumulate (tcgen05); fp32 clip + Adam",
-                  "step": "2 x frl_cfm_loss_grad_p (fwd + dgrad + wgrad) + [all-reduce] + frl_clip_adam + weight re-pack"
+                  "step": "frl_cfm_loss_grad_pair (both roles stacked: fwd + dgrad + wgrad) + [all-reduce] + frl_clip_adam + weight re-pack"
                           + ("; replayed as one CUDA graph" if use_graph else ""),
                   "fp32_ffma_samples_per_sec": train_rates["fp32"],
                   "algorithmic_tflops": train_rate * 3 * f_fwd_train / 1e12,

@@ -137,6 +137,24 @@ int frl_cfm_loss_grad_p(frl_net* net, float role_sign, const float* s_dev, const
                         const float* noise_dev, long long B, long long mean_divisor, float grad_scale,
                         int accumulate, float* loss_dev, float* grad_dev, int precision, void* stream);
 
+/* The two CFM terms of one reward-model update in ONE pass (flowril.py:244-253: loss = rate_E * fm_loss(expert batch)
+ * + rate_A * fm_loss(agent batch), same net for the coupled-residual model): the two batches are stacked row-wise, so
+ * every layer GEMM runs once over B_0 + B_1 rows (fewer, fuller waves than two passes).  terms[0..1] as in
+ * frl_cfm_loss_grad_p (grad_scale = the term's rate); each loss_dev receives its own scalar; grad_dev receives the sum.
+ * FRL_PREC_FP32 runs the two FFMA passes back to back (same results as two frl_cfm_loss_grad calls). */
+typedef struct {
+    float role_sign;
+    const float* s_dev;
+    const float* a0_dev;
+    const float* t_dev;
+    const float* noise_dev;
+    long long B, mean_divisor;
+    float grad_scale;
+    float* loss_dev;
+} frl_cfm_term;
+int frl_cfm_loss_grad_pair(frl_net* net, const frl_cfm_term* terms, int accumulate, float* grad_dev, int precision,
+                           void* stream);
+
 /* Anti-divergence and Jacobian-stability regularisers of the coupled-residual (n_heads == 2) model with their
  * parameter gradients (flowril.py:255-264: `_hutch_div(mix_a, r, k=1).square().mean()` and
  * `_jacobian_frobenius(mix_a, v_c + r).mean()`, pretrain.py:163-177, :55-59; the reference differentiates them by

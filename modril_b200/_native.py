@@ -24,13 +24,18 @@ EXPORTS = (
     "frl_net_set_params", "frl_vfield", "frl_logprob", "frl_score", "frl_score_host", "frl_cfm_loss_grad",
     "frl_clip_adam", "frl_reg_loss_grad", "frl_grad_axpy", "frl_tensor_norms", "frl_normalise_rewards", "frl_cfm_loss_grad_p", "frl_clip_adam_dev",
     "frl_vnet_create", "frl_vnet_destroy", "frl_vnet_num_params", "frl_vnet_set_params", "frl_vnet_forward",
-    "frl_vnet_sample", "frl_bcf_loss_grad", "frl_compute_returns", "frl_normalise_advantages",
+    "frl_vnet_sample", "frl_bcf_loss_grad", "frl_compute_returns", "frl_normalise_advantages", "frl_cfm_loss_grad_pair",
 )
 
 
 class NetConfig(C.Structure):
     _fields_ = [("s_dim", C.c_int), ("a_dim", C.c_int), ("hidden", C.c_int), ("depth", C.c_int),
                 ("n_heads", C.c_int), ("device", C.c_int)]
+
+
+class CfmTerm(C.Structure):
+    _fields_ = [("role_sign", C.c_float), ("s", C.c_void_p), ("a0", C.c_void_p), ("t", C.c_void_p), ("noise", C.c_void_p),
+                ("B", C.c_longlong), ("mean_divisor", C.c_longlong), ("grad_scale", C.c_float), ("loss", C.c_void_p)]
 
 
 class VNetConfig(C.Structure):
@@ -86,6 +91,7 @@ def lib():
     L.frl_vnet_forward.argtypes = [vp, vp, vp, vp, vp, ll, vp]
     L.frl_vnet_sample.argtypes = [vp, vp, vp, i32, vp, ll, vp]
     L.frl_bcf_loss_grad.argtypes = [vp, vp, vp, vp, vp, ll, ll, f32, f32, i32, vp, vp, vp]
+    L.frl_cfm_loss_grad_pair.argtypes = [vp, C.POINTER(CfmTerm), i32, vp, i32, vp]
     L.frl_compute_returns.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f64, f64, i32, vp, i32, vp]
     L.frl_normalise_advantages.argtypes = [vp, vp, ll, f32, vp, vp, vp, i32, vp]
     for name in EXPORTS:

@@ -1,6 +1,7 @@
 // C-ABI entry points (see include/flowril_b200.h for the contract and the reference interfaces replaced).
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <vector>
 
@@ -236,8 +237,55 @@ extern "C" int frl_cfm_loss_grad_p(frl_net* net, float role_sign, const float* s
         return FRL_ERR_UNSUPPORTED;
     }
     FRL_CUDA(cudaSetDevice(net->cfg.device));
-    return cfm_loss_grad_tc(net, role_sign >= 0.f ? 1.f : -1.f, s, a0, t, noise, B, mean_divisor, grad_scale,
-                            accumulate, loss, grad, (cudaStream_t)stream);
+    const CfmTerm term{role_sign >= 0.f ? 1.f : -1.f, s, a0, t, noise, B, mean_divisor, grad_scale, loss};
+    return cfm_loss_grad_tc(net, &term, 1, accumulate, grad, (cudaStream_t)stream);
+}
+
+extern "C" int frl_cfm_loss_grad_pair(frl_net* net, const frl_cfm_term* terms, int accumulate, float* grad, int precision,
+                                      void* stream) {
+    FRL_REQUIRE(terms != nullptr, "null terms");
+    if (precision == FRL_PREC_FP32) {   // FFMA path: one pass per term
+        for (int i = 0; i < 2; ++i) {
+            int rc = frl_cfm_loss_grad(net, terms[i].role_sign, terms[i].s_dev, terms[i].a0_dev, terms[i].t_dev, terms[i].noise_dev,
+                                       terms[i].B, terms[i].mean_divisor, terms[i].grad_scale, i == 0 ? accumulate : 1,
+                                       terms[i].loss_dev, grad, stream);
+            if (rc != FRL_OK) return rc;
+        }
+        return FRL_OK;
+    }
+    int rc = check_net(net);
+    if (rc != FRL_OK) return rc;
+    if (precision != FRL_PREC_FP16) {
+        set_error("frl_cfm_loss_grad_pair: the tensor-core training path computes with fp16 operands (FRL_PREC_FP16)");
+        return FRL_ERR_UNSUPPORTED;
+    }
+    if (net->n_out_p > 64) {
+        set_error("tensor-core training is not available for this net (a_dim too large)");
+        return FRL_ERR_UNSUPPORTED;
+    }
+    CfmTerm t2[2];
+    double scale[2];
+    for (int i = 0; i < 2; ++i) {
+        scale[i] = (double)terms[i].grad_scale / (double)(terms[i].mean_divisor > 0 ? terms[i].mean_divisor : std::max(1ll, terms[i].B));
+    }
+    if (scale[0] != 0.0 && scale[1] != 0.0 && (std::abs(scale[1] / scale[0]) > 256.0 || std::abs(scale[1] / scale[0]) < 1.0 / 256.0)) {
+        // very unequal per-row scales would cost fp16 range in the stacked pass: one pass per term instead
+        for (int i = 0; i < 2; ++i) {
+            rc = frl_cfm_loss_grad_p(net, terms[i].role_sign, terms[i].s_dev, terms[i].a0_dev, terms[i].t_dev, terms[i].noise_dev,
+                                     terms[i].B, terms[i].mean_divisor, terms[i].grad_scale, i == 0 ? accumulate : 1,
+                                     terms[i].loss_dev, grad, precision, stream);
+            if (rc != FRL_OK) return rc;
+        }
+        return FRL_OK;
+    }
+    for (int i = 0; i < 2; ++i) {
+        FRL_REQUIRE(terms[i].s_dev && terms[i].a0_dev && terms[i].t_dev && terms[i].noise_dev, "null input");
+        FRL_REQUIRE(terms[i].B > 0, "empty batch");
+        t2[i] = CfmTerm{terms[i].role_sign >= 0.f ? 1.f : -1.f, terms[i].s_dev, terms[i].a0_dev, terms[i].t_dev, terms[i].noise_dev,
+                        terms[i].B, terms[i].mean_divisor, terms[i].grad_scale, terms[i].loss_dev};
+    }
+    FRL_CUDA(cudaSetDevice(net->cfg.device));
+    return cfm_loss_grad_tc(net, t2, 2, accumulate, grad, (cudaStream_t)stream);
 }
 
 extern "C" int frl_reg_loss_grad(frl_net* net, const float* s, const float* a, const float* t, const float* probe,

@@ -143,9 +143,15 @@ int grad_axpy(float* y, const float* x, long long n, float alpha, const float* n
 
 // train_tc.cu
 int tc_train_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
-int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float* a0, const float* t, const float* noise,
-                     long long B, long long mean_divisor, float grad_scale, int accumulate, float* loss, float* grad,
-                     cudaStream_t stream);
+// one CFM loss term (a role's batch); up to two terms are stacked row-wise into ONE pass over the net
+struct CfmTerm {
+    float sign;
+    const float *s, *a0, *t, *noise;
+    long long B, mean_divisor;
+    float grad_scale;
+    float* loss;   // device scalar (may be null)
+};
+int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumulate, float* grad, cudaStream_t stream);
 
 // adam.cu
 int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, long long* step_dev, double lr, double beta1,

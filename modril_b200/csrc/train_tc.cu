@@ -51,13 +51,15 @@ struct LayerParams {
     uint8_t* out_tiles;         // [tile][N/8][128][8]
     const uint8_t* mask_tiles;  // [tile][N/8][128][8] (EPI_MASK)
     int K, N, n_tiles, n_stages;
-    // EPI_LOSS
-    const float* a0;
-    const float* noise;
-    const float* t;
-    float sign;
+    // EPI_LOSS: up to two terms (roles) stacked by tiles: term 1 starts at tile `tile_split` (== n_tiles if there is one)
+    const float* a0[2];
+    const float* noise[2];
+    const float* t[2];
+    float sign[2];
+    float rel[2];           // dV multiplier of the term (its grad_scale / mean divisor relative to the final scale)
+    long long B[2];
+    int tile_split;
     int a_dim, n_heads;
-    long long B;
     double* loss_partial;   // [n_tiles * 4]
     float* dvsum_partial;   // [n_tiles * 4][N]
 };
@@ -232,23 +234,28 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[g16 + i] = __uint_as_float(r16[i]) + sBias[g16 + i];
                 }
-                const long long g = (long long)tile * kRows + row;
+                const int term_i = tile >= p.tile_split ? 1 : 0;
+                const long long g = (long long)(tile - (term_i ? p.tile_split : 0)) * kRows + row;
+                const float sign = p.sign[term_i];
                 const int A = p.a_dim;
                 double term = 0.0;
-                if (g < p.B) {
-                    const float w = powf(1.f - p.t[g], 1.5f);
+                if (g < p.B[term_i]) {
+                    const float* noise = p.noise[term_i];
+                    const float* a0 = p.a0[term_i];
+                    const float w = powf(1.f - p.t[term_i][g], 1.5f);
+                    const float w2 = 2.f * w * p.rel[term_i];
                     float acc = 0.f;
                     for (int j = 0; j < A; ++j) {
                         float pred = v[j], th = 0.f;
                         if (p.n_heads == 2) {
                             th = tanhf(v[A + j]);
-                            pred += p.sign * th;
+                            pred += sign * th;
                         }
-                        const float diff = pred - (p.noise[g * A + j] - p.a0[g * A + j]);
+                        const float diff = pred - (noise[g * A + j] - a0[g * A + j]);
                         acc += diff * diff;
-                        const float d = 2.f * w * diff;
+                        const float d = w2 * diff;
                         v[j] = d;
-                        if (p.n_heads == 2) v[A + j] = d * p.sign * (1.f - th * th);
+                        if (p.n_heads == 2) v[A + j] = d * sign * (1.f - th * th);
                     }
                     for (int j = p.n_heads * A; j < p.N; ++j) v[j] = 0.f;
                     term = (double)(w * acc);
@@ -523,13 +530,25 @@ __global__ void tc_reduce_kernel(RedParams rp, float* __restrict__ grad) {
 }
 
 // block 0: loss;  block 1 + o: bias gradient of head output o
+// (the loss partials of tiles [0, n_part0) belong to term 0, the rest to term 1)
 __global__ void __launch_bounds__(256) tc_reduce_small_kernel(const double* __restrict__ lpart, const float* __restrict__ dvsum,
-                                                              int n_part, int NOp, RedParams rp, double inv_div,
-                                                              float* __restrict__ loss, float* __restrict__ grad) {
+                                                              int n_part, int n_part0, int NOp, RedParams rp, double inv_div0,
+                                                              double inv_div1, float* __restrict__ loss0,
+                                                              float* __restrict__ loss1, float* __restrict__ grad) {
     __shared__ double sh[256];
     double acc = 0.0;
     if (blockIdx.x == 0) {
-        for (int i = threadIdx.x; i < n_part; i += 256) acc += lpart[i];
+        double acc1 = 0.0;
+        for (int i = threadIdx.x; i < n_part0; i += 256) acc += lpart[i];
+        for (int i = n_part0 + threadIdx.x; i < n_part; i += 256) acc1 += lpart[i];
+        sh[threadIdx.x] = acc1;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0 && loss1) loss1[0] = (float)(sh[0] * inv_div1);
+        __syncthreads();
     } else {
         const int o = blockIdx.x - 1;
         for (int i = threadIdx.x; i < n_part; i += 256) acc += (double)dvsum[(size_t)i * NOp + o];
@@ -542,7 +561,7 @@ __global__ void __launch_bounds__(256) tc_reduce_small_kernel(const double* __re
     }
     if (threadIdx.x != 0) return;
     if (blockIdx.x == 0) {
-        if (loss) loss[0] = (float)(sh[0] * inv_div);
+        if (loss0) loss0[0] = (float)(sh[0] * inv_div0);
     } else if (grad) {
         const int o = blockIdx.x - 1;
         const int h = o / rp.a_dim, j = o % rp.a_dim;
@@ -694,13 +713,17 @@ static int launch_layer(const ttc::LayerParams& p0, int device, cudaStream_t st)
     return FRL_OK;
 }
 
-int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float* a0, const float* t, const float* noise,
-                     long long B, long long mean_divisor, float grad_scale, int accumulate, float* loss, float* grad,
-                     cudaStream_t st) {
+int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumulate, float* grad, cudaStream_t st) {
     using namespace ttc;
     const int H = net->cfg.hidden, A = net->cfg.a_dim, depth = net->cfg.depth;
     const int K0p = net->d_in_p, NOp = net->n_out_p;
-    FRL_REQUIRE(B > 0 && B < (1ll << 30), "batch size out of range");
+    FRL_REQUIRE(n_terms == 1 || n_terms == 2, "one or two loss terms");
+    long long B_total = 0;
+    for (int i = 0; i < n_terms; ++i) {
+        FRL_REQUIRE(terms[i].B > 0 && terms[i].B < (1ll << 30), "batch size out of range");
+        B_total += terms[i].B;
+    }
+    FRL_REQUIRE(B_total < (1ll << 30), "batch size out of range");
     {
         int rcp = ensure_pack(net, PACK_TRAIN, st);   // fp16 GEMM images
         if (rcp != FRL_OK) return rcp;
@@ -709,8 +732,18 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
     }
     FRL_REQUIRE(net->pack_train != nullptr, "tensor-core training weights missing");
     FRL_REQUIRE(NOp <= 64, "a_dim too large for the tensor-core training path");
-    const double div = (double)(mean_divisor > 0 ? mean_divisor : B);
-    const int nt = (int)((B + kRows - 1) / kRows);
+    // every term starts on a tile boundary; the final reduction applies the scale of the first term with a non-zero
+    // scale, the loss epilogue multiplies the other term's dV by the ratio
+    int nt_of[2] = {0, 0};
+    double scale_of[2] = {0.0, 0.0}, inv_div[2] = {0.0, 0.0};
+    for (int i = 0; i < n_terms; ++i) {
+        nt_of[i] = (int)((terms[i].B + kRows - 1) / kRows);
+        const double div = (double)(terms[i].mean_divisor > 0 ? terms[i].mean_divisor : terms[i].B);
+        inv_div[i] = 1.0 / div;
+        scale_of[i] = (double)terms[i].grad_scale / div;
+    }
+    const int nt = nt_of[0] + nt_of[1];
+    const double final_scale = scale_of[0] != 0.0 ? scale_of[0] : (scale_of[1] != 0.0 ? scale_of[1] : 1.0);
     const int device = net->cfg.device;
     const TrainPack tp = train_pack_layout(net);
     const uint8_t* pk = static_cast<const uint8_t*>(net->pack_train);
@@ -751,9 +784,11 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
     float* dvsum = reinterpret_cast<float*>(ws + o_dvs);
 
     // ---- forward ----
-    {
-        const long long n = (long long)nt * (K0p / 8) * kRows;
-        tc_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, a0, t, noise, ws + o_x0, B, nt, net->cfg.s_dim, A, K0p);
+    for (int i = 0; i < n_terms; ++i) {
+        const long long n = (long long)nt_of[i] * (K0p / 8) * kRows;
+        tc_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(terms[i].s, terms[i].a0, terms[i].t, terms[i].noise,
+                                                                      ws + o_x0 + (i ? (size_t)nt_of[0] * tileX : 0), terms[i].B,
+                                                                      nt_of[i], net->cfg.s_dim, A, K0p);
         FRL_CUDA(cudaGetLastError());
     }
     for (int l = 0; l < depth; ++l) {
@@ -777,7 +812,13 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
         p.K = H;
         p.N = NOp;
         p.n_tiles = nt;
-        p.a0 = a0; p.noise = noise; p.t = t; p.sign = role_sign; p.a_dim = A; p.n_heads = net->cfg.n_heads; p.B = B;
+        for (int i = 0; i < 2; ++i) {
+            const CfmTerm& tm = terms[i < n_terms ? i : 0];
+            p.a0[i] = tm.a0; p.noise[i] = tm.noise; p.t[i] = tm.t; p.sign[i] = tm.sign; p.B[i] = i < n_terms ? tm.B : 0;
+            p.rel[i] = (float)(scale_of[i] / final_scale);
+        }
+        p.tile_split = nt_of[0];
+        p.a_dim = A; p.n_heads = net->cfg.n_heads;
         p.loss_partial = lpart;
         p.dvsum_partial = dvsum;
         rc = launch_layer<EPI_LOSS>(p, device, st);
@@ -790,11 +831,12 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
     for (int h = 0; h < net->cfg.n_heads; ++h) { rp.off_wh[h] = net->off_wh[h]; rp.off_bh[h] = net->off_bh[h]; }
     rp.n_trunk = net->off_wh[0];
     rp.n_params = net->n_params;
-    rp.scale = (float)((double)grad_scale / div);
+    rp.scale = (float)final_scale;
     rp.accumulate = accumulate;
     for (int j = 0; j < n_jobs; ++j) { rp.part[j] = reinterpret_cast<const float*>(ws + o_part[j]); rp.ldp[j] = ldp[j]; }
     if (!grad) {
-        tc_reduce_small_kernel<<<1, 256, 0, st>>>(lpart, dvsum, nt * 4, NOp, rp, 1.0 / div, loss, nullptr);
+        tc_reduce_small_kernel<<<1, 256, 0, st>>>(lpart, dvsum, nt * 4, nt_of[0] * 4, NOp, rp, inv_div[0], inv_div[1], terms[0].loss,
+                                                  n_terms > 1 ? terms[1].loss : nullptr, nullptr);
         FRL_CUDA(cudaGetLastError());
         return FRL_OK;
     }
@@ -844,7 +886,8 @@ int cfm_loss_grad_tc(frl_net* net, float role_sign, const float* s, const float*
         FRL_CUDA(cudaGetLastError());
     }
     tc_reduce_kernel<<<(unsigned)((net->n_params + 255) / 256), 256, 0, st>>>(rp, grad);
-    tc_reduce_small_kernel<<<1 + net->cfg.n_heads * A, 256, 0, st>>>(lpart, dvsum, nt * 4, NOp, rp, 1.0 / div, loss, grad);
+    tc_reduce_small_kernel<<<1 + net->cfg.n_heads * A, 256, 0, st>>>(lpart, dvsum, nt * 4, nt_of[0] * 4, NOp, rp, inv_div[0], inv_div[1],
+                                                                     terms[0].loss, n_terms > 1 ? terms[1].loss : nullptr, grad);
     FRL_CUDA(cudaGetLastError());
     return FRL_OK;
 }

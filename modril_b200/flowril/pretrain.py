@@ -536,7 +536,13 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
     losses = []
     ws = 1 if world is None else world[1]
     global_rows = world[2] if (world is not None and len(world) > 2) else None
-    for term in terms:
+    def inputs(term, dev):
+        return (as_f32_cuda(term["s"], dev, "s"), as_f32_cuda(term["a0"], dev, "a0"),
+                as_f32_cuda(term["t"], dev, "t").reshape(-1), as_f32_cuda(term["noise"], dev, "noise"))
+
+    i = 0
+    while i < len(terms):
+        term = terms[i]
         net = term["net"]
         dev = net.flat_params().device
         h = net.native()
@@ -544,17 +550,34 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
         first = all(net is not n for n in seen)
         if first:
             seen.append(net)
-        s = as_f32_cuda(term["s"], dev, "s")
-        a0 = as_f32_cuda(term["a0"], dev, "a0")
-        t = as_f32_cuda(term["t"], dev, "t").reshape(-1)
-        noise = as_f32_cuda(term["noise"], dev, "noise")
-        B = a0.shape[0]
-        loss = torch.empty(1, device=dev)
-        _native.check(L.frl_cfm_loss_grad_p(h, float(term["sign"]), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B,
-                                            int(global_rows) if global_rows else B * ws,
-                                            float(term.get("rate", 1.0)), 0 if first else 1, _ptr(loss), _ptr(g), prec,
-                                            _current_stream(dev)), "frl_cfm_loss_grad_p")
-        losses.append(loss)
+        # two consecutive terms on the same net (scrf: expert + agent batch) go through the net in ONE stacked pass on
+        # the tensor-core route
+        pair = prec != _native.PREC_FP32 and i + 1 < len(terms) and terms[i + 1]["net"] is net
+        group = terms[i:i + 2] if pair else [term]
+        keep, out = [], []
+        arr = (_native.CfmTerm * 2)()
+        for k, tm in enumerate(group):
+            s, a0, t, noise = inputs(tm, dev)
+            B = a0.shape[0]
+            loss = torch.empty(1, device=dev)
+            keep.append((s, a0, t, noise))
+            out.append(loss)
+            arr[k].role_sign = float(tm["sign"])
+            arr[k].s, arr[k].a0, arr[k].t, arr[k].noise = s.data_ptr(), a0.data_ptr(), t.data_ptr(), noise.data_ptr()
+            arr[k].B = B
+            arr[k].mean_divisor = int(global_rows) if global_rows else B * ws
+            arr[k].grad_scale = float(tm.get("rate", 1.0))
+            arr[k].loss = loss.data_ptr()
+        if pair:
+            _native.check(L.frl_cfm_loss_grad_pair(h, arr, 0 if first else 1, _ptr(g), prec, _current_stream(dev)),
+                          "frl_cfm_loss_grad_pair")
+        else:
+            s, a0, t, noise = keep[0]
+            _native.check(L.frl_cfm_loss_grad_p(h, arr[0].role_sign, _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), arr[0].B,
+                                                arr[0].mean_divisor, arr[0].grad_scale, 0 if first else 1, _ptr(out[0]),
+                                                _ptr(g), prec, _current_stream(dev)), "frl_cfm_loss_grad_p")
+        losses.extend(out)
+        i += len(group)
     grads = []
     for net in opt.nets:
         g = net.flat_grad()

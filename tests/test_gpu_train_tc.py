@@ -168,3 +168,52 @@ def test_tc_training_curve_vs_reference():
     ma = lambda x: np.stack([np.convolve(x[:, j], np.ones(k) / k, mode="valid") for j in range(2)], 1)
     rel = np.abs(ma(curve) - ma(ref)) / np.abs(ma(ref))
     assert rel.max() <= 5e-2, rel.max()
+
+
+@pytest.mark.parametrize("B0,B1,rates", [(1000, 300, (1.0, 0.5)), (128, 128, (1.0, 1.0)), (4096, 5000, (0.0, 2.0))])
+def test_stacked_pair_pass_equals_two_single_passes(B0, B1, rates):
+    """frl_cfm_loss_grad_pair (both roles' batches stacked row-wise through the net in one pass) against two
+    frl_cfm_loss_grad_p calls.  With equal per-row scales the two routes round identically and differ only in the split
+    of the batch reductions (<= 1e-5 relative); with unequal scales (ragged batches, unequal rates, a zero rate) the second
+    term's dV is rounded to fp16 after its relative scale instead of before, which is fp16 noise (bar 3e-3)."""
+    import ctypes as C
+
+    from modril_b200 import _native
+    from modril_b200.flowril.networks import _current_stream, _ptr
+
+    spec = cf.NetSpec(11, 3, 256, 4, 2)
+    m = build_model(spec, cf.make_params(spec, 77, 1.0))
+    net = m.net
+    h = net.native()
+    L = _native.lib()
+    ins, single, losses1 = [], None, []
+    g = torch.zeros_like(net.flat_params())
+    for k, (B, sign) in enumerate(((B0, 1.0), (B1, -1.0))):
+        s, a = synth.states_actions(500 + k, B, 11, 3)
+        t, noise = synth.cfm_draws(600 + k, B, 3)
+        d = tuple(dev(x) for x in (s, a, t.reshape(-1), noise))
+        ins.append(d)
+        loss = torch.empty(1, device="cuda:0")
+        _native.check(L.frl_cfm_loss_grad_p(h, sign, _ptr(d[0]), _ptr(d[1]), _ptr(d[2]), _ptr(d[3]), B, 0, rates[k], k, _ptr(loss),
+                                            _ptr(g), _native.PREC_FP16, _current_stream(g.device)), "single")
+        losses1.append(loss)
+    single = g.clone()
+    arr = (_native.CfmTerm * 2)()
+    losses2 = [torch.empty(1, device="cuda:0") for _ in range(2)]
+    for k, (B, sign) in enumerate(((B0, 1.0), (B1, -1.0))):
+        d = ins[k]
+        arr[k].role_sign, arr[k].B, arr[k].mean_divisor, arr[k].grad_scale = sign, B, 0, rates[k]
+        arr[k].s, arr[k].a0, arr[k].t, arr[k].noise = (x.data_ptr() for x in d)
+        arr[k].loss = losses2[k].data_ptr()
+    g2 = torch.full_like(g, 7.0)    # overwritten (accumulate = 0)
+    _native.check(L.frl_cfm_loss_grad_pair(h, arr, 0, _ptr(g2), _native.PREC_FP16, _current_stream(g.device)), "pair")
+    for l1, l2 in zip(losses1, losses2):
+        assert abs(float(l1) - float(l2)) <= 1e-6 * abs(float(l1))
+    tol = 1e-5 if (B0 == B1 and rates[0] == rates[1]) else 3e-3
+    assert _rel_l2(g2.cpu().numpy(), single.cpu().numpy()) <= tol
+    # accumulate = 1 adds on top; FP32 precision runs the two FFMA passes
+    _native.check(L.frl_cfm_loss_grad_pair(h, arr, 1, _ptr(g2), _native.PREC_FP16, _current_stream(g.device)), "pair acc")
+    assert _rel_l2(g2.cpu().numpy(), 2 * single.cpu().numpy()) <= tol
+    g3 = torch.zeros_like(g)
+    _native.check(L.frl_cfm_loss_grad_pair(h, arr, 0, _ptr(g3), _native.PREC_FP32, _current_stream(g.device)), "pair fp32")
+    assert _rel_l2(g3.cpu().numpy(), single.cpu().numpy()) <= 3e-2      # fp32 vs fp16 operands
