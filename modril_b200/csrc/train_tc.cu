@@ -49,7 +49,8 @@ struct LayerParams {
     const uint8_t* w_img;       // [K/8][N][8]
     const float* bias;          // [N] (EPI_RELU, EPI_LOSS)
     uint8_t* out_tiles;         // [tile][N/8][128][8]
-    const uint8_t* mask_tiles;  // [tile][N/8][128][8] (EPI_MASK)
+    const uint32_t* mask_bits;  // [tile][N/32][128]: bit c of word (chunk, row) = activation (row, 32*chunk + c) > 0 (EPI_MASK)
+    uint32_t* bits_out;         // same layout, written by EPI_RELU for the backward pass (may be null)
     int K, N, n_tiles, n_stages;
     // EPI_LOSS: up to two terms (roles) stacked by tiles: term 1 starts at tile `tile_split` (== n_tiles if there is one)
     const float* a0[2];
@@ -195,28 +196,30 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
             if (EPI == EPI_RELU || EPI == EPI_MASK) {
                 const int half = p.N / 2;
                 uint8_t* out = p.out_tiles + (size_t)tile * p.N * (kRows * 2) + (size_t)row * 16;
-                const uint8_t* msk = EPI == EPI_MASK ? p.mask_tiles + (size_t)tile * p.N * (kRows * 2) + (size_t)row * 16 : nullptr;
+                // ReLU masks travel as one bit per activation (4 KB per tile instead of re-reading the 64 KB tile)
+                const size_t bit_row = (size_t)tile * (p.N / 32) * kRows + row;
                 for (int c0 = ch * half; c0 < (ch + 1) * half; c0 += 32) {
                     uint32_t z[32];
                     tmem_ld32(taddr + (uint32_t)c0, z);
-                    uint4 mk[4];
-                    if (EPI == EPI_MASK) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            mk[i] = __ldg(reinterpret_cast<const uint4*>(msk + (size_t)(c0 / 8 + i) * (kRows * 16)));
-                    }
+                    uint32_t bits = 0;
+                    if (EPI == EPI_MASK) bits = __ldg(p.mask_bits + bit_row + (size_t)(c0 / 32) * kRows);
                     tmem_ld_wait_dep(z);
                     uint32_t o[16];
                     if (EPI == EPI_RELU) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
+                        for (int j = 0; j < 16; ++j) {
                             o[j] = pack2_f16_relu(__uint_as_float(z[2 * j]) + sBias[c0 + 2 * j],
                                                   __uint_as_float(z[2 * j + 1]) + sBias[c0 + 2 * j + 1]);
+                            // H >= 0 after ReLU, so H > 0  <=>  its fp16 bits are non-zero
+                            bits |= ((o[j] & 0xFFFFu) ? 1u : 0u) << (2 * j) | ((o[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+                        }
+                        if (p.bits_out) p.bits_out[bit_row + (size_t)(c0 / 32) * kRows] = bits;
                     } else {
-                        const uint32_t* mw = reinterpret_cast<const uint32_t*>(mk);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)  // H >= 0 after ReLU, so H > 0  <=>  its fp16 bits are non-zero
-                            o[j] = pack2_f16(__uint_as_float(z[2 * j]), __uint_as_float(z[2 * j + 1])) & __vcmpne2(mw[j], 0u);
+                        for (int j = 0; j < 16; ++j) {
+                            const uint32_t keep = ((bits >> (2 * j)) & 1u ? 0x0000FFFFu : 0u) | ((bits >> (2 * j + 1)) & 1u ? 0xFFFF0000u : 0u);
+                            o[j] = pack2_f16(__uint_as_float(z[2 * j]), __uint_as_float(z[2 * j + 1])) & keep;
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -763,6 +766,8 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     size_t o_h[kMaxDepth], o_dz[kMaxDepth];
     for (int l = 0; l < depth; ++l) o_h[l] = take(tileH * nt);
     for (int l = 0; l < depth; ++l) o_dz[l] = take(tileH * nt);
+    size_t o_bits[kMaxDepth];
+    for (int l = 0; l < depth; ++l) o_bits[l] = take((size_t)nt * (H / 32) * kRows * sizeof(uint32_t));
     const size_t o_dv = take(tileV * nt);
     const size_t o_lp = take((size_t)nt * 4 * sizeof(double));
     const size_t o_dvs = take((size_t)nt * 4 * NOp * sizeof(float));
@@ -797,6 +802,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         p.w_img = pk + tp.wf[l];
         p.bias = net->f32.b[l];
         p.out_tiles = ws + o_h[l];
+        p.bits_out = grad ? reinterpret_cast<uint32_t*>(ws + o_bits[l]) : nullptr;
         p.K = l == 0 ? K0p : H;
         p.N = H;
         p.n_tiles = nt;
@@ -847,7 +853,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         p.a_tiles = ws + o_dv;
         p.w_img = pk + tp.whd;
         p.out_tiles = ws + o_dz[depth - 1];
-        p.mask_tiles = ws + o_h[depth - 1];
+        p.mask_bits = reinterpret_cast<const uint32_t*>(ws + o_bits[depth - 1]);
         p.K = NOp;
         p.N = H;
         p.n_tiles = nt;
@@ -859,7 +865,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         p.a_tiles = ws + o_dz[l];
         p.w_img = pk + tp.wd[l];
         p.out_tiles = ws + o_dz[l - 1];
-        p.mask_tiles = ws + o_h[l - 1];
+        p.mask_bits = reinterpret_cast<const uint32_t*>(ws + o_bits[l - 1]);
         p.K = H;
         p.N = H;
         p.n_tiles = nt;
