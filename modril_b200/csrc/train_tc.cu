@@ -39,7 +39,11 @@ using namespace tcc;
 
 constexpr int kRows = 128;
 constexpr int kChunkBytes = 16384;  // 64 features x 128 rows x 2 B
-constexpr int kLayerThreads = 320;  // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2..9 epilogue
+#ifndef FRL_TRAIN_EPI_WARPS
+#define FRL_TRAIN_EPI_WARPS 16
+#endif
+constexpr int kLayerEpiWarps = FRL_TRAIN_EPI_WARPS;   // 8 or 16: four TMEM lane quarters x (2 or 4) column slices
+constexpr int kLayerThreads = (2 + kLayerEpiWarps) * 32;  // warp 0 producer, warp 1 MMA issuer + TMEM owner, then the epilogue warps
 constexpr int kWgradThreads = 192;  // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue
 constexpr int kMaxStages = 8;
 enum { EPI_RELU = 0, EPI_MASK = 1, EPI_LOSS = 2 };
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
         mbar_init(w_full, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(tmem_full(i), 1);
-            mbar_init(tmem_empty(i), 8);
+            mbar_init(tmem_empty(i), kLayerEpiWarps);
         }
         fence_barrier_init();
     }
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
         // ------------------------------------------------ epilogue ------------------------------------------------
         const int ew = warp - 2;
         const int q = warp & 3;      // TMEM lane quarter this warp may access
-        const int ch = ew >> 2;      // column half
+        const int ch = ew >> 2;      // column slice
         const int row = q * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
@@ -194,16 +198,11 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
             if (EPI == EPI_RELU || EPI == EPI_MASK) {
-                const int half = p.N / 2;
+                const int half = p.N / (kLayerEpiWarps / 4);   // columns per slice
                 uint8_t* out = p.out_tiles + (size_t)tile * p.N * (kRows * 2) + (size_t)row * 16;
                 // ReLU masks travel as one bit per activation (4 KB per tile instead of re-reading the 64 KB tile)
                 const size_t bit_row = (size_t)tile * (p.N / 32) * kRows + row;
-                for (int c0 = ch * half; c0 < (ch + 1) * half; c0 += 32) {
-                    uint32_t z[32];
-                    tmem_ld32(taddr + (uint32_t)c0, z);
-                    uint32_t bits = 0;
-                    if (EPI == EPI_MASK) bits = __ldg(p.mask_bits + bit_row + (size_t)(c0 / 32) * kRows);
-                    tmem_ld_wait_dep(z);
+                auto finish = [&](int c0, const uint32_t (&z)[32], uint32_t bits) {
                     uint32_t o[16];
                     if (EPI == EPI_RELU) {
 #pragma unroll
@@ -225,6 +224,28 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
                     for (int i = 0; i < 4; ++i)
                         *reinterpret_cast<uint4*>(out + (size_t)(c0 / 8 + i) * (kRows * 16)) =
                             make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                };
+                // two 32-column chunks per round (one when a slice is only 32 columns wide: H = 128 with 16 epilogue warps):
+                // both TMEM loads are in flight together
+                const bool two = half >= 64;
+                for (int c0 = ch * half; c0 < (ch + 1) * half; c0 += two ? 64 : 32) {
+                    uint32_t z0[32], z1[32];
+                    tmem_ld32(taddr + (uint32_t)c0, z0);
+                    if (two) tmem_ld32(taddr + (uint32_t)c0 + 32, z1);
+                    uint32_t bits0 = 0, bits1 = 0;
+                    if (EPI == EPI_MASK) {
+                        bits0 = __ldg(p.mask_bits + bit_row + (size_t)(c0 / 32) * kRows);
+                        if (two) bits1 = __ldg(p.mask_bits + bit_row + (size_t)(c0 / 32 + 1) * kRows);
+                    }
+                    tmem_ld_wait_dep(z0);
+                    if (two) tmem_ld_wait_dep(z1);
+                    if (c0 + (two ? 64 : 32) >= (ch + 1) * half) {   // the accumulator stage is drained: the MMAs of tile i + 2 may start
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tmem_empty(as));
+                    }
+                    finish(c0, z0, bits0);
+                    if (two) finish(c0 + 32, z1, bits1);
                 }
             } else if (ch == 0) {
                 // heads: V = D + b;  loss term and dL/dV (scaled by 2 w only: 1/B and the caller's grad_scale are applied
@@ -289,9 +310,11 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
                 for (int s = 16; s > 0; s >>= 1) term += __shfl_xor_sync(0xffffffffu, term, s);
                 if (lane == 0) p.loss_partial[(size_t)tile * 4 + q] = term;
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty(as));
+            if (EPI == EPI_LOSS) {   // (the other epilogues release the accumulator stage as soon as it is in registers)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty(as));
+            }
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
