@@ -205,18 +205,25 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
                 auto finish = [&](int c0, const uint32_t (&z)[32], uint32_t bits) {
                     uint32_t o[16];
                     if (EPI == EPI_RELU) {
+                        const float4* b4 = reinterpret_cast<const float4*>(sBias + c0);   // broadcast vector loads
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 b = b4[j4];
+                            o[2 * j4] = pack2_f16_relu(__uint_as_float(z[4 * j4]) + b.x, __uint_as_float(z[4 * j4 + 1]) + b.y);
+                            o[2 * j4 + 1] = pack2_f16_relu(__uint_as_float(z[4 * j4 + 2]) + b.z, __uint_as_float(z[4 * j4 + 3]) + b.w);
+                        }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            o[j] = pack2_f16_relu(__uint_as_float(z[2 * j]) + sBias[c0 + 2 * j],
-                                                  __uint_as_float(z[2 * j + 1]) + sBias[c0 + 2 * j + 1]);
-                            // H >= 0 after ReLU, so H > 0  <=>  its fp16 bits are non-zero
-                            bits |= ((o[j] & 0xFFFFu) ? 1u : 0u) << (2 * j) | ((o[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+                            // H >= 0 after ReLU, so H > 0  <=>  its fp16 bits are non-zero: 0x0001 per non-zero half
+                            const uint32_t nz = __vcmpne2(o[j], 0u) & 0x00010001u;
+                            bits |= ((nz | (nz >> 15)) & 3u) << (2 * j);
                         }
                         if (p.bits_out) p.bits_out[bit_row + (size_t)(c0 / 32) * kRows] = bits;
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const uint32_t keep = ((bits >> (2 * j)) & 1u ? 0x0000FFFFu : 0u) | ((bits >> (2 * j + 1)) & 1u ? 0xFFFF0000u : 0u);
+                            const uint32_t two = (bits >> (2 * j)) & 3u;                       // bit 0 -> low half, bit 1 -> high half
+                            const uint32_t keep = ((two & 1u) | ((two & 2u) << 15)) * 0xFFFFu;   // 0x0001 / 0x10000 -> 0xFFFF masks
                             o[j] = pack2_f16(__uint_as_float(z[2 * j]), __uint_as_float(z[2 * j + 1])) & keep;
                         }
                     }
