@@ -51,6 +51,27 @@ def measured_peak_tflops():
         return 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
 
 
+def measured_hbm_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6550.0   # B200_PROFILING.md fallback
+
+
+def train_hbm_bytes_per_row(d_in, a_dim, H=HIDDEN, depth=DEPTH, n_heads=2):
+    """HBM bytes one training row costs in the tensor-core path (fp16 activation tiles, 1 mask bit per activation):
+    forward: read the layer input + write its output (+ mask bits); loss: read h; dgrad: read dZ + bits, write dZ;
+    wgrad: read dZ and the layer input of every layer."""
+    k0 = -(-d_in // 16) * 16
+    nop = -(-(n_heads * a_dim) // 16) * 16
+    h, bits = 2 * H, H // 8
+    fwd = (2 * k0 + h + bits) + (depth - 1) * (2 * h + bits) + (h + 2 * nop)
+    dgrad = (2 * nop + bits + h) + (depth - 1) * (2 * h + bits)
+    wgrad = (h + 2 * k0) + (depth - 1) * (2 * h) + (h + 2 * nop)
+    return fwd + dgrad + wgrad
+
+
 class ClockSampler:
     """Samples SM clock + throttle reasons through NVML while the timed region runs."""
 
@@ -453,6 +474,11 @@ def run_ours(args):
                           + ("; replayed as one CUDA graph" if use_graph else ""),
                   "fp32_ffma_samples_per_sec": train_rates["fp32"],
                   "algorithmic_tflops": train_rate * 3 * f_fwd_train / 1e12,
+                  # what bounds it: the per-layer kernels stream fp16 activation tiles through HBM
+                  "hbm": {"bytes_per_row": train_hbm_bytes_per_row(d_in_t, a_dim),
+                          "achieved_gbs": train_rate * train_hbm_bytes_per_row(d_in_t, a_dim) / 1e9 / world,
+                          "peak_gbs": measured_hbm_gbs(),
+                          "frac": train_rate * train_hbm_bytes_per_row(d_in_t, a_dim) / 1e9 / world / measured_hbm_gbs()},
                   "frac_of_peak": train_rate * 3 * f_fwd_train / 1e12 / measured_peak_tflops()[0] / world,
                   "collective": "NCCL all-reduce of the flat grad" if world > 1 else "none"},
         "bcf": bcf_info,
