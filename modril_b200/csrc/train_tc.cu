@@ -56,6 +56,8 @@ struct LayerParams {
     const uint32_t* mask_bits;  // [tile][N/32][128]: bit c of word (chunk, row) = activation (row, 32*chunk + c) > 0 (EPI_MASK)
     uint32_t* bits_out;         // same layout, written by EPI_RELU for the backward pass (may be null)
     int K, N, n_tiles, n_stages;
+    int reverse;                // walk the tiles from the last to the first: consecutive kernels alternate, so a kernel
+                                // starts with the tiles its predecessor wrote last (still in L2)
     // EPI_LOSS: up to two terms (roles) stacked by tiles: term 1 starts at tile `tile_split` (== n_tiles if there is one)
     const float* a0[2];
     const float* noise[2];
@@ -146,7 +148,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
                 bulk_g2s(smem_u32(sW + off), p.w_img + off, min((uint32_t)kChunkBytes, w_bytes - off), w_full);
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int it = blockIdx.x; it < p.n_tiles; it += gridDim.x) {
+                const int tile = p.reverse ? p.n_tiles - 1 - it : it;
                 const uint8_t* src = p.a_tiles + (size_t)tile * p.K * (kRows * 2);
                 for (int c = 0; c < n_chunks; ++c) {
                     const uint32_t bytes = (uint32_t)min(64, p.K - 64 * c) * (kRows * 2);
@@ -193,7 +196,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
         const int row = q * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int it = blockIdx.x; it < p.n_tiles; it += gridDim.x) {
+            const int tile = p.reverse ? p.n_tiles - 1 - it : it;
             mbar_wait(tmem_full(as), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
@@ -818,6 +822,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     double* lpart = reinterpret_cast<double*>(ws + o_lp);
     float* dvsum = reinterpret_cast<float*>(ws + o_dvs);
 
+    int n_launch = 0;   // layer kernels alternate their tile order (see LayerParams::reverse)
     // ---- forward ----
     for (int i = 0; i < n_terms; ++i) {
         const long long n = (long long)nt_of[i] * (K0p / 8) * kRows;
@@ -833,6 +838,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         p.bias = net->f32.b[l];
         p.out_tiles = ws + o_h[l];
         p.bits_out = grad ? reinterpret_cast<uint32_t*>(ws + o_bits[l]) : nullptr;
+        p.reverse = (n_launch++) & 1;
         p.K = l == 0 ? K0p : H;
         p.N = H;
         p.n_tiles = nt;
@@ -854,6 +860,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
             p.rel[i] = (float)(scale_of[i] / final_scale);
         }
         p.tile_split = nt_of[0];
+        p.reverse = (n_launch++) & 1;
         p.a_dim = A; p.n_heads = net->cfg.n_heads;
         p.loss_partial = lpart;
         p.dvsum_partial = dvsum;
@@ -884,6 +891,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         p.w_img = pk + tp.whd;
         p.out_tiles = ws + o_dz[depth - 1];
         p.mask_bits = reinterpret_cast<const uint32_t*>(ws + o_bits[depth - 1]);
+        p.reverse = (n_launch++) & 1;
         p.K = NOp;
         p.N = H;
         p.n_tiles = nt;
@@ -896,6 +904,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         p.w_img = pk + tp.wd[l];
         p.out_tiles = ws + o_dz[l - 1];
         p.mask_bits = reinterpret_cast<const uint32_t*>(ws + o_bits[l - 1]);
+        p.reverse = (n_launch++) & 1;
         p.K = H;
         p.N = H;
         p.n_tiles = nt;
