@@ -347,25 +347,41 @@ def run_ours(args):
     tt_ = (torch.rand(2, Bt, 1, generator=g) * (1 - 2e-3) + 1e-3).to(device)
     zz = torch.randn(2, Bt, a_dim, generator=g).to(device)
     grp = (dist.group.WORLD, world) if world > 1 else None
-    use_graph = world == 1   # one CUDA graph per update (all kernels of both roles + clip + Adam + weight re-pack)
+    # N = 1: one CUDA graph per update (all kernels of both roles + clip + Adam + weight re-pack).  N > 1: two graphs
+    # (gradients | clip + Adam + re-pack) with the NCCL all-reduce launched between them, outside of any graph.
+    # FRL_BENCH_NO_GRAPH=1 launches everything from Python instead.
+    use_graph = os.environ.get("FRL_BENCH_NO_GRAPH", "0") != "1"
     opt = FusedAdam([model.net], lr=1e-4, capturable=use_graph)
 
-    def tstep(prec_t):
+    def tstep(prec_t, phase=None, losses=None):
         return train_step([dict(net=model.net, sign=1.0, s=ts, a0=ta, t=tt_[0], noise=zz[0]),
                            dict(net=model.net, sign=-1.0, s=ts, a0=ta, t=tt_[1], noise=zz[1])], opt, 1.0, world=grp,
-                          precision=prec_t)
+                          precision=prec_t, phase=phase, losses=losses)
 
     train_rates = {}
     for prec_t in ("fp32", "fp16"):
         for _ in range(3):
             tstep(prec_t)
         run = lambda: tstep(prec_t)
-        if use_graph:
+        if use_graph and world == 1:
             torch.cuda.synchronize(device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 tstep(prec_t)
             run = graph.replay
+            run()
+        elif use_graph:
+            torch.cuda.synchronize(device)
+            g_grad, g_apply = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_grad):
+                step_losses = tstep(prec_t, phase="grad")
+            with torch.cuda.graph(g_apply):
+                tstep(prec_t, phase="apply", losses=step_losses)
+
+            def run(step_losses=step_losses, g_grad=g_grad, g_apply=g_apply):
+                g_grad.replay()
+                tstep(prec_t, phase="reduce", losses=step_losses)
+                g_apply.replay()
             run()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -471,7 +487,8 @@ def run_ours(args):
         "train": {"metric": "cfm_train_samples_per_sec", "value": train_rate, "unit": "samples/s",
                   "rows_per_step_per_gpu": 2 * Bt, "dtype": "fp16 operands / fp32 accumulate (tcgen05); fp32 clip + Adam",
                   "step": "frl_cfm_loss_grad_pair (both roles stacked: fwd + dgrad + wgrad) + [all-reduce] + frl_clip_adam + weight re-pack"
-                          + ("; replayed as one CUDA graph" if use_graph else ""),
+                          + (("; replayed as one CUDA graph" if world == 1 else
+                              "; two CUDA graphs with the NCCL all-reduce between them") if use_graph else ""),
                   "fp32_ffma_samples_per_sec": train_rates["fp32"],
                   "algorithmic_tflops": train_rate * 3 * f_fwd_train / 1e12,
                   # what bounds it: the per-layer kernels stream fp16 activation tiles through HBM

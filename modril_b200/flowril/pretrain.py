@@ -508,7 +508,8 @@ class FusedAdam(torch.optim.Optimizer):
         self._bind_state()
 
 
-def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=None, precision=None):
+def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=None, precision=None, phase=None,
+               losses=None):
     """One reward-model update on the all-native route (reference flowril.py:311-330):
     zero grads; for each term accumulate rate * d fm_loss / d theta; [regularisers]; [all-reduce];
     clip_grad_norm_(max_norm); Adam.
@@ -528,8 +529,51 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
                                       written back into them
            On return reg["out"] holds loss_anti / loss_stable (device scalars) and grad_anti / grad_stable.
     precision: 'fp32' (FFMA) or 'fp16' (tcgen05 tensor cores) for the CFM terms; default: ``set_train_precision``.
+    phase: None runs the whole update.  'grad' (losses + gradients), 'reduce' (the all-reduce) and 'apply' (regulariser
+           weights, clip, Adam) run one part each, so that a data-parallel loop can capture 'grad' and 'apply' into CUDA
+           graphs and keep the NCCL call between them outside of any graph; pass the 'grad' phase's return value as
+           ``losses=`` to the later phases.
     Returns the per-term loss tensors (device scalars; under DP the local shard's contribution summed over ranks).
     """
+    if phase not in (None, "grad", "reduce", "apply"):
+        raise ValueError(f"unknown phase {phase!r}")
+    ws = 1 if world is None else world[1]
+    if phase in (None, "grad"):
+        losses = _train_step_grad(terms, opt, world, reg, precision)
+        if phase == "grad":
+            return [l.reshape(()) for l in losses]
+    losses = [] if losses is None else list(losses)
+    grads = [net.flat_grad() for net in opt.nets]
+    rout = reg.get("out") if reg is not None else None
+    if phase in (None, "reduce") and world is not None and ws > 1:
+        from ..dist import allreduce_flat
+
+        extra_g = [] if rout is None else [rout[k] for k in ("grad_anti", "grad_stable") if k in rout]
+        extra_l = [] if rout is None else [rout[k] for k in ("loss_anti", "loss_stable") if k in rout]
+        allreduce_flat(grads + extra_g, losses + extra_l, world[0])
+    if phase == "reduce":
+        return [l.reshape(()) for l in losses]
+    if rout is not None:
+        target = reg["net"].flat_grad()
+        for key in ("anti", "stable"):
+            spec = reg.get(key)
+            if spec is None:
+                continue
+            g_reg, l_reg, gate = rout["grad_" + key], rout["loss_" + key], reg.get("gate_" + key)
+            if isinstance(spec, torch.Tensor):
+                _axpy(target, g_reg, 1.0, num=spec.reshape(-1), gate=gate, coef_out=gate)
+            elif isinstance(spec, tuple) and spec[0] == "warmup":
+                _axpy(target, g_reg, float(spec[1]), num=losses[0], den=l_reg.reshape(-1), eps=float(spec[2]),
+                      gate=gate, coef_out=gate)
+            else:
+                _axpy(target, g_reg, float(spec), gate=gate, coef_out=gate)
+    opt.step_flat(grads, max_norm)
+    return [l.reshape(()) for l in losses]
+
+
+def _train_step_grad(terms, opt, world, reg, precision):
+    """Losses and gradients of one update (the part of ``train_step`` before the all-reduce); the regulariser outputs go
+    to reg["out"]."""
     L = _native.lib()
     prec = _train_precision_code(precision)
     seen = []
@@ -591,26 +635,6 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
         rout = reg_losses_native(rnet, reg["s"], reg["a"], reg["t"], reg["probe"], anti=reg.get("anti") is not None,
                                  stable=reg.get("stable") is not None, need_grad=True,
                                  mean_divisor=int(reg["global_rows"]) if reg.get("global_rows") else N * ws)
+    if reg is not None:
         reg["out"] = rout
-    if world is not None and ws > 1:
-        from ..dist import allreduce_flat
-
-        extra_g = [] if rout is None else [rout[k] for k in ("grad_anti", "grad_stable") if k in rout]
-        extra_l = [] if rout is None else [rout[k] for k in ("loss_anti", "loss_stable") if k in rout]
-        allreduce_flat(grads + extra_g, losses + extra_l, world[0])
-    if rout is not None:
-        target = reg["net"].flat_grad()
-        for key in ("anti", "stable"):
-            spec = reg.get(key)
-            if spec is None:
-                continue
-            g_reg, l_reg, gate = rout["grad_" + key], rout["loss_" + key], reg.get("gate_" + key)
-            if isinstance(spec, torch.Tensor):
-                _axpy(target, g_reg, 1.0, num=spec.reshape(-1), gate=gate, coef_out=gate)
-            elif isinstance(spec, tuple) and spec[0] == "warmup":
-                _axpy(target, g_reg, float(spec[1]), num=losses[0], den=l_reg.reshape(-1), eps=float(spec[2]),
-                      gate=gate, coef_out=gate)
-            else:
-                _axpy(target, g_reg, float(spec), gate=gate, coef_out=gate)
-    opt.step_flat(grads, max_norm)
-    return [l.reshape(()) for l in losses]
+    return losses

@@ -227,3 +227,32 @@ def test_torch_optimizer_route_matches_native_route():
                    o2, max_norm=1.0)
     p1, p2 = m1.net.flat_params().cpu().numpy(), m2.net.flat_params().cpu().numpy()
     assert np.abs(p1 - p2).max() <= 1e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_train_step_phases_equal_the_whole_step(precision):
+    """train_step(phase='grad') -> 'reduce' -> 'apply' (the split a data-parallel loop captures into two CUDA graphs
+    around the NCCL call) gives bit-identical losses and weights to the one-call update."""
+    from modril_b200.flowril import FusedAdam, train_step
+
+    spec = cf.NetSpec(11, 3, 256, 4, 2)
+    flat = cf.make_params(spec, 31, 1.0)
+    B = 300
+    s, a = synth.states_actions(71, B, 11, 3)
+    draws = [synth.cfm_draws(72 + k, B, 3) for k in range(2)]
+    models = [build_model(spec, flat) for _ in range(2)]
+    opts = [FusedAdam([m.net], lr=1e-3) for m in models]
+
+    def terms(m):
+        return [dict(net=m.net, sign=sg, s=dev(s), a0=dev(a), t=dev(t), noise=dev(z), rate=r)
+                for (t, z), sg, r in zip(draws, (1.0, -1.0), (1.0, 0.5))]
+
+    for _ in range(3):
+        whole = train_step(terms(models[0]), opts[0], 1.0, precision=precision)
+        part = train_step(terms(models[1]), opts[1], 1.0, precision=precision, phase="grad")
+        part = train_step(terms(models[1]), opts[1], 1.0, precision=precision, phase="reduce", losses=part)
+        part = train_step(terms(models[1]), opts[1], 1.0, precision=precision, phase="apply", losses=part)
+        assert all(torch.equal(x, y) for x, y in zip(whole, part))
+        assert torch.equal(models[0].net.flat_params(), models[1].net.flat_params())
+    with pytest.raises(ValueError):
+        train_step(terms(models[0]), opts[0], 1.0, phase="bogus")
