@@ -1,18 +1,22 @@
-// tcgen05 fused log-density integrator for CTA PAIRS (sm_100a, cta_group::2): the 64-sample / N = 256 design of
-// logprob_tc2.cu with every MMA spanning two SMs.
+// tcgen05 fused log-density integrator for CTA PAIRS (sm_100a, cta_group::2) -- the default tensor-core scoring kernel.
+// It is the 64-sample / N = 256 design of logprob_tc2.cu with every MMA spanning two SMs.
 //
 // logprob_tc2.cu showed that one CTA cannot hold two in-flight 64-sample tiles AND a weight ring deep enough for the lag
 // between them (profiles/r01f_tc2_experiment.md).  Here two CTAs of a cluster form a pair:
 //   * one tcgen05.mma.cta_group::2 (M = 256) multiplies the 128 operand rows of BOTH CTAs with the same weight block, so
 //     a thread of the leader CTA issues for two SMs (half the issue cost per pipe cycle);
-//   * each CTA loads only its N/2 = 128 rows of a weight block (B is split across the pair): 16 KB per [K = 64] block,
-//     so the 80 KB ring holds five blocks, and the B-operand shared-memory bandwidth per SM halves;
-//   * each CTA keeps its own two tiles ("slots"), accumulators (2 x 256 TMEM columns), epilogue warps and producer.
-// Cross-CTA signalling: the peer's epilogue warps arrive on the leader's a_ready barriers through DSMEM
-// (mapa + mbarrier.arrive.release.cluster), a forwarder thread in the peer relays "my half of the weight block has
-// landed", and tcgen05.commit.cta_group::2 ... multicast::cluster releases ring slots / publishes accumulators in both
-// CTAs at once.  Row layout, 16x256b epilogue and state handling are those of logprob_tc2.cu; reference arithmetic:
-// modril/flowril/pretrain.py:192-214 / :112-134.
+//   * each CTA loads only its N/2 = 128 rows of a weight block (B is split across the pair): 16 KB per [K = 64] block
+//     (+ 4 KB of bias rows in the first block of a layer), four ring slots, and half the B-operand shared-memory
+//     bandwidth per SM;
+//   * each CTA keeps its own two tiles ("slots"), accumulators (2 x 256 TMEM columns), epilogue warps and producer;
+//   * every layer's blocks are streamed once per slot ([layer l for slot 0][layer l for slot 1][layer l + 1 ...]), so a
+//     ring slot is refilled as soon as the MMAs of the slot that read it commit (FRL_TC3_SHARED=1: one shared stream).
+// Cross-CTA signalling: the peer's epilogue warps arrive on the leader's a_ready barriers through DSMEM (mapa + plain
+// mbarrier.arrive.shared::cluster after fence.proxy.async), a relay thread in the peer forwards "my half of the weight
+// block has landed", and tcgen05.commit.cta_group::2 ... multicast::cluster releases ring slots / publishes accumulators
+// in both CTAs at once.  Row layout, 16x256b epilogue and state handling are those of logprob_tc2.cu; reference
+// arithmetic: modril/flowril/pretrain.py:192-214 / :112-134.  Measurements and the optimisation log:
+// profiles/r01h_logprob_tc3_default.md.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
