@@ -51,7 +51,8 @@ enum { EPI_RELU = 0, EPI_MASK = 1, EPI_LOSS = 2 };
 struct LayerParams {
     const uint8_t* a_tiles;     // [tile][K/8][128][8]
     const uint8_t* w_img;       // [K/8][N][8]
-    const float* bias;          // [N] (EPI_RELU, EPI_LOSS)
+    const float* bias;          // [N] (EPI_RELU); EPI_LOSS: bias of head 0 [a_dim] ...
+    const float* bias2;         // ... and of head 1 [a_dim] (null for one head), straight from the flat parameters
     uint8_t* out_tiles;         // [tile][N/8][128][8]
     const uint32_t* mask_bits;  // [tile][N/32][128]: bit c of word (chunk, row) = activation (row, 32*chunk + c) > 0 (EPI_MASK)
     uint32_t* bits_out;         // same layout, written by EPI_RELU for the backward pass (may be null)
@@ -71,9 +72,13 @@ struct LayerParams {
     float* dvsum_partial;   // [n_tiles * 4][N]
 };
 
-// X0 tiles: [tile][K0p/8][128][8];  one thread per (tile, 8-feature chunk, row)
-__global__ void tc_prepare_kernel(const float* __restrict__ s, const float* __restrict__ a0, const float* __restrict__ t,
-                                  const float* __restrict__ noise, uint8_t* __restrict__ X0t, long long B, int n_tiles,
+// X0 tiles: [tile][K0p/8][128][8];  one thread per (tile, 8-feature chunk, row).  Tiles [0, tile_split) hold term 0, the
+// rest term 1 (each term starts on a tile boundary).
+struct PrepTerm {
+    const float *s, *a0, *t, *noise;
+    long long B;
+};
+__global__ void tc_prepare_kernel(PrepTerm term0, PrepTerm term1, int tile_split, uint8_t* __restrict__ X0t, int n_tiles,
                                   int s_dim, int a_dim, int K0p) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int chunks = K0p / 8;
@@ -81,7 +86,14 @@ __global__ void tc_prepare_kernel(const float* __restrict__ s, const float* __re
     const int r = (int)(i % kRows);
     const int kc = (int)((i / kRows) % chunks);
     const long long tile = i / ((long long)kRows * chunks);
-    const long long row = tile * kRows + r;
+    const bool second = tile >= tile_split;
+    const PrepTerm& tm = second ? term1 : term0;
+    const float* __restrict__ s = tm.s;
+    const float* __restrict__ a0 = tm.a0;
+    const float* __restrict__ t = tm.t;
+    const float* __restrict__ noise = tm.noise;
+    const long long B = tm.B;
+    const long long row = (tile - (second ? tile_split : 0)) * kRows + r;
     __half h[8];
     float tt = 0.f;
     if (row < B) tt = t[row];
@@ -133,8 +145,11 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc512(smem_u32(tmem_slot));
-    if (EPI != EPI_MASK)
+    if (EPI == EPI_RELU)
         for (int i = threadIdx.x; i < p.N; i += kLayerThreads) sBias[i] = p.bias[i];
+    if (EPI == EPI_LOSS)   // head columns: [head 0 (a_dim) | head 1 (a_dim) | padding]
+        for (int i = threadIdx.x; i < p.N; i += kLayerThreads)
+            sBias[i] = i < p.a_dim ? p.bias[i] : (i < 2 * p.a_dim && p.bias2 ? p.bias2[i - p.a_dim] : 0.f);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -764,7 +779,6 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     {
         int rcp = ensure_pack(net, PACK_TRAIN, st);   // fp16 GEMM images
         if (rcp != FRL_OK) return rcp;
-        rcp = ensure_pack(net, PACK_F32, st);          // fp32 biases
         if (rcp != FRL_OK) return rcp;
     }
     FRL_REQUIRE(net->pack_train != nullptr, "tensor-core training weights missing");
@@ -824,18 +838,19 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
 
     int n_launch = 0;   // layer kernels alternate their tile order (see LayerParams::reverse)
     // ---- forward ----
-    for (int i = 0; i < n_terms; ++i) {
-        const long long n = (long long)nt_of[i] * (K0p / 8) * kRows;
-        tc_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(terms[i].s, terms[i].a0, terms[i].t, terms[i].noise,
-                                                                      ws + o_x0 + (i ? (size_t)nt_of[0] * tileX : 0), terms[i].B,
-                                                                      nt_of[i], net->cfg.s_dim, A, K0p);
+    {
+        const CfmTerm& t1 = terms[n_terms - 1];
+        const PrepTerm p0{terms[0].s, terms[0].a0, terms[0].t, terms[0].noise, terms[0].B};
+        const PrepTerm p1{t1.s, t1.a0, t1.t, t1.noise, t1.B};
+        const long long n = (long long)nt * (K0p / 8) * kRows;
+        tc_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p0, p1, nt_of[0], ws + o_x0, nt, net->cfg.s_dim, A, K0p);
         FRL_CUDA(cudaGetLastError());
     }
     for (int l = 0; l < depth; ++l) {
         LayerParams p{};
         p.a_tiles = l == 0 ? ws + o_x0 : ws + o_h[l - 1];
         p.w_img = pk + tp.wf[l];
-        p.bias = net->f32.b[l];
+        p.bias = net->params_dev + net->off_b[l];   // biases are read from the flat parameters (no fp32 pack needed)
         p.out_tiles = ws + o_h[l];
         p.bits_out = grad ? reinterpret_cast<uint32_t*>(ws + o_bits[l]) : nullptr;
         p.reverse = (n_launch++) & 1;
@@ -849,7 +864,8 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         LayerParams p{};
         p.a_tiles = ws + o_h[depth - 1];
         p.w_img = pk + tp.whf;
-        p.bias = net->f32.bh;
+        p.bias = net->params_dev + net->off_bh[0];
+        p.bias2 = net->cfg.n_heads == 2 ? net->params_dev + net->off_bh[1] : nullptr;
         p.out_tiles = ws + o_dv;
         p.K = H;
         p.N = NOp;
