@@ -76,6 +76,9 @@ struct frl_net {
     size_t ws_floats = 0;
     // host-staging state for frl_score_host
     void* host_stage = nullptr;
+    void* ws_x0s = nullptr;             // per-launch layer-0 operand images of wide-input nets (logprob_tc3.cu)
+    size_t ws_x0s_bytes = 0;
+    cudaEvent_t x0s_event = nullptr;    // recorded after the launch that reads ws_x0s (the next launch, on any stream, waits)
 };
 
 void frl_host_stage_free(frl_net* net);  // api.cu

@@ -81,6 +81,10 @@ struct Params {
     unsigned long long* trace;   // FRL_TC_TRACE: [4 roles][8192] clock stamps of CTA 0 (timing experiments only)
     uint32_t off_a, off_x0, off_ones, off_bias, off_state, off_rec, off_rrec, off_ring;
     uint32_t x0_bytes, state_floats;   // per slot
+    int x0_in_a;   // wide layer-0 inputs (K0p > 32): no room for a persistent layer-0 operand tile.  The operand is rebuilt inside
+                   // the slot's activation tile every step: one bulk copy of the tile's pre-built image (state columns in
+                   // place, everything else zero; x0s, L2-resident) + the a / t / probe entries from the fp32 state
+    const uint8_t* x0s;   // [tile][K0p/8][128][8] images of the state columns (x0_in_a only)
     Blk blk[kMaxBlocks];
     // Ring order of one Euler step.  Private streams (default): every layer's blocks are streamed twice, once per tile
     // slot -- [layer l for slot 0][layer l for slot 1][layer l+1 for slot 0] ... -- so the two slots run half a period
@@ -243,6 +247,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     auto a_ready = [&](int slot, int ch) { return bar0 + 8u * (3 * kMaxSlots + slot * 2 + ch); };   // leader only
     auto d_full = [&](int slot) { return bar0 + 8u * (3 * kMaxSlots + 4 + slot); };
     auto hand = [&](int slot, int x) { return bar0 + 8u * (3 * kMaxSlots + 6 + slot * 2 + x); };   // leader only
+    auto x0_full = [&](int slot) { return bar0 + 8u * (3 * kMaxSlots + 10 + slot); };   // wide inputs: operand image has landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
 
     constexpr uint32_t a_tile_bytes = (uint32_t)H * kRows * 2;   // 64 KB per slot
@@ -271,6 +276,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
             mbar_init(a_ready(slot, 0), kEpiWarps);   // 4 warps of this column half in each of the two CTAs
             mbar_init(a_ready(slot, 1), kEpiWarps);
             mbar_init(d_full(slot), 1);
+            mbar_init(x0_full(slot), 1);
             mbar_init(hand(slot, 0), 1);
             mbar_init(hand(slot, 1), 1);
         }
@@ -291,7 +297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     for (int i = threadIdx.x; i < 2 * p.n_blocks; i += kThreads) {
         const int slot = i / p.n_blocks, b = i % p.n_blocks;
         const Blk& k = p.blk[b];
-        const uint32_t src = k.src == 0 ? smem_u32(sA) + slot * a_tile_bytes : smem_u32(sX0) + slot * p.x0_bytes;
+        const uint32_t src = (k.src == 0 || p.x0_in_a) ? smem_u32(sA) + slot * a_tile_bytes : smem_u32(sX0) + slot * p.x0_bytes;
         const uint32_t a_lo = (((src + (uint32_t)k.a_koff * kChunk) >> 4) & 0x3FFF) | ((kChunk >> 4) << 16);
         // M = 256 over the pair, N = nrows (each CTA holds nrows / 2 rows of B)
         const uint32_t idesc = (1u << 4) | (Cvt<T16>::kFmt << 7) | (Cvt<T16>::kFmt << 10) | ((uint32_t)(256 >> 4) << 24) |
@@ -437,6 +443,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         Tracer tr;   // role 0: leader CTA's first epilogue warp, role 3: the peer CTA's
         tr.init((lane == 0 && (ew == 0 || ew == p.debug) && cta_rank == 0) ? p.trace : nullptr, ew == 0 ? 0 : 3, 0);
 
+        // wide inputs: start the bulk copy of a tile's state-column image into the slot's activation tile (one thread), and
+        // -- once it has landed -- write the a / t (primal rows) and probe (tangent rows) entries of a sample from the fp32 state
+        uint32_t par_x0[2] = {0, 0};
+        const uint32_t x0_img_bytes = (uint32_t)p.K0p * kRows * 2;
+        auto x0_fetch = [&](int slot, long long tile) {
+            mbar_expect_tx(x0_full(slot), x0_img_bytes);
+            const uint8_t* src = p.x0s + (size_t)tile * x0_img_bytes;
+            for (uint32_t off = 0; off < x0_img_bytes; off += 16384u)
+                bulk_g2s(smem_u32(sA) + slot * a_tile_bytes + off, src + off, min(16384u, x0_img_bytes - off), x0_full(slot));
+        };
+        auto x0_sample = [&](uint8_t* x0, const float* sA_state, const float* sP_state, int srow, int j0, int jstep, bool write_t, float tval) {
+            const int rowp = row_primal(srow);
+            for (int j = j0; j < p.a_dim; j += jstep) {
+                *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + rowp * 16 + (j & 7) * 2) = Cvt<T16>::one(sA_state[j * kSamp + srow]);
+                *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + (rowp + 8) * 16 + (j & 7) * 2) = Cvt<T16>::one(sP_state[j * kSamp + srow]);
+            }
+            if (write_t) *reinterpret_cast<uint16_t*>(x0 + (t_col >> 3) * kChunk + rowp * 16 + (t_col & 7) * 2) = Cvt<T16>::one(tval);
+        };
+
         for (long long quad = cluster_id; quad < n_quads; quad += n_clusters) {
             const int role = (int)(quad % p.n_roles);
             const long long tile0 = 4 * (quad / p.n_roles) + 2 * cta_rank;   // this CTA's two tiles (padding tiles run masked)
@@ -450,6 +475,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                 uint8_t* x0 = sX0 + slot * p.x0_bytes;
                 float* sA_state = sState + slot * p.state_floats;
                 float* sP_state = sA_state + p.a_dim * kSamp;
+                if (p.x0_in_a) {   // fp32 state first, then (after the barrier below) the operand from it
+                    for (int idx = et; idx < kSamp * p.a_dim; idx += kEpiWarps * 32) {
+                        const int r = idx / p.a_dim, c = idx % p.a_dim;
+                        const long long g = row0 + r;
+                        float pr = 0.f;
+                        if (g < p.B) pr = p.basis >= 0 ? (c == p.basis ? 1.f : 0.f) : p.probe[g * p.a_dim + c];
+                        sA_state[c * kSamp + r] = g < p.B ? p.a[g * p.a_dim + c] : 0.f;
+                        sP_state[c * kSamp + r] = pr;
+                    }
+                    log_det[slot][0] = log_det[slot][1] = 0.f;
+                    continue;
+                }
                 for (int idx = et; idx < kSamp * p.s_dim; idx += kEpiWarps * 32) {
                     const int r = idx / p.s_dim, c = idx % p.s_dim;
                     const long long g = row0 + r;
@@ -472,6 +509,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                     *reinterpret_cast<uint16_t*>(x0 + (t_col >> 3) * kChunk + row_primal(et) * 16 + (t_col & 7) * 2) =
                         Cvt<T16>::one(p.t_mid[0]);
                 log_det[slot][0] = log_det[slot][1] = 0.f;
+            }
+            if (p.x0_in_a) {
+                named_sync(1, kEpiWarps * 32);   // the fp32 state of both tiles is complete
+                if (et == 0)
+                    for (int slot = 0; slot < n_slots; ++slot) x0_fetch(slot, tile0 + slot);
+                for (int slot = 0; slot < n_slots; ++slot) {
+                    mbar_wait(x0_full(slot), par_x0[slot]);
+                    par_x0[slot] ^= 1;
+                    const float* sA_state = sState + slot * p.state_floats;
+                    if (et < kSamp) x0_sample(sA + slot * a_tile_bytes, sA_state, sA_state + p.a_dim * kSamp, et, 0, 1, true, p.t_mid[0]);
+                }
             }
             fence_async_smem();
             named_sync(1, kEpiWarps * 32);
@@ -548,9 +596,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                     par_d[slot] ^= 1;
                     tc_fence_after();
                     tr.mark(0x2F0 + slot);
+                    // wide inputs: the activation tile is free (its last reader, the heads MMA, is done): fetch the next step's
+                    // layer-0 operand image while the heads are evaluated
+                    if (p.x0_in_a && step + 1 < p.n_steps && et == 0) x0_fetch(slot, tile0 + slot);
                     {
                         // the heads have only NOp <= 64 columns: the two warps of a lane quarter split its two 16-row groups
-                        uint8_t* x0 = sX0 + slot * p.x0_bytes;
+                        uint8_t* x0 = p.x0_in_a ? sA + slot * a_tile_bytes : sX0 + slot * p.x0_bytes;
                         float* sA_state = sState + slot * p.state_floats;
                         float* sP_state = sA_state + p.a_dim * kSamp;
                         if (ch % (kEpiWarps / 8) == 0) {   // one warp per 16-row group works on the heads
@@ -577,7 +628,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                                             div = fmaf(dv, sP_state[j * kSamp + srow], div);
                                             const float an = sA_state[j * kSamp + srow] + v * p.delta;
                                             sA_state[j * kSamp + srow] = an;
-                                            *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + rowp * 16 + (j & 7) * 2) = Cvt<T16>::one(an);
+                                            if (!p.x0_in_a)
+                                                *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + rowp * 16 + (j & 7) * 2) = Cvt<T16>::one(an);
                                         }
                                     } else {
 #pragma unroll
@@ -588,7 +640,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                                                 div = fmaf(__uint_as_float(vv[4 * k + 2 + e]), sP_state[j * kSamp + srow], div);
                                                 const float an = sA_state[j * kSamp + srow] + v * p.delta;
                                                 sA_state[j * kSamp + srow] = an;
-                                                *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + rowp * 16 + (j & 7) * 2) = Cvt<T16>::one(an);
+                                                if (!p.x0_in_a)
+                                                    *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + rowp * 16 + (j & 7) * 2) = Cvt<T16>::one(an);
                                             }
                                         }
                                     }
@@ -600,15 +653,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                             log_det[slot][grp] -= p.delta * div;
                             __syncwarp();   // the state of this sample (written by its four threads) is complete
                             if (step + 1 < p.n_steps) {
-                                if (tq == 0)
+                                if (tq == 0 && !p.x0_in_a)
                                     *reinterpret_cast<uint16_t*>(x0 + (t_col >> 3) * kChunk + rowp * 16 + (t_col & 7) * 2) =
                                         Cvt<T16>::one(p.t_mid[step + 1]);
                                 if (p.probe_step_stride != 0) {
                                     for (int j = tq; j < p.a_dim; j += 4) {
                                         const float pr = g < p.B ? p.probe[(step + 1) * p.probe_step_stride + g * p.a_dim + j] : 0.f;
                                         sP_state[j * kSamp + srow] = pr;
-                                        *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + (rowp + 8) * 16 + (j & 7) * 2) =
-                                            Cvt<T16>::one(pr);
+                                        if (!p.x0_in_a)
+                                            *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + (rowp + 8) * 16 + (j & 7) * 2) =
+                                                Cvt<T16>::one(pr);
                                     }
                                 }
                             } else if (tq == 0 && g < p.B) {
@@ -626,6 +680,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         }
                     }
                     if (step + 1 < p.n_steps) {
+                        if (p.x0_in_a) {   // the image has landed: this thread's entries of its sample (a, probe; t by the first of the four)
+                            mbar_wait(x0_full(slot), par_x0[slot]);
+                            par_x0[slot] ^= 1;
+                            if (ch % (kEpiWarps / 8) == 0) {
+                                const float* sA_state = sState + slot * p.state_floats;
+                                x0_sample(sA + slot * a_tile_bytes, sA_state, sA_state + p.a_dim * kSamp,
+                                          q * 16 + (ch / (kEpiWarps / 8)) * 8 + tr8, tq, 4, tq == 0, p.t_mid[step + 1]);
+                            }
+                        }
                         tc_fence_before();
                         fence_async_smem();
                         __syncwarp();
@@ -648,6 +711,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     }
 }
 
+// Wide inputs: operand images of the state columns, one per 64-sample tile, in the layout of the layer-0 operand
+// ([K0p/8][128 rows][8]; primal rows carry s in columns [a_dim, a_dim + s_dim), everything else is zero).  Built once per
+// launch; the integrator copies a tile's image into shared memory at every Euler step (L2 hits after the first).
+template <typename T16>
+__global__ void tc3_state_image_kernel(const float* __restrict__ s, uint8_t* __restrict__ img, long long B, long long n_tiles,
+                                       int s_dim, int a_dim, int K0p) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int chunks = K0p / 8;
+    if (i >= n_tiles * chunks * kRows) return;
+    const int rowi = (int)(i % kRows);
+    const int chunk = (int)((i / kRows) % chunks);
+    const long long tile = i / ((long long)kRows * chunks);
+    uint32_t w[4] = {0, 0, 0, 0};
+    if ((rowi & 8) == 0) {
+        const long long g = tile * kSamp + (((rowi >> 4) << 3) | (rowi & 7));
+        if (g < B) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = chunk * 8 + e - a_dim;
+                const uint32_t h = (c >= 0 && c < s_dim) ? Cvt<T16>::one(s[g * s_dim + c]) : 0u;
+                w[e >> 1] |= h << (16 * (e & 1));
+            }
+        }
+    }
+    *reinterpret_cast<uint4*>(img + (size_t)i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // Block stream of one Euler step (shared by the packer and the kernel).  One kernel block = one ring slot of each CTA =
 // one tcgen05.commit: [K = 64][N = 256] for the trunk (each CTA of the pair holds 128 of the 256 rows: 16 KB), the whole
 // (<= 32 column) layer-0 input, or half of the heads' K.  Blk::goff / Blk::bytes describe ONE CTA's half.
@@ -658,7 +748,10 @@ struct Schedule {
 };
 
 static bool supported(const frl_net* net) {
-    return net->cfg.hidden == H && net->d_in_p <= 32 && net->n_out_p <= 64;
+    return net->cfg.hidden == H && net->d_in_p <= 192 && net->n_out_p <= 64;
+}
+static bool wide_inputs(const frl_net* net) {   // the layer-0 operand shares the activation tile (Params::x0_in_a)
+    return net->d_in_p > 32;
 }
 
 // Shared-memory bytes in front of the ring (worst case: two roles), and the plan it leaves room for:
@@ -668,13 +761,13 @@ static bool supported(const frl_net* net) {
 static uint32_t front_bytes(const frl_net* net, int n_roles) {
     uint32_t off = 1024;
     off += 2u * H * kRows * 2;
-    off += 2u * (uint32_t)net->d_in_p * kRows * 2;
+    if (!wide_inputs(net)) off += 2u * (uint32_t)net->d_in_p * kRows * 2;
     off += 2u * kRows * 16;
     off += (uint32_t)(n_roles * net->n_out_p) * 4;
     off = (off + 15) / 16 * 16;
     off += 2u * (2u * net->cfg.a_dim * kSamp) * 4;
     off = (off + 15) / 16 * 16;
-    off += 5u * (uint32_t)(5 * net->cfg.depth + 3) * 16;   // issue + ring records (upper bound on the block count)
+    off += 5u * (uint32_t)(5 * net->cfg.depth + 6) * 16;   // issue + ring records (upper bound on the block count)
     return (off + 1023) / 1024 * 1024;
 }
 static int choose_plan(const frl_net* net) {
@@ -707,7 +800,16 @@ static Schedule make_schedule(const frl_net* net) {
     };
     // the accumulator-overwriting first block of every layer waits a_ready[slot][0] and [1]: both column halves of the
     // previous epilogue (in both CTAs) have drained the accumulator and written the whole operand
-    add(0, H, 0, K0p, 0, 1, 1, 1, 1, 3);
+    if (!wide_inputs(net)) {
+        add(0, H, 0, K0p, 0, 1, 1, 1, 1, 3);
+    } else {   // layer 0 in ring-slot sized pieces: [bias16 + K64 | K48] [K64] ...
+        const int first_k = plan == 0 ? 64 : 48;
+        for (int k0 = 0; k0 < K0p;) {
+            const int klen = std::min(k0 == 0 ? first_k : 64, K0p - k0);
+            add(0, H, k0, klen, k0 / 8, 1, k0 == 0, k0 == 0, k0 + klen >= K0p, k0 == 0 ? 3 : 0);
+            k0 += klen;
+        }
+    }
     for (int l = 1; l < depth; ++l) {
         if (plan == 0) {
             for (int k0 = 0; k0 < H; k0 += 64) add(l, H, k0, 64, k0 / 8, 0, k0 == 0, k0 == 0, k0 + 64 >= H, k0 == 0 ? 3 : 0);
@@ -823,7 +925,8 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
 
     uint32_t off = 1024;   // barriers + TMEM slot
     p.off_a = off; off += 2u * H * kRows * 2;
-    p.x0_bytes = (uint32_t)p.K0p * kRows * 2;
+    p.x0_in_a = wide_inputs(n0) ? 1 : 0;
+    p.x0_bytes = p.x0_in_a ? 0u : (uint32_t)p.K0p * kRows * 2;
     p.off_x0 = off; off += 2u * p.x0_bytes;
     p.off_ones = off; off += 2u * kRows * 16;
     p.off_bias = off; off += (uint32_t)(a.n_roles * n0->n_out_p) * 4;
@@ -850,9 +953,38 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
     const long long n_quads = ((tiles_per_role + 3) / 4) * a.n_roles;
     const int grid = 2 * (int)std::min<long long>(n_quads, sms / 2);   // clusters of two CTAs
 
+    if (p.x0_in_a) {
+        const long long img_tiles = ((tiles_per_role + 3) / 4) * 4;   // padding tiles of the last quad included
+        const size_t img_bytes = (size_t)p.K0p * kRows * 2, need = (size_t)img_tiles * img_bytes;
+        frl_net* nm = const_cast<frl_net*>(n0);
+        if (nm->ws_x0s_bytes < need) {
+            if (nm->ws_x0s) FRL_CUDA(cudaFree(nm->ws_x0s));   // synchronises: earlier launches are done with it
+            nm->ws_x0s = nullptr;
+            nm->ws_x0s_bytes = 0;
+            FRL_CUDA(cudaMalloc(&nm->ws_x0s, need));
+            nm->ws_x0s_bytes = need;
+        }
+        // the images are per launch: a launch on another stream (frl_score_host alternates two) waits for the previous reader
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        FRL_CUDA(cudaStreamIsCapturing(stream, &cap));
+        if (!nm->x0s_event) FRL_CUDA(cudaEventCreateWithFlags(&nm->x0s_event, cudaEventDisableTiming));
+        else if (cap == cudaStreamCaptureStatusNone) FRL_CUDA(cudaStreamWaitEvent(stream, nm->x0s_event, 0));
+        const long long n_items = img_tiles * (p.K0p / 8) * kRows;
+        const unsigned blocks = (unsigned)((n_items + 255) / 256);
+        if (f16) tc3_state_image_kernel<__half><<<blocks, 256, 0, stream>>>(a.s, static_cast<uint8_t*>(nm->ws_x0s), a.B, img_tiles, p.s_dim, p.a_dim, p.K0p);
+        else tc3_state_image_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(a.s, static_cast<uint8_t*>(nm->ws_x0s), a.B, img_tiles, p.s_dim, p.a_dim, p.K0p);
+        FRL_CUDA(cudaGetLastError());
+        p.x0s = static_cast<const uint8_t*>(nm->ws_x0s);
+    }
     auto run = [&](const Params& q) {
-        return f16 ? launch_tc3<__half>(q, smem_bytes, grid, n0->cfg.device, stream)
-                   : launch_tc3<__nv_bfloat16>(q, smem_bytes, grid, n0->cfg.device, stream);
+        int rc = f16 ? launch_tc3<__half>(q, smem_bytes, grid, n0->cfg.device, stream)
+                     : launch_tc3<__nv_bfloat16>(q, smem_bytes, grid, n0->cfg.device, stream);
+        if (rc == FRL_OK && q.x0_in_a) {
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            FRL_CUDA(cudaStreamIsCapturing(stream, &cap));
+            if (cap == cudaStreamCaptureStatusNone) FRL_CUDA(cudaEventRecord(n0->x0s_event, stream));
+        }
+        return rc;
     };
     if (const char* tp = getenv("FRL_TC_TRACE")) {
         // timing experiment: stamp CTA 0's roles with clock64 and dump them (synchronises!)

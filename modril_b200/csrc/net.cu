@@ -132,6 +132,8 @@ extern "C" int frl_net_destroy(frl_net* net) {
     for (int k = 0; k < 5; ++k)
         if (net->pack_event[k]) cudaEventDestroy(net->pack_event[k]);
     if (net->ws_tc) cudaFree(net->ws_tc);
+    if (net->ws_x0s) cudaFree(net->ws_x0s);
+    if (net->x0s_event) cudaEventDestroy(net->x0s_event);
     frl_host_stage_free(net);
     delete net;
     return FRL_OK;

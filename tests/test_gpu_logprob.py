@@ -310,7 +310,9 @@ def test_baseline_full_sizes_tensor_core_properties(task, B, n_steps):
 
 
 @pytest.mark.parametrize("task,B,n_steps,mode", [("maze", 4097, 20, "fp16"), ("hopper", 20000, 32, "bf16"),
-                                                 ("sine", 130, 8, "fp16"), ("pick", 9000, 32, "fp16")])
+                                                 ("sine", 130, 8, "fp16"), ("pick", 9000, 32, "fp16"),
+                                                 ("ant", 5000, 12, "fp16"), ("hand", 3000, 8, "bf16"),
+                                                 ("ant111", 700, 5, "fp16")])
 def test_cta_pair_integrator_is_bit_identical_to_single_cta_kernel(task, B, n_steps, mode, monkeypatch):
     """The default tensor-core kernel (CTA pairs, tcgen05 cta_group::2, csrc/logprob_tc3.cu) performs exactly the
     arithmetic of the 128-sample single-CTA kernel (FRL_TC_V1=1, csrc/logprob_tc.cu) -- same operand rounding, same
