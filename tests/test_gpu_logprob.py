@@ -354,3 +354,19 @@ def test_private_and_shared_weight_streams_agree_bit_for_bit(task, B, n_steps, m
     monkeypatch.delenv("FRL_TC3_SHARED")
     for g, r in zip(got, ref):
         assert torch.equal(g, r)
+
+
+def test_score_host_wide_inputs_two_chunks():
+    """Wide-input nets keep per-launch operand images in the handle; the host entry point alternates two streams over
+    its 262144-row chunks, so the second chunk's images must wait for the first chunk's kernel (event in the handle)."""
+    from modril_b200.flowril import score_pair_host
+    spec = cf.NetSpec(132, 8, 256, 4, 2)
+    m = build_model(spec, cf.make_params(spec, 24, 1.0))
+    B, n = 262144 + 70001, 3
+    s, a = synth.states_actions(45, B, 132, 8)
+    probe = synth.rademacher(46, (B, 8))
+    ref = m.score(dev(s), dev(a), n_steps=n, probe=dev(probe), precision="fp16")
+    outs = score_pair_host(m.net, m.net, torch.from_numpy(s).pin_memory(), torch.from_numpy(a).pin_memory(),
+                           torch.from_numpy(probe).pin_memory(), n_steps=n, precision="fp16")
+    for got, want in zip(outs, ref):
+        assert torch.equal(got, want.cpu())
