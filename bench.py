@@ -480,7 +480,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(world * B * (s_dim + 2 * a_dim) * 4),
                 "d2h_bytes_per_step": int(world * B * 3 * 4), "api": "frl_score_host via score_pair_host, pinned host buffers",
                 "max_abs_diff_vs_device_path": e2e_check},
-        "gpu_launches": 2 * args.steps,
+        # per step: the fused integrator + the reward transform (+ the state-image pre-pass of wide-input nets)
+        "gpu_launches": (3 if (prec != "fp32" and -(-(s_dim + a_dim + 1) // 16) * 16 > 32) else 2) * args.steps,
         "clocks": clocks.summary(),
         "parity": parity,
         "other_modes_samples_per_sec": extra,
