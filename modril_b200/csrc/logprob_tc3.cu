@@ -238,7 +238,9 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
                  : "memory");
 }
 
-template <typename T16>
+// WIDE: the wide-input mode (Params::x0_in_a) is a separate instantiation, so the common narrow-input kernel carries none
+// of its code or registers.
+template <typename T16, bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob_tc3_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem);
@@ -297,7 +299,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     for (int i = threadIdx.x; i < 2 * p.n_blocks; i += kThreads) {
         const int slot = i / p.n_blocks, b = i % p.n_blocks;
         const Blk& k = p.blk[b];
-        const uint32_t src = (k.src == 0 || p.x0_in_a) ? smem_u32(sA) + slot * a_tile_bytes : smem_u32(sX0) + slot * p.x0_bytes;
+        const uint32_t src = (k.src == 0 || WIDE) ? smem_u32(sA) + slot * a_tile_bytes : smem_u32(sX0) + slot * p.x0_bytes;
         const uint32_t a_lo = (((src + (uint32_t)k.a_koff * kChunk) >> 4) & 0x3FFF) | ((kChunk >> 4) << 16);
         // M = 256 over the pair, N = nrows (each CTA holds nrows / 2 rows of B)
         const uint32_t idesc = (1u << 4) | (Cvt<T16>::kFmt << 7) | (Cvt<T16>::kFmt << 10) | ((uint32_t)(256 >> 4) << 24) |
@@ -475,7 +477,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                 uint8_t* x0 = sX0 + slot * p.x0_bytes;
                 float* sA_state = sState + slot * p.state_floats;
                 float* sP_state = sA_state + p.a_dim * kSamp;
-                if (p.x0_in_a) {   // fp32 state first, then (after the barrier below) the operand from it
+                if (WIDE) {   // fp32 state first, then (after the barrier below) the operand from it
                     for (int idx = et; idx < kSamp * p.a_dim; idx += kEpiWarps * 32) {
                         const int r = idx / p.a_dim, c = idx % p.a_dim;
                         const long long g = row0 + r;
@@ -510,7 +512,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         Cvt<T16>::one(p.t_mid[0]);
                 log_det[slot][0] = log_det[slot][1] = 0.f;
             }
-            if (p.x0_in_a) {
+            if (WIDE) {
                 named_sync(1, kEpiWarps * 32);   // the fp32 state of both tiles is complete
                 if (et == 0)
                     for (int slot = 0; slot < n_slots; ++slot) x0_fetch(slot, tile0 + slot);
@@ -598,10 +600,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                     tr.mark(0x2F0 + slot);
                     // wide inputs: the activation tile is free (its last reader, the heads MMA, is done): fetch the next step's
                     // layer-0 operand image while the heads are evaluated
-                    if (p.x0_in_a && step + 1 < p.n_steps && et == 0) x0_fetch(slot, tile0 + slot);
+                    if (WIDE && step + 1 < p.n_steps && et == 0) x0_fetch(slot, tile0 + slot);
                     {
                         // the heads have only NOp <= 64 columns: the two warps of a lane quarter split its two 16-row groups
-                        uint8_t* x0 = p.x0_in_a ? sA + slot * a_tile_bytes : sX0 + slot * p.x0_bytes;
+                        uint8_t* x0 = WIDE ? sA + slot * a_tile_bytes : sX0 + slot * p.x0_bytes;
                         float* sA_state = sState + slot * p.state_floats;
                         float* sP_state = sA_state + p.a_dim * kSamp;
                         if (ch % (kEpiWarps / 8) == 0) {   // one warp per 16-row group works on the heads
@@ -628,7 +630,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                                             div = fmaf(dv, sP_state[j * kSamp + srow], div);
                                             const float an = sA_state[j * kSamp + srow] + v * p.delta;
                                             sA_state[j * kSamp + srow] = an;
-                                            if (!p.x0_in_a)
+                                            if (!WIDE)
                                                 *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + rowp * 16 + (j & 7) * 2) = Cvt<T16>::one(an);
                                         }
                                     } else {
@@ -640,7 +642,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                                                 div = fmaf(__uint_as_float(vv[4 * k + 2 + e]), sP_state[j * kSamp + srow], div);
                                                 const float an = sA_state[j * kSamp + srow] + v * p.delta;
                                                 sA_state[j * kSamp + srow] = an;
-                                                if (!p.x0_in_a)
+                                                if (!WIDE)
                                                     *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + rowp * 16 + (j & 7) * 2) = Cvt<T16>::one(an);
                                             }
                                         }
@@ -653,14 +655,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                             log_det[slot][grp] -= p.delta * div;
                             __syncwarp();   // the state of this sample (written by its four threads) is complete
                             if (step + 1 < p.n_steps) {
-                                if (tq == 0 && !p.x0_in_a)
+                                if (tq == 0 && !WIDE)
                                     *reinterpret_cast<uint16_t*>(x0 + (t_col >> 3) * kChunk + rowp * 16 + (t_col & 7) * 2) =
                                         Cvt<T16>::one(p.t_mid[step + 1]);
                                 if (p.probe_step_stride != 0) {
                                     for (int j = tq; j < p.a_dim; j += 4) {
                                         const float pr = g < p.B ? p.probe[(step + 1) * p.probe_step_stride + g * p.a_dim + j] : 0.f;
                                         sP_state[j * kSamp + srow] = pr;
-                                        if (!p.x0_in_a)
+                                        if (!WIDE)
                                             *reinterpret_cast<uint16_t*>(x0 + (j >> 3) * kChunk + (rowp + 8) * 16 + (j & 7) * 2) =
                                                 Cvt<T16>::one(pr);
                                     }
@@ -680,7 +682,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         }
                     }
                     if (step + 1 < p.n_steps) {
-                        if (p.x0_in_a) {   // the image has landed: this thread's entries of its sample (a, probe; t by the first of the four)
+                        if (WIDE) {   // the image has landed: this thread's entries of its sample (a, probe; t by the first of the four)
                             mbar_wait(x0_full(slot), par_x0[slot]);
                             par_x0[slot] ^= 1;
                             if (ch % (kEpiWarps / 8) == 0) {
@@ -849,9 +851,9 @@ int tc3_pack(frl_net* net, const float* params_dev, cudaStream_t stream) {
     return FRL_OK;
 }
 
-template <typename T16>
+template <typename T16, bool WIDE>
 static int launch_tc3(const tc3::Params& p, size_t smem_bytes, int grid, int device, cudaStream_t stream) {
-    auto kern = tc3::logprob_tc3_kernel<T16>;
+    auto kern = tc3::logprob_tc3_kernel<T16, WIDE>;
     static std::mutex mu;
     static bool done[64] = {};
     {
@@ -977,8 +979,13 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
         p.x0s = static_cast<const uint8_t*>(nm->ws_x0s);
     }
     auto run = [&](const Params& q) {
-        int rc = f16 ? launch_tc3<__half>(q, smem_bytes, grid, n0->cfg.device, stream)
-                     : launch_tc3<__nv_bfloat16>(q, smem_bytes, grid, n0->cfg.device, stream);
+        int rc;
+        if (q.x0_in_a)
+            rc = f16 ? launch_tc3<__half, true>(q, smem_bytes, grid, n0->cfg.device, stream)
+                     : launch_tc3<__nv_bfloat16, true>(q, smem_bytes, grid, n0->cfg.device, stream);
+        else
+            rc = f16 ? launch_tc3<__half, false>(q, smem_bytes, grid, n0->cfg.device, stream)
+                     : launch_tc3<__nv_bfloat16, false>(q, smem_bytes, grid, n0->cfg.device, stream);
         if (rc == FRL_OK && q.x0_in_a) {
             cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
             FRL_CUDA(cudaStreamIsCapturing(stream, &cap));
