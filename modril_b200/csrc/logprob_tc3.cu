@@ -42,6 +42,7 @@ constexpr int kEpiWarps = FRL_TC3_EPI_WARPS;   // 8 or 16: four lane quarters x 
 constexpr int kColW = 256 / (kEpiWarps / 4);    // accumulator columns per epilogue warp (128 or 64)
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // warp 0 producer, warps 1-4 MMA issuers (2 per slot), warp 5 TMEM owner / peer relay, epilogue warps
 constexpr int kSlotBytesA = 20480;  // plan A ring slot = this CTA's half of one weight block: [16 bias rows +] K = 64 rows of 128
+constexpr int kSlotBytesH = 18432;  // halves plan: [16 bias rows +] K = 128 rows of 64
 constexpr int kSlotBytesB = 16384;  // plan B (wider layer-0 inputs leave less room): blocks of at most 64 rows
 constexpr int kMaxSlots = 16;
 constexpr int kRows = 128;      // rows of the UMMA operand
@@ -56,10 +57,12 @@ struct Blk {
     uint8_t n_k16;      // K = 16 MMAs
     uint8_t src;        // A operand: 0 activations, 1 layer-0 input
     uint8_t first;      // first MMA overwrites the accumulator
-    uint8_t commit;     // last block of a layer: commit d_full
+    uint8_t commit;     // last block of a layer / accumulator half: bit 0 / bit 1 = commit d_full[0] / d_full[1];
+                        // bit 2 = commit ka_done (halves plan: the last block of the layer that reads operand columns < 128)
     uint8_t wait;       // bit0 / bit1: wait a_ready[slot][0 / 1] before issuing
     uint8_t bias;       // the block starts with 16 bias rows: first MMA = ones tile x bias rows, overwrites the accumulator
-    uint8_t pad[2];
+    uint8_t dhalf;      // accumulator half (TMEM column offset 128 * dhalf) the block accumulates into / commits
+    uint8_t pad[1];
 };
 
 struct Params {
@@ -74,6 +77,7 @@ struct Params {
     long long B;
     int n_roles, n_heads, depth, s_dim, a_dim, K0p, NOp;
     int n_steps, basis, accumulate, n_blocks, n_stages;
+    int halves;   // trunk layers run as two N = 128 accumulator halves with their own d_full barriers (see make_schedule)
     float delta;
     uint32_t slot_bytes;         // ring slot size of the plan in use
     int debug;                   // FRL_TC_DEBUG (timing experiments): 8 skip epilogue stores, 16 skip the bias add
@@ -247,9 +251,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     auto w_full = [&](int s) { return bar0 + 8u * s; };                    // own half of the block has landed (tx)
     auto w_empty = [&](int s) { return bar0 + 8u * (2 * kMaxSlots + s); }; // both issuers' MMAs on the slot completed
     auto a_ready = [&](int slot, int ch) { return bar0 + 8u * (3 * kMaxSlots + slot * 2 + ch); };   // leader only
-    auto d_full = [&](int slot) { return bar0 + 8u * (3 * kMaxSlots + 4 + slot); };
+    auto d_full = [&](int slot, int half) { return bar0 + 8u * (3 * kMaxSlots + (half ? 12 : 4) + slot); };
     auto hand = [&](int slot, int x) { return bar0 + 8u * (3 * kMaxSlots + 6 + slot * 2 + x); };   // leader only
     auto x0_full = [&](int slot) { return bar0 + 8u * (3 * kMaxSlots + 10 + slot); };   // wide inputs: operand image has landed
+    // halves plan: the layer's MMAs no longer read operand columns 0..127, so the epilogue of half 0 may overwrite them (the
+    // activation tile is updated in place while the MMAs of half 1 are still running)
+    auto ka_done = [&](int slot) { return bar0 + 8u * (3 * kMaxSlots + 14 + slot); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
 
     constexpr uint32_t a_tile_bytes = (uint32_t)H * kRows * 2;   // 64 KB per slot
@@ -277,7 +284,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         for (int slot = 0; slot < 2; ++slot) {
             mbar_init(a_ready(slot, 0), kEpiWarps);   // 4 warps of this column half in each of the two CTAs
             mbar_init(a_ready(slot, 1), kEpiWarps);
-            mbar_init(d_full(slot), 1);
+            mbar_init(d_full(slot, 0), 1);
+            mbar_init(d_full(slot, 1), 1);
+            mbar_init(ka_done(slot), 1);
             mbar_init(x0_full(slot), 1);
             mbar_init(hand(slot, 0), 1);
             mbar_init(hand(slot, 1), 1);
@@ -304,8 +313,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         // M = 256 over the pair, N = nrows (each CTA holds nrows / 2 rows of B)
         const uint32_t idesc = (1u << 4) | (Cvt<T16>::kFmt << 7) | (Cvt<T16>::kFmt << 10) | ((uint32_t)(256 >> 4) << 24) |
                                ((uint32_t)(k.nrows >> 3) << 17);
-        sRec[2 * i] = make_uint4(a_lo, idesc, (uint32_t)k.nrows | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24),
-                                 (uint32_t)slot * 256);
+        sRec[2 * i] = make_uint4(a_lo, idesc,
+                                 (uint32_t)k.nrows | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24),
+                                 (uint32_t)slot * 256 + (uint32_t)k.dhalf * 128);
         const uint32_t pos = p.ring_pos[slot][b];   // ring position inside a step, as (wraps, stage) of the ring
         sRec[2 * i + 1] = make_uint4((uint32_t)k.n_k16 | ((uint32_t)k.first << 8) | ((uint32_t)k.bias << 16),
                                      ((smem_u32(sOnes) >> 4) & 0x3FFF) | ((kChunk >> 4) << 16),
@@ -420,7 +430,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                             }
                             mbar_arrive(hand(slot, x ^ 1));
                             umma2_commit_both(w_empty(stage));
-                            if ((r0.z >> 16) & 0xFF) umma2_commit_both(d_full(slot));
+                            const uint32_t cm = (r0.z >> 16) & 0xFF;
+                            if (cm & 4) umma2_commit_both(ka_done(slot));
+                            if (cm & 1) umma2_commit_both(d_full(slot, 0));
+                            if (cm & 2) umma2_commit_both(d_full(slot, 1));
                             tr.mark(0x400 + b);
                         }
                     }
@@ -440,7 +453,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         const int tq = lane & 3, tr8 = lane >> 2;   // position inside the 16x256b fragment: column pair, row
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         const int t_col = p.a_dim + p.s_dim;
-        uint32_t par_d[2] = {0, 0};
+        uint32_t par_d[2] = {0, 0}, par_k[2] = {0, 0};
+        // halves mode: this warp drains accumulator half `ah` and follows d_full[ah] only (the heads commit both barriers, so
+        // no warp ever skips a phase of the barrier it waits on)
+        const int dh = p.halves ? ah : 0;
         float log_det[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [slot][16-row group]
         Tracer tr;   // role 0: leader CTA's first epilogue warp, role 3: the peer CTA's
         tr.init((lane == 0 && (ew == 0 || ew == p.debug) && cta_rank == 0) ? p.trace : nullptr, ew == 0 ? 0 : 3, 0);
@@ -533,7 +549,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                 for (int l = 0; l < p.depth; ++l) {
                     for (int slot = 0; slot < n_slots; ++slot) {
                         tr.mark(0x100 + l * 2 + slot);
-                        mbar_wait(d_full(slot), par_d[slot]);
+                        mbar_wait(d_full(slot, dh), par_d[slot]);
                         par_d[slot] ^= 1;
                         tc_fence_after();
                         tr.mark(0x200 + l * 2 + slot);
@@ -577,6 +593,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         for (int half = 0; half < kHalves; ++half) tmem_ld_wait_dep(z[0][half]);
                         tr.mark(0x500 + l * 2 + slot);
                         load_grp(1);
+                        if (p.halves && ah == 0) {   // in-place update: wait until half 1's MMAs are past operand columns 0..127
+                            mbar_wait(ka_done(slot), par_k[slot]);
+                            par_k[slot] ^= 1;
+                        }
                         store_grp(0);
                         tr.mark(0x600 + l * 2 + slot);
 #pragma unroll
@@ -594,7 +614,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                 // ---- heads: tanh, divergence, Euler update (pretrain.py:205-211) ----
                 for (int slot = 0; slot < n_slots; ++slot) {
                     tr.mark(0x1F0 + slot);
-                    mbar_wait(d_full(slot), par_d[slot]);
+                    mbar_wait(d_full(slot, dh), par_d[slot]);
                     par_d[slot] ^= 1;
                     tc_fence_after();
                     tr.mark(0x2F0 + slot);
@@ -752,57 +772,95 @@ struct Schedule {
 static bool supported(const frl_net* net) {
     return net->cfg.hidden == H && net->d_in_p <= 192 && net->n_out_p <= 64;
 }
-static bool wide_inputs(const frl_net* net) {   // the layer-0 operand shares the activation tile (Params::x0_in_a)
-    return net->d_in_p > 32;
-}
-
-// Shared-memory bytes in front of the ring (worst case: two roles), and the plan it leaves room for:
-//   plan A: four 20 KB slots, trunk layer = 4 blocks  [bias16 + K64] [K64] [K64] [K64]
-//   plan B: four 16 KB slots, trunk layer = 5 blocks  [bias16 + K48] [K64] [K64] [K64] [K16]
+// Shared-memory layout of a net: the weight-stream plan and whether the layer-0 operand shares the activation tile
+// (Params::x0_in_a: needed when it is wider than 32 columns, and chosen when dropping the separate tiles is what makes the
+// halves plan fit).  Plans:
+//   halves: four 18 KB slots, trunk layer = 4 blocks of N = 128  [h0: bias16 + K128 | K128] [h1: bias16 + K128 | K128]
+//   A:      four 20 KB slots, trunk layer = 4 blocks of N = 256  [bias16 + K64] [K64] [K64] [K64]
+//   B:      four 16 KB slots, trunk layer = 5 blocks of N = 256  [bias16 + K48] [K64] [K64] [K64] [K16]
 // The choice depends only on the net's dimensions, so the packer and every launch agree.
-static uint32_t front_bytes(const frl_net* net, int n_roles) {
+struct Layout {
+    int plan;    // 2 halves, 0 A, 1 B, -1 none (the caller falls back to the single-CTA kernel)
+    bool wide;
+};
+static int block_count(const frl_net* net, int plan, bool wide) {
+    const int depth = net->cfg.depth, K0p = net->d_in_p;
+    if (plan == 2) return 2 * ((K0p + 127) / 128) + 4 * (depth - 1) + 2;
+    const int first_k = plan == 0 ? 64 : 48;
+    const int l0 = wide ? 1 + (std::max(0, K0p - first_k) + 63) / 64 : 1;
+    return l0 + (plan == 0 ? 4 : 5) * (depth - 1) + 2;
+}
+static uint32_t front_bytes(const frl_net* net, int n_roles, int plan, bool wide) {
     uint32_t off = 1024;
     off += 2u * H * kRows * 2;
-    if (!wide_inputs(net)) off += 2u * (uint32_t)net->d_in_p * kRows * 2;
+    if (!wide) off += 2u * (uint32_t)net->d_in_p * kRows * 2;
     off += 2u * kRows * 16;
     off += (uint32_t)(n_roles * net->n_out_p) * 4;
     off = (off + 15) / 16 * 16;
     off += 2u * (2u * net->cfg.a_dim * kSamp) * 4;
     off = (off + 15) / 16 * 16;
-    off += 5u * (uint32_t)(5 * net->cfg.depth + 6) * 16;   // issue + ring records (upper bound on the block count)
+    off += (uint32_t)block_count(net, plan, wide) * (4u * 16 + 8);   // issue records (2 slots x 2 uint4) + producer records
     return (off + 1023) / 1024 * 1024;
 }
-static int choose_plan(const frl_net* net) {
+static Layout choose_layout(const frl_net* net) {
     const uint32_t max_smem = 232448;   // sm_100a opt-in maximum of dynamic shared memory per CTA
-    const uint32_t front = front_bytes(net, 2);
-    if (const char* force = getenv("FRL_TC3_PLAN")) return atoi(force);   // experiments only
-    if (front + 4u * kSlotBytesA <= max_smem) return 0;
-    if (front + 4u * kSlotBytesB <= max_smem) return 1;
-    return -1;
+    const bool must_wide = net->d_in_p > 32;
+    if (const char* force = getenv("FRL_TC3_PLAN")) return Layout{atoi(force), must_wide};   // experiments only
+    if (!must_wide && front_bytes(net, 2, 2, false) + 4u * kSlotBytesH <= max_smem) return Layout{2, false};
+    if (front_bytes(net, 2, 2, true) + 4u * kSlotBytesH <= max_smem) return Layout{2, true};
+    if (front_bytes(net, 2, 0, must_wide) + 4u * kSlotBytesA <= max_smem) return Layout{0, must_wide};
+    if (front_bytes(net, 2, 1, must_wide) + 4u * kSlotBytesB <= max_smem) return Layout{1, must_wide};
+    return Layout{-1, must_wide};
 }
 
 static Schedule make_schedule(const frl_net* net) {
     Schedule sc;
     const int depth = net->cfg.depth, K0p = net->d_in_p, NOp = net->n_out_p;
-    const int plan = choose_plan(net);
+    const Layout lay = choose_layout(net);
+    const int plan = lay.plan;
     uint32_t goff = 0;
-    auto add = [&](int layer, int nrows, int k0, int klen, int a_koff, int src, int bias, int first, int commit, int wait) {
+    // n_base: first output feature of the block (both CTAs together hold features n_base .. n_base + nrows - 1, rank r the
+    // r-th half of them); dhalf: accumulator half
+    auto add = [&](int layer, int nrows, int k0, int klen, int a_koff, int src, int bias, int first, int commit, int wait,
+                   int n_base = 0, int dhalf = 0) {
         Blk b{};
         b.goff = goff; b.nrows = (uint16_t)nrows; b.a_koff = (uint16_t)a_koff;
         b.n_k16 = (uint8_t)(klen / 16); b.src = (uint8_t)src; b.first = (uint8_t)first; b.commit = (uint8_t)commit;
-        b.wait = (uint8_t)wait; b.bias = (uint8_t)bias;
+        b.wait = (uint8_t)wait; b.bias = (uint8_t)bias; b.dhalf = (uint8_t)dhalf;
         if (bias) {
-            for (int r = 0; r < 2; ++r) sc.pack[r].push_back(tc::PackBlk{goff, nrows / 2, 16, r * (nrows / 2), -1, layer});
+            for (int r = 0; r < 2; ++r) sc.pack[r].push_back(tc::PackBlk{goff, nrows / 2, 16, n_base + r * (nrows / 2), -1, layer});
             goff += (uint32_t)(nrows / 2) * 16 * 2;
         }
-        for (int r = 0; r < 2; ++r) sc.pack[r].push_back(tc::PackBlk{goff, nrows / 2, klen, r * (nrows / 2), k0, layer});
+        for (int r = 0; r < 2; ++r) sc.pack[r].push_back(tc::PackBlk{goff, nrows / 2, klen, n_base + r * (nrows / 2), k0, layer});
         goff += (uint32_t)(nrows / 2) * klen * 2;
         b.bytes = goff - b.goff;
         sc.blk.push_back(b);
     };
     // the accumulator-overwriting first block of every layer waits a_ready[slot][0] and [1]: both column halves of the
     // previous epilogue (in both CTAs) have drained the accumulator and written the whole operand
-    if (!wide_inputs(net)) {
+    if (plan == 2) {
+        // Halves: every trunk layer runs as two N = 128 accumulator halves (output features 0..127 / 128..255), each with
+        // its own d_full barrier, in K = 128 blocks: [h0: K 0..127 | K 128..255] [h1: K 0..127 | K 128..255].  The epilogue
+        // warps of half 0 drain it while the MMAs of half 1 run, and the next layer's first block (h0, K 0..127: it needs
+        // only the activations and the accumulator columns of half 0) starts while half 1 is still being drained.
+        for (int h = 0; h < 2; ++h)   // layer 0: the whole (narrow) input, or K = 128 pieces of a wide one
+            for (int k0 = 0; k0 < K0p; k0 += 128) {
+                const int klen = std::min(128, K0p - k0);
+                add(0, 128, k0, klen, k0 / 8, 1, k0 == 0, k0 == 0, (k0 + klen >= K0p ? 1 << h : 0) | ((h == 1 && k0 == 0) ? 4 : 0),
+                    (h == 0 && k0 == 0) ? 3 : 0, 128 * h, h);
+            }
+        for (int l = 1; l < depth; ++l) {
+            for (int h = 0; h < 2; ++h)
+                for (int k0 = 0; k0 < H; k0 += 128)
+                    add(l, 128, k0, 128, k0 / 8, 0, k0 == 0, k0 == 0, (k0 == 128 ? 1 << h : 0) | ((h == 1 && k0 == 0) ? 4 : 0),
+                        h == 0 ? (k0 == 0 ? 1 : 2) : 0, 128 * h, h);
+        }
+        add(depth, NOp, 0, H / 2, 0, 0, 0, 1, 0, 1);
+        add(depth, NOp, H / 2, H / 2, (H / 2) / 8, 0, 0, 0, 3, 2);   // both barriers: see the epilogue's d_full note
+        sc.image_bytes = goff;
+        return sc;
+    }
+    if (!lay.wide) {
         add(0, H, 0, K0p, 0, 1, 1, 1, 1, 3);
     } else {   // layer 0 in ring-slot sized pieces: [bias16 + K64 | K48] [K64] ...
         const int first_k = plan == 0 ? 64 : 48;
@@ -837,7 +895,7 @@ static size_t rank_image_stride(const frl_net* net, uint32_t image_bytes) {
 
 int tc3_pack(frl_net* net, const float* params_dev, cudaStream_t stream) {
     using namespace tc3;
-    if (!supported(net) || choose_plan(net) < 0) return FRL_OK;
+    if (!supported(net) || choose_layout(net).plan < 0) return FRL_OK;
     Schedule sc = make_schedule(net);
     if ((int)sc.blk.size() > kMaxBlocks) return FRL_OK;
     // [rank 0: fp16 image | bf16 image | bias] [rank 1: ...]
@@ -915,7 +973,7 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
         p.w_consumers = 1;
         for (int b0 = 0; b0 < p.n_blocks;) {
             int b1 = b0;
-            while (!p.blk[b1].commit) ++b1;   // a layer ends with the block that commits the accumulator
+            while (!(p.blk[b1].commit & 3)) ++b1;   // a phase ends with a block that commits an accumulator (half)
             for (int slot = 0; slot < 2; ++slot)
                 for (int b = b0; b <= b1; ++b) {
                     p.ring_pos[slot][b] = (uint8_t)p.ring_len;
@@ -927,7 +985,8 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
 
     uint32_t off = 1024;   // barriers + TMEM slot
     p.off_a = off; off += 2u * H * kRows * 2;
-    p.x0_in_a = wide_inputs(n0) ? 1 : 0;
+    const Layout lay = choose_layout(n0);
+    p.x0_in_a = lay.wide ? 1 : 0;
     p.x0_bytes = p.x0_in_a ? 0u : (uint32_t)p.K0p * kRows * 2;
     p.off_x0 = off; off += 2u * p.x0_bytes;
     p.off_ones = off; off += 2u * kRows * 16;
@@ -943,7 +1002,9 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
     int max_smem = 0, sms = 0;
     FRL_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, n0->cfg.device));
     FRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, n0->cfg.device));
-    p.slot_bytes = choose_plan(n0) == 0 ? kSlotBytesA : kSlotBytesB;
+    const int plan = lay.plan;
+    p.slot_bytes = plan == 2 ? kSlotBytesH : plan == 0 ? kSlotBytesA : kSlotBytesB;
+    p.halves = plan == 2 ? 1 : 0;
     int stages = ((int)max_smem - (int)off) / (int)p.slot_bytes;
     if (stages > kMaxSlots) stages = kMaxSlots;
     if (const char* cap = getenv("FRL_TC3_STAGES")) stages = std::min(stages, atoi(cap));   // experiments only
