@@ -576,6 +576,177 @@ def gen_gae():
         print("wrote", name, float(st.returns.abs().mean()))
 
 
+def load_policy_classes():
+    """The reference's ``MLPBasic`` (rlf/rl/model.py:246-296) and ``DiagGaussian`` (rlf/rl/distributions.py:26-75) class
+    objects plus ``def_mlp_weight_init``, compiled from the reference sources as they lie under /root/reference (the
+    ``rlf`` package itself imports gym).  NOTE: distributions.py patches ``torch.distributions.Normal`` in place
+    (log_probs / entropy summed over the last axis / mode); this generator runs last for that reason."""
+    import ast
+
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    base = os.path.join(ref_shim.REFERENCE_ROOT, "deps", "rl-toolkit", "rlf", "rl")
+    ns = {"torch": torch, "nn": nn, "np": np, "F": F, "math": __import__("math")}
+    path = os.path.join(base, "model.py")
+    tree = ast.parse(open(path).read())
+    names = ("weight_init", "def_mlp_weight_init", "BaseNet", "MLPBase", "MLPBasic")
+    keep = [n for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.name in names]
+    assert len(keep) == len(names), [n.name for n in keep]
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    path = os.path.join(base, "distributions.py")
+    tree = ast.parse(open(path).read())
+    keep = []
+    for n in tree.body:
+        if isinstance(n, ast.ClassDef) and n.name == "DiagGaussian":
+            keep.append(n)
+        elif isinstance(n, ast.Assign) and "Normal" in ast.unparse(n) or (isinstance(n, ast.Assign) and "normal" in ast.unparse(n)):
+            keep.append(n)
+    assert sum(isinstance(n, ast.ClassDef) for n in keep) == 1 and len(keep) == 7, [ast.unparse(n)[:40] for n in keep]
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns["MLPBasic"], ns["DiagGaussian"], ns["def_mlp_weight_init"]
+
+
+def build_policy(classes, spec, flat, dtype=None):
+    """The module tree DistActorCritic.init builds for get_ppo_policy (deps/baselines/get_policy.py:16-23): same
+    sub-module names and registration order (critic, critic_head: base_actor_critic.py:42-44; actor, dist:
+    dist_actor_critic.py:43-47), so state_dict order is the reference's."""
+    import torch
+    import torch.nn as nn
+
+    MLPBasic, DiagGaussian, def_init = classes
+
+    class Holder(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.critic = MLPBasic(spec.obs_dim, hidden_size=spec.hidden, num_layers=spec.layers)
+            self.critic_head = def_init(nn.Linear(spec.hidden, 1))
+            self.actor = MLPBasic(spec.obs_dim, hidden_size=spec.hidden, num_layers=spec.layers)
+            self.dist = DiagGaussian(spec.hidden, spec.a_dim)
+
+        def forward(self, state):                                   # dist_actor_critic.py:63-74, identity base net
+            value = self.critic_head(self.critic(state, None, None)[0])
+            return self.dist(self.actor(state, None, None)[0]), value
+
+    m = Holder()
+    sd = m.state_dict()
+    assert [k for k in sd] == [n for n, _ in spec.shapes()], list(sd)
+    off = 0
+    for name, shape in spec.shapes():
+        n = int(np.prod(shape))
+        sd[name].copy_(torch.from_numpy(np.asarray(flat[off:off + n], np.float32).reshape(shape)))
+        off += n
+    return m.double() if dtype == "f64" else m
+
+
+def ref_ppo_loss(model, obs, action, old_logp, adv, ret, old_value, clip, vcoef, ecoef):
+    """evaluate_actions (dist_actor_critic.py:76-86) + the loss statements of PPO.update (ppo.py:29-49)."""
+    import torch
+
+    dt = next(model.parameters()).dtype
+    obs, action, old_logp, adv, ret, old_value = (torch.from_numpy(np.asarray(v)).to(dt)
+                                                  for v in (obs, action, old_logp, adv, ret, old_value))
+    dist, value = model(obs)
+    log_prob, ent = dist.log_probs(action), dist.entropy()
+    ratio = torch.exp(log_prob - old_logp)
+    surr1 = ratio * adv
+    surr2 = torch.clamp(ratio, 1.0 - clip, 1.0 + clip) * adv
+    actor_loss = -torch.min(surr1, surr2).mean(0)
+    value_pred_clipped = old_value + (value - old_value).clamp(-clip, clip)
+    value_losses = (value - ret).pow(2)
+    value_losses_clipped = (value_pred_clipped - ret).pow(2)
+    value_loss = 0.5 * torch.max(value_losses, value_losses_clipped).mean()
+    loss = (value_loss * vcoef + actor_loss - ent.mean() * ecoef)
+    return loss.sum(), value_loss, actor_loss.sum(), ent.mean(), (value, log_prob, ent, dist.mean)
+
+
+PPO_CASES = (  # (task, hidden, layers, B, clip, value_coef, entropy_coef)
+    ("hopper", 64, 2, 1024, 0.2, 0.5, 0.01),       # the reference's defaults: 128 steps x 32 processes / 4 minibatches
+    ("maze", 256, 3, 128, 0.2, 0.5, 0.01),
+    ("ant", 64, 2, 200, 0.1, 1.0, 0.0),
+    ("sine", 16, 1, 37, 0.3, 0.5, 0.05),
+    ("hand", 128, 2, 64, 0.2, 0.25, 0.001),
+)
+
+
+def ppo_inputs(spec, flat, seed, B):
+    """A synthetic minibatch whose 'old' quantities come from a slightly different policy, so that a fair share of the
+    rows hits the ratio clip and the value clip."""
+    from oracle import ppo_closed_form as pcf
+
+    g = synth.rng(seed)
+    obs, _ = synth.states_actions(seed + 1, B, spec.obs_dim, spec.a_dim)
+    old = (flat.astype(np.float64) + 0.02 * g.standard_normal(flat.size)).astype(np.float32)
+    noise = g.standard_normal((B, spec.a_dim)).astype(np.float32)
+    old_value, action, old_logp = (x.astype(np.float32) for x in pcf.ac_act(spec, old, obs, noise))
+    adv = g.standard_normal((B, 1)).astype(np.float32)
+    ret = (old_value + 0.5 * g.standard_normal((B, 1))).astype(np.float32)
+    return obs, action, old_logp, adv, ret, old_value, noise
+
+
+def gen_ppo():
+    """ppo_*.npz: value / action mean / log-prob / entropy of the reference's policy classes, the clipped-PPO loss and
+    its autograd gradients (fp32 as the reference runs + an fp64 copy of the same modules); ppotrain_*.npz: minibatch
+    updates with _standard_step (clip_grad_norm_ 0.5, Adam lr 1e-3 eps 1e-12: base_net_algo.py:84-146)."""
+    import torch
+
+    from oracle import ppo_closed_form as pcf
+
+    classes = load_policy_classes()
+    for idx, (task, hidden, layers, B, clip, vcoef, ecoef) in enumerate(PPO_CASES):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        spec = pcf.ACSpec(s_dim, a_dim, hidden, layers)
+        seed = 9000 + idx
+        flat = pcf.ac_make_params(spec, seed)
+        obs, action, old_logp, adv, ret, old_value, noise = ppo_inputs(spec, flat, seed, B)
+        out = {"meta": np.array([s_dim, a_dim, hidden, layers, B, seed]), "coefs": np.array([clip, vcoef, ecoef])}
+        for tag in ("f32", "f64"):
+            m = build_policy(classes, spec, flat, tag)
+            loss, vl, al, ent, (value, logp, ents, mean) = ref_ppo_loss(m, obs, action, old_logp, adv, ret, old_value,
+                                                                        clip, vcoef, ecoef)
+            loss.backward()
+            out[f"loss_{tag}"] = np.array([loss.item(), vl.item(), al.item(), ent.item()])
+            g = np.concatenate([p.grad.numpy().ravel() for p in m.parameters()])
+            out[f"grad_{tag}"] = g if g.size < 100_000 else g.astype(np.float32)   # keep the fixtures small
+            out[f"value_{tag}"], out[f"logp_{tag}"] = value.detach().numpy(), logp.detach().numpy()
+            out[f"ent_{tag}"], out[f"mean_{tag}"] = ents.detach().numpy(), mean.detach().numpy()
+            if tag == "f32":
+                ratio = np.exp(out["logp_f32"] - old_logp)
+                out["clip_frac"] = np.array([np.mean(np.abs(ratio - 1) > clip), np.mean(np.abs(out["value_f32"] - old_value) > clip)])
+        name = f"ppo_{idx:02d}_{task}_h{hidden}x{layers}.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print("wrote", name, out["loss_f32"], "clipped (ratio, value):", out["clip_frac"])
+
+    for idx, (task, hidden, layers, rows, nmb, epochs) in enumerate((("hopper", 64, 2, 1024, 4, 10), ("maze", 128, 3, 512, 4, 8))):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        spec = pcf.ACSpec(s_dim, a_dim, hidden, layers)
+        seed, lr = 9500 + idx, 1e-3
+        flat = pcf.ac_make_params(spec, seed)
+        obs, action, old_logp, adv, ret, old_value, _ = ppo_inputs(spec, flat, seed, rows)
+        m = build_policy(classes, spec, flat)
+        opt = torch.optim.Adam(m.parameters(), lr=lr, eps=1e-12)
+        steps = epochs * nmb
+        curve, norms = np.zeros((steps, 4), np.float32), np.zeros(steps, np.float32)
+        mb = rows // nmb
+        for e in range(epochs):
+            perm = synth.rng(seed + 100 + e).permutation(rows)       # stands in for SubsetRandomSampler (:270-272)
+            for k in range(nmb):
+                i = perm[k * mb:(k + 1) * mb]
+                loss, vl, al, ent, _ = ref_ppo_loss(m, obs[i], action[i], old_logp[i], adv[i], ret[i], old_value[i],
+                                                    0.2, 0.5, 0.01)
+                opt.zero_grad()
+                loss.backward()
+                norms[e * nmb + k] = float(torch.nn.utils.clip_grad_norm_(m.parameters(), 0.5))
+                opt.step()
+                curve[e * nmb + k] = (loss.item(), vl.item(), al.item(), ent.item())
+        name = f"ppotrain_{idx:02d}_{task}_h{hidden}x{layers}_{steps}steps.npz"
+        np.savez_compressed(os.path.join(OUT, name), meta=np.array([s_dim, a_dim, hidden, layers, rows, nmb, epochs, seed]),
+                            lr=np.float32(lr), curve=curve, gradnorm=norms,
+                            final_params=np.concatenate([p.detach().numpy().ravel() for p in m.parameters()]))
+        print("wrote", name, curve[0], curve[-1])
+
+
 def main():
     import torch
 
@@ -583,7 +754,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     P = ref_shim.load()
-    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "bcf", "gae"]
+    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "bcf", "gae", "ppo"]
     if "logprob" in which:
         gen_logprob(P)
     if "vfield" in which:
@@ -602,6 +773,8 @@ def main():
         gen_bcf()
     if "gae" in which:
         gen_gae()
+    if "ppo" in which:
+        gen_ppo()
 
 
 if __name__ == "__main__":
