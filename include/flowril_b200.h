@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FRL_ABI_VERSION 4
+#define FRL_ABI_VERSION 5
 #define FRL_MAX_STEPS 256
 #define FRL_MAX_DEPTH 8
 
@@ -266,6 +266,53 @@ int frl_compute_returns(const float* rewards_dev, float* value_preds_dev, const 
  * scratch_dev: 256 doubles.  stats_out_dev (may be NULL) receives {mean, std}. */
 int frl_normalise_advantages(const float* returns_dev, const float* value_preds_dev, long long n, float eps,
                              float* adv_dev, double* scratch_dev, float* stats_out_dev, int device, void* stream);
+
+/* ---- PPO consumer, second part: the actor-critic policy and the clipped-PPO minibatch loss (scope row f4) ----------
+ * The policy get_ppo_policy builds (deps/baselines/get_policy.py:12-23): DistActorCritic with an identity base net, a
+ * critic MLPBasic(obs, hidden, layers) -> critic_head Linear(H,1) and an actor MLPBasic(obs, hidden, layers) ->
+ * DiagGaussian(fc_mean Linear(H,A), state-independent logstd); tanh after EVERY trunk layer (rlf/rl/model.py:246-296).
+ * Parameters are ONE flat FP32 vector in the policy's state_dict() order: critic.net.{0,2,..}.{weight,bias},
+ * critic_head.{weight [1,H], bias [1]}, actor.net.{0,2,..}.{weight,bias}, dist.logstd [1,A], dist.fc_mean.{weight [A,H],
+ * bias [A]}.  hidden must be a multiple of 16; 1 <= layers <= 8. */
+typedef struct {
+    int obs_dim, a_dim, hidden, layers; /* --ppo-hidden-dim (64), --ppo-layers (2): deps/baselines/main.py:106-107 */
+    int device;
+} frl_acnet_config;
+typedef struct frl_acnet frl_acnet;
+int frl_acnet_create(const frl_acnet_config* cfg, frl_acnet** out);
+int frl_acnet_destroy(frl_acnet* net);
+long long frl_acnet_num_params(const frl_acnet* net);
+/* Same contract as frl_net_set_params: params_dev stays owned by the caller, kernel-side layouts are rebuilt lazily. */
+int frl_acnet_set_params(frl_acnet* net, const float* params_dev, void* stream);
+
+/* DistActorCritic.forward (rlf/policies/actor_critic/dist_actor_critic.py:63-74): obs [B,S] -> value [B] (may be NULL:
+ * the critic is skipped) and the action mean [B,A] (may be NULL: the actor is skipped; get_value, base_actor_critic.py:52-56). */
+int frl_acnet_forward(frl_acnet* net, const float* obs_dev, long long B, float* value_dev, float* mean_dev, void* stream);
+
+/* get_action (dist_actor_critic.py:48-61): action = mean + exp(logstd) * noise with the caller's N(0,1) draw noise [B,A]
+ * (NULL = dist.mode(), args.deterministic_policy), its log-prob [B] (FixedNormal.log_probs, rlf/rl/distributions.py:31-34)
+ * and the entropy [B] (:36-37).  value / logp / ent may be NULL. */
+int frl_acnet_act(frl_acnet* net, const float* obs_dev, const float* noise_dev, long long B, float* value_dev,
+                  float* action_dev, float* logp_dev, float* ent_dev, void* stream);
+
+/* evaluate_actions (dist_actor_critic.py:76-86): value [B], log-prob of the given actions [B], entropy [B]. */
+int frl_acnet_evaluate(frl_acnet* net, const float* obs_dev, const float* action_dev, long long B, float* value_dev,
+                       float* logp_dev, float* ent_dev, void* stream);
+
+/* Loss and parameter gradient of one PPO.update minibatch (rlf/algos/on_policy/ppo.py:23-49):
+ *   ratio = exp(logp - old_logp);  actor = -mean(min(ratio adv, clamp(ratio, 1 -+ clip) adv));
+ *   value = 0.5 mean(max((v - ret)^2, (old_v + clamp(v - old_v, -+clip) - ret)^2));
+ *   loss = value_loss_coef value + actor - entropy_coef mean(entropy).
+ * idx_dev (int64 [B], may be NULL) gathers the minibatch rows out of the flattened rollout arrays (the BatchSampler
+ * indices of RolloutStorage.feed_forward_generator, rollout_storage.py:270-323): obs [*,S], action [*,A], old_logp / adv /
+ * ret / old_value [*].  losses_dev (may be NULL) receives {loss, value_loss, actor_loss, entropy}; grad_dev (flat,
+ * state_dict order; may be NULL) receives grad_scale * dloss/dparams, overwritten or accumulated.  mean_divisor: rows
+ * the means are taken over (0 = B; the global minibatch under data parallelism, losses are then this rank's share).
+ * Ties of torch.min / torch.max split the gradient like autograd does.  Deterministic. */
+int frl_ppo_loss_grad(frl_acnet* net, const float* obs_dev, const float* action_dev, const float* old_logp_dev,
+                      const float* adv_dev, const float* ret_dev, const float* old_value_dev, const long long* idx_dev,
+                      long long B, long long mean_divisor, float clip_param, float value_loss_coef, float entropy_coef,
+                      float grad_scale, int accumulate, float* losses_dev, float* grad_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libflowril_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3
 HAS_TC = True  # tensor-core (tcgen05) log-density kernels are built in
 PROBE_SHARED, PROBE_PER_STEP, PROBE_EXACT = 0, 1, 2
@@ -25,6 +25,8 @@ EXPORTS = (
     "frl_clip_adam", "frl_reg_loss_grad", "frl_grad_axpy", "frl_tensor_norms", "frl_normalise_rewards", "frl_cfm_loss_grad_p", "frl_clip_adam_dev",
     "frl_vnet_create", "frl_vnet_destroy", "frl_vnet_num_params", "frl_vnet_set_params", "frl_vnet_forward",
     "frl_vnet_sample", "frl_bcf_loss_grad", "frl_compute_returns", "frl_normalise_advantages", "frl_cfm_loss_grad_pair",
+    "frl_acnet_create", "frl_acnet_destroy", "frl_acnet_num_params", "frl_acnet_set_params", "frl_acnet_forward",
+    "frl_acnet_act", "frl_acnet_evaluate", "frl_ppo_loss_grad",
 )
 
 
@@ -40,6 +42,10 @@ class CfmTerm(C.Structure):
 
 class VNetConfig(C.Structure):
     _fields_ = [("s_dim", C.c_int), ("a_dim", C.c_int), ("hidden", C.c_int), ("time_dim", C.c_int), ("device", C.c_int)]
+
+
+class ACNetConfig(C.Structure):
+    _fields_ = [("obs_dim", C.c_int), ("a_dim", C.c_int), ("hidden", C.c_int), ("layers", C.c_int), ("device", C.c_int)]
 
 
 class AdamSegment(C.Structure):
@@ -94,9 +100,18 @@ def lib():
     L.frl_cfm_loss_grad_pair.argtypes = [vp, C.POINTER(CfmTerm), i32, vp, i32, vp]
     L.frl_compute_returns.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f64, f64, i32, vp, i32, vp]
     L.frl_normalise_advantages.argtypes = [vp, vp, ll, f32, vp, vp, vp, i32, vp]
+    L.frl_acnet_create.argtypes = [C.POINTER(ACNetConfig), C.POINTER(vp)]
+    L.frl_acnet_destroy.argtypes = [vp]
+    L.frl_acnet_num_params.argtypes = [vp]
+    L.frl_acnet_num_params.restype = ll
+    L.frl_acnet_set_params.argtypes = [vp, vp, vp]
+    L.frl_acnet_forward.argtypes = [vp, vp, ll, vp, vp, vp]
+    L.frl_acnet_act.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp, vp]
+    L.frl_acnet_evaluate.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp]
+    L.frl_ppo_loss_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, f32, f32, f32, f32, i32, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("frl_last_error", "frl_net_num_params", "frl_vnet_num_params"):
+        if name not in ("frl_last_error", "frl_net_num_params", "frl_vnet_num_params", "frl_acnet_num_params"):
             fn.restype = i32
     if L.frl_abi_version() != ABI_VERSION:
         raise NativeError(f"ABI mismatch: library {L.frl_abi_version()} != binding {ABI_VERSION}")

@@ -1,0 +1,502 @@
+// PPO consumer of the rewards (scope row f4, second part): the actor-critic policy the reference builds for
+// --alg flowril and the clipped-PPO minibatch loss + gradient, FP32 on the SGEMM building block of sgemm.cuh.
+// Replaces  DistActorCritic.forward / get_action / evaluate_actions
+// (deps/rl-toolkit/rlf/policies/actor_critic/dist_actor_critic.py:48-86; MLPBasic actor / critic with tanh after every
+// layer, rlf/rl/model.py:246-296; critic_head Linear(H,1), rlf/policies/utils.py:16-19; DiagGaussian,
+// rlf/rl/distributions.py:60-75)  and the loss / backward of  PPO.update  (rlf/algos/on_policy/ppo.py:23-49).
+//
+//   value = wv . hc_L + bv,   hc_l = tanh(Wc_l hc_{l-1} + bc_l),  hc_0 = obs
+//   mean  = Wm ha_L + bm,     ha_l = tanh(Wa_l ha_{l-1} + ba_l),  ha_0 = obs,   std = exp(logstd)
+// The minibatch gather of RolloutStorage.feed_forward_generator (rlf/storage/rollout_storage.py:270-323) is folded into
+// the kernels (optional int64 row index).  Batch reductions are split and reduced in a fixed order (deterministic).
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "frl_internal.h"
+#include "sgemm.cuh"
+
+constexpr int kAcMaxLayers = 8;
+
+struct frl_acnet {
+    frl_acnet_config cfg;
+    int Sp, Aop;                                   // obs width / action width padded to 16
+    // flat offsets (state_dict order): [net 0 = critic, 1 = actor][layer]
+    long long off_w[2][kAcMaxLayers], off_b[2][kAcMaxLayers], off_hw[2], off_hb[2], off_logstd;
+    long long n_params;
+    float* pack = nullptr;
+    size_t o_Wt[2][kAcMaxLayers], o_W[2][kAcMaxLayers], o_b[2][kAcMaxLayers], o_Wht[2], o_Wh[2], o_bh[2], o_logstd;
+    size_t pack_floats = 0;
+    const float* params_dev = nullptr;
+    unsigned long long version = 0, packed = 0;
+    float* ws = nullptr;
+    size_t ws_floats = 0;
+};
+
+namespace frl {
+
+struct APackJob {
+    long long src_off, dst_off, first;
+    int rows, cols, dst_ld, transpose;
+};
+struct APackTable {
+    APackJob job[6 * kAcMaxLayers + 8];
+    int n_jobs;
+    long long total;
+};
+__global__ void acnet_pack_kernel(const float* __restrict__ src, float* __restrict__ dst, APackTable tab) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tab.total; i += (long long)gridDim.x * blockDim.x) {
+        int j = 0;
+        while (j + 1 < tab.n_jobs && tab.job[j + 1].first <= i) ++j;
+        const APackJob& jb = tab.job[j];
+        const long long e = i - jb.first;
+        const int r = (int)(e / jb.cols), c = (int)(e % jb.cols);
+        const float v = src[jb.src_off + e];
+        if (jb.transpose) dst[jb.dst_off + (long long)c * jb.dst_ld + r] = v;
+        else dst[jb.dst_off + (long long)r * jb.dst_ld + c] = v;
+    }
+}
+
+static int acnet_ensure_pack(frl_acnet* n, cudaStream_t st) {
+    if (n->packed == n->version) return FRL_OK;
+    const int H = n->cfg.hidden, S = n->cfg.obs_dim, A = n->cfg.a_dim, L = n->cfg.layers;
+    FRL_CUDA(cudaMemsetAsync(n->pack, 0, n->pack_floats * sizeof(float), st));
+    APackTable tab{};
+    long long total = 0;
+    auto add = [&](long long src, size_t dst, int rows, int cols, int dst_ld, int transpose) {
+        APackJob& j = tab.job[tab.n_jobs++];
+        j = APackJob{src, (long long)dst, total, rows, cols, dst_ld, transpose};
+        total += (long long)rows * cols;
+    };
+    for (int net = 0; net < 2; ++net) {
+        for (int l = 0; l < L; ++l) {
+            const int K = l == 0 ? S : H, Kp = l == 0 ? n->Sp : H;
+            add(n->off_w[net][l], n->o_Wt[net][l], H, K, H, 1);     // [Kp][H]
+            add(n->off_w[net][l], n->o_W[net][l], H, K, Kp, 0);     // [H][Kp]
+            add(n->off_b[net][l], n->o_b[net][l], 1, H, H, 0);
+        }
+        const int NO = net == 0 ? 1 : A;
+        add(n->off_hw[net], n->o_Wht[net], NO, H, n->Aop, 1);       // [H][Aop]
+        add(n->off_hw[net], n->o_Wh[net], NO, H, H, 0);             // [Aop][H]
+        add(n->off_hb[net], n->o_bh[net], 1, NO, n->Aop, 0);
+    }
+    add(n->off_logstd, n->o_logstd, 1, A, n->Aop, 0);
+    tab.total = total;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 592);
+    acnet_pack_kernel<<<blocks, 256, 0, st>>>(n->params_dev, n->pack, tab);
+    FRL_CUDA(cudaGetLastError());
+    n->packed = n->version;
+    return FRL_OK;
+}
+
+static int acnet_ws(frl_acnet* n, size_t floats) {
+    if (n->ws_floats >= floats) return FRL_OK;
+    if (n->ws) FRL_CUDA(cudaFree(n->ws));
+    n->ws = nullptr;
+    n->ws_floats = 0;
+    FRL_CUDA(cudaMalloc(&n->ws, floats * sizeof(float)));
+    n->ws_floats = floats;
+    return FRL_OK;
+}
+
+// observations (optionally gathered through idx) into the zero-padded GEMM operand [B][Sp]
+__global__ void acnet_gather_obs_kernel(const float* __restrict__ obs, const long long* __restrict__ idx,
+                                        float* __restrict__ Xp, long long B, int S, int Sp) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= B * Sp) return;
+    const long long r = i / Sp;
+    const int c = (int)(i % Sp);
+    const long long src = idx ? idx[r] : r;
+    Xp[i] = c < S ? obs[src * S + c] : 0.f;
+}
+
+constexpr float kLogSqrt2Pi = 0.91893853320467274178f;   // math.log(math.sqrt(2 * math.pi)), torch Normal.log_prob
+
+// FixedNormal.log_probs of one row (distributions.py:31-34) in torch's operation order
+__device__ __forceinline__ float row_logp(const float* __restrict__ x, const float* __restrict__ mean,
+                                          const float* __restrict__ logstd, int A) {
+    float acc = 0.f;
+    for (int j = 0; j < A; ++j) {
+        const float scale = expf(logstd[j]);
+        const float d = x[j] - mean[j];
+        acc += -(d * d) / (2.f * (scale * scale)) - logf(scale) - kLogSqrt2Pi;
+    }
+    return acc;
+}
+__device__ __forceinline__ float row_entropy(const float* __restrict__ logstd, int A) {
+    float acc = 0.f;
+    for (int j = 0; j < A; ++j) acc += 0.5f + kLogSqrt2Pi + logf(expf(logstd[j]));   // Normal.entropy summed (:36-37)
+    return acc;
+}
+
+// get_action / evaluate_actions epilogue.  mode 0: outputs value, mean.  mode 1 (act): action = mean + std * noise
+// (noise NULL: dist.mode()), log-prob of it.  mode 2 (evaluate): log-prob of the given action, entropy.
+__global__ void acnet_head_kernel(const float* __restrict__ V, const float* __restrict__ M, int ld,
+                                  const float* __restrict__ logstd, const float* __restrict__ noise,
+                                  const float* __restrict__ action_in, float* __restrict__ value, float* __restrict__ mean_out,
+                                  float* __restrict__ action_out, float* __restrict__ logp, float* __restrict__ ent, long long B,
+                                  int A, int mode) {
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    const float* m = M + r * ld;
+    if (value) value[r] = V[r * ld];
+    if (mean_out)
+        for (int j = 0; j < A; ++j) mean_out[r * A + j] = m[j];
+    if (mode == 1) {
+        float acc = 0.f;
+        for (int j = 0; j < A; ++j) {
+            const float scale = expf(logstd[j]);
+            const float x = noise ? __fadd_rn(m[j], __fmul_rn(scale, noise[r * A + j])) : m[j];
+            action_out[r * A + j] = x;
+            const float d = x - m[j];
+            acc += -(d * d) / (2.f * (scale * scale)) - logf(scale) - kLogSqrt2Pi;
+        }
+        if (logp) logp[r] = acc;
+    } else if (mode == 2) {
+        if (logp) logp[r] = row_logp(action_in + r * A, m, logstd, A);
+    }
+    if (ent) ent[r] = row_entropy(logstd, A);
+}
+
+// ppo.py:29-49 per row + dL/dvalue and dL/dmean written in place of value / mean.  partial[block] = {sum of
+// max(vl, vlc), sum of min(surr1, surr2), d logstd_j sums (A)} in double.
+__global__ void __launch_bounds__(256) ppo_loss_kernel(float* __restrict__ V, float* __restrict__ M, int ld,
+                                                       const float* __restrict__ logstd, const float* __restrict__ action,
+                                                       const float* __restrict__ old_logp, const float* __restrict__ adv,
+                                                       const float* __restrict__ ret, const float* __restrict__ old_value,
+                                                       const long long* __restrict__ idx, long long B, int A, float clip,
+                                                       float scale_actor, float scale_value, double* __restrict__ partial) {
+    extern __shared__ double sh_p[];   // [8 warps][2 + A]
+    const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int W = 2 + A, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double vsum = 0.0, asum = 0.0;
+    float d_logp = 0.f;
+    const long long src = r < B ? (idx ? idx[r] : r) : 0;
+    if (r < B) {
+        float* m = M + r * ld;
+        const float value = V[r * ld];
+        const float logp = row_logp(action + src * A, m, logstd, A);
+        const float ratio = expf(logp - old_logp[src]);
+        const float ad = adv[src];
+        const float surr1 = ratio * ad;
+        const float surr2 = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip) * ad;
+        asum = (double)fminf(surr1, surr2);
+        // torch.min splits the gradient on ties; clamp passes it on the closed interval
+        const float w1 = surr1 < surr2 ? 1.f : (surr1 > surr2 ? 0.f : 0.5f);
+        const float in_r = (ratio >= 1.f - clip && ratio <= 1.f + clip) ? 1.f : 0.f;
+        d_logp = -(ad * scale_actor) * (w1 + (1.f - w1) * in_r) * ratio;
+        const float ov = old_value[src], rt = ret[src];
+        const float dv = value - ov;
+        const float vpc = ov + fminf(fmaxf(dv, -clip), clip);
+        const float e1 = value - rt, e2 = vpc - rt;
+        const float vl = e1 * e1, vlc = e2 * e2;
+        vsum = (double)fmaxf(vl, vlc);
+        const float wv = vl > vlc ? 1.f : (vl < vlc ? 0.f : 0.5f);
+        const float in_v = (dv >= -clip && dv <= clip) ? 1.f : 0.f;
+        V[r * ld] = scale_value * (wv * 2.f * e1 + (1.f - wv) * 2.f * e2 * in_v);
+        for (int j = 1; j < ld; ++j) V[r * ld + j] = 0.f;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+        asum += __shfl_xor_sync(0xffffffffu, asum, o);
+    }
+    if (lane == 0) { sh_p[warp * W] = vsum; sh_p[warp * W + 1] = asum; }
+    for (int j = 0; j < A; ++j) {
+        double g = 0.0;
+        if (r < B) {
+            float* m = M + r * ld;
+            const float scale = expf(logstd[j]);
+            const float var = scale * scale;
+            const float d = action[src * A + j] - m[j];
+            g = (double)(d_logp * (d * d / var - 1.f));
+            m[j] = d_logp * d / var;
+        }
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+        if (lane == 0) sh_p[warp * W + 2 + j] = g;
+    }
+    if (r < B)
+        for (int j = A; j < ld; ++j) M[r * ld + j] = 0.f;
+    __syncthreads();
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        double acc = 0.0;
+        for (int w = 0; w < 8; ++w) acc += sh_p[w * W + c];
+        partial[(size_t)blockIdx.x * W + c] = acc;
+    }
+}
+
+// losses = {loss, value_loss, actor_loss, entropy}; d logstd (+)= sums - entropy_coef * local share
+__global__ void ppo_loss_final_kernel(const double* __restrict__ partial, int n_blocks, int A, double inv_div, float value_coef,
+                                      float ent_coef, float ent_share, float grad_scale, const float* __restrict__ logstd,
+                                      float* __restrict__ losses, float* __restrict__ g_logstd, int accumulate) {
+    const int c = threadIdx.x;
+    double acc = 0.0;
+    if (c < 2 + A)
+        for (int b = 0; b < n_blocks; ++b) acc += partial[(size_t)b * (2 + A) + c];
+    __shared__ float sh[2];
+    if (c < 2) sh[c] = c == 0 ? (float)(0.5 * acc * inv_div) : (float)(-acc * inv_div);
+    __syncthreads();
+    if (c >= 2 && c < 2 + A && g_logstd) {
+        const float g = (float)acc - grad_scale * ent_coef * ent_share;
+        g_logstd[c - 2] = accumulate ? g_logstd[c - 2] + g : g;
+    }
+    if (c == 0 && losses) {
+        const float ent = row_entropy(logstd, A);
+        losses[0] = sh[0] * value_coef + sh[1] - ent * ent_coef * ent_share;   // ppo.py:48-49 (this rank's share)
+        losses[1] = sh[0];
+        losses[2] = sh[1];
+        losses[3] = ent;
+    }
+}
+
+struct ABuf {
+    float *Xp, *act[2], *out[2];   // act[net]: L activation matrices [B][H] back to back; out[net]: [B][Aop]
+};
+
+static ABuf ac_carve(const frl_acnet* n, float* ws, size_t B, size_t* used) {
+    const size_t H = n->cfg.hidden, L = n->cfg.layers;
+    size_t off = 0;
+    auto take = [&](size_t f) { size_t o = off; off += (f + 3) / 4 * 4; return ws ? ws + o : (float*)nullptr; };
+    ABuf b;
+    b.Xp = take(B * n->Sp);
+    for (int net = 0; net < 2; ++net) { b.act[net] = take(B * H * L); b.out[net] = take(B * n->Aop); }
+    *used = off;
+    return b;
+}
+
+// both trunks + heads for B rows whose padded observations are in b.Xp (net_mask: bit 0 critic, bit 1 actor)
+static int ac_forward(frl_acnet* n, const ABuf& b, int B, int net_mask, cudaStream_t st) {
+    const int H = n->cfg.hidden, L = n->cfg.layers;
+    const float* pk = n->pack;
+    for (int net = 0; net < 2; ++net) {
+        if (!(net_mask >> net & 1)) continue;
+        const float* x = b.Xp;
+        int K = n->Sp;
+        for (int l = 0; l < L; ++l) {
+            float* h = b.act[net] + (size_t)l * B * H;
+            int rc = run_gemm<false, EPI_BIAS_TANH>(x, K, pk + n->o_Wt[net][l], H, h, H, B, H, K, pk + n->o_b[net][l], nullptr, 0, 1, K, st);
+            if (rc != FRL_OK) return rc;
+            x = h;
+            K = H;
+        }
+        int rc = run_gemm<false, EPI_BIAS>(x, H, pk + n->o_Wht[net], n->Aop, b.out[net], n->Aop, B, n->Aop, H, pk + n->o_bh[net], nullptr, 0, 1, H, st);
+        if (rc != FRL_OK) return rc;
+    }
+    return FRL_OK;
+}
+
+static int ac_prepare(frl_acnet* n, const float* obs, const long long* idx, long long B, size_t extra_floats, ABuf* out,
+                      size_t* used, cudaStream_t st) {
+    int rc = acnet_ensure_pack(n, st);
+    if (rc != FRL_OK) return rc;
+    ac_carve(n, nullptr, (size_t)B, used);
+    rc = acnet_ws(n, *used + extra_floats);
+    if (rc != FRL_OK) return rc;
+    *out = ac_carve(n, n->ws, (size_t)B, used);
+    acnet_gather_obs_kernel<<<(unsigned)((B * n->Sp + 255) / 256), 256, 0, st>>>(obs, idx, out->Xp, B, n->cfg.obs_dim, n->Sp);
+    FRL_CUDA(cudaGetLastError());
+    return FRL_OK;
+}
+
+}  // namespace frl
+
+using namespace frl;
+
+extern "C" int frl_acnet_create(const frl_acnet_config* cfg, frl_acnet** out) {
+    FRL_REQUIRE(cfg && out, "null config/out");
+    FRL_REQUIRE(cfg->obs_dim >= 1 && cfg->obs_dim <= 4096 && cfg->a_dim >= 1 && cfg->a_dim <= 64, "bad obs_dim / a_dim");
+    FRL_REQUIRE(cfg->hidden >= 16 && cfg->hidden % 16 == 0 && cfg->hidden <= 1024, "hidden must be a multiple of 16, <= 1024");
+    FRL_REQUIRE(cfg->layers >= 1 && cfg->layers <= kAcMaxLayers, "layers must be in 1..8");
+    int ndev = 0;
+    FRL_CUDA(cudaGetDeviceCount(&ndev));
+    FRL_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "bad device ordinal");
+    FRL_CUDA(cudaSetDevice(cfg->device));
+    frl_acnet* n = new (std::nothrow) frl_acnet();
+    if (!n) { set_error("out of host memory"); return FRL_ERR_NOMEM; }
+    n->cfg = *cfg;
+    const int H = cfg->hidden, S = cfg->obs_dim, A = cfg->a_dim, L = cfg->layers;
+    n->Sp = round_up(S, 16);
+    n->Aop = round_up(A, 16);
+    long long off = 0;
+    auto adv = [&](long long k) { long long o = off; off += k; return o; };
+    // state_dict order: critic.net.*, critic_head.*, actor.net.*, dist.logstd, dist.fc_mean.*
+    for (int l = 0; l < L; ++l) { n->off_w[0][l] = adv((long long)H * (l == 0 ? S : H)); n->off_b[0][l] = adv(H); }
+    n->off_hw[0] = adv(H);
+    n->off_hb[0] = adv(1);
+    for (int l = 0; l < L; ++l) { n->off_w[1][l] = adv((long long)H * (l == 0 ? S : H)); n->off_b[1][l] = adv(H); }
+    n->off_logstd = adv(A);
+    n->off_hw[1] = adv((long long)A * H);
+    n->off_hb[1] = adv(A);
+    n->n_params = off;
+    size_t f = 0;
+    auto take = [&](size_t x) { size_t o = f; f += (x + 3) / 4 * 4; return o; };
+    for (int net = 0; net < 2; ++net) {
+        for (int l = 0; l < L; ++l) {
+            const size_t Kp = l == 0 ? n->Sp : H;
+            n->o_Wt[net][l] = take(Kp * H);
+            n->o_W[net][l] = take((size_t)H * Kp);
+            n->o_b[net][l] = take(H);
+        }
+        n->o_Wht[net] = take((size_t)H * n->Aop);
+        n->o_Wh[net] = take((size_t)n->Aop * H);
+        n->o_bh[net] = take(n->Aop);
+    }
+    n->o_logstd = take(n->Aop);
+    n->pack_floats = f;
+    cudaError_t e = cudaMalloc(&n->pack, f * sizeof(float));
+    if (e != cudaSuccess) { delete n; return cuda_fail(e, "cudaMalloc(acnet pack)", __FILE__, __LINE__); }
+    *out = n;
+    return FRL_OK;
+}
+
+extern "C" int frl_acnet_destroy(frl_acnet* n) {
+    if (!n) return FRL_OK;
+    cudaSetDevice(n->cfg.device);
+    if (n->pack) cudaFree(n->pack);
+    if (n->ws) cudaFree(n->ws);
+    delete n;
+    return FRL_OK;
+}
+
+extern "C" long long frl_acnet_num_params(const frl_acnet* n) { return n ? n->n_params : -1; }
+
+extern "C" int frl_acnet_set_params(frl_acnet* n, const float* params_dev, void* /*stream*/) {
+    FRL_REQUIRE(n && params_dev, "null net/params");
+    n->params_dev = params_dev;
+    n->version += 1;
+    return FRL_OK;
+}
+
+static int acnet_eval_common(frl_acnet* n, const float* obs, const float* noise, const float* action_in, long long B,
+                             float* value, float* mean, float* action_out, float* logp, float* ent, int mode, void* stream) {
+    FRL_REQUIRE(n && n->version > 0, "frl_acnet_set_params has not been called");
+    if (B <= 0) return FRL_OK;
+    FRL_REQUIRE(obs, "null observations");
+    FRL_REQUIRE(B < (1ll << 31) / std::max(n->cfg.hidden, n->Sp), "batch too large");
+    FRL_CUDA(cudaSetDevice(n->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ABuf b;
+    size_t used = 0;
+    int rc = ac_prepare(n, obs, nullptr, B, 0, &b, &used, st);
+    if (rc != FRL_OK) return rc;
+    const bool need_actor = mean || action_out || logp;
+    rc = ac_forward(n, b, (int)B, (value ? 1 : 0) | (need_actor ? 2 : 0), st);
+    if (rc != FRL_OK) return rc;
+    acnet_head_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(b.out[0], b.out[1], n->Aop, n->pack + n->o_logstd, noise, action_in,
+                                                                 value, mean, action_out, logp, ent, B, n->cfg.a_dim, mode);
+    FRL_CUDA(cudaGetLastError());
+    return FRL_OK;
+}
+
+extern "C" int frl_acnet_forward(frl_acnet* n, const float* obs, long long B, float* value, float* mean, void* stream) {
+    return acnet_eval_common(n, obs, nullptr, nullptr, B, value, mean, nullptr, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int frl_acnet_act(frl_acnet* n, const float* obs, const float* noise, long long B, float* value, float* action,
+                             float* logp, float* ent, void* stream) {
+    FRL_REQUIRE(B <= 0 || action, "null action output");
+    return acnet_eval_common(n, obs, noise, nullptr, B, value, nullptr, action, logp, ent, 1, stream);
+}
+
+extern "C" int frl_acnet_evaluate(frl_acnet* n, const float* obs, const float* action, long long B, float* value, float* logp,
+                                  float* ent, void* stream) {
+    FRL_REQUIRE(B <= 0 || (action && logp), "null action / log-prob");
+    return acnet_eval_common(n, obs, nullptr, action, B, value, nullptr, nullptr, logp, ent, 2, stream);
+}
+
+extern "C" int frl_ppo_loss_grad(frl_acnet* n, const float* obs, const float* action, const float* old_logp, const float* adv,
+                                 const float* ret, const float* old_value, const long long* idx, long long B,
+                                 long long mean_divisor, float clip_param, float value_loss_coef, float entropy_coef,
+                                 float grad_scale, int accumulate, float* losses, float* grad, void* stream) {
+    FRL_REQUIRE(n && n->version > 0, "frl_acnet_set_params has not been called");
+    FRL_REQUIRE(obs && action && old_logp && adv && ret && old_value, "null input");
+    FRL_REQUIRE(B > 0 && B < (1ll << 31) / std::max(n->cfg.hidden, n->Sp), "batch size out of range");
+    FRL_REQUIRE(clip_param >= 0.f, "clip_param must be >= 0");
+    FRL_CUDA(cudaSetDevice(n->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int H = n->cfg.hidden, S = n->cfg.obs_dim, A = n->cfg.a_dim, L = n->cfg.layers, Aop = n->Aop;
+    const int R = (int)B;
+    const double div = (double)(mean_divisor > 0 ? mean_divisor : B);
+
+    auto plan_splits = [&](int tiles) {
+        int want = std::max(1, 296 / std::max(1, tiles));
+        int maxs = std::max(1, (R + 63) / 64);
+        return std::min(want, maxs);
+    };
+    const int sp_hh = plan_splits(((H + 127) / 128) * ((std::max(H, n->Sp) + 127) / 128));
+    const int sp_small = plan_splits(2);
+    const int max_sp = std::max(sp_hh, sp_small);
+    const int cs_chunks = std::max(1, std::min(148, (R + 255) / 256));
+    const int cs_rows = (R + cs_chunks - 1) / cs_chunks;
+    const int loss_blocks = (R + 255) / 256;
+    const int Wp = 2 + A;
+
+    size_t used = 0;
+    ac_carve(n, nullptr, (size_t)R, &used);
+    size_t off = used;
+    auto take = [&](size_t f) { size_t o = off; off += (f + 3) / 4 * 4; return o; };
+    const size_t o_dz0 = take((size_t)R * H), o_dz1 = take((size_t)R * H);
+    const size_t o_part = take((size_t)max_sp * H * std::max(H, n->Sp));
+    const size_t o_cs = take((size_t)cs_chunks * H);
+    const size_t o_lp = take((size_t)loss_blocks * Wp * 2 + 4);
+    ABuf b;
+    int rc = ac_prepare(n, obs, idx, B, off - used, &b, &used, st);
+    if (rc != FRL_OK) return rc;
+    float* ws = n->ws;
+    float *dZ[2] = {ws + o_dz0, ws + o_dz1}, *part = ws + o_part, *cs = ws + o_cs;
+    double* lpart = reinterpret_cast<double*>(ws + o_lp);   // offsets are multiples of 4 floats
+    const float* pk = n->pack;
+
+    rc = ac_forward(n, b, R, 3, st);
+    if (rc != FRL_OK) return rc;
+    ppo_loss_kernel<<<loss_blocks, 256, (size_t)8 * Wp * sizeof(double), st>>>(
+        b.out[0], b.out[1], Aop, pk + n->o_logstd, action, old_logp, adv, ret, old_value, idx, B, A, clip_param,
+        (float)((double)grad_scale / div), (float)((double)grad_scale * 0.5 * value_loss_coef / div), lpart);
+    FRL_CUDA(cudaGetLastError());
+    if (losses || grad) {
+        ppo_loss_final_kernel<<<1, round_up(Wp, 32), 0, st>>>(lpart, loss_blocks, A, 1.0 / div, value_loss_coef, entropy_coef,
+                                                              (float)((double)B / div), grad_scale, pk + n->o_logstd, losses,
+                                                              grad ? grad + n->off_logstd : nullptr, accumulate);
+        FRL_CUDA(cudaGetLastError());
+    }
+    if (!grad) return FRL_OK;
+
+    auto ksplit = [&](int splits) { return round_up((R + splits - 1) / splits, BK); };
+    auto wgrad = [&](const float* dZm, int ldz, int rows, const float* X, int ldx, int Kp, int K, long long goff, int sp) -> int {
+        int r = run_gemm<true, EPI_NONE>(dZm, ldz, X, ldx, part, Kp, rows, Kp, R, nullptr, nullptr, 0, sp, ksplit(sp), st);
+        if (r != FRL_OK) return r;
+        reduce_wgrad_kernel<<<(rows * K + 255) / 256, 256, 0, st>>>(part, sp, (size_t)rows * Kp, Kp, rows, K, grad + goff, accumulate);
+        FRL_CUDA(cudaGetLastError());
+        return FRL_OK;
+    };
+    auto bgrad = [&](const float* dZm, int ldz, int cols, long long goff) -> int {
+        colsum_partial_kernel<<<dim3((cols + 127) / 128, cs_chunks), 128, 0, st>>>(dZm, ldz, R, cols, cs_rows, cs);
+        reduce_bias_kernel<<<(cols + 127) / 128, 128, 0, st>>>(cs, cs_chunks, cols, 0, cols, grad + goff, accumulate);
+        FRL_CUDA(cudaGetLastError());
+        return FRL_OK;
+    };
+    for (int net = 0; net < 2; ++net) {
+        const int NO = net == 0 ? 1 : A;
+        const float* hL = b.act[net] + (size_t)(L - 1) * R * H;
+        rc = wgrad(b.out[net], Aop, NO, hL, H, H, H, n->off_hw[net], sp_small);           // critic_head / dist.fc_mean
+        if (rc != FRL_OK) return rc;
+        rc = bgrad(b.out[net], Aop, NO, n->off_hb[net]);
+        if (rc != FRL_OK) return rc;
+        rc = run_gemm<false, EPI_DTANH>(b.out[net], Aop, pk + n->o_Wh[net], H, dZ[0], H, R, H, Aop, nullptr, hL, H, 1, Aop, st);
+        if (rc != FRL_OK) return rc;
+        int cur = 0;
+        for (int l = L - 1; l >= 0; --l) {
+            const float* X = l == 0 ? b.Xp : b.act[net] + (size_t)(l - 1) * R * H;
+            const int Kp = l == 0 ? n->Sp : H, K = l == 0 ? S : H;
+            rc = wgrad(dZ[cur], H, H, X, Kp, Kp, K, n->off_w[net][l], l == 0 ? sp_small : sp_hh);
+            if (rc != FRL_OK) return rc;
+            rc = bgrad(dZ[cur], H, H, n->off_b[net][l]);
+            if (rc != FRL_OK) return rc;
+            if (l > 0) {
+                rc = run_gemm<false, EPI_DTANH>(dZ[cur], H, pk + n->o_W[net][l], H, dZ[cur ^ 1], H, R, H, H, nullptr, X, H, 1, H, st);
+                if (rc != FRL_OK) return rc;
+                cur ^= 1;
+            }
+        }
+    }
+    return FRL_OK;
+}

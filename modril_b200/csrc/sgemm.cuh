@@ -1,4 +1,4 @@
-// FP32 SGEMM building block shared by the FFMA training kernels (train_f32.cu, bcf_f32.cu).
+// FP32 SGEMM building block shared by the FFMA training kernels (train_f32.cu, bcf_f32.cu, ppo_f32.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -6,7 +6,8 @@
 
 namespace frl {
 
-enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_MASK = 3 };
+// EPI_BIAS_TANH: tanh(acc + bias) (the PPO actor / critic trunks); EPI_DTANH: acc * (1 - h^2) with h = mask (their backward)
+enum { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_RELU = 2, EPI_MASK = 3, EPI_BIAS_TANH = 4, EPI_DTANH = 5 };
 constexpr int BK = 16;
 
 // C[M][N] (+ split offset) = op(A) * B.   A_TRANS=false: A is [M][lda] (k contiguous); true: A is [K][lda]
@@ -85,8 +86,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
             const int n = n0 + tx * TN + j;
             if (n >= N) continue;
             float v = acc[i][j];
-            if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) v += __ldg(bias + n);
+            if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU || EPI == EPI_BIAS_TANH) v += __ldg(bias + n);
             if (EPI == EPI_BIAS_RELU) v = v > 0.f ? v : 0.f;
+            if (EPI == EPI_BIAS_TANH) v = tanhf(v);
+            if (EPI == EPI_DTANH) { const float h = mask[(size_t)m * ldmask + n]; v *= 1.f - h * h; }
             // mask_rows < M: the rows are two stacked batches that share one mask matrix (regularisers)
             if (EPI == EPI_MASK) v = mask[(size_t)(m >= mask_rows ? m - mask_rows : m) * ldmask + n] > 0.f ? v : 0.f;
             C[(size_t)m * ldc + n] = v;

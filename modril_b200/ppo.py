@@ -1,4 +1,5 @@
-"""Returns / GAE and advantage normalisation on the device (scope row f4, first part).
+"""The PPO consumer of the rewards on the device (scope row f4): returns / GAE and advantage normalisation, the
+actor-critic policy of ``get_ppo_policy`` and the clipped-PPO minibatch update.
 
 Mirrors ``RolloutStorage.compute_returns`` / ``compute_advantages``
 (``deps/rl-toolkit/rlf/storage/rollout_storage.py:178-239``) as two functions over the storage's tensors: the T-step python
@@ -7,10 +8,14 @@ normalisation one ``frl_normalise_advantages`` call.  CUDA tensors only; no PyTo
 """
 from __future__ import annotations
 
+import math
+
 import torch
+import torch.nn as nn
 
 from . import _native
-from .flowril.networks import _current_stream, _ptr
+from .flowril.networks import _FlatVNet, _current_stream, _ptr, as_f32_cuda
+from .flowril.pretrain import FusedAdam  # noqa: F401  (the optimiser to pair with ppo_update)
 
 
 def _f32(x, dev, what):
@@ -60,3 +65,178 @@ def compute_advantages(returns, value_preds, eps: float = 1e-5, return_stats: bo
                                                          _ptr(scratch), _ptr(stats), dev.index or 0, _current_stream(dev)),
                   "frl_normalise_advantages")
     return (adv, stats) if return_stats else adv
+
+
+# ---- actor-critic policy + clipped-PPO update (row f4, second part) ---------------------------------------------------
+class _MLPBasic(nn.Module):
+    """``MLPBasic`` (deps/rl-toolkit/rlf/rl/model.py:246-296): ``net`` = [Linear, Tanh] * num_layers, orthogonal weights
+    with gain sqrt(2) and zero biases (``def_mlp_weight_init``, model.py:22-25).  Parameter container only."""
+
+    def __init__(self, num_inputs, hidden_size, num_layers):
+        super().__init__()
+        layers, k = [], num_inputs
+        for _ in range(num_layers):
+            lin = nn.Linear(k, hidden_size)
+            nn.init.orthogonal_(lin.weight.data, gain=math.sqrt(2))
+            nn.init.constant_(lin.bias.data, 0)
+            layers += [lin, nn.Tanh()]
+            k = hidden_size
+        self.net = nn.Sequential(*layers)
+
+
+class _DiagGaussian(nn.Module):
+    """``DiagGaussian`` (rlf/rl/distributions.py:60-75): ``logstd`` [1,A] zeros, ``fc_mean`` orthogonal (gain 1)."""
+
+    def __init__(self, num_inputs, num_outputs):
+        super().__init__()
+        self.fc_mean = nn.Linear(num_inputs, num_outputs)
+        nn.init.orthogonal_(self.fc_mean.weight.data)
+        nn.init.constant_(self.fc_mean.bias.data, 0)
+        self.logstd = nn.Parameter(torch.zeros(1, num_outputs))
+
+
+class DistActorCritic(_FlatVNet):
+    """The policy ``get_ppo_policy`` builds for ``--alg flowril`` (deps/baselines/get_policy.py:12-23):
+    ``DistActorCritic`` (rlf/policies/actor_critic/dist_actor_critic.py:13-89) with the identity base net, an
+    ``MLPBasic`` critic + ``critic_head`` (base_actor_critic.py:37-50) and an ``MLPBasic`` actor + ``DiagGaussian``.
+    Same sub-module names and registration order, hence the same ``state_dict`` keys (``critic.net.0.weight`` ...
+    ``dist.logstd``, ``dist.fc_mean.weight``).  All arithmetic runs in ``frl_acnet_*`` / ``frl_ppo_loss_grad``."""
+
+    _ABI = ("frl_acnet_create", "frl_acnet_destroy", "frl_acnet_set_params")
+
+    def __init__(self, obs_dim: int, action_dim: int, ppo_hidden_dim: int = 64, ppo_layers: int = 2,
+                 deterministic_policy: bool = False):
+        super().__init__()
+        self.obs_dim, self.action_dim = int(obs_dim), int(action_dim)
+        self.ppo_layers = int(ppo_layers)
+        self.deterministic_policy = bool(deterministic_policy)
+        self.critic = _MLPBasic(obs_dim, ppo_hidden_dim, ppo_layers)
+        self.critic_head = nn.Linear(ppo_hidden_dim, 1)                      # rlf/policies/utils.py:16-19
+        nn.init.orthogonal_(self.critic_head.weight.data, gain=math.sqrt(2))
+        nn.init.constant_(self.critic_head.bias.data, 0)
+        self.actor = _MLPBasic(obs_dim, ppo_hidden_dim, ppo_layers)
+        self.dist = _DiagGaussian(ppo_hidden_dim, action_dim)
+        self._finish_init(obs_dim, action_dim, ppo_hidden_dim)
+
+    def _native_config(self, device_index: int):
+        return _native.ACNetConfig(self.obs_dim, self.action_dim, self.hidden, self.ppo_layers, device_index)
+
+    def _obs(self, state):
+        state = as_f32_cuda(state, self._flat.device, "state")
+        if state.dim() != 2 or state.shape[1] != self.obs_dim:
+            raise ValueError(f"expected state [B,{self.obs_dim}], got {tuple(state.shape)}")
+        return state
+
+    def forward(self, state, add_state=None, hxs=None, masks=None):
+        """-> (action mean [B,A], value [B,1]); the distribution is Normal(mean, exp(dist.logstd))."""
+        h = self.native()
+        state = self._obs(state)
+        B = state.shape[0]
+        value = torch.empty(B, 1, device=state.device)
+        mean = torch.empty(B, self.action_dim, device=state.device)
+        _native.check(_native.lib().frl_acnet_forward(h, _ptr(state), B, _ptr(value), _ptr(mean), _current_stream(state.device)),
+                      "frl_acnet_forward")
+        return mean, value
+
+    def get_value(self, inputs, add_inputs=None, hxs=None, masks=None):
+        """base_actor_critic.py:52-56 (only the critic runs)."""
+        h = self.native()
+        state = self._obs(inputs)
+        value = torch.empty(state.shape[0], 1, device=state.device)
+        _native.check(_native.lib().frl_acnet_forward(h, _ptr(state), state.shape[0], _ptr(value), None,
+                                                      _current_stream(state.device)), "frl_acnet_forward")
+        return value
+
+    def get_action(self, state, add_state=None, hxs=None, masks=None, step_info=None, *, noise=None):
+        """dist_actor_critic.py:48-61 -> dict(value [B,1], action [B,A], action_log_probs [B,1], dist_entropy [B]).
+        ``noise`` is the N(0,1) draw of ``Normal.sample`` (drawn here when omitted; ignored by a deterministic policy)."""
+        h = self.native()
+        state = self._obs(state)
+        B, dev = state.shape[0], state.device
+        if self.deterministic_policy:
+            noise = None
+        elif noise is None:
+            noise = torch.randn(B, self.action_dim, device=dev)
+        else:
+            noise = as_f32_cuda(noise, dev, "noise")
+            if noise.shape != (B, self.action_dim):
+                raise ValueError(f"expected noise [B,{self.action_dim}], got {tuple(noise.shape)}")
+        value, logp = torch.empty(B, 1, device=dev), torch.empty(B, 1, device=dev)
+        action, ent = torch.empty(B, self.action_dim, device=dev), torch.empty(B, device=dev)
+        _native.check(_native.lib().frl_acnet_act(h, _ptr(state), _ptr(noise), B, _ptr(value), _ptr(action), _ptr(logp),
+                                                  _ptr(ent), _current_stream(dev)), "frl_acnet_act")
+        return {"value": value, "action": action, "action_log_probs": logp, "dist_entropy": ent}
+
+    def evaluate_actions(self, state, add_state, hxs, masks, action):
+        """dist_actor_critic.py:76-86 -> {'value' [B,1], 'log_prob' [B,1], 'ent' [B]}."""
+        h = self.native()
+        state = self._obs(state)
+        B, dev = state.shape[0], state.device
+        action = as_f32_cuda(action, dev, "action")
+        if action.shape != (B, self.action_dim):
+            raise ValueError(f"expected action [B,{self.action_dim}], got {tuple(action.shape)}")
+        value, logp, ent = torch.empty(B, 1, device=dev), torch.empty(B, 1, device=dev), torch.empty(B, device=dev)
+        _native.check(_native.lib().frl_acnet_evaluate(h, _ptr(state), _ptr(action), B, _ptr(value), _ptr(logp), _ptr(ent),
+                                                       _current_stream(dev)), "frl_acnet_evaluate")
+        return {"value": value, "log_prob": logp, "ent": ent}
+
+    def ppo_loss(self, state, action, prev_log_prob, adv, ret, value, *, indices=None, clip_param=0.2, value_loss_coef=0.5,
+                 entropy_coef=0.01, grad=True, accumulate=False, mean_divisor: int = 0, grad_scale: float = 1.0):
+        """Loss of one PPO.update minibatch (ppo.py:23-49) and, with ``grad=True``, its parameter gradient into
+        ``flat_grad()``.  With ``indices`` (int64 [B]) the tensors are the flattened rollout arrays and the minibatch is
+        gathered inside the kernels.  Returns the device tensor ``[loss, value_loss, actor_loss, dist_entropy]``."""
+        h = self.native()
+        dev = self._flat.device
+        state = self._obs(state)
+        rows = state.shape[0]
+        action = as_f32_cuda(action, dev, "action")
+        cols = [as_f32_cuda(x, dev, n).reshape(-1) for n, x in (("prev_log_prob", prev_log_prob), ("adv", adv),
+                                                                 ("return", ret), ("value", value))]
+        if action.shape != (rows, self.action_dim) or any(c.numel() != rows for c in cols):
+            raise ValueError("state / action / prev_log_prob / adv / return / value disagree on the number of rows")
+        if indices is not None:
+            if indices.dtype != torch.int64 or indices.device != dev or not indices.is_contiguous():
+                raise TypeError("indices must be a contiguous int64 CUDA tensor")
+            B = indices.numel()
+        else:
+            B = rows
+        losses = torch.empty(4, device=dev)
+        g = self.flat_grad() if grad else None
+        _native.check(_native.lib().frl_ppo_loss_grad(h, _ptr(state), _ptr(action), *(_ptr(c) for c in cols), _ptr(indices), B,
+                                                      int(mean_divisor), float(clip_param), float(value_loss_coef),
+                                                      float(entropy_coef), float(grad_scale), int(bool(accumulate)),
+                                                      _ptr(losses), _ptr(g), _current_stream(dev)), "frl_ppo_loss_grad")
+        return losses
+
+
+def ppo_update(policy: DistActorCritic, opt: FusedAdam, obs, actions, action_log_probs, value_preds, returns, advantages, *,
+               num_epochs=4, num_mini_batch=4, clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01, max_grad_norm=0.5,
+               perms=None):
+    """``PPO.update`` after the returns / advantages are in place (ppo.py:17-64): ``num_epochs`` passes of
+    ``num_mini_batch`` minibatches (``BatchSampler(SubsetRandomSampler(range(T*N)), T*N // num_mini_batch,
+    drop_last=True)``, rollout_storage.py:258-272), each one loss + backward + ``clip_grad_norm_(max_grad_norm)`` +
+    ``Adam.step`` (``_standard_step``, base_net_algo.py:84-100).  Inputs are the rollout tensors with the time and
+    process axes flattened: obs [T*N,S] (``storage.obs[:-1]``), actions [T*N,A], action_log_probs / value_preds[:-1] /
+    returns[:-1] / advantages [T*N(,1)].  ``perms``: optional list of ``num_epochs`` int64 CUDA permutations (tests; the
+    reference draws them from the global RNG).  No host synchronisation inside the loop; returns the reference's
+    ``log_vals`` dict (one device->host copy at the end)."""
+    dev = policy.flat_params().device
+    rows = obs.shape[0]
+    if rows < num_mini_batch:
+        raise ValueError(f"PPO requires T*N ({rows}) >= num_mini_batch ({num_mini_batch})")   # rollout_storage.py:262-268
+    mb = rows // num_mini_batch
+    acc = torch.zeros(4, device=dev)
+    n_updates = 0
+    for e in range(num_epochs):
+        perm = perms[e] if perms is not None else torch.randperm(rows, device=dev)
+        for k in range(rows // mb):                                   # drop_last=True
+            losses = policy.ppo_loss(obs, actions, action_log_probs, advantages, returns, value_preds,
+                                     indices=perm[k * mb:(k + 1) * mb].contiguous(), clip_param=clip_param,
+                                     value_loss_coef=value_loss_coef, entropy_coef=entropy_coef)
+            opt.step_flat([policy.flat_grad()], max_norm=max_grad_norm if max_grad_norm > 0 else float("inf"))
+            acc += losses
+            n_updates += 1
+    a = acc.tolist()
+    n = num_epochs * num_mini_batch                                   # ppo.py:59-64
+    return {"value_loss": a[1] / n, "actor_loss": a[2] / n, "dist_entropy": a[3] / n,
+            "policy_update_data": float(num_mini_batch * n_updates)}
