@@ -425,6 +425,26 @@ def run_ours(args):
             bcf_info[f"sample32_ms_B{Bb}"] = timed(lambda: pol.get_action(bs_, x0=bx0), n_it)
             bcf_info[f"bc_update_ms_B{Bb}"] = timed(lambda: bc_step(pol, bopt, bs_, ba_, x0=bx0, t=bt_), n_it)
 
+    # ---- PPO consumer (scope row f4), informational: acting latency and one whole PPO.update of the reference's
+    # default shape (128 steps x 32 processes, 4 epochs x 4 minibatches, --ppo-hidden-dim 64 x --ppo-layers 2)
+    ppo_info = None
+    if world == 1:
+        from modril_b200.ppo import DistActorCritic, ppo_update
+
+        ppo_info = {}
+        for tag, hid, rows in (("default_h64x2_rows4096", 64, 4096), ("h256x2_rows65536", 256, 65536)):
+            if rows > B:
+                continue
+            pol_ac = DistActorCritic(s_dim, a_dim, hid, 2).to(device)
+            popt = FusedAdam([pol_ac], lr=1e-3, eps=1e-12)
+            po = st[:rows]
+            out = pol_ac.get_action(po)
+            pdata = (po, out["action"], out["action_log_probs"], out["value"], out["value"] + 0.1 * torch.randn_like(out["value"]),
+                     torch.randn(rows, 1, device=device))
+            ppo_info[f"act_ms_B32_{tag}"] = timed(lambda: pol_ac.get_action(po[:32]), 50)
+            ppo_info[f"update_ms_{tag}"] = timed(lambda: ppo_update(pol_ac, popt, *pdata), 5)
+            ppo_info[f"update_rows_per_sec_{tag}"] = 4 * rows / (ppo_info[f"update_ms_{tag}"] / 1e3)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -500,6 +520,7 @@ def run_ours(args):
                   "frac_of_peak": train_rate * 3 * f_fwd_train / 1e12 / measured_peak_tflops()[0] / world,
                   "collective": "NCCL all-reduce of the flat grad" if world > 1 else "none"},
         "bcf": bcf_info,
+        "ppo": ppo_info,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
