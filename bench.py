@@ -429,7 +429,7 @@ def run_ours(args):
     # default shape (128 steps x 32 processes, 4 epochs x 4 minibatches, --ppo-hidden-dim 64 x --ppo-layers 2)
     ppo_info = None
     if world == 1:
-        from modril_b200.ppo import DistActorCritic, ppo_update
+        from modril_b200.ppo import DistActorCritic, PPOUpdateGraph, ppo_update
 
         ppo_info = {}
         for tag, hid, rows in (("default_h64x2_rows4096", 64, 4096), ("h256x2_rows65536", 256, 65536)):
@@ -443,7 +443,10 @@ def run_ours(args):
                      torch.randn(rows, 1, device=device))
             ppo_info[f"act_ms_B32_{tag}"] = timed(lambda: pol_ac.get_action(po[:32]), 50)
             ppo_info[f"update_ms_{tag}"] = timed(lambda: ppo_update(pol_ac, popt, *pdata), 5)
-            ppo_info[f"update_rows_per_sec_{tag}"] = 4 * rows / (ppo_info[f"update_ms_{tag}"] / 1e3)
+            gopt = FusedAdam([pol_ac], lr=1e-3, eps=1e-12, capturable=True)
+            graphed = PPOUpdateGraph(pol_ac, gopt, rows)
+            ppo_info[f"update_graph_ms_{tag}"] = timed(lambda: graphed(*pdata), 5)
+            ppo_info[f"update_rows_per_sec_{tag}"] = 4 * rows / (ppo_info[f"update_graph_ms_{tag}"] / 1e3)
 
     if rank != 0:
         if world > 1:

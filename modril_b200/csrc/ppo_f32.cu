@@ -11,6 +11,7 @@
 // the kernels (optional int64 row index).  Batch reductions are split and reduced in a fixed order (deterministic).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "frl_internal.h"
@@ -297,6 +298,245 @@ static int ac_prepare(frl_acnet* n, const float* obs, const long long* idx, long
     return FRL_OK;
 }
 
+// ---- fused minibatch kernel for nets that fit in shared memory (the reference's 64 x 2 default) ------------------------
+// One CTA keeps BOTH nets' weights in shared memory (natural [H][K] layout read straight from the flat parameter vector,
+// rows padded to K+1 so that the forward pass (threads over j) and the dgrad (threads over k) are both bank-conflict
+// free) and walks its row tiles: gather -> critic / actor forward -> PPO loss per row -> both backward passes -> weight
+// gradient partials.  A CTA accumulates its partials in its own row of `part` (no atomics: fixed tile -> CTA mapping, fixed
+// order), ppo_fused_reduce_kernel sums the rows.  Two launches per minibatch instead of ~35.
+struct FusedOffs {
+    int off_w[2][kAcMaxLayers], off_b[2][kAcMaxLayers], off_hw[2], off_hb[2], off_logstd, n_params;
+};
+
+__device__ __forceinline__ void emit(float* p, float v, bool first) { *p = first ? v : *p + v; }
+
+__global__ void __launch_bounds__(256) ppo_fused_kernel(const float* __restrict__ params, FusedOffs fo, const float* __restrict__ obs,
+                                                        const float* __restrict__ action, const float* __restrict__ old_logp,
+                                                        const float* __restrict__ adv, const float* __restrict__ ret,
+                                                        const float* __restrict__ old_value, const long long* __restrict__ idx,
+                                                        long long B, int S, int A, int H, int L, int R, float clip,
+                                                        float scale_actor, float scale_value, float* __restrict__ part,
+                                                        int part_stride) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // ---- carve shared memory ----
+    float* p = sm;
+    float *sW[2][kAcMaxLayers], *sb[2][kAcMaxLayers], *sWh[2], *sbh[2];
+    for (int net = 0; net < 2; ++net) {
+        for (int l = 0; l < L; ++l) {
+            const int K = l == 0 ? S : H;
+            sW[net][l] = p; p += H * (K + 1);
+            sb[net][l] = p; p += H;
+        }
+        const int NO = net == 0 ? 1 : A;
+        sWh[net] = p; p += NO * (H + 1);
+        sbh[net] = p; p += NO;
+    }
+    float* slog = p; p += A;
+    float* X = p; p += R * S;
+    float* act[2];
+    for (int net = 0; net < 2; ++net) { act[net] = p; p += L * R * H; }
+    float* dz0 = p; p += R * H;
+    float* dz1 = p; p += R * H;
+    float* outV = p; p += R;            // value, then dL/dvalue
+    float* outM = p; p += R * A;        // mean, then dL/dmean
+    float* rstat = p; p += R * (2 + A); // per row: max(vl, vlc), min(surr), d logstd_j contributions
+    long long* src = reinterpret_cast<long long*>(p + ((p - sm) & 1));   // 8-byte aligned
+
+    // ---- weights: once per CTA ----
+    for (int net = 0; net < 2; ++net) {
+        for (int l = 0; l < L; ++l) {
+            const int K = l == 0 ? S : H;
+            const float* g = params + fo.off_w[net][l];
+            for (int i = tid; i < H * K; i += nt) sW[net][l][(i / K) * (K + 1) + i % K] = g[i];
+            for (int i = tid; i < H; i += nt) sb[net][l][i] = params[fo.off_b[net][l] + i];
+        }
+        const int NO = net == 0 ? 1 : A;
+        for (int i = tid; i < NO * H; i += nt) sWh[net][(i / H) * (H + 1) + i % H] = params[fo.off_hw[net] + i];
+        for (int i = tid; i < NO; i += nt) sbh[net][i] = params[fo.off_hb[net] + i];
+    }
+    for (int i = tid; i < A; i += nt) slog[i] = params[fo.off_logstd + i];
+    float* mypart = part + (size_t)blockIdx.x * part_stride;
+    const long long n_tiles = (B + R - 1) / R;
+    bool first = true;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, first = false) {
+        const long long row0 = tile * R;
+        __syncthreads();   // weights loaded / previous tile done with the buffers
+        for (int r = tid; r < R; r += nt) src[r] = row0 + r < B ? (idx ? idx[row0 + r] : row0 + r) : -1;
+        __syncthreads();
+        for (int i = tid; i < R * S; i += nt) { const long long q = src[i / S]; X[i] = q >= 0 ? obs[q * S + i % S] : 0.f; }
+        __syncthreads();
+        // ---- forward, both nets ----
+        for (int l = 0; l < L; ++l) {
+            const int K = l == 0 ? S : H;
+            for (int o = tid; o < 2 * R * H; o += nt) {
+                const int net = o / (R * H), q = o % (R * H), r = q / H, j = q % H;
+                const float* x = l == 0 ? X + r * S : act[net] + ((size_t)(l - 1) * R + r) * H;
+                const float* w = sW[net][l] + j * (K + 1);
+                float acc = sb[net][l][j];
+                for (int k = 0; k < K; ++k) acc = fmaf(x[k], w[k], acc);
+                act[net][((size_t)l * R + r) * H + j] = tanhf(acc);
+            }
+            __syncthreads();
+        }
+        for (int o = tid; o < R * (1 + A); o += nt) {
+            const int r = o / (1 + A), c = o % (1 + A), net = c == 0 ? 0 : 1, oo = c == 0 ? 0 : c - 1;
+            const float* x = act[net] + ((size_t)(L - 1) * R + r) * H;
+            const float* w = sWh[net] + oo * (H + 1);
+            float acc = sbh[net][oo];
+            for (int k = 0; k < H; ++k) acc = fmaf(x[k], w[k], acc);
+            if (c == 0) outV[r] = acc; else outM[r * A + oo] = acc;
+        }
+        __syncthreads();
+        // ---- PPO loss per row (ppo.py:29-49), same statements as ppo_loss_kernel ----
+        for (int r = tid; r < R; r += nt) {
+            const long long q = src[r];
+            float* st = rstat + r * (2 + A);
+            if (q < 0) {
+                for (int c = 0; c < 2 + A; ++c) st[c] = 0.f;
+                outV[r] = 0.f;
+                for (int j = 0; j < A; ++j) outM[r * A + j] = 0.f;
+                continue;
+            }
+            float* m = outM + r * A;
+            const float value = outV[r];
+            const float logp = row_logp(action + q * A, m, slog, A);
+            const float ratio = expf(logp - old_logp[q]);
+            const float ad = adv[q];
+            const float surr1 = ratio * ad;
+            const float surr2 = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip) * ad;
+            const float w1 = surr1 < surr2 ? 1.f : (surr1 > surr2 ? 0.f : 0.5f);
+            const float in_r = (ratio >= 1.f - clip && ratio <= 1.f + clip) ? 1.f : 0.f;
+            const float d_logp = -(ad * scale_actor) * (w1 + (1.f - w1) * in_r) * ratio;
+            const float ov = old_value[q], rt = ret[q];
+            const float dv = value - ov;
+            const float vpc = ov + fminf(fmaxf(dv, -clip), clip);
+            const float e1 = value - rt, e2 = vpc - rt;
+            const float vl = e1 * e1, vlc = e2 * e2;
+            const float wv = vl > vlc ? 1.f : (vl < vlc ? 0.f : 0.5f);
+            const float in_v = (dv >= -clip && dv <= clip) ? 1.f : 0.f;
+            st[0] = fmaxf(vl, vlc);
+            st[1] = fminf(surr1, surr2);
+            outV[r] = scale_value * (wv * 2.f * e1 + (1.f - wv) * 2.f * e2 * in_v);
+            for (int j = 0; j < A; ++j) {
+                const float scale = expf(slog[j]);
+                const float var = scale * scale;
+                const float d = action[q * A + j] - m[j];
+                st[2 + j] = d_logp * (d * d / var - 1.f);
+                m[j] = d_logp * d / var;
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < 2 + A; c += nt) {
+            float acc = 0.f;
+            for (int r = 0; r < R; ++r) acc += rstat[r * (2 + A) + c];
+            emit(mypart + (c < 2 ? fo.n_params + c : fo.off_logstd + c - 2), acc, first);
+        }
+        // ---- backward, one net after the other (dz buffers are shared) ----
+        for (int net = 0; net < 2; ++net) {
+            const int NO = net == 0 ? 1 : A;
+            const float* dOut = net == 0 ? outV : outM;
+            const float* hL = act[net] + (size_t)(L - 1) * R * H;
+            for (int o = tid; o < NO * H + NO; o += nt) {
+                float acc = 0.f;
+                if (o < NO * H) {
+                    const int oo = o / H, k = o % H;
+                    for (int r = 0; r < R; ++r) acc = fmaf(dOut[r * NO + oo], hL[r * H + k], acc);
+                    emit(mypart + fo.off_hw[net] + o, acc, first);
+                } else {
+                    const int oo = o - NO * H;
+                    for (int r = 0; r < R; ++r) acc += dOut[r * NO + oo];
+                    emit(mypart + fo.off_hb[net] + oo, acc, first);
+                }
+            }
+            for (int o = tid; o < R * H; o += nt) {
+                const int r = o / H, k = o % H;
+                float acc = 0.f;
+                for (int oo = 0; oo < NO; ++oo) acc = fmaf(dOut[r * NO + oo], sWh[net][oo * (H + 1) + k], acc);
+                const float h = hL[o];
+                dz0[o] = acc * (1.f - h * h);
+            }
+            __syncthreads();
+            float *dz = dz0, *dzn = dz1;
+            for (int l = L - 1; l >= 0; --l) {
+                const int K = l == 0 ? S : H;
+                const float* in = l == 0 ? X : act[net] + (size_t)(l - 1) * R * H;
+                for (int o = tid; o < H * K + H; o += nt) {
+                    float acc = 0.f;
+                    if (o < H * K) {
+                        const int j = o / K, k = o % K;
+                        for (int r = 0; r < R; ++r) acc = fmaf(dz[r * H + j], in[r * K + k], acc);
+                        emit(mypart + fo.off_w[net][l] + o, acc, first);
+                    } else {
+                        const int j = o - H * K;
+                        for (int r = 0; r < R; ++r) acc += dz[r * H + j];
+                        emit(mypart + fo.off_b[net][l] + j, acc, first);
+                    }
+                }
+                if (l > 0) {
+                    for (int o = tid; o < R * H; o += nt) {
+                        const int r = o / H, k = o % H;
+                        float acc = 0.f;
+                        for (int j = 0; j < H; ++j) acc = fmaf(dz[r * H + j], sW[net][l][j * (H + 1) + k], acc);
+                        const float h = in[o];
+                        dzn[o] = acc * (1.f - h * h);
+                    }
+                }
+                __syncthreads();
+                float* t = dz; dz = dzn; dzn = t;
+            }
+        }
+    }
+}
+
+// grad (+)= sum over the CTAs' partial rows; the entropy term of d logstd; losses like ppo_loss_final_kernel
+__global__ void ppo_fused_reduce_kernel(const float* __restrict__ part, int n_cta, int part_stride, int n_params, int off_logstd,
+                                        int A, double inv_div, float value_coef, float ent_coef, float ent_share, float grad_scale,
+                                        const float* __restrict__ logstd, float* __restrict__ losses, float* __restrict__ grad,
+                                        int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_params && grad) {
+        float acc = 0.f;
+        for (int c = 0; c < n_cta; ++c) acc += part[(size_t)c * part_stride + i];
+        if (i >= off_logstd && i < off_logstd + A) acc -= grad_scale * ent_coef * ent_share;
+        grad[i] = accumulate ? grad[i] + acc : acc;
+    }
+    if (i == 0 && losses) {
+        double v = 0.0, a = 0.0;
+        for (int c = 0; c < n_cta; ++c) { v += part[(size_t)c * part_stride + n_params]; a += part[(size_t)c * part_stride + n_params + 1]; }
+        const float vl = (float)(0.5 * v * inv_div), al = (float)(-a * inv_div);
+        const float ent = row_entropy(logstd, A);
+        losses[0] = vl * value_coef + al - ent * ent_coef * ent_share;
+        losses[1] = vl;
+        losses[2] = al;
+        losses[3] = ent;
+    }
+}
+
+struct FusedPlan {
+    bool ok;
+    int R, n_cta;
+    size_t smem;
+};
+static FusedPlan plan_fused(const frl_acnet* n, long long B) {
+    const int H = n->cfg.hidden, S = n->cfg.obs_dim, A = n->cfg.a_dim, L = n->cfg.layers;
+    size_t w = 0;
+    for (int l = 0; l < L; ++l) w += (size_t)H * ((l == 0 ? S : H) + 1) + H;
+    w = 2 * w + (size_t)(1 + A) * (H + 1) + 1 + A + A;
+    FusedPlan best{false, 0, 0, 0};
+    const int cand[3] = {32, 16, 8};
+    for (int R : cand) {
+        // small minibatches: 8-row tiles spread the rows over the SMs
+        if (R > 8 && (B + 7) / 8 <= 296) continue;
+        const size_t acts = (size_t)R * S + 2 * (size_t)L * R * H + 2 * (size_t)R * H + R + (size_t)R * A + (size_t)R * (2 + A);
+        const size_t bytes = (w + acts + 2) * sizeof(float) + (size_t)R * sizeof(long long);
+        if (bytes > 200 * 1024) continue;
+        best = FusedPlan{true, R, (int)std::min<long long>((B + R - 1) / R, 296), bytes};
+        break;
+    }
+    return best;
+}
+
 }  // namespace frl
 
 using namespace frl;
@@ -416,6 +656,36 @@ extern "C" int frl_ppo_loss_grad(frl_acnet* n, const float* obs, const float* ac
     const int H = n->cfg.hidden, S = n->cfg.obs_dim, A = n->cfg.a_dim, L = n->cfg.layers, Aop = n->Aop;
     const int R = (int)B;
     const double div = (double)(mean_divisor > 0 ? mean_divisor : B);
+
+    // nets that fit in shared memory: one fused kernel + a reduction (FRL_PPO_GEMM=1 forces the per-layer GEMM path)
+    const FusedPlan fp = plan_fused(n, B);
+    if (fp.ok && !getenv("FRL_PPO_GEMM")) {
+        const int stride = round_up((int)n->n_params + 2, 4);
+        int rc = acnet_ws(n, (size_t)fp.n_cta * stride);
+        if (rc != FRL_OK) return rc;
+        static bool attr_done[64] = {};
+        if (!attr_done[n->cfg.device & 63]) {
+            FRL_CUDA(cudaFuncSetAttribute(ppo_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done[n->cfg.device & 63] = true;
+        }
+        FusedOffs fo;
+        for (int net = 0; net < 2; ++net) {
+            for (int l = 0; l < L; ++l) { fo.off_w[net][l] = (int)n->off_w[net][l]; fo.off_b[net][l] = (int)n->off_b[net][l]; }
+            fo.off_hw[net] = (int)n->off_hw[net];
+            fo.off_hb[net] = (int)n->off_hb[net];
+        }
+        fo.off_logstd = (int)n->off_logstd;
+        fo.n_params = (int)n->n_params;
+        ppo_fused_kernel<<<fp.n_cta, 256, fp.smem, st>>>(n->params_dev, fo, obs, action, old_logp, adv, ret, old_value, idx, B, S, A, H,
+                                                        L, fp.R, clip_param, (float)((double)grad_scale / div),
+                                                        (float)((double)grad_scale * 0.5 * value_loss_coef / div), n->ws, stride);
+        FRL_CUDA(cudaGetLastError());
+        ppo_fused_reduce_kernel<<<((int)n->n_params + 255) / 256, 256, 0, st>>>(
+            n->ws, fp.n_cta, stride, (int)n->n_params, (int)n->off_logstd, A, 1.0 / div, value_loss_coef, entropy_coef,
+            (float)((double)B / div), grad_scale, n->params_dev + n->off_logstd, losses, grad, accumulate);
+        FRL_CUDA(cudaGetLastError());
+        return FRL_OK;
+    }
 
     auto plan_splits = [&](int tiles) {
         int want = std::max(1, 296 / std::max(1, tiles));

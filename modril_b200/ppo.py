@@ -240,3 +240,76 @@ def ppo_update(policy: DistActorCritic, opt: FusedAdam, obs, actions, action_log
     n = num_epochs * num_mini_batch                                   # ppo.py:59-64
     return {"value_loss": a[1] / n, "actor_loss": a[2] / n, "dist_entropy": a[3] / n,
             "policy_update_data": float(num_mini_batch * n_updates)}
+
+
+class PPOUpdateGraph:
+    """``ppo_update`` captured ONCE as a CUDA graph and replayed per ``PPO.update``: all ``num_epochs x num_mini_batch``
+    minibatches (weight re-pack, forward, loss, backward, clip, Adam: ~40 small launches each at the reference's size) cost
+    one graph launch instead of ~600 kernel launches driven from Python.  The rollout tensors are copied into static
+    buffers and the sampler's permutations are written into a static index buffer before the replay.
+
+    ``opt`` must be a ``FusedAdam([policy], ..., capturable=True)`` (step count on the device)."""
+
+    def __init__(self, policy: DistActorCritic, opt: FusedAdam, rows: int, *, num_epochs=4, num_mini_batch=4, clip_param=0.2,
+                 value_loss_coef=0.5, entropy_coef=0.01, max_grad_norm=0.5):
+        if opt._step_dev is None:
+            raise ValueError("PPOUpdateGraph needs FusedAdam(..., capturable=True)")
+        if rows < num_mini_batch:
+            raise ValueError(f"PPO requires T*N ({rows}) >= num_mini_batch ({num_mini_batch})")
+        dev = policy.flat_params().device
+        self.policy, self.opt, self.rows = policy, opt, int(rows)
+        self.num_epochs, self.num_mini_batch = int(num_epochs), int(num_mini_batch)
+        self._obs = torch.zeros(rows, policy.obs_dim, device=dev)
+        self._act = torch.zeros(rows, policy.action_dim, device=dev)
+        self._cols = [torch.zeros(rows, device=dev) for _ in range(4)]      # prev_log_prob, value_preds, returns, adv
+        self._perm = torch.arange(rows, device=dev).repeat(num_epochs, 1).contiguous()
+        self._acc = torch.zeros(4, device=dev)
+        mb = rows // num_mini_batch
+        max_norm = max_grad_norm if max_grad_norm > 0 else float("inf")
+        kw = dict(clip_param=clip_param, value_loss_coef=value_loss_coef, entropy_coef=entropy_coef)
+
+        def minibatch(e, k):
+            losses = policy.ppo_loss(self._obs, self._act, self._cols[0], self._cols[3], self._cols[2], self._cols[1],
+                                     indices=self._perm[e, k * mb:(k + 1) * mb], **kw)
+            opt.step_flat([policy.flat_grad()], max_norm=max_norm)
+            self._acc += losses
+
+        # warm-up outside the capture (workspaces, the optimiser's buffers), then put the state back
+        snap = [t.clone() for t in (policy.flat_params(), opt._m[0], opt._v[0], opt._step_dev)]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            minibatch(0, 0)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        with torch.no_grad():
+            for dst, src in zip((policy.flat_params(), opt._m[0], opt._v[0], opt._step_dev), snap):
+                dst.copy_(src)
+        policy.mark_dirty()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._acc.zero_()
+            for e in range(self.num_epochs):
+                for k in range(rows // mb):
+                    minibatch(e, k)
+        # the capture itself does not execute anything, but it left the module's pack key pointing at "packed"
+        policy.mark_dirty()
+
+    def __call__(self, obs, actions, action_log_probs, value_preds, returns, advantages, perms=None):
+        """Same arguments and return value as ``ppo_update``."""
+        with torch.no_grad():
+            self._obs.copy_(obs.reshape(self.rows, -1))
+            self._act.copy_(actions.reshape(self.rows, -1))
+            for dst, src in zip(self._cols, (action_log_probs, value_preds, returns, advantages)):
+                dst.copy_(src.reshape(-1))
+            for e in range(self.num_epochs):
+                if perms is not None:
+                    self._perm[e].copy_(perms[e])
+                else:
+                    torch.randperm(self.rows, device=self._perm.device, out=self._perm[e])
+        self._graph.replay()
+        self.policy.mark_dirty()
+        a = self._acc.tolist()
+        n = self.num_epochs * self.num_mini_batch
+        n_updates = self.num_epochs * (self.rows // (self.rows // self.num_mini_batch))
+        return {"value_loss": a[1] / n, "actor_loss": a[2] / n, "dist_entropy": a[3] / n,
+                "policy_update_data": float(self.num_mini_batch * n_updates)}

@@ -49,8 +49,19 @@ def test_state_dict_keys_and_init_match_reference_policy():
         m.get_value(torch.zeros(2, 11))                                                       # CPU tensors: no fallback
 
 
+@pytest.fixture(params=["fused", "gemm"])
+def kernel_path(request, monkeypatch):
+    """frl_ppo_loss_grad has two CUDA paths: the fused shared-memory kernel (nets that fit; the default) and the per-layer
+    GEMM path (FRL_PPO_GEMM=1 forces it).  Both must meet the same bar."""
+    if request.param == "gemm":
+        monkeypatch.setenv("FRL_PPO_GEMM", "1")
+    else:
+        monkeypatch.delenv("FRL_PPO_GEMM", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "ppo_*.npz"))), ids=os.path.basename)
-def test_policy_loss_grad_vs_reference(path):
+def test_policy_loss_grad_vs_reference(path, kernel_path):
     g = np.load(path)
     s_dim, a_dim, hidden, layers, B, seed = (int(x) for x in g["meta"])
     clip, vcoef, ecoef = (float(x) for x in g["coefs"])
@@ -141,10 +152,38 @@ def test_ppo_update_follows_reference_curve(path):
     assert torch.isfinite(m2.flat_params()).all()
 
 
-def test_large_ragged_batch_matches_oracle_and_is_deterministic():
-    spec = pcf.ACSpec(17, 6, 256, 2)
+def test_graphed_update_equals_eager_update():
+    """PPOUpdateGraph (one CUDA-graph replay per PPO.update) == ppo_update with the same capturable optimiser, bit for bit,
+    over two consecutive updates with different data."""
+    from modril_b200.ppo import FusedAdam, PPOUpdateGraph, ppo_update
+
+    spec = pcf.ACSpec(11, 3, 64, 2)
+    flat = pcf.ac_make_params(spec, 5)
+    rows, nmb, epochs = 1000, 4, 3                      # 1000 // 4 = 250-row minibatches
+    pols = [build_policy(spec, flat) for _ in range(2)]
+    opts = [FusedAdam([p], lr=1e-3, eps=1e-12, capturable=True) for p in pols]
+    graphed = PPOUpdateGraph(pols[1], opts[1], rows, num_epochs=epochs, num_mini_batch=nmb)
+    assert torch.equal(pols[1].flat_params().cpu(), torch.from_numpy(flat)) and opts[1].step_count() == 0   # warm-up undone
+    for rnd in range(2):
+        obs, action, old_logp, adv, ret, old_value, _ = ppo_inputs(spec, flat, 50 + rnd, rows)
+        data = (dev(obs), dev(action), dev(old_logp), dev(old_value), dev(ret), dev(adv))
+        perms = [torch.from_numpy(synth.rng(60 + 10 * rnd + e).permutation(rows)).cuda() for e in range(epochs)]
+        la = ppo_update(pols[0], opts[0], *data, num_epochs=epochs, num_mini_batch=nmb, perms=perms)
+        lb = graphed(*data, perms=perms)
+        assert la == lb
+        assert torch.equal(pols[0].flat_params(), pols[1].flat_params())
+        assert opts[0].step_count() == opts[1].step_count() == (rnd + 1) * epochs * nmb
+        # the policy is usable right after a replay (weights re-packed): same values from both
+        assert torch.equal(pols[0].get_value(data[0]), pols[1].get_value(data[0]))
+    graphed(*data)                                       # own permutations
+    assert torch.isfinite(pols[1].flat_params()).all()
+
+
+@pytest.mark.parametrize("hidden", [64, 128, 256])
+def test_large_ragged_batch_matches_oracle_and_is_deterministic(hidden, kernel_path):
+    spec = pcf.ACSpec(17, 6, hidden, 2)          # 64 / 128: fused kernel with several tiles per CTA; 256: GEMM path
     flat = pcf.ac_make_params(spec, 77)
-    B = 4099
+    B = 4099 if hidden == 256 else 20011
     obs, action, old_logp, adv, ret, old_value, _ = ppo_inputs(spec, flat, 770, B)
     m = build_policy(spec, flat)
     args = [dev(x) for x in (obs, action, old_logp, adv, ret, old_value)]
