@@ -314,6 +314,13 @@ int frl_ppo_loss_grad(frl_acnet* net, const float* obs_dev, const float* action_
                       long long B, long long mean_divisor, float clip_param, float value_loss_coef, float entropy_coef,
                       float grad_scale, int accumulate, float* losses_dev, float* grad_dev, void* stream);
 
+/* ---- offline pre-trainer: demonstration pre-processing (modril/flowril/pretrain.py:33-39, :269-285) -----------------
+ * frl_column_moments: mean = x.mean(0), std = x.std(0) (unbiased) of x [n,d] -> mean_dev [d], std_dev [d].
+ * frl_norm_vec: norm_vec(x, mean, std) = clamp((x - mean) / (std + 1e-8), -10, 10) -> out_dev [n,d] (may alias x_dev). */
+int frl_column_moments(const float* x_dev, long long n, int d, float* mean_dev, float* std_dev, int device, void* stream);
+int frl_norm_vec(const float* x_dev, const float* mean_dev, const float* std_dev, long long n, int d, float* out_dev,
+                 int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ EXPORTS = (
     "frl_vnet_create", "frl_vnet_destroy", "frl_vnet_num_params", "frl_vnet_set_params", "frl_vnet_forward",
     "frl_vnet_sample", "frl_bcf_loss_grad", "frl_compute_returns", "frl_normalise_advantages", "frl_cfm_loss_grad_pair",
     "frl_acnet_create", "frl_acnet_destroy", "frl_acnet_num_params", "frl_acnet_set_params", "frl_acnet_forward",
-    "frl_acnet_act", "frl_acnet_evaluate", "frl_ppo_loss_grad",
+    "frl_acnet_act", "frl_acnet_evaluate", "frl_ppo_loss_grad", "frl_column_moments", "frl_norm_vec",
 )
 
 
@@ -108,6 +108,8 @@ def lib():
     L.frl_acnet_forward.argtypes = [vp, vp, ll, vp, vp, vp]
     L.frl_acnet_act.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp, vp]
     L.frl_acnet_evaluate.argtypes = [vp, vp, vp, ll, vp, vp, vp, vp]
+    L.frl_column_moments.argtypes = [vp, ll, i32, vp, vp, i32, vp]
+    L.frl_norm_vec.argtypes = [vp, vp, vp, ll, i32, vp, i32, vp]
     L.frl_ppo_loss_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, f32, f32, f32, f32, i32, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

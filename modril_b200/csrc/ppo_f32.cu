@@ -310,7 +310,7 @@ struct FusedOffs {
 
 __device__ __forceinline__ void emit(float* p, float v, bool first) { *p = first ? v : *p + v; }
 
-__global__ void __launch_bounds__(256) ppo_fused_kernel(const float* __restrict__ params, FusedOffs fo, const float* __restrict__ obs,
+__global__ void __launch_bounds__(512) ppo_fused_kernel(const float* __restrict__ params, FusedOffs fo, const float* __restrict__ obs,
                                                         const float* __restrict__ action, const float* __restrict__ old_logp,
                                                         const float* __restrict__ adv, const float* __restrict__ ret,
                                                         const float* __restrict__ old_value, const long long* __restrict__ idx,
@@ -320,18 +320,13 @@ __global__ void __launch_bounds__(256) ppo_fused_kernel(const float* __restrict_
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, nt = blockDim.x;
     // ---- carve shared memory ----
-    float* p = sm;
-    float *sW[2][kAcMaxLayers], *sb[2][kAcMaxLayers], *sWh[2], *sbh[2];
-    for (int net = 0; net < 2; ++net) {
-        for (int l = 0; l < L; ++l) {
-            const int K = l == 0 ? S : H;
-            sW[net][l] = p; p += H * (K + 1);
-            sb[net][l] = p; p += H;
-        }
-        const int NO = net == 0 ? 1 : A;
-        sWh[net] = p; p += NO * (H + 1);
-        sbh[net] = p; p += NO;
-    }
+    // weights: [critic trunk][actor trunk][critic head][actor head]; layer l of a trunk at a closed-form offset
+    const int L0 = H * (S + 1) + H, LH = H * (H + 1) + H, T = L0 + (L - 1) * LH;
+    auto sWl = [&](int net, int l) { return sm + net * T + (l == 0 ? 0 : L0 + (l - 1) * LH); };
+    auto sbl = [&](int net, int l) { return sWl(net, l) + H * ((l == 0 ? S : H) + 1); };
+    auto sWhd = [&](int net) { return sm + 2 * T + (net == 0 ? 0 : (H + 1) + 1); };
+    auto sbhd = [&](int net) { return sWhd(net) + (net == 0 ? 1 : A) * (H + 1); };
+    float* p = sm + 2 * T + (1 + A) * (H + 1) + 1 + A;
     float* slog = p; p += A;
     float* X = p; p += R * S;
     float* act[2];
@@ -348,12 +343,12 @@ __global__ void __launch_bounds__(256) ppo_fused_kernel(const float* __restrict_
         for (int l = 0; l < L; ++l) {
             const int K = l == 0 ? S : H;
             const float* g = params + fo.off_w[net][l];
-            for (int i = tid; i < H * K; i += nt) sW[net][l][(i / K) * (K + 1) + i % K] = g[i];
-            for (int i = tid; i < H; i += nt) sb[net][l][i] = params[fo.off_b[net][l] + i];
+            for (int i = tid; i < H * K; i += nt) sWl(net, l)[(i / K) * (K + 1) + i % K] = g[i];
+            for (int i = tid; i < H; i += nt) sbl(net, l)[i] = params[fo.off_b[net][l] + i];
         }
         const int NO = net == 0 ? 1 : A;
-        for (int i = tid; i < NO * H; i += nt) sWh[net][(i / H) * (H + 1) + i % H] = params[fo.off_hw[net] + i];
-        for (int i = tid; i < NO; i += nt) sbh[net][i] = params[fo.off_hb[net] + i];
+        for (int i = tid; i < NO * H; i += nt) sWhd(net)[(i / H) * (H + 1) + i % H] = params[fo.off_hw[net] + i];
+        for (int i = tid; i < NO; i += nt) sbhd(net)[i] = params[fo.off_hb[net] + i];
     }
     for (int i = tid; i < A; i += nt) slog[i] = params[fo.off_logstd + i];
     float* mypart = part + (size_t)blockIdx.x * part_stride;
@@ -372,8 +367,8 @@ __global__ void __launch_bounds__(256) ppo_fused_kernel(const float* __restrict_
             for (int o = tid; o < 2 * R * H; o += nt) {
                 const int net = o / (R * H), q = o % (R * H), r = q / H, j = q % H;
                 const float* x = l == 0 ? X + r * S : act[net] + ((size_t)(l - 1) * R + r) * H;
-                const float* w = sW[net][l] + j * (K + 1);
-                float acc = sb[net][l][j];
+                const float* w = sWl(net, l) + j * (K + 1);
+                float acc = sbl(net, l)[j];
                 for (int k = 0; k < K; ++k) acc = fmaf(x[k], w[k], acc);
                 act[net][((size_t)l * R + r) * H + j] = tanhf(acc);
             }
@@ -382,8 +377,8 @@ __global__ void __launch_bounds__(256) ppo_fused_kernel(const float* __restrict_
         for (int o = tid; o < R * (1 + A); o += nt) {
             const int r = o / (1 + A), c = o % (1 + A), net = c == 0 ? 0 : 1, oo = c == 0 ? 0 : c - 1;
             const float* x = act[net] + ((size_t)(L - 1) * R + r) * H;
-            const float* w = sWh[net] + oo * (H + 1);
-            float acc = sbh[net][oo];
+            const float* w = sWhd(net) + oo * (H + 1);
+            float acc = sbhd(net)[oo];
             for (int k = 0; k < H; ++k) acc = fmaf(x[k], w[k], acc);
             if (c == 0) outV[r] = acc; else outM[r * A + oo] = acc;
         }
@@ -452,7 +447,7 @@ __global__ void __launch_bounds__(256) ppo_fused_kernel(const float* __restrict_
             for (int o = tid; o < R * H; o += nt) {
                 const int r = o / H, k = o % H;
                 float acc = 0.f;
-                for (int oo = 0; oo < NO; ++oo) acc = fmaf(dOut[r * NO + oo], sWh[net][oo * (H + 1) + k], acc);
+                for (int oo = 0; oo < NO; ++oo) acc = fmaf(dOut[r * NO + oo], sWhd(net)[oo * (H + 1) + k], acc);
                 const float h = hL[o];
                 dz0[o] = acc * (1.f - h * h);
             }
@@ -477,7 +472,7 @@ __global__ void __launch_bounds__(256) ppo_fused_kernel(const float* __restrict_
                     for (int o = tid; o < R * H; o += nt) {
                         const int r = o / H, k = o % H;
                         float acc = 0.f;
-                        for (int j = 0; j < H; ++j) acc = fmaf(dz[r * H + j], sW[net][l][j * (H + 1) + k], acc);
+                        for (int j = 0; j < H; ++j) acc = fmaf(dz[r * H + j], sWl(net, l)[j * (H + 1) + k], acc);
                         const float h = in[o];
                         dzn[o] = acc * (1.f - h * h);
                     }
@@ -494,14 +489,21 @@ __global__ void ppo_fused_reduce_kernel(const float* __restrict__ part, int n_ct
                                         int A, double inv_div, float value_coef, float ent_coef, float ent_share, float grad_scale,
                                         const float* __restrict__ logstd, float* __restrict__ losses, float* __restrict__ grad,
                                         int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_params && grad) {
-        float acc = 0.f;
-        for (int c = 0; c < n_cta; ++c) acc += part[(size_t)c * part_stride + i];
+    // block (32 parameters, 8 row groups): group y adds the partial rows y, y+8, ...; the 8 sums are added in a fixed order
+    __shared__ float sh[8][33];
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (i < n_params && grad)
+        for (int c = threadIdx.y; c < n_cta; c += 8) acc += part[(size_t)c * part_stride + i];
+    sh[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < n_params && grad) {
+        acc = sh[0][threadIdx.x];
+        for (int y = 1; y < 8; ++y) acc += sh[y][threadIdx.x];
         if (i >= off_logstd && i < off_logstd + A) acc -= grad_scale * ent_coef * ent_share;
         grad[i] = accumulate ? grad[i] + acc : acc;
     }
-    if (i == 0 && losses) {
+    if (i == 0 && threadIdx.y == 1 && losses) {
         double v = 0.0, a = 0.0;
         for (int c = 0; c < n_cta; ++c) { v += part[(size_t)c * part_stride + n_params]; a += part[(size_t)c * part_stride + n_params + 1]; }
         const float vl = (float)(0.5 * v * inv_div), al = (float)(-a * inv_div);
@@ -676,11 +678,11 @@ extern "C" int frl_ppo_loss_grad(frl_acnet* n, const float* obs, const float* ac
         }
         fo.off_logstd = (int)n->off_logstd;
         fo.n_params = (int)n->n_params;
-        ppo_fused_kernel<<<fp.n_cta, 256, fp.smem, st>>>(n->params_dev, fo, obs, action, old_logp, adv, ret, old_value, idx, B, S, A, H,
+        ppo_fused_kernel<<<fp.n_cta, 512, fp.smem, st>>>(n->params_dev, fo, obs, action, old_logp, adv, ret, old_value, idx, B, S, A, H,
                                                         L, fp.R, clip_param, (float)((double)grad_scale / div),
                                                         (float)((double)grad_scale * 0.5 * value_loss_coef / div), n->ws, stride);
         FRL_CUDA(cudaGetLastError());
-        ppo_fused_reduce_kernel<<<((int)n->n_params + 255) / 256, 256, 0, st>>>(
+        ppo_fused_reduce_kernel<<<((int)n->n_params + 31) / 32, dim3(32, 8), 0, st>>>(
             n->ws, fp.n_cta, stride, (int)n->n_params, (int)n->off_logstd, A, 1.0 / div, value_loss_coef, entropy_coef,
             (float)((double)B / div), grad_scale, n->params_dev + n->off_logstd, losses, grad, accumulate);
         FRL_CUDA(cudaGetLastError());

@@ -638,3 +638,218 @@ def _train_step_grad(terms, opt, world, reg, precision):
     if reg is not None:
         reg["out"] = rout
     return losses
+
+
+# ------------------------------------------------------------------------------------------------------------
+# offline pre-training (reference pretrain.py:217-526, the ``__main__`` of the module) with a device-resident sampler
+# ------------------------------------------------------------------------------------------------------------
+def norm_vec(x, mean, std):
+    """``clamp((x - mean) / (std + 1e-8), -10, 10)`` (reference pretrain.py:33-39) as one ``frl_norm_vec`` launch."""
+    dev = x.device
+    x = as_f32_cuda(x, dev, "x")
+    mean, std = as_f32_cuda(mean, dev, "mean").reshape(-1), as_f32_cuda(std, dev, "std").reshape(-1)
+    if x.dim() != 2 or mean.numel() != x.shape[1] or std.numel() != x.shape[1]:
+        raise ValueError("norm_vec expects x [n,d] and mean / std [d]")
+    out = torch.empty_like(x)
+    _native.check(_native.lib().frl_norm_vec(_ptr(x), _ptr(mean), _ptr(std), x.shape[0], x.shape[1], _ptr(out),
+                                             dev.index or 0, _current_stream(dev)), "frl_norm_vec")
+    return out
+
+
+def column_moments(x):
+    """``x.mean(0), x.std(0)`` (unbiased) of a CUDA matrix [n,d] in one ``frl_column_moments`` launch."""
+    dev = x.device
+    x = as_f32_cuda(x, dev, "x")
+    mean, std = torch.empty(x.shape[1], device=dev), torch.empty(x.shape[1], device=dev)
+    _native.check(_native.lib().frl_column_moments(_ptr(x), x.shape[0], x.shape[1], _ptr(mean), _ptr(std), dev.index or 0,
+                                                   _current_stream(dev)), "frl_column_moments")
+    return mean, std
+
+
+class _TorchDraws:
+    """The random draws of one pre-training batch, from torch's global RNG in the reference's order (pretrain.py:368-378:
+    fm_loss(expert) -> rand, Normal.sample; randn_like(a); fm_loss(agent) -> rand, Normal.sample; rand_like(t_noise))."""
+
+    def __init__(self, device, a_dim, eps):
+        self.device, self.a_dim, self.eps = device, a_dim, eps
+
+    def perm(self, n):                       # DataLoader(shuffle=True)
+        return torch.randperm(n, device=self.device)
+
+    def cfm(self, B):
+        t = torch.rand(B, 1, device=self.device) * (1 - 2 * self.eps) + self.eps
+        return t, torch.randn(B, self.a_dim, device=self.device)
+
+    def normal(self, B):                     # randn_like(a): the agent perturbation (scrf) / the dequantisation (2fs)
+        return torch.randn(B, self.a_dim, device=self.device)
+
+    def t_mix(self, B):
+        return torch.rand(B, 1, device=self.device)
+
+
+class OfflinePretrainer:
+    """The training loop of the reference's offline pre-trainer (pretrain.py:269-440) with the demonstrations resident in
+    HBM: optional ``norm_vec`` of observations and actions with their own column moments (:273-285), the odd-row rule
+    (:289-290), shuffled 128-row batches (:297; the last one ragged), and per batch
+
+      scrf: ``fm_loss(s, a, expert) + fm_loss(s, a + 0.1 randn, agent)`` (:368-372) plus the anti-divergence /
+            Jacobian-stability terms on ``(s, a_noise)`` (:374-381) with fixed weights (``autotune`` false, :383-387) or the
+            warm-up weights ``L_E / (L_reg + 1e-8) * 1e-3`` (:391-402; the reference never leaves this branch because
+            ``gradnorm(...)`` is only called after it), ``clip_grad_norm_(1)`` and Adam (:417-420);
+      2fs:  ``FlowMatching.fm_loss(s, a)`` (:414-415).
+
+    Every batch is one ``train_step`` (fused loss + gradient kernels, clip + Adam kernel); nothing is copied to the host
+    inside an epoch.  ``draws`` (tests) replaces the torch RNG: an object with ``perm / cfm / normal / t_mix``."""
+
+    def __init__(self, obs, actions, *, option="scrf", hidden_dim=128, depth=4, eps=1e-2, lr=1e-4, norm=True,
+                 enable_loss_anti=True, enable_loss_stable=True, autotune=True, loss_anti=1e-4, loss_stable=1e-6,
+                 batch_size=128, device="cuda", precision=None):
+        if option not in ("scrf", "2fs"):
+            raise NotImplementedError(option)
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("the pre-trainer computes only on CUDA (sm_100a) devices; there is no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        obs = torch.as_tensor(obs).to(dev, torch.float32).contiguous()
+        actions = torch.as_tensor(actions).to(dev, torch.float32).contiguous()
+        if obs.dim() != 2 or actions.dim() != 2 or obs.shape[0] != actions.shape[0]:
+            raise ValueError("obs [n,s_dim] and actions [n,a_dim] must have the same number of rows")
+        self.obs_moments = self.action_moments = None
+        if norm:
+            self.obs_moments = column_moments(obs)
+            obs = norm_vec(obs, *self.obs_moments)
+            self.action_moments = column_moments(actions)
+            actions = norm_vec(actions, *self.action_moments)
+        if obs.shape[0] % 2 == 1:                                    # pretrain.py:289-290
+            obs, actions = obs[1:].contiguous(), actions[1:].contiguous()
+        self.obs, self.actions = obs, actions
+        self.s_dim, self.a_dim = obs.shape[1], actions.shape[1]
+        self.option, self.batch_size, self.precision, self.device = option, int(batch_size), precision, dev
+        self.autotune = bool(autotune)
+        if option == "scrf":
+            self.estimator = CoupledResidualFM(self.s_dim, self.a_dim, hidden_dim, depth=depth, eps=eps).to(dev)
+        else:
+            self.estimator = FlowMatching(self.s_dim, self.a_dim, hidden_dim, depth=depth, eps=eps).to(dev)
+        self.estimator.train()
+        self.opt = FusedAdam([self.estimator.net], lr=lr)
+        w_a = float(loss_anti) if enable_loss_anti else 0.0          # pretrain.py:336-339
+        w_s = float(loss_stable) if enable_loss_stable else 0.0
+        self._w_init = (w_a, w_s)
+        self._w_anti = torch.tensor([w_a, 0.0], device=dev)          # args.loss_anti / args.loss_stable on the device
+        self._w_stable = torch.tensor([w_s, 0.0], device=dev)
+        self.train_loss_list = []
+        self.steps = 0
+
+    # one batch: rows `i` of the resident dataset
+    def _step(self, i, draws):
+        s, a = self.obs[i], self.actions[i]
+        B = a.shape[0]
+        net = self.estimator.net
+        if self.option == "2fs":
+            a0 = a + draws.normal(B) * 0.02                          # FlowMatching.fm_loss dequantisation (:98)
+            t, noise = draws.cfm(B)
+            losses = train_step([dict(net=net, sign=1.0, s=s, a0=a0, t=t, noise=noise, rate=1.0)], self.opt, max_norm=1.0,
+                                precision=self.precision)
+            return losses[0], losses[0]
+        tE, nE = draws.cfm(B)
+        a_noise = a + 0.1 * draws.normal(B)                          # :370-371
+        tA, nA = draws.cfm(B)
+        terms = [dict(net=net, sign=1.0, s=s, a0=a, t=tE, noise=nE, rate=1.0),
+                 dict(net=net, sign=-1.0, s=s, a0=a_noise, t=tA, noise=nA, rate=1.0)]
+        reg = None
+        if self._w_init[0] > 0 or self._w_init[1] > 0:               # use_anti / use_stable (:374-376)
+            spec = ("warmup", 1e-3, 1e-8) if self.autotune else None
+            reg = dict(net=net, s=s, a=a_noise, t=draws.t_mix(B), probe=_rademacher((B, self.a_dim), device=self.device),
+                       anti=(spec or self._w_init[0]) if self._w_init[0] > 0 else None,
+                       stable=(spec or self._w_init[1]) if self._w_init[1] > 0 else None,
+                       gate_anti=self._w_anti, gate_stable=self._w_stable)
+        lE, lA = train_step(terms, self.opt, max_norm=1.0, reg=reg, precision=self.precision)
+        loss = lE + lA
+        if reg is not None and reg.get("out"):
+            out = reg["out"]
+            if "loss_anti" in out:
+                loss = loss + self._w_anti[0] * out["loss_anti"].reshape(())
+            if "loss_stable" in out:
+                loss = loss + self._w_stable[0] * out["loss_stable"].reshape(())
+        return loss, lE
+
+    def epoch(self, draws=None):
+        """One pass over the demonstrations (pretrain.py:362-440); returns the device tensor of per-batch
+        ``[loss, loss_expert]`` rows and appends the epoch's average loss to ``train_loss_list``."""
+        draws = draws or _TorchDraws(self.device, self.a_dim, self.estimator.eps)
+        n = self.obs.shape[0]
+        perm = draws.perm(n)
+        rows = []
+        for k in range(0, n, self.batch_size):
+            loss, l_e = self._step(perm[k:k + self.batch_size], draws)
+            rows.append(torch.stack([loss.reshape(()), l_e.reshape(())]))
+            self.steps += 1
+        out = torch.stack(rows)
+        self.train_loss_list.append(float(out[:, 0].mean()))        # the epoch's one device->host copy
+        return out
+
+    def fit(self, num_epoch, log_every=0):
+        for t in range(1, num_epoch + 1):
+            self.epoch()
+            if log_every and t % log_every == 0:
+                print(f"epoch {t}: loss {self.train_loss_list[-1]:.6f}", flush=True)
+        return self.train_loss_list
+
+    def save(self, save_path, env, task):
+        """The reference's files (pretrain.py:520-526): ``<save_path>/<env>/<task>/trained_models/<env>_fm.pt`` (the
+        estimator's ``state_dict``, loadable through ``--flow-path``) and ``<env>_train_loss.pt``."""
+        import os
+
+        d = os.path.join(save_path, env, task, "trained_models")
+        os.makedirs(d, exist_ok=True)
+        torch.save({k: v.detach().cpu() for k, v in self.estimator.state_dict().items()}, os.path.join(d, f"{env}_fm.pt"))
+        torch.save(self.train_loss_list, os.path.join(d, f"{env}_train_loss.pt"))
+        return d
+
+
+def main(argv=None):
+    """``python -m modril_b200.flowril.pretrain`` -- the reference's command line (pretrain.py:217-262), same flags."""
+    import argparse
+
+    str2bool = lambda v: v.lower() == "true"
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--traj-load-path', type=str, default='modril/expert_datasets/sine.pt')
+    parser.add_argument('--hidden-dim', type=int, default=128)
+    parser.add_argument('--depth', type=int, default=4)
+    parser.add_argument('--norm', type=str2bool, default=True)
+    parser.add_argument('--lr', type=float, default=1e-4)
+    parser.add_argument('--eps', type=float, default=1e-2)
+    parser.add_argument('--option', type=str, default='scrf', choices=['scrf', '2fs'])
+    parser.add_argument('--num-epoch', type=int, default=8000)
+    parser.add_argument('--prefix', type=str, default='')
+    parser.add_argument('--save-path', type=str, default='data/pre')
+    parser.add_argument('--enable-loss-anti', type=str2bool, default=True)
+    parser.add_argument('--enable-loss-stable', type=str2bool, default=True)
+    parser.add_argument('--autotune', type=str2bool, default=True)
+    parser.add_argument('--loss-anti', type=float, default=1e-4)
+    parser.add_argument('--loss-stable', type=float, default=1e-6)
+    args = parser.parse_args(argv)
+    task = args.option                                               # pretrain.py:240-251
+    if not args.enable_loss_anti and args.enable_loss_stable:
+        task = f"{task}_no_a"
+    if not args.enable_loss_stable and args.enable_loss_anti:
+        task = f"{task}_no_s"
+    if not args.enable_loss_anti and not args.enable_loss_stable:
+        task = f"{task}_no_as"
+    env = args.traj_load_path.split('/')[-1][:-3]
+    if env.lower() == "sine":
+        args.norm = False                                            # :258-259
+    data = torch.load(args.traj_load_path)
+    trainer = OfflinePretrainer(data["obs"], data["actions"], option=args.option, hidden_dim=args.hidden_dim, depth=args.depth,
+                                eps=args.eps, lr=args.lr, norm=args.norm, enable_loss_anti=args.enable_loss_anti,
+                                enable_loss_stable=args.enable_loss_stable, autotune=args.autotune, loss_anti=args.loss_anti,
+                                loss_stable=args.loss_stable)
+    print(f"Task = {task}\nHidden dimension = {args.hidden_dim}\nDepth = {args.depth}\nobs {tuple(trainer.obs.shape)} "
+          f"actions {tuple(trainer.actions.shape)}")
+    trainer.fit(args.num_epoch, log_every=max(1, args.num_epoch // 20))
+    print("saved to", trainer.save(args.save_path, env, task))
+
+
+if __name__ == "__main__":
+    main()

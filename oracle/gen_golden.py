@@ -747,6 +747,106 @@ def gen_ppo():
         print("wrote", name, curve[0], curve[-1])
 
 
+PRETRAIN_CASES = (  # (task, rows, hidden, epochs, lr, mode)   mode: autotune (warm-up weights) / fixed weights / 2fs
+    ("hopper", 1001, 128, 3, 1e-3, "autotune"),
+    ("maze", 600, 128, 2, 1e-3, "fixed"),
+    ("sine", 500, 128, 2, 1e-3, "2fs"),
+)
+
+
+def pretrain_dataset(seed, task, rows):
+    """Un-normalised synthetic demonstrations (observations with per-column offsets / scales so that norm_vec matters)."""
+    s_dim, a_dim = synth.TASK_DIMS[task]
+    g = synth.rng(seed)
+    s, _ = synth.states_actions(seed + 1, rows, s_dim, a_dim)
+    a = synth.expert_actions(seed + 2, s, a_dim)
+    scale = g.uniform(0.5, 4.0, s_dim).astype(np.float32)
+    shift = g.uniform(-2.0, 2.0, s_dim).astype(np.float32)
+    return (s * scale + shift).astype(np.float32), (a * np.float32(1.7) + np.float32(0.3)).astype(np.float32)
+
+
+def pretrain_draws(seed, epoch, k, B, a_dim, eps):
+    """The draws of batch k of an epoch in the order the reference makes them (pretrain.py:368-378)."""
+    g = synth.rng(seed + 1000 * (epoch + 1) + k)
+    d = {}
+    for tag in ("E", "A"):
+        d["u" + tag] = g.random((B, 1), dtype=np.float32)
+        d["t" + tag] = (d["u" + tag] * np.float32(1 - 2 * eps) + np.float32(eps)).astype(np.float32)
+        d["n" + tag] = g.standard_normal((B, a_dim)).astype(np.float32)
+        if tag == "E":
+            d["z"] = g.standard_normal((B, a_dim)).astype(np.float32)       # randn_like(a) between the two fm_loss calls
+    d["t_mix"] = g.random((B, 1), dtype=np.float32)
+    d["probe"] = synth.rademacher(seed + 7, (B, a_dim))                     # shape-deterministic in the reference
+    return d
+
+
+def gen_pretrain(P):
+    """pretrain_*.npz: the loop of the reference's offline pre-trainer (pretrain.py:269-440) on a small synthetic
+    demonstration set: norm_vec with the data's own moments, the odd-row rule, shuffled 128-row batches (ragged last
+    batch), expert + perturbed-agent CFM terms, regularisers with warm-up / fixed weights, clip 1, Adam."""
+    import torch
+
+    eps, B = 1e-2, 128
+    for idx, (task, rows, hidden, epochs, lr, mode) in enumerate(PRETRAIN_CASES):
+        s_dim, a_dim = synth.TASK_DIMS[task]
+        seed = 11000 + 100 * idx
+        obs_raw, act_raw = pretrain_dataset(seed, task, rows)
+        obs, actions = torch.from_numpy(obs_raw), torch.from_numpy(act_raw)
+        do_norm = task != "sine"                                              # pretrain.py:258-259
+        moments = {}
+        if do_norm:                                                           # :273-285, the reference's own norm_vec
+            moments = {"obs_mean": obs.mean(0), "obs_std": obs.std(0), "act_mean": actions.mean(0), "act_std": actions.std(0)}
+            obs = P.norm_vec(obs, moments["obs_mean"], moments["obs_std"])
+            actions = P.norm_vec(actions, moments["act_mean"], moments["act_std"])
+        dataset = torch.cat((obs, actions), 1)
+        if dataset.size(0) % 2 == 1:                                          # :289-290
+            dataset = dataset[1:]
+        dataset = dataset.float()
+        n = dataset.size(0)
+        n_heads = 1 if mode == "2fs" else 2
+        spec = cf.NetSpec(s_dim, a_dim, hidden, 4, n_heads)
+        flat0 = cf.make_params(spec, seed + 5, 1.0)
+        model = build_ref(P, spec, flat0, eps=eps)
+        params = list(model.parameters())
+        opt = torch.optim.Adam(params, lr=lr)
+        w_anti, w_st = 1e-4, 1e-6                                             # --loss-anti / --loss-stable defaults
+        curve, weights, norms = [], [], []
+        for e in range(epochs):
+            perm = synth.rng(seed + 50 + e).permutation(n)
+            for k, lo in enumerate(range(0, n, B)):
+                i = perm[lo:lo + B]
+                batch = dataset[torch.from_numpy(i)]
+                s, a = batch[:, :s_dim].numpy(), batch[:, s_dim:].numpy()
+                d = pretrain_draws(seed, e, k, len(i), a_dim, eps)
+                if mode == "2fs":
+                    loss = ref_fm_loss(P, model, spec, s, a, None, d["uE"], d["nE"], dequant=d["z"])   # :414-415
+                    l_e, l_anti, l_st = loss, torch.zeros(()), torch.zeros(())
+                else:
+                    l_e = ref_fm_loss(P, model, spec, s, a, "expert", d["uE"], d["nE"])
+                    a_noise = (torch.from_numpy(a) + 0.1 * torch.from_numpy(d["z"])).numpy()            # :370-371
+                    l_a = ref_fm_loss(P, model, spec, s, a_noise, "agent", d["uA"], d["nA"])
+                    loss = l_e + l_a
+                    l_anti, l_st = ref_reg_losses(P, model, s, a_noise, d["t_mix"], d["probe"])
+                    if mode == "autotune":                                    # warm-up branch (:391-402)
+                        w_anti = l_e.detach() / (l_anti.detach() + 1e-8) * 1e-3
+                        w_st = l_e.detach() / (l_st.detach() + 1e-8) * 1e-3
+                    loss = loss + w_anti * l_anti + w_st * l_st
+                opt.zero_grad()
+                loss.backward()
+                norms.append(float(torch.nn.utils.clip_grad_norm_(params, 1)))                          # :417-420
+                opt.step()
+                curve.append((loss.item(), l_e.item(), l_anti.item(), l_st.item()))
+                weights.append((float(w_anti), float(w_st)))
+        out = {"meta": np.array([s_dim, a_dim, hidden, rows, epochs, seed, n_heads, int(do_norm)]), "lr": np.float32(lr),
+               "mode": np.array(["autotune", "fixed", "2fs"].index(mode)), "curve": np.array(curve, np.float32),
+               "weights": np.array(weights, np.float32), "gradnorm": np.array(norms, np.float32),
+               "dataset": dataset.numpy(), "final_params": np.concatenate([p.detach().numpy().ravel() for p in params])}
+        out.update({k: v.numpy() for k, v in moments.items()})
+        name = f"pretrain_{idx:02d}_{task}_{mode}_h{hidden}_{epochs}epochs.npz"
+        np.savez_compressed(os.path.join(OUT, name), **out)
+        print("wrote", name, len(curve), "steps", curve[0], curve[-1])
+
+
 def main():
     import torch
 
@@ -754,7 +854,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     P = ref_shim.load()
-    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "bcf", "gae", "ppo"]
+    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "pretrain", "bcf", "gae", "ppo"]
     if "logprob" in which:
         gen_logprob(P)
     if "vfield" in which:
@@ -769,6 +869,8 @@ def main():
         gen_train_reg(P)
     if "gradnorm" in which:
         gen_gradnorm()
+    if "pretrain" in which:
+        gen_pretrain(P)
     if "bcf" in which:
         gen_bcf()
     if "gae" in which:
