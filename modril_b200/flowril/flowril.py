@@ -549,8 +549,43 @@ if HAVE_RLF:
             super().__init__([FlowMatchingEstimation(), agent_updater or PPO()], 1)
 else:
     class FLOWRIL(object):
-        """``NestedAlgo([FlowMatchingEstimation(), PPO()], 1)`` needs rl-toolkit (reference flowril.py:21-23)."""
+        """Stand-alone stand-in for ``NestedAlgo([FlowMatchingEstimation(), PPO()], 1)`` (reference flowril.py:21-23,
+        deps/rl-toolkit/rlf/algos/nested_algo.py:6-106) when rl-toolkit is not importable: the reward module followed by
+        the device PPO updater of ``modril_b200.ppo``.  ``policy`` must be a ``modril_b200.ppo.DistActorCritic`` carrying
+        ``obs_space`` / ``action_space`` (what rl-toolkit's ``BasePolicy.init`` would have stored)."""
 
-        def __init__(self, *a, **k):
-            raise ImportError("FLOWRIL (the NestedAlgo wrapper) needs rl-toolkit (rlf); "
-                              "FlowMatchingEstimation works stand-alone")
+        def __init__(self, agent_updater=None):
+            if agent_updater is None:
+                from ..ppo import PPO as DevicePPO
+
+                agent_updater = DevicePPO()
+            self.modules = [FlowMatchingEstimation(), agent_updater]
+            self.designated_rl_idx = 1
+
+        def init(self, policy, args):
+            for module in self.modules:
+                module.init(policy, args)
+
+        def pre_update(self, cur_update):
+            for module in self.modules:
+                if hasattr(module, "pre_update"):
+                    module.pre_update(cur_update)
+
+        def get_add_args(self, parser):
+            for module in self.modules:
+                module.get_add_args(parser)
+
+        def update(self, storage, args=None, beginning=False, t=1):
+            log_vals = {}                                            # nested_algo.py:91-106
+            mods = self.modules[:1] if getattr(args, "freeze_policy", False) else self.modules
+            for module in mods:
+                log_vals = {**log_vals, **module.update(storage, beginning, t)}
+            return log_vals
+
+        def save(self, checkpointer):
+            for module in self.modules:
+                module.save(checkpointer)
+
+        def load_resume(self, checkpointer):
+            for module in self.modules:
+                module.load_resume(checkpointer)

@@ -313,3 +313,83 @@ class PPOUpdateGraph:
         n_updates = self.num_epochs * (self.rows // (self.rows // self.num_mini_batch))
         return {"value_loss": a[1] / n, "actor_loss": a[2] / n, "dist_entropy": a[3] / n,
                 "policy_update_data": float(self.num_mini_batch * n_updates)}
+
+
+class PPO:
+    """The agent updater of ``FLOWRIL(NestedAlgo([FlowMatchingEstimation(), PPO()]))`` (reference flowril.py:21-23):
+    mirror of ``rlf.algos.on_policy.ppo.PPO`` (ppo.py:8-80) with ``OnPolicy._compute_returns`` (on_policy_base.py:23-40)
+    and the optimiser handling of ``BaseNetAlgo`` (base_net_algo.py:31-146: Adam(lr, eps), ``--max-grad-norm``,
+    ``--linear-lr-decay``) for a ``DistActorCritic`` policy.  ``update(rollouts)`` consumes the rewards the reward module
+    wrote into ``rollouts.rewards`` and runs entirely on the device: next value -> returns / GAE scan -> advantage
+    normalisation -> ``num_epochs x num_mini_batch`` clipped-PPO minibatches; one device->host copy (the logged means).
+
+    ``rollouts`` needs the tensors of ``RolloutStorage`` (rlf/storage/rollout_storage.py:31-110) on the policy's device:
+    ``obs`` [T+1,N,S], ``actions`` [T,N,A], ``action_log_probs`` [T,N,1], ``rewards`` [T,N,1], ``value_preds`` /
+    ``returns`` [T+1,N,1], ``masks`` / ``bad_masks`` [T+1,N,1]."""
+
+    def __init__(self):
+        self.arg_prefix = ""
+        self._graph = None
+
+    def init(self, policy: DistActorCritic, args):
+        self.policy, self.args = policy, args
+        self._initial_lr = float(args.lr)
+        self.opt = FusedAdam([policy], lr=float(args.lr), eps=float(args.eps), capturable=True)
+        # total number of updates of the run (base_net_algo.py:48-58); only the lr schedule needs it
+        per_update = int(args.num_steps) * int(args.num_processes)
+        self.lr_updates = max(1, int(getattr(args, "num_env_steps", per_update)) // per_update)
+
+    def pre_update(self, cur_update):
+        if getattr(self.args, "linear_lr_decay", True):              # autils.linear_lr_schedule (rlf/algos/utils.py:76-79)
+            lr = self._initial_lr - (self._initial_lr * (cur_update / float(self.lr_updates)))
+            for group in self.opt.param_groups:
+                group["lr"] = lr
+            self._graph = None                                       # the learning rate is a kernel argument of the graph
+
+    def _compute_returns(self, rollouts):
+        a = self.args
+        next_value = self.policy.get_value(rollouts.obs[-1])         # on_policy_base.py:23-36
+        compute_returns(rollouts.rewards, rollouts.value_preds, rollouts.masks, getattr(rollouts, "bad_masks", None),
+                        next_value, rollouts.returns, gamma=a.gamma, gae_lambda=a.gae_lambda, use_gae=a.use_gae,
+                        use_proper_time_limits=getattr(a, "use_proper_time_limits", False))
+
+    def update(self, rollouts, args=None, beginning=False, t=1, *, perms=None, graph=None):
+        """ppo.py:9-64.  ``graph``: replay the minibatch loop as one CUDA graph (default: when the learning rate is
+        constant, i.e. ``--linear-lr-decay False``)."""
+        a = self.args
+        self._compute_returns(rollouts)
+        advantages = compute_advantages(rollouts.returns, rollouts.value_preds)
+        T, N = rollouts.rewards.shape[:2]
+        rows = T * N
+        flat = (rollouts.obs[:-1].reshape(rows, -1), rollouts.actions.reshape(rows, -1), rollouts.action_log_probs.reshape(rows),
+                rollouts.value_preds[:-1].reshape(rows), rollouts.returns[:-1].reshape(rows), advantages.reshape(rows))
+        kw = dict(num_epochs=a.num_epochs, num_mini_batch=a.num_mini_batch, clip_param=a.clip_param,
+                  value_loss_coef=a.value_loss_coef, entropy_coef=a.entropy_coef, max_grad_norm=a.max_grad_norm)
+        if graph is None:
+            graph = not getattr(a, "linear_lr_decay", True)
+        if graph:
+            if self._graph is None or self._graph.rows != rows:
+                self._graph = PPOUpdateGraph(self.policy, self.opt, rows, **kw)
+            return self._graph(*flat, perms=perms)
+        return ppo_update(self.policy, self.opt, *flat, perms=perms, **kw)
+
+    def get_add_args(self, parser):
+        """The flags of OnPolicy / PPO / BaseNetAlgo (on_policy_base.py:13-21, ppo.py:66-80, base_net_algo.py:105-146)."""
+        str2bool = lambda v: v.lower() == "true"
+        p = self.arg_prefix
+        parser.add_argument(f"--{p}num-epochs", type=int, default=4)
+        parser.add_argument(f"--{p}num-mini-batch", type=int, default=4)
+        parser.add_argument(f"--{p}clip-param", type=float, default=0.2)
+        parser.add_argument(f"--{p}entropy-coef", type=float, default=0.01)
+        parser.add_argument(f"--{p}value-loss-coef", type=float, default=0.5)
+        parser.add_argument(f"--{p}max-grad-norm", type=float, default=0.5)
+        parser.add_argument(f"--{p}linear-lr-decay", type=str2bool, default=True)
+        parser.add_argument(f"--{p}eps", type=float, default=1e-12)
+        parser.add_argument(f"--{p}lr", type=float, default=1e-3)
+
+    def save(self, checkpointer):
+        checkpointer.save_key("actor_opt", self.opt.state_dict())    # base_net_algo.py:66-69
+
+    def load_resume(self, checkpointer):
+        self.opt.load_state_dict(checkpointer.get_key("actor_opt"))  # base_net_algo.py:60-64
+        self._graph = None

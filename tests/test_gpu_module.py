@@ -294,3 +294,48 @@ def test_device_return_normalisation_vs_oracle(T, N):
         assert abs(rms_dev.var[0] - rms_ref.var[0]) <= 2e-6 * rms_ref.var[0]
         assert abs(rms_dev.mean[0] - rms_ref.mean[0]) <= 2e-6 * max(1.0, abs(rms_ref.mean[0]))
         assert rms_dev.count == rms_ref.count
+
+
+def test_standalone_flowril_chain_reward_module_then_device_ppo():
+    """FLOWRIL() without rl-toolkit = [FlowMatchingEstimation, modril_b200.ppo.PPO]: one ``update(storage)`` trains the
+    reward model, writes the (normalised) rewards for every rollout step and runs the PPO consumer on them."""
+    from modril_b200.flowril.flowril import FLOWRIL, HAVE_RLF
+    from modril_b200.ppo import DistActorCritic
+
+    if HAVE_RLF:
+        pytest.skip("rl-toolkit is importable: FLOWRIL is the real NestedAlgo")
+    args = make_args(num_steps=16, num_processes=8, traj_batch_size=16, lr=1e-3, eps=1e-12, gae_lambda=0.95, use_gae=True,
+                     num_epochs=2, num_mini_batch=4, clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01,
+                     max_grad_norm=0.5, linear_lr_decay=False)
+    T, N, s_dim, a_dim = args.num_steps, args.num_processes, 11, 3
+    g = synth.rng(99)
+    obs = torch.from_numpy(g.standard_normal((64, s_dim)).astype(np.float32))
+    args.expert_dataset = {"obs": obs, "actions": torch.from_numpy(synth.expert_actions(5, obs.numpy(), a_dim))}
+    torch.manual_seed(0)
+    policy = DistActorCritic(s_dim, a_dim).to(args.device)
+    policy.obs_space, policy.action_space = Space(s_dim), Space(a_dim)
+    algo = FLOWRIL()
+    algo.init(policy, args)
+    storage = FakeStorage(T, N, s_dim, a_dim, 7, args.device)
+    out = policy.get_action(storage.obs[:-1].reshape(T * N, s_dim))
+    storage.actions = out["action"].reshape(T, N, a_dim)
+    storage.action_log_probs = out["action_log_probs"].reshape(T, N, 1)
+    storage.value_preds = torch.cat([out["value"].reshape(T, N, 1), torch.zeros(1, N, 1, device=args.device)])
+    storage.returns = torch.zeros(T + 1, N, 1, device=args.device)
+    storage.bad_masks = torch.ones_like(storage.masks)
+    before = policy.flat_params().clone()
+    reward_before = algo.modules[0].flow_net.net.flat_params().clone()
+    for it in range(2):
+        algo.pre_update(it)
+        logs = algo.update(storage, args)
+        assert {"flow_loss", "agent_loss", "value_loss", "actor_loss", "dist_entropy"} <= set(logs), logs
+        assert all(np.isfinite(v) for v in logs.values())
+        assert float(storage.rewards.abs().sum()) > 0 and torch.isfinite(storage.returns).all()
+    assert not torch.equal(before, policy.flat_params()) and torch.isfinite(policy.flat_params()).all()
+    assert not torch.equal(reward_before, algo.modules[0].flow_net.net.flat_params())
+    assert algo.modules[1].opt.step_count() == 2 * args.num_epochs * args.num_mini_batch
+    # freeze_policy (nested_algo.py:99-101): only the reward module updates
+    frozen = policy.flat_params().clone()
+    args.freeze_policy = True
+    algo.update(storage, args)
+    assert torch.equal(frozen, policy.flat_params())

@@ -179,6 +179,73 @@ def test_graphed_update_equals_eager_update():
     assert torch.isfinite(pols[1].flat_params()).all()
 
 
+def test_ppo_updater_runs_the_whole_consumer_chain_on_the_device():
+    """PPO.update (next value -> returns / GAE -> advantages -> minibatches) against the oracle's composition of the same
+    steps on the first minibatch, eager and graphed; flags and checkpoint keys of the reference class."""
+    import argparse
+    from types import SimpleNamespace
+
+    from modril_b200.ppo import PPO
+
+    T, N, S, A = 64, 8, 11, 3
+    spec = pcf.ACSpec(S, A, 64, 2)
+    flat = pcf.ac_make_params(spec, 31)
+    g = synth.rng(32)
+    obs = g.standard_normal((T + 1, N, S)).astype(np.float32)
+    noise = g.standard_normal((T * N, A)).astype(np.float32)
+    value, action, logp = (x.astype(np.float32) for x in pcf.ac_act(spec, flat, obs[:-1].reshape(T * N, S), noise))
+    rewards = g.standard_normal((T, N, 1)).astype(np.float32)
+    masks = (g.random((T + 1, N, 1)) > 0.05).astype(np.float32)
+    parser = argparse.ArgumentParser()
+    updater = PPO()
+    updater.get_add_args(parser)
+    args = parser.parse_args(["--linear-lr-decay", "false"])
+    assert (args.num_epochs, args.num_mini_batch, args.clip_param, args.max_grad_norm, args.eps) == (4, 4, 0.2, 0.5, 1e-12)
+    args.gamma, args.gae_lambda, args.use_gae, args.num_steps, args.num_processes = 0.99, 0.95, True, T, N
+
+    def storage():
+        vp = np.concatenate([value.reshape(T, N, 1), np.zeros((1, N, 1), np.float32)])
+        return SimpleNamespace(obs=dev(obs), actions=dev(action.reshape(T, N, A)), action_log_probs=dev(logp.reshape(T, N, 1)),
+                               rewards=dev(rewards), value_preds=dev(vp), returns=torch.zeros(T + 1, N, 1, device="cuda"),
+                               masks=dev(masks), bad_masks=dev(np.ones_like(masks)))
+
+    perms = [torch.from_numpy(synth.rng(40 + e).permutation(T * N)).cuda() for e in range(4)]
+    finals = []
+    for graph in (False, True):
+        pol = build_policy(spec, flat)
+        updater = PPO()
+        updater.init(pol, args)
+        st = storage()
+        logs = updater.update(st, perms=perms, graph=graph)
+        finals.append(pol.flat_params().clone())
+        assert set(logs) == {"value_loss", "actor_loss", "dist_entropy", "policy_update_data"}
+        assert updater.opt.step_count() == 16
+    assert torch.equal(finals[0], finals[1])
+    # oracle composition: next value, GAE, normalised advantages, then the first minibatch of epoch 0
+    nv = pcf.ac_forward(spec, flat, obs[-1])[0].astype(np.float32)
+    vp = np.concatenate([value.reshape(T, N, 1), np.zeros((1, N, 1), np.float32)])
+    returns, vp = pcf.compute_returns(rewards, vp, masks, np.ones_like(masks), nv, 0.99, 0.95, True, False)
+    assert np.abs(st.returns[:-1].cpu().numpy() - returns[:-1]).max() <= 1e-5
+    adv = pcf.compute_advantages(returns, vp)
+    i = perms[0][:T * N // 4].cpu().numpy()
+    flat_rows = lambda x: x.reshape(T * N, -1)[i]
+    losses, _ = pcf.ppo_loss_and_grad(spec, flat, flat_rows(obs[:-1]), flat_rows(action), flat_rows(logp), flat_rows(adv),
+                                      flat_rows(returns[:-1]), flat_rows(vp[:-1]))
+    pol = build_policy(spec, flat)
+    got = pol.ppo_loss(st.obs[:-1].reshape(T * N, S), st.actions.reshape(T * N, A), st.action_log_probs.reshape(-1),
+                       dev(adv).reshape(-1), st.returns[:-1].reshape(-1), st.value_preds[:-1].reshape(-1),
+                       indices=perms[0][:T * N // 4].contiguous()).cpu().numpy()
+    assert np.allclose(got, losses, rtol=5e-5, atol=5e-6), (got, losses)
+    # lr decay (base_net_algo.py:78-82) and the checkpoint key
+    args.linear_lr_decay, args.num_env_steps = True, 10 * T * N
+    updater.init(pol, args)
+    updater.pre_update(5)
+    assert abs(updater.opt.param_groups[0]["lr"] - 0.5e-3) < 1e-12
+    saved = {}
+    updater.save(SimpleNamespace(save_key=saved.__setitem__))
+    assert "actor_opt" in saved and "state" in saved["actor_opt"]
+
+
 @pytest.mark.parametrize("hidden", [64, 128, 256])
 def test_large_ragged_batch_matches_oracle_and_is_deterministic(hidden, kernel_path):
     spec = pcf.ACSpec(17, 6, hidden, 2)          # 64 / 128: fused kernel with several tiles per CTA; 256: GEMM path
