@@ -26,8 +26,12 @@ WORKLOADS = {
     "maze": ("maze", 65536, 20),
     "hopper": ("hopper", 262144, 32),
     "halfcheetah": ("halfcheetah", 262144, 32),
+    "walker": ("walker", 262144, 32),
     "ant": ("ant", 1048576, 32),
+    "ant111": ("ant111", 1048576, 32),
     "hand": ("hand", 1048576, 32),
+    "pick": ("pick", 1048576, 32),
+    "push": ("push", 1048576, 32),
 }
 HIDDEN, DEPTH = 256, 4
 
