@@ -515,6 +515,98 @@ __global__ void ppo_fused_reduce_kernel(const float* __restrict__ part, int n_ct
     }
 }
 
+// ---- fused acting / evaluation kernel (same residency rule as ppo_fused_kernel) -----------------------------------------
+// get_action is called once per environment step with one row per environment (32 by default): one launch, 8 rows per
+// CTA, the needed nets' weights read straight from the flat parameter vector into shared memory.
+__global__ void __launch_bounds__(256) acnet_fused_eval_kernel(const float* __restrict__ params, FusedOffs fo,
+                                                               const float* __restrict__ obs, const float* __restrict__ noise,
+                                                               const float* __restrict__ action_in, float* __restrict__ value,
+                                                               float* __restrict__ mean_out, float* __restrict__ action_out,
+                                                               float* __restrict__ logp, float* __restrict__ ent, long long B,
+                                                               int S, int A, int H, int L, int R, int net_mask, int mode) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int L0 = H * (S + 1) + H, LH = H * (H + 1) + H, T = L0 + (L - 1) * LH;
+    auto sWl = [&](int net, int l) { return sm + net * T + (l == 0 ? 0 : L0 + (l - 1) * LH); };
+    auto sbl = [&](int net, int l) { return sWl(net, l) + H * ((l == 0 ? S : H) + 1); };
+    auto sWhd = [&](int net) { return sm + 2 * T + (net == 0 ? 0 : (H + 1) + 1); };
+    auto sbhd = [&](int net) { return sWhd(net) + (net == 0 ? 1 : A) * (H + 1); };
+    float* p = sm + 2 * T + (1 + A) * (H + 1) + 1 + A;
+    float* slog = p; p += A;
+    float* X = p; p += R * S;
+    float* hbuf[2] = {p, p + 2 * R * H}; p += 4 * R * H;   // ping-pong activations, both nets side by side
+    float* outV = p; p += R;
+    float* outM = p; p += R * A;
+    for (int net = 0; net < 2; ++net) {
+        if (!(net_mask >> net & 1)) continue;
+        for (int l = 0; l < L; ++l) {
+            const int K = l == 0 ? S : H;
+            const float* g = params + fo.off_w[net][l];
+            for (int i = tid; i < H * K; i += nt) sWl(net, l)[(i / K) * (K + 1) + i % K] = g[i];
+            for (int i = tid; i < H; i += nt) sbl(net, l)[i] = params[fo.off_b[net][l] + i];
+        }
+        const int NO = net == 0 ? 1 : A;
+        for (int i = tid; i < NO * H; i += nt) sWhd(net)[(i / H) * (H + 1) + i % H] = params[fo.off_hw[net] + i];
+        for (int i = tid; i < NO; i += nt) sbhd(net)[i] = params[fo.off_hb[net] + i];
+    }
+    for (int i = tid; i < A; i += nt) slog[i] = params[fo.off_logstd + i];
+    const long long n_tiles = (B + R - 1) / R;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row0 = tile * R;
+        __syncthreads();
+        for (int i = tid; i < R * S; i += nt) { const long long q = row0 + i / S; X[i] = q < B ? obs[q * S + i % S] : 0.f; }
+        __syncthreads();
+        for (int l = 0; l < L; ++l) {
+            const float* in = hbuf[(l + 1) & 1];
+            float* out = hbuf[l & 1];
+            const int K = l == 0 ? S : H;
+            for (int o = tid; o < 2 * R * H; o += nt) {
+                const int net = o / (R * H), q = o % (R * H), r = q / H, j = q % H;
+                if (!(net_mask >> net & 1)) continue;
+                const float* x = l == 0 ? X + r * S : in + net * R * H + r * H;
+                const float* w = sWl(net, l) + j * (K + 1);
+                float acc = sbl(net, l)[j];
+                for (int k = 0; k < K; ++k) acc = fmaf(x[k], w[k], acc);
+                out[o] = tanhf(acc);
+            }
+            __syncthreads();
+        }
+        const float* hL = hbuf[(L - 1) & 1];
+        for (int o = tid; o < R * (1 + A); o += nt) {
+            const int r = o / (1 + A), c = o % (1 + A), net = c == 0 ? 0 : 1, oo = c == 0 ? 0 : c - 1;
+            if (!(net_mask >> net & 1)) continue;
+            const float* x = hL + net * R * H + r * H;
+            const float* w = sWhd(net) + oo * (H + 1);
+            float acc = sbhd(net)[oo];
+            for (int k = 0; k < H; ++k) acc = fmaf(x[k], w[k], acc);
+            if (c == 0) outV[r] = acc; else outM[r * A + oo] = acc;
+        }
+        __syncthreads();
+        for (int r = tid; r < R; r += nt) {
+            const long long q = row0 + r;
+            if (q >= B) continue;
+            const float* m = outM + r * A;
+            if (value) value[q] = outV[r];
+            if (mean_out)
+                for (int j = 0; j < A; ++j) mean_out[q * A + j] = m[j];
+            if (mode == 1) {
+                float acc = 0.f;
+                for (int j = 0; j < A; ++j) {
+                    const float scale = expf(slog[j]);
+                    const float x = noise ? __fadd_rn(m[j], __fmul_rn(scale, noise[q * A + j])) : m[j];
+                    action_out[q * A + j] = x;
+                    const float d = x - m[j];
+                    acc += -(d * d) / (2.f * (scale * scale)) - logf(scale) - kLogSqrt2Pi;
+                }
+                if (logp) logp[q] = acc;
+            } else if (mode == 2) {
+                if (logp) logp[q] = row_logp(action_in + q * A, m, slog, A);
+            }
+            if (ent) ent[q] = row_entropy(slog, A);
+        }
+    }
+}
+
 struct FusedPlan {
     bool ok;
     int R, n_cta;
@@ -616,11 +708,38 @@ static int acnet_eval_common(frl_acnet* n, const float* obs, const float* noise,
     FRL_REQUIRE(B < (1ll << 31) / std::max(n->cfg.hidden, n->Sp), "batch too large");
     FRL_CUDA(cudaSetDevice(n->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
+    const bool need_actor = mean || action_out || logp;
+    {   // nets that fit in shared memory: one launch (FRL_PPO_GEMM=1 forces the per-layer GEMM path)
+        const int H = n->cfg.hidden, S = n->cfg.obs_dim, A = n->cfg.a_dim, L = n->cfg.layers, R = 8;
+        size_t w = 0;
+        for (int l = 0; l < L; ++l) w += (size_t)H * ((l == 0 ? S : H) + 1) + H;
+        w = 2 * w + (size_t)(1 + A) * (H + 1) + 1 + A + A;
+        const size_t smem = (w + (size_t)R * S + 4 * (size_t)R * H + R + (size_t)R * A) * sizeof(float);
+        if (smem <= 200 * 1024 && !getenv("FRL_PPO_GEMM")) {
+            static bool attr_done[64] = {};
+            if (!attr_done[n->cfg.device & 63]) {
+                FRL_CUDA(cudaFuncSetAttribute(acnet_fused_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_done[n->cfg.device & 63] = true;
+            }
+            FusedOffs fo;
+            for (int net = 0; net < 2; ++net) {
+                for (int l = 0; l < L; ++l) { fo.off_w[net][l] = (int)n->off_w[net][l]; fo.off_b[net][l] = (int)n->off_b[net][l]; }
+                fo.off_hw[net] = (int)n->off_hw[net];
+                fo.off_hb[net] = (int)n->off_hb[net];
+            }
+            fo.off_logstd = (int)n->off_logstd;
+            fo.n_params = (int)n->n_params;
+            const int grid = (int)std::min<long long>((B + R - 1) / R, 592);
+            acnet_fused_eval_kernel<<<grid, 256, smem, st>>>(n->params_dev, fo, obs, noise, action_in, value, mean, action_out, logp,
+                                                            ent, B, S, A, H, L, R, (value ? 1 : 0) | (need_actor ? 2 : 0), mode);
+            FRL_CUDA(cudaGetLastError());
+            return FRL_OK;
+        }
+    }
     ABuf b;
     size_t used = 0;
     int rc = ac_prepare(n, obs, nullptr, B, 0, &b, &used, st);
     if (rc != FRL_OK) return rc;
-    const bool need_actor = mean || action_out || logp;
     rc = ac_forward(n, b, (int)B, (value ? 1 : 0) | (need_actor ? 2 : 0), st);
     if (rc != FRL_OK) return rc;
     acnet_head_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(b.out[0], b.out[1], n->Aop, n->pack + n->o_logstd, noise, action_in,
