@@ -195,6 +195,31 @@ def cpu_port_rate(task, B_sample, n_steps, flat, threads, reps=1):
     return B_sample / best, best
 
 
+def cpu_train_rate(task, B_sample, flat, threads, steps=3):
+    """CFM train rows/s of the torch-CPU port (fm_loss x 2 -> backward -> clip_grad_norm_ -> Adam.step; flowril.py:311-330)
+    on B_sample expert + B_sample agent rows per step."""
+    import torch
+
+    from oracle import closed_form as cf
+    from oracle import synth, torch_port
+
+    torch.set_num_threads(threads)
+    s_dim, a_dim = synth.TASK_DIMS[task]
+    spec = cf.NetSpec(s_dim, a_dim, HIDDEN, DEPTH, 2)
+    s, a = synth.states_actions(3, B_sample, s_dim, a_dim)
+    t, noise = synth.cfm_draws(4, B_sample, a_dim)
+    st, at, tt, nt = (torch.from_numpy(x) for x in (s, a, t, noise))
+    ft = torch.from_numpy(flat).clone().requires_grad_(True)
+    opt = torch.optim.Adam([ft], lr=1e-4)
+    batches = [(st, at, "expert", tt, nt), (st, at, "agent", tt, nt)]
+    torch_port.train_step(spec, ft, opt, batches)          # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        torch_port.train_step(spec, ft, opt, batches)
+    dt = (time.perf_counter() - t0) / steps
+    return 2 * B_sample / dt, dt
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (torch port, all host threads)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -481,7 +506,7 @@ def run_ours(args):
             "algorithmic_flops_per_sample": algorithmic_flops_per_sample(s_dim, a_dim, n_steps)}
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
-    cpu = None
+    cpu, cpu_train = None, None
     if world == 1 and not args.no_cpu:
         from oracle import closed_form as cf
 
@@ -493,6 +518,10 @@ def run_ours(args):
         cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
                "sample": f"{Bs} of {B} rows, one pass ({dt:.1f} s), torch-CPU port of the reference op sequence "
                          f"(oracle/torch_port.py) with {threads} threads"}
+        trate, tdt = cpu_train_rate(task, 8192, flat, threads)
+        cpu_train = {"value": trate, "unit": "samples/s", "cores": threads, "kind": "port",
+                     "sample": f"3 updates of 2 x 8192 rows ({tdt:.2f} s each): fm_loss x 2, backward, clip_grad_norm_, Adam "
+                               f"(oracle/torch_port.py::train_step) with {threads} threads"}
 
     line = {
         "metric": "scored_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -525,7 +554,8 @@ def run_ours(args):
                           "peak_gbs": measured_hbm_gbs(),
                           "frac": train_rate * train_hbm_bytes_per_row(d_in_t, a_dim) / 1e9 / world / measured_hbm_gbs()},
                   "frac_of_peak": train_rate * 3 * f_fwd_train / 1e12 / measured_peak_tflops()[0] / world,
-                  "collective": "NCCL all-reduce of the flat grad" if world > 1 else "none"},
+                  "collective": "NCCL all-reduce of the flat grad" if world > 1 else "none",
+                  "cpu_baseline": cpu_train},
         "bcf": bcf_info,
         "ppo": ppo_info,
     }

@@ -85,4 +85,4 @@ def train_step(spec, flat, opt, batches, max_norm=1.0):
     sum(losses).backward()
     torch.nn.utils.clip_grad_norm_([flat], max_norm)
     opt.step()
-    return [float(l) for l in losses]
+    return [float(l.detach()) for l in losses]
