@@ -125,3 +125,27 @@ def test_norm_vec_and_cli_roundtrip(tmp_path):
     assert list(sd)[:2] == ["net.shared.0.weight", "net.shared.0.bias"] and len(torch.load(d / "hopper_train_loss.pt")) == 2
     with pytest.raises(RuntimeError):
         pt.OfflinePretrainer(obs, act, device="cpu")
+
+
+def test_pretrained_checkpoint_feeds_the_reward_module(tmp_path):
+    """The file the pre-trainer saves is what ``--flow-path`` loads (reference flowril.py:48-58): the scrf reward module
+    starts from it, freezes the shared trunk and head_c and fine-tunes head_r only."""
+    from modril_b200.flowril import pretrain as pt
+    from tests.test_gpu_module import FakeStorage, make_args, make_module
+
+    obs, act = pretrain_dataset(3, "hopper", 400)
+    tr = pt.OfflinePretrainer(obs, act, hidden_dim=128, lr=1e-3, norm=True)
+    tr.fit(2)
+    d = tr.save(str(tmp_path), "hopper", "scrf")
+    args = make_args(flow_path=f"{d}/hopper_fm.pt", flowril_reward_norm=False)
+    mod = make_module(args)
+    net = mod.flow_net.net
+    assert torch.equal(net.flat_params(), tr.estimator.net.flat_params())
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 12, args.device)
+    logs = mod.update(storage)
+    after = net.state_dict()
+    for k in before:
+        same = torch.equal(before[k], after[k])
+        assert same != k.startswith("head_r"), k
+    assert np.isfinite(logs["flow_loss"]) and torch.isfinite(storage.rewards).all()
