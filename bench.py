@@ -250,9 +250,11 @@ def run_reference(args):
         "impl": "reference", "metric": "scored_samples_per_sec", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{task}: s {s_dim} + a {a_dim}, {n_steps}-step ODE log-density, both roles + reward, "
-                               f"scrf H={HIDDEN} depth={DEPTH}", "batch_per_step_sample": Bs, "batch_full": B,
-                   "n_steps": n_steps},
+        # same workload / config keys as the GPU arm; the CPU steps a bounded sample of the batch
+        "config": {"workload": f"{task}: s {s_dim} + a {a_dim}, {n_steps}-step ODE log-density (Hutchinson, caller "
+                               f"probe), both roles + reward, scrf H={HIDDEN} depth={DEPTH}",
+                   "batch_per_gpu": B, "n_steps": n_steps, "batch_per_step_sample": Bs,
+                   "parallelism": f"host CPU, {threads} threads"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
                          "sample": f"{Bs} of {B} rows per step; torch-CPU port of the reference op sequence "
                                    f"(oracle/torch_port.py), torch {torch.__version__}"},
