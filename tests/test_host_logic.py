@@ -189,3 +189,70 @@ def test_every_package_module_imports_and_bcf_ppo_mirrors_refuse_cpu():
         FlowPolicy(net).get_action(torch.zeros(2, 11))
     with pytest.raises(RuntimeError):
         compute_advantages(torch.zeros(3, 2, 1), torch.zeros(3, 2, 1))
+
+
+def test_ppo_policy_surface_without_a_gpu():
+    """DistActorCritic mirror: the reference policy's state_dict keys / shapes / init, one flat buffer, no CPU fallback;
+    PPO's flags are the reference's."""
+    import argparse
+
+    from modril_b200.ppo import PPO, DistActorCritic
+    from oracle import ppo_closed_form as pcf
+
+    m = DistActorCritic(17, 6, 64, 3)
+    spec = pcf.ACSpec(17, 6, 64, 3)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(n, tuple(s)) for n, s in spec.shapes()]
+    assert m.flat_params().numel() == spec.n_params()
+    off = 0
+    for p in m.parameters():
+        assert p.data_ptr() == m.flat_params().data_ptr() + 4 * off
+        off += p.numel()
+    new = pcf.ac_make_params(spec, 2)
+    m.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in pcf.ac_unpack(spec, new).items()})
+    assert np.array_equal(m.flat_params().numpy(), new)
+    with pytest.raises(RuntimeError):
+        m.get_value(torch.zeros(2, 17))
+    with pytest.raises(RuntimeError):
+        m.ppo_loss(torch.zeros(2, 17), torch.zeros(2, 6), *(torch.zeros(2) for _ in range(4)))
+    parser = argparse.ArgumentParser()
+    PPO().get_add_args(parser)
+    a = parser.parse_args([])
+    assert (a.num_epochs, a.num_mini_batch, a.clip_param, a.entropy_coef, a.value_loss_coef, a.max_grad_norm, a.lr, a.eps,
+            a.linear_lr_decay) == (4, 4, 0.2, 0.01, 0.5, 0.5, 1e-3, 1e-12, True)
+
+
+def test_ppo_oracle_tie_and_clip_rules_match_autograd():
+    """The oracle's hand-written backward follows autograd on the non-smooth points: ratio exactly inside / outside the
+    clip range, value clip active, zero advantages (torch.min / torch.max ties)."""
+    from oracle import ppo_closed_form as pcf
+
+    spec = pcf.ACSpec(5, 2, 16, 1)
+    flat = pcf.ac_make_params(spec, 4).astype(np.float64)
+    g = np.random.default_rng(0)
+    B = 64
+    obs, act = g.standard_normal((B, 5)), g.standard_normal((B, 2)) * 0.3
+    _, logp, _ = pcf.ac_evaluate(spec, flat, obs, act)
+    old_logp = logp + g.choice([-0.5, 0.0, 0.5], size=(B, 1))        # ratio = exp(+-0.5) or exactly 1
+    adv = g.choice([-1.0, 0.0, 1.0], size=(B, 1))
+    value = pcf.ac_forward(spec, flat, obs)[0]
+    old_value = value + g.choice([-0.5, 0.0, 0.5], size=(B, 1))
+    ret = value + g.standard_normal((B, 1))
+    losses, grad = pcf.ppo_loss_and_grad(spec, flat, obs, act, old_logp, adv, ret, old_value)
+    t = torch.tensor(flat, requires_grad=True)
+    P, off = {}, 0
+    for n, s in spec.shapes():
+        k = int(np.prod(s))
+        P[n] = t[off:off + k].view(*s)
+        off += k
+    o = torch.tensor(obs)
+    v = torch.tanh(o @ P["critic.net.0.weight"].T + P["critic.net.0.bias"]) @ P["critic_head.weight"].T + P["critic_head.bias"]
+    mean = torch.tanh(o @ P["actor.net.0.weight"].T + P["actor.net.0.bias"]) @ P["dist.fc_mean.weight"].T + P["dist.fc_mean.bias"]
+    d = torch.distributions.Normal(mean, P["dist.logstd"].expand_as(mean).exp())
+    lp, ent = d.log_prob(torch.tensor(act)).sum(-1, keepdim=True), d.entropy().sum(-1)
+    ratio, A = torch.exp(lp - torch.tensor(old_logp)), torch.tensor(adv)
+    al = -torch.min(ratio * A, torch.clamp(ratio, 0.8, 1.2) * A).mean(0)
+    vpc = torch.tensor(old_value) + (v - torch.tensor(old_value)).clamp(-0.2, 0.2)
+    vl = 0.5 * torch.max((v - torch.tensor(ret)).pow(2), (vpc - torch.tensor(ret)).pow(2)).mean()
+    (vl * 0.5 + al - ent.mean() * 0.01).sum().backward()
+    assert abs(losses[0] - float(vl * 0.5 + al - ent.mean() * 0.01)) < 1e-12
+    assert np.abs(grad - t.grad.numpy()).max() < 1e-12
