@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <vector>
 
 #include "frl_internal.h"
 #include "sgemm.cuh"
@@ -32,6 +33,9 @@ struct frl_acnet {
     unsigned long long version = 0, packed = 0;
     float* ws = nullptr;
     size_t ws_floats = 0;
+    // Workspaces that were outgrown stay allocated until the handle is destroyed: a captured CUDA graph (PPOUpdateGraph)
+    // may still reference them, and a later, larger eager call must not pull the memory from under its replays.
+    std::vector<float*> retired;
 };
 
 namespace frl {
@@ -92,7 +96,7 @@ static int acnet_ensure_pack(frl_acnet* n, cudaStream_t st) {
 
 static int acnet_ws(frl_acnet* n, size_t floats) {
     if (n->ws_floats >= floats) return FRL_OK;
-    if (n->ws) FRL_CUDA(cudaFree(n->ws));
+    if (n->ws) n->retired.push_back(n->ws);
     n->ws = nullptr;
     n->ws_floats = 0;
     FRL_CUDA(cudaMalloc(&n->ws, floats * sizeof(float)));
@@ -687,6 +691,7 @@ extern "C" int frl_acnet_destroy(frl_acnet* n) {
     cudaSetDevice(n->cfg.device);
     if (n->pack) cudaFree(n->pack);
     if (n->ws) cudaFree(n->ws);
+    for (float* r : n->retired) cudaFree(r);
     delete n;
     return FRL_OK;
 }

@@ -175,6 +175,10 @@ def test_graphed_update_equals_eager_update():
         assert opts[0].step_count() == opts[1].step_count() == (rnd + 1) * epochs * nmb
         # the policy is usable right after a replay (weights re-packed): same values from both
         assert torch.equal(pols[0].get_value(data[0]), pols[1].get_value(data[0]))
+        if rnd == 0:
+            # a larger eager call outgrows the workspace the graph was captured with: the old buffer must stay alive
+            big = ppo_inputs(spec, flat, 99, 40000)[:6]
+            pols[1].ppo_loss(*(dev(x) for x in big), grad=False)
     graphed(*data)                                       # own permutations
     assert torch.isfinite(pols[1].flat_params()).all()
 
