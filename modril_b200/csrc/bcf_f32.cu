@@ -29,6 +29,7 @@ struct frl_vnet {
     unsigned long long version = 0, packed = 0;
     float* ws = nullptr;
     size_t ws_floats = 0;
+    std::vector<float*> retired;
 };
 
 namespace frl {
@@ -92,7 +93,7 @@ static int vnet_ensure_pack(frl_vnet* n, cudaStream_t st) {
 
 static int vnet_ws(frl_vnet* n, size_t floats) {
     if (n->ws_floats >= floats) return FRL_OK;
-    if (n->ws) FRL_CUDA(cudaFree(n->ws));
+    if (n->ws) n->retired.push_back(n->ws);   // kept alive until destroy (captured graphs / in-flight launches)
     n->ws = nullptr;
     n->ws_floats = 0;
     FRL_CUDA(cudaMalloc(&n->ws, floats * sizeof(float)));
@@ -411,6 +412,7 @@ extern "C" int frl_vnet_destroy(frl_vnet* n) {
     cudaSetDevice(n->cfg.device);
     if (n->pack) cudaFree(n->pack);
     if (n->ws) cudaFree(n->ws);
+    for (float* r : n->retired) cudaFree(r);
     delete n;
     return FRL_OK;
 }

@@ -79,6 +79,9 @@ struct frl_net {
     void* ws_x0s = nullptr;             // per-launch layer-0 operand images of wide-input nets (logprob_tc3.cu)
     size_t ws_x0s_bytes = 0;
     cudaEvent_t x0s_event = nullptr;    // recorded after the launch that reads ws_x0s (the next launch, on any stream, waits)
+    // Workspaces that were outgrown stay allocated until frl_net_destroy: a captured CUDA graph of an update (or a launch
+    // still in flight) may reference them, so a later, larger call must not free the memory under it.
+    std::vector<void*> retired;
 };
 
 void frl_host_stage_free(frl_net* net);  // api.cu

@@ -1021,7 +1021,7 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
         const size_t img_bytes = (size_t)p.K0p * kRows * 2, need = (size_t)img_tiles * img_bytes;
         frl_net* nm = const_cast<frl_net*>(n0);
         if (nm->ws_x0s_bytes < need) {
-            if (nm->ws_x0s) FRL_CUDA(cudaFree(nm->ws_x0s));   // synchronises: earlier launches are done with it
+            if (nm->ws_x0s) nm->retired.push_back(nm->ws_x0s);   // kept alive: see frl_net::retired
             nm->ws_x0s = nullptr;
             nm->ws_x0s_bytes = 0;
             FRL_CUDA(cudaMalloc(&nm->ws_x0s, need));

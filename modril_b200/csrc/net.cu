@@ -133,6 +133,7 @@ extern "C" int frl_net_destroy(frl_net* net) {
         if (net->pack_event[k]) cudaEventDestroy(net->pack_event[k]);
     if (net->ws_tc) cudaFree(net->ws_tc);
     if (net->ws_x0s) cudaFree(net->ws_x0s);
+    for (void* r : net->retired) cudaFree(r);
     if (net->x0s_event) cudaEventDestroy(net->x0s_event);
     frl_host_stage_free(net);
     delete net;

@@ -87,7 +87,7 @@ __global__ void loss_final_kernel(const double* __restrict__ partial, int n, dou
 
 static int ensure_ws(frl_net* net, size_t floats) {
     if (net->ws_floats >= floats) return FRL_OK;
-    if (net->ws) FRL_CUDA(cudaFree(net->ws));  // synchronises the device: earlier work has finished using it
+    if (net->ws) net->retired.push_back(net->ws);   // kept alive: see frl_net::retired
     net->ws = nullptr;
     net->ws_floats = 0;
     FRL_CUDA(cudaMalloc(&net->ws, floats * sizeof(float)));

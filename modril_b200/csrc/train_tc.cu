@@ -826,7 +826,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         o_part[j] = take((size_t)n_splits * H * ldp[j] * sizeof(float));
     }
     if (net->ws_tc_bytes < off) {
-        if (net->ws_tc) FRL_CUDA(cudaFree(net->ws_tc));   // synchronises: earlier work is done with it
+        if (net->ws_tc) net->retired.push_back(net->ws_tc);   // kept alive: see frl_net::retired
         net->ws_tc = nullptr;
         net->ws_tc_bytes = 0;
         FRL_CUDA(cudaMalloc(&net->ws_tc, off));
