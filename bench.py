@@ -220,6 +220,27 @@ def cpu_train_rate(task, B_sample, flat, threads, steps=3):
     return 2 * B_sample / dt, dt
 
 
+def cpu_baseline_leg(task, B, n_steps, flat):
+    """`cpu_baseline` (scoring) and `train.cpu_baseline` of the GPU arm: the torch-CPU port of the reference op sequence on
+    all host threads over a bounded sample (~12 s), plus the single-thread rate (the reference itself runs with
+    torch.set_num_threads(1), rlf/run_settings.py:25-32) on a smaller one."""
+    threads = os.cpu_count() or 1
+    rate, _ = cpu_port_rate(task, 1024, n_steps, flat, threads, reps=2)
+    Bs = int(min(4 * B, max(2048, rate * 12.0))) // 1024 * 1024  # ~12 s of CPU work
+    rate, dt = cpu_port_rate(task, Bs, n_steps, flat, threads)
+    rate1, dt1 = cpu_port_rate(task, 1024, n_steps, flat, 1)
+    cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+           "sample": f"{Bs} of {B} rows, one pass ({dt:.1f} s), torch-CPU port of the reference op sequence "
+                     f"(oracle/torch_port.py) with {threads} threads",
+           "single_thread": {"value": rate1, "cores": 1, "sample": f"1024 rows, one pass ({dt1:.1f} s); the reference's own "
+                                                                   f"setting (torch.set_num_threads(1))"}}
+    trate, tdt = cpu_train_rate(task, 8192, flat, threads)
+    cpu_train = {"value": trate, "unit": "samples/s", "cores": threads, "kind": "port",
+                 "sample": f"3 updates of 2 x 8192 rows ({tdt:.2f} s each): fm_loss x 2, backward, clip_grad_norm_, Adam "
+                           f"(oracle/torch_port.py::train_step) with {threads} threads"}
+    return cpu, cpu_train
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (torch port, all host threads)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -521,20 +542,7 @@ def run_ours(args):
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
     cpu, cpu_train = None, None
     if world == 1 and not args.no_cpu:
-        from oracle import closed_form as cf
-
-        flat = model.net.flat_params().detach().cpu().numpy().copy()
-        threads = os.cpu_count() or 1
-        rate, _ = cpu_port_rate(task, 1024, n_steps, flat, threads, reps=2)
-        Bs = int(min(4 * B, max(2048, rate * 12.0))) // 1024 * 1024  # ~12 s of CPU work
-        rate, dt = cpu_port_rate(task, Bs, n_steps, flat, threads)
-        cpu = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"{Bs} of {B} rows, one pass ({dt:.1f} s), torch-CPU port of the reference op sequence "
-                         f"(oracle/torch_port.py) with {threads} threads"}
-        trate, tdt = cpu_train_rate(task, 8192, flat, threads)
-        cpu_train = {"value": trate, "unit": "samples/s", "cores": threads, "kind": "port",
-                     "sample": f"3 updates of 2 x 8192 rows ({tdt:.2f} s each): fm_loss x 2, backward, clip_grad_norm_, Adam "
-                               f"(oracle/torch_port.py::train_step) with {threads} threads"}
+        cpu, cpu_train = cpu_baseline_leg(task, B, n_steps, model.net.flat_params().detach().cpu().numpy().copy())
 
     line = {
         "metric": "scored_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
