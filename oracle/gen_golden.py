@@ -847,6 +847,23 @@ def gen_pretrain(P):
         print("wrote", name, len(curve), "steps", curve[0], curve[-1])
 
 
+def gen_yaml_keys():
+    """flowril_yaml_keys.json: the sweep parameters of the reference's flowril configs (configs/sine/flowril*.yaml: the only
+    flowril YAMLs the reference ships), so that the flag-compatibility test runs where /root/reference is absent."""
+    import glob
+    import json
+
+    import yaml
+
+    out = {}
+    for f in sorted(glob.glob(os.path.join(ref_shim.REFERENCE_ROOT, "configs", "sine", "flowril*.yaml"))):
+        y = yaml.safe_load(open(f))
+        out[os.path.basename(f)] = {k: v for k, v in y.get("parameters", {}).items()}
+    with open(os.path.join(OUT, "flowril_yaml_keys.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+    print("wrote flowril_yaml_keys.json", {k: len(v) for k, v in out.items()})
+
+
 def main():
     import torch
 
@@ -854,7 +871,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     P = ref_shim.load()
-    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "pretrain", "bcf", "gae", "ppo"]
+    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "pretrain", "bcf", "gae", "yaml", "ppo"]
     if "logprob" in which:
         gen_logprob(P)
     if "vfield" in which:
@@ -875,6 +892,8 @@ def main():
         gen_bcf()
     if "gae" in which:
         gen_gae()
+    if "yaml" in which:
+        gen_yaml_keys()
     if "ppo" in which:
         gen_ppo()
 

@@ -256,3 +256,36 @@ def test_ppo_oracle_tie_and_clip_rules_match_autograd():
     (vl * 0.5 + al - ent.mean() * 0.01).sum().backward()
     assert abs(losses[0] - float(vl * 0.5 + al - ent.mean() * 0.01)) < 1e-12
     assert np.abs(grad - t.grad.numpy()).max() < 1e-12
+
+
+def test_reference_sweep_yaml_keys_parse_with_our_flags():
+    """Every parameter of the reference's flowril sweep configs (configs/sine/flowril*.yaml, fixture written by
+    oracle/gen_golden.py::gen_yaml_keys) that the reward module or the PPO updater owns is accepted by our
+    get_add_args with the YAML's value; the rest are rl-toolkit's general run flags (rlf/args.py, base_il.py), which stay
+    with the framework."""
+    import argparse
+    import json
+    import os
+
+    from modril_b200.flowril.flowril import FlowMatchingEstimation
+    from modril_b200.ppo import PPO
+
+    framework = {"seed", "alg", "prefix", "env-name", "cuda", "eval-interval", "traj-load-path", "eval-num-processes",
+                 "num-eval", "num-env-steps"}
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flowril_yaml_keys.json")
+    configs = json.load(open(path))
+    assert len(configs) >= 5
+    for name, params in configs.items():
+        parser = argparse.ArgumentParser()
+        FlowMatchingEstimation().get_add_args(parser)
+        PPO().get_add_args(parser)
+        argv = []
+        for k, v in params.items():
+            if k in framework:
+                continue
+            val = v["value"] if "value" in v else v["values"][0]
+            argv += [f"--{k}", str(val)]
+        ns = parser.parse_args(argv)            # unknown flag -> SystemExit
+        assert ns.reward_type in ("raw", "norm", "exp", "clip", "smooth"), name
+        if "2fs" in name:
+            assert ns.option == "2fs" and ns.flow_path.endswith("sine_fm.pt")
