@@ -60,3 +60,28 @@ def test_enums_match_header():
                       ("FRL_REWARD_SMOOTH", 4)):
         m = re.search(name + r"\s*=\s*(-?\d+)", text)
         assert m and int(m.group(1)) == val, name
+
+
+def test_header_is_plain_c(tmp_path, lib):
+    """The boundary is a C ABI: the header compiles as C99 (-pedantic) and a C translation unit that takes the address of
+    every declared entry point links against the library (no C++ or torch types in any signature)."""
+    import shutil
+    import subprocess
+
+    from modril_b200 import _native
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = os.path.join(root, "include", "flowril_b200.h")
+    subprocess.check_call(["gcc", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", header])
+    names = _declared_symbols()
+    assert set(names) == set(_native.EXPORTS)
+    src = tmp_path / "link_all.c"
+    body = "\n".join(f"    p[{i}] = (void (*)(void))&{n};" for i, n in enumerate(names))
+    src.write_text('#include "flowril_b200.h"\n#include <stdio.h>\nint main(void) {\n    void (*p[%d])(void);\n%s\n'
+                   '    printf("%%d %%d\\n", (int)(p[0] != 0), %d);\n    return 0;\n}\n' % (len(names), body, len(names)))
+    exe = tmp_path / "link_all"
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wno-pedantic", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-lflowril_b200", f"-Wl,-rpath,{lib_dir}"])
