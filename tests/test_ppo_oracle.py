@@ -69,3 +69,34 @@ def test_oracle_updates_follow_reference_curve(path):
             assert np.allclose(losses, g["curve"][it], rtol=tol, atol=tol * 0.1), (it, losses, g["curve"][it])
             assert abs(norm - g["gradnorm"][it]) <= (2e-3 if it < 8 else 2e-2) * g["gradnorm"][it]
             it += 1
+
+
+def test_oracle_limits():
+    """Closed-form limits of the PPO oracle: on-policy data (ratio = 1) gives actor_loss = -mean(adv); a huge clip
+    switches both clips off; GAE with lambda = 1 and no episode ends is the discounted return."""
+    spec = ppo.ACSpec(7, 3, 32, 2)
+    flat = ppo.ac_make_params(spec, 8).astype(np.float64)
+    g = np.random.default_rng(1)
+    B = 100
+    obs, act = g.standard_normal((B, 7)), g.standard_normal((B, 3)) * 0.4
+    value, logp, ent = ppo.ac_evaluate(spec, flat, obs, act)
+    adv, ret = g.standard_normal((B, 1)), g.standard_normal((B, 1))
+    losses, _ = ppo.ppo_loss_and_grad(spec, flat, obs, act, logp, adv, ret, value)
+    assert abs(losses[2] + adv.mean()) < 1e-12 and abs(losses[1] - 0.5 * ((value - ret) ** 2).mean()) < 1e-12
+    assert abs(losses[3] - ent.mean()) < 1e-12
+    old_logp, old_value = logp + g.standard_normal((B, 1)), value + g.standard_normal((B, 1))
+    losses, _ = ppo.ppo_loss_and_grad(spec, flat, obs, act, old_logp, adv, ret, old_value, clip=1e9)
+    assert abs(losses[2] + (np.exp(logp - old_logp) * adv).mean()) < 1e-12
+    assert abs(losses[1] - 0.5 * ((value - ret) ** 2).mean()) < 1e-12
+    T, N, gamma = 12, 3, 0.9
+    r = g.standard_normal((T, N, 1)).astype(np.float32)
+    vp = g.standard_normal((T + 1, N, 1)).astype(np.float32)
+    ones = np.ones((T + 1, N, 1), np.float32)
+    nv = g.standard_normal((N, 1)).astype(np.float32)
+    returns, _ = ppo.compute_returns(r, vp, ones, ones, nv, gamma, 1.0, True, False)
+    want = np.zeros((T, N, 1))
+    acc = nv.astype(np.float64)
+    for t in reversed(range(T)):
+        acc = r[t] + gamma * acc
+        want[t] = acc
+    assert np.abs(returns[:-1] - want).max() < 1e-4
