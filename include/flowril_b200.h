@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FRL_ABI_VERSION 5
+#define FRL_ABI_VERSION 6
 #define FRL_MAX_STEPS 256
 #define FRL_MAX_DEPTH 8
 
@@ -47,7 +47,9 @@ typedef enum {
 typedef enum {
     FRL_PREC_FP32 = 0,    /* FP32 FFMA on CUDA cores: the 1e-4 parity mode                               */
     FRL_PREC_BF16 = 1,    /* tcgen05 tensor cores, bf16 operands, fp32 accumulate, fp32 ODE state/trace  */
-    FRL_PREC_BF16X3 = 2,  /* reserved (3-term operand split, fp32-grade products): returns FRL_ERR_UNSUPPORTED   */
+    FRL_PREC_FP16X3 = 2,  /* tcgen05 tensor cores, 3-term fp16 operand split (x_hi W_hi + x_lo W_hi + x_hi W_lo): fp32-grade
+                             products, the 1e-4 parity mode on tensor cores (nets outside its plan run the FP32 kernel)  */
+    FRL_PREC_BF16X3 = 2,  /* former name of FRL_PREC_FP16X3 (ABI <= 5 reserved it)                               */
     FRL_PREC_FP16 = 3     /* tcgen05 tensor cores, fp16 operands (11-bit significand), fp32 accumulate   */
 } frl_precision;
 

@@ -11,12 +11,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libflowril_b200.so")
 
-ABI_VERSION = 5
-PREC_FP32, PREC_BF16, PREC_BF16X3, PREC_FP16 = 0, 1, 2, 3
+ABI_VERSION = 6
+PREC_FP32, PREC_BF16, PREC_FP16X3, PREC_FP16 = 0, 1, 2, 3
+PREC_BF16X3 = PREC_FP16X3   # former (reserved) name
 HAS_TC = True  # tensor-core (tcgen05) log-density kernels are built in
 PROBE_SHARED, PROBE_PER_STEP, PROBE_EXACT = 0, 1, 2
 REWARD_TYPES = {"raw": 0, "norm": 1, "exp": 2, "clip": 3, "smooth": 4}
-PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16}   # PREC_BF16X3 (2) is reserved
+# "fp16x3": 3-term fp16 operand split on the tensor cores = fp32-grade products (the parity mode, and the default)
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp16": PREC_FP16, "fp16x3": PREC_FP16X3}
 
 # every symbol include/flowril_b200.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = (

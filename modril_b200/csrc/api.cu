@@ -38,7 +38,19 @@ int dispatch_score(const ScoreArgs& args, int precision, cudaStream_t st) {
     int rc;
     if (precision == FRL_PREC_FP32) {
         rc = launch_logprob_f32(args, st);
-    } else if (precision == FRL_PREC_BF16 || precision == FRL_PREC_BF16X3 || precision == FRL_PREC_FP16) {
+    } else if (precision == FRL_PREC_FP16X3) {
+        // fp32-grade products on the tensor cores (3-term fp16 split).  Nets outside the kernel's plan (H != 256, very wide
+        // inputs / outputs) take the FP32 FFMA kernel: the same accuracy class, so the mode never changes meaning.
+        rc = 1;
+        if (tc3x_supported(args.net[0])) {
+            for (int r = 0; r < args.n_roles; ++r) {
+                rc = ensure_pack(args.net[r], PACK_TC3X, st);
+                if (rc != FRL_OK) return rc;
+            }
+            rc = launch_logprob_tc3x(args, st);
+        }
+        if (rc > 0) rc = launch_logprob_f32(args, st);
+    } else if (precision == FRL_PREC_BF16 || precision == FRL_PREC_FP16) {
         rc = launch_logprob_tc(args, precision, st);
     } else {
         set_error("invalid argument: unknown precision");

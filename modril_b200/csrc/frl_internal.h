@@ -57,16 +57,16 @@ struct frl_net {
     // tensor-core packing (bf16 hi/mid/lo canonical UMMA tiles), see logprob_tc.cu
     void* pack_tc = nullptr;
     size_t pack_tc_bytes = 0;
-    void* pack_tc2 = nullptr;           // block stream of the 64+64-row / N = 256 integrator (logprob_tc2.cu)
     void* pack_tc3 = nullptr;           // per-CTA-rank block streams of the CTA-pair integrator (logprob_tc3.cu)
+    void* pack_tc3x = nullptr;          // the same for the 3-term split integrator (logprob_tc3x.cu): scaled W_hi / W_lo blocks
     bool has_params = false;
     // Lazy packing: frl_net_set_params only records the master vector and bumps `version`; each kernel family
     // (re)builds its own layout on first use after a change (frl::ensure_pack), on the consumer's stream.
     const float* params_dev = nullptr;
     unsigned long long version = 0;
-    unsigned long long packed[5] = {0, 0, 0, 0, 0};
-    cudaEvent_t pack_event[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t pack_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long packed[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t pack_event[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t pack_stream[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // tensor-core training: fp16 weight images (train_tc.cu) and workspace
     void* pack_train = nullptr;
     void* ws_tc = nullptr;
@@ -89,7 +89,7 @@ void frl_host_stage_free(frl_net* net);  // api.cu
 namespace frl {
 
 // net.cu: weight layouts, built lazily
-enum PackKind { PACK_F32 = 0, PACK_TC1 = 1, PACK_TC2 = 2, PACK_TC3 = 3, PACK_TRAIN = 4 };
+enum PackKind { PACK_F32 = 0, PACK_TC1 = 1, PACK_TC2 = 2, PACK_TC3 = 3, PACK_TRAIN = 4, PACK_TC3X = 5, PACK_KINDS = 6 };
 int ensure_pack(const frl_net* net, int kind, cudaStream_t stream);
 int pack_f32(frl_net* net, const float* params_dev, cudaStream_t stream);
 
@@ -121,20 +121,22 @@ constexpr int kMaxBlocks = 72;
 struct PackBlk {
     uint32_t goff;                   // bytes
     int nrows, klen, n0, k0, layer;  // layer == depth -> heads;  k0 < 0 -> bias block (rows k=0..2 = hi/mid/lo split)
+    int part = 0;                    // 0: the rounded value; 1 / 2: hi / lo term of the 2-term 16-bit split of (scale * value)
 };
 }  // namespace tc
 int tc_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
 int tc_pack_images(frl_net* net, const std::vector<tc::PackBlk>& pack, uint32_t image_bytes, void** dst,
-                   const float* params_dev, cudaStream_t stream);
+                   const float* params_dev, cudaStream_t stream, float scale = 1.f);
 int launch_logprob_tc(const ScoreArgs& args, int precision, cudaStream_t stream);
-
-// logprob_tc2.cu
-int tc2_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
-int launch_logprob_tc2(const ScoreArgs& args, int precision, cudaStream_t stream);
 
 // logprob_tc3.cu
 int tc3_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
 int launch_logprob_tc3(const ScoreArgs& args, int precision, cudaStream_t stream);
+
+// logprob_tc3x.cu (FRL_PREC_FP16X3)
+bool tc3x_supported(const frl_net* net);
+int tc3x_pack(frl_net* net, const float* params_dev, cudaStream_t stream);
+int launch_logprob_tc3x(const ScoreArgs& args, cudaStream_t stream);
 
 // train_f32.cu
 int cfm_loss_grad_f32(frl_net* net, float role_sign, const float* s, const float* a0, const float* t,

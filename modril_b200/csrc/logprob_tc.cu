@@ -593,6 +593,7 @@ struct PackParams {
     long long off_w[kMaxDepth], off_b[kMaxDepth], off_wh[2], off_bh[2];
     int depth, H, d_in, a_dim, n_heads, NOp;
     uint32_t image_bytes;   // bytes of one 16-bit image
+    float scale;            // weights and trunk biases are multiplied by it (a power of two) before rounding / splitting
 };
 
 __global__ void tc_pack_kernel(const float* __restrict__ flat, uint8_t* __restrict__ img_f16,
@@ -628,7 +629,7 @@ __global__ void tc_pack_kernel(const float* __restrict__ flat, uint8_t* __restri
                 hv[e] = __float2half_rn(0.f);
                 bv[e] = __float2bfloat16_rn(0.f);
                 if (j == 0 && e < 3) {
-                    const float b = flat[pp.off_b[k.layer] + ng];
+                    const float b = flat[pp.off_b[k.layer] + ng] * pp.scale;
                     float rh = b, rb = b;
                     __half th = __float2half_rn(0.f);
                     __nv_bfloat16 tb = __float2bfloat16_rn(0.f);
@@ -650,8 +651,13 @@ __global__ void tc_pack_kernel(const float* __restrict__ flat, uint8_t* __restri
                 const int a = pp.n_heads == 2 ? ng >> 1 : ng, head = pp.n_heads == 2 ? (ng & 1) : 0;
                 if (a < pp.a_dim) v = flat[pp.off_wh[head] + (long long)a * pp.H + kg];
             }
+            v *= pp.scale;
             hv[e] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
             bv[e] = __float2bfloat16_rn(v);
+            if (k.part == 2) {   // lo term of the 2-term split
+                hv[e] = __float2half_rn(v - __half2float(hv[e]));
+                bv[e] = __float2bfloat16_rn(v - __bfloat162float(bv[e]));
+            }
         }
         const size_t o = (size_t)k.goff + (size_t)c * 16;
         *reinterpret_cast<uint4*>(img_f16 + o) = *reinterpret_cast<uint4*>(hv);
@@ -727,7 +733,7 @@ struct TcPack {
 // fp16 + bf16 images of a block list (+ the fp32 bias vector) into *dst (allocated on first use):
 // layout [fp16 image | bf16 image | bias], each image rounded up to 256 B
 int tc_pack_images(frl_net* net, const std::vector<tc::PackBlk>& pack, uint32_t image_bytes, void** dst,
-                   const float* params_dev, cudaStream_t stream) {
+                   const float* params_dev, cudaStream_t stream, float scale) {
     using namespace tc;
     const int nb = net->cfg.depth * net->cfg.hidden + net->n_out_p;
     const size_t img = ((size_t)image_bytes + 255) / 256 * 256;
@@ -739,7 +745,7 @@ int tc_pack_images(frl_net* net, const std::vector<tc::PackBlk>& pack, uint32_t 
     for (int l = 0; l < net->cfg.depth; ++l) { pp.off_w[l] = net->off_w[l]; pp.off_b[l] = net->off_b[l]; }
     for (int h = 0; h < net->cfg.n_heads; ++h) { pp.off_wh[h] = net->off_wh[h]; pp.off_bh[h] = net->off_bh[h]; }
     pp.depth = net->cfg.depth; pp.H = net->cfg.hidden; pp.d_in = net->d_in; pp.a_dim = net->cfg.a_dim;
-    pp.n_heads = net->cfg.n_heads; pp.NOp = net->n_out_p; pp.image_bytes = image_bytes;
+    pp.n_heads = net->cfg.n_heads; pp.NOp = net->n_out_p; pp.image_bytes = image_bytes; pp.scale = scale;
     uint8_t* base = static_cast<uint8_t*>(*dst);
     tc_pack_kernel<<<dim3(4, pp.n_blocks + 1), 256, 0, stream>>>(params_dev, base, base + img,
                                                                  reinterpret_cast<float*>(base + 2 * img), pp);
@@ -766,24 +772,10 @@ static int launch_tc(const tc::Params& p, size_t smem_bytes, int grid, cudaStrea
 int launch_logprob_tc(const ScoreArgs& a, int precision, cudaStream_t stream) {
     using namespace tc;
     const frl_net* n0 = a.net[0];
-    if (precision == FRL_PREC_BF16X3) {
-        set_error("FRL_PREC_BF16X3 is not implemented in this build");
-        return FRL_ERR_UNSUPPORTED;
-    }
     // Kernel selection.  Default: the CTA-pair integrator (logprob_tc3.cu, cta_group::2) whenever the net fits its plan
-    // (H = 256, padded input width <= 32, <= 64 head columns, >= 4 ring slots); otherwise -- or with FRL_TC_V1=1 -- the
-    // 128-sample single-CTA kernel below.  FRL_TC_V2=1 selects the single-CTA N = 256 experiment (logprob_tc2.cu).
-    if (getenv("FRL_TC_V2")) {
-        for (int r = 0; r < a.n_roles; ++r) {
-            int rcp = ensure_pack(a.net[r], PACK_TC2, stream);
-            if (rcp != FRL_OK) return rcp;
-        }
-        if (n0->pack_tc2) {
-            const int rc2 = launch_logprob_tc2(a, precision, stream);
-            if (rc2 <= 0) return rc2;   // > 0: shapes that do not fit the 64-sample kernel's shared-memory plan
-        }
-    }
-    if (!getenv("FRL_TC_V1") && !getenv("FRL_TC_V2") && precision != FRL_PREC_BF16X3) {
+    // (H = 256, padded input width <= 192, <= 64 head columns, >= 4 ring slots); otherwise -- or with FRL_TC_V1=1 -- the
+    // 128-sample single-CTA kernel below.
+    if (!getenv("FRL_TC_V1")) {
         for (int r = 0; r < a.n_roles; ++r) {
             int rcp = ensure_pack(a.net[r], PACK_TC3, stream);
             if (rcp != FRL_OK) return rcp;

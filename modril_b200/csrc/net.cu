@@ -125,11 +125,11 @@ extern "C" int frl_net_destroy(frl_net* net) {
     cudaSetDevice(net->cfg.device);
     if (net->pack_f32) cudaFree(net->pack_f32);
     if (net->pack_tc) cudaFree(net->pack_tc);
-    if (net->pack_tc2) cudaFree(net->pack_tc2);
     if (net->pack_tc3) cudaFree(net->pack_tc3);
+    if (net->pack_tc3x) cudaFree(net->pack_tc3x);
     if (net->ws) cudaFree(net->ws);
     if (net->pack_train) cudaFree(net->pack_train);
-    for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < PACK_KINDS; ++k)
         if (net->pack_event[k]) cudaEventDestroy(net->pack_event[k]);
     if (net->ws_tc) cudaFree(net->ws_tc);
     if (net->ws_x0s) cudaFree(net->ws_x0s);
@@ -194,8 +194,9 @@ int ensure_pack(const frl_net* cnet, int kind, cudaStream_t st) {
     switch (kind) {
         case PACK_F32: rc = pack_f32(net, net->params_dev, st); break;
         case PACK_TC1: rc = tc_pack(net, net->params_dev, st); break;
-        case PACK_TC2: rc = tc2_pack(net, net->params_dev, st); break;
+        case PACK_TC2: set_error("pack kind 2 is retired"); return FRL_ERR_INVALID;
         case PACK_TC3: rc = tc3_pack(net, net->params_dev, st); break;
+        case PACK_TC3X: rc = tc3x_pack(net, net->params_dev, st); break;
         case PACK_TRAIN: rc = net->n_out_p <= 64 ? tc_train_pack(net, net->params_dev, st) : FRL_OK; break;
         default: set_error("bad pack kind"); return FRL_ERR_INVALID;
     }

@@ -17,6 +17,8 @@ What is pinned (reference call sites in brackets):
                   :55-59] and their double-backward parameter gradients; trainreg_*.npz: the update loop with them.
   bcf_*.npz       VectorNetwork.forward, the BCF loss + gradients and the Euler action sampler [rlf/rl/model.py:391-432,
                   rlf/algos/il/bcf.py:108-128, rlf/policies/flow_policy.py:49-63]; bcftrain_*.npz: _bc_step updates.
+  retnorm_*.npz   FlowMatchingEstimation._get_reward [flowril.py:210-230] with the reference RunningMeanStd
+                  [rlf/baselines/common/running_mean_std.py:3-35]: the return normalisation of row a10.
   gae_*.npz       RolloutStorage.compute_returns / compute_advantages [rlf/storage/rollout_storage.py:178-239]
   train_*.npz     the update loop of flowril.py:311-335 (zero_grad, backward, clip_grad_norm_, Adam.step) for
                   scrf (all params), scrf fine-tune (head_r only, flowril.py:52-63) and 2fs; loss curves + final
@@ -74,11 +76,25 @@ def gen_logprob(P):
     cases.append(("hopper", 2, 32, 128, 4, 1.0))
     cases.append(("hopper", 2, 8, 128, 2, 2.0))
     cases.append(("maze", 1, 32, 128, 3, 2.0))
+    _gen_logprob_cases(P, cases, "", 1000)
+
+
+def gen_logprob_smooth(P):
+    """logprob_sNN_*.npz: the same quantities on nets at the scale of the reference's default init (gain 1) for every
+    task dimension -- the nets on which the single-pass 16-bit tensor-core modes are held to north_star's 2e-3 bar
+    (the gain-2 nets above amplify every operand rounding through the ReLU kinks)."""
+    cases = [(task, 2, 20 if task == "maze" else 32, 256, 4, 1.0)
+             for task in ("sine", "maze", "hopper", "halfcheetah", "ant", "hand", "pick")]
+    cases += [("maze", 1, 20, 256, 4, 1.0), ("hopper", 1, 32, 256, 4, 1.0)]
+    _gen_logprob_cases(P, cases, "s", 1500)
+
+
+def _gen_logprob_cases(P, cases, tag, seed0):
     for idx, (task, n_heads, n_steps, hidden, depth, gain) in enumerate(cases):
         s_dim, a_dim = synth.TASK_DIMS[task]
         spec = cf.NetSpec(s_dim, a_dim, hidden, depth, n_heads)
         B = 96
-        seed = 1000 + idx
+        seed = seed0 + idx
         out = {"meta": np.array([s_dim, a_dim, hidden, depth, n_heads, n_steps, B, seed]), "gain": np.float32(gain)}
         s, a = synth.states_actions(seed, B, s_dim, a_dim)
         probe = synth.rademacher(seed + 1, (B, a_dim))
@@ -100,7 +116,7 @@ def gen_logprob(P):
                     runs.append(ref_log_prob(P, model, spec, s, a, role, e, n_steps).astype(np.float64))
                 zero = ref_log_prob(P, model, spec, s, a, role, np.zeros((B, a_dim), np.float32), n_steps)
                 out[f"logp_{role}_exact"] = (sum(runs) - (a_dim - 1) * zero.astype(np.float64)).astype(np.float32)
-        name = f"logprob_{idx:02d}_{task}_{'scrf' if n_heads == 2 else '2fs'}_h{hidden}d{depth}_n{n_steps}.npz"
+        name = f"logprob_{tag}{idx:02d}_{task}_{'scrf' if n_heads == 2 else '2fs'}_h{hidden}d{depth}_n{n_steps}.npz"
         np.savez_compressed(os.path.join(OUT, name), **out)
         print("wrote", name, out["logp_expert"][:3])
 
@@ -576,6 +592,66 @@ def gen_gae():
         print("wrote", name, float(st.returns.abs().mean()))
 
 
+RETNORM_CASES = [  # (T, N, gamma, rollouts, reward scale)
+    (16, 8, 0.99, 1, 1.0),
+    (128, 32, 0.99, 3, 5.0),     # the production shape (--num-steps 128 x --num-processes 32), state carried over rollouts
+    (7, 1, 0.9, 2, 0.01),
+]
+
+
+def retnorm_inputs(seed, T, N, rollouts, scale):
+    g = synth.rng(seed)
+    rewards = (g.standard_normal((rollouts, T, N, 1)) * scale - 0.3 * scale).astype(np.float32)
+    masks = (g.random((rollouts, T, N, 1)) > 0.04).astype(np.float32)
+    return rewards, masks
+
+
+def gen_retnorm():
+    """retnorm_*.npz: FlowMatchingEstimation._get_reward [modril/flowril/flowril.py:210-230] run as it is -- the method is
+    compiled from the reference file and bound to a stand-in object whose ``_compute_flow_reward`` returns the injected
+    reward -- with the reference's own ``RunningMeanStd`` [rlf/baselines/common/running_mean_std.py:3-35] imported by path
+    (numpy only).  Pins row a10: the discounted-return recursion, the float32 running moments, the scaling."""
+    import ast
+    import importlib.util
+    import types
+
+    import torch
+
+    rms_path = os.path.join(ref_shim.REFERENCE_ROOT, "deps", "rl-toolkit", "rlf", "baselines", "common", "running_mean_std.py")
+    spec_ = importlib.util.spec_from_file_location("ref_running_mean_std", rms_path)
+    rms_mod = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(rms_mod)
+    path = os.path.join(ref_shim.REFERENCE_ROOT, "modril", "flowril", "flowril.py")
+    tree = ast.parse(open(path).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "FlowMatchingEstimation"][0]
+    keep = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "_get_reward"]
+    assert len(keep) == 1
+    ns = {"torch": torch, "np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    net = types.SimpleNamespace(eval=lambda: None)
+    for idx, (T, N, gamma, rollouts, scale) in enumerate(RETNORM_CASES):
+        seed = 8800 + idx
+        rewards, masks = retnorm_inputs(seed, T, N, rollouts, scale)
+        obj = types.SimpleNamespace(
+            args=types.SimpleNamespace(option="scrf", flowril_reward_norm=True, gamma=gamma), flow_net=net, returns=None,
+            ret_rms=rms_mod.RunningMeanStd(shape=()))
+        out = np.empty_like(rewards)
+        state = []
+        for ro in range(rollouts):
+            storage = types.SimpleNamespace(masks=torch.from_numpy(masks[ro]))
+            for step in range(T):
+                obj._compute_flow_reward = lambda storage, step, add_info, ro=ro: torch.from_numpy(rewards[ro, step].copy())
+                r, _ = ns["_get_reward"](obj, step, storage, {})
+                out[ro, step] = r.numpy()
+            state.append((np.float32(obj.ret_rms.mean), np.float32(obj.ret_rms.var), np.float64(obj.ret_rms.count)))
+        name = f"retnorm_{idx:02d}_T{T}_N{N}_R{rollouts}.npz"
+        np.savez_compressed(os.path.join(OUT, name), meta=np.array([T, N, rollouts, seed]), gamma=np.float64(gamma),
+                            scale=np.float64(scale), normalised=out, final_returns=obj.returns.numpy(),
+                            rms_mean=np.array([s[0] for s in state]), rms_var=np.array([s[1] for s in state]),
+                            rms_count=np.array([s[2] for s in state]))
+        print("wrote", name, float(np.abs(out).mean()))
+
+
 def load_policy_classes():
     """The reference's ``MLPBasic`` (rlf/rl/model.py:246-296) and ``DiagGaussian`` (rlf/rl/distributions.py:26-75) class
     objects plus ``def_mlp_weight_init``, compiled from the reference sources as they lie under /root/reference (the
@@ -871,9 +947,11 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     P = ref_shim.load()
-    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "pretrain", "bcf", "gae", "yaml", "ppo"]
+    which = sys.argv[1:] or ["logprob", "vfield", "fmloss", "train", "reg", "trainreg", "gradnorm", "pretrain", "bcf", "gae", "yaml", "ppo", "retnorm"]
     if "logprob" in which:
         gen_logprob(P)
+    if "logprob_smooth" in which or "logprob" in which:
+        gen_logprob_smooth(P)
     if "vfield" in which:
         gen_vfield(P)
     if "fmloss" in which:
@@ -896,6 +974,8 @@ def main():
         gen_yaml_keys()
     if "ppo" in which:
         gen_ppo()
+    if "retnorm" in which:
+        gen_retnorm()
 
 
 if __name__ == "__main__":

@@ -1,6 +1,7 @@
 """The reward-module mirror (FlowMatchingEstimation hooks) on the GPU against the oracle, with a fake rollout storage.
 Reference call sites: flowril.py:175-230 (_get_reward), :232-350 (_update_reward_func), base_irl.py:37-72 (update)."""
 import argparse
+import os
 import copy
 
 import numpy as np
@@ -294,6 +295,27 @@ def test_device_return_normalisation_vs_oracle(T, N):
         assert abs(rms_dev.var[0] - rms_ref.var[0]) <= 2e-6 * rms_ref.var[0]
         assert abs(rms_dev.mean[0] - rms_ref.mean[0]) <= 2e-6 * max(1.0, abs(rms_ref.mean[0]))
         assert rms_dev.count == rms_ref.count
+
+
+@pytest.mark.parametrize("path", sorted(__import__("glob").glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "retnorm_*.npz"))),
+                         ids=os.path.basename)
+def test_device_return_normalisation_vs_reference_goldens(path):
+    """Row a10 against the REFERENCE: frl_normalise_rewards vs the committed outputs of the reference's own _get_reward
+    (flowril.py:210-230) + RunningMeanStd (running_mean_std.py:3-35), over consecutive rollouts (oracle/gen_golden.py)."""
+    from modril_b200.flowril.flowril import DeviceRunningMeanStd
+    from tests.test_oracle_vs_golden import _retnorm_inputs
+    g = np.load(path)
+    rewards, masks = _retnorm_inputs(g)
+    rms_dev, ret_dev = DeviceRunningMeanStd("cuda:0"), None
+    for ro in range(rewards.shape[0]):
+        got, ret_dev = rms_dev.normalise(torch.from_numpy(rewards[ro]).cuda(), torch.from_numpy(masks[ro]).cuda(),
+                                         float(g["gamma"]), ret_dev)
+        ref = g["normalised"][ro]
+        assert np.abs(got.cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
+        assert abs(rms_dev.var[0] - g["rms_var"][ro]) <= 2e-6 * g["rms_var"][ro]
+        assert abs(rms_dev.mean[0] - g["rms_mean"][ro]) <= 2e-6 * max(1.0, abs(g["rms_mean"][ro]))
+        assert rms_dev.count == float(g["rms_count"][ro])
+    assert np.abs(ret_dev.cpu().numpy() - g["final_returns"]).max() <= 1e-6 * max(1.0, np.abs(g["final_returns"]).max())
 
 
 def test_standalone_flowril_chain_reward_module_then_device_ppo():

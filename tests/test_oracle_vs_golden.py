@@ -131,3 +131,28 @@ def test_regularisers(path):
         if f"grad_{name}" in g:
             ref = g[f"grad_{name}"]
             assert np.abs(grad - ref).max() <= 5e-5 * np.abs(ref).max(), np.abs(grad - ref).max() / np.abs(ref).max()
+
+
+def _retnorm_inputs(g):
+    """Same draws as oracle/gen_golden.py::retnorm_inputs."""
+    T, N, rollouts, seed = (int(x) for x in g["meta"])
+    rg = synth.rng(seed)
+    scale = float(g["scale"])
+    rewards = (rg.standard_normal((rollouts, T, N, 1)) * scale - 0.3 * scale).astype(np.float32)
+    masks = (rg.random((rollouts, T, N, 1)) > 0.04).astype(np.float32)
+    return rewards, masks
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "retnorm_*.npz"))), ids=os.path.basename)
+def test_return_normalisation(path):
+    """Row a10: cf.normalise_rewards / cf.RunningMeanStd against the reference's own _get_reward (flowril.py:210-230) +
+    RunningMeanStd (rlf/baselines/common/running_mean_std.py:3-35) over consecutive rollouts (state carried over)."""
+    g = np.load(path)
+    rewards, masks = _retnorm_inputs(g)
+    rms, ret = None, None
+    for ro in range(rewards.shape[0]):
+        out, ret, rms = cf.normalise_rewards(rewards[ro], masks[ro], float(g["gamma"]), rms, ret)
+        assert np.array_equal(out, g["normalised"][ro]), np.abs(out - g["normalised"][ro]).max()
+        assert np.float32(rms.mean) == g["rms_mean"][ro] and np.float32(rms.var) == g["rms_var"][ro]
+        assert float(rms.count) == float(g["rms_count"][ro])
+    assert np.array_equal(ret, g["final_returns"])
