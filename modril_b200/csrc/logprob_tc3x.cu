@@ -11,8 +11,9 @@
 // 16x256b epilogue, DSMEM barrier relays) with ONE 64-sample tile per CTA instead of two: the tile's operand is held as
 // two 64 KB images (hi, lo), which is all the shared memory there is.  The tensor pipe stays busy inside a layer because
 // every trunk layer is 3x the MMA work of the one-pass kernel while the epilogue of accumulator half 0 runs under the
-// MMAs of half 1 (and vice versa across layers).  A weight block (one ring slot) is consumed by up to three MMA groups
-// ("segments"): [ones x bias rows] [x_hi x W_hi] [x_lo x W_hi], or [x_hi x W_lo] (up to four per block).
+// MMAs of half 1 (and vice versa across layers).  A weight block (one ring slot, K = 64) holds [bias rows] [W_hi] [W_lo]
+// and is read by two concurrent issue streams: [ones x bias rows] [x_hi x W_hi] into the main accumulator and
+// [x_lo x W_hi] [x_hi x W_lo] into the small-terms accumulator (see make_schedule for the block order and why).
 // Accumulators: the tensor core adds each K = 16 group into the fp32 TMEM accumulator with round-toward-zero, a bias
 // that is coherent over all units of a layer (measured: 48 chained MMAs per product put the median error of a stress
 // net at 8e-7, ten times the FFMA kernel's, and a numpy emulation of per-MMA truncation reproduces that figure to the
@@ -37,10 +38,11 @@ namespace tc3x {
 using namespace tcc;
 using namespace tc3h;
 
-constexpr int kEpiWarp0 = 4;    // warp 0 producer, warps 1-2 MMA issuers, warp 3 TMEM owner / peer relay, 8 epilogue warps
+constexpr int kEpiWarp0 = 6;    // warp 0 producer + TMEM owner, warps 1-5 MMA issuers (leader; main stream 2, small stream 3) / relay (peer: warp 1), 8 epilogue warps
+constexpr int kIssuers0 = 2, kIssuers1 = 2;   // issue threads of the main / small-terms stream (up to 2 / 3)
 constexpr int kEpiWarps = 8;    // four TMEM lane quarters x two 64-column slices of the accumulator half being drained
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
-constexpr int kSlotBytes = 18432;   // [16 bias rows +] K = 128 rows of this CTA's 64 output features
+constexpr int kSlotBytes = 18432;   // [16 bias rows +] W_hi and W_lo, K = 64, of this CTA's 64 output features
 constexpr int kMaxSlots = 8;
 constexpr int kRows = 128;      // rows of the UMMA operand: 64 samples x (primal, tangent)
 constexpr int kSamp = 64;
@@ -54,18 +56,21 @@ struct Seg {
     uint8_t n_k16;      // K = 16 MMAs of the segment (0: unused)
     uint16_t a_koff;    // first 8-feature chunk of the A operand
     uint16_t b_chunk;   // first 8-feature chunk of the ring slot the B operand starts at
-    uint16_t flags;     // bit 0: the first MMA of the segment overwrites its accumulator;  bit 1: the segment accumulates
-                        // into the small-terms accumulator (TMEM columns + 256)
+    uint16_t over;      // the first MMA of the segment overwrites its accumulator
 };
+// wait bits of a block
+constexpr int kWaitA = 1;        // << kq: operand columns 64 kq .. 64 kq + 63 written (a_ready[kq])
+constexpr int kWaitFree = 16;    // << h:  accumulator half h (main and small) drained (acc_free[h])
+// commit bits of a block
+constexpr int kCommitD = 1;      // << h: d_full[h]
+constexpr int kCommitKa = 4;     // << c: ka_done[c]
 struct Blk {
     uint32_t goff, bytes;   // ONE CTA's half of the weight block
     uint16_t nrows;         // N of the UMMA (both CTAs together)
     uint8_t src;            // A operand: 0 activations, 1 layer-0 input
-    uint8_t commit;         // bit 0 / 1: commit d_full[0] / d_full[1];  bit 2: commit ka_done
-    uint8_t wait;           // bit 0 / 1: wait a_ready[0] / a_ready[1] before issuing
-    uint8_t dhalf;          // accumulator half (TMEM column offset 128 * dhalf)
-    uint8_t n_seg;
-    Seg seg[4];
+    uint8_t commit, wait;
+    uint8_t dhalf;          // accumulator half (TMEM column offset 128 * dhalf; the small-terms accumulator is 256 columns further)
+    Seg seg[2][2];          // [stream: 0 main accumulator, 1 small-terms accumulator][up to two segments]
 };
 
 struct Params {
@@ -86,6 +91,9 @@ struct Params {
     uint32_t x0_bytes;           // one image (hi or lo) of the layer-0 operand; 0 when it lives inside the activation tile
     int x0_in_a;                 // wide inputs: see logprob_tc3.cu (the operand is rebuilt inside the activation images)
     const uint8_t* x0s;          // [tile][hi | lo][K0p/8][128][8] images of the state columns (x0_in_a only)
+    unsigned long long* trace;   // FRL_TC_TRACE: [4 roles][kTraceCap] {tag, clock} stamps of cluster 0's leader (timing experiments only)
+    int trace_step;              // the Euler step (of the first tile) that is recorded
+    uint32_t off_trace;          // shared-memory staging of the stamps
     Blk blk[kMaxBlocks];
     float t_mid[kMaxSteps];
 };
@@ -102,13 +110,12 @@ __device__ __forceinline__ uint32_t pack2_sat_f16(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack2_f16(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
 
-// (primal c, c+1; tangent c, c+1) accumulators -> the hi and lo operand words of the next layer: relu on the primal, the
-// tangent (and both lo words) masked by the sign of the primal pre-activation
-__device__ __forceinline__ void split4(uint32_t zp0, uint32_t zp1, uint32_t zt0, uint32_t zt1, uint32_t& ph, uint32_t& th,
-                                       uint32_t& pl, uint32_t& tl) {
-    const uint32_t keep = ~neg_mask16x2(zp0, zp1);
-    const float p0 = __uint_as_float(zp0) * kInvW, p1 = __uint_as_float(zp1) * kInvW;
-    const float t0 = __uint_as_float(zt0) * kInvW, t1 = __uint_as_float(zt1) * kInvW;
+// (primal c, c+1; tangent c, c+1) pre-activations (x 2^6) -> the hi and lo operand words of the next layer: relu on the
+// primal, the tangent (and both lo words) masked by the sign of the primal pre-activation
+__device__ __forceinline__ void split4(float zp0, float zp1, float zt0, float zt1, uint32_t& ph, uint32_t& th, uint32_t& pl,
+                                       uint32_t& tl) {
+    const uint32_t keep = ~neg_mask16x2(__float_as_uint(zp0), __float_as_uint(zp1));
+    const float p0 = zp0 * kInvW, p1 = zp1 * kInvW, t0 = zt0 * kInvW, t1 = zt1 * kInvW;
     ph = pack2_relu_f16(p0, p1);
     const uint32_t tr = pack2_sat_f16(t0, t1);
     const float2 pf = unpack2_f16(ph), tf = unpack2_f16(tr);
@@ -124,17 +131,38 @@ __device__ __forceinline__ void put_split(uint8_t* img_hi, uint32_t lo_off, uint
     *reinterpret_cast<__half*>(img_hi + lo_off + off) = l;
 }
 
+// FRL_TC_TRACE (timing experiments): clock stamps of ONE Euler step of cluster 0's leader, recorded in shared memory
+// (a stamp costs ~40 cycles; the global-memory tracer of logprob_tc3.cu distorts the issue threads) and copied out at exit.
+constexpr int kTraceCap = 160;   // stamps per role
+struct LTracer {
+    uint2* buf;
+    int n;
+    bool on;
+    __device__ __forceinline__ void init(uint8_t* base, int role, bool enable) {
+        buf = enable ? reinterpret_cast<uint2*>(base) + (size_t)role * kTraceCap : nullptr;
+        n = 0;
+        on = false;
+    }
+    __device__ __forceinline__ void arm(bool a) { on = a && buf != nullptr; }
+    __device__ __forceinline__ void mark(unsigned tag) {
+        if (on && n < kTraceCap) buf[n++] = make_uint2(tag, (unsigned)clock());
+    }
+};
+
 template <bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob_tc3x_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem);
     auto w_full = [&](int s) { return bar0 + 8u * s; };                  // own half of the block has landed (tx)
-    auto w_empty = [&](int s) { return bar0 + 8u * (kMaxSlots + s); };   // the MMAs that read the slot completed
-    auto a_ready = [&](int ch) { return bar0 + 8u * (2 * kMaxSlots + ch); };        // leader only
-    auto d_full = [&](int half) { return bar0 + 8u * (2 * kMaxSlots + 2 + half); };
-    auto hand = [&](int x) { return bar0 + 8u * (2 * kMaxSlots + 4 + x); };         // leader only
-    const uint32_t x0_full = bar0 + 8u * (2 * kMaxSlots + 6);    // wide inputs: the operand images have landed
-    const uint32_t ka_done = bar0 + 8u * (2 * kMaxSlots + 7);    // the layer's MMAs no longer read operand columns 0..127
+    auto w_empty = [&](int s) { return bar0 + 8u * (kMaxSlots + s); };   // both streams' MMAs on the slot completed
+    auto a_ready = [&](int kq) { return bar0 + 8u * (2 * kMaxSlots + kq); };         // leader only: operand columns 64 kq .. written
+    auto acc_free = [&](int h) { return bar0 + 8u * (2 * kMaxSlots + 4 + h); };      // leader only: accumulator half h drained
+    auto d_full = [&](int h) { return bar0 + 8u * (2 * kMaxSlots + 6 + h); };        // both streams' MMAs into half h completed
+    // the layer's MMAs no longer read operand columns 64 c .. 64 c + 63 (c = 0, 1): the epilogue of accumulator half 0 may
+    // overwrite them (the activation images are updated in place while the MMAs of half 1 are still running)
+    auto ka_done = [&](int c) { return bar0 + 8u * (2 * kMaxSlots + 8 + c); };
+    auto hand = [&](int st, int x) { return bar0 + 8u * (2 * kMaxSlots + 10 + st * 3 + x); };   // leader only: issue batons
+    const uint32_t x0_full = bar0 + 8u * (2 * kMaxSlots + 16);   // wide inputs: the operand images have landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
 
     constexpr uint32_t a_tile_bytes = (uint32_t)H * kRows * 2;   // 64 KB per image
@@ -144,9 +172,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     uint8_t* sOnes = smem + p.off_ones;   // [2][128][8]: feature 0..2 = 1.0 on the primal rows (bias hi/mid/lo terms)
     float* sBias = reinterpret_cast<float*>(smem + p.off_bias);     // [roles][NOp] head biases (trunk biases ride in the MMA)
     float* sState = reinterpret_cast<float*>(smem + p.off_state);   // a [a_dim][64], probe [a_dim][64]
-    uint4* sRec = reinterpret_cast<uint4*>(smem + p.off_rec);       // [n_blocks][5]: block header + up to four segments
+    uint4* sRec = reinterpret_cast<uint4*>(smem + p.off_rec);       // [n_blocks][5]: block header + 2 streams x 2 segments
     uint2* sRingRec = reinterpret_cast<uint2*>(smem + p.off_rrec);  // [n_blocks] {offset, bytes} of the producer's loads
     uint8_t* sRing = smem + p.off_ring;
+    uint8_t* sTrace = smem + p.off_trace;
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();          // 0 = leader (issues the MMAs of the pair)
@@ -156,19 +186,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
             mbar_init(w_full(s), cta_rank == 0 ? 2 : 1);   // leader: own producer + the peer's relay
-            mbar_init(w_empty(s), 1);
+            mbar_init(w_empty(s), 2);                      // one commit per stream
         }
-        mbar_init(a_ready(0), 2 * kEpiWarps);   // every epilogue warp of the two CTAs works on both column halves
-        mbar_init(a_ready(1), 2 * kEpiWarps);
-        mbar_init(d_full(0), 1);
-        mbar_init(d_full(1), 1);
-        mbar_init(hand(0), 1);
-        mbar_init(hand(1), 1);
+        for (int kq = 0; kq < 4; ++kq) mbar_init(a_ready(kq), kEpiWarps);   // the 4 warps of that column slice in each of the two CTAs
+        for (int h = 0; h < 2; ++h) {
+            mbar_init(acc_free(h), 2 * kEpiWarps);   // every epilogue warp of both CTAs
+            mbar_init(d_full(h), 2);
+            mbar_init(ka_done(h), 2);
+            for (int x = 0; x < 3; ++x) mbar_init(hand(h, x), 1);
+        }
         mbar_init(x0_full, 1);
-        mbar_init(ka_done, 1);
         fence_barrier_init();
     }
-    if (warp == 3) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
@@ -185,19 +215,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         const uint32_t nhalf = k.nrows >> 1;
         // M = 256 over the pair, N = nrows (each CTA holds nrows / 2 rows of B); fp16 x fp16 -> fp32
         const uint32_t idesc = (1u << 4) | ((uint32_t)(256 >> 4) << 24) | ((uint32_t)(k.nrows >> 3) << 17);
-        sRec[5 * b] = make_uint4(idesc, (uint32_t)k.nrows | ((uint32_t)k.commit << 16) | ((uint32_t)k.wait << 24),
-                                 (uint32_t)k.dhalf * 128, (uint32_t)k.n_seg);
-        for (int sg = 0; sg < 4; ++sg) {
-            const Seg& g = k.seg[sg];
-            uint32_t src;
-            if (g.a_img == 2) src = smem_u32(sOnes);
-            else if (k.src == 0 || WIDE) src = smem_u32(sA) + g.a_img * a_tile_bytes;
-            else src = smem_u32(sX0) + g.a_img * p.x0_bytes;
-            const uint32_t a_lo = (((src + (uint32_t)g.a_koff * kChunk) >> 4) & 0x3FFF) | ((kChunk >> 4) << 16);
-            sRec[5 * b + 1 + sg] = make_uint4(a_lo, (uint32_t)g.b_chunk * nhalf, sg < k.n_seg ? g.n_k16 : 0u, (uint32_t)g.flags);
-        }
+        sRec[5 * b] = make_uint4(idesc, (uint32_t)k.nrows | ((uint32_t)k.commit << 16), (uint32_t)k.wait, (uint32_t)k.dhalf * 128);
+        for (int st = 0; st < 2; ++st)
+            for (int sg = 0; sg < 2; ++sg) {
+                const Seg& g = k.seg[st][sg];
+                uint32_t src;
+                if (g.a_img == 2) src = smem_u32(sOnes);
+                else if (k.src == 0 || WIDE) src = smem_u32(sA) + g.a_img * a_tile_bytes;
+                else src = smem_u32(sX0) + g.a_img * p.x0_bytes;
+                const uint32_t a_lo = (((src + (uint32_t)g.a_koff * kChunk) >> 4) & 0x3FFF) | ((kChunk >> 4) << 16);
+                sRec[5 * b + 1 + 2 * st + sg] = make_uint4(a_lo, (uint32_t)g.b_chunk * nhalf, g.n_k16, g.over);
+            }
         sRingRec[b] = make_uint2(k.goff, k.bytes);
     }
+    if (tracing)
+        for (int i = threadIdx.x; i < 4 * kTraceCap; i += kThreads) reinterpret_cast<uint2*>(sTrace)[i] = make_uint2(0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -218,12 +250,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            LTracer tr; tr.init(sTrace, 3, tracing);
             for (long long duo = cluster_id; duo < n_duos; duo += n_clusters) {
                 const uint8_t* wbase = p.wpack[duo % p.n_roles] + (size_t)cta_rank * p.rank_stride;
                 for (int step = 0; step < p.n_steps; ++step) {
+                    tr.arm(duo == cluster_id && step == p.trace_step);
                     for (int i = 0; i < p.n_blocks; ++i) {
                         const uint2 k = sRingRec[i];
                         mbar_wait(w_empty(stage), phase ^ 1);
+                        tr.mark(0x200 + i);
                         mbar_expect_tx(w_full(stage), k.y);
                         bulk_g2s(smem_u32(sRing + (size_t)stage * kSlotBytes), wbase + k.x, k.y, w_full(stage));
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
@@ -231,7 +266,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                 }
             }
         }
-    } else if (warp == 3 && cta_rank == 1) {
+    } else if (warp == 1 && cta_rank == 1) {
         // ------------------------------- peer: tell the leader when my half of a block has landed -----------------
         if (lane == 0) {
             int stage = 0;
@@ -244,36 +279,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
         }
-    } else if (warp >= 1 && warp <= 2 && cta_rank == 0) {
-        // ------------------------------- leader: the two MMA issuers (for both CTAs) ------------------------------
-        // They alternate blocks with a baton (see logprob_tc3.cu): issuer x issues block seq (seq % 2 == x), hands the
-        // baton over and only then pays for its commits, which run in the shadow of the partner's MMAs.
+    } else if (warp >= 1 && warp <= 5 && cta_rank == 0) {
+        // ------------------------------- leader: the MMA issuers (for both CTAs) ----------------------------------
+        // Two STREAMS run concurrently on every weight block: stream 0 issues the products that go to the main accumulator
+        // ([ones x bias rows], x_hi W_hi), stream 1 those of the small-terms accumulator (x_lo W_hi, x_hi W_lo).  The streams
+        // write different accumulators, so their relative order in the pipe does not matter (deterministic).  A thread pays
+        // ~60-80 cycles per tcgen05.mma, ~250 per tcgen05.commit and ~100-500 per barrier wait, against 64 pipe cycles per
+        // N = 128 MMA: inside a stream the threads take the blocks round-robin and pass a baton once their MMAs are
+        // issued, so the commits and waits of one run in the shadow of the others' MMAs while the baton keeps the accumulation
+        // order of the stream fixed.  EVERY issuer observes every phase of every readiness barrier, in block order: a thread
+        // that asked for phase n before phase n-1 had completed would see the parity of phase n-1's predecessor and pass.
+        // (Measured: three threads in the small-terms stream, or polling with mbarrier.test_wait instead of the suspending
+        // try_wait, are both SLOWER -- the kernel is bound by shared-memory operand traffic, which polling adds to.)
         if (lane == 0) {
-            const int x = warp - 1;
-            uint32_t par_a0 = 0, par_a1 = 0, par_h = 0;
+            const int st = warp <= kIssuers0 ? 0 : 1;
+            const int n_x = st == 0 ? kIssuers0 : kIssuers1, x = st == 0 ? warp - 1 : warp - 1 - kIssuers0;
+            uint32_t par_a = 0, par_f = 0, par_h = 0;   // parity bits of a_ready[0..3] / acc_free[0..1]
             long long seq = 0;
+            int turn = 0;                               // seq % n_x
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t ring_lo = smem_u32(sRing) >> 4;
             constexpr uint32_t kDescHi = (uint32_t)(128 >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
+            LTracer tr; tr.init(sTrace, 1 + st, tracing && x == 0);           // roles 1 / 2: first issuer of stream 0 / 1
             for (long long duo = cluster_id; duo < n_duos; duo += n_clusters) {
                 for (int step = 0; step < p.n_steps; ++step) {
+                    tr.arm(duo == cluster_id && step == p.trace_step);
                     for (int b = 0; b < p.n_blocks; ++b, ++seq) {
                         const uint4 r0 = sRec[5 * b];
-                        // every issuer observes every readiness phase of the operand (a skipped phase would alias parities)
-                        if (r0.y & (1u << 24)) { mbar_wait_cluster(a_ready(0), par_a0); par_a0 ^= 1; }
-                        if (r0.y & (2u << 24)) { mbar_wait_cluster(a_ready(1), par_a1); par_a1 ^= 1; }
-                        if ((int)(seq & 1) == x) {
-                            if (seq > 0) { mbar_wait(hand(x), par_h); par_h ^= 1; }
+                        const bool mine = turn == x;
+                        if (r0.z) {
+#pragma unroll
+                            for (int kq = 0; kq < 4; ++kq)
+                                if (r0.z & (kWaitA << kq)) {
+                                    mbar_wait_cluster(a_ready(kq), (par_a >> kq) & 1);
+                                    par_a ^= 1u << kq;
+                                }
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                if (r0.z & (kWaitFree << h)) {
+                                    mbar_wait_cluster(acc_free(h), (par_f >> h) & 1);
+                                    par_f ^= 1u << h;
+                                }
+                        }
+                        if (mine) {
+                            tr.mark(0x600 + b);   // readiness of the block's operands / accumulator observed
+                            if (seq > 0) { mbar_wait(hand(st, x), par_h); par_h ^= 1; }
                             mbar_wait(w_full(stage), phase);   // both halves of the block are in the two CTAs' rings
+                            tr.mark(0x300 + b);
                             tc_fence_after();
-                            const uint32_t nhalf = (r0.y & 0xFFFF) >> 1, n_seg = r0.w;
+                            const uint32_t nhalf = (r0.y & 0xFFFF) >> 1;
                             const uint32_t b_base = ((ring_lo + (uint32_t)stage * (kSlotBytes >> 4)) & 0x3FFF) | (nhalf << 16);
-                            for (uint32_t sg = 0; sg < n_seg; ++sg) {
-                                const uint4 r = sRec[5 * b + 1 + sg];
+                            const uint32_t d_addr = tmem + r0.w + (st ? 256u : 0u);
+#pragma unroll
+                            for (int sg = 0; sg < 2; ++sg) {
+                                const uint4 r = sRec[5 * b + 1 + 2 * st + sg];
                                 uint32_t a_lo = r.x, b_lo = b_base + r.y;
-                                uint32_t acc = (r.w & 1) ? 0u : 1u;
-                                const uint32_t d_addr = tmem + r0.z + ((r.w & 2) ? 256u : 0u);
+                                uint32_t acc = r.w ? 0u : 1u;
                                 for (uint32_t u = 0; u < r.z; ++u) {
                                     umma2_f16(d_addr, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, r0.x, acc);
                                     acc = 1u;
@@ -281,13 +343,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                                     b_lo += 2 * nhalf;
                                 }
                             }
-                            mbar_arrive(hand(x ^ 1));
+                            mbar_arrive(hand(st, x + 1 == n_x ? 0 : x + 1));
+                            tr.mark(0x700 + b);
                             umma2_commit_both(w_empty(stage));
                             const uint32_t cm = (r0.y >> 16) & 0xFF;
-                            if (cm & 4) umma2_commit_both(ka_done);
-                            if (cm & 1) umma2_commit_both(d_full(0));
-                            if (cm & 2) umma2_commit_both(d_full(1));
+                            if (cm & kCommitKa) umma2_commit_both(ka_done(0));
+                            if (cm & (kCommitKa << 1)) umma2_commit_both(ka_done(1));
+                            if (cm & kCommitD) umma2_commit_both(d_full(0));
+                            if (cm & (kCommitD << 1)) umma2_commit_both(d_full(1));
+                            tr.mark(0x400 + b);
                         }
+                        if (++turn == n_x) turn = 0;
                         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -295,9 +361,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         }
     } else if (warp >= kEpiWarp0) {
         // ------------------------------------------------ epilogue ------------------------------------------------
-        // Every warp works on BOTH accumulator halves in turn (the halves complete one after the other, so this puts all
-        // eight warps on the half that has just completed): warp (q, cs) owns TMEM lane quarter q and the 64-column slice
-        // cs of each half.  The heads (<= 64 columns) are split by 16-row group instead.
+        // Every warp works on BOTH accumulator halves in turn: warp (q, cs) owns TMEM lane quarter q and the 64-column
+        // slice cs of each half, i.e. operand columns 128 h + 64 cs .. + 63 = K quarter 2 h + cs of the next layer.  The heads
+        // (<= 64 columns) are split by 16-row group instead.
         const int ew = warp - kEpiWarp0;
         const int q = warp & 3;                 // TMEM lane quarter: operand rows 32q .. 32q+31 = samples 16q .. 16q+15
         const int cs = ew >> 2;                 // trunk: 64-column slice of the half;  heads: 16-row group
@@ -312,6 +378,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         float* const sA_state = sState;
         float* const sP_state = sState + p.a_dim * kSamp;
         const uint32_t x0_img_bytes = (uint32_t)p.K0p * kRows * 2;
+        LTracer tr; tr.init(sTrace, 0, tracing && lane == 0 && ew == 0);
 
         // wide inputs: bulk copies of a tile's state-column images (hi, lo) into the activation images (one thread) ...
         auto x0_fetch = [&](long long tile) {
@@ -330,6 +397,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                 put_split(x0, lo_off, (j >> 3) * kChunk + (rowp + 8) * 16 + (j & 7) * 2, sP_state[j * kSamp + srow]);
             }
             if (write_t) put_split(x0, lo_off, (t_col >> 3) * kChunk + rowp * 16 + (t_col & 7) * 2, tval);
+        };
+        // the layer-0 operand is complete and the head accumulators are drained: every barrier the issuers wait on gets one
+        // phase (warp (q, cs) arrives for the operand quarters cs and 2 + cs, so that each collects its 4 + 4 arrivals)
+        auto arrive_all = [&]() {
+            if (lane == 0) {
+                arrive_leader(acc_free(0));
+                arrive_leader(acc_free(1));
+                arrive_leader(a_ready(cs));
+                arrive_leader(a_ready(2 + cs));
+            }
         };
 
         for (long long duo = cluster_id; duo < n_duos; duo += n_clusters) {
@@ -371,33 +448,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
             log_det = 0.f;
             fence_async_smem();
             named_sync(1, kEpiWarps * 32);
-            if (lane == 0) {
-                arrive_leader(a_ready(0));
-                arrive_leader(a_ready(1));
-            }
+            arrive_all();
 
             for (int step = 0; step < p.n_steps; ++step) {
+                tr.arm(duo == cluster_id && step == p.trace_step);
                 // ---- trunk layers: accumulator half h (main + small terms) -> columns 128 h .. 128 h + 127 of the operand images ----
                 for (int l = 0; l < p.depth; ++l) {
 #pragma unroll 1
                     for (int h = 0; h < 2; ++h) {
+                        tr.mark(0x100 + l * 2 + h);
                         mbar_wait(d_full(h), par_d[h]);
                         par_d[h] ^= 1;
                         tc_fence_after();
-                        // both 16-row groups of this warp's lane quarter in two software-pipelined rounds (see logprob_tc3.cu)
-                        uint32_t z[2][32], y[2][32];
+                        tr.mark(0x200 + l * 2 + h);
+                        // z = main + small accumulator (fp32, round-to-nearest) of both 16-row groups of this warp's lane quarter
+                        float z[2][32];
                         const uint32_t col0 = (uint32_t)(h * 128 + cs * 64);
-                        auto load_grp = [&](int grp) {
-                            const uint32_t tb = lane_addr + ((uint32_t)(grp * 16) << 16) + col0;
-                            tmem_ld_16x256b_x8(tb, z[grp]);
-                            tmem_ld_16x256b_x8(tb + 256, y[grp]);
-                        };
-                        auto sum_grp = [&](int grp) {   // main + small accumulator, fp32 round-to-nearest
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                z[grp][i] = __float_as_uint(__uint_as_float(z[grp][i]) + __uint_as_float(y[grp][i]));
-                        };
-                        auto store_grp = [&](int grp) {
+                        for (int grp = 0; grp < 2; ++grp) {
+                            uint32_t zm[32], zs[32];
+                            const uint32_t tb = lane_addr + ((uint32_t)(grp * 16) << 16) + col0;
+                            tmem_ld_16x256b_x8(tb, zm);
+                            tmem_ld_16x256b_x8(tb + 256, zs);
+                            tmem_ld_wait_dep(zm);
+                            tmem_ld_wait_dep(zs);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) z[grp][i] = __uint_as_float(zm[i]) + __uint_as_float(zs[i]);
+                        }
+                        // the accumulator half is in registers: the next layer's MMAs may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) arrive_leader(acc_free(h));
+                        tr.mark(0x500 + l * 2 + h);
+                        if (h == 0) {   // in-place update: wait until half 1's MMAs are past this warp's operand columns
+                            mbar_wait(ka_done(cs), (par_k >> cs) & 1);
+                            par_k ^= 1u << cs;
+                        }
+#pragma unroll
+                        for (int grp = 0; grp < 2; ++grp) {
                             // lane i addresses row i%8 of matrix i/8: matrices 0/1 = primal/tangent rows of chunk k,
                             // matrices 2/3 = the same of chunk k+1
                             const uint32_t rowa = (uint32_t)(q * 32 + grp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8);
@@ -413,34 +501,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                                 stmatrix_x4(addr + a_tile_bytes, wl[0], wl[1], wl[2], wl[3]);
                                 addr += 2 * kChunk;
                             }
-                        };
-                        load_grp(0);
-                        tmem_ld_wait_dep(z[0]);
-                        tmem_ld_wait_dep(y[0]);
-                        load_grp(1);
-                        sum_grp(0);
-                        if (h == 0) {   // in-place update: wait until half 1's MMAs are past operand columns 0..127
-                            mbar_wait(ka_done, par_k);
-                            par_k ^= 1;
                         }
-                        store_grp(0);
-                        tmem_ld_wait_dep(z[1]);
-                        tmem_ld_wait_dep(y[1]);
-                        sum_grp(1);
-                        store_grp(1);
-                        tc_fence_before();
                         fence_async_smem();
                         __syncwarp();
-                        if (lane == 0) arrive_leader(a_ready(h));
+                        if (lane == 0) arrive_leader(a_ready(2 * h + cs));
+                        tr.mark(0x300 + l * 2 + h);
                     }
                 }
                 // ---- heads: tanh, divergence, Euler update (pretrain.py:205-211) ----
+                tr.mark(0x1F0);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {   // the heads block commits both barriers: every warp follows both
+                for (int h = 0; h < 2; ++h) {   // the last heads block commits both barriers: every warp follows both
                     mbar_wait(d_full(h), par_d[h]);
                     par_d[h] ^= 1;
                 }
                 tc_fence_after();
+                tr.mark(0x2F0);
                 // wide inputs: the activation images are free (their last reader, the heads MMA, is done): fetch the next
                 // step's layer-0 operand images while the heads are evaluated
                 if (WIDE && step + 1 < p.n_steps && et == 0) x0_fetch(tile);
@@ -528,12 +604,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         tc_fence_before();
                         fence_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
-                            arrive_leader(a_ready(0));
-                            arrive_leader(a_ready(1));
-                        }
+                        arrive_all();
                     }
                 }
+                tr.mark(0x3F0);
             }
             // the next tile's init rewrites X0 / state: every epilogue warp must be done with this tile first
             tc_fence_before();
@@ -542,8 +616,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     }
     tc_fence_before();
     __syncthreads();
+    if (tracing)
+        for (int i = threadIdx.x; i < 4 * kTraceCap; i += kThreads) {
+            const uint2 v = reinterpret_cast<const uint2*>(sTrace)[i];
+            p.trace[i] = ((unsigned long long)v.x << 32) | v.y;
+        }
     cluster_sync_all();   // the leader's last MMAs read the peer's shared memory: nobody leaves or frees TMEM early
-    if (warp == 3) {
+    if (warp == 0) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
     }
@@ -594,7 +673,7 @@ static bool supported(const frl_net* net) {
     return net->cfg.hidden == H && net->d_in_p <= 192 && net->n_out_p <= 64;
 }
 static int block_count(const frl_net* net, bool wide) {
-    const int l0 = wide ? 2 * 2 * ((net->d_in_p + 127) / 128) : 2;
+    const int l0 = wide ? 2 * ((net->d_in_p + 63) / 64) : 2;
     return l0 + 8 * (net->cfg.depth - 1) + 2;
 }
 static uint32_t front_bytes(const frl_net* net, int n_roles, bool wide) {
@@ -618,74 +697,73 @@ static int choose_layout(const frl_net* net) {
     return -1;
 }
 
+// One Euler step as a list of weight blocks.  A block is one ring slot: [16 bias rows] [W_hi piece] [W_lo piece] of one
+// (layer, accumulator half, K piece), read by both streams.  Trunk layers run in K = 64 pieces ("K quarters" kq = the 64
+// operand columns one epilogue warp slice writes) in the order
+//        (h0,k0) (h0,k1) (h1,k0) (h0,k2) (h0,k3) (h1,k1) (h1,k2) (h1,k3)
+// chosen against the dependency chain of a single tile: the previous layer's epilogue of half 1 (operand quarters k2, k3)
+// ends ~2000 cycles after that layer's last MMA, and three pieces (2300 pipe cycles) need only k0, k1; half 0 completes
+// after the fifth piece, so its own epilogue (quarters k0, k1 of the NEXT layer) runs under the last three.
 static Schedule make_schedule(const frl_net* net) {
     Schedule sc;
     const int depth = net->cfg.depth, K0p = net->d_in_p, NOp = net->n_out_p;
     const bool wide = choose_layout(net) == 1;
     uint32_t goff = 0;
-    struct Piece { int part; int k0, klen; };   // part: 0 bias rows (k0 = -1), 1 W_hi, 2 W_lo
-    // one block: `pieces` are laid out back to back in the ring slot (rank r holds rows n_base + r * nrows/2 ...), `segs` are
-    // the MMA groups that read them
-    auto add = [&](int layer, int nrows, int n_base, int src, std::vector<Piece> pieces, std::vector<Seg> segs, int commit,
-                   int wait, int dhalf) {
+    // k0 < 0: no piece.  The block's slot holds [bias16 if `bias`] [W_hi k0..k0+klen) [W_lo k0..k0+klen)].
+    auto add = [&](int layer, int nrows, int n_base, int src, bool bias, int k0, int klen, bool open_small, bool open_main,
+                   int commit, int wait, int dhalf) {
         Blk b{};
         b.goff = goff; b.nrows = (uint16_t)nrows; b.src = (uint8_t)src; b.commit = (uint8_t)commit;
-        b.wait = (uint8_t)wait; b.dhalf = (uint8_t)dhalf; b.n_seg = (uint8_t)segs.size();
-        for (size_t i = 0; i < segs.size(); ++i) b.seg[i] = segs[i];
-        for (const Piece& pc : pieces) {
+        b.wait = (uint8_t)wait; b.dhalf = (uint8_t)dhalf;
+        auto piece = [&](int part, int pk0, int pklen) {
             for (int r = 0; r < 2; ++r) {
-                tc::PackBlk pb{goff, nrows / 2, pc.klen, n_base + r * (nrows / 2), pc.k0, layer};
-                pb.part = pc.part;
+                tc::PackBlk pb{goff, nrows / 2, pklen, n_base + r * (nrows / 2), pk0, layer};
+                pb.part = part;
                 sc.pack[r].push_back(pb);
             }
-            goff += (uint32_t)(nrows / 2) * pc.klen * 2;
-        }
+            goff += (uint32_t)(nrows / 2) * pklen * 2;
+        };
+        const int nk = klen / 16, c_hi = bias ? 2 : 0, c_lo = c_hi + klen / 8;
+        if (bias) piece(0, -1, 16);
+        piece(1, k0, klen);
+        piece(2, k0, klen);
+        int m = 0;
+        if (bias) b.seg[0][m++] = Seg{2, 1, 0, 0, 1};                                              // ones x bias rows opens the main accumulator
+        b.seg[0][m++] = Seg{0, (uint8_t)nk, (uint16_t)(k0 / 8), (uint16_t)c_hi, (uint16_t)((open_main && !bias) ? 1 : 0)};   // x_hi W_hi
+        b.seg[1][0] = Seg{1, (uint8_t)nk, (uint16_t)(k0 / 8), (uint16_t)c_hi, (uint16_t)(open_small ? 1 : 0)};              // x_lo W_hi
+        b.seg[1][1] = Seg{0, (uint8_t)nk, (uint16_t)(k0 / 8), (uint16_t)c_lo, 0};                                           // x_hi W_lo
         b.bytes = goff - b.goff;
         sc.blk.push_back(b);
     };
-    constexpr int OVER = 1, SMALL = 2;   // Seg::flags
-    auto seg = [](int a_img, int n_k16, int a_koff, int b_chunk, int flags) {
-        return Seg{(uint8_t)a_img, (uint8_t)n_k16, (uint16_t)a_koff, (uint16_t)b_chunk, (uint16_t)flags};
-    };
-    // In every (layer, accumulator half): the bias MMA opens the main accumulator, the first x_lo W_hi MMA the small one.
-    // layer 0
+    const int wait_all_a = kWaitA * 15;
+    // layer 0: the whole (narrow) input per accumulator half, or K = 64 pieces of a wide one
     for (int h = 0; h < 2; ++h) {
-        if (!wide) {   // [bias16 | W_hi K0p | W_lo K0p]: one block per accumulator half
-            const int nk = K0p / 16;
-            add(0, 128, 128 * h, 1, {{0, -1, 16}, {1, 0, K0p}, {2, 0, K0p}},
-                {seg(2, 1, 0, 0, OVER), seg(0, nk, 0, 2, 0), seg(1, nk, 0, 2, SMALL | OVER), seg(0, nk, 0, 2 + K0p / 8, SMALL)},
-                (1 << h) | (h == 1 ? 4 : 0), h == 0 ? 3 : 0, h);
-        } else {
-            for (int k0 = 0; k0 < K0p; k0 += 128) {
-                const int klen = std::min(128, K0p - k0), nk = klen / 16;
-                const bool last = k0 + klen >= K0p;
-                if (k0 == 0)
-                    add(0, 128, 128 * h, 1, {{0, -1, 16}, {1, k0, klen}},
-                        {seg(2, 1, 0, 0, OVER), seg(0, nk, k0 / 8, 2, 0), seg(1, nk, k0 / 8, 2, SMALL | OVER)}, 0, h == 0 ? 3 : 0, h);
-                else
-                    add(0, 128, 128 * h, 1, {{1, k0, klen}}, {seg(0, nk, k0 / 8, 0, 0), seg(1, nk, k0 / 8, 0, SMALL)}, 0, 0, h);
-                add(0, 128, 128 * h, 1, {{2, k0, klen}}, {seg(0, nk, k0 / 8, 0, SMALL)},
-                    (last ? 1 << h : 0) | ((h == 1 && k0 == 0) ? 4 : 0), 0, h);
-            }
+        const int step = wide ? 64 : K0p;
+        for (int k0 = 0; k0 < K0p; k0 += step) {
+            const int klen = std::min(step, K0p - k0);
+            const bool first = k0 == 0, last = k0 + klen >= K0p;
+            add(0, 128, 128 * h, 1, first, k0, klen, first, false,
+                (last ? kCommitD << h : 0) | ((last && h == 1) ? kCommitKa * 3 : 0),
+                first ? (kWaitFree << h) | (h == 0 ? wait_all_a : 0) : 0, h);
         }
     }
-    // trunk layers 1 .. depth-1: per accumulator half  [bias16 + W_hi K 0..127] [W_lo K 0..127] [W_hi K 128..255] [W_lo K 128..255]
+    // trunk layers 1 .. depth-1
+    static const int order[8][2] = {{0, 0}, {0, 1}, {1, 0}, {0, 2}, {0, 3}, {1, 1}, {1, 2}, {1, 3}};
     for (int l = 1; l < depth; ++l)
-        for (int h = 0; h < 2; ++h)
-            for (int k0 = 0; k0 < H; k0 += 128) {
-                if (k0 == 0)
-                    add(l, 128, 128 * h, 0, {{0, -1, 16}, {1, 0, 128}},
-                        {seg(2, 1, 0, 0, OVER), seg(0, 8, 0, 2, 0), seg(1, 8, 0, 2, SMALL | OVER)}, 0, h == 0 ? 1 : 0, h);
-                else
-                    add(l, 128, 128 * h, 0, {{1, k0, 128}}, {seg(0, 8, k0 / 8, 0, 0), seg(1, 8, k0 / 8, 0, SMALL)}, 0, h == 0 ? 2 : 0, h);
-                add(l, 128, 128 * h, 0, {{2, k0, 128}}, {seg(0, 8, k0 / 8, 0, SMALL)},
-                    (k0 == 128 ? 1 << h : 0) | ((h == 1 && k0 == 0) ? 4 : 0), 0, h);
-            }
-    // heads: [W_hi K 0..127 | W_lo K 0..127] [W_hi K 128..255 | W_lo K 128..255]; biases are added in the epilogue in fp32
+        for (int i = 0; i < 8; ++i) {
+            const int h = order[i][0], kq = order[i][1];
+            int wait = 0, commit = 0;
+            if (h == 0) wait |= kWaitA << kq;              // first reader of operand quarter kq
+            if (kq == 0) wait |= kWaitFree << h;           // first MMAs into accumulator half h
+            if (kq == 3) commit |= kCommitD << h;          // half h complete
+            if (h == 1 && kq < 2) commit |= kCommitKa << kq;   // last reader of operand quarter kq (kq = 0, 1)
+            add(l, 128, 128 * h, 0, kq == 0, 64 * kq, 64, kq == 0, false, commit, wait, h);
+        }
+    // heads: two K = 128 blocks [W_hi | W_lo]; biases are added in the epilogue in fp32
     for (int k0 = 0; k0 < H; k0 += 128) {
-        const int ov = k0 == 0 ? OVER : 0;
-        add(depth, NOp, 0, 0, {{1, k0, 128}, {2, k0, 128}},
-            {seg(0, 8, k0 / 8, 0, ov), seg(1, 8, k0 / 8, 0, SMALL | ov), seg(0, 8, k0 / 8, 16, SMALL)}, k0 == 0 ? 0 : 3, k0 == 0 ? 1 : 2, 0);
+        const bool first = k0 == 0;
+        add(depth, NOp, 0, 0, false, k0, 128, first, first, first ? 0 : kCommitD * 3,
+            (first ? kWaitA * 3 | kWaitFree : kWaitA * 12 | (kWaitFree << 1)), 0);
     }
     sc.image_bytes = goff;
     return sc;
@@ -822,12 +900,42 @@ int launch_logprob_tc3x(const ScoreArgs& a, cudaStream_t stream) {
         FRL_CUDA(cudaGetLastError());
         p.x0s = static_cast<const uint8_t*>(nm->ws_x0s);
     }
+    auto q_launch = [&](const Params& q, size_t smem) {
+        return q.x0_in_a ? launch_tc3x<true>(q, smem, grid, n0->cfg.device, stream)
+                         : launch_tc3x<false>(q, smem, grid, n0->cfg.device, stream);
+    };
     auto run = [&](const Params& q) {
-        int rc = q.x0_in_a ? launch_tc3x<true>(q, smem_bytes, grid, n0->cfg.device, stream)
-                           : launch_tc3x<false>(q, smem_bytes, grid, n0->cfg.device, stream);
+        int rc = q_launch(q, smem_bytes);
         if (rc == FRL_OK && q.x0_in_a && cap == cudaStreamCaptureStatusNone) FRL_CUDA(cudaEventRecord(n0->x0s_event, stream));
         return rc;
     };
+    if (const char* tp = getenv("FRL_TC_TRACE")) {
+        // timing experiment: stamp the roles of cluster 0's leader CTA during one Euler step and dump them (synchronises!)
+        if (smem_bytes + 4 * kTraceCap * 8 > (size_t)max_smem) {
+            set_error("FRL_TC_TRACE: no shared memory left for the stamps with this net");
+            return FRL_ERR_UNSUPPORTED;
+        }
+        unsigned long long* d = nullptr;
+        FRL_CUDA(cudaMalloc(&d, 4 * kTraceCap * sizeof(unsigned long long)));
+        FRL_CUDA(cudaMemset(d, 0, 4 * kTraceCap * sizeof(unsigned long long)));
+        p.trace = d;
+        p.trace_step = getenv("FRL_TC_TRACE_STEP") ? atoi(getenv("FRL_TC_TRACE_STEP")) : std::min(10, p.n_steps - 1);
+        p.off_trace = (uint32_t)smem_bytes;
+        p.basis = -1;
+        int rc = q_launch(p, smem_bytes + 4 * kTraceCap * 8);
+        if (rc != FRL_OK) return rc;
+        FRL_CUDA(cudaDeviceSynchronize());
+        std::vector<unsigned long long> h(4 * kTraceCap);
+        FRL_CUDA(cudaMemcpy(h.data(), d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        cudaFree(d);
+        if (FILE* f = fopen(tp, "w")) {
+            for (int r = 0; r < 4; ++r)
+                for (int i = 0; i < kTraceCap && h[(size_t)r * kTraceCap + i]; ++i)
+                    fprintf(f, "%d %llx %llu\n", r, h[(size_t)r * kTraceCap + i] >> 32, h[(size_t)r * kTraceCap + i] & 0xFFFFFFFFull);
+            fclose(f);
+        }
+        return FRL_OK;
+    }
     if (a.probe_mode == FRL_PROBE_EXACT) {
         for (int i = 0; i < p.a_dim; ++i) {
             p.basis = i;

@@ -519,7 +519,7 @@ class FlowMatchingEstimation(BaseIRLAlgo):
         parser.add_argument('--animation-type', type=str, default='gif')
         parser.add_argument('--animation-fps', type=int, default=20)
         # B200-only knobs (not in the reference)
-        parser.add_argument('--flowril-precision', type=str, default=None, choices=[None, 'fp32', 'fp16', 'bf16'])
+        parser.add_argument('--flowril-precision', type=str, default=None, choices=[None, 'fp16x3', 'fp32', 'fp16', 'bf16'])
         parser.add_argument('--flowril-batched-scoring', type=str2bool, default=True)
 
     def load_resume(self, checkpointer):

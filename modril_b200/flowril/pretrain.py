@@ -31,12 +31,15 @@ CMAP = 'viridis'
 PLOT_KW = dict(density=1.2, linewidth=1, arrowstyle='-|>')
 ALPHA_BG = 0.85
 
-_DEFAULT_PRECISION = "fp32"
+# "fp16x3": fp32-grade products on the tensor cores (3-term fp16 operand split, csrc/logprob_tc3x.cu) -- the reference
+# computes in fp32 (pretrain.py:192-214), and this is the mode that meets the 1e-4 parity bar at tensor-core speed.
+_DEFAULT_PRECISION = "fp16x3"
 
 
 def set_default_precision(name: str):
-    """'fp32' (FFMA, 1e-4 parity), 'fp16' or 'bf16' (tcgen05 tensor cores) for log_prob calls that do not
-    pass ``precision=`` explicitly."""
+    """Arithmetic of log_prob / score calls that do not pass ``precision=``: 'fp16x3' (default: tcgen05 tensor cores, 3-term
+    fp16 split = fp32-grade, 1e-4 parity), 'fp32' (FFMA kernels, 1e-4 parity), 'fp16' or 'bf16' (single-pass tensor-core
+    modes: 2e-3 on default-init-scale / trained nets, looser on rough nets -- README 'Precision modes')."""
     global _DEFAULT_PRECISION
     if name not in _native.PRECISIONS:
         raise ValueError(f"unknown precision {name!r}; choose from {sorted(_native.PRECISIONS)}")

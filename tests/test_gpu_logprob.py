@@ -1,8 +1,9 @@
 """GPU parity of the fused log-density integrator / velocity field / reward (through the C ABI).
 
-Bars: FP32 mode 1e-4 * max(1,|ref|) per sample against (i) the committed outputs of the reference code and
-(ii) the float64 oracle; tensor-core modes 2e-3.  A small fraction of samples may sit on a ReLU kink (see
-gpu_common.assert_close)."""
+Bars: the parity modes (fp32 FFMA kernels; fp16x3 = 3-term fp16 split on the tensor cores, the default) 1e-4 *
+max(1,|ref|) per sample against (i) the committed outputs of the reference code and (ii) the float64 oracle; the
+single-pass 16-bit tensor-core modes 2e-3 per sample on default-init-scale and trained nets (see TC_MODES below for what
+they do NOT meet).  A ReLU-kink row is excused only where stated (gpu_common.assert_close)."""
 import glob
 import os
 
@@ -17,33 +18,42 @@ from tests.gpu_common import assert_close, build_model, dev, spec_of
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-MODES = [("fp32", 1e-4, 0.011)]
-# Single-pass 16-bit tensor-core modes.  The north_star bar for them is 2e-3 per sample; it is asserted on nets at the
-# scale of the reference's default init (gain 1) -- and reported by bench.py on CFM-trained nets.  On the gain-2
-# "stress" nets used by most goldens every rounding error is amplified through the ReLU kinks ('numerics':
-# CPU emulation of fp16/bf16 operand rounding gives the same distribution), so there the tests pin the measured
-# error distribution instead: median and a cap.  The 1e-4 parity path is the fp32 mode.
-TC_MODES = {"fp16": dict(smooth=(2e-3, 0.02), stress_median=1.5e-3, stress_cap=0.1),
-            "bf16": dict(smooth=(2e-3, 0.02), stress_median=6e-3, stress_cap=0.25)}
+# Parity modes (bar 1e-4 per sample): "fp32" = FFMA kernels, "fp16x3" = the 3-term fp16 split on the tensor cores (the
+# module default).  A golden has 96 rows; ONE row per output may sit on a ReLU kink (a pre-activation within rounding
+# error of 0 flips a mask between two correct implementations: the reference's own fp32 result differs from the float64
+# oracle on 3 of ~8000 golden rows by 3e-4 .. 6e-4).  0.011 = 1 / 96 rounded up; the rate over ALL goldens is pinned
+# separately in test_parity_modes_kink_rate_over_all_goldens.
+MODES = [("fp32", 1e-4, 0.011), ("fp16x3", 1e-4, 0.011)]
+# Single-pass 16-bit tensor-core modes: north_star's bar is 2e-3 per sample.  It is asserted per sample -- no outlier
+# allowance except rows on which the FP32 kernel itself misses 1e-4 (a kink in fp32 too), cap 5e-3 -- on nets at the scale
+# of the reference's default init (the logprob_s* goldens, gain 1) and on CFM-trained nets (bench.py `parity`).  On the
+# gain-2 stress goldens operand rounding (2^-11 fp16, 2^-8 bf16) flips ReLU masks on a large share of the rows and the
+# single-pass modes DO NOT meet 2e-3 (fp16: 4-13 % of rows over, bf16: about half; README 'Precision modes'): there the
+# tests only check that the kernels run deterministically and stay in the distribution measured in DESIGN.md section 5 --
+# a regression guard, not a parity claim.  Parity on those nets is what the fp16x3 mode is for.
+TC_MODES = {"fp16": dict(stress_median=1.5e-3, stress_cap=0.1), "bf16": dict(stress_median=6e-3, stress_cap=0.25)}
 
 
 def _modes():
     return MODES
 
 
-def _check_tc(got, ref, mode, gain, what):
+def _check_tc(got, ref, fp32_got, mode, gain, what):
     from tests.gpu_common import rel_err
-    cfg = TC_MODES[mode]
+    err = rel_err(got, ref)
     if gain <= 1.0:
-        assert_close(got, ref, cfg["smooth"][0], f"{mode} {what}", cfg["smooth"][1], kink_cap=2e-2)
+        excused = rel_err(fp32_got, ref) > 1e-4          # the row is a kink for the FP32 kernel as well
+        bad = (err > 2e-3) & ~excused
+        assert not bad.any(), f"{mode} {what}: {int(bad.sum())}/{bad.size} rows over 2e-3 (max {err.max():.2e})"
+        assert err.max() <= 5e-3, f"{mode} {what}: max {err.max():.2e}"
     else:
-        err = rel_err(got, ref)
-        assert np.median(err) <= cfg["stress_median"], f"{mode} {what}: median {np.median(err):.2e}"
-        assert err.max() <= cfg["stress_cap"], f"{mode} {what}: max {err.max():.2e}"
+        cfg = TC_MODES[mode]
+        assert np.isfinite(got).all()
+        assert np.median(err) <= cfg["stress_median"], f"{mode} {what}: median {np.median(err):.2e} (regression guard)"
+        assert err.max() <= cfg["stress_cap"], f"{mode} {what}: max {err.max():.2e} (regression guard)"
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "logprob_*.npz"))), ids=os.path.basename)
-def test_logprob_vs_reference_goldens(path):
+def _golden_case(path):
     g = np.load(path)
     spec = spec_of(g["meta"])
     n_steps, B, seed = (int(x) for x in g["meta"][5:8])
@@ -51,44 +61,85 @@ def test_logprob_vs_reference_goldens(path):
     s, a = synth.states_actions(seed, B, spec.s_dim, spec.a_dim)
     probe = synth.rademacher(seed + 1, (B, spec.a_dim))
     probe_steps = synth.rademacher(seed + 2, (n_steps, B, spec.a_dim))
+    return g, spec, n_steps, B, seed, gain, s, a, probe, probe_steps
+
+
+def _caller(m, spec, st, at, role, n_steps, mode):
+    if spec.n_heads == 2:
+        return lambda **kw: m.log_prob(st, at, role, n_steps=n_steps, precision=mode, **kw)
+    return lambda **kw: m.log_prob(torch.cat([st, at], dim=-1), n_steps=n_steps, precision=mode, **kw)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "logprob_*.npz"))), ids=os.path.basename)
+def test_logprob_vs_reference_goldens(path):
+    g, spec, n_steps, B, seed, gain, s, a, probe, probe_steps = _golden_case(path)
     st, at, pt, pst = dev(s), dev(a), dev(probe), dev(probe_steps)
+    fp32_out = {}
     for mode, tol, kink in _modes():
         outs = {}
         for ri, role in enumerate(("expert", "agent")):
             flat = cf.make_params(spec, seed + (10 * ri if spec.n_heads == 1 else 0), gain)
             m = build_model(spec, flat)
-            if spec.n_heads == 2:
-                call = lambda **kw: m.log_prob(st, at, role, n_steps=n_steps, precision=mode, **kw)
-            else:
-                call = lambda **kw: m.log_prob(torch.cat([st, at], dim=-1), n_steps=n_steps, precision=mode, **kw)
+            call = _caller(m, spec, st, at, role, n_steps, mode)
             got = call(probe=pt).cpu().numpy()
             assert_close(got, g[f"logp_{role}"], tol, f"{mode} {role} shared probe", kink)
             outs[role] = got
-            got = call(probe=pst).cpu().numpy()
-            assert_close(got, g[f"logp_{role}_stepprobe"], tol, f"{mode} {role} per-step probe", kink)
+            got_s = call(probe=pst).cpu().numpy()
+            assert_close(got_s, g[f"logp_{role}_stepprobe"], tol, f"{mode} {role} per-step probe", kink)
+            got_x = None
             if f"logp_{role}_exact" in g:
-                got = call(exact=True).cpu().numpy()
-                assert_close(got, g[f"logp_{role}_exact"], 2 * tol, f"{mode} {role} exact trace", 2 * kink)
+                got_x = call(exact=True).cpu().numpy()
+                assert_close(got_x, g[f"logp_{role}_exact"], 2 * tol, f"{mode} {role} exact trace", 2 * kink)
+            if mode == "fp32":
+                fp32_out[role] = (got, got_s, got_x)
+            assert np.array_equal(got, call(probe=pt).cpu().numpy()), f"{mode} must be deterministic"
         if spec.n_heads == 2:  # fused two-role launch == two single-role launches, bit for bit
             le, la, rw = m.score(st, at, n_steps=n_steps, probe=pt, precision=mode)
             assert np.array_equal(le.cpu().numpy(), outs["expert"])
             assert np.array_equal(la.cpu().numpy(), outs["agent"])
             assert np.array_equal(rw.cpu().numpy(), outs["expert"] - outs["agent"])
-    # ---- tensor-core (tcgen05) modes ----
+    # ---- single-pass 16-bit tensor-core modes ----
     for mode in TC_MODES:
         for ri, role in enumerate(("expert", "agent")):
             flat = cf.make_params(spec, seed + (10 * ri if spec.n_heads == 1 else 0), gain)
             m = build_model(spec, flat)
-            if spec.n_heads == 2:
-                call = lambda **kw: m.log_prob(st, at, role, n_steps=n_steps, precision=mode, **kw)
-            else:
-                call = lambda **kw: m.log_prob(torch.cat([st, at], dim=-1), n_steps=n_steps, precision=mode, **kw)
-            _check_tc(call(probe=pt).cpu().numpy(), g[f"logp_{role}"], mode, gain, f"{role} shared probe")
-            _check_tc(call(probe=pst).cpu().numpy(), g[f"logp_{role}_stepprobe"], mode, gain, f"{role} per-step probe")
+            call = _caller(m, spec, st, at, role, n_steps, mode)
+            f32 = fp32_out[role]
+            _check_tc(call(probe=pt).cpu().numpy(), g[f"logp_{role}"], f32[0], mode, gain, f"{role} shared probe")
+            _check_tc(call(probe=pst).cpu().numpy(), g[f"logp_{role}_stepprobe"], f32[1], mode, gain, f"{role} per-step probe")
             if f"logp_{role}_exact" in g:
-                _check_tc(call(exact=True).cpu().numpy(), g[f"logp_{role}_exact"], mode, gain, f"{role} exact trace")
+                _check_tc(call(exact=True).cpu().numpy(), g[f"logp_{role}_exact"], f32[2], mode, gain, f"{role} exact trace")
             again = call(probe=pt).cpu().numpy()
             assert np.array_equal(again, call(probe=pt).cpu().numpy()), "tensor-core path must be deterministic"
+
+
+def test_parity_modes_kink_rate_over_all_goldens():
+    """The share of golden rows (all nets, roles, shared + per-step probes) outside the 1e-4 bar, per parity mode, next to
+    the same figure for the float64 oracle (i.e. how often the REFERENCE's own fp32 arithmetic lands on a kink).  Bars are
+    the measured rates with head-room (B200, round 2, 11520 rows: oracle 0.035 % = 4 rows, fp32 kernel 0.017 % = 2 rows,
+    fp16x3 0.061 % = 7 rows; worst row 5.8e-4 / 8.8e-4 / 3.1e-4); every row stays under 2e-3."""
+    from tests.gpu_common import rel_err
+    over = {"oracle": 0, "fp32": 0, "fp16x3": 0}
+    worst = dict(over)
+    rows = 0
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "logprob_*.npz"))):
+        g, spec, n_steps, B, seed, gain, s, a, probe, probe_steps = _golden_case(path)
+        st, at, pt, pst = dev(s), dev(a), dev(probe), dev(probe_steps)
+        for ri, role in enumerate(("expert", "agent")):
+            flat = cf.make_params(spec, seed + (10 * ri if spec.n_heads == 1 else 0), gain)
+            m = build_model(spec, flat)
+            for key, pr_np, pr_dev in ((f"logp_{role}", probe, pt), (f"logp_{role}_stepprobe", probe_steps, pst)):
+                rows += B
+                errs = {"oracle": rel_err(cf.log_prob(spec, flat, s, a, role, pr_np, n_steps), g[key])}
+                for mode in ("fp32", "fp16x3"):
+                    errs[mode] = rel_err(_caller(m, spec, st, at, role, n_steps, mode)(probe=pr_dev).cpu().numpy(), g[key])
+                for k, e in errs.items():
+                    over[k] += int((e > 1e-4).sum())
+                    worst[k] = max(worst[k], float(e.max()))
+    rates = {k: v / rows for k, v in over.items()}
+    print(f"kink rates over {rows} golden rows: {rates}; worst: {worst}")
+    assert rates["fp32"] <= 1e-3 and rates["fp16x3"] <= 1.5e-3, (rates, worst)
+    assert max(worst.values()) <= 2e-3, worst
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "vfield_*.npz"))), ids=os.path.basename)
@@ -114,8 +165,8 @@ def test_vfield_vs_reference_goldens(path):
 @pytest.mark.parametrize("mode", ["fp16", "bf16"])
 @pytest.mark.parametrize("B", [1, 127, 128, 129, 1000, 20000])
 def test_tc_ragged_batches_smooth_net_meets_2e3(B, mode):
-    """Tile edges of the tensor-core kernel (128-row tiles, 148 persistent CTAs) at the 2e-3 bar, on a net at the
-    reference's default-init scale."""
+    """Tile edges of the tensor-core kernel (64-sample tiles, CTA pairs) at the 2e-3 bar -- every sample, no outlier
+    allowance -- on a net at the reference's default-init scale."""
     spec = cf.NetSpec(17, 6, 256, 4, 2)
     flat = cf.make_params(spec, 78, 1.0)
     m = build_model(spec, flat)
@@ -125,9 +176,9 @@ def test_tc_ragged_batches_smooth_net_meets_2e3(B, mode):
     n = min(B, 512)
     for role, got in (("expert", le), ("agent", la)):
         ref = cf.log_prob(spec, flat, s[-n:], a[-n:], role, probe[-n:], 16)
-        assert_close(got[-n:].cpu().numpy(), ref, 2e-3, f"{mode} B={B} {role}", max(0.02, 1.5 / n), kink_cap=2e-2)
+        assert_close(got[-n:].cpu().numpy(), ref, 2e-3, f"{mode} B={B} {role}", 0.0, kink_cap=2e-3)   # every sample
     fe, fa, _ = m.score(dev(s), dev(a), n_steps=16, probe=dev(probe), precision="fp32")
-    assert_close(le.cpu().numpy(), fe.cpu().numpy(), 2e-3, f"{mode} vs fp32 kernel", 0.02, kink_cap=2e-2)
+    assert_close(le.cpu().numpy(), fe.cpu().numpy(), 2e-3, f"{mode} vs fp32 kernel", 0.0, kink_cap=2e-3)
 
 
 @pytest.mark.parametrize("B", [1, 31, 32, 33, 127, 129, 1000])
@@ -197,7 +248,7 @@ def test_score_host_matches_device():
     B, n = 3000, 12
     s, a = synth.states_actions(41, B, 17, 6)
     probe = synth.rademacher(42, (B, 6))
-    le, la, rw = m.score(dev(s), dev(a), n_steps=n, probe=dev(probe), reward_type="smooth")
+    le, la, rw = m.score(dev(s), dev(a), n_steps=n, probe=dev(probe), reward_type="smooth", precision="fp32")
     h = m.net.native()
     outs = [np.empty(B, np.float32) for _ in range(3)]
     ptr = lambda x: C.c_void_p(x.ctypes.data)
@@ -209,7 +260,7 @@ def test_score_host_matches_device():
     assert np.array_equal(outs[2], rw.cpu().numpy())
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16", "fp16x3"])
 @pytest.mark.parametrize("per_step", [False, True])
 def test_score_host_pinned_and_pageable_buffers(precision, per_step):
     """Host entry point with pinned and with pageable buffers: bit-identical to the device-resident path, for shared
@@ -256,35 +307,15 @@ def test_full_size_properties():
     assert torch.isfinite(rw).all()
 
 
-@pytest.mark.parametrize("task", ["maze", "hopper", "sine", "pick"])
-def test_experimental_n256_integrator_matches_default_kernel(task, monkeypatch):
-    """The experimental 64-sample-tile / N = 256 tcgen05 integrator (FRL_TC_V2=1, csrc/logprob_tc2.cu) computes the same
-    fp16 arithmetic as the default 128-sample kernel up to fp32 bias rounding (it adds trunk biases in the epilogue
-    instead of folding a 3-term split into the MMA): agreement far inside the fp16 mode's own 2e-3 bar, ragged B."""
-    sd, ad = synth.TASK_DIMS[task]
-    spec = cf.NetSpec(sd, ad, 256, 4, 2)
-    m = build_model(spec, cf.make_params(spec, 21, 1.0))
-    B = 1000
-    s, a = synth.states_actions(31, B, sd, ad)
-    probe = synth.rademacher(32, (B, ad))
-    ref = m.score(dev(s), dev(a), n_steps=20, probe=dev(probe), precision="fp16")
-    monkeypatch.setenv("FRL_TC_V2", "1")
-    got = m.score(dev(s), dev(a), n_steps=20, probe=dev(probe), precision="fp16")
-    monkeypatch.delenv("FRL_TC_V2")
-    f32 = m.score(dev(s), dev(a), n_steps=20, probe=dev(probe), precision="fp32")
-    for g, r, f in zip(got, ref, f32):
-        assert_close(g.cpu().numpy(), f.cpu().numpy(), 2e-3, f"{task} v2 vs fp32", kink_frac=0.02)
-        d = (g - r).abs() / r.abs().clamp_min(1.0)
-        assert float(d.median()) <= 2e-4, float(d.median())
-
-
-@pytest.mark.parametrize("task,B,n_steps", [("hopper", 262144, 32), ("halfcheetah", 262144, 32), ("ant", 1048576, 32),
-                                            ("hand", 1048576, 32)])
-def test_baseline_full_sizes_tensor_core_properties(task, B, n_steps):
-    """BASELINE.json configs at their full sizes on the tensor-core path (fp16): size-independent properties --
-    determinism, row-permutation equivariance (tiles regroup, results must not move), the exported host entry point
-    equals the device path, reward == logp_E - logp_A, and a slice agrees with the FP32 kernels / the float64 oracle
-    within the mode's 2e-3 bar."""
+@pytest.mark.parametrize("task,B,n_steps,mode", [("hopper", 262144, 32, "fp16"), ("halfcheetah", 262144, 32, "fp16"),
+                                                 ("ant", 1048576, 32, "fp16"), ("hand", 1048576, 32, "fp16"),
+                                                 ("hopper", 262144, 32, "fp16x3"), ("hand", 262144, 32, "fp16x3"),
+                                                 ("ant", 1048576, 32, "fp16x3")])
+def test_baseline_full_sizes_tensor_core_properties(task, B, n_steps, mode):
+    """BASELINE.json configs at their full sizes on the tensor-core paths (fp16: one pass; fp16x3: the fp32-grade split):
+    size-independent properties -- determinism, row-permutation equivariance (tiles regroup, results must not move),
+    reward == logp_E - logp_A, and a slice agrees with the FP32 kernels / the float64 oracle within the mode's bar
+    (2e-3 per sample for fp16 on these default-init-scale nets, 1e-4 for fp16x3)."""
     sd, ad = synth.TASK_DIMS[task]
     spec = cf.NetSpec(sd, ad, 256, 4, 2)
     flat = cf.make_params(spec, 60, 1.0)
@@ -292,21 +323,22 @@ def test_baseline_full_sizes_tensor_core_properties(task, B, n_steps):
     s, a = synth.states_actions(61, B, sd, ad)
     probe = synth.rademacher(62, (B, ad))
     st, at, pt = dev(s), dev(a), dev(probe)
-    le, la, rw = m.score(st, at, n_steps=n_steps, probe=pt, precision="fp16")
-    le2, la2, rw2 = m.score(st, at, n_steps=n_steps, probe=pt, precision="fp16")
+    bar = 2e-3 if mode == "fp16" else 1e-4
+    le, la, rw = m.score(st, at, n_steps=n_steps, probe=pt, precision=mode)
+    le2, la2, rw2 = m.score(st, at, n_steps=n_steps, probe=pt, precision=mode)
     assert torch.equal(le, le2) and torch.equal(la, la2) and torch.equal(rw, rw2)
     assert torch.isfinite(le).all() and torch.isfinite(la).all()
     assert torch.equal(rw, le - la)
     perm = torch.randperm(B, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
-    lep, lap, _ = m.score(st[perm], at[perm], n_steps=n_steps, probe=pt[perm], precision="fp16")
+    lep, lap, _ = m.score(st[perm], at[perm], n_steps=n_steps, probe=pt[perm], precision=mode)
     assert torch.equal(lep, le[perm]) and torch.equal(lap, la[perm])
     lo = B // 3
     sl = slice(lo, lo + 2048)
     f32 = m.score(st[sl], at[sl], n_steps=n_steps, probe=pt[sl], precision="fp32")
-    assert_close(le[sl].cpu().numpy(), f32[0].cpu().numpy(), 2e-3, f"{task} fp16 vs fp32 kernels", kink_frac=0.01)
+    assert_close(le[sl].cpu().numpy(), f32[0].cpu().numpy(), bar, f"{task} {mode} vs fp32 kernels", kink_frac=0.0, kink_cap=bar)
     ref = cf.log_prob(spec, flat, s[lo:lo + 256], a[lo:lo + 256], "agent", probe[lo:lo + 256], n_steps)
-    assert_close(la[lo:lo + 256].cpu().numpy(), ref, 2e-3, f"{task} fp16 vs oracle", kink_frac=0.02)
-    assert_close(f32[1][:256].cpu().numpy(), ref, 1e-4, f"{task} fp32 vs oracle", kink_frac=0.02)
+    assert_close(la[lo:lo + 256].cpu().numpy(), ref, bar, f"{task} {mode} vs oracle", kink_frac=0.0, kink_cap=bar)
+    assert_close(f32[1][:256].cpu().numpy(), ref, 1e-4, f"{task} fp32 vs oracle", kink_frac=0.0, kink_cap=1e-4)
 
 
 @pytest.mark.parametrize("task,B,n_steps,mode", [("maze", 4097, 20, "fp16"), ("hopper", 20000, 32, "bf16"),
