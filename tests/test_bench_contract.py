@@ -8,10 +8,29 @@ import pytest
 import bench
 
 
+def _fake_arm(monkeypatch, kind="port"):
+    class Arm:
+        s_dim, a_dim = 6, 2
+        desc = "stand-in"
+
+        def __init__(self, task, flat=None):
+            self.kind = kind
+
+        def score_rate(self, B, n_steps, threads, reps=1):
+            return 2000.0, B / 2000.0
+
+        def train_rate(self, B, threads, steps=3):
+            return 50000.0, 2 * B / 50000.0
+
+    monkeypatch.setattr(bench, "CpuArm", Arm)
+
+
 def test_reference_arm_line_has_the_contract_keys(monkeypatch, capsys):
-    monkeypatch.setattr(bench, "cpu_port_rate", lambda task, B, n_steps, flat, threads, reps=1: (2000.0, B / 2000.0))
+    _fake_arm(monkeypatch)
     monkeypatch.delenv("RANK", raising=False)
-    args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="reference", workload="maze", precision="fp16", batch=0, no_cpu=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    args = argparse.Namespace(gpus=1, steps=2, warmup=1, impl="reference", workload="maze", precision="fp16x3", batch=0,
+                              no_cpu=False, metric="score")
     bench.run_reference(args)
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "scored_samples_per_sec" and line["unit"] == "samples/s"
@@ -21,11 +40,61 @@ def test_reference_arm_line_has_the_contract_keys(monkeypatch, capsys):
     assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("maze: s 6 + a 2, 20-step ODE log-density")
     assert line["config"]["batch_per_gpu"] == 65536 and line["gpu_launches"] == 0
+    # both arms build `config` with the same function: identical dictionaries for the same workload and GPU count
+    assert line["config"] == bench.config_dict("maze", 6, 2, 20, 65536, 1)
+
+
+def test_reference_arm_train_metric(monkeypatch, capsys):
+    _fake_arm(monkeypatch, "reference")
+    monkeypatch.delenv("RANK", raising=False)
+    args = argparse.Namespace(gpus=1, steps=1, warmup=0, impl="reference", workload="maze", precision="fp16x3", batch=0,
+                              no_cpu=False, metric="train")
+    bench.run_reference(args)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["metric"] == "cfm_train_samples_per_sec" and line["cpu_baseline"]["kind"] == "reference"
+    assert line["value"] == pytest.approx(50000.0, rel=1e-6)
+
+
+def test_cpu_arm_times_the_staged_reference_when_present():
+    """oracle/_ref (built by oracle/build_ref.py from the reference checkout) makes the CPU arm the reference's own classes;
+    its log-density agrees with the oracle on the arm's own weights."""
+    import numpy as np
+    import torch
+
+    from oracle import build_ref
+    from oracle import closed_form as cf
+
+    if build_ref.build() is None:
+        pytest.skip("no reference checkout and no staged oracle/_ref")
+    arm = bench.CpuArm("maze", cf.make_params(cf.NetSpec(6, 2, 256, 4, 2), 3, 1.0))
+    assert arm.kind == "reference"
+    rate, dt = arm.score_rate(64, 4, 1)
+    assert rate > 0 and dt > 0
+    _, _, s, a, probe = bench.make_inputs("maze", 64, 4)
+    ref = cf.log_prob(arm.spec, arm.flat, s, a, "expert", np.ones_like(probe), 4, exact=True)   # a_dim = 2: probe-free check
+    with torch.enable_grad():
+        runs = []
+        for i in range(2):   # exact trace from two basis-probe runs of the reference (as oracle/gen_golden.py does)
+            e = torch.zeros(64, 2)
+            e[:, i] = 1.0
+            arm.P._rademacher, saved = (lambda *a_, **k: e.clone()), arm.P._rademacher
+            try:
+                runs.append(arm.model.log_prob(torch.from_numpy(s), torch.from_numpy(a), "expert", n_steps=4).detach().numpy())
+            finally:
+                arm.P._rademacher = saved
+        z = torch.zeros(64, 2)
+        arm.P._rademacher, saved = (lambda *a_, **k: z.clone()), arm.P._rademacher
+        try:
+            zero = arm.model.log_prob(torch.from_numpy(s), torch.from_numpy(a), "expert", n_steps=4).detach().numpy()
+        finally:
+            arm.P._rademacher = saved
+    got = runs[0].astype(np.float64) + runs[1] - zero
+    assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
 
 
 def test_reference_arm_other_ranks_print_nothing(monkeypatch, capsys):
     monkeypatch.setenv("RANK", "3")
-    bench.run_reference(argparse.Namespace(gpus=8, steps=1, warmup=0, workload="maze"))
+    bench.run_reference(argparse.Namespace(gpus=8, steps=1, warmup=0, workload="maze", metric="score", batch=0))
     assert capsys.readouterr().out == ""
 
 
