@@ -578,11 +578,19 @@ def run_ours(args):
     g = torch.Generator(device="cpu").manual_seed(9 + rank)
     tt_ = (torch.rand(2, Bt, 1, generator=g) * (1 - 2e-3) + 1e-3).to(device)
     zz = torch.randn(2, Bt, a_dim, generator=g).to(device)
-    grp = (dist.group.WORLD, world) if world > 1 else None
-    # N = 1: one CUDA graph per update (all kernels of both roles + clip + Adam + weight re-pack).  N > 1: two graphs
-    # (gradients | clip + Adam + re-pack) with the NCCL all-reduce launched between them, outside of any graph.
-    # FRL_BENCH_NO_GRAPH=1 launches everything from Python instead.
+    # One CUDA graph per update (all kernels of both roles + [gradient all-reduce] + clip + Adam + weight re-pack).  N > 1:
+    # the all-reduce is the device-side one-shot exchange over NVLink peer memory (modril_b200.dist.PeerAllReduce,
+    # csrc/comm.cu: two kernels inside the graph).  FRL_BENCH_NCCL=1 takes the NCCL route instead: two graphs (gradients |
+    # clip + Adam + re-pack) with ncclAllReduce launched between them from Python.  FRL_BENCH_NO_GRAPH=1 launches
+    # everything from Python.
     use_graph = os.environ.get("FRL_BENCH_NO_GRAPH", "0") != "1"
+    use_nccl = os.environ.get("FRL_BENCH_NCCL", "0") == "1"
+    peer_comm = None
+    if world > 1 and not use_nccl:
+        from modril_b200.dist import PeerAllReduce
+
+        peer_comm = PeerAllReduce(model.net.flat_params().numel() + 64, device=device)
+    grp = ((peer_comm if peer_comm is not None else dist.group.WORLD), world) if world > 1 else None
     opt = FusedAdam([model.net], lr=1e-4, capturable=use_graph)
 
     def tstep(prec_t, phase=None, losses=None, batch=None):
@@ -596,8 +604,9 @@ def run_ours(args):
         for _ in range(3):
             tstep(prec_t)
         run = lambda: tstep(prec_t)
-        if use_graph and world == 1:
+        if use_graph and (world == 1 or peer_comm is not None):
             torch.cuda.synchronize(device)
+            barrier()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 tstep(prec_t)
@@ -730,7 +739,7 @@ def run_ours(args):
         "metric": "cfm_train_samples_per_sec", "value": train_rate, "unit": "samples/s", "ms_per_step": train_ms["fp16"],
         "rows_per_step_per_gpu": 2 * Bt, "dtype": "fp16 operands / fp32 accumulate (tcgen05); fp32 clip + Adam",
         "step": "frl_cfm_loss_grad_pair (both roles stacked) + [all-reduce] + frl_clip_adam + weight re-pack"
-                + (("; replayed as one CUDA graph" if world == 1 else
+                + (("; replayed as one CUDA graph" if (world == 1 or peer_comm is not None) else
                     "; two CUDA graphs with the NCCL all-reduce between them") if use_graph else ""),
         "fp32_ffma_samples_per_sec": train_rates["fp32"],
         "algorithmic_tflops": train_rate * 3 * f_fwd_train / 1e12,
@@ -743,7 +752,10 @@ def run_ours(args):
                 "algorithmic_bytes_per_row": (s_dim + 2 * a_dim + 1) * 4},
         "e2e": {"value": train_e2e, "unit": "samples/s", "h2d_bytes_per_step": train_h2d, "d2h_bytes_per_step": 8 * world,
                 "api": "train_step on device copies refreshed from pinned host memory every step; the two losses read back"},
-        "collective": "NCCL all-reduce of the flat grad" if world > 1 else "none",
+        "collective": "none" if world == 1 else (
+            "device-side one-shot all-reduce of the flat fp32 gradient over NVLink peer memory (csrc/comm.cu), inside the graph"
+            if peer_comm is not None else "NCCL all-reduce of the flat grad, launched from Python between two graphs"),
+        "collective_timeouts": peer_comm.timeouts() if peer_comm is not None else None,
         "cpu_baseline": cpu_train}
 
     line = {

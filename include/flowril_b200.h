@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FRL_ABI_VERSION 6
+#define FRL_ABI_VERSION 7
 #define FRL_MAX_STEPS 256
 #define FRL_MAX_DEPTH 8
 
@@ -215,6 +215,44 @@ int frl_clip_adam(const frl_adam_segment* segs, int n_segs, long long step, doub
  * whole update (frl_cfm_loss_grad_p ... frl_clip_adam_dev, frl_net_set_params) replays correctly step after step. */
 int frl_clip_adam_dev(const frl_adam_segment* segs, int n_segs, long long* step_dev, double lr, double beta1,
                       double beta2, double eps, double max_norm, float* norm_out_dev, int device, void* stream);
+
+/* ---- reward hook helpers ---------------------------------------------------------------------------------------------
+ * frl_reward: the reward transform of _compute_flow_reward (flowril.py:191-208) on two log-density vectors that were
+ * produced by separate launches (2fs: each net integrates with its own probes): reward = transform(logp_e - logp_a),
+ * reward_type 0 raw, 1 norm, 2 exp, 3 clip, 4 smooth (same codes as frl_score).
+ * frl_rademacher_calls: the Hutchinson probes FlowMatching._hutch_div (pretrain.py:88-92) would draw from torch's CUDA
+ * generator over a whole rollout -- n_outer rollout steps x n_nets nets x n_steps Euler steps, each a
+ * randint_like([numel], 0, 2) * 2 - 1 -- replayed bit for bit in one launch from the generator's (seed, offset):
+ * out<net>_dev [n_steps][n_outer][numel].  The caller advances the generator offset by 4 * n_outer * n_nets * n_steps. */
+int frl_reward(const float* logp_e_dev, const float* logp_a_dev, float* reward_dev, long long B, int reward_type, int device,
+               void* stream);
+int frl_rademacher_calls(unsigned long long seed, unsigned long long offset, int n_outer, int n_nets, int n_steps, int numel,
+                         float* out0_dev, float* out1_dev, int device, void* stream);
+
+/* ---- data-parallel gradient all-reduce over NVLink peer memory ------------------------------------------
+ * Replaces what torch.distributed / DistributedDataParallel would do around the reference's update
+ * (modril/flowril/flowril.py:311-330: backward -> [gradient all-reduce] -> clip_grad_norm_ -> Adam.step) by two ordinary
+ * kernels on the caller's stream: graph-capturable, no host synchronisation, no collective library launch between the
+ * gradient kernels and clip + Adam.  One process per GPU: every rank creates a comm (an exchange buffer of
+ * max_floats fp32 values, double-buffered), passes its 64-byte handle to all ranks by any host channel
+ * (torch.distributed.all_gather_object) and connects with the [world][64] array of all handles.  Within ONE process
+ * driving several GPUs, frl_comm_connect_local takes the comm objects instead.
+ *   frl_comm_allreduce: bufs[k][0..ns[k]) (k < n_bufs <= 8, fp32, device) <- sum over ranks, in place.  The sum runs in
+ *   rank order on every rank, so all ranks hold bit-identical results (the same clip + Adam then keeps the weights
+ *   identical without a broadcast).  Every rank must issue the same sequence of calls with the same sizes.
+ *   frl_comm_publish / frl_comm_reduce: the two halves (publish my vector; wait for all peers and sum), for callers that
+ *   place independent work between them.
+ *   frl_comm_timeouts: how many waits gave up because a peer never arrived within ~10 s (0 in a healthy job; synchronises). */
+typedef struct frl_comm frl_comm;
+int frl_comm_create(int rank, int world, int device, long long max_floats, frl_comm** out);
+int frl_comm_handle(const frl_comm* comm, void* out_handle_64_bytes);
+int frl_comm_connect(frl_comm* comm, const void* all_handles_world_x_64_bytes);
+int frl_comm_connect_local(frl_comm* comm, frl_comm* const* all_comms);
+int frl_comm_publish(frl_comm* comm, float* const* bufs_dev, const long long* ns, int n_bufs, void* stream);
+int frl_comm_reduce(frl_comm* comm, float* const* bufs_dev, const long long* ns, int n_bufs, void* stream);
+int frl_comm_allreduce(frl_comm* comm, float* const* bufs_dev, const long long* ns, int n_bufs, void* stream);
+long long frl_comm_timeouts(frl_comm* comm);
+int frl_comm_destroy(frl_comm* comm);
 
 /* ---- BCF flow-matching policy (behaviour cloning with a flow-matching actor; scope row f3) ------------------------
  * VectorNetwork (deps/rl-toolkit/rlf/rl/model.py:391-432): three embeddings + a two-layer velocity head,

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libflowril_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 PREC_FP32, PREC_BF16, PREC_FP16X3, PREC_FP16 = 0, 1, 2, 3
 PREC_BF16X3 = PREC_FP16X3   # former (reserved) name
 HAS_TC = True  # tensor-core (tcgen05) log-density kernels are built in
@@ -29,6 +29,8 @@ EXPORTS = (
     "frl_vnet_sample", "frl_bcf_loss_grad", "frl_compute_returns", "frl_normalise_advantages", "frl_cfm_loss_grad_pair",
     "frl_acnet_create", "frl_acnet_destroy", "frl_acnet_num_params", "frl_acnet_set_params", "frl_acnet_forward",
     "frl_acnet_act", "frl_acnet_evaluate", "frl_ppo_loss_grad", "frl_column_moments", "frl_norm_vec",
+    "frl_comm_create", "frl_comm_handle", "frl_comm_connect", "frl_comm_connect_local", "frl_comm_publish",
+    "frl_comm_reduce", "frl_comm_allreduce", "frl_comm_timeouts", "frl_comm_destroy", "frl_reward", "frl_rademacher_calls",
 )
 
 
@@ -113,9 +115,21 @@ def lib():
     L.frl_column_moments.argtypes = [vp, ll, i32, vp, vp, i32, vp]
     L.frl_norm_vec.argtypes = [vp, vp, vp, ll, i32, vp, i32, vp]
     L.frl_ppo_loss_grad.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ll, ll, f32, f32, f32, f32, i32, vp, vp, vp]
+    L.frl_reward.argtypes = [vp, vp, vp, ll, i32, i32, vp]
+    L.frl_rademacher_calls.argtypes = [C.c_ulonglong, C.c_ulonglong, i32, i32, i32, i32, vp, vp, i32, vp]
+    L.frl_comm_create.argtypes = [i32, i32, i32, ll, C.POINTER(vp)]
+    L.frl_comm_handle.argtypes = [vp, vp]
+    L.frl_comm_connect.argtypes = [vp, vp]
+    L.frl_comm_connect_local.argtypes = [vp, C.POINTER(vp)]
+    for name in ("frl_comm_publish", "frl_comm_reduce", "frl_comm_allreduce"):
+        getattr(L, name).argtypes = [vp, C.POINTER(vp), C.POINTER(ll), i32, vp]
+    L.frl_comm_timeouts.argtypes = [vp]
+    L.frl_comm_timeouts.restype = ll
+    L.frl_comm_destroy.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("frl_last_error", "frl_net_num_params", "frl_vnet_num_params", "frl_acnet_num_params"):
+        if name not in ("frl_last_error", "frl_net_num_params", "frl_vnet_num_params", "frl_acnet_num_params",
+                        "frl_comm_timeouts"):
             fn.restype = i32
     if L.frl_abi_version() != ABI_VERSION:
         raise NativeError(f"ABI mismatch: library {L.frl_abi_version()} != binding {ABI_VERSION}")

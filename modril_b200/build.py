@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libflowril_b200.so")
-SOURCES = ["net.cu", "logprob_f32.cu", "logprob_tc.cu", "logprob_tc3.cu", "logprob_tc3x.cu", "train_f32.cu", "train_tc.cu", "adam.cu", "returns.cu", "bcf_f32.cu", "gae.cu", "ppo_f32.cu", "dataset.cu", "api.cu"]
+SOURCES = ["net.cu", "logprob_f32.cu", "logprob_tc.cu", "logprob_tc3.cu", "logprob_tc3x.cu", "train_f32.cu", "train_tc.cu", "adam.cu", "comm.cu", "probe.cu", "returns.cu", "bcf_f32.cu", "gae.cu", "ppo_f32.cu", "dataset.cu", "api.cu"]
 
 
 def _nvcc() -> str:

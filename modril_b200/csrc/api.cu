@@ -57,6 +57,10 @@ int dispatch_score(const ScoreArgs& args, int precision, cudaStream_t st) {
         return FRL_ERR_INVALID;
     }
     if (rc != FRL_OK) return rc;
+    for (int r = 0; r < args.n_roles; ++r) {
+        rc = note_reader(args.net[r], st);
+        if (rc != FRL_OK) return rc;
+    }
     if (args.out_reward && args.reward_type >= 0)
         rc = launch_reward(args.out_logp[0], args.out_logp[1], args.out_reward, args.B, args.reward_type, st);
     return rc;
@@ -91,7 +95,8 @@ extern "C" int frl_vfield(const frl_net* net, const float* s, const float* a, co
     FRL_REQUIRE(precision == FRL_PREC_FP32, "frl_vfield: only FRL_PREC_FP32 is implemented");
     if (B <= 0) return FRL_OK;
     FRL_CUDA(cudaSetDevice(net->cfg.device));
-    return launch_vfield_f32(net, s, a, t, out0, out1, B, (cudaStream_t)stream);
+    rc = launch_vfield_f32(net, s, a, t, out0, out1, B, (cudaStream_t)stream);
+    return rc != FRL_OK ? rc : note_reader(net, (cudaStream_t)stream);
 }
 
 extern "C" int frl_logprob(const frl_net* net, float role_sign, const float* s, const float* a, const float* probe,
@@ -227,8 +232,9 @@ extern "C" int frl_cfm_loss_grad(frl_net* net, float role_sign, const float* s, 
     FRL_REQUIRE(s && a0 && t && noise, "null input");
     FRL_REQUIRE(B > 0, "empty batch");
     FRL_CUDA(cudaSetDevice(net->cfg.device));
-    return cfm_loss_grad_f32(net, role_sign >= 0.f ? 1.f : -1.f, s, a0, t, noise, B, mean_divisor, grad_scale,
-                             accumulate, loss, grad, (cudaStream_t)stream);
+    rc = cfm_loss_grad_f32(net, role_sign >= 0.f ? 1.f : -1.f, s, a0, t, noise, B, mean_divisor, grad_scale,
+                           accumulate, loss, grad, (cudaStream_t)stream);
+    return rc != FRL_OK ? rc : note_reader(net, (cudaStream_t)stream);
 }
 
 extern "C" int frl_cfm_loss_grad_p(frl_net* net, float role_sign, const float* s, const float* a0, const float* t,
@@ -250,7 +256,8 @@ extern "C" int frl_cfm_loss_grad_p(frl_net* net, float role_sign, const float* s
     }
     FRL_CUDA(cudaSetDevice(net->cfg.device));
     const CfmTerm term{role_sign >= 0.f ? 1.f : -1.f, s, a0, t, noise, B, mean_divisor, grad_scale, loss};
-    return cfm_loss_grad_tc(net, &term, 1, accumulate, grad, (cudaStream_t)stream);
+    rc = cfm_loss_grad_tc(net, &term, 1, accumulate, grad, (cudaStream_t)stream);
+    return rc != FRL_OK ? rc : note_reader(net, (cudaStream_t)stream);
 }
 
 extern "C" int frl_cfm_loss_grad_pair(frl_net* net, const frl_cfm_term* terms, int accumulate, float* grad, int precision,
@@ -297,7 +304,8 @@ extern "C" int frl_cfm_loss_grad_pair(frl_net* net, const frl_cfm_term* terms, i
                         terms[i].B, terms[i].mean_divisor, terms[i].grad_scale, terms[i].loss_dev};
     }
     FRL_CUDA(cudaSetDevice(net->cfg.device));
-    return cfm_loss_grad_tc(net, t2, 2, accumulate, grad, (cudaStream_t)stream);
+    rc = cfm_loss_grad_tc(net, t2, 2, accumulate, grad, (cudaStream_t)stream);
+    return rc != FRL_OK ? rc : note_reader(net, (cudaStream_t)stream);
 }
 
 extern "C" int frl_reg_loss_grad(frl_net* net, const float* s, const float* a, const float* t, const float* probe,
@@ -310,8 +318,9 @@ extern "C" int frl_reg_loss_grad(frl_net* net, const float* s, const float* a, c
     FRL_REQUIRE(N > 0, "empty batch");
     FRL_REQUIRE(which >= 1 && which <= 3, "which: bit 0 = anti, bit 1 = stable");
     FRL_CUDA(cudaSetDevice(net->cfg.device));
-    return reg_loss_grad_f32(net, s, a, t, probe, N, mean_divisor, which, loss_anti, loss_stable, grad_anti,
-                             grad_stable, (cudaStream_t)stream);
+    rc = reg_loss_grad_f32(net, s, a, t, probe, N, mean_divisor, which, loss_anti, loss_stable, grad_anti,
+                           grad_stable, (cudaStream_t)stream);
+    return rc != FRL_OK ? rc : note_reader(net, (cudaStream_t)stream);
 }
 
 extern "C" int frl_grad_axpy(float* y, const float* x, long long n, float alpha, const float* num, const float* den,

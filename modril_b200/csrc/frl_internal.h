@@ -67,6 +67,13 @@ struct frl_net {
     unsigned long long packed[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t pack_event[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t pack_stream[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // Streams on which kernels that READ the packed layouts were launched since the layouts were built, with an event
+    // recorded after the latest such launch (frl::note_reader): a re-pack after frl_net_set_params rewrites the layouts in
+    // place, so its stream first waits for every reader on another stream.
+    static constexpr int kMaxReaders = 4;
+    cudaEvent_t reader_event[kMaxReaders] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t reader_stream[kMaxReaders] = {nullptr, nullptr, nullptr, nullptr};
+    bool reader_used[kMaxReaders] = {false, false, false, false};
     // tensor-core training: fp16 weight images (train_tc.cu) and workspace
     void* pack_train = nullptr;
     void* ws_tc = nullptr;
@@ -91,6 +98,7 @@ namespace frl {
 // net.cu: weight layouts, built lazily
 enum PackKind { PACK_F32 = 0, PACK_TC1 = 1, PACK_TC2 = 2, PACK_TC3 = 3, PACK_TRAIN = 4, PACK_TC3X = 5, PACK_KINDS = 6 };
 int ensure_pack(const frl_net* net, int kind, cudaStream_t stream);
+int note_reader(const frl_net* net, cudaStream_t stream);   // call after launching kernels that read the net's packed layouts
 int pack_f32(frl_net* net, const float* params_dev, cudaStream_t stream);
 
 // logprob_f32.cu

@@ -134,6 +134,8 @@ extern "C" int frl_net_destroy(frl_net* net) {
     if (net->ws_tc) cudaFree(net->ws_tc);
     if (net->ws_x0s) cudaFree(net->ws_x0s);
     for (void* r : net->retired) cudaFree(r);
+    for (int i = 0; i < frl_net::kMaxReaders; ++i)
+        if (net->reader_event[i]) cudaEventDestroy(net->reader_event[i]);
     if (net->x0s_event) cudaEventDestroy(net->x0s_event);
     frl_host_stage_free(net);
     delete net;
@@ -180,17 +182,53 @@ int pack_f32(frl_net* net, const float* params_dev, cudaStream_t st) {
     return FRL_OK;
 }
 
+static int is_capturing(cudaStream_t st, bool* out) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    FRL_CUDA(cudaStreamIsCapturing(st, &cap));
+    *out = cap != cudaStreamCaptureStatusNone;
+    return FRL_OK;
+}
+
+// Record that kernels reading this net's packed layouts have just been launched on `st`.  (Inside a stream capture the
+// graph's own edges order a later re-pack captured in the same graph; events cannot cross the capture boundary.)
+int note_reader(const frl_net* cnet, cudaStream_t st) {
+    frl_net* net = const_cast<frl_net*>(cnet);
+    bool cap = false;
+    int rc = is_capturing(st, &cap);
+    if (rc != FRL_OK || cap) return rc;
+    int slot = -1;
+    for (int i = 0; i < frl_net::kMaxReaders; ++i)
+        if (net->reader_used[i] && net->reader_stream[i] == st) slot = i;
+    if (slot < 0)
+        for (int i = 0; i < frl_net::kMaxReaders && slot < 0; ++i)
+            if (!net->reader_used[i]) slot = i;
+    if (slot < 0) {   // more distinct reader streams than slots: retire the oldest one by waiting for it here
+        slot = 0;
+        FRL_CUDA(cudaEventSynchronize(net->reader_event[0]));
+    }
+    if (!net->reader_event[slot]) FRL_CUDA(cudaEventCreateWithFlags(&net->reader_event[slot], cudaEventDisableTiming));
+    FRL_CUDA(cudaEventRecord(net->reader_event[slot], st));
+    net->reader_stream[slot] = st;
+    net->reader_used[slot] = true;
+    return FRL_OK;
+}
+
 // Build the layout `kind` from the current master weights if it is stale.  Runs on the consumer's stream, so the pack
 // is ordered before the kernel that needs it; a different stream that finds the layout up to date waits on the event
-// recorded after the pack.
+// recorded after the pack, and the pack itself first waits for the readers of the old image on other streams.
 int ensure_pack(const frl_net* cnet, int kind, cudaStream_t st) {
     frl_net* net = const_cast<frl_net*>(cnet);
+    bool cap = false;
+    int rc = is_capturing(st, &cap);
+    if (rc != FRL_OK) return rc;
     if (net->packed[kind] == net->version) {
-        if (net->pack_stream[kind] != st && net->pack_event[kind])
+        if (!cap && net->pack_stream[kind] != st && net->pack_event[kind])
             FRL_CUDA(cudaStreamWaitEvent(st, net->pack_event[kind], 0));
         return FRL_OK;
     }
-    int rc = FRL_OK;
+    if (!cap)
+        for (int i = 0; i < frl_net::kMaxReaders; ++i)
+            if (net->reader_used[i] && net->reader_stream[i] != st) FRL_CUDA(cudaStreamWaitEvent(st, net->reader_event[i], 0));
     switch (kind) {
         case PACK_F32: rc = pack_f32(net, net->params_dev, st); break;
         case PACK_TC1: rc = tc_pack(net, net->params_dev, st); break;
@@ -201,8 +239,10 @@ int ensure_pack(const frl_net* cnet, int kind, cudaStream_t st) {
         default: set_error("bad pack kind"); return FRL_ERR_INVALID;
     }
     if (rc != FRL_OK) return rc;
-    if (!net->pack_event[kind]) FRL_CUDA(cudaEventCreateWithFlags(&net->pack_event[kind], cudaEventDisableTiming));
-    FRL_CUDA(cudaEventRecord(net->pack_event[kind], st));
+    if (!cap) {   // an event recorded inside a capture could not be waited on from outside of it
+        if (!net->pack_event[kind]) FRL_CUDA(cudaEventCreateWithFlags(&net->pack_event[kind], cudaEventDisableTiming));
+        FRL_CUDA(cudaEventRecord(net->pack_event[kind], st));
+    }
     net->pack_stream[kind] = st;
     net->packed[kind] = net->version;
     return FRL_OK;

@@ -6,9 +6,13 @@ SURVEY.md section 8(e):
   * CFM training is data parallel -- every rank runs the fused gradient kernels on its shard with the GLOBAL batch
     as mean divisor, ONE all-reduce(SUM) of the flat fp32 gradient (< 1 MB: latency-bound on NVLink 5), then the
     same deterministic clip+Adam everywhere, so the weights stay bit-identical without a broadcast.
-The functions here are device-agnostic (the gloo tests run them on CPU tensors).
+The functions here are device-agnostic (the gloo tests run them on CPU tensors), except `PeerAllReduce`: the device-side
+one-shot all-reduce over NVLink peer memory (csrc/comm.cu) that replaces the NCCL call of the training step, so that a
+whole data-parallel update is ONE CUDA graph.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import torch
 import torch.distributed as dist
@@ -30,6 +34,109 @@ def allreduce_flat(grads, losses, group=None):
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
         for l, v in zip(losses, packed):
             l.copy_(v.reshape(l.shape))
+
+
+class PeerAllReduce:
+    """Sum-all-reduce of small fp32 device vectors (the flat gradient, < 1 MB) through peer-mapped exchange buffers:
+    two ordinary kernels on the current stream (``frl_comm_allreduce``), graph-capturable, bit-identical result on every
+    rank.  ``torch.distributed`` is used ONCE, at construction, to pass the 64-byte memory handles around (host side,
+    any backend).  Pass an instance as ``world[0]`` of ``train_step`` in place of the process group.
+
+    Single-process use (tests, one process driving several GPUs): ``PeerAllReduce.local_group(devices, max_floats)``.
+    """
+
+    def __init__(self, max_floats: int, device=None, group=None, _connect=True):
+        from . import _native
+
+        self._native = _native
+        self.group = group
+        if _connect:
+            self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("PeerAllReduce needs a CUDA device (there is no CPU path)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.max_floats = int(max_floats)
+        self._h = None
+        if _connect:
+            self._create()
+            self._connect_group()
+
+    def _create(self):
+        L = self._native.lib()
+        h = C.c_void_p()
+        self._native.check(L.frl_comm_create(self.rank, self.world, self.device.index, self.max_floats, C.byref(h)),
+                           "frl_comm_create")
+        self._h = h
+
+    def _connect_group(self):
+        L = self._native.lib()
+        mine = (C.c_ubyte * 64)()
+        self._native.check(L.frl_comm_handle(self._h, mine), "frl_comm_handle")
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(mine), group=self.group)
+        else:
+            handles[0] = bytes(mine)
+        blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        self._native.check(L.frl_comm_connect(self._h, blob), "frl_comm_connect")
+        if self.world > 1:
+            dist.barrier(group=self.group)   # every rank has mapped every buffer before the first flag is written
+
+    @classmethod
+    def local_group(cls, devices, max_floats: int):
+        """One comm per device of THIS process, connected to each other (no torch.distributed needed)."""
+        comms = []
+        for r, d in enumerate(devices):
+            c = cls(max_floats, device=d, _connect=False)
+            c.rank, c.world = r, len(devices)
+            c._create()
+            comms.append(c)
+        arr = (C.c_void_p * len(comms))(*[c._h for c in comms])
+        for c in comms:
+            c._native.check(c._native.lib().frl_comm_connect_local(c._h, arr), "frl_comm_connect_local")
+        return comms
+
+    def _call(self, fn, name, tensors):
+        ts = [t for t in tensors]
+        for t in ts:
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device:
+                raise ValueError(f"{name}: contiguous float32 tensors on {self.device} expected")
+        ptrs = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        ns = (C.c_longlong * len(ts))(*[t.numel() for t in ts])
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._native.check(fn(self._h, ptrs, ns, len(ts), C.c_void_p(stream)), name)
+
+    def allreduce(self, tensors):
+        """In place: every tensor <- its sum over the ranks (up to 8 tensors per call, all ranks the same sizes)."""
+        self._call(self._native.lib().frl_comm_allreduce, "frl_comm_allreduce", tensors)
+
+    def publish(self, tensors):
+        self._call(self._native.lib().frl_comm_publish, "frl_comm_publish", tensors)
+
+    def reduce(self, tensors):
+        self._call(self._native.lib().frl_comm_reduce, "frl_comm_reduce", tensors)
+
+    def timeouts(self) -> int:
+        return int(self._native.lib().frl_comm_timeouts(self._h))
+
+    def close(self):
+        if self._h is not None:
+            self._native.lib().frl_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def allreduce_peer(comm: PeerAllReduce, grads, losses):
+    """`allreduce_flat` through a PeerAllReduce: gradients and loss scalars in ONE publish + reduce pair."""
+    comm.allreduce(list(grads) + [l.reshape(-1) for l in losses])
 
 
 def gather_rows(local: torch.Tensor, n_rows: int, group=None):

@@ -55,23 +55,6 @@ try:  # the real plugin API, when rl-toolkit and its simulators are installed
 except Exception:  # pragma: no cover - exercised in this repo's tests
     HAVE_RLF = False
 
-    class RunningMeanStd(object):
-        """float32 running moments (rlf/baselines/common/running_mean_std.py:3-35)."""
-
-        def __init__(self, epsilon=1e-4, shape=()):
-            self.mean = np.zeros(shape, "float32")
-            self.var = np.ones(shape, "float32")
-            self.count = epsilon
-
-        def update(self, x):
-            bm = np.mean(x, axis=0, dtype="float32")
-            bv = np.var(x, axis=0, dtype="float32")
-            n = x.shape[0]
-            delta = bm - self.mean
-            tot = self.count + n
-            m2 = self.var * self.count + bv * n + np.square(delta, dtype="float32") * self.count * n / tot
-            self.mean, self.var, self.count = self.mean + delta * n / tot, m2 / tot, tot
-
     class _Utils:
         @staticmethod
         def get_obs_shape(space):
@@ -128,12 +111,42 @@ except Exception:  # pragma: no cover - exercised in this repo's tests
             return x
 
         def update(self, storage, gradient_clip=False, t=1):
-            for step in range(self.args.num_steps):
+            """base_irl.py:37-72: wipe the environment rewards, train the reward model (the hook is first tried with the
+            caller's extra arguments, then without), relabel every rollout step through ``_get_reward``, and keep the
+            per-process running sums that become ``culm_irl_<key>`` (mean over the last ``log_smooth_len`` finished
+            episodes) in the log."""
+            T, N = self.args.num_steps, self.args.num_processes
+            if not hasattr(self, "ep_log_vals"):
+                from collections import deque
+
+                self.ep_log_vals = defaultdict(lambda: deque(maxlen=getattr(self.args, "log_smooth_len", 10)))
+                self.culm_log_vals = defaultdict(lambda: [0.0] * N)
+            for step in range(T):
                 storage.rewards[step] = 0
-            log_vals = self._update_reward_func(storage)
-            for step in range(self.args.num_steps):
-                rewards, _ = self._get_reward(step, storage, {})
+            try:
+                log_vals = self._update_reward_func(storage, gradient_clip, t)
+            except TypeError:
+                log_vals = self._update_reward_func(storage)
+            per_step = defaultdict(list)
+            for step in range(T):
+                rewards, ep_vals = self._get_reward(step, storage, {})
                 storage.rewards[step] = rewards
+                for k, v in dict(ep_vals, reward=rewards).items():
+                    per_step[k].append(v.detach().reshape(-1))
+            # the logging of base_irl.py:57-67 from ONE device->host copy per key (the reference calls .item() per
+            # process and step, and compares the mask on the device each time)
+            ended = (storage.masks[:T].reshape(T, -1) == 0.0).cpu().numpy()
+            host = {k: torch.stack(v).cpu().numpy() for k, v in per_step.items()}
+            for step in range(T):
+                for i in range(N):
+                    for k, vals in host.items():
+                        self.culm_log_vals[k][i] += float(vals[step, i])
+                    if ended[step, i]:
+                        for k in host:
+                            self.ep_log_vals[k].append(self.culm_log_vals[k][i])
+                            self.culm_log_vals[k][i] = 0.0
+            for k, vals in self.ep_log_vals.items():
+                log_vals[f"culm_irl_{k}"] = np.mean(vals)
             return log_vals
 
         def save(self, checkpointer):
@@ -146,6 +159,15 @@ except Exception:  # pragma: no cover - exercised in this repo's tests
     PPO = None
 
 
+def _canonical_device(device):
+    """torch.device('cuda') -> torch.device('cuda', current index): tensors report an indexed device, and the native
+    layer compares devices exactly."""
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
 class DeviceRunningMeanStd(object):
     """The float32 running moments of rlf's RunningMeanStd (running_mean_std.py:3-35) kept ON THE DEVICE and advanced
     by ``frl_normalise_rewards`` together with the discounted-return recursion (reference flowril.py:221-228), so the
@@ -153,7 +175,7 @@ class DeviceRunningMeanStd(object):
     (one sync) with the shapes the numpy object has after its first update (``var[0]`` works)."""
 
     def __init__(self, device, epsilon=1e-4):
-        self.device = torch.device(device)
+        self.device = _canonical_device(device)
         self.mean_var = torch.tensor([0.0, 1.0], device=self.device)
         self.count_t = torch.tensor([epsilon], dtype=torch.float64, device=self.device)
 
@@ -198,6 +220,7 @@ class FlowMatchingEstimation(BaseIRLAlgo):
         self.step = 0
         self._rollout_cache = None
         self._norm_cache = None
+        self._serve = None
 
     # ---- construction (reference flowril.py:34-121) -------------------------------------------------------------
     def _create_flow_net(self):
@@ -248,6 +271,7 @@ class FlowMatchingEstimation(BaseIRLAlgo):
                 self.opt = FusedAdam([self.flow_net_e.net, self.flow_net_a.net], lr=lr)
 
     def init(self, policy, args):
+        args.device = _canonical_device(args.device)
         super().init(policy, args)
         self.policy = policy
         self.args = args
@@ -273,11 +297,9 @@ class FlowMatchingEstimation(BaseIRLAlgo):
         return settings
 
     def _norm_expert_state(self, state, obsfilt):
-        if not self.args.flowril_state_norm:
-            return state
-        state = state.cpu().numpy()
-        if obsfilt is not None:
-            state = obsfilt(state, update=False)
+        if not self.args.flowril_state_norm or obsfilt is None:
+            return state   # (without a filter the reference's numpy round trip, flowril.py:157-161, is the identity)
+        state = obsfilt(state.cpu().numpy(), update=False)
         return torch.tensor(state).to(self.args.device)
 
     def _trans_agent_state(self, state, other_state=None):
@@ -315,27 +337,72 @@ class FlowMatchingEstimation(BaseIRLAlgo):
         return le, la, None
 
     def _reward_from(self, le, la, rw):
-        if rw is not None:
-            return rw.unsqueeze(-1)
-        r = (le - la).unsqueeze(-1)
-        s = torch.sigmoid(r)
-        eps = 1e-20
-        rt = self.args.reward_type
-        if rt == "norm":
-            return (s + eps).log() - (1 - s + eps).log()
-        if rt == "exp":
-            e = torch.exp(r)
-            return -e / (1 + e)
-        if rt == "raw":
-            return r
-        if rt == "clip":
-            return torch.clamp(r, min=-20.0, max=20.0)
-        if rt == "smooth":
-            return -torch.log1p(torch.exp(-r))
-        raise ValueError(f"Unrecognized reward type {rt}")
+        if rw is None:   # 2fs: the two nets were integrated by separate launches
+            rw = self._reward_native(le, la, self.args.reward_type)
+        return rw.unsqueeze(-1)
 
     def _batched(self):
-        return getattr(self.args, "flowril_batched_scoring", True) and self.args.option == "scrf"
+        return getattr(self.args, "flowril_batched_scoring", True)
+
+    # ---- 2fs: the per-step probes of a whole rollout in the reference's RNG order, one launch ------------------------
+    _replay_ok = {}   # device index -> bool: the Philox replay reproduced real randint_like calls on this device
+
+    def _draw_loop(self, T, N, n_steps):
+        """The reference's own sequence of draws (flowril.py:186-189 per rollout step: expert net's n_steps probes, then
+        the agent net's), T x 2 x n_steps small launches."""
+        like = torch.empty(N, self.action_dim, device=self.args.device)
+        pe = torch.empty(n_steps, T, N * self.action_dim, device=self.args.device)
+        pa = torch.empty_like(pe)
+        for t in range(T):
+            for buf in (pe, pa):
+                for k in range(n_steps):
+                    buf[k, t] = torch.randint_like(like, 0, 2).float().mul_(2).sub_(1).reshape(-1)
+        return pe, pa
+
+    def _draw_replay(self, T, N, n_steps):
+        from .. import _native
+        from .networks import _current_stream, _ptr
+
+        dev = self.args.device
+        gen = torch.cuda.default_generators[dev.index]
+        seed, offset = gen.initial_seed(), gen.get_offset()
+        numel = N * self.action_dim
+        pe = torch.empty(n_steps, T, numel, device=dev)
+        pa = torch.empty_like(pe)
+        _native.check(_native.lib().frl_rademacher_calls(seed, offset, T, 2, n_steps, numel, _ptr(pe), _ptr(pa), dev.index,
+                                                         _current_stream(dev)), "frl_rademacher_calls")
+        gen.set_offset(offset + 4 * T * 2 * n_steps)
+        return pe, pa
+
+    def _rollout_probes_2fs(self, T, N, n_steps=32):
+        """([n_steps, T*N, a], same) for the expert and the agent net: the values -- and the generator state afterwards --
+        the reference's T x 2 x n_steps ``randint_like`` calls would produce, from ONE launch (csrc/probe.cu).  The replay
+        is checked against real draws once per device and process; if torch's generator kernel ever changes, the loop of
+        real draws is used instead."""
+        dev = self.args.device
+        ok = FlowMatchingEstimation._replay_ok.get(dev.index)
+        if ok is None:
+            gen = torch.cuda.default_generators[dev.index]
+            state = gen.get_state()
+            want = self._draw_loop(2, N, 3)
+            end = gen.get_offset()
+            gen.set_state(state)
+            got = self._draw_replay(2, N, 3)
+            ok = gen.get_offset() == end and all(torch.equal(w, g) for w, g in zip(want, got))
+            gen.set_state(state)
+            FlowMatchingEstimation._replay_ok[dev.index] = ok
+        pe, pa = (self._draw_replay if ok else self._draw_loop)(T, N, n_steps)
+        shape = (n_steps, T * N, self.action_dim)
+        return pe.reshape(shape), pa.reshape(shape)
+
+    def _reward_native(self, le, la, reward_type):
+        from .. import _native
+        from .networks import _current_stream, _ptr
+
+        out = torch.empty_like(le)
+        _native.check(_native.lib().frl_reward(_ptr(le), _ptr(la), _ptr(out), le.numel(), _native.REWARD_TYPES[reward_type],
+                                               le.device.index, _current_stream(le.device)), "frl_reward")
+        return out
 
     def _compute_flow_reward(self, storage, step, add_info):
         if self.args.reward_type not in ("raw", "norm", "exp", "clip", "smooth"):
@@ -351,11 +418,21 @@ class FlowMatchingEstimation(BaseIRLAlgo):
                                    for t in range(T)])
             N = states.shape[1]
             ne, na = self._nets()
-            probe = self._probe(N).repeat(T, 1)  # the same [N, a] probe at every rollout step, like the reference
-            le, la, rw = score_pair(ne, na, states.reshape(T * N, -1), actions.reshape(T * N, -1), probe, n_steps=32,
-                                    reward_type=self.args.reward_type, precision=self.precision)
+            if self.args.option == "scrf":
+                probe = self._probe(N).repeat(T, 1)  # the same [N, a] probe at every rollout step, like the reference
+                le, la, rw = score_pair(ne, na, states.reshape(T * N, -1), actions.reshape(T * N, -1), probe, n_steps=32,
+                                        reward_type=self.args.reward_type, precision=self.precision)
+            else:
+                # 2fs: every net integrates with its own per-step probes (drawn in the reference's order), two launches
+                # over all T*N rows + the reward transform
+                pe, pa = self._rollout_probes_2fs(T, N)
+                x = torch.cat([states.reshape(T * N, -1), actions.reshape(T * N, -1)], dim=-1)
+                le = self.flow_net_e.log_prob(x, probe=pe, precision=self.precision)
+                la = self.flow_net_a.log_prob(x, probe=pa, precision=self.precision)
+                rw = self._reward_native(le, la, self.args.reward_type)
             self._rollout_cache = rw.reshape(T, N, 1)
             self._norm_cache = None
+            self._serve = None
         return self._rollout_cache[step]
 
     def _get_reward(self, step, storage, add_info):
@@ -364,6 +441,10 @@ class FlowMatchingEstimation(BaseIRLAlgo):
                 m.eval()
             reward = self._compute_flow_reward(storage, step, add_info)
             if not self.args.flowril_reward_norm:
+                if self._batched():
+                    if step == 0 or self._serve is None:
+                        self._serve = self._host_block(self._rollout_cache)
+                    return self._serve[step], {}
                 return reward, {}
             # discounted-return recursion + running moments + scaling (reference flowril.py:221-228) on the device
             if self._batched():
@@ -372,10 +453,21 @@ class FlowMatchingEstimation(BaseIRLAlgo):
                     masks = torch.stack([storage.masks[t].to(self.args.device) for t in range(T)])
                     self._norm_cache, self.returns = self.ret_rms.normalise(self._rollout_cache, masks,
                                                                             self.args.gamma, self.returns)
-                return self._norm_cache[step], {}
+                    self._serve = self._host_block(self._norm_cache)
+                return self._serve[step], {}
             out, self.returns = self.ret_rms.normalise(reward.unsqueeze(0), storage.masks[step].unsqueeze(0),
                                                        self.args.gamma, self.returns)
             return out[0], {}
+
+    def _host_block(self, block):
+        """Under rl-toolkit's own update loop (base_irl.py:57-67) every returned reward is read element by element with
+        ``.item()`` -- T x N device->host syncs per update if the rows live on the device.  ``--flowril-host-rewards``
+        (default: on when ``rlf`` drives the module) brings the whole [T, N, 1] block to the host ONCE; the per-step
+        rows handed out are then host tensors (``storage.rewards[step] = rewards`` copies them back, no sync)."""
+        host = getattr(self.args, "flowril_host_rewards", None)
+        if host is None:
+            host = HAVE_RLF
+        return block.cpu() if host else block
 
     def _compute_disc_val(self, state, action):
         state, action = state.to(self.args.device), action.to(self.args.device)
@@ -423,7 +515,7 @@ class FlowMatchingEstimation(BaseIRLAlgo):
             mode = lambda w: float(w)                       # fixed weights (flowril.py:266-270)
             reg["anti"] = mode(self._w_anti_init) if anti_on else None
             reg["stable"] = mode(self._w_stable_init) if stable_on else None
-        elif int(self.gradnorm.step_count) <= self.gradnorm.warmup_steps:
+        elif self.gradnorm.steps <= self.gradnorm.warmup_steps:   # host mirror: no sync
             warm = ("warmup", self.global_scale, self.eps)  # w = L_E / (L_reg + eps) * global_scale (flowril.py:272-284)
             reg["anti"] = warm if anti_on else None
             reg["stable"] = warm if stable_on else None
@@ -521,6 +613,7 @@ class FlowMatchingEstimation(BaseIRLAlgo):
         # B200-only knobs (not in the reference)
         parser.add_argument('--flowril-precision', type=str, default=None, choices=[None, 'fp16x3', 'fp32', 'fp16', 'bf16'])
         parser.add_argument('--flowril-batched-scoring', type=str2bool, default=True)
+        parser.add_argument('--flowril-host-rewards', type=str2bool, default=None)
 
     def load_resume(self, checkpointer):
         super().load_resume(checkpointer)

@@ -222,68 +222,87 @@ class ConditionalVNet(_FlatVNet):
 
 
 class GradNorm2D(nn.Module):
-    """GradNorm balancing of the two regulariser weights -- mirror of reference networks.py:52-138: same constructor
+    """GradNorm balancing of the two regulariser weights -- same contract as reference networks.py:52-138: constructor
     arguments, parameters (``log_beta``, ``log_gamma``), buffers (``step_count``, ``L0_anti``, ``L0_jpen``,
-    ``ema_g_anti``, ``ema_g_jpen``) and update rule, so its ``state_dict`` round-trips.
+    ``ema_g_anti``, ``ema_g_jpen``) and update rule, so its ``state_dict`` round-trips with the reference's.
 
-    One difference in mechanism: the reference's ``update`` obtains the two gradient norms with
+    Differences in mechanism: (1) the reference's ``update`` obtains the two gradient norms with
     ``torch.autograd.grad(loss, params)`` (networks.py:108-117); here the regulariser gradients come out of the fused
-    kernels (``frl_reg_loss_grad``), so ``update`` takes the two sums of per-tensor norms directly
-    (``g_anti=`` / ``g_jpen=``, see ``pretrain.tensor_grad_norm_sum``).
+    kernels (``frl_reg_loss_grad``), so ``update`` takes the two sums of per-tensor norms directly (``g_anti=`` /
+    ``g_jpen=``, see ``pretrain.tensor_grad_norm_sum``).  (2) The step counter has a host-side mirror (``steps``): the
+    branches on it (warm-up, update cadence) never read the device buffer, so they cost no device->host sync.
     """
+
+    _TERMS = (("anti", "beta"), ("jpen", "gamma"))   # (buffer suffix, weight name) of the two regularisers
 
     def __init__(self, beta_init=1e-4, gamma_init=1e-5, alpha=0.1, eps=1e-8, beta_min=1e-6, beta_max=1e1,
                  gamma_min=1e-8, gamma_max=1e-2, warmup_steps=100, update_freq=10, ema_decay=0.9, enable_beta=True,
                  enable_gamma=True):
         super().__init__()
-        self.alpha, self.eps = alpha, eps
-        self.beta_min, self.beta_max = beta_min, beta_max
-        self.gamma_min, self.gamma_max = gamma_min, gamma_max
-        self.warmup_steps = warmup_steps
-        self.update_freq = update_freq
-        self.ema_decay = ema_decay
-        self.enable_beta = enable_beta
-        self.enable_gamma = enable_gamma
-        self.log_beta = nn.Parameter(torch.log(torch.tensor(beta_init)))
-        self.log_gamma = nn.Parameter(torch.log(torch.tensor(gamma_init)))
+        self.alpha, self.eps, self.ema_decay = alpha, eps, ema_decay
+        self.warmup_steps, self.update_freq = warmup_steps, update_freq
+        self.beta_min, self.beta_max, self.gamma_min, self.gamma_max = beta_min, beta_max, gamma_min, gamma_max
+        self.enable_beta, self.enable_gamma = enable_beta, enable_gamma
+        for name, init in (("beta", beta_init), ("gamma", gamma_init)):
+            setattr(self, "log_" + name, nn.Parameter(torch.log(torch.tensor(init))))
         self.register_buffer("step_count", torch.tensor(0))
-        self.register_buffer("L0_anti", torch.tensor(0.))
-        self.register_buffer("L0_jpen", torch.tensor(0.))
-        self.register_buffer("ema_g_anti", torch.tensor(0.))
-        self.register_buffer("ema_g_jpen", torch.tensor(0.))
+        for buf in ("L0_anti", "L0_jpen", "ema_g_anti", "ema_g_jpen"):
+            self.register_buffer(buf, torch.tensor(0.))
+        self._steps = 0
+
+    @property
+    def steps(self) -> int:
+        """Host mirror of ``step_count`` (the number of ``forward`` calls so far)."""
+        return self._steps
+
+    def set_steps(self, n: int):
+        """Set the step counter (device buffer and host mirror) -- what advancing ``step_count`` externally means here."""
+        self._steps = int(n)
+        self.step_count.fill_(int(n))
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        key = prefix + "step_count"
+        if key in state_dict:
+            self._steps = int(state_dict[key])
+
+    def _enabled(self, weight):
+        return self.enable_beta if weight == "beta" else self.enable_gamma
 
     def forward(self, loss_anti, j_pen):
-        if self.step_count < self.warmup_steps:
-            self.L0_anti += loss_anti.detach()
-            self.L0_jpen += j_pen.detach()
-            if self.step_count == self.warmup_steps - 1:
-                self.L0_anti /= float(self.warmup_steps)
-                self.L0_jpen /= float(self.warmup_steps)
+        losses = {"anti": loss_anti, "jpen": j_pen}
+        n = self._steps
+        if n < self.warmup_steps:   # L0 = mean of the two losses over the first warmup_steps calls
+            for suffix, _ in self._TERMS:
+                ref = getattr(self, "L0_" + suffix)
+                ref += losses[suffix].detach()
+                if n + 1 == self.warmup_steps:
+                    ref /= float(self.warmup_steps)
+        self._steps = n + 1
         self.step_count += 1
-        beta = self.log_beta.exp() if self.enable_beta else torch.tensor(0.0, device=loss_anti.device)
-        gamma = self.log_gamma.exp() if self.enable_gamma else torch.tensor(0.0, device=j_pen.device)
-        return beta * loss_anti + gamma * j_pen, beta, gamma
+        w = {name: (getattr(self, "log_" + name).exp() if self._enabled(name)
+                    else torch.tensor(0.0, device=losses[suffix].device)) for suffix, name in self._TERMS}
+        return w["beta"] * loss_anti + w["gamma"] * j_pen, w["beta"], w["gamma"]
 
     @torch.no_grad()
     def update(self, loss_anti, j_pen, params=None, *, g_anti=0.0, g_jpen=0.0):
         import math
 
-        if self.step_count <= self.warmup_steps or self.step_count % self.update_freq != 0:
+        if self._steps <= self.warmup_steps or self._steps % self.update_freq != 0:
             return
-        g_anti = float(g_anti) if self.enable_beta else 0.0
-        g_jpen = float(g_jpen) if self.enable_gamma else 0.0
-        self.ema_g_anti = self.ema_decay * self.ema_g_anti + (1 - self.ema_decay) * g_anti
-        self.ema_g_jpen = self.ema_decay * self.ema_g_jpen + (1 - self.ema_decay) * g_jpen
-        g_anti, g_jpen = float(self.ema_g_anti), float(self.ema_g_jpen)
-        r_anti = (loss_anti.detach() / (self.L0_anti + self.eps)).item()
-        r_jpen = (j_pen.detach() / (self.L0_jpen + self.eps)).item()
-        r_bar = 0.5 * (r_anti + r_jpen) + self.eps
-        inv_mean_g = 0.5 * (g_anti + g_jpen) + self.eps
-        if self.enable_beta:
-            delta_b = self.alpha * (g_anti / inv_mean_g * (r_anti / r_bar) - 1)
-            self.log_beta.data += delta_b
-            self.log_beta.data.clamp_(math.log(self.beta_min), math.log(self.beta_max))
-        if self.enable_gamma:
-            delta_g = self.alpha * (g_jpen / inv_mean_g * (r_jpen / r_bar) - 1)
-            self.log_gamma.data += delta_g
-            self.log_gamma.data.clamp_(math.log(self.gamma_min), math.log(self.gamma_max))
+        losses = {"anti": loss_anti, "jpen": j_pen}
+        norms = {"anti": float(g_anti) if self.enable_beta else 0.0, "jpen": float(g_jpen) if self.enable_gamma else 0.0}
+        g, r = {}, {}
+        for suffix, _ in self._TERMS:   # smoothed gradient norms and loss ratios L / L0 of the two terms
+            ema = self.ema_decay * getattr(self, "ema_g_" + suffix) + (1 - self.ema_decay) * norms[suffix]
+            setattr(self, "ema_g_" + suffix, ema)
+            g[suffix] = float(ema)
+            r[suffix] = (losses[suffix].detach() / (getattr(self, "L0_" + suffix) + self.eps)).item()
+        r_mean = 0.5 * (r["anti"] + r["jpen"]) + self.eps
+        g_mean = 0.5 * (g["anti"] + g["jpen"]) + self.eps
+        for suffix, name in self._TERMS:
+            if not self._enabled(name):
+                continue
+            log_w = getattr(self, "log_" + name)
+            log_w.data += self.alpha * (g[suffix] / g_mean * (r[suffix] / r_mean) - 1)
+            log_w.data.clamp_(math.log(getattr(self, name + "_min")), math.log(getattr(self, name + "_max")))

@@ -520,7 +520,9 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
     terms: list of dicts {net, sign, s, a0, t, noise, rate}; several terms may share a net (scrf: expert + agent).
     world: optional (process_group, world_size[, global_rows]) for data-parallel training: each rank passes its shard,
            the mean divisor becomes the global batch (``global_rows`` per term when the shards are ragged, else
-           local rows * world_size) and the flat gradients are all-reduced (sum) before the clip.
+           local rows * world_size) and the flat gradients are all-reduced (sum) before the clip.  ``process_group`` may
+           be a ``modril_b200.dist.PeerAllReduce``: the all-reduce then runs as two kernels on the current stream over
+           NVLink peer memory and the whole update (phase=None) can be captured as ONE CUDA graph.
     reg:   optional dict for the scrf regularisers (reference flowril.py:255-290):
              net, s, a, t, probe      the mixed batch, its times and Rademacher probe
              anti / stable            how each term is weighted: None (off), a float (fixed weight,
@@ -549,11 +551,14 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
     grads = [net.flat_grad() for net in opt.nets]
     rout = reg.get("out") if reg is not None else None
     if phase in (None, "reduce") and world is not None and ws > 1:
-        from ..dist import allreduce_flat
+        from ..dist import PeerAllReduce, allreduce_flat, allreduce_peer
 
         extra_g = [] if rout is None else [rout[k] for k in ("grad_anti", "grad_stable") if k in rout]
         extra_l = [] if rout is None else [rout[k] for k in ("loss_anti", "loss_stable") if k in rout]
-        allreduce_flat(grads + extra_g, losses + extra_l, world[0])
+        if isinstance(world[0], PeerAllReduce):   # two kernels on this stream (graph-capturable), no NCCL launch
+            allreduce_peer(world[0], grads + extra_g, losses + extra_l)
+        else:
+            allreduce_flat(grads + extra_g, losses + extra_l, world[0])
     if phase == "reduce":
         return [l.reshape(()) for l in losses]
     if rout is not None:
@@ -572,6 +577,54 @@ def train_step(terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=Non
                 _axpy(target, g_reg, float(spec), gate=gate, coef_out=gate)
     opt.step_flat(grads, max_norm)
     return [l.reshape(()) for l in losses]
+
+
+class TrainStepGraph:
+    """One whole update -- ``train_step(terms, opt, ...)``: gradient kernels, [device-side all-reduce], clip, Adam, weight
+    re-pack -- captured ONCE as a CUDA graph and replayed per call.  The tensors inside ``terms`` / ``reg`` are the
+    graph's static inputs: copy each new batch into them (``copy_``) before calling.  Replays advance the weights through
+    raw pointers, which torch's version counters do not see, so every call marks the nets dirty: scoring launched afterwards
+    re-packs its own weight layout instead of silently using the one from before the update.
+
+    ``opt`` must be ``FusedAdam(..., capturable=True)`` (step count on the device).  Data parallel: pass
+    ``world=(PeerAllReduce, world_size[, global_rows])``; an NCCL process group cannot be captured (use ``train_step``'s
+    phases around the collective instead).  Construction runs one eager update to size the workspaces (allocation is
+    illegal during capture) and then restores weights and optimizer state, so it has no effect on training."""
+
+    def __init__(self, terms, opt: FusedAdam, max_norm: float = 1.0, world=None, reg=None, precision=None):
+        if opt._step_dev is None:
+            raise ValueError("TrainStepGraph needs FusedAdam(..., capturable=True)")
+        if world is not None and world[1] > 1:
+            from ..dist import PeerAllReduce
+
+            if not isinstance(world[0], PeerAllReduce):
+                raise ValueError("TrainStepGraph: a captured data-parallel update needs world[0] = PeerAllReduce")
+        self.opt, self.terms = opt, terms
+        dev = opt.nets[0].flat_params().device
+        saved = [(net.flat_params().clone(), m.clone(), v.clone()) for net, m, v in zip(opt.nets, opt._m, opt._v)]
+        step = opt._step_dev.clone()
+        run = lambda: train_step(terms, opt, max_norm, world=world, reg=reg, precision=precision)
+        run()
+        with torch.no_grad():
+            for net, m, v, (p0, m0, v0) in zip(opt.nets, opt._m, opt._v, saved):
+                net.flat_params().copy_(p0)
+                m.copy_(m0)
+                v.copy_(v0)
+                net.mark_dirty()
+            opt._step_dev.copy_(step)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = run()
+        with torch.no_grad():   # (capture does not execute, but the host-side dirty flags were touched)
+            for net in opt.nets:
+                net.mark_dirty()
+
+    def __call__(self):
+        self.graph.replay()
+        for net in self.opt.nets:
+            net.mark_dirty()
+        return self.losses
 
 
 def _train_step_grad(terms, opt, world, reg, precision):

@@ -34,7 +34,7 @@ def test_header_symbols_are_exported(lib):
 
 def test_abi_version_and_error_string(lib):
     from modril_b200 import _native
-    assert lib.frl_abi_version() == _native.ABI_VERSION == 6
+    assert lib.frl_abi_version() == _native.ABI_VERSION == 7
     assert isinstance(lib.frl_last_error(), bytes)
 
 

@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q, prec):
+def _worker(rank, world, port, q, prec, comm="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -49,10 +49,15 @@ def _worker(rank, world, port, q, prec):
         lo, hi = shard_rows(B, rank, world)
         m_dp, m_full = model(), model()
         o_dp, o_full = FusedAdam([m_dp.net], lr=1e-3), FusedAdam([m_full.net], lr=1e-3)
+        group = dist.group.WORLD
+        if comm == "peer":   # device-side all-reduce over NVLink peer memory instead of the NCCL call
+            from modril_b200.dist import PeerAllReduce
+
+            group = PeerAllReduce(m_dp.net.flat_params().numel() + 64, device=dev)
         for it in range(3):
             terms = lambda m, sl: [dict(net=m.net, sign=sg, s=to(s[sl]), a0=to(a[sl]), t=to(t[sl]), noise=to(z[sl]), rate=1.0)
                                    for sg, (t, z) in zip((1.0, -1.0), ts)]
-            l_dp = train_step(terms(m_dp, slice(lo, hi)), o_dp, 1.0, world=(dist.group.WORLD, world, B), precision=prec)
+            l_dp = train_step(terms(m_dp, slice(lo, hi)), o_dp, 1.0, world=(group, world, B), precision=prec)
             l_full = train_step(terms(m_full, slice(0, B)), o_full, 1.0, precision=prec)
             if it == 0:  # the all-reduced shard gradients ARE the full-batch gradient (same weights on both sides here)
                 g_dp, g_full = m_dp.net.flat_grad().double(), m_full.net.flat_grad().double()
@@ -67,20 +72,24 @@ def _worker(rank, world, port, q, prec):
         le, la, rw = score_sharded(m_full, to(s), to(a), probe=to(probe), n_steps=8, gather=True, precision="fp32")
         le1, la1, rw1 = m_full.score(to(s), to(a), n_steps=8, probe=to(probe), precision="fp32")
         score_equal = torch.equal(le, le1) and torch.equal(la, la1) and torch.equal(rw, rw1)
+        if comm == "peer":
+            assert group.timeouts() == 0
+            group.close()
         q.put((rank, same_across_ranks, diff, loss_diff, score_equal, grad_rel))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
+@pytest.mark.parametrize("comm", ["nccl", "peer"])
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
-def test_dp_training_and_sharded_scoring_two_gpus(prec):
+def test_dp_training_and_sharded_scoring_two_gpus(prec, comm):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, prec)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, prec, comm)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
@@ -95,3 +104,56 @@ def test_dp_training_and_sharded_scoring_two_gpus(prec):
         assert diff <= 1e-3, diff
         assert loss_diff <= 1e-5, loss_diff
         assert score_equal
+
+
+# ---- the device-side all-reduce (csrc/comm.cu) by itself -------------------------------------------------------------
+def test_peer_allreduce_single_rank_is_the_identity_and_replays_in_a_graph():
+    from modril_b200.dist import PeerAllReduce
+
+    dev = torch.device("cuda", 0)
+    comm = PeerAllReduce(5000, device=dev)   # world 1 (no process group): publish + reduce through the exchange buffer
+    g = torch.Generator(device="cpu").manual_seed(0)
+    bufs = [torch.randn(n, generator=g).to(dev) for n in (4099, 1, 1, 257)]   # ragged lengths: padded to 4 floats inside
+    want = [b.clone() for b in bufs]
+    for _ in range(3):   # both data slots
+        comm.allreduce(bufs)
+    assert all(torch.equal(b, w) for b, w in zip(bufs, want))
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        comm.allreduce(bufs)
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize(dev)
+    assert all(torch.equal(b, w) for b, w in zip(bufs, want))
+    assert comm.timeouts() == 0
+    with pytest.raises(ValueError):
+        comm.allreduce([torch.zeros(6000, device=dev)])   # larger than the exchange buffer
+    comm.close()
+
+
+@pytest.mark.timeout(120)
+def test_peer_allreduce_two_gpus_one_process_sums_in_rank_order():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from modril_b200.dist import PeerAllReduce
+
+    devs = [torch.device("cuda", i) for i in range(2)]
+    n = 200_000
+    comms = PeerAllReduce.local_group(devs, n + 8)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    for it in range(4):
+        host = [torch.randn(n, generator=g) for _ in devs]
+        loss = [torch.randn(1, generator=g) for _ in devs]
+        bufs = [[h.to(d), l.to(d)] for h, l, d in zip(host, loss, devs)]
+        for c, b, d in zip(comms, bufs, devs):
+            with torch.cuda.device(d):
+                c.allreduce(b)
+        for d in devs:
+            torch.cuda.synchronize(d)
+        want, want_l = host[0] + host[1], loss[0] + loss[1]     # fp32 sum in rank order
+        for b in bufs:
+            assert torch.equal(b[0].cpu(), want) and torch.equal(b[1].cpu(), want_l)
+    assert all(c.timeouts() == 0 for c in comms)
+    for c in comms:
+        c.close()

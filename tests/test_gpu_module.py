@@ -246,7 +246,7 @@ def test_gradnorm_branch_runs_when_step_count_is_past_warmup():
     args = make_args(num_steps=4, num_processes=8, traj_batch_size=16, enable_loss_anti=True, enable_loss_stable=True,
                      params_autotune=True)
     mod = make_module(args)
-    mod.gradnorm.step_count.fill_(mod.gradnorm.warmup_steps + 9)   # next forward() makes it a multiple of update_freq
+    mod.gradnorm.set_steps(mod.gradnorm.warmup_steps + 9)   # next forward() makes it a multiple of update_freq
     mod.gradnorm.L0_anti.fill_(1.0)
     mod.gradnorm.L0_jpen.fill_(1.0)
     storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 9, args.device)
@@ -361,3 +361,70 @@ def test_standalone_flowril_chain_reward_module_then_device_ppo():
     args.freeze_policy = True
     algo.update(storage, args)
     assert torch.equal(frozen, policy.flat_params())
+
+
+# ---- 2fs: batched rollout scoring with the probes drawn in the reference's RNG order (csrc/probe.cu) -----------------
+def test_probe_replay_reproduces_the_sequence_of_randint_like_calls():
+    """One launch == the T x 2 x n_steps small ``randint_like`` draws of the reference (pretrain.py:90 under flowril.py:186-189),
+    values AND generator state afterwards."""
+    args = make_args(option="2fs", flowril_reward_norm=False)
+    mod = make_module(args)
+    dev = args.device
+    gen = torch.cuda.default_generators[dev.index]
+    for T, N, n_steps in ((3, 8, 5), (2, 1, 32), (1, 700, 2)):
+        torch.cuda.manual_seed(1234 + T)
+        torch.rand(10, device=dev)                      # a non-zero starting offset
+        state = gen.get_state()
+        want = mod._draw_loop(T, N, n_steps)
+        end = gen.get_offset()
+        gen.set_state(state)
+        got = mod._draw_replay(T, N, n_steps)
+        assert gen.get_offset() == end
+        for w, g in zip(want, got):
+            assert torch.equal(w, g)
+            assert set(torch.unique(g).tolist()) <= {-1.0, 1.0}
+    assert type(mod)._replay_ok.get(dev.index, True)
+
+
+@pytest.mark.parametrize("reward_type", ["raw", "smooth"])
+def test_2fs_batched_rollout_scoring_equals_per_step_scoring(reward_type):
+    """The whole rollout in two launches (one per net) == T per-step calls, bit for bit, when the global generator starts
+    from the same state: same probes (replayed), same kernels, and the same reward transform kernel."""
+    rewards = {}
+    for batched in (True, False):
+        args = make_args(option="2fs", flowril_reward_norm=False, reward_type=reward_type, flowril_batched_scoring=batched,
+                         num_steps=5, num_processes=6)
+        mod = make_module(args)
+        storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 21, args.device)
+        torch.cuda.manual_seed(77)
+        if batched:
+            type(mod)._replay_ok.pop(args.device.index, None)   # exercise the self-check too (it restores the generator)
+        rows = [mod._get_reward(t, storage, {})[0].clone() for t in range(args.num_steps)]
+        rewards[batched] = torch.stack(rows)
+        assert rewards[batched].shape == (args.num_steps, args.num_processes, 1)
+    assert torch.equal(rewards[True], rewards[False])
+
+
+def test_stand_in_update_loop_logs_like_base_irl():
+    """The stand-in of ``BaseIRLAlgo.update`` (used when rl-toolkit is absent) keeps base_irl.py:57-67's logging:
+    per-process running reward sums, pushed to ``ep_log_vals`` when an episode ends, reported as ``culm_irl_reward``."""
+    from modril_b200.flowril.flowril import HAVE_RLF
+
+    if HAVE_RLF:
+        pytest.skip("rl-toolkit is importable: the real loop is tested in test_gpu_plugin_loop.py")
+    args = make_args(num_steps=7, num_processes=4, log_smooth_len=100)
+    mod = make_module(args)
+    storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 31, args.device)
+    logs = mod.update(storage)
+    r = storage.rewards.detach().cpu().numpy()[:, :, 0]
+    m = storage.masks.detach().cpu().numpy()[:args.num_steps, :, 0]
+    culm, done = [0.0] * args.num_processes, []
+    for t in range(args.num_steps):
+        for i in range(args.num_processes):
+            culm[i] += float(r[t, i])
+            if m[t, i] == 0.0:
+                done.append(culm[i])
+                culm[i] = 0.0
+    assert done, "fixture: at least one episode must end inside the rollout"
+    assert np.isclose(logs["culm_irl_reward"], np.mean(done), rtol=1e-6)
+    assert mod.culm_log_vals["reward"] == pytest.approx(culm, rel=1e-6)

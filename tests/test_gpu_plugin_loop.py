@@ -1,0 +1,31 @@
+"""GPU: the reward module driven by rl-toolkit's OWN loop -- ``NestedAlgo.update`` (rlf/algos/nested_algo.py:91-106) ->
+``BaseIRLAlgo.update`` (rlf/algos/il/base_irl.py:37-72) -> our hooks -> the device PPO updater -- over rlf's
+``RolloutStorage`` and ``TransitionDataset`` (all unmodified reference code staged under oracle/_ref/rl-toolkit, see
+oracle/build_ref.py).  Checks what the stand-in loop cannot: ``culm_irl_reward`` comes out of the reference's own logging
+code, the environment rewards are wiped and replaced, and our hooks synchronise the host at most twice per update (the
+logged losses; ONE copy of the [T, N] reward block) although the loop reads every reward with ``.item()``."""
+import math
+
+import pytest
+
+from tests.test_plugin_import import run_runner
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("option", ["scrf", "2fs"])
+def test_real_rl_toolkit_update_loop(option):
+    res = run_runner("loop", option, timeout=540)
+    assert res["have_rlf"] and res["update_is_the_reference_loop"]
+    assert len(res["updates"]) == 3
+    for i, u in enumerate(res["updates"]):
+        assert "culm_irl_reward" in u["keys"] and "flow_loss" in u["keys"] and "agent_loss" in u["keys"], u["keys"]
+        assert "actor_opt_lr" in u["keys"]                       # BaseNetAlgo.update ran (base_net_algo.py:44-51)
+        assert math.isfinite(u["culm_irl_reward"]) and math.isfinite(u["flow_loss"]) and math.isfinite(u["agent_loss"])
+        assert u["rewards_finite"] and u["rewards_replaced"] and u["rewards_std"] > 0
+        assert u["episodes_logged"] == 2 * (i + 1)               # two episode ends per rollout reach ep_log_vals
+        assert u["syncs"]["update_reward_func"] <= 1, u["syncs"]  # the two logged losses, one copy
+        assert u["syncs"]["get_reward"] <= 1, u["syncs"]          # the reward block, one copy for all T steps
+    assert res["storage_equals_block"]
+    assert res["reward_rows_on_host"]

@@ -217,3 +217,45 @@ def test_stacked_pair_pass_equals_two_single_passes(B0, B1, rates):
     g3 = torch.zeros_like(g)
     _native.check(L.frl_cfm_loss_grad_pair(h, arr, 0, _ptr(g3), _native.PREC_FP32, _current_stream(g.device)), "pair fp32")
     assert _rel_l2(g3.cpu().numpy(), single.cpu().numpy()) <= 3e-2      # fp32 vs fp16 operands
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+def test_train_step_graph_equals_eager_steps_and_scoring_sees_the_new_weights(prec):
+    """A whole update replayed as ONE CUDA graph (TrainStepGraph) == the same updates launched eagerly, bit for bit; building
+    the graph leaves weights and optimizer state untouched; and scoring after a replay uses the UPDATED weights (the
+    wrapper marks the nets dirty -- raw-pointer writes do not bump torch's version counters)."""
+    from modril_b200.flowril import FusedAdam, TrainStepGraph, train_step
+
+    spec = cf.NetSpec(11, 3, 256, 4, 2)
+    flat = cf.make_params(spec, 5, 1.0)
+    B = 700
+    s, a = synth.states_actions(3, B, 11, 3)
+    draws = [synth.cfm_draws(10 + i, B, 3) for i in range(2)]
+    probe = dev(synth.rademacher(4, (B, 3)))
+
+    def make():
+        m = build_model(spec, flat)
+        terms = [dict(net=m.net, sign=sg, s=dev(s), a0=dev(a), t=dev(t), noise=dev(z), rate=1.0)
+                 for sg, (t, z) in zip((1.0, -1.0), draws)]
+        return m, terms, FusedAdam([m.net], lr=1e-3, capturable=True)
+
+    m_e, terms_e, opt_e = make()
+    m_g, terms_g, opt_g = make()
+    before = m_g.net.flat_params().clone()
+    score0 = m_g.score(dev(s), dev(a), n_steps=4, probe=probe, precision="fp32")[0].clone()
+    graph = TrainStepGraph(terms_g, opt_g, 1.0, precision=prec)
+    assert torch.equal(m_g.net.flat_params(), before) and opt_g.step_count() == 0
+    for it in range(4):
+        l_e = train_step(terms_e, opt_e, 1.0, precision=prec)
+        l_g = graph()
+        assert all(torch.equal(x, y) for x, y in zip(l_e, l_g))
+        assert torch.equal(m_e.net.flat_params(), m_g.net.flat_params()), it
+        if it == 1:   # new batch contents go in through the static input tensors
+            for te, tg in zip(terms_e, terms_g):
+                for k in ("t", "noise"):
+                    te[k].copy_(te[k].flip(0))
+                    tg[k].copy_(tg[k].flip(0))
+    assert opt_g.step_count() == 4
+    score_g = m_g.score(dev(s), dev(a), n_steps=4, probe=probe, precision="fp32")[0]
+    score_e = m_e.score(dev(s), dev(a), n_steps=4, probe=probe, precision="fp32")[0]
+    assert torch.equal(score_g, score_e) and not torch.equal(score_g, score0)
