@@ -1,4 +1,4 @@
-// One-shot all-reduce (sum) of the data-parallel gradient over NVLink peer memory, as ordinary kernels on the caller's
+// One-shot all-reduce (sum) of the data-parallel gradient over NVLink peer memory, as an ordinary kernel on the caller's
 // stream: graph-capturable, no host synchronisation, no NCCL launch between the gradient kernels and clip + Adam.
 // Replaces what torch.distributed / DistributedDataParallel would do for the reference's update
 // (modril/flowril/flowril.py:311-330 under data parallelism).
@@ -55,73 +55,97 @@ __host__ __device__ inline size_t comm_data_offset(int world, long long max_floa
     return flags + (size_t)slot * (((size_t)max_floats * 4 + 255) / 256 * 256);
 }
 
-__global__ void __launch_bounds__(kCommThreads) comm_publish_kernel(CommBufs b, uint8_t* const* __restrict__ peer, int rank, int world,
-                                                                    long long max_floats, unsigned long long* state) {
-    const unsigned long long epoch = state[0] + 1;
-    float* slot = reinterpret_cast<float*>(peer[rank] + comm_data_offset(world, max_floats, (int)(epoch & 1)));
-    const long long total = b.first[b.n];
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int k = 0;
-        while (k + 1 < b.n && b.first[k + 1] <= i) ++k;
-        const long long j = i - b.first[k];
-        slot[i] = j < b.len[k] ? b.ptr[k][j] : 0.f;
-    }
-    __threadfence_system();   // the slot is visible to the peers before the flag below
-    __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0) last = atomicAdd(&state[1], 1ull) == gridDim.x - 1;
-    __syncthreads();
-    if (last) {
-        __threadfence_system();
-        for (int r = threadIdx.x; r < world; r += blockDim.x) {
-            volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(peer[r] + (size_t)rank * kFlagStride);
-            *flag = epoch;
+// Element i of the packed vector (all buffers back to back, each padded to a multiple of 4 floats) <-> buffer k, offset j.
+// The buffer loop is unrolled with compile-time indices: CommBufs stays in the constant bank (a dynamic index into kernel
+// parameters makes every thread copy the struct to local memory first).
+template <typename F>
+__device__ __forceinline__ void for_each_quad(const CommBufs& b, F&& body) {
+#pragma unroll
+    for (int k = 0; k < kMaxBufs; ++k) {
+        if (k < b.n) {
+            const long long quads = (b.len[k] + 3) / 4;
+            const bool vec = (reinterpret_cast<uintptr_t>(b.ptr[k]) & 15) == 0;
+            for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x)
+                body(b.ptr[k] + 4 * q, b.first[k] / 4 + q, (int)min(4ll, b.len[k] - 4 * q), vec);
         }
-        if (threadIdx.x == 0) state[1] = 0;
     }
 }
 
-__global__ void __launch_bounds__(kCommThreads) comm_reduce_kernel(CommBufs b, uint8_t* const* __restrict__ peer, int rank, int world,
-                                                                   long long max_floats, unsigned long long* state, long long spin_limit) {
+// PHASES: 1 = publish, 2 = wait + reduce, 3 = both in one launch (every block of the grid is resident: grid <= SMs)
+template <int PHASES>
+__global__ void __launch_bounds__(kCommThreads) comm_kernel(const __grid_constant__ CommBufs b, uint8_t* const* __restrict__ peer, int rank,
+                                                            int world, long long max_floats, unsigned long long* state,
+                                                            long long spin_limit) {
     const unsigned long long epoch = state[0] + 1;
-    if (threadIdx.x < world) {
-        volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(peer[rank] + (size_t)threadIdx.x * kFlagStride);
-        const long long t0 = clock64();
-        while (*flag < epoch) {
-            if (clock64() - t0 > spin_limit) {   // a peer never arrived (dead process): give up instead of hanging the GPU
-                atomicAdd(&state[3], 1ull);
-                break;
+    const size_t off = comm_data_offset(world, max_floats, (int)(epoch & 1));
+    if (PHASES & 1) {
+        float4* slot = reinterpret_cast<float4*>(peer[rank] + off);
+        for_each_quad(b, [&](float* src, long long q, int valid, bool vec) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec && valid == 4) {
+                v = *reinterpret_cast<const float4*>(src);
+            } else {
+                if (valid > 0) v.x = src[0];
+                if (valid > 1) v.y = src[1];
+                if (valid > 2) v.z = src[2];
+                if (valid > 3) v.w = src[3];
+            }
+            slot[q] = v;
+        });
+        // the block's part of the slot is visible to the peers before the flag below: ONE system-scope fence per block
+        // (bar.sync orders the other threads' stores before thread 0's fence; fences are cumulative)
+        __syncthreads();
+        __shared__ bool last;
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            last = atomicAdd(&state[1], 1ull) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (last) {               // the whole vector of this rank is in its slot: raise my flag in every peer's buffer
+            __threadfence_system();
+            for (int r = threadIdx.x; r < world; r += blockDim.x)
+                *reinterpret_cast<volatile unsigned long long*>(peer[r] + (size_t)rank * kFlagStride) = epoch;
+            if (threadIdx.x == 0) state[1] = 0;
+        }
+    }
+    if (PHASES & 2) {
+        if (threadIdx.x < world) {
+            volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(peer[rank] + (size_t)threadIdx.x * kFlagStride);
+            const long long t0 = clock64();
+            while (*flag < epoch) {
+                if (clock64() - t0 > spin_limit) {   // a peer never arrived (dead process): give up instead of hanging the GPU
+                    atomicAdd(&state[3], 1ull);
+                    break;
+                }
             }
         }
-    }
-    __syncthreads();
-    __threadfence_system();
-    const size_t off = comm_data_offset(world, max_floats, (int)(epoch & 1));
-    const long long total4 = b.first[b.n] / 4;
-    for (long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 < total4; i4 += (long long)gridDim.x * blockDim.x) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r0 = 0; r0 < world; r0 += 8) {   // up to eight peer loads in flight; summed in rank order (bit-identical on every rank)
-            float4 v[8];
+        if (threadIdx.x < world) __threadfence_system();   // acquire side of the flags read above
+        __syncthreads();
+        for_each_quad(b, [&](float* dst, long long q, int valid, bool vec) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r0 = 0; r0 < world; r0 += 8) {   // up to eight peer loads in flight; summed in rank order (bit-identical on every rank)
+                float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (r0 + u < world) v[u] = ld_peer_v4(reinterpret_cast<const float*>(peer[r0 + u] + off) + 4 * i4);
+                for (int u = 0; u < 8; ++u)
+                    if (r0 + u < world) v[u] = ld_peer_v4(reinterpret_cast<const float*>(peer[r0 + u] + off) + 4 * q);
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (r0 + u < world) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+                for (int u = 0; u < 8; ++u)
+                    if (r0 + u < world) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+            }
+            if (vec && valid == 4) {
+                *reinterpret_cast<float4*>(dst) = acc;
+            } else {
+                if (valid > 0) dst[0] = acc.x;
+                if (valid > 1) dst[1] = acc.y;
+                if (valid > 2) dst[2] = acc.z;
+                if (valid > 3) dst[3] = acc.w;
+            }
+        });
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(&state[2], 1ull) == gridDim.x - 1) {
+            state[2] = 0;
+            state[0] = epoch;   // the next all-reduce uses the other slot
         }
-        const long long i = 4 * i4;
-        int k = 0;
-        while (k + 1 < b.n && b.first[k + 1] <= i) ++k;
-        const long long j = i - b.first[k];
-        const float out[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (j + e < b.len[k]) b.ptr[k][j + e] = out[e];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(&state[2], 1ull) == gridDim.x - 1) {
-        state[2] = 0;
-        state[0] = epoch;   // the next all-reduce uses the other slot
     }
 }
 
@@ -226,32 +250,29 @@ extern "C" int frl_comm_connect_local(frl_comm* c, frl_comm* const* all) {
     return finish_connect(c);
 }
 
-extern "C" int frl_comm_publish(frl_comm* c, float* const* bufs, const long long* ns, int n_bufs, void* stream) {
-    CommBufs b;
-    int rc = make_bufs(c, bufs, ns, n_bufs, &b);
-    if (rc != FRL_OK) return rc;
-    FRL_CUDA(cudaSetDevice(c->device));
-    comm_publish_kernel<<<kCommBlocks, kCommThreads, 0, (cudaStream_t)stream>>>(b, c->peer_dev, c->rank, c->world, c->max_floats, c->state);
-    FRL_CUDA(cudaGetLastError());
-    return FRL_OK;
-}
-
-extern "C" int frl_comm_reduce(frl_comm* c, float* const* bufs, const long long* ns, int n_bufs, void* stream) {
+template <int PHASES>
+static int comm_launch(frl_comm* c, float* const* bufs, const long long* ns, int n_bufs, void* stream) {
     CommBufs b;
     int rc = make_bufs(c, bufs, ns, n_bufs, &b);
     if (rc != FRL_OK) return rc;
     FRL_CUDA(cudaSetDevice(c->device));
     const long long spin_limit = 20ll * 1000 * 1000 * 1000;   // ~10 s of SM clocks
-    comm_reduce_kernel<<<kCommBlocks, kCommThreads, 0, (cudaStream_t)stream>>>(b, c->peer_dev, c->rank, c->world, c->max_floats, c->state,
-                                                                               spin_limit);
+    comm_kernel<PHASES><<<kCommBlocks, kCommThreads, 0, (cudaStream_t)stream>>>(b, c->peer_dev, c->rank, c->world, c->max_floats,
+                                                                                c->state, spin_limit);
     FRL_CUDA(cudaGetLastError());
     return FRL_OK;
 }
 
+extern "C" int frl_comm_publish(frl_comm* c, float* const* bufs, const long long* ns, int n_bufs, void* stream) {
+    return comm_launch<1>(c, bufs, ns, n_bufs, stream);
+}
+
+extern "C" int frl_comm_reduce(frl_comm* c, float* const* bufs, const long long* ns, int n_bufs, void* stream) {
+    return comm_launch<2>(c, bufs, ns, n_bufs, stream);
+}
+
 extern "C" int frl_comm_allreduce(frl_comm* c, float* const* bufs, const long long* ns, int n_bufs, void* stream) {
-    int rc = frl_comm_publish(c, bufs, ns, n_bufs, stream);
-    if (rc != FRL_OK) return rc;
-    return frl_comm_reduce(c, bufs, ns, n_bufs, stream);
+    return comm_launch<3>(c, bufs, ns, n_bufs, stream);   // one launch: 128 blocks, all resident, so the in-kernel wait cannot deadlock
 }
 
 extern "C" long long frl_comm_timeouts(frl_comm* c) {

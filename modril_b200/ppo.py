@@ -387,6 +387,33 @@ class PPO:
         parser.add_argument(f"--{p}eps", type=float, default=1e-12)
         parser.add_argument(f"--{p}lr", type=float, default=1e-3)
 
+    # the rest of rlf's BaseAlgo surface that NestedAlgo fans out to its modules (nested_algo.py:25-89); nothing to do here
+    def set_env_ref(self, envs):
+        self.envs = envs
+
+    def set_get_policy(self, get_policy_fn, policy_args):
+        self._get_policy_fn, self._policy_args = get_policy_fn, policy_args
+
+    def first_train(self, log, eval_policy, env_interface):
+        pass
+
+    def on_traj_finished(self, traj):
+        pass
+
+    def load(self, checkpointer):
+        if checkpointer.has_load_key("actor_opt"):                   # base_net_algo.py:71-75
+            self.load_resume(checkpointer)
+
+    def get_steps_generator(self, update_iter):
+        return range(self.args.num_steps)                            # base_algo.py:62-64
+
+    def get_num_updates(self):                                       # base_algo.py:97-108
+        a = self.args
+        return 0 if a.num_steps == 0 else int(a.num_env_steps) // a.num_steps // a.num_processes
+
+    def get_completed_update_steps(self, num_updates):
+        return num_updates * self.args.num_processes * self.args.num_steps
+
     def save(self, checkpointer):
         checkpointer.save_key("actor_opt", self.opt.state_dict())    # base_net_algo.py:66-69
 

@@ -415,6 +415,9 @@ def test_stand_in_update_loop_logs_like_base_irl():
     args = make_args(num_steps=7, num_processes=4, log_smooth_len=100)
     mod = make_module(args)
     storage = FakeStorage(args.num_steps, args.num_processes, 11, 3, 31, args.device)
+    storage.masks[2, 1] = 0.0
+    storage.masks[5, 1] = 0.0
+    storage.masks[6, 3] = 0.0
     logs = mod.update(storage)
     r = storage.rewards.detach().cpu().numpy()[:, :, 0]
     m = storage.masks.detach().cpu().numpy()[:args.num_steps, :, 0]
