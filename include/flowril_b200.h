@@ -216,6 +216,12 @@ int frl_clip_adam(const frl_adam_segment* segs, int n_segs, long long step, doub
 int frl_clip_adam_dev(const frl_adam_segment* segs, int n_segs, long long* step_dev, double lr, double beta1,
                       double beta2, double eps, double max_norm, float* norm_out_dev, int device, void* stream);
 
+/* Diagnostics of the fused tensor-core update (frl_cfm_loss_grad_p / _pair with a gradient): its stages hand row tiles to
+ * each other through flags in global memory, and every such wait is bounded (~2 s) so that a lost stage cannot hang the
+ * GPU.  Returns how many waits have given up on this net so far (0 in a healthy process; > 0 means the gradients of
+ * that update were garbage), or -1 on a CUDA error.  Synchronises the device. */
+long long frl_train_timeouts(const frl_net* net);
+
 /* ---- reward hook helpers ---------------------------------------------------------------------------------------------
  * frl_reward: the reward transform of _compute_flow_reward (flowril.py:191-208) on two log-density vectors that were
  * produced by separate launches (2fs: each net integrates with its own probes): reward = transform(logp_e - logp_a),

@@ -31,6 +31,7 @@ EXPORTS = (
     "frl_acnet_act", "frl_acnet_evaluate", "frl_ppo_loss_grad", "frl_column_moments", "frl_norm_vec",
     "frl_comm_create", "frl_comm_handle", "frl_comm_connect", "frl_comm_connect_local", "frl_comm_publish",
     "frl_comm_reduce", "frl_comm_allreduce", "frl_comm_timeouts", "frl_comm_destroy", "frl_reward", "frl_rademacher_calls",
+    "frl_train_timeouts",
 )
 
 
@@ -125,11 +126,13 @@ def lib():
         getattr(L, name).argtypes = [vp, C.POINTER(vp), C.POINTER(ll), i32, vp]
     L.frl_comm_timeouts.argtypes = [vp]
     L.frl_comm_timeouts.restype = ll
+    L.frl_train_timeouts.argtypes = [vp]
+    L.frl_train_timeouts.restype = ll
     L.frl_comm_destroy.argtypes = [vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("frl_last_error", "frl_net_num_params", "frl_vnet_num_params", "frl_acnet_num_params",
-                        "frl_comm_timeouts"):
+                        "frl_comm_timeouts", "frl_train_timeouts"):
             fn.restype = i32
     if L.frl_abi_version() != ABI_VERSION:
         raise NativeError(f"ABI mismatch: library {L.frl_abi_version()} != binding {ABI_VERSION}")

@@ -308,6 +308,8 @@ extern "C" int frl_cfm_loss_grad_pair(frl_net* net, const frl_cfm_term* terms, i
     return rc != FRL_OK ? rc : note_reader(net, (cudaStream_t)stream);
 }
 
+extern "C" long long frl_train_timeouts(const frl_net* net) { return net ? train_timeouts(net) : -1; }
+
 extern "C" int frl_reg_loss_grad(frl_net* net, const float* s, const float* a, const float* t, const float* probe,
                                  long long N, long long mean_divisor, int which, float* loss_anti, float* loss_stable,
                                  float* grad_anti, float* grad_stable, void* stream) {

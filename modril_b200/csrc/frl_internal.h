@@ -78,6 +78,7 @@ struct frl_net {
     void* pack_train = nullptr;
     void* ws_tc = nullptr;
     size_t ws_tc_bytes = 0;
+    unsigned* train_flags = nullptr;   // inside ws_tc: [0] = time-out count of the fused training kernel's global waits
     // training workspace (grown on demand)
     float* ws = nullptr;
     size_t ws_floats = 0;
@@ -168,6 +169,7 @@ struct CfmTerm {
     float* loss;   // device scalar (may be null)
 };
 int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumulate, float* grad, cudaStream_t stream);
+long long train_timeouts(const frl_net* net);
 
 // adam.cu
 int clip_adam(const frl_adam_segment* segs, int n_segs, long long step, long long* step_dev, double lr, double beta1,

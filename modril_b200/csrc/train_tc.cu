@@ -25,6 +25,7 @@
 //                            gradient (column sums of dZ) from the same shared-memory tiles; partial sums per split
 //   tc_reduce_kernel(s)      fixed-order reduction of the partials into the flat fp32 gradient (deterministic)
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -48,17 +49,33 @@ constexpr int kWgradThreads = 192;  // warp 0 producer, warp 1 MMA issuer + TMEM
 constexpr int kMaxStages = 8;
 enum { EPI_RELU = 0, EPI_MASK = 1, EPI_LOSS = 2 };
 
+// One tile stream between two stages: R slots of `slot_bytes` (+ optionally `bits_words` mask words per slot).  With
+// ready == done == nullptr it is a plain per-tile array (R = number of tiles) written by an earlier kernel.
+struct Edge {
+    uint8_t* tiles;            // [R][slot_bytes]
+    uint32_t* bits;            // [R][bits_words] ReLU masks travelling with the tiles (may be null)
+    unsigned* ready;           // [R] cumulative arrivals of the producer's epilogue warps (null: always ready)
+    unsigned* done;            // [R] cumulative releases by the consumers                 (null: slots are never reused)
+    int R;
+    unsigned ready_per_tile;   // arrivals that make one tile ready
+    unsigned done_per_tile;    // releases that free one slot (sum over all consumers)
+    uint32_t slot_bytes, bits_words;
+    __device__ __forceinline__ int slot(int tile) const { return tile % R; }
+    __device__ __forceinline__ unsigned use(int tile) const { return (unsigned)(tile / R); }
+};
+
 struct LayerParams {
-    const uint8_t* a_tiles;     // [tile][K/8][128][8]
+    Edge in;                    // A tiles [K/8][128][8]
+    Edge out;                   // out tiles [N/8][128][8] (+ mask bits written by EPI_RELU when out.bits != null)
+    Edge mask;                  // EPI_MASK: the stream whose bits are applied ([N/32][128] words per tile: bit c of word
+                                // (chunk, row) = activation (row, 32*chunk + c) > 0)
     const uint8_t* w_img;       // [K/8][N][8]
     const float* bias;          // [N] (EPI_RELU); EPI_LOSS: bias of head 0 [a_dim] ...
     const float* bias2;         // ... and of head 1 [a_dim] (null for one head), straight from the flat parameters
-    uint8_t* out_tiles;         // [tile][N/8][128][8]
-    const uint32_t* mask_bits;  // [tile][N/32][128]: bit c of word (chunk, row) = activation (row, 32*chunk + c) > 0 (EPI_MASK)
-    uint32_t* bits_out;         // same layout, written by EPI_RELU for the backward pass (may be null)
+    unsigned* err;              // time-out counter of the global waits (may be null)
     int K, N, n_tiles, n_stages;
-    int reverse;                // walk the tiles from the last to the first: consecutive kernels alternate, so a kernel
-                                // starts with the tiles its predecessor wrote last (still in L2)
+    int reverse;                // (unfused launches) walk the tiles from the last to the first: consecutive kernels
+                                // alternate, so a kernel starts with the tiles its predecessor wrote last (still in L2)
     // EPI_LOSS: up to two terms (roles) stacked by tiles: term 1 starts at tile `tile_split` (== n_tiles if there is one)
     const float* a0[2];
     const float* noise[2];
@@ -71,6 +88,41 @@ struct LayerParams {
     double* loss_partial;   // [n_tiles * 4]
     float* dvsum_partial;   // [n_tiles * 4][N]
 };
+
+// ---- global flags ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {   // L2 (ring slots are rewritten: never a stale L1 line)
+    uint32_t v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+constexpr long long kSpinLimit = 4ll * 1000 * 1000 * 1000;   // ~2 s of SM clocks
+// wait until *p >= target (wrap-safe); gives up after kSpinLimit cycles and counts the time-out
+__device__ __noinline__ void wait_ge(const unsigned* p, unsigned target, unsigned* err) {
+    if ((int)(ld_acquire_gpu(p) - target) >= 0) return;
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_gpu(p) - target) < 0) {
+        __nanosleep(64);
+        if (clock64() - t0 > kSpinLimit) {
+            if (err) atomicAdd(err, 1u);
+            return;
+        }
+    }
+}
+__device__ __forceinline__ void wait_ready(const Edge& e, int tile, unsigned* err) {
+    if (e.ready) wait_ge(e.ready + e.slot(tile), (e.use(tile) + 1) * e.ready_per_tile, err);
+}
+__device__ __forceinline__ void wait_free(const Edge& e, int tile, unsigned* err) {
+    if (e.done) wait_ge(e.done + e.slot(tile), e.use(tile) * e.done_per_tile, err);
+}
 
 // X0 tiles: [tile][K0p/8][128][8];  one thread per (tile, 8-feature chunk, row).  Tiles [0, tile_split) hold term 0, the
 // rest term 1 (each term starts on a tile boundary).
@@ -114,8 +166,9 @@ __global__ void tc_prepare_kernel(PrepTerm term0, PrepTerm term1, int tile_split
     *reinterpret_cast<uint4*>(X0t + (size_t)i * 16) = *reinterpret_cast<uint4*>(h);
 }
 
+// One GEMM stage over the row tiles rank, rank + pool, ... (rank = blockIdx.x, pool = gridDim.x for the stand-alone kernel)
 template <int EPI>
-__global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid_constant__ LayerParams p) {
+__device__ __forceinline__ void layer_body(const LayerParams& p, const int rank, const int pool) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem);
     auto full = [&](int s) { return bar0 + 8u * s; };
@@ -163,9 +216,13 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
                 bulk_g2s(smem_u32(sW + off), p.w_img + off, min((uint32_t)kChunkBytes, w_bytes - off), w_full);
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = blockIdx.x; it < p.n_tiles; it += gridDim.x) {
+            for (int it = rank; it < p.n_tiles; it += pool) {
                 const int tile = p.reverse ? p.n_tiles - 1 - it : it;
-                const uint8_t* src = p.a_tiles + (size_t)tile * p.K * (kRows * 2);
+                // the tile (and, for the dgrad stages, the masks that its epilogue will read) has been published
+                wait_ready(p.in, tile, p.err);
+                if (EPI == EPI_MASK) wait_ready(p.mask, tile, p.err);
+                if (p.in.ready) fence_proxy_async_all();   // other SMs' generic-proxy stores -> this bulk (async-proxy) read
+                const uint8_t* src = p.in.tiles + (size_t)p.in.slot(tile) * p.in.slot_bytes;
                 for (int c = 0; c < n_chunks; ++c) {
                     const uint32_t bytes = (uint32_t)min(64, p.K - 64 * c) * (kRows * 2);
                     mbar_wait(empty(stage), phase ^ 1);
@@ -183,12 +240,15 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             mbar_wait(w_full, 0);
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int it = rank; it < p.n_tiles; it += pool) {
+                const int tile = p.reverse ? p.n_tiles - 1 - it : it;
                 mbar_wait(tmem_empty(as), aphase ^ 1);
                 tc_fence_after();
                 for (int c = 0; c < n_chunks; ++c) {
                     const int nk = min(64, p.K - 64 * c) / 16;
                     mbar_wait(full(stage), phase);
+                    // the whole input tile is in shared memory: its ring slot may be rewritten
+                    if (c == n_chunks - 1 && p.in.done) red_release_gpu(p.in.done + p.in.slot(tile), 1u);
                     tc_fence_after();
                     for (int j = 0; j < nk; ++j) {
                         const uint64_t da = make_desc(ring_addr + stage * kChunkBytes + j * (2 * kRows * 16), kRows * 16, 128);
@@ -211,16 +271,24 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
         const int row = q * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
-        for (int it = blockIdx.x; it < p.n_tiles; it += gridDim.x) {
+        for (int it = rank; it < p.n_tiles; it += pool) {
             const int tile = p.reverse ? p.n_tiles - 1 - it : it;
+            const int oslot = p.out.slot(tile);
+            if (p.out.done) {   // every consumer of the tile that used this output slot before has copied it out
+                if (lane == 0) wait_free(p.out, tile, p.err);
+                __syncwarp();
+            }
             mbar_wait(tmem_full(as), aphase);
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
+            uint8_t* const out_tile = p.out.tiles + (size_t)oslot * p.out.slot_bytes;
             if (EPI == EPI_RELU || EPI == EPI_MASK) {
                 const int half = p.N / (kLayerEpiWarps / 4);   // columns per slice
-                uint8_t* out = p.out_tiles + (size_t)tile * p.N * (kRows * 2) + (size_t)row * 16;
+                uint8_t* out = out_tile + (size_t)row * 16;
                 // ReLU masks travel as one bit per activation (4 KB per tile instead of re-reading the 64 KB tile)
-                const size_t bit_row = (size_t)tile * (p.N / 32) * kRows + row;
+                uint32_t* const bits_out = p.out.bits ? p.out.bits + (size_t)oslot * p.out.bits_words + row : nullptr;
+                const uint32_t* const bits_in =
+                    EPI == EPI_MASK ? p.mask.bits + (size_t)p.mask.slot(tile) * p.mask.bits_words + row : nullptr;
                 auto finish = [&](int c0, const uint32_t (&z)[32], uint32_t bits) {
                     uint32_t o[16];
                     if (EPI == EPI_RELU) {
@@ -237,7 +305,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
                             const uint32_t nz = __vcmpne2(o[j], 0u) & 0x00010001u;
                             bits |= ((nz | (nz >> 15)) & 3u) << (2 * j);
                         }
-                        if (p.bits_out) p.bits_out[bit_row + (size_t)(c0 / 32) * kRows] = bits;
+                        if (bits_out) bits_out[(size_t)(c0 / 32) * kRows] = bits;
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -260,8 +328,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
                     if (two) tmem_ld32(taddr + (uint32_t)c0 + 32, z1);
                     uint32_t bits0 = 0, bits1 = 0;
                     if (EPI == EPI_MASK) {
-                        bits0 = __ldg(p.mask_bits + bit_row + (size_t)(c0 / 32) * kRows);
-                        if (two) bits1 = __ldg(p.mask_bits + bit_row + (size_t)(c0 / 32 + 1) * kRows);
+                        bits0 = ld_cg_u32(bits_in + (size_t)(c0 / 32) * kRows);
+                        if (two) bits1 = ld_cg_u32(bits_in + (size_t)(c0 / 32 + 1) * kRows);
                     }
                     tmem_ld_wait_dep(z0);
                     if (two) tmem_ld_wait_dep(z1);
@@ -312,7 +380,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
                 } else {
                     for (int j = 0; j < p.N; ++j) v[j] = 0.f;
                 }
-                uint8_t* out = p.out_tiles + (size_t)tile * p.N * (kRows * 2) + (size_t)row * 16;
+                uint8_t* out = out_tile + (size_t)row * 16;
                 for (int c8 = 0; c8 < p.N; c8 += 8) {
                     uint32_t o[4];
 #pragma unroll
@@ -341,6 +409,15 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty(as));
             }
+            if (p.out.ready || (EPI == EPI_MASK && p.mask.done)) {
+                // publish this warp's part of the output tile (16 arrivals make it ready) and give the mask slot back
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) {
+                    if (p.out.ready) red_release_gpu(p.out.ready + oslot, 1u);
+                    if (EPI == EPI_MASK && p.mask.done) red_release_gpu(p.mask.done + p.mask.slot(tile), 1u);
+                }
+            }
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
@@ -353,6 +430,11 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
     }
 }
 
+template <int EPI>
+__global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid_constant__ LayerParams p) {
+    layer_body<EPI>(p, (int)blockIdx.x, (int)gridDim.x);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // wgrad:  partial[split][m][0..FQ) = sum_{tiles of the split} sum_b P[b][m] Q[b][.]   for all FP features m of P,
 //         partial[split][m][FQ]    = sum_b P[b][m]                                      (bias gradient)
@@ -363,10 +445,10 @@ __global__ void __launch_bounds__(kLayerThreads, 1) tc_layer_kernel(const __grid
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kMaxJobs = kMaxDepth + 1;
 struct WgradJob {
-    const uint8_t* p_tiles;   // [tile][FP/8][128][8]
-    const uint8_t* q_tiles;   // [tile][FQ/8][128][8]
+    Edge P;                   // tiles [FP/8][128][8]
+    Edge Q;                   // tiles [FQ/8][128][8]
     float* partial;           // [n_splits][FP][FQ + 16]
-    uint32_t p_tile_bytes, q_tile_bytes;
+    unsigned* err;
     int FP, FQ;
 };
 struct WgradParams {
@@ -377,7 +459,9 @@ constexpr uint32_t kWgPSlot = 32768, kWgQSlot = 65536;
 constexpr uint32_t kWgPOff = 1024, kWgQOff = kWgPOff + 2 * kWgPSlot;
 constexpr uint32_t kWgSmemBytes = kWgQOff + 2 * kWgQSlot;
 
-__global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
+// Split `rank` of `pool` accumulates the row tiles rank, rank + pool, ... (all of them resident in its TMEM) and writes
+// partial[rank].  Uses the first kWgradThreads threads of the CTA.
+__device__ __forceinline__ void wgrad_body(const WgradJob& jb, const int n_tiles, const int rank, const int pool) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t bar0 = smem_u32(smem);
     auto p_full = [&](int s) { return bar0 + 8u * s; };
@@ -389,10 +473,10 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
     uint8_t* sP = smem + kWgPOff;
     uint8_t* sQ = smem + kWgQOff;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const WgradJob& jb = p.job[blockIdx.y];
-    const int split = blockIdx.x;
-    const int t0 = (int)((long long)split * p.n_tiles / p.n_splits), t1 = (int)((long long)(split + 1) * p.n_tiles / p.n_splits);
+    const int split = rank;
+    const int t0 = rank, t1 = n_tiles, dt = pool;
     const int n_halves = jb.FP / kRows;
+    const uint32_t q_tile_bytes = jb.Q.slot_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -417,18 +501,22 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
             auto load_p = [&](int tile, int mh) {
                 mbar_wait(p_empty(ps), pph ^ 1);
                 mbar_expect_tx(p_full(ps), kWgPSlot);
-                const uint8_t* src = jb.p_tiles + (size_t)tile * jb.p_tile_bytes + (size_t)mh * kWgPSlot;
+                const uint8_t* src = jb.P.tiles + (size_t)jb.P.slot(tile) * jb.P.slot_bytes + (size_t)mh * kWgPSlot;
                 bulk_g2s(smem_u32(sP + ps * kWgPSlot), src, 16384u, p_full(ps));
                 bulk_g2s(smem_u32(sP + ps * kWgPSlot + 16384), src + 16384, 16384u, p_full(ps));
                 if (++ps == 2) { ps = 0; pph ^= 1; }
             };
-            for (int tile = t0; tile < t1; ++tile) {
+            for (int tile = t0; tile < t1; tile += dt) {
+                wait_ready(jb.P, tile, jb.err);
+                wait_ready(jb.Q, tile, jb.err);
+                if (jb.P.ready || jb.Q.ready) fence_proxy_async_all();
                 load_p(tile, 0);
                 mbar_wait(q_empty(qs), qph ^ 1);
-                mbar_expect_tx(q_full(qs), jb.q_tile_bytes);
-                for (uint32_t off = 0; off < jb.q_tile_bytes; off += kChunkBytes)
-                    bulk_g2s(smem_u32(sQ + qs * kWgQSlot + off), jb.q_tiles + (size_t)tile * jb.q_tile_bytes + off,
-                             min((uint32_t)kChunkBytes, jb.q_tile_bytes - off), q_full(qs));
+                mbar_expect_tx(q_full(qs), q_tile_bytes);
+                const uint8_t* qsrc = jb.Q.tiles + (size_t)jb.Q.slot(tile) * q_tile_bytes;
+                for (uint32_t off = 0; off < q_tile_bytes; off += kChunkBytes)
+                    bulk_g2s(smem_u32(sQ + qs * kWgQSlot + off), qsrc + off, min((uint32_t)kChunkBytes, q_tile_bytes - off),
+                             q_full(qs));
                 if (++qs == 2) { qs = 0; qph ^= 1; }
                 for (int mh = 1; mh < n_halves; ++mh) load_p(tile, mh);
             }
@@ -439,10 +527,14 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
             const uint32_t p_addr = smem_u32(sP), q_addr = smem_u32(sQ);
             int ps = 0, qs = 0;
             uint32_t pph = 0, qph = 0;
-            for (int tile = t0; tile < t1; ++tile) {
+            for (int tile = t0; tile < t1; tile += dt) {
                 for (int mh = 0; mh < n_halves; ++mh) {
                     mbar_wait(p_full(ps), pph);
-                    if (mh == 0) mbar_wait(q_full(qs), qph);
+                    if (mh == 0) {
+                        mbar_wait(q_full(qs), qph);
+                        if (jb.Q.done) red_release_gpu(jb.Q.done + jb.Q.slot(tile), 1u);   // copied out: the slot may be reused
+                    }
+                    if (mh == n_halves - 1 && jb.P.done) red_release_gpu(jb.P.done + jb.P.slot(tile), 1u);
                     tc_fence_after();
                     for (int kk = 0; kk < kRows / 16; ++kk) {
                         // MN-major: 8-row groups are 128 B apart (LBO), 8-feature chunks 128*16 B apart (SBO)
@@ -458,7 +550,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
             }
             umma_commit(acc_full);
         }
-    } else {
+    } else if (warp < kWgradThreads / 32) {
         const int q = warp & 3;
         const int et = (warp - 2) * 32 + lane;     // 0..127
         // column sums of P: thread (chunk = et / 8, g = et % 8) adds rows g, g + 8, ... of one 8-feature chunk
@@ -470,7 +562,7 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
             for (int e = 0; e < 8; ++e) bsum[h][e] = 0.f;
         int ps = 0;
         uint32_t pph = 0;
-        for (int tile = t0; tile < t1; ++tile) {
+        for (int tile = t0; tile < t1; tile += dt) {
 #pragma unroll
             for (int mh = 0; mh < 2; ++mh) {
                 if (mh < n_halves) {
@@ -531,6 +623,39 @@ __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid
     }
 }
 
+__global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
+    wgrad_body(p.job[blockIdx.y], p.n_tiles, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The fused update: every stage of the chain at once, one CTA per SM, tiles handed from stage to stage through L2 rings
+// (see the header comment).  Stage s owns the CTAs [first[s], first[s + 1]).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxLayerStages = 2 * kMaxDepth + 2;   // forward 0..depth-1, heads + loss, dgrad heads, dgrad depth-1..1
+struct FusedParams {
+    LayerParams layer[kMaxLayerStages];
+    WgradJob job[kMaxJobs];
+    int epi[kMaxLayerStages];
+    int first[kMaxLayerStages + kMaxJobs + 1];
+    int n_layer_stages, n_jobs, n_tiles;
+};
+
+__global__ void __launch_bounds__(kLayerThreads, 1) tc_fused_kernel(const __grid_constant__ FusedParams fp) {
+    const int n_stages = fp.n_layer_stages + fp.n_jobs;
+    int s = 0;
+    while (s + 1 < n_stages && (int)blockIdx.x >= fp.first[s + 1]) ++s;
+    const int rank = (int)blockIdx.x - fp.first[s], pool = fp.first[s + 1] - fp.first[s];
+    if (rank >= fp.n_tiles) return;   // fewer tiles than CTAs in this pool: nothing to do (its partial is not read)
+    if (s < fp.n_layer_stages) {
+        const int epi = fp.epi[s];
+        if (epi == EPI_RELU) layer_body<EPI_RELU>(fp.layer[s], rank, pool);
+        else if (epi == EPI_MASK) layer_body<EPI_MASK>(fp.layer[s], rank, pool);
+        else layer_body<EPI_LOSS>(fp.layer[s], rank, pool);
+    } else {
+        wgrad_body(fp.job[s - fp.n_layer_stages], fp.n_tiles, rank, pool);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // reductions of the partials into the flat gradient (fixed order: deterministic)
 // ---------------------------------------------------------------------------------------------------------------
@@ -538,7 +663,8 @@ struct RedParams {
     const float* part[kMaxJobs];   // per wgrad job
     int ldp[kMaxJobs];
     long long off_w[kMaxDepth], off_b[kMaxDepth], off_wh[2], off_bh[2];
-    int depth, H, d_in, a_dim, n_heads, n_splits;
+    int depth, H, d_in, a_dim, n_heads;
+    int n_splits[kMaxJobs];   // partial sums per wgrad job
     long long n_trunk;   // number of flat entries before the heads
     long long n_params;
     float scale;
@@ -576,7 +702,8 @@ __global__ void tc_reduce_kernel(RedParams rp, float* __restrict__ grad) {
     const float* P = rp.part[job];
     const int ldp = rp.ldp[job];
     float acc = 0.f;
-    for (int s = 0; s < rp.n_splits; ++s) acc += P[((size_t)s * rp.H + m) * ldp + col];
+    const int n_splits = rp.n_splits[job];
+    for (int s = 0; s < n_splits; ++s) acc += P[((size_t)s * rp.H + m) * ldp + col];
     acc *= rp.scale;
     grad[e] = rp.accumulate ? grad[e] + acc : acc;
 }
@@ -740,29 +867,30 @@ static int dev_info(int device, DevInfo* out) {
     return FRL_OK;
 }
 
-template <int EPI>
-static int launch_layer(const ttc::LayerParams& p0, int device, cudaStream_t st) {
-    using namespace ttc;
-    LayerParams p = p0;
-    DevInfo di{};
-    int rc0 = dev_info(device, &di);
-    if (rc0 != FRL_OK) return rc0;
-    const int max_smem = di.max_smem, sms = di.sms;
-    const size_t base = 2048 + ((size_t)p.K * p.N * 2 + 1023) / 1024 * 1024;
-    int stages = (int)(((size_t)max_smem - base) / kChunkBytes);
-    stages = std::min(stages, kMaxStages);
-    if (stages < 2) {
-        set_error("tensor-core training: layer does not fit in shared memory");
-        return FRL_ERR_UNSUPPORTED;
+// (fused path) how many CTAs each stage gets: proportional to its estimated cycles per tile, at least one each
+static void size_pools(const std::vector<double>& cost, int budget, std::vector<int>* pool) {
+    const int n = (int)cost.size();
+    pool->assign(n, 1);
+    double total = 0;
+    for (double c : cost) total += c;
+    int used = n;
+    for (int i = 0; i < n; ++i) {
+        const int extra = std::max(0, (int)(cost[i] / total * budget) - 1);
+        (*pool)[i] += extra;
+        used += extra;
     }
-    p.n_stages = stages;
-    // > half of the SM's shared memory, so exactly one CTA (and its 512 TMEM columns) lives on an SM
-    const size_t smem_bytes = std::max(base + (size_t)stages * kChunkBytes, (size_t)120 * 1024);
-    auto kern = tc_layer_kernel<EPI>;
-    FRL_CUDA(set_smem_attr(kern, device, (int)smem_bytes));
-    kern<<<std::min(p.n_tiles, sms), kLayerThreads, smem_bytes, st>>>(p);
-    FRL_CUDA(cudaGetLastError());
-    return FRL_OK;
+    while (used < budget) {   // leftovers to the stages with the most work per CTA
+        int best = 0;
+        for (int i = 1; i < n; ++i)
+            if (cost[i] / (*pool)[i] > cost[best] / (*pool)[best]) best = i;
+        ++(*pool)[best];
+        ++used;
+    }
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
 }
 
 int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumulate, float* grad, cudaStream_t st) {
@@ -778,7 +906,6 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     FRL_REQUIRE(B_total < (1ll << 30), "batch size out of range");
     {
         int rcp = ensure_pack(net, PACK_TRAIN, st);   // fp16 GEMM images
-        if (rcp != FRL_OK) return rcp;
         if (rcp != FRL_OK) return rcp;
     }
     FRL_REQUIRE(net->pack_train != nullptr, "tensor-core training weights missing");
@@ -804,18 +931,50 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     if (rc != FRL_OK) return rc;
     const int sms = di.sms;
     const int n_jobs = depth + 1;                 // trunk layers + heads
-    const int n_splits = std::max(1, std::min(nt, sms / n_jobs));
+    const int n_layer_stages = 2 * depth + 1;     // forward 0..depth-1, heads + loss, dgrad heads, dgrad depth-1..1
+    const int n_stages_total = n_layer_stages + n_jobs;
+    // The fused dataflow kernel needs every stage resident at once; the per-layer launches remain for loss-only calls,
+    // tiny devices and FRL_TRAIN_UNFUSED=1 (A/B tests).
+    const bool fused = grad != nullptr && sms >= 2 * n_stages_total && env_int("FRL_TRAIN_UNFUSED", 0) == 0;
+
+    // ---- stage pools (fused) / split count (per-layer launches) ----
+    // stage order: [F_0 .. F_{depth-1}] [LOSS] [DH] [D_{depth-1} .. D_1] [W_0 .. W_{depth-1}] [W_heads]
+    std::vector<int> pool(n_stages_total, 1);
+    if (fused) {
+        std::vector<double> cost(n_stages_total, 0.0);
+        const double heavy = env_int("FRL_FUSED_COST_GEMM", 2600), wg = env_int("FRL_FUSED_COST_WGRAD", 3000);
+        for (int l = 0; l < depth; ++l) cost[l] = l == 0 ? 900.0 + heavy * K0p / H : heavy;
+        cost[depth] = env_int("FRL_FUSED_COST_LOSS", 1500);
+        cost[depth + 1] = 900.0 + heavy * NOp / H;
+        for (int l = depth - 1; l >= 1; --l) cost[depth + 2 + (depth - 1 - l)] = heavy;
+        for (int l = 0; l < depth; ++l) cost[n_layer_stages + l] = l == 0 ? 700.0 + wg * K0p / H : wg;
+        cost[n_layer_stages + depth] = 700.0 + wg * NOp / H;
+        size_pools(cost, std::min(sms, env_int("FRL_FUSED_CTAS", sms)), &pool);
+    }
+    const int n_splits_unfused = std::max(1, std::min(nt, sms / n_jobs));
+    int n_splits[kMaxJobs];
+    for (int j = 0; j < n_jobs; ++j) n_splits[j] = fused ? std::min(pool[n_layer_stages + j], nt) : n_splits_unfused;
+
+    // ---- rings (fused): slots per stream ~ (stages between the producer and the last consumer + 2) x tiles in flight per stage
+    int maxpool = 1;
+    for (int v : pool) maxpool = std::max(maxpool, v);
+    const int inflight = std::max(4, (maxpool + 4) * env_int("FRL_FUSED_RING_PCT", 100) / 100);
+    int R_h[kMaxDepth], R_dz[kMaxDepth];
+    for (int l = 0; l < depth; ++l) {
+        R_h[l] = fused ? std::min(nt, (2 * (depth - l) + 2) * inflight) : nt;
+        R_dz[l] = fused ? std::min(nt, 3 * inflight) : nt;
+    }
 
     // ---- workspace (bytes) ----
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
     const size_t tileH = (size_t)H * kRows * 2, tileX = (size_t)K0p * kRows * 2, tileV = (size_t)NOp * kRows * 2;
+    const size_t bitsW = (size_t)(H / 32) * kRows;   // mask words per tile
     const size_t o_x0 = take(tileX * nt);
-    size_t o_h[kMaxDepth], o_dz[kMaxDepth];
-    for (int l = 0; l < depth; ++l) o_h[l] = take(tileH * nt);
-    for (int l = 0; l < depth; ++l) o_dz[l] = take(tileH * nt);
-    size_t o_bits[kMaxDepth];
-    for (int l = 0; l < depth; ++l) o_bits[l] = take((size_t)nt * (H / 32) * kRows * sizeof(uint32_t));
+    size_t o_h[kMaxDepth], o_dz[kMaxDepth], o_bits[kMaxDepth];
+    for (int l = 0; l < depth; ++l) o_h[l] = take(tileH * R_h[l]);
+    for (int l = 0; l < depth; ++l) o_dz[l] = take(tileH * R_dz[l]);
+    for (int l = 0; l < depth; ++l) o_bits[l] = take((size_t)R_h[l] * bitsW * sizeof(uint32_t));
     const size_t o_dv = take(tileV * nt);
     const size_t o_lp = take((size_t)nt * 4 * sizeof(double));
     const size_t o_dvs = take((size_t)nt * 4 * NOp * sizeof(float));
@@ -823,8 +982,17 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     int ldp[kMaxJobs];
     for (int j = 0; j < n_jobs; ++j) {
         ldp[j] = (j == 0 ? K0p : (j == depth ? NOp : H)) + 16;
-        o_part[j] = take((size_t)n_splits * H * ldp[j] * sizeof(float));
+        o_part[j] = take((size_t)n_splits[j] * H * ldp[j] * sizeof(float));
     }
+    // flags: [err][ready / done of every stream]
+    size_t n_flags = 1;
+    size_t f_h[kMaxDepth], f_dz[kMaxDepth], f_dv = 0;
+    if (fused) {
+        for (int l = 0; l < depth; ++l) { f_h[l] = n_flags; n_flags += 2 * (size_t)R_h[l]; }
+        for (int l = 0; l < depth; ++l) { f_dz[l] = n_flags; n_flags += 2 * (size_t)R_dz[l]; }
+        f_dv = n_flags; n_flags += (size_t)nt;
+    }
+    const size_t o_flags = take(n_flags * sizeof(unsigned));
     if (net->ws_tc_bytes < off) {
         if (net->ws_tc) net->retired.push_back(net->ws_tc);   // kept alive: see frl_net::retired
         net->ws_tc = nullptr;
@@ -835,9 +1003,127 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     uint8_t* ws = static_cast<uint8_t*>(net->ws_tc);
     double* lpart = reinterpret_cast<double*>(ws + o_lp);
     float* dvsum = reinterpret_cast<float*>(ws + o_dvs);
+    unsigned* flags = reinterpret_cast<unsigned*>(ws + o_flags);
+    net->train_flags = flags;
+    if (fused) FRL_CUDA(cudaMemsetAsync(flags + 1, 0, (n_flags - 1) * sizeof(unsigned), st));   // (flags[0], the time-out count, persists)
 
-    int n_launch = 0;   // layer kernels alternate their tile order (see LayerParams::reverse)
-    // ---- forward ----
+    // ---- the streams ----
+    constexpr unsigned kW = (unsigned)kLayerEpiWarps;   // arrivals of a layer stage per tile
+    auto plain = [&](size_t o_tiles, size_t slot_bytes, int R) {
+        Edge e{};
+        e.tiles = ws + o_tiles; e.R = R; e.slot_bytes = (uint32_t)slot_bytes; e.ready_per_tile = kW; e.done_per_tile = 1;
+        return e;
+    };
+    const Edge e_x0 = plain(o_x0, tileX, nt);
+    Edge e_h[kMaxDepth], e_dz[kMaxDepth], e_dv = plain(o_dv, tileV, nt);
+    for (int l = 0; l < depth; ++l) {
+        e_h[l] = plain(o_h[l], tileH, R_h[l]);
+        e_h[l].bits = grad ? reinterpret_cast<uint32_t*>(ws + o_bits[l]) : nullptr;
+        e_h[l].bits_words = (uint32_t)bitsW;
+        e_dz[l] = plain(o_dz[l], tileH, R_dz[l]);
+        if (fused) {
+            e_h[l].ready = flags + f_h[l]; e_h[l].done = flags + f_h[l] + R_h[l];
+            e_h[l].done_per_tile = 1 + 1 + kW;   // next forward stage (or heads), wgrad of the next layer (or heads), the dgrad epilogue that applies its masks
+            e_dz[l].ready = flags + f_dz[l]; e_dz[l].done = flags + f_dz[l] + R_dz[l];
+            e_dz[l].done_per_tile = l >= 1 ? 2 : 1;   // dgrad through layer l (l >= 1) and wgrad of layer l
+        }
+    }
+    if (fused) e_dv.ready = flags + f_dv;   // one slot per tile: never reused
+
+    // ---- stage parameters ----
+    LayerParams LP[kMaxLayerStages] = {};
+    int epi_of[kMaxLayerStages];
+    int n_launch = 0;   // (per-layer launches) the kernels alternate their tile order (see LayerParams::reverse)
+    auto finish_layer = [&](LayerParams& p, int epi, int idx) -> int {
+        p.n_tiles = nt;
+        p.err = fused ? flags : nullptr;
+        p.reverse = fused ? 0 : ((n_launch++) & 1);
+        const size_t base = 2048 + ((size_t)p.K * p.N * 2 + 1023) / 1024 * 1024;
+        int stages = (int)(((size_t)di.max_smem - base) / kChunkBytes);
+        stages = std::min(stages, kMaxStages);
+        if (stages < 2) {
+            set_error("tensor-core training: layer does not fit in shared memory");
+            return FRL_ERR_UNSUPPORTED;
+        }
+        p.n_stages = stages;
+        epi_of[idx] = epi;
+        return FRL_OK;
+    };
+    for (int l = 0; l < depth; ++l) {   // forward
+        LayerParams& p = LP[l];
+        p.in = l == 0 ? e_x0 : e_h[l - 1];
+        p.out = e_h[l];
+        p.w_img = pk + tp.wf[l];
+        p.bias = net->params_dev + net->off_b[l];   // biases are read from the flat parameters (no fp32 pack needed)
+        p.K = l == 0 ? K0p : H;
+        p.N = H;
+        if ((rc = finish_layer(p, EPI_RELU, l)) != FRL_OK) return rc;
+    }
+    {   // heads + loss
+        LayerParams& p = LP[depth];
+        p.in = e_h[depth - 1];
+        p.out = e_dv;
+        p.w_img = pk + tp.whf;
+        p.bias = net->params_dev + net->off_bh[0];
+        p.bias2 = net->cfg.n_heads == 2 ? net->params_dev + net->off_bh[1] : nullptr;
+        p.K = H;
+        p.N = NOp;
+        for (int i = 0; i < 2; ++i) {
+            const CfmTerm& tm = terms[i < n_terms ? i : 0];
+            p.a0[i] = tm.a0; p.noise[i] = tm.noise; p.t[i] = tm.t; p.sign[i] = tm.sign; p.B[i] = i < n_terms ? tm.B : 0;
+            p.rel[i] = (float)(scale_of[i] / final_scale);
+        }
+        p.tile_split = nt_of[0];
+        p.a_dim = A; p.n_heads = net->cfg.n_heads;
+        p.loss_partial = lpart;
+        p.dvsum_partial = dvsum;
+        if ((rc = finish_layer(p, EPI_LOSS, depth)) != FRL_OK) return rc;
+    }
+    {   // dgrad through the heads: dZ_{depth-1} = (dV Wh) * mask_{depth-1}
+        LayerParams& p = LP[depth + 1];
+        p.in = e_dv;
+        p.out = e_dz[depth - 1];
+        p.mask = e_h[depth - 1];
+        p.w_img = pk + tp.whd;
+        p.K = NOp;
+        p.N = H;
+        if ((rc = finish_layer(p, EPI_MASK, depth + 1)) != FRL_OK) return rc;
+    }
+    for (int l = depth - 1; l >= 1; --l) {   // dgrad through layer l: dZ_{l-1} = (dZ_l W_l) * mask_{l-1}
+        const int idx = depth + 2 + (depth - 1 - l);
+        LayerParams& p = LP[idx];
+        p.in = e_dz[l];
+        p.out = e_dz[l - 1];
+        p.mask = e_h[l - 1];
+        p.w_img = pk + tp.wd[l];
+        p.K = H;
+        p.N = H;
+        if ((rc = finish_layer(p, EPI_MASK, idx)) != FRL_OK) return rc;
+    }
+    WgradJob WJ[kMaxJobs] = {};
+    for (int l = 0; l < n_jobs; ++l) {
+        WgradJob& jb = WJ[l];
+        jb.P = l == depth ? e_h[depth - 1] : e_dz[l];
+        jb.FP = H;
+        if (l == 0) { jb.Q = e_x0; jb.FQ = K0p; }
+        else if (l == depth) { jb.Q = e_dv; jb.FQ = NOp; }
+        else { jb.Q = e_h[l - 1]; jb.FQ = H; }
+        jb.partial = reinterpret_cast<float*>(ws + o_part[l]);
+        jb.err = fused ? flags : nullptr;
+    }
+
+    RedParams rp{};
+    rp.depth = depth; rp.H = H; rp.d_in = net->d_in; rp.a_dim = A; rp.n_heads = net->cfg.n_heads;
+    for (int j = 0; j < n_jobs; ++j) rp.n_splits[j] = n_splits[j];
+    for (int l = 0; l < depth; ++l) { rp.off_w[l] = net->off_w[l]; rp.off_b[l] = net->off_b[l]; }
+    for (int h = 0; h < net->cfg.n_heads; ++h) { rp.off_wh[h] = net->off_wh[h]; rp.off_bh[h] = net->off_bh[h]; }
+    rp.n_trunk = net->off_wh[0];
+    rp.n_params = net->n_params;
+    rp.scale = (float)final_scale;
+    rp.accumulate = accumulate;
+    for (int j = 0; j < n_jobs; ++j) { rp.part[j] = reinterpret_cast<const float*>(ws + o_part[j]); rp.ldp[j] = ldp[j]; }
+
+    // ---- X0 tiles ----
     {
         const CfmTerm& t1 = terms[n_terms - 1];
         const PrepTerm p0{terms[0].s, terms[0].a0, terms[0].t, terms[0].noise, terms[0].B};
@@ -846,104 +1132,54 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         tc_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p0, p1, nt_of[0], ws + o_x0, nt, net->cfg.s_dim, A, K0p);
         FRL_CUDA(cudaGetLastError());
     }
-    for (int l = 0; l < depth; ++l) {
-        LayerParams p{};
-        p.a_tiles = l == 0 ? ws + o_x0 : ws + o_h[l - 1];
-        p.w_img = pk + tp.wf[l];
-        p.bias = net->params_dev + net->off_b[l];   // biases are read from the flat parameters (no fp32 pack needed)
-        p.out_tiles = ws + o_h[l];
-        p.bits_out = grad ? reinterpret_cast<uint32_t*>(ws + o_bits[l]) : nullptr;
-        p.reverse = (n_launch++) & 1;
-        p.K = l == 0 ? K0p : H;
-        p.N = H;
-        p.n_tiles = nt;
-        rc = launch_layer<EPI_RELU>(p, device, st);
-        if (rc != FRL_OK) return rc;
-    }
-    {
-        LayerParams p{};
-        p.a_tiles = ws + o_h[depth - 1];
-        p.w_img = pk + tp.whf;
-        p.bias = net->params_dev + net->off_bh[0];
-        p.bias2 = net->cfg.n_heads == 2 ? net->params_dev + net->off_bh[1] : nullptr;
-        p.out_tiles = ws + o_dv;
-        p.K = H;
-        p.N = NOp;
-        p.n_tiles = nt;
-        for (int i = 0; i < 2; ++i) {
-            const CfmTerm& tm = terms[i < n_terms ? i : 0];
-            p.a0[i] = tm.a0; p.noise[i] = tm.noise; p.t[i] = tm.t; p.sign[i] = tm.sign; p.B[i] = i < n_terms ? tm.B : 0;
-            p.rel[i] = (float)(scale_of[i] / final_scale);
-        }
-        p.tile_split = nt_of[0];
-        p.reverse = (n_launch++) & 1;
-        p.a_dim = A; p.n_heads = net->cfg.n_heads;
-        p.loss_partial = lpart;
-        p.dvsum_partial = dvsum;
-        rc = launch_layer<EPI_LOSS>(p, device, st);
-        if (rc != FRL_OK) return rc;
-    }
-    RedParams rp{};
-    rp.depth = depth; rp.H = H; rp.d_in = net->d_in; rp.a_dim = A; rp.n_heads = net->cfg.n_heads;
-    rp.n_splits = n_splits;
-    for (int l = 0; l < depth; ++l) { rp.off_w[l] = net->off_w[l]; rp.off_b[l] = net->off_b[l]; }
-    for (int h = 0; h < net->cfg.n_heads; ++h) { rp.off_wh[h] = net->off_wh[h]; rp.off_bh[h] = net->off_bh[h]; }
-    rp.n_trunk = net->off_wh[0];
-    rp.n_params = net->n_params;
-    rp.scale = (float)final_scale;
-    rp.accumulate = accumulate;
-    for (int j = 0; j < n_jobs; ++j) { rp.part[j] = reinterpret_cast<const float*>(ws + o_part[j]); rp.ldp[j] = ldp[j]; }
-    if (!grad) {
-        tc_reduce_small_kernel<<<1, 256, 0, st>>>(lpart, dvsum, nt * 4, nt_of[0] * 4, NOp, rp, inv_div[0], inv_div[1], terms[0].loss,
-                                                  n_terms > 1 ? terms[1].loss : nullptr, nullptr);
-        FRL_CUDA(cudaGetLastError());
-        return FRL_OK;
-    }
 
-    // ---- backward: dgrad chain ----
-    {
-        LayerParams p{};
-        p.a_tiles = ws + o_dv;
-        p.w_img = pk + tp.whd;
-        p.out_tiles = ws + o_dz[depth - 1];
-        p.mask_bits = reinterpret_cast<const uint32_t*>(ws + o_bits[depth - 1]);
-        p.reverse = (n_launch++) & 1;
-        p.K = NOp;
-        p.N = H;
-        p.n_tiles = nt;
-        rc = launch_layer<EPI_MASK>(p, device, st);
-        if (rc != FRL_OK) return rc;
-    }
-    for (int l = depth - 1; l >= 1; --l) {
-        LayerParams p{};
-        p.a_tiles = ws + o_dz[l];
-        p.w_img = pk + tp.wd[l];
-        p.out_tiles = ws + o_dz[l - 1];
-        p.mask_bits = reinterpret_cast<const uint32_t*>(ws + o_bits[l - 1]);
-        p.reverse = (n_launch++) & 1;
-        p.K = H;
-        p.N = H;
-        p.n_tiles = nt;
-        rc = launch_layer<EPI_MASK>(p, device, st);
-        if (rc != FRL_OK) return rc;
-    }
-    // ---- wgrad ----
-    {
-        WgradParams wp{};
-        wp.n_jobs = n_jobs; wp.n_tiles = nt; wp.n_splits = n_splits;
-        for (int l = 0; l < n_jobs; ++l) {
-            WgradJob& jb = wp.job[l];
-            jb.p_tiles = l == depth ? ws + o_h[depth - 1] : ws + o_dz[l];
-            jb.p_tile_bytes = (uint32_t)tileH;
-            jb.FP = H;
-            if (l == 0) { jb.q_tiles = ws + o_x0; jb.q_tile_bytes = (uint32_t)tileX; jb.FQ = K0p; }
-            else if (l == depth) { jb.q_tiles = ws + o_dv; jb.q_tile_bytes = (uint32_t)tileV; jb.FQ = NOp; }
-            else { jb.q_tiles = ws + o_h[l - 1]; jb.q_tile_bytes = (uint32_t)tileH; jb.FQ = H; }
-            jb.partial = reinterpret_cast<float*>(ws + o_part[l]);
+    if (fused) {
+        FusedParams fp{};
+        fp.n_layer_stages = n_layer_stages; fp.n_jobs = n_jobs; fp.n_tiles = nt;
+        for (int i = 0; i < n_layer_stages; ++i) { fp.layer[i] = LP[i]; fp.epi[i] = epi_of[i]; }
+        for (int j = 0; j < n_jobs; ++j) fp.job[j] = WJ[j];
+        int first = 0;
+        for (int i = 0; i < n_stages_total; ++i) { fp.first[i] = first; first += pool[i]; }
+        fp.first[n_stages_total] = first;
+        FRL_CUDA(set_smem_attr(tc_fused_kernel, device, di.max_smem));
+        tc_fused_kernel<<<first, kLayerThreads, (size_t)di.max_smem, st>>>(fp);
+        FRL_CUDA(cudaGetLastError());
+    } else {
+        auto launch = [&](int idx) -> int {
+            const LayerParams& p = LP[idx];
+            // > half of the SM's shared memory, so exactly one CTA (and its 512 TMEM columns) lives on an SM
+            const size_t base = 2048 + ((size_t)p.K * p.N * 2 + 1023) / 1024 * 1024;
+            const size_t smem_bytes = std::max(base + (size_t)p.n_stages * kChunkBytes, (size_t)120 * 1024);
+            const int grid = std::min(p.n_tiles, sms);
+            if (epi_of[idx] == EPI_RELU) {
+                FRL_CUDA(set_smem_attr(tc_layer_kernel<EPI_RELU>, device, (int)smem_bytes));
+                tc_layer_kernel<EPI_RELU><<<grid, kLayerThreads, smem_bytes, st>>>(p);
+            } else if (epi_of[idx] == EPI_MASK) {
+                FRL_CUDA(set_smem_attr(tc_layer_kernel<EPI_MASK>, device, (int)smem_bytes));
+                tc_layer_kernel<EPI_MASK><<<grid, kLayerThreads, smem_bytes, st>>>(p);
+            } else {
+                FRL_CUDA(set_smem_attr(tc_layer_kernel<EPI_LOSS>, device, (int)smem_bytes));
+                tc_layer_kernel<EPI_LOSS><<<grid, kLayerThreads, smem_bytes, st>>>(p);
+            }
+            FRL_CUDA(cudaGetLastError());
+            return FRL_OK;
+        };
+        for (int idx = 0; idx <= depth; ++idx)
+            if ((rc = launch(idx)) != FRL_OK) return rc;
+        if (!grad) {
+            tc_reduce_small_kernel<<<1, 256, 0, st>>>(lpart, dvsum, nt * 4, nt_of[0] * 4, NOp, rp, inv_div[0], inv_div[1], terms[0].loss,
+                                                      n_terms > 1 ? terms[1].loss : nullptr, nullptr);
+            FRL_CUDA(cudaGetLastError());
+            return FRL_OK;
         }
+        for (int idx = depth + 1; idx < n_layer_stages; ++idx)
+            if ((rc = launch(idx)) != FRL_OK) return rc;
+        WgradParams wp{};
+        wp.n_jobs = n_jobs; wp.n_tiles = nt; wp.n_splits = n_splits_unfused;
+        for (int l = 0; l < n_jobs; ++l) wp.job[l] = WJ[l];
         const size_t smem_bytes = kWgSmemBytes;
         FRL_CUDA(set_smem_attr(tc_wgrad_kernel, device, (int)smem_bytes));
-        tc_wgrad_kernel<<<dim3(n_splits, n_jobs), kWgradThreads, smem_bytes, st>>>(wp);
+        tc_wgrad_kernel<<<dim3(n_splits_unfused, n_jobs), kWgradThreads, smem_bytes, st>>>(wp);
         FRL_CUDA(cudaGetLastError());
     }
     tc_reduce_kernel<<<(unsigned)((net->n_params + 255) / 256), 256, 0, st>>>(rp, grad);
@@ -951,6 +1187,16 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
                                                                      terms[0].loss, n_terms > 1 ? terms[1].loss : nullptr, grad);
     FRL_CUDA(cudaGetLastError());
     return FRL_OK;
+}
+
+// number of global waits of the fused training kernel that gave up (0 in a healthy run); synchronises the device
+long long train_timeouts(const frl_net* net) {
+    if (!net->train_flags) return 0;
+    unsigned v = 0;
+    if (cudaSetDevice(net->cfg.device) != cudaSuccess) return -1;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, net->train_flags, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (long long)v;
 }
 
 }  // namespace frl

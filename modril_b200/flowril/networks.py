@@ -161,6 +161,12 @@ class _FlatVNet(nn.Module):
             self._packed_key = key
         return self._handle
 
+    def train_timeouts(self) -> int:
+        """Diagnostic: global waits of the fused tensor-core update that gave up on this net (0 when healthy).  Synchronises."""
+        if self._handle is None or not hasattr(_native.lib(), "frl_train_timeouts") or self._ABI[0] != "frl_net_create":
+            return 0
+        return int(_native.lib().frl_train_timeouts(self._handle))
+
     def mark_dirty(self):
         """Force a re-pack on next use (needed only after writing weights through ``.data`` or raw pointers)."""
         self._packed_key = None

@@ -40,4 +40,4 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(f"{task} B={B} {prec}{' graph' if use_graph else ''}: {ms:.3f} ms/step, {2 * B / ms / 1e3:.2f} M rows/s, "
-      f"adam steps {opt.step_count()}", flush=True)
+      f"adam steps {opt.step_count()}, stage time-outs {model.net.train_timeouts()}, losses {[float(x) for x in step()]}", flush=True)

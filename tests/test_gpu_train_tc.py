@@ -16,6 +16,26 @@ from oracle import synth
 from tests.gpu_common import assert_close, build_model, dev, spec_of
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_stage_timeouts(monkeypatch):
+    """Every net a test of this file trains must finish without a time-out in the fused kernel's stage hand-offs."""
+    from modril_b200.flowril import networks
+
+    made = []
+    orig = networks._FlatVNet._finish_init
+
+    def tracking(self, *a, **k):
+        orig(self, *a, **k)
+        made.append(self)
+
+    monkeypatch.setattr(networks._FlatVNet, "_finish_init", tracking)
+    yield
+    for net in made:
+        assert net.train_timeouts() == 0
+
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
