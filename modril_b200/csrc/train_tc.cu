@@ -44,7 +44,10 @@ constexpr int kChunkBytes = 16384;  // 64 features x 128 rows x 2 B
 #define FRL_TRAIN_EPI_WARPS 16
 #endif
 constexpr int kLayerEpiWarps = FRL_TRAIN_EPI_WARPS;   // 8 or 16: four TMEM lane quarters x (2 or 4) column slices
-constexpr int kLayerThreads = (2 + kLayerEpiWarps) * 32;  // warp 0 producer, warp 1 MMA issuer + TMEM owner, then the epilogue warps
+// warp 0 producer, warp 1 MMA issuer + TMEM owner, then the epilogue warps, and one publisher warp (fused kernel: it releases
+// the finished tiles to the next stage, so that the gpu-scope fence is off the epilogue warps' critical path)
+constexpr int kLayerThreads = (3 + kLayerEpiWarps) * 32;
+constexpr int kPubWarp = 2 + kLayerEpiWarps;
 constexpr int kWgradThreads = 192;  // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue
 constexpr int kMaxStages = 8;
 enum { EPI_RELU = 0, EPI_MASK = 1, EPI_LOSS = 2 };
@@ -67,12 +70,13 @@ struct Edge {
 struct LayerParams {
     Edge in;                    // A tiles [K/8][128][8]
     Edge out;                   // out tiles [N/8][128][8] (+ mask bits written by EPI_RELU when out.bits != null)
-    Edge mask;                  // EPI_MASK: the stream whose bits are applied ([N/32][128] words per tile: bit c of word
-                                // (chunk, row) = activation (row, 32*chunk + c) > 0)
+    Edge mask;                  // EPI_MASK: the stream whose bits are applied ([N/32][128] words per tile: bits j / 16 + j of
+                                // word (chunk, row) = activation (row, 32*chunk + 2j / 2j + 1) > 0)
     const uint8_t* w_img;       // [K/8][N][8]
     const float* bias;          // [N] (EPI_RELU); EPI_LOSS: bias of head 0 [a_dim] ...
     const float* bias2;         // ... and of head 1 [a_dim] (null for one head), straight from the flat parameters
     unsigned* err;              // time-out counter of the global waits (may be null)
+    unsigned long long* trace;  // FRL_FUSED_TRACE: [CTA][8] cycle counters (null otherwise)
     int K, N, n_tiles, n_stages;
     int reverse;                // (unfused launches) walk the tiles from the last to the first: consecutive kernels
                                 // alternate, so a kernel starts with the tiles its predecessor wrote last (still in L2)
@@ -98,30 +102,52 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 __device__ __forceinline__ void red_release_gpu(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {   // L2 (ring slots are rewritten: never a stale L1 line)
     uint32_t v;
     asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-constexpr long long kSpinLimit = 4ll * 1000 * 1000 * 1000;   // ~2 s of SM clocks
-// wait until *p >= target (wrap-safe); gives up after kSpinLimit cycles and counts the time-out
-__device__ __noinline__ void wait_ge(const unsigned* p, unsigned target, unsigned* err) {
+constexpr long long kSpinLimit = 1000ll * 1000 * 1000;   // ~0.5 s of SM clocks (a healthy update takes ~0.2 ms in total)
+// wait until *p >= target (wrap-safe).  Gives up after kSpinLimit cycles and counts the time-out; once any wait of the
+// launch has timed out, all the others return at once, so a broken hand-off costs one limit, not one per tile.
+__device__ __noinline__ void wait_ge(const unsigned* p, unsigned target, unsigned* err, unsigned err0) {
     if ((int)(ld_acquire_gpu(p) - target) >= 0) return;
     const long long t0 = clock64();
     while ((int)(ld_acquire_gpu(p) - target) < 0) {
         __nanosleep(64);
+        if (err && ld_acquire_gpu(err) != err0) return;
         if (clock64() - t0 > kSpinLimit) {
             if (err) atomicAdd(err, 1u);
             return;
         }
     }
 }
-__device__ __forceinline__ void wait_ready(const Edge& e, int tile, unsigned* err) {
-    if (e.ready) wait_ge(e.ready + e.slot(tile), (e.use(tile) + 1) * e.ready_per_tile, err);
+__device__ __forceinline__ void wait_ready(const Edge& e, int tile, unsigned* err, unsigned err0) {
+    if (e.ready) wait_ge(e.ready + e.slot(tile), (e.use(tile) + 1) * e.ready_per_tile, err, err0);
 }
-__device__ __forceinline__ void wait_free(const Edge& e, int tile, unsigned* err) {
-    if (e.done) wait_ge(e.done + e.slot(tile), e.use(tile) * e.done_per_tile, err);
+// Slot reuse: the consumers bump `done` after their copy of the tile has LANDED in their shared memory, so nothing the
+// producer writes afterwards can reach them: a relaxed poll is enough (the stores depend on it through control flow).
+// `probe` is the counter value read one tile earlier (its latency is hidden behind that tile's epilogue).
+__device__ __forceinline__ void wait_free(const Edge& e, int tile, unsigned probe, unsigned* err, unsigned err0) {
+    if (!e.done) return;
+    const unsigned target = e.use(tile) * e.done_per_tile;
+    if ((int)(probe - target) >= 0) return;
+    const unsigned* p = e.done + e.slot(tile);
+    const long long t0 = clock64();
+    while ((int)(ld_relaxed_gpu(p) - target) < 0) {
+        __nanosleep(32);
+        if (err && ld_relaxed_gpu(err) != err0) return;
+        if (clock64() - t0 > kSpinLimit) {
+            if (err) atomicAdd(err, 1u);
+            return;
+        }
+    }
 }
 
 // X0 tiles: [tile][K0p/8][128][8];  one thread per (tile, 8-feature chunk, row).  Tiles [0, tile_split) hold term 0, the
@@ -176,6 +202,8 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
     const uint32_t w_full = bar0 + 8u * (2 * kMaxStages);
     auto tmem_full = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 1 + i); };
     auto tmem_empty = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 3 + i); };
+    auto stored = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 5 + i); };      // epilogue warps -> publisher: tile written
+    auto published = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 7 + i); };   // publisher -> epilogue warps: barrier reusable
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
     float* sBias = reinterpret_cast<float*>(smem + 1024);   // [N <= 256]
     uint8_t* sW = smem + 2048;
@@ -184,6 +212,7 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = (p.K + 63) / 64;
+    const unsigned err0 = p.err ? p.err[1] : 0u;   // the time-out count when this update was enqueued (copied by the host side memset chain)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.n_stages; ++s) {
@@ -194,10 +223,13 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
         for (int i = 0; i < 2; ++i) {
             mbar_init(tmem_full(i), 1);
             mbar_init(tmem_empty(i), kLayerEpiWarps);
+            mbar_init(stored(i), kLayerEpiWarps);
+            mbar_init(published(i), 1);
         }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc512(smem_u32(tmem_slot));
+    const bool publish = p.out.ready != nullptr || (EPI == EPI_MASK && p.mask.done != nullptr);
     if (EPI == EPI_RELU)
         for (int i = threadIdx.x; i < p.N; i += kLayerThreads) sBias[i] = p.bias[i];
     if (EPI == EPI_LOSS)   // head columns: [head 0 (a_dim) | head 1 (a_dim) | padding]
@@ -216,20 +248,32 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
                 bulk_g2s(smem_u32(sW + off), p.w_img + off, min((uint32_t)kChunkBytes, w_bytes - off), w_full);
             int stage = 0;
             uint32_t phase = 0;
+            long long t_wait = 0, t_ring = 0;
+            const long long t_begin = clock64();
             for (int it = rank; it < p.n_tiles; it += pool) {
                 const int tile = p.reverse ? p.n_tiles - 1 - it : it;
                 // the tile (and, for the dgrad stages, the masks that its epilogue will read) has been published
-                wait_ready(p.in, tile, p.err);
-                if (EPI == EPI_MASK) wait_ready(p.mask, tile, p.err);
+                const long long tw = clock64();
+                wait_ready(p.in, tile, p.err, err0);
+                if (EPI == EPI_MASK) wait_ready(p.mask, tile, p.err, err0);
+                t_wait += clock64() - tw;
                 if (p.in.ready) fence_proxy_async_all();   // other SMs' generic-proxy stores -> this bulk (async-proxy) read
                 const uint8_t* src = p.in.tiles + (size_t)p.in.slot(tile) * p.in.slot_bytes;
                 for (int c = 0; c < n_chunks; ++c) {
                     const uint32_t bytes = (uint32_t)min(64, p.K - 64 * c) * (kRows * 2);
+                    const long long tr = clock64();
                     mbar_wait(empty(stage), phase ^ 1);
+                    t_ring += clock64() - tr;
                     mbar_expect_tx(full(stage), bytes);
                     bulk_g2s(smem_u32(sRing + (size_t)stage * kChunkBytes), src + (size_t)c * kChunkBytes, bytes, full(stage));
                     if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
+            }
+            if (p.trace) {
+                unsigned long long* tr = p.trace + (size_t)blockIdx.x * 8;
+                tr[0] = (unsigned long long)(clock64() - t_begin);   // load thread: total, waiting for input tiles, waiting for a free smem slot
+                tr[1] = (unsigned long long)t_wait;
+                tr[2] = (unsigned long long)t_ring;
             }
         }
     } else if (warp == 1) {
@@ -240,13 +284,18 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
             int stage = 0, as = 0;
             uint32_t phase = 0, aphase = 0;
             mbar_wait(w_full, 0);
+            long long t_acc = 0, t_full = 0;
             for (int it = rank; it < p.n_tiles; it += pool) {
                 const int tile = p.reverse ? p.n_tiles - 1 - it : it;
+                const long long ta = clock64();
                 mbar_wait(tmem_empty(as), aphase ^ 1);
+                t_acc += clock64() - ta;
                 tc_fence_after();
                 for (int c = 0; c < n_chunks; ++c) {
                     const int nk = min(64, p.K - 64 * c) / 16;
+                    const long long tf = clock64();
                     mbar_wait(full(stage), phase);
+                    t_full += clock64() - tf;
                     // the whole input tile is in shared memory: its ring slot may be rewritten
                     if (c == n_chunks - 1 && p.in.done) red_release_gpu(p.in.done + p.in.slot(tile), 1u);
                     tc_fence_after();
@@ -262,6 +311,28 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
             }
+            if (p.trace) {
+                unsigned long long* tr = p.trace + (size_t)blockIdx.x * 8;
+                tr[3] = (unsigned long long)t_acc;    // MMA thread: waiting for a free accumulator (epilogue behind), for operand chunks
+                tr[4] = (unsigned long long)t_full;
+            }
+        }
+    } else if (warp == kPubWarp) {
+        // ------------------------------------------------ publisher -----------------------------------------------
+        // One thread hands every finished tile to the next stage: its release covers the 16 epilogue warps' stores (they
+        // arrived on `stored`, which it acquired), and its gpu-scope fence costs the epilogue warps nothing.
+        if (lane == 0 && publish) {
+            int as = 0;
+            uint32_t ph = 0;
+            for (int it = rank; it < p.n_tiles; it += pool) {
+                const int tile = p.reverse ? p.n_tiles - 1 - it : it;
+                mbar_wait(stored(as), ph);
+                if (p.out.ready) red_release_gpu(p.out.ready + p.out.slot(tile), (unsigned)kLayerEpiWarps);
+                if (EPI == EPI_MASK && p.mask.done) red_release_gpu(p.mask.done + p.mask.slot(tile), (unsigned)kLayerEpiWarps);
+                mbar_arrive(published(as));
+                as ^= 1;
+                if (as == 0) ph ^= 1;
+            }
         }
     } else {
         // ------------------------------------------------ epilogue ------------------------------------------------
@@ -271,14 +342,25 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
         const int row = q * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
-        for (int it = rank; it < p.n_tiles; it += pool) {
+        long long t_free = 0, t_tm = 0, t_pub = 0;
+        unsigned probe = 0;   // lane 0: `done` counter of the NEXT tile's output slot, read one tile ahead
+        if (p.out.done && lane == 0 && rank < p.n_tiles) probe = ld_relaxed_gpu(p.out.done + p.out.slot(rank));
+        int n_done = 0;
+        for (int it = rank; it < p.n_tiles; it += pool, ++n_done) {
             const int tile = p.reverse ? p.n_tiles - 1 - it : it;
             const int oslot = p.out.slot(tile);
+            const long long t0e = clock64();
             if (p.out.done) {   // every consumer of the tile that used this output slot before has copied it out
-                if (lane == 0) wait_free(p.out, tile, p.err);
+                if (lane == 0) {
+                    wait_free(p.out, tile, probe, p.err, err0);
+                    if (it + pool < p.n_tiles) probe = ld_relaxed_gpu(p.out.done + p.out.slot(it + pool));
+                }
                 __syncwarp();
             }
+            const long long t1e = clock64();
             mbar_wait(tmem_full(as), aphase);
+            t_free += t1e - t0e;
+            t_tm += clock64() - t1e;
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
             uint8_t* const out_tile = p.out.tiles + (size_t)oslot * p.out.slot_bytes;
@@ -300,17 +382,15 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
                             o[2 * j4 + 1] = pack2_f16_relu(__uint_as_float(z[4 * j4 + 2]) + b.z, __uint_as_float(z[4 * j4 + 3]) + b.w);
                         }
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            // H >= 0 after ReLU, so H > 0  <=>  its fp16 bits are non-zero: 0x0001 per non-zero half
-                            const uint32_t nz = __vcmpne2(o[j], 0u) & 0x00010001u;
-                            bits |= ((nz | (nz >> 15)) & 3u) << (2 * j);
-                        }
+                        for (int j = 0; j < 16; ++j)
+                            // H >= 0 after ReLU, so H > 0  <=>  (H + 0x7FFF) has bit 15 set (no carry between the halves):
+                            // bit j = column 2j, bit 16 + j = column 2j + 1 of the 32-column chunk
+                            bits |= ((o[j] + 0x7FFF7FFFu) >> (15 - j)) & (0x00010001u << j);
                         if (bits_out) bits_out[(size_t)(c0 / 32) * kRows] = bits;
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const uint32_t two = (bits >> (2 * j)) & 3u;                       // bit 0 -> low half, bit 1 -> high half
-                            const uint32_t keep = ((two & 1u) | ((two & 2u) << 15)) * 0xFFFFu;   // 0x0001 / 0x10000 -> 0xFFFF masks
+                            const uint32_t keep = ((bits >> j) & 0x00010001u) * 0xFFFFu;   // 0x0001 / 0x10000 -> 0xFFFF masks
                             o[j] = pack2_f16(__uint_as_float(z[2 * j]), __uint_as_float(z[2 * j + 1])) & keep;
                         }
                     }
@@ -409,17 +489,24 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty(as));
             }
-            if (p.out.ready || (EPI == EPI_MASK && p.mask.done)) {
-                // publish this warp's part of the output tile (16 arrivals make it ready) and give the mask slot back
-                __threadfence();
+            if (publish) {
+                // this warp's part of the output tile is written (and its mask words are read): tell the publisher
+                const long long tp = clock64();
                 __syncwarp();
                 if (lane == 0) {
-                    if (p.out.ready) red_release_gpu(p.out.ready + oslot, 1u);
-                    if (EPI == EPI_MASK && p.mask.done) red_release_gpu(p.mask.done + p.mask.slot(tile), 1u);
+                    if (n_done >= 2) mbar_wait(published(as), (uint32_t)(((n_done >> 1) - 1) & 1));
+                    mbar_arrive(stored(as));
                 }
+                t_pub += clock64() - tp;
             }
             as ^= 1;
             if (as == 0) aphase ^= 1;
+        }
+        if (p.trace && warp == 2 && lane == 0) {
+            unsigned long long* tr = p.trace + (size_t)blockIdx.x * 8;
+            tr[5] = (unsigned long long)t_free;   // epilogue warp 0: waiting for a free output slot, for the accumulator, in the fence
+            tr[6] = (unsigned long long)t_tm;
+            tr[7] = (unsigned long long)t_pub;
         }
     }
     tc_fence_before();
@@ -449,6 +536,7 @@ struct WgradJob {
     Edge Q;                   // tiles [FQ/8][128][8]
     float* partial;           // [n_splits][FP][FQ + 16]
     unsigned* err;
+    unsigned long long* trace;
     int FP, FQ;
 };
 struct WgradParams {
@@ -477,6 +565,7 @@ __device__ __forceinline__ void wgrad_body(const WgradJob& jb, const int n_tiles
     const int t0 = rank, t1 = n_tiles, dt = pool;
     const int n_halves = jb.FP / kRows;
     const uint32_t q_tile_bytes = jb.Q.slot_bytes;
+    const unsigned err0 = jb.err ? jb.err[1] : 0u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -506,9 +595,13 @@ __device__ __forceinline__ void wgrad_body(const WgradJob& jb, const int n_tiles
                 bulk_g2s(smem_u32(sP + ps * kWgPSlot + 16384), src + 16384, 16384u, p_full(ps));
                 if (++ps == 2) { ps = 0; pph ^= 1; }
             };
+            long long t_wait = 0;
+            const long long t_begin = clock64();
             for (int tile = t0; tile < t1; tile += dt) {
-                wait_ready(jb.P, tile, jb.err);
-                wait_ready(jb.Q, tile, jb.err);
+                const long long tw = clock64();
+                wait_ready(jb.P, tile, jb.err, err0);
+                wait_ready(jb.Q, tile, jb.err, err0);
+                t_wait += clock64() - tw;
                 if (jb.P.ready || jb.Q.ready) fence_proxy_async_all();
                 load_p(tile, 0);
                 mbar_wait(q_empty(qs), qph ^ 1);
@@ -519,6 +612,11 @@ __device__ __forceinline__ void wgrad_body(const WgradJob& jb, const int n_tiles
                              q_full(qs));
                 if (++qs == 2) { qs = 0; qph ^= 1; }
                 for (int mh = 1; mh < n_halves; ++mh) load_p(tile, mh);
+            }
+            if (jb.trace) {
+                unsigned long long* tr = jb.trace + (size_t)blockIdx.x * 8;
+                tr[0] = (unsigned long long)(clock64() - t_begin);
+                tr[1] = (unsigned long long)t_wait;
             }
         }
     } else if (warp == 1) {
@@ -942,13 +1040,17 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     std::vector<int> pool(n_stages_total, 1);
     if (fused) {
         std::vector<double> cost(n_stages_total, 0.0);
-        const double heavy = env_int("FRL_FUSED_COST_GEMM", 2600), wg = env_int("FRL_FUSED_COST_WGRAD", 3000);
-        for (int l = 0; l < depth; ++l) cost[l] = l == 0 ? 900.0 + heavy * K0p / H : heavy;
-        cost[depth] = env_int("FRL_FUSED_COST_LOSS", 1500);
-        cost[depth + 1] = 900.0 + heavy * NOp / H;
+        // cycles-per-tile estimates (relative weights): measured per-tile times of the stages on a B200
+        const double heavy = env_int("FRL_FUSED_COST_GEMM", 3000), wg = env_int("FRL_FUSED_COST_WGRAD", 2900);
+        const double c_l0 = env_int("FRL_FUSED_COST_L0", 2900), c_loss = env_int("FRL_FUSED_COST_LOSS", 4000);
+        const double c_dh = env_int("FRL_FUSED_COST_DH", 2900), c_w0 = env_int("FRL_FUSED_COST_W0", 1500);
+        const double c_wh = env_int("FRL_FUSED_COST_WH", 1500);
+        for (int l = 0; l < depth; ++l) cost[l] = l == 0 ? c_l0 + heavy * K0p / H : heavy;
+        cost[depth] = c_loss;
+        cost[depth + 1] = c_dh + heavy * NOp / H;
         for (int l = depth - 1; l >= 1; --l) cost[depth + 2 + (depth - 1 - l)] = heavy;
-        for (int l = 0; l < depth; ++l) cost[n_layer_stages + l] = l == 0 ? 700.0 + wg * K0p / H : wg;
-        cost[n_layer_stages + depth] = 700.0 + wg * NOp / H;
+        for (int l = 0; l < depth; ++l) cost[n_layer_stages + l] = l == 0 ? c_w0 + wg * K0p / H : wg;
+        cost[n_layer_stages + depth] = c_wh + wg * NOp / H;
         size_pools(cost, std::min(sms, env_int("FRL_FUSED_CTAS", sms)), &pool);
     }
     const int n_splits_unfused = std::max(1, std::min(nt, sms / n_jobs));
@@ -970,6 +1072,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
     const size_t tileH = (size_t)H * kRows * 2, tileX = (size_t)K0p * kRows * 2, tileV = (size_t)NOp * kRows * 2;
     const size_t bitsW = (size_t)(H / 32) * kRows;   // mask words per tile
+    const size_t o_err = take(2 * sizeof(unsigned));   // [time-out count][its value when this update was enqueued]: first, so it stays put
     const size_t o_x0 = take(tileX * nt);
     size_t o_h[kMaxDepth], o_dz[kMaxDepth], o_bits[kMaxDepth];
     for (int l = 0; l < depth; ++l) o_h[l] = take(tileH * R_h[l]);
@@ -984,8 +1087,8 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         ldp[j] = (j == 0 ? K0p : (j == depth ? NOp : H)) + 16;
         o_part[j] = take((size_t)n_splits[j] * H * ldp[j] * sizeof(float));
     }
-    // flags: [err][ready / done of every stream]
-    size_t n_flags = 1;
+    // flags: ready / done counters of every stream
+    size_t n_flags = 0;
     size_t f_h[kMaxDepth], f_dz[kMaxDepth], f_dv = 0;
     if (fused) {
         for (int l = 0; l < depth; ++l) { f_h[l] = n_flags; n_flags += 2 * (size_t)R_h[l]; }
@@ -999,13 +1102,29 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         net->ws_tc_bytes = 0;
         FRL_CUDA(cudaMalloc(&net->ws_tc, off));
         net->ws_tc_bytes = off;
+        net->train_flags = nullptr;
     }
     uint8_t* ws = static_cast<uint8_t*>(net->ws_tc);
     double* lpart = reinterpret_cast<double*>(ws + o_lp);
     float* dvsum = reinterpret_cast<float*>(ws + o_dvs);
     unsigned* flags = reinterpret_cast<unsigned*>(ws + o_flags);
-    net->train_flags = flags;
-    if (fused) FRL_CUDA(cudaMemsetAsync(flags + 1, 0, (n_flags - 1) * sizeof(unsigned), st));   // (flags[0], the time-out count, persists)
+    unsigned* err = reinterpret_cast<unsigned*>(ws + o_err);
+    if (net->train_flags != err) {   // new workspace: the time-out count starts at 0
+        FRL_CUDA(cudaMemsetAsync(err, 0, 2 * sizeof(unsigned), st));
+        net->train_flags = err;
+    }
+    if (fused) {
+        FRL_CUDA(cudaMemsetAsync(flags, 0, n_flags * sizeof(unsigned), st));
+        FRL_CUDA(cudaMemcpyAsync(err + 1, err, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
+    }
+
+    // FRL_FUSED_TRACE=file: per-CTA cycle counters of one launch (synchronises; debugging only)
+    const char* trace_path = fused ? getenv("FRL_FUSED_TRACE") : nullptr;
+    unsigned long long* trace_dev = nullptr;
+    if (trace_path && *trace_path) {
+        FRL_CUDA(cudaMalloc(&trace_dev, (size_t)sms * 8 * sizeof(unsigned long long)));
+        FRL_CUDA(cudaMemsetAsync(trace_dev, 0, (size_t)sms * 8 * sizeof(unsigned long long), st));
+    }
 
     // ---- the streams ----
     constexpr unsigned kW = (unsigned)kLayerEpiWarps;   // arrivals of a layer stage per tile
@@ -1036,7 +1155,8 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     int n_launch = 0;   // (per-layer launches) the kernels alternate their tile order (see LayerParams::reverse)
     auto finish_layer = [&](LayerParams& p, int epi, int idx) -> int {
         p.n_tiles = nt;
-        p.err = fused ? flags : nullptr;
+        p.err = fused ? err : nullptr;
+        p.trace = trace_dev;
         p.reverse = fused ? 0 : ((n_launch++) & 1);
         const size_t base = 2048 + ((size_t)p.K * p.N * 2 + 1023) / 1024 * 1024;
         int stages = (int)(((size_t)di.max_smem - base) / kChunkBytes);
@@ -1109,7 +1229,8 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         else if (l == depth) { jb.Q = e_dv; jb.FQ = NOp; }
         else { jb.Q = e_h[l - 1]; jb.FQ = H; }
         jb.partial = reinterpret_cast<float*>(ws + o_part[l]);
-        jb.err = fused ? flags : nullptr;
+        jb.err = fused ? err : nullptr;
+        jb.trace = trace_dev;
     }
 
     RedParams rp{};
@@ -1144,6 +1265,30 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         FRL_CUDA(set_smem_attr(tc_fused_kernel, device, di.max_smem));
         tc_fused_kernel<<<first, kLayerThreads, (size_t)di.max_smem, st>>>(fp);
         FRL_CUDA(cudaGetLastError());
+        if (trace_dev) {
+            std::vector<unsigned long long> h((size_t)sms * 8);
+            FRL_CUDA(cudaStreamSynchronize(st));
+            FRL_CUDA(cudaMemcpy(h.data(), trace_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            FRL_CUDA(cudaFree(trace_dev));
+            if (FILE* f = fopen(trace_path, "w")) {
+                fprintf(f, "# tiles %d; stage: F<l> forward, LOSS, DH dgrad heads, D<l> dgrad through layer l, W<l> wgrad (W%d = heads)\n", nt, depth);
+                fprintf(f, "# cta stage rank pool | load thread: total wait_in wait_smem_slot | mma: wait_acc wait_chunks | epilogue warp 0: wait_out_slot wait_acc fence\n");
+                for (int i = 0; i < n_stages_total; ++i) {
+                    char name[16];
+                    if (i < depth) snprintf(name, sizeof name, "F%d", i);
+                    else if (i == depth) snprintf(name, sizeof name, "LOSS");
+                    else if (i == depth + 1) snprintf(name, sizeof name, "DH");
+                    else if (i < n_layer_stages) snprintf(name, sizeof name, "D%d", depth - 1 - (i - depth - 2));
+                    else snprintf(name, sizeof name, "W%d", i - n_layer_stages);
+                    for (int r = 0; r < pool[i]; ++r) {
+                        const unsigned long long* t = &h[(size_t)(fp.first[i] + r) * 8];
+                        fprintf(f, "%3d %-4s %2d %2d | %8llu %8llu %8llu | %8llu %8llu | %8llu %8llu %8llu\n", fp.first[i] + r, name, r, pool[i],
+                                t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+                    }
+                }
+                fclose(f);
+            }
+        }
     } else {
         auto launch = [&](int idx) -> int {
             const LayerParams& p = LP[idx];
