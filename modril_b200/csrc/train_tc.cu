@@ -60,6 +60,8 @@ struct Edge {
     unsigned* ready;           // [R] cumulative arrivals of the producer's epilogue warps (null: always ready)
     unsigned* done;            // [R] cumulative releases by the consumers                 (null: slots are never reused)
     int R;
+    int bits_R;                // slots of the mask-bit array (a plain per-tile array in the fused kernel: the masks are read
+                               // by the far end of the pipeline, and 4 KB per tile is cheap to keep for all tiles)
     unsigned ready_per_tile;   // arrivals that make one tile ready
     unsigned done_per_tile;    // releases that free one slot (sum over all consumers)
     uint32_t slot_bytes, bits_words;
@@ -101,6 +103,12 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 }
 __device__ __forceinline__ void red_release_gpu(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// slot give-back by a consumer: its copy of the tile has already landed in its shared memory (observed through the
+// mbarrier), so later writes to the slot cannot reach it -- no fence needed (a release here would stall the MMA thread
+// for a gpu-scope membar per tile)
+__device__ __forceinline__ void red_relaxed_gpu(unsigned* p, unsigned v) {
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
     unsigned v;
@@ -200,11 +208,18 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
     auto full = [&](int s) { return bar0 + 8u * s; };
     auto empty = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
     const uint32_t w_full = bar0 + 8u * (2 * kMaxStages);
+    // Accumulator stages: two of 256 columns, every epilogue warp works on every tile.  The heads stage (EPI_LOSS) has a
+    // narrow accumulator and a long, latency-bound epilogue per row (loads of t / a0 / noise, powf, tanhf): FOUR stages of
+    // 64 columns, and the four column-slice groups of epilogue warps each take every fourth tile, so four tiles' epilogues
+    // run side by side.
+    constexpr int kAcc = EPI == EPI_LOSS ? 4 : 2;
+    constexpr uint32_t kAccCols = EPI == EPI_LOSS ? 64 : 256;
+    constexpr int kArr = EPI == EPI_LOSS ? 4 : kLayerEpiWarps;   // epilogue warps per tile
     auto tmem_full = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 1 + i); };
-    auto tmem_empty = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 3 + i); };
-    auto stored = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 5 + i); };      // epilogue warps -> publisher: tile written
-    auto published = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 7 + i); };   // publisher -> epilogue warps: barrier reusable
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+    auto tmem_empty = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 5 + i); };
+    auto stored = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 9 + i); };       // epilogue warps -> publisher: tile written
+    auto published = [&](int i) { return bar0 + 8u * (2 * kMaxStages + 13 + i); };   // publisher -> epilogue warps: barrier reusable
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
     float* sBias = reinterpret_cast<float*>(smem + 1024);   // [N <= 256]
     uint8_t* sW = smem + 2048;
     const uint32_t w_bytes = (uint32_t)p.K * p.N * 2;
@@ -220,10 +235,10 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
             mbar_init(empty(s), 1);
         }
         mbar_init(w_full, 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kAcc; ++i) {
             mbar_init(tmem_full(i), 1);
-            mbar_init(tmem_empty(i), kLayerEpiWarps);
-            mbar_init(stored(i), kLayerEpiWarps);
+            mbar_init(tmem_empty(i), kArr);
+            mbar_init(stored(i), kArr);
             mbar_init(published(i), 1);
         }
         fence_barrier_init();
@@ -281,12 +296,14 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
         if (lane == 0) {
             const uint32_t idesc = make_idesc_f16((uint32_t)p.N, false, false);
             const uint32_t w_addr = smem_u32(sW), ring_addr = smem_u32(sRing);
-            int stage = 0, as = 0;
-            uint32_t phase = 0, aphase = 0;
+            int stage = 0, n = 0;
+            uint32_t phase = 0;
             mbar_wait(w_full, 0);
             long long t_acc = 0, t_full = 0;
-            for (int it = rank; it < p.n_tiles; it += pool) {
+            for (int it = rank; it < p.n_tiles; it += pool, ++n) {
                 const int tile = p.reverse ? p.n_tiles - 1 - it : it;
+                const int as = n % kAcc;
+                const uint32_t aphase = (uint32_t)(n / kAcc) & 1u;
                 const long long ta = clock64();
                 mbar_wait(tmem_empty(as), aphase ^ 1);
                 t_acc += clock64() - ta;
@@ -297,19 +314,17 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
                     mbar_wait(full(stage), phase);
                     t_full += clock64() - tf;
                     // the whole input tile is in shared memory: its ring slot may be rewritten
-                    if (c == n_chunks - 1 && p.in.done) red_release_gpu(p.in.done + p.in.slot(tile), 1u);
+                    if (c == n_chunks - 1 && p.in.done) red_relaxed_gpu(p.in.done + p.in.slot(tile), 1u);
                     tc_fence_after();
                     for (int j = 0; j < nk; ++j) {
                         const uint64_t da = make_desc(ring_addr + stage * kChunkBytes + j * (2 * kRows * 16), kRows * 16, 128);
                         const uint64_t db = make_desc(w_addr + (uint32_t)(c * 8 + 2 * j) * (uint32_t)p.N * 16, (uint32_t)p.N * 16, 128);
-                        umma_f16(tmem + (uint32_t)as * 256, da, db, idesc, (c | j) != 0);
+                        umma_f16(tmem + (uint32_t)as * kAccCols, da, db, idesc, (c | j) != 0);
                     }
                     umma_commit(empty(stage));
                     if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tmem_full(as));
-                as ^= 1;
-                if (as == 0) aphase ^= 1;
             }
             if (p.trace) {
                 unsigned long long* tr = p.trace + (size_t)blockIdx.x * 8;
@@ -322,16 +337,14 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
         // One thread hands every finished tile to the next stage: its release covers the 16 epilogue warps' stores (they
         // arrived on `stored`, which it acquired), and its gpu-scope fence costs the epilogue warps nothing.
         if (lane == 0 && publish) {
-            int as = 0;
-            uint32_t ph = 0;
-            for (int it = rank; it < p.n_tiles; it += pool) {
+            int n = 0;
+            for (int it = rank; it < p.n_tiles; it += pool, ++n) {
                 const int tile = p.reverse ? p.n_tiles - 1 - it : it;
-                mbar_wait(stored(as), ph);
+                const int as = n % kAcc;
+                mbar_wait(stored(as), (uint32_t)(n / kAcc) & 1u);
                 if (p.out.ready) red_release_gpu(p.out.ready + p.out.slot(tile), (unsigned)kLayerEpiWarps);
                 if (EPI == EPI_MASK && p.mask.done) red_release_gpu(p.mask.done + p.mask.slot(tile), (unsigned)kLayerEpiWarps);
                 mbar_arrive(published(as));
-                as ^= 1;
-                if (as == 0) ph ^= 1;
             }
         }
     } else {
@@ -340,20 +353,21 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
         const int q = warp & 3;      // TMEM lane quarter this warp may access
         const int ch = ew >> 2;      // column slice
         const int row = q * 32 + lane;
-        int as = 0;
-        uint32_t aphase = 0;
         long long t_free = 0, t_tm = 0, t_pub = 0;
+        // local tile n of this CTA is row tile rank + n * pool; EPI_LOSS: warp group `ch` takes n = ch, ch + 4, ...
+        const int n0 = EPI == EPI_LOSS ? ch : 0, dn = EPI == EPI_LOSS ? 4 : 1;
         unsigned probe = 0;   // lane 0: `done` counter of the NEXT tile's output slot, read one tile ahead
-        if (p.out.done && lane == 0 && rank < p.n_tiles) probe = ld_relaxed_gpu(p.out.done + p.out.slot(rank));
-        int n_done = 0;
-        for (int it = rank; it < p.n_tiles; it += pool, ++n_done) {
+        if (p.out.done && lane == 0 && rank + n0 * pool < p.n_tiles) probe = ld_relaxed_gpu(p.out.done + p.out.slot(rank + n0 * pool));
+        for (int n = n0, it = rank + n0 * pool; it < p.n_tiles; n += dn, it += dn * pool) {
             const int tile = p.reverse ? p.n_tiles - 1 - it : it;
             const int oslot = p.out.slot(tile);
+            const int as = n % kAcc;
+            const uint32_t aphase = (uint32_t)(n / kAcc) & 1u;
             const long long t0e = clock64();
             if (p.out.done) {   // every consumer of the tile that used this output slot before has copied it out
                 if (lane == 0) {
                     wait_free(p.out, tile, probe, p.err, err0);
-                    if (it + pool < p.n_tiles) probe = ld_relaxed_gpu(p.out.done + p.out.slot(it + pool));
+                    if (it + dn * pool < p.n_tiles) probe = ld_relaxed_gpu(p.out.done + p.out.slot(it + dn * pool));
                 }
                 __syncwarp();
             }
@@ -362,15 +376,15 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
             t_free += t1e - t0e;
             t_tm += clock64() - t1e;
             tc_fence_after();
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * 256;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)as * kAccCols;
             uint8_t* const out_tile = p.out.tiles + (size_t)oslot * p.out.slot_bytes;
             if (EPI == EPI_RELU || EPI == EPI_MASK) {
                 const int half = p.N / (kLayerEpiWarps / 4);   // columns per slice
                 uint8_t* out = out_tile + (size_t)row * 16;
                 // ReLU masks travel as one bit per activation (4 KB per tile instead of re-reading the 64 KB tile)
-                uint32_t* const bits_out = p.out.bits ? p.out.bits + (size_t)oslot * p.out.bits_words + row : nullptr;
+                uint32_t* const bits_out = p.out.bits ? p.out.bits + (size_t)(tile % p.out.bits_R) * p.out.bits_words + row : nullptr;
                 const uint32_t* const bits_in =
-                    EPI == EPI_MASK ? p.mask.bits + (size_t)p.mask.slot(tile) * p.mask.bits_words + row : nullptr;
+                    EPI == EPI_MASK ? p.mask.bits + (size_t)(tile % p.mask.bits_R) * p.mask.bits_words + row : nullptr;
                 auto finish = [&](int c0, const uint32_t (&z)[32], uint32_t bits) {
                     uint32_t o[16];
                     if (EPI == EPI_RELU) {
@@ -421,7 +435,7 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
                     finish(c0, z0, bits0);
                     if (two) finish(c0 + 32, z1, bits1);
                 }
-            } else if (ch == 0) {
+            } else {
                 // heads: V = D + b;  loss term and dL/dV (scaled by 2 w only: 1/B and the caller's grad_scale are applied
                 // in the final reduction so that fp16 keeps the values at O(1))  -- pretrain.py:184-189
                 float v[64];
@@ -494,13 +508,11 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
                 const long long tp = clock64();
                 __syncwarp();
                 if (lane == 0) {
-                    if (n_done >= 2) mbar_wait(published(as), (uint32_t)(((n_done >> 1) - 1) & 1));
+                    if (n >= kAcc) mbar_wait(published(as), (uint32_t)((n / kAcc - 1) & 1));
                     mbar_arrive(stored(as));
                 }
                 t_pub += clock64() - tp;
             }
-            as ^= 1;
-            if (as == 0) aphase ^= 1;
         }
         if (p.trace && warp == 2 && lane == 0) {
             unsigned long long* tr = p.trace + (size_t)blockIdx.x * 8;
@@ -630,9 +642,9 @@ __device__ __forceinline__ void wgrad_body(const WgradJob& jb, const int n_tiles
                     mbar_wait(p_full(ps), pph);
                     if (mh == 0) {
                         mbar_wait(q_full(qs), qph);
-                        if (jb.Q.done) red_release_gpu(jb.Q.done + jb.Q.slot(tile), 1u);   // copied out: the slot may be reused
+                        if (jb.Q.done) red_relaxed_gpu(jb.Q.done + jb.Q.slot(tile), 1u);   // copied out: the slot may be reused
                     }
-                    if (mh == n_halves - 1 && jb.P.done) red_release_gpu(jb.P.done + jb.P.slot(tile), 1u);
+                    if (mh == n_halves - 1 && jb.P.done) red_relaxed_gpu(jb.P.done + jb.P.slot(tile), 1u);
                     tc_fence_after();
                     for (int kk = 0; kk < kRows / 16; ++kk) {
                         // MN-major: 8-row groups are 128 B apart (LBO), 8-feature chunks 128*16 B apart (SBO)
@@ -1031,9 +1043,11 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     const int n_jobs = depth + 1;                 // trunk layers + heads
     const int n_layer_stages = 2 * depth + 1;     // forward 0..depth-1, heads + loss, dgrad heads, dgrad depth-1..1
     const int n_stages_total = n_layer_stages + n_jobs;
-    // The fused dataflow kernel needs every stage resident at once; the per-layer launches remain for loss-only calls,
-    // tiny devices and FRL_TRAIN_UNFUSED=1 (A/B tests).
-    const bool fused = grad != nullptr && sms >= 2 * n_stages_total && env_int("FRL_TRAIN_UNFUSED", 0) == 0;
+    // FRL_TRAIN_FUSED=1 selects the dataflow kernel (every stage resident at once).  Measured on a B200 (maze, 2 x 65536
+    // rows, profiles/r02_fused_train.md): activations stay in L2 and its stages run ~2x faster per tile than the HBM-fed
+    // per-layer kernels, but 14 stage pools of 7-12 CTAs fill, drain and balance badly at ~90 tiles per CTA: 0.42 ms per
+    // update against 0.35 ms for the per-layer launches, which therefore remain the default.
+    const bool fused = grad != nullptr && sms >= 2 * n_stages_total && env_int("FRL_TRAIN_FUSED", 0) != 0;
 
     // ---- stage pools (fused) / split count (per-layer launches) ----
     // stage order: [F_0 .. F_{depth-1}] [LOSS] [DH] [D_{depth-1} .. D_1] [W_0 .. W_{depth-1}] [W_heads]
@@ -1041,10 +1055,10 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     if (fused) {
         std::vector<double> cost(n_stages_total, 0.0);
         // cycles-per-tile estimates (relative weights): measured per-tile times of the stages on a B200
-        const double heavy = env_int("FRL_FUSED_COST_GEMM", 3000), wg = env_int("FRL_FUSED_COST_WGRAD", 2900);
-        const double c_l0 = env_int("FRL_FUSED_COST_L0", 2900), c_loss = env_int("FRL_FUSED_COST_LOSS", 4000);
-        const double c_dh = env_int("FRL_FUSED_COST_DH", 2900), c_w0 = env_int("FRL_FUSED_COST_W0", 1500);
-        const double c_wh = env_int("FRL_FUSED_COST_WH", 1500);
+        const double heavy = env_int("FRL_FUSED_COST_GEMM", 2850), wg = env_int("FRL_FUSED_COST_WGRAD", 2500);
+        const double c_l0 = env_int("FRL_FUSED_COST_L0", 2500), c_loss = env_int("FRL_FUSED_COST_LOSS", 2400);
+        const double c_dh = env_int("FRL_FUSED_COST_DH", 1450), c_w0 = env_int("FRL_FUSED_COST_W0", 2050);
+        const double c_wh = env_int("FRL_FUSED_COST_WH", 1950);
         for (int l = 0; l < depth; ++l) cost[l] = l == 0 ? c_l0 + heavy * K0p / H : heavy;
         cost[depth] = c_loss;
         cost[depth + 1] = c_dh + heavy * NOp / H;
@@ -1077,7 +1091,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     size_t o_h[kMaxDepth], o_dz[kMaxDepth], o_bits[kMaxDepth];
     for (int l = 0; l < depth; ++l) o_h[l] = take(tileH * R_h[l]);
     for (int l = 0; l < depth; ++l) o_dz[l] = take(tileH * R_dz[l]);
-    for (int l = 0; l < depth; ++l) o_bits[l] = take((size_t)R_h[l] * bitsW * sizeof(uint32_t));
+    for (int l = 0; l < depth; ++l) o_bits[l] = take((size_t)nt * bitsW * sizeof(uint32_t));
     const size_t o_dv = take(tileV * nt);
     const size_t o_lp = take((size_t)nt * 4 * sizeof(double));
     const size_t o_dvs = take((size_t)nt * 4 * NOp * sizeof(float));
@@ -1139,10 +1153,11 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         e_h[l] = plain(o_h[l], tileH, R_h[l]);
         e_h[l].bits = grad ? reinterpret_cast<uint32_t*>(ws + o_bits[l]) : nullptr;
         e_h[l].bits_words = (uint32_t)bitsW;
+        e_h[l].bits_R = nt;
         e_dz[l] = plain(o_dz[l], tileH, R_dz[l]);
         if (fused) {
             e_h[l].ready = flags + f_h[l]; e_h[l].done = flags + f_h[l] + R_h[l];
-            e_h[l].done_per_tile = 1 + 1 + kW;   // next forward stage (or heads), wgrad of the next layer (or heads), the dgrad epilogue that applies its masks
+            e_h[l].done_per_tile = 2;   // next forward stage (or heads) and wgrad of the next layer (or heads)
             e_dz[l].ready = flags + f_dz[l]; e_dz[l].done = flags + f_dz[l] + R_dz[l];
             e_dz[l].done_per_tile = l >= 1 ? 2 : 1;   // dgrad through layer l (l >= 1) and wgrad of layer l
         }
@@ -1161,6 +1176,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         const size_t base = 2048 + ((size_t)p.K * p.N * 2 + 1023) / 1024 * 1024;
         int stages = (int)(((size_t)di.max_smem - base) / kChunkBytes);
         stages = std::min(stages, kMaxStages);
+        if (fused) stages = std::min(stages, std::max(2, env_int("FRL_FUSED_SMEM_STAGES", kMaxStages)));
         if (stages < 2) {
             set_error("tensor-core training: layer does not fit in shared memory");
             return FRL_ERR_UNSUPPORTED;
@@ -1204,6 +1220,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         p.in = e_dv;
         p.out = e_dz[depth - 1];
         p.mask = e_h[depth - 1];
+        p.mask.done = nullptr;   // (the masks live in a per-tile array: nothing to give back)
         p.w_img = pk + tp.whd;
         p.K = NOp;
         p.N = H;
@@ -1215,6 +1232,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         p.in = e_dz[l];
         p.out = e_dz[l - 1];
         p.mask = e_h[l - 1];
+        p.mask.done = nullptr;
         p.w_img = pk + tp.wd[l];
         p.K = H;
         p.N = H;

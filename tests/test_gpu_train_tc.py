@@ -279,3 +279,29 @@ def test_train_step_graph_equals_eager_steps_and_scoring_sees_the_new_weights(pr
     score_g = m_g.score(dev(s), dev(a), n_steps=4, probe=probe, precision="fp32")[0]
     score_e = m_e.score(dev(s), dev(a), n_steps=4, probe=probe, precision="fp32")[0]
     assert torch.equal(score_g, score_e) and not torch.equal(score_g, score0)
+
+
+def test_fused_dataflow_kernel_matches_the_per_layer_launches(monkeypatch):
+    """FRL_TRAIN_FUSED=1 (one persistent kernel, every GEMM stage resident on its own SMs, tiles handed over through L2
+    rings) computes the same stacked-pair gradient as the per-layer launches: identical MMAs per tile, identical fixed-order
+    reduction of per-tile partials -- only the grouping of row tiles into wgrad partial sums differs (fp32 round-off)."""
+    from modril_b200.flowril import FusedAdam, train_step
+
+    spec = cf.NetSpec(17, 6, 256, 4, 2)
+    flat = cf.make_params(spec, 8, 1.0)
+    grads, losses = {}, {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("FRL_TRAIN_FUSED", fused)
+        m = build_model(spec, flat)
+        opt = FusedAdam([m.net], lr=1e-3)
+        terms = []
+        for i, (sg, B) in enumerate(((1.0, 5000), (-1.0, 3333))):
+            s, a = synth.states_actions(20 + i, B, 17, 6)
+            t, z = synth.cfm_draws(30 + i, B, 6)
+            terms.append(dict(net=m.net, sign=sg, s=dev(s), a0=dev(a), t=dev(t), noise=dev(z), rate=1.0))
+        for _ in range(3):   # ring slots and flags are reused across launches
+            losses[fused] = [float(x) for x in train_step(terms, opt, 1.0, precision="fp16")]
+        grads[fused] = m.net.flat_grad().double().cpu().numpy()
+        assert m.net.train_timeouts() == 0
+    assert losses["0"] == pytest.approx(losses["1"], rel=1e-6)
+    assert _rel_l2(grads["1"], grads["0"]) <= 2e-6
