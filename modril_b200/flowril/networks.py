@@ -51,11 +51,70 @@ class _FlatVNet(nn.Module):
         self._flat_grad = None
         self._handle = None
         self._packed_key = None
+        self._pad = None
         self._flatten()
+
+    # ---- free --hidden-dim (reference flowril.py:562, pretrain CLI): the kernels are built for trunk widths 128 and 256;
+    # any other width <= 256 runs as the next of the two with the extra units' weights and biases held at ZERO --
+    # relu(0) = 0 feeds nothing forward, so values, tangents and the gradients of the real entries are unchanged.  The
+    # nn.Parameters keep the reference's shapes; the library sees a zero-padded image of the flat vector.
+    def native_hidden(self) -> int:
+        return self.hidden
+
+    def _pad_plan(self):
+        """(index of every true flat entry inside the padded flat vector, padded length), or None without padding."""
+        Hp = self.native_hidden()
+        if Hp == self.hidden:
+            return None
+        pad = self.__dict__.get("_pad")
+        dev = self._flat.device
+        if pad is not None and pad[0].device == dev:
+            return pad
+        H, A, d_in = self.hidden, self.a_dim, self.a_dim + self.s_dim + 1
+        ar = lambda n: torch.arange(n, device=dev)
+        parts, off = [], 0
+        for l in range(self.depth):
+            K, Kp = (d_in, d_in) if l == 0 else (H, Hp)
+            parts += [(ar(H)[:, None] * Kp + ar(K)[None, :] + off).reshape(-1), ar(H) + off + Hp * Kp]
+            off += Hp * Kp + Hp
+        for _ in range(self.n_heads):
+            parts += [(ar(A)[:, None] * Hp + ar(H)[None, :] + off).reshape(-1), ar(A) + off + A * Hp]
+            off += A * Hp + A
+        idx = torch.cat(parts)
+        assert idx.numel() == self._flat.numel()
+        self.__dict__["_pad"] = (idx, off, torch.zeros(off, device=dev), {})
+        return self.__dict__["_pad"]
+
+    def native_grad(self, key="grad", rows: int = 0):
+        """The buffer to hand to the library for a flat gradient: the caller's own true-size buffer for native widths,
+        a persistent zero-padded one otherwise (``rows`` > 0: a [rows, n] block)."""
+        pad = self._pad_plan()
+        n = self._flat.numel() if pad is None else pad[1]
+        cache = self.__dict__.setdefault("_native_grads", {})
+        buf = cache.get(key)
+        shape = (rows, n) if rows else (n,)
+        if buf is None or buf.device != self._flat.device or tuple(buf.shape) != shape:
+            buf = torch.zeros(shape, device=self._flat.device)
+            cache[key] = buf
+        return buf
+
+    def from_native_grad(self, buf, out=None):
+        """True-layout view of a gradient the library wrote into a ``native_grad`` buffer (a gather for padded nets)."""
+        pad = self._pad_plan()
+        if pad is None:
+            if out is not None and out.data_ptr() != buf.data_ptr():
+                out.copy_(buf)
+            return buf if out is None else out
+        got = buf.index_select(buf.dim() - 1, pad[0])
+        if out is None:
+            return got
+        out.copy_(got)
+        return out
 
     def __getstate__(self):
         st = self.__dict__.copy()
-        st.update(_handle=None, _packed_key=None, _flat=None, _flat_grad=None, _plist=None)  # native handle is per-object
+        st.update(_handle=None, _packed_key=None, _flat=None, _flat_grad=None, _plist=None, _pad=None,
+                  _native_grads={})  # native handle and device buffers are per-object
         return st
 
     def __setstate__(self, st):
@@ -89,6 +148,8 @@ class _FlatVNet(nn.Module):
         self._flat = flat
         self._flat_grad = None
         self._packed_key = None
+        self.__dict__["_pad"] = None
+        self.__dict__["_native_grads"] = {}
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)
@@ -126,7 +187,7 @@ class _FlatVNet(nn.Module):
     _ABI = ("frl_net_create", "frl_net_destroy", "frl_net_set_params")
 
     def _native_config(self, device_index: int):
-        return _native.NetConfig(self.s_dim, self.a_dim, self.hidden, self.depth, self.n_heads, device_index)
+        return _native.NetConfig(self.s_dim, self.a_dim, self.native_hidden(), self.depth, self.n_heads, device_index)
 
     def _release(self):
         if getattr(self, "_handle", None):
@@ -156,8 +217,13 @@ class _FlatVNet(nn.Module):
             self._handle = h
         key = (self._flat.data_ptr(), tuple(p._version for p in self._ordered_params()))
         if key != self._packed_key:
-            _native.check(getattr(L, self._ABI[2])(self._handle, _ptr(self._flat), _current_stream(dev)),
-                          self._ABI[2])
+            src = self._flat
+            pad = self._pad_plan()
+            if pad is not None:   # refresh the zero-padded image the library packs from
+                src = pad[2]
+                with torch.no_grad():
+                    src.index_copy_(0, pad[0], self._flat.detach())
+            _native.check(getattr(L, self._ABI[2])(self._handle, _ptr(src), _current_stream(dev)), self._ABI[2])
             self._packed_key = key
         return self._handle
 
@@ -188,7 +254,14 @@ class _FlatVNet(nn.Module):
         return out0, out1
 
 
-class SharedVNet(_FlatVNet):
+class _VelocityNet(_FlatVNet):
+    def native_hidden(self) -> int:
+        if not 1 <= self.hidden <= 256:
+            raise ValueError(f"hidden_dim {self.hidden}: the sm_100a kernels cover trunk widths up to 256")
+        return 128 if self.hidden <= 128 else 256
+
+
+class SharedVNet(_VelocityNet):
     """Shared trunk with two heads: returns (v_c, tanh(r))  -- reference networks.py:5-25."""
 
     n_heads = 2
@@ -208,7 +281,7 @@ class SharedVNet(_FlatVNet):
         return self._vfield(a, s, t)
 
 
-class ConditionalVNet(_FlatVNet):
+class ConditionalVNet(_VelocityNet):
     """Time-conditioned vector field v(a_t, s, t) -- reference networks.py:28-49."""
 
     n_heads = 1

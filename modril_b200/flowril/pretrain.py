@@ -172,12 +172,12 @@ class _FMLoss(torch.autograd.Function):
         h = net.native()
         B = a0.shape[0]
         loss = torch.empty(1, device=dev)
-        grad = torch.empty_like(net.flat_params()) if need_grad else None
+        gbuf = net.native_grad("fmloss") if need_grad else None
         _native.check(_native.lib().frl_cfm_loss_grad_p(h, float(sign), _ptr(s), _ptr(a0), _ptr(t), _ptr(noise), B, 0,
-                                                        1.0, 0, _ptr(loss), _ptr(grad), prec, _current_stream(dev)),
+                                                        1.0, 0, _ptr(loss), _ptr(gbuf), prec, _current_stream(dev)),
                       "frl_cfm_loss_grad_p")
         ctx.net = net
-        ctx.flat_grad = grad
+        ctx.flat_grad = net.from_native_grad(gbuf).clone() if need_grad else None   # (the buffer is reused by the next call)
         return loss.reshape(())
 
     @staticmethod
@@ -244,10 +244,7 @@ def reg_losses_native(net, s, a, t, probe, anti=True, stable=True, need_grad=Tru
     which = (1 if anti else 0) | (2 if stable else 0)
     if which == 0:
         return {}
-    buf = getattr(net, "_reg_buf", None)
-    if buf is None or buf.device != dev or buf.shape[1] != net.flat_params().numel():
-        buf = torch.zeros(2, net.flat_params().numel(), device=dev)
-        net._reg_buf = buf
+    buf = net.native_grad("reg", rows=2)
     losses = torch.zeros(2, device=dev)
     la, ls = losses[0:1], losses[1:2]
     ga = buf[0] if (need_grad and anti) else None
@@ -255,6 +252,14 @@ def reg_losses_native(net, s, a, t, probe, anti=True, stable=True, need_grad=Tru
     _native.check(_native.lib().frl_reg_loss_grad(h, _ptr(s), _ptr(a), _ptr(t), _ptr(probe), N, int(mean_divisor),
                                                   which, _ptr(la if anti else None), _ptr(ls if stable else None),
                                                   _ptr(ga), _ptr(gs), _current_stream(dev)), "frl_reg_loss_grad")
+    if need_grad and net.native_hidden() != net.hidden:   # padded width: back to the true layout
+        true = getattr(net, "_reg_true", None)
+        if true is None or true.device != dev:
+            true = torch.zeros(2, net.flat_params().numel(), device=dev)
+            net._reg_true = true
+        net.from_native_grad(buf, out=true)
+        ga = true[0] if anti else None
+        gs = true[1] if stable else None
     out = {}
     if anti:
         out["loss_anti"], out["grad_anti"] = la.reshape(()), ga
@@ -646,7 +651,8 @@ def _train_step_grad(terms, opt, world, reg, precision):
         net = term["net"]
         dev = net.flat_params().device
         h = net.native()
-        g = net.flat_grad()
+        padded = net.native_hidden() != net.hidden
+        g = net.native_grad("step") if padded else net.flat_grad()   # (padded width: gathered into flat_grad() below)
         first = all(net is not n for n in seen)
         if first:
             seen.append(net)
@@ -683,6 +689,8 @@ def _train_step_grad(terms, opt, world, reg, precision):
         g = net.flat_grad()
         if all(net is not n for n in seen):
             g.zero_()
+        elif net.native_hidden() != net.hidden:
+            net.from_native_grad(net.native_grad("step"), out=g)
         grads.append(g)
     rout = None
     if reg is not None and (reg.get("anti") is not None or reg.get("stable") is not None):

@@ -289,3 +289,35 @@ def test_reference_sweep_yaml_keys_parse_with_our_flags():
         assert ns.reward_type in ("raw", "norm", "exp", "clip", "smooth"), name
         if "2fs" in name:
             assert ns.option == "2fs" and ns.flow_path.endswith("sine_fm.pt")
+
+
+def test_free_hidden_dim_pad_plan_places_every_true_entry_in_a_zero_padded_image():
+    """Trunk widths other than the kernels' 128 / 256 run zero-padded (networks.py::_pad_plan): every entry of the true
+    flat vector (state_dict order, reference shapes) lands at its [row, column] inside the padded layer blocks, the
+    rest of the image stays zero, and gathering a padded gradient returns the true layout."""
+    import torch
+
+    from modril_b200.flowril.networks import ConditionalVNet, SharedVNet
+
+    for cls, kw in ((SharedVNet, dict(s_dim=5, a_dim=2, hidden=100, depth=3)),
+                    (ConditionalVNet, dict(s_dim=4, a_dim=3, hidden=192, depth=4)),
+                    (SharedVNet, dict(s_dim=3, a_dim=1, hidden=7, depth=2))):
+        net = cls(**kw)
+        idx, total, image, _ = net._pad_plan()
+        H, Hp, d_in = net.hidden, net.native_hidden(), net.a_dim + net.s_dim + 1
+        assert Hp in (128, 256) and Hp >= H
+        assert total == Hp * d_in + Hp + (net.depth - 1) * (Hp * Hp + Hp) + net.n_heads * (net.a_dim * Hp + net.a_dim)
+        assert idx.unique().numel() == idx.numel() == net.flat_params().numel() and int(idx.max()) < total
+        image.index_copy_(0, idx, net.flat_params().detach())
+        if net.depth >= 2:
+            off = Hp * d_in + Hp
+            block = image[off:off + Hp * Hp].view(Hp, Hp)
+            name = [k for k, _ in net.named_parameters() if k.endswith("2.weight")][0]
+            assert torch.equal(block[:H, :H], dict(net.named_parameters())[name].detach())
+            assert float(block[H:].abs().sum()) == 0.0 and float(block[:, H:].abs().sum()) == 0.0
+        assert float(image.abs().sum()) == pytest.approx(float(net.flat_params().detach().abs().sum()), rel=1e-6)
+        assert torch.equal(net.from_native_grad(image), net.flat_params().detach())
+    native = SharedVNet(5, 2, hidden=256, depth=4)
+    assert native._pad_plan() is None and native.native_hidden() == 256
+    with pytest.raises(ValueError):
+        SharedVNet(5, 2, hidden=300, depth=2).native_hidden()
