@@ -551,7 +551,9 @@ class FlowMatchingEstimation(BaseIRLAlgo):
         if self.args.option != "scrf":
             a0 = a0 + torch.randn_like(a0) * 0.02
         t = torch.rand(B, 1, device=dev) * (1 - 2 * eps) + eps
-        noise = torch.distributions.Normal(0., 1.).sample((B, self.action_dim)).to(dev)
+        # the reference draws the noise from the CPU generator (Normal(0., 1.).sample, pretrain.py:99 / :183) and moves it
+        # over; same draw here, but through pinned memory with an asynchronous copy: no stream synchronisation per batch
+        noise = torch.distributions.Normal(0., 1.).sample((B, self.action_dim)).pin_memory().to(dev, non_blocking=True)
         return dict(term, a0=a0, a0_raw=term["a0"], t=t, noise=noise)
 
     def _update_reward_func(self, storage):

@@ -92,7 +92,10 @@ def main():
     module = algo.modules[0]
 
     # count the device->host synchronisations made inside OUR hooks (torch's sync debug mode warns on each one)
-    syncs = {"update_reward_func": 0, "get_reward": 0}
+    # ... attributed to the Python line that triggered them: `ours` = lines of modril_b200/, `caller` = rl-toolkit's own
+    # code running inside the hook (the rollout generator indexes seven device tensors with a Python list per minibatch)
+    syncs = {"update_reward_func": 0, "get_reward": 0, "caller": 0}
+    where = {}
 
     def counted(name, fn):
         def wrapper(*a, **k):
@@ -103,7 +106,13 @@ def main():
                     return fn(*a, **k)
                 finally:
                     torch.cuda.set_sync_debug_mode("default")
-                    syncs[name] += sum("synchroniz" in str(x.message).lower() for x in w)
+                    for x in w:
+                        if "synchroniz" not in str(x.message).lower():
+                            continue
+                        ours = os.sep + "modril_b200" + os.sep in x.filename
+                        syncs[name if ours else "caller"] += 1
+                        key = f"{os.path.relpath(x.filename, ROOT)}:{x.lineno}"
+                        where[key] = where.get(key, 0) + 1
         return wrapper
 
     module._update_reward_func = counted("update_reward_func", module._update_reward_func)
@@ -124,6 +133,7 @@ def main():
         storage.rewards.fill_(123.0)     # "environment rewards": must be wiped and replaced by the IRL reward
         for k in syncs:
             syncs[k] = 0
+        where.clear()
         algo.pre_update(it)
         log = algo.update(storage, args, False, 1)
         rewards = storage.rewards.detach().cpu()
@@ -135,6 +145,7 @@ def main():
                      "rewards_std": float(rewards.std()), "syncs": dict(syncs),
                      "episodes_logged": len(module.ep_log_vals["reward"])})
     out["updates"] = logs
+    out["sync_sites_last_update"] = where
     # the per-step rows the real loop wrote == the module's own batched block (host copy round trip is exact)
     block = module._norm_cache if module._norm_cache is not None else module._rollout_cache
     out["storage_equals_block"] = bool(torch.equal(storage.rewards.detach().cpu(), block.detach().cpu()))

@@ -25,7 +25,10 @@ def test_real_rl_toolkit_update_loop(option):
         assert math.isfinite(u["culm_irl_reward"]) and math.isfinite(u["flow_loss"]) and math.isfinite(u["agent_loss"])
         assert u["rewards_finite"] and u["rewards_replaced"] and u["rewards_std"] > 0
         assert u["episodes_logged"] == 2 * (i + 1)               # two episode ends per rollout reach ep_log_vals
-        assert u["syncs"]["update_reward_func"] <= 1, u["syncs"]  # the two logged losses, one copy
-        assert u["syncs"]["get_reward"] <= 1, u["syncs"]          # the reward block, one copy for all T steps
+        # host synchronisations triggered by lines of modril_b200/ inside the two hooks (torch's sync debug mode; the
+        # rollout generator of rl-toolkit itself, which runs inside _update_reward_func, adds 7 per minibatch and is
+        # counted separately as "caller"): ONE for the logged losses, ONE for the [T, N] reward block
+        assert u["syncs"]["update_reward_func"] <= 1, u["syncs"]
+        assert u["syncs"]["get_reward"] <= (1 if i > 0 else 4), u["syncs"]   # (first update: one-time probe-replay self-check)
     assert res["storage_equals_block"]
     assert res["reward_rows_on_host"]
