@@ -201,10 +201,11 @@ def gen_fmloss(P):
         print("wrote", name, out["loss_expert"], out["loss_agent"])
 
 
-def gen_train(P):
+def gen_train(P, only=None):
     """flowril.py:311-335 for scrf (no regularisers: configs/sine/flowril-no-as.yaml), scrf fine-tune with frozen
     trunk + head_c (flowril.py:52-63) and 2fs both nets (flowril.py:108-109).  Role swap quirk
-    lives above fm_loss and is not part of this fixture: batch 'E' is fed to role expert, batch 'A' to role agent."""
+    lives above fm_loss and is not part of this fixture: batch 'E' is fed to role expert, batch 'A' to role agent.
+    ``only``: indices of the cases to (re)generate (``python -m oracle.gen_golden train:4``)."""
     import torch
 
     for idx, (task, kind, hidden, steps, lr) in enumerate((
@@ -212,7 +213,10 @@ def gen_train(P):
             ("hopper", "scrf_ft", 128, 50, 1e-3),
             ("maze", "2fs", 128, 50, 1e-3),
             ("sine", "scrf", 128, 200, 1e-3),
+            ("maze", "scrf", 256, 1000, 1e-3),   # the module's default width (flowril.py:562) and the benchmarked net
     )):
+        if only is not None and idx not in only:
+            continue
         s_dim, a_dim = synth.TASK_DIMS[task]
         n_heads = 1 if kind == "2fs" else 2
         spec = cf.NetSpec(s_dim, a_dim, hidden, 4, n_heads)
@@ -958,6 +962,9 @@ def main():
         gen_fmloss(P)
     if "train" in which:
         gen_train(P)
+    for w in which:
+        if w.startswith("train:"):
+            gen_train(P, only=[int(x) for x in w.split(":", 1)[1].split(",")])
     if "reg" in which:
         gen_reg(P)
     if "trainreg" in which:
