@@ -107,8 +107,11 @@ def test_dp_training_and_sharded_scoring_two_gpus(prec, comm):
 
 
 # ---- the device-side all-reduce (csrc/comm.cu) by itself -------------------------------------------------------------
-def test_peer_allreduce_single_rank_is_the_identity_and_replays_in_a_graph():
+@pytest.mark.parametrize("algo", ["", "one_shot", "two_shot"])
+def test_peer_allreduce_single_rank_is_the_identity_and_replays_in_a_graph(algo, monkeypatch):
     from modril_b200.dist import PeerAllReduce
+
+    monkeypatch.setenv("FRL_COMM_ALGO", algo)   # default: the LL kernel; the two flag-based kernels are kept for A/B tests
 
     dev = torch.device("cuda", 0)
     comm = PeerAllReduce(5000, device=dev)   # world 1 (no process group): publish + reduce through the exchange buffer
@@ -133,10 +136,13 @@ def test_peer_allreduce_single_rank_is_the_identity_and_replays_in_a_graph():
 
 
 @pytest.mark.timeout(120)
-def test_peer_allreduce_two_gpus_one_process_sums_in_rank_order():
+@pytest.mark.parametrize("algo", ["", "one_shot", "two_shot"])
+def test_peer_allreduce_two_gpus_one_process_sums_in_rank_order(algo, monkeypatch):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from modril_b200.dist import PeerAllReduce
+
+    monkeypatch.setenv("FRL_COMM_ALGO", algo)
 
     devs = [torch.device("cuda", i) for i in range(2)]
     n = 200_000
