@@ -28,7 +28,7 @@ __device__ __forceinline__ double block_sum(double v) {
     return t;  // valid in thread 0
 }
 
-__global__ void __launch_bounds__(kNormThreads) sumsq_kernel(Segs sg, double* __restrict__ partial,
+__global__ void __launch_bounds__(kNormThreads) sumsq_kernel(const __grid_constant__ Segs sg, double* __restrict__ partial,
                                                              long long* __restrict__ step_dev) {
     // device-resident step counter (CUDA-graph replay): advance it here, the Adam kernel that follows reads it
     if (step_dev && blockIdx.x == 0 && threadIdx.x == 0) step_dev[0] += 1;
@@ -37,9 +37,12 @@ __global__ void __launch_bounds__(kNormThreads) sumsq_kernel(Segs sg, double* __
     const long long lo = blockIdx.x * per, hi = min(total, lo + per);
     double acc = 0.0;
     for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        int k = 0;
-        while (k + 1 < sg.n && sg.first[k + 1] <= i) ++k;
-        const float g = sg.s[k].grad[i - sg.first[k]];
+        // segment lookup with compile-time indices: the parameter struct stays in the constant bank
+        const float* gp = sg.s[0].grad + i;
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+            if (k < sg.n && i >= sg.first[k]) gp = sg.s[k].grad + (i - sg.first[k]);
+        const float g = *gp;
         acc += (double)g * (double)g;
     }
     acc = block_sum(acc);
@@ -51,7 +54,7 @@ struct AdamScalars {
     double lr, beta1, beta2;   // used only with a device-resident step counter
 };
 
-__global__ void __launch_bounds__(256) adam_kernel(Segs sg, const double* __restrict__ partial, int n_partial,
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ Segs sg, const double* __restrict__ partial, int n_partial,
                                                    AdamScalars sc, float* __restrict__ norm_out,
                                                    const long long* __restrict__ step_dev) {
     __shared__ float s_coef, s_sqrt_bc2, s_neg_step;
@@ -64,7 +67,9 @@ __global__ void __launch_bounds__(256) adam_kernel(Segs sg, const double* __rest
             s_neg_step = (float)(-sc.lr / (1.0 - pow(sc.beta1, st)));
         }
         double t = 0.0;
-        for (int i = 0; i < n_partial; ++i) t += partial[i];  // same order in every block
+        for (int i = 0; i < n_partial; i += 4)   // same order in every block (four independent chains, then a fixed tree)
+            t += (partial[i] + (i + 1 < n_partial ? partial[i + 1] : 0.0)) +
+                 ((i + 2 < n_partial ? partial[i + 2] : 0.0) + (i + 3 < n_partial ? partial[i + 3] : 0.0));
         const float norm = (float)sqrt(t);
         float coef = sc.max_norm / (norm + 1e-6f);               // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
         s_coef = coef < 1.f ? coef : 1.f;
@@ -77,19 +82,29 @@ __global__ void __launch_bounds__(256) adam_kernel(Segs sg, const double* __rest
     const long long total = sg.first[sg.n];
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        int k = 0;
-        while (k + 1 < sg.n && sg.first[k + 1] <= i) ++k;
-        const long long j = i - sg.first[k];
-        const frl_adam_segment& s = sg.s[k];
-        const float g = s.grad[j] * coef;
-        float m = s.exp_avg[j];
-        float v = s.exp_avg_sq[j];
+        // segment lookup with compile-time indices (see sumsq_kernel)
+        float* pp = sg.s[0].params + i;
+        const float* gp = sg.s[0].grad + i;
+        float* mp = sg.s[0].exp_avg + i;
+        float* vp = sg.s[0].exp_avg_sq + i;
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+            if (k < sg.n && i >= sg.first[k]) {
+                const long long j = i - sg.first[k];
+                pp = sg.s[k].params + j;
+                gp = sg.s[k].grad + j;
+                mp = sg.s[k].exp_avg + j;
+                vp = sg.s[k].exp_avg_sq + j;
+            }
+        const float g = *gp * coef;
+        float m = *mp;
+        float v = *vp;
         m = m + (g - m) * sc.one_minus_b1;                         // exp_avg.lerp_(grad, 1 - beta1)
         v = v * sc.b2 + sc.one_minus_b2 * g * g;                   // mul_(beta2).addcmul_(g, g, 1 - beta2)
         const float denom = sqrtf(v) / sc.sqrt_bc2 + sc.eps;  // sqrt(v)/sqrt(bc2) + eps
-        s.params[j] = s.params[j] + sc.neg_step_size * (m / denom);
-        s.exp_avg[j] = m;
-        s.exp_avg_sq[j] = v;
+        *pp = *pp + sc.neg_step_size * (m / denom);
+        *mp = m;
+        *vp = v;
     }
 }
 

@@ -875,16 +875,21 @@ int launch_logprob_tc3(const ScoreArgs& a, int precision, cudaStream_t stream) {
         const long long img_tiles = ((tiles_per_role + 3) / 4) * 4;   // padding tiles of the last quad included
         const size_t img_bytes = (size_t)p.K0p * kRows * 2, need = (size_t)img_tiles * img_bytes;
         frl_net* nm = const_cast<frl_net*>(n0);
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        FRL_CUDA(cudaStreamIsCapturing(stream, &cap));
         if (nm->ws_x0s_bytes < need) {
+            if (cap != cudaStreamCaptureStatusNone) {
+                set_error("the wide-input operand workspace must grow: run one launch of this size before capturing a graph");
+                return FRL_ERR_UNSUPPORTED;
+            }
+            const size_t grow = std::max(need, nm->ws_x0s_bytes * 2);   // geometric: a growing batch retires O(log) buffers
             if (nm->ws_x0s) nm->retired.push_back(nm->ws_x0s);   // kept alive: see frl_net::retired
             nm->ws_x0s = nullptr;
             nm->ws_x0s_bytes = 0;
-            FRL_CUDA(cudaMalloc(&nm->ws_x0s, need));
-            nm->ws_x0s_bytes = need;
+            FRL_CUDA(cudaMalloc(&nm->ws_x0s, grow));
+            nm->ws_x0s_bytes = grow;
         }
         // the images are per launch: a launch on another stream (frl_score_host alternates two) waits for the previous reader
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        FRL_CUDA(cudaStreamIsCapturing(stream, &cap));
         if (!nm->x0s_event) FRL_CUDA(cudaEventCreateWithFlags(&nm->x0s_event, cudaEventDisableTiming));
         else if (cap == cudaStreamCaptureStatusNone) FRL_CUDA(cudaStreamWaitEvent(stream, nm->x0s_event, 0));
         const long long n_items = img_tiles * (p.K0p / 8) * kRows;

@@ -884,10 +884,10 @@ int launch_logprob_tc3x(const ScoreArgs& a, cudaStream_t stream) {
                 set_error("the wide-input operand workspace must grow: run one launch of this size before capturing a graph");
                 return FRL_ERR_UNSUPPORTED;
             }
+            const size_t grow = std::max(need, nm->ws_x0s_bytes * 2);   // geometric: a growing batch retires O(log) buffers
             if (nm->ws_x0s) nm->retired.push_back(nm->ws_x0s);   // kept alive: see frl_net::retired
             nm->ws_x0s = nullptr;
             nm->ws_x0s_bytes = 0;
-            const size_t grow = std::max(need, nm->ws_x0s_bytes * 2);
             FRL_CUDA(cudaMalloc(&nm->ws_x0s, grow));
             nm->ws_x0s_bytes = grow;
         }

@@ -781,8 +781,8 @@ struct RedParams {
     int accumulate;
 };
 
-__global__ void tc_reduce_kernel(RedParams rp, float* __restrict__ grad) {
-    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+__device__ __forceinline__ void reduce_main_body(const RedParams& rp, float* __restrict__ grad, const int block) {
+    const long long e = block * (long long)blockDim.x + threadIdx.x;
     if (e >= rp.n_params) return;
     int job, m, col;
     if (e < rp.n_trunk) {
@@ -802,7 +802,7 @@ __global__ void tc_reduce_kernel(RedParams rp, float* __restrict__ grad) {
         m = n;
     } else {
         int h = (rp.n_heads == 2 && e >= rp.off_wh[1]) ? 1 : 0;
-        if (e >= rp.off_bh[h]) return;   // head biases: tc_reduce_small_kernel
+        if (e >= rp.off_bh[h]) return;   // head biases: reduce_small_body
         const long long i = e - rp.off_wh[h];
         const int j = (int)(i / rp.H), k = (int)(i % rp.H);
         job = rp.depth;
@@ -820,13 +820,24 @@ __global__ void tc_reduce_kernel(RedParams rp, float* __restrict__ grad) {
 
 // block 0: loss;  block 1 + o: bias gradient of head output o
 // (the loss partials of tiles [0, n_part0) belong to term 0, the rest to term 1)
-__global__ void __launch_bounds__(256) tc_reduce_small_kernel(const double* __restrict__ lpart, const float* __restrict__ dvsum,
-                                                              int n_part, int n_part0, int NOp, RedParams rp, double inv_div0,
-                                                              double inv_div1, float* __restrict__ loss0,
-                                                              float* __restrict__ loss1, float* __restrict__ grad) {
+struct SmallParams {
+    const double* lpart;
+    const float* dvsum;
+    int n_part, n_part0, NOp;
+    double inv_div0, inv_div1;
+    float *loss0, *loss1;
+};
+// block 0: the two losses;  block 1 + o: bias gradient of head output o
+__device__ __forceinline__ void reduce_small_body(const SmallParams& sp, const RedParams& rp, float* __restrict__ grad, const int block) {
+    const double* __restrict__ lpart = sp.lpart;
+    const float* __restrict__ dvsum = sp.dvsum;
+    const int n_part = sp.n_part, n_part0 = sp.n_part0, NOp = sp.NOp;
+    const double inv_div0 = sp.inv_div0, inv_div1 = sp.inv_div1;
+    float* loss0 = sp.loss0;
+    float* loss1 = sp.loss1;
     __shared__ double sh[256];
     double acc = 0.0;
-    if (blockIdx.x == 0) {
+    if (block == 0) {
         double acc1 = 0.0;
         for (int i = threadIdx.x; i < n_part0; i += 256) acc += lpart[i];
         for (int i = n_part0 + threadIdx.x; i < n_part; i += 256) acc1 += lpart[i];
@@ -839,7 +850,7 @@ __global__ void __launch_bounds__(256) tc_reduce_small_kernel(const double* __re
         if (threadIdx.x == 0 && loss1) loss1[0] = (float)(sh[0] * inv_div1);
         __syncthreads();
     } else {
-        const int o = blockIdx.x - 1;
+        const int o = block - 1;
         for (int i = threadIdx.x; i < n_part; i += 256) acc += (double)dvsum[(size_t)i * NOp + o];
     }
     sh[threadIdx.x] = acc;
@@ -849,10 +860,10 @@ __global__ void __launch_bounds__(256) tc_reduce_small_kernel(const double* __re
         __syncthreads();
     }
     if (threadIdx.x != 0) return;
-    if (blockIdx.x == 0) {
+    if (block == 0) {
         if (loss0) loss0[0] = (float)(sh[0] * inv_div0);
     } else if (grad) {
-        const int o = blockIdx.x - 1;
+        const int o = block - 1;
         const int h = o / rp.a_dim, j = o % rp.a_dim;
         if (h < rp.n_heads) {
             const float v = (float)sh[0] * rp.scale;
@@ -860,6 +871,14 @@ __global__ void __launch_bounds__(256) tc_reduce_small_kernel(const double* __re
             *g = rp.accumulate ? *g + v : v;
         }
     }
+}
+
+// ONE launch for the whole reduction: blocks [0, main_blocks) the weight / trunk-bias gradients, the rest the losses and
+// the head-bias gradients
+__global__ void __launch_bounds__(256) tc_reduce_kernel(const __grid_constant__ RedParams rp, const __grid_constant__ SmallParams sp,
+                                                        float* __restrict__ grad, int main_blocks) {
+    if ((int)blockIdx.x < main_blocks) reduce_main_body(rp, grad, (int)blockIdx.x);
+    else reduce_small_body(sp, rp, grad, (int)blockIdx.x - main_blocks);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -917,8 +936,10 @@ static TrainPack train_pack_layout(const frl_net* net) {
 int tc_train_pack(frl_net* net, const float* params_dev, cudaStream_t st) {
     using namespace ttc;
     const TrainPack tp = train_pack_layout(net);
-    if (!net->pack_train) FRL_CUDA(cudaMalloc(&net->pack_train, tp.total));
-    FRL_CUDA(cudaMemsetAsync(net->pack_train, 0, tp.total, st));
+    if (!net->pack_train) {   // the padding of the images is written once: re-packs only rewrite the weights
+        FRL_CUDA(cudaMalloc(&net->pack_train, tp.total));
+        FRL_CUDA(cudaMemsetAsync(net->pack_train, 0, tp.total, st));
+    }
     const int H = net->cfg.hidden, depth = net->cfg.depth, A = net->cfg.a_dim;
     ImgTable tab{};
     long long total = 0;
@@ -1261,6 +1282,8 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     rp.scale = (float)final_scale;
     rp.accumulate = accumulate;
     for (int j = 0; j < n_jobs; ++j) { rp.part[j] = reinterpret_cast<const float*>(ws + o_part[j]); rp.ldp[j] = ldp[j]; }
+    const SmallParams small{lpart, dvsum, nt * 4, nt_of[0] * 4, NOp, inv_div[0], inv_div[1], terms[0].loss,
+                            n_terms > 1 ? terms[1].loss : nullptr};
 
     // ---- X0 tiles ----
     {
@@ -1330,8 +1353,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         for (int idx = 0; idx <= depth; ++idx)
             if ((rc = launch(idx)) != FRL_OK) return rc;
         if (!grad) {
-            tc_reduce_small_kernel<<<1, 256, 0, st>>>(lpart, dvsum, nt * 4, nt_of[0] * 4, NOp, rp, inv_div[0], inv_div[1], terms[0].loss,
-                                                      n_terms > 1 ? terms[1].loss : nullptr, nullptr);
+            tc_reduce_kernel<<<1, 256, 0, st>>>(rp, small, nullptr, 0);   // the losses only
             FRL_CUDA(cudaGetLastError());
             return FRL_OK;
         }
@@ -1345,9 +1367,8 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         tc_wgrad_kernel<<<dim3(n_splits_unfused, n_jobs), kWgradThreads, smem_bytes, st>>>(wp);
         FRL_CUDA(cudaGetLastError());
     }
-    tc_reduce_kernel<<<(unsigned)((net->n_params + 255) / 256), 256, 0, st>>>(rp, grad);
-    tc_reduce_small_kernel<<<1 + net->cfg.n_heads * A, 256, 0, st>>>(lpart, dvsum, nt * 4, nt_of[0] * 4, NOp, rp, inv_div[0], inv_div[1],
-                                                                     terms[0].loss, n_terms > 1 ? terms[1].loss : nullptr, grad);
+    const int main_blocks = (int)((net->n_params + 255) / 256);
+    tc_reduce_kernel<<<main_blocks + 1 + net->cfg.n_heads * A, 256, 0, st>>>(rp, small, grad, main_blocks);
     FRL_CUDA(cudaGetLastError());
     return FRL_OK;
 }
