@@ -58,6 +58,11 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ Segs 
                                                    AdamScalars sc, float* __restrict__ norm_out,
                                                    const long long* __restrict__ step_dev) {
     __shared__ float s_coef, s_sqrt_bc2, s_neg_step;
+    // total of the per-block partial sums: every block forms it with the same fixed tree (all threads load in parallel;
+    // a serial loop in thread 0 is ~75 dependent L2 round trips in EVERY block)
+    double part = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += blockDim.x) part += partial[i];
+    const double total_sq = block_sum(part);   // valid in thread 0
     if (threadIdx.x == 0) {
         s_sqrt_bc2 = sc.sqrt_bc2;
         s_neg_step = sc.neg_step_size;
@@ -66,11 +71,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ Segs 
             s_sqrt_bc2 = (float)sqrt(1.0 - pow(sc.beta2, st));
             s_neg_step = (float)(-sc.lr / (1.0 - pow(sc.beta1, st)));
         }
-        double t = 0.0;
-        for (int i = 0; i < n_partial; i += 4)   // same order in every block (four independent chains, then a fixed tree)
-            t += (partial[i] + (i + 1 < n_partial ? partial[i + 1] : 0.0)) +
-                 ((i + 2 < n_partial ? partial[i + 2] : 0.0) + (i + 3 < n_partial ? partial[i + 3] : 0.0));
-        const float norm = (float)sqrt(t);
+        const float norm = (float)sqrt(total_sq);
         float coef = sc.max_norm / (norm + 1e-6f);               // clip_grad_norm_: clamp(max_norm/(norm+1e-6), max=1)
         s_coef = coef < 1.f ? coef : 1.f;
         if (blockIdx.x == 0 && norm_out) norm_out[0] = norm;

@@ -186,7 +186,7 @@ def test_tc_training_curve_vs_reference(path):
         log.append(torch.stack(train_step(terms, opt, max_norm=1.0, precision="fp16")))
     curve = torch.stack(log).cpu().numpy()
     ref = g["curve"]
-    assert_close(curve[:50], ref[:50], 1.5e-2, "first steps")
+    assert_close(curve[:50], ref[:50], 1.5e-2, "first steps", kink_cap=1.5e-2)
     k = 50
     ma = lambda x: np.stack([np.convolve(x[:, j], np.ones(k) / k, mode="valid") for j in range(2)], 1)
     rel = np.abs(ma(curve) - ma(ref)) / np.abs(ma(ref))
