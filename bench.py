@@ -586,10 +586,14 @@ def run_ours(args):
     use_graph = os.environ.get("FRL_BENCH_NO_GRAPH", "0") != "1"
     use_nccl = os.environ.get("FRL_BENCH_NCCL", "0") == "1"
     peer_comm = None
+    peer_note = None
     if world > 1 and not use_nccl:
         from modril_b200.dist import PeerAllReduce
 
-        peer_comm = PeerAllReduce(model.net.flat_params().numel() + 64, device=device)
+        try:
+            peer_comm = PeerAllReduce(model.net.flat_params().numel() + 64, device=device)
+        except RuntimeError as e:   # raised on every rank together: all of them take the NCCL route
+            peer_comm, use_nccl, peer_note = None, True, str(e)[:300]
     grp = ((peer_comm if peer_comm is not None else dist.group.WORLD), world) if world > 1 else None
     opt = FusedAdam([model.net], lr=1e-4, capturable=use_graph)
 
@@ -797,6 +801,7 @@ def run_ours(args):
             "device-side one-shot all-reduce of the flat fp32 gradient over NVLink peer memory (csrc/comm.cu), inside the graph"
             if peer_comm is not None else "NCCL all-reduce of the flat grad, launched from Python between two graphs"),
         "collective_timeouts": peer_comm.timeouts() if peer_comm is not None else None,
+        "collective_fallback": peer_note,
         "cpu_baseline": cpu_train}
 
     line = {

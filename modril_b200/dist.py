@@ -61,7 +61,6 @@ class PeerAllReduce:
         self.max_floats = int(max_floats)
         self._h = None
         if _connect:
-            self._create()
             self._connect_group()
 
     def _create(self):
@@ -72,18 +71,38 @@ class PeerAllReduce:
         self._h = h
 
     def _connect_group(self):
+        """Create the local buffer, pass the handles around, map the peers.  A failure on ANY rank (no peer access, IPC
+        disabled in a container, ...) raises on EVERY rank, after the same number of collectives, so that callers can fall
+        back to NCCL together instead of dead-locking."""
         L = self._native.lib()
-        mine = (C.c_ubyte * 64)()
-        self._native.check(L.frl_comm_handle(self._h, mine), "frl_comm_handle")
+        err, mine = None, (C.c_ubyte * 64)()
+        try:
+            self._create()
+            self._native.check(L.frl_comm_handle(self._h, mine), "frl_comm_handle")
+        except Exception as e:   # noqa: BLE001 - reported to all ranks below
+            err = f"rank {self.rank}: {e}"
         handles = [None] * self.world
         if self.world > 1:
-            dist.all_gather_object(handles, bytes(mine), group=self.group)
+            dist.all_gather_object(handles, (err, bytes(mine)), group=self.group)
         else:
-            handles[0] = bytes(mine)
-        blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
-        self._native.check(L.frl_comm_connect(self._h, blob), "frl_comm_connect")
-        if self.world > 1:
-            dist.barrier(group=self.group)   # every rank has mapped every buffer before the first flag is written
+            handles[0] = (err, bytes(mine))
+        errs = [h[0] for h in handles if h[0]]
+        if not errs:
+            try:
+                blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(h[1] for h in handles))
+                self._native.check(L.frl_comm_connect(self._h, blob), "frl_comm_connect")
+            except Exception as e:   # noqa: BLE001
+                err = f"rank {self.rank}: {e}"
+            if self.world > 1:
+                # every rank has mapped every buffer before the first cell is written -- and learns of a failure elsewhere
+                oks = [None] * self.world
+                dist.all_gather_object(oks, err, group=self.group)
+                errs = [e for e in oks if e]
+            elif err:
+                errs = [err]
+        if errs:
+            self.close()
+            raise RuntimeError("PeerAllReduce: peer-memory exchange unavailable (" + "; ".join(errs) + ")")
 
     @classmethod
     def local_group(cls, devices, max_floats: int):
