@@ -798,7 +798,7 @@ def run_ours(args):
         "e2e": {"value": train_e2e, "unit": "samples/s", "h2d_bytes_per_step": train_h2d, "d2h_bytes_per_step": 8 * world,
                 "api": e2e_api},
         "collective": "none" if world == 1 else (
-            "device-side one-shot all-reduce of the flat fp32 gradient over NVLink peer memory (csrc/comm.cu), inside the graph"
+            "device-side LL two-shot all-reduce of the flat fp32 gradient over NVLink peer memory (csrc/comm.cu), one kernel inside the update's graph"
             if peer_comm is not None else "NCCL all-reduce of the flat grad, launched from Python between two graphs"),
         "collective_timeouts": peer_comm.timeouts() if peer_comm is not None else None,
         "collective_fallback": peer_note,
