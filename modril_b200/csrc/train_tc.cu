@@ -553,7 +553,8 @@ struct WgradJob {
 };
 struct WgradParams {
     WgradJob job[kMaxJobs];
-    int n_jobs, n_tiles, n_splits;
+    int first[kMaxJobs + 1];   // job j owns the CTAs [first[j], first[j + 1]): its splits, sized by the bytes it moves per tile
+    int n_jobs, n_tiles;
 };
 constexpr uint32_t kWgPSlot = 32768, kWgQSlot = 65536;
 constexpr uint32_t kWgPOff = 1024, kWgQOff = kWgPOff + 2 * kWgPSlot;
@@ -734,7 +735,9 @@ __device__ __forceinline__ void wgrad_body(const WgradJob& jb, const int n_tiles
 }
 
 __global__ void __launch_bounds__(kWgradThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
-    wgrad_body(p.job[blockIdx.y], p.n_tiles, (int)blockIdx.x, (int)gridDim.x);
+    int j = 0;
+    while (j + 1 < p.n_jobs && (int)blockIdx.x >= p.first[j + 1]) ++j;
+    wgrad_body(p.job[j], p.n_tiles, (int)blockIdx.x - p.first[j], p.first[j + 1] - p.first[j]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1088,9 +1091,18 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         cost[n_layer_stages + depth] = c_wh + wg * NOp / H;
         size_pools(cost, std::min(sms, env_int("FRL_FUSED_CTAS", sms)), &pool);
     }
-    const int n_splits_unfused = std::max(1, std::min(nt, sms / n_jobs));
+    // per-layer launches: the wgrad kernel is HBM-bound, so a job gets CTAs in proportion to the bytes it reads per tile (a
+    // trunk layer: two 64 KB tiles; layer 0 and the heads: one 64 KB tile and a narrow one)
     int n_splits[kMaxJobs];
-    for (int j = 0; j < n_jobs; ++j) n_splits[j] = fused ? std::min(pool[n_layer_stages + j], nt) : n_splits_unfused;
+    if (fused) {
+        for (int j = 0; j < n_jobs; ++j) n_splits[j] = std::min(pool[n_layer_stages + j], nt);
+    } else {
+        std::vector<double> bytes(n_jobs);
+        for (int j = 0; j < n_jobs; ++j) bytes[j] = (double)H + (j == 0 ? K0p : (j == depth ? NOp : H));
+        std::vector<int> share;
+        size_pools(bytes, std::max(n_jobs, sms), &share);
+        for (int j = 0; j < n_jobs; ++j) n_splits[j] = std::max(1, std::min(share[j], nt));
+    }
 
     // ---- rings (fused): slots per stream ~ (stages between the producer and the last consumer + 2) x tiles in flight per stage
     int maxpool = 1;
@@ -1360,11 +1372,13 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         for (int idx = depth + 1; idx < n_layer_stages; ++idx)
             if ((rc = launch(idx)) != FRL_OK) return rc;
         WgradParams wp{};
-        wp.n_jobs = n_jobs; wp.n_tiles = nt; wp.n_splits = n_splits_unfused;
-        for (int l = 0; l < n_jobs; ++l) wp.job[l] = WJ[l];
+        wp.n_jobs = n_jobs; wp.n_tiles = nt;
+        int first = 0;
+        for (int l = 0; l < n_jobs; ++l) { wp.job[l] = WJ[l]; wp.first[l] = first; first += n_splits[l]; }
+        wp.first[n_jobs] = first;
         const size_t smem_bytes = kWgSmemBytes;
         FRL_CUDA(set_smem_attr(tc_wgrad_kernel, device, (int)smem_bytes));
-        tc_wgrad_kernel<<<dim3(n_splits_unfused, n_jobs), kWgradThreads, smem_bytes, st>>>(wp);
+        tc_wgrad_kernel<<<first, kWgradThreads, smem_bytes, st>>>(wp);
         FRL_CUDA(cudaGetLastError());
     }
     const int main_blocks = (int)((net->n_params + 255) / 256);
