@@ -139,6 +139,44 @@ __device__ __noinline__ void wait_ge(const unsigned* p, unsigned target, unsigne
 __device__ __forceinline__ void wait_ready(const Edge& e, int tile, unsigned* err, unsigned err0) {
     if (e.ready) wait_ge(e.ready + e.slot(tile), (e.use(tile) + 1) * e.ready_per_tile, err, err0);
 }
+// The same with the counter value read one tile EARLIER (relaxed, so that the load thread does not sit out an L2 round trip
+// per tile and stream): if the old value already says "published", an acquire fence orders the copies behind it.
+__device__ __forceinline__ unsigned probe_ready(const Edge& e, int tile, int n_tiles) {
+    return (e.ready && tile < n_tiles) ? ld_relaxed_gpu(e.ready + e.slot(tile)) : 0u;
+}
+// Relaxed polling (FRL_FUSED_POLL=1 builds use it; see the note at kRelaxedPoll).
+__device__ __noinline__ void wait_ge_relaxed(const unsigned* p, unsigned target, unsigned* err, unsigned err0) {
+    if ((int)(ld_relaxed_gpu(p) - target) >= 0) return;
+    const long long t0 = clock64();
+    while ((int)(ld_relaxed_gpu(p) - target) < 0) {
+        __nanosleep(32);
+        if (err && ld_relaxed_gpu(err) != err0) return;
+        if (clock64() - t0 > kSpinLimit) {
+            if (err) atomicAdd(err, 1u);
+            return;
+        }
+    }
+}
+// An acquire load (or an acquire fence) in the load thread costs 1.5 - 3 k cycles per tile here -- the membar it implies
+// waits behind the 64 KB of epilogue stores the same SM has in flight -- which is as long as a whole tile takes.  With
+// kRelaxedPoll the load thread polls the counter with relaxed gpu-scope loads (served by the L2) and issues the bulk copies
+// behind the control dependency: the producer's publisher fenced and RELEASED the tile before it bumped the counter, so the
+// data are in the L2 when the new counter value is; the copies read the L2 (never an L1 line), and fence.proxy.async
+// orders them behind the poll in this thread.
+#ifndef FRL_FUSED_RELAXED_POLL
+#define FRL_FUSED_RELAXED_POLL 1
+#endif
+constexpr bool kRelaxedPoll = FRL_FUSED_RELAXED_POLL != 0;
+__device__ __forceinline__ void wait_ready_probed(const Edge& e, int tile, unsigned probe, unsigned* err, unsigned err0) {
+    if (!e.ready) return;
+    const unsigned target = (e.use(tile) + 1) * e.ready_per_tile;
+    if (kRelaxedPoll && e.done == nullptr) {   // (measured: helps the chains of mode 2, hurts the ring-reusing kernel of mode 1)
+        if ((int)(probe - target) >= 0) return;
+        wait_ge_relaxed(e.ready + e.slot(tile), target, err, err0);
+    } else {
+        wait_ge(e.ready + e.slot(tile), target, err, err0);
+    }
+}
 // Slot reuse: the consumers bump `done` after their copy of the tile has LANDED in their shared memory, so nothing the
 // producer writes afterwards can reach them: a relaxed poll is enough (the stores depend on it through control flow).
 // `probe` is the counter value read one tile earlier (its latency is hidden behind that tile's epilogue).
@@ -265,12 +303,16 @@ __device__ __forceinline__ void layer_body(const LayerParams& p, const int rank,
             uint32_t phase = 0;
             long long t_wait = 0, t_ring = 0;
             const long long t_begin = clock64();
+            // (flagged streams are walked forwards: reverse == 0)
+            unsigned pr_in = probe_ready(p.in, rank, p.n_tiles), pr_mask = EPI == EPI_MASK ? probe_ready(p.mask, rank, p.n_tiles) : 0u;
             for (int it = rank; it < p.n_tiles; it += pool) {
                 const int tile = p.reverse ? p.n_tiles - 1 - it : it;
                 // the tile (and, for the dgrad stages, the masks that its epilogue will read) has been published
                 const long long tw = clock64();
-                wait_ready(p.in, tile, p.err, err0);
-                if (EPI == EPI_MASK) wait_ready(p.mask, tile, p.err, err0);
+                wait_ready_probed(p.in, tile, pr_in, p.err, err0);
+                if (EPI == EPI_MASK) wait_ready_probed(p.mask, tile, pr_mask, p.err, err0);
+                pr_in = probe_ready(p.in, it + pool, p.n_tiles);                         // next tile's counters: in flight while
+                if (EPI == EPI_MASK) pr_mask = probe_ready(p.mask, it + pool, p.n_tiles);   // this tile's chunks are issued
                 t_wait += clock64() - tw;
                 if (p.in.ready) fence_proxy_async_all();   // other SMs' generic-proxy stores -> this bulk (async-proxy) read
                 const uint8_t* src = p.in.tiles + (size_t)p.in.slot(tile) * p.in.slot_bytes;
@@ -610,10 +652,13 @@ __device__ __forceinline__ void wgrad_body(const WgradJob& jb, const int n_tiles
             };
             long long t_wait = 0;
             const long long t_begin = clock64();
+            unsigned pr_p = probe_ready(jb.P, t0, t1), pr_q = probe_ready(jb.Q, t0, t1);
             for (int tile = t0; tile < t1; tile += dt) {
                 const long long tw = clock64();
-                wait_ready(jb.P, tile, jb.err, err0);
-                wait_ready(jb.Q, tile, jb.err, err0);
+                wait_ready_probed(jb.P, tile, pr_p, jb.err, err0);
+                wait_ready_probed(jb.Q, tile, pr_q, jb.err, err0);
+                pr_p = probe_ready(jb.P, tile + dt, t1);
+                pr_q = probe_ready(jb.Q, tile + dt, t1);
                 t_wait += clock64() - tw;
                 if (jb.P.ready || jb.Q.ready) fence_proxy_async_all();
                 load_p(tile, 0);
@@ -1067,16 +1112,23 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     const int n_jobs = depth + 1;                 // trunk layers + heads
     const int n_layer_stages = 2 * depth + 1;     // forward 0..depth-1, heads + loss, dgrad heads, dgrad depth-1..1
     const int n_stages_total = n_layer_stages + n_jobs;
-    // FRL_TRAIN_FUSED=1 selects the dataflow kernel (every stage resident at once).  Measured on a B200 (maze, 2 x 65536
-    // rows, profiles/r02_fused_train.md): activations stay in L2 and its stages run ~2x faster per tile than the HBM-fed
-    // per-layer kernels, but 14 stage pools of 7-12 CTAs fill, drain and balance badly at ~90 tiles per CTA: 0.42 ms per
-    // update against 0.35 ms for the per-layer launches, which therefore remain the default.
-    const bool fused = grad != nullptr && sms >= 2 * n_stages_total && env_int("FRL_TRAIN_FUSED", 0) != 0;
+    // How the GEMM part is launched (FRL_TRAIN_FUSED):
+    //   0  one kernel per layer GEMM (11 launches), every tile through HBM between them;
+    //   1  ONE dataflow kernel for everything (tiles in L2 rings; profiles/r02_fused_train.md: 210 B of HBM per row, but ten
+    //      stages deep with 7-12 CTAs per stage it fills, drains and balances badly: 0.42 ms against 0.33 ms);
+    //   2  two SHORT dataflow kernels -- the forward chain [F_0 .. F_{depth-1}, heads + loss] and the dgrad chain
+    //      [dgrad heads, D_{depth-1} .. D_1] -- each on all SMs, then the stand-alone wgrad kernel.  Inside a chain a tile
+    //      goes to the next stage through the L2 (ready flags, no slot reuse: every tile is also written out for wgrad and
+    //      the masks), so the chains read almost nothing from HBM and run L2-fed; only wgrad streams the tiles back in.
+    const int want_mode = env_int("FRL_TRAIN_FUSED", 0);
+    const int mode = (grad != nullptr && sms >= 2 * n_stages_total) ? want_mode : 0;
+    const bool fused = mode == 1;        // everything in one kernel, ring slots reused
+    const bool chains = mode == 2;       // two chain kernels + wgrad kernel, plain per-tile arrays with ready flags
 
-    // ---- stage pools (fused) / split count (per-layer launches) ----
+    // ---- stage pools (dataflow kernels) / split count (per-layer launches) ----
     // stage order: [F_0 .. F_{depth-1}] [LOSS] [DH] [D_{depth-1} .. D_1] [W_0 .. W_{depth-1}] [W_heads]
     std::vector<int> pool(n_stages_total, 1);
-    if (fused) {
+    if (fused || chains) {
         std::vector<double> cost(n_stages_total, 0.0);
         // cycles-per-tile estimates (relative weights): measured per-tile times of the stages on a B200
         const double heavy = env_int("FRL_FUSED_COST_GEMM", 2850), wg = env_int("FRL_FUSED_COST_WGRAD", 2500);
@@ -1089,7 +1141,17 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         for (int l = depth - 1; l >= 1; --l) cost[depth + 2 + (depth - 1 - l)] = heavy;
         for (int l = 0; l < depth; ++l) cost[n_layer_stages + l] = l == 0 ? c_w0 + wg * K0p / H : wg;
         cost[n_layer_stages + depth] = c_wh + wg * NOp / H;
-        size_pools(cost, std::min(sms, env_int("FRL_FUSED_CTAS", sms)), &pool);
+        const int budget = std::min(sms, env_int("FRL_FUSED_CTAS", sms));
+        if (fused) {
+            size_pools(cost, budget, &pool);
+        } else {   // every chain gets all the SMs
+            std::vector<int> part;
+            const std::vector<double> fwd(cost.begin(), cost.begin() + depth + 1), bwd(cost.begin() + depth + 1, cost.begin() + n_layer_stages);
+            size_pools(fwd, budget, &part);
+            std::copy(part.begin(), part.end(), pool.begin());
+            size_pools(bwd, budget, &part);
+            std::copy(part.begin(), part.end(), pool.begin() + depth + 1);
+        }
     }
     // per-layer launches: the wgrad kernel is HBM-bound, so a job gets CTAs in proportion to the bytes it reads per tile (a
     // trunk layer: two 64 KB tiles; layer 0 and the heads: one 64 KB tile and a narrow one)
@@ -1097,7 +1159,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     if (fused) {
         for (int j = 0; j < n_jobs; ++j) n_splits[j] = std::min(pool[n_layer_stages + j], nt);
     } else {
-        std::vector<double> bytes(n_jobs);
+        std::vector<double> bytes(n_jobs);   // (also mode 2: its wgrad is the stand-alone kernel)
         for (int j = 0; j < n_jobs; ++j) bytes[j] = (double)H + (j == 0 ? K0p : (j == depth ? NOp : H));
         std::vector<int> share;
         size_pools(bytes, std::max(n_jobs, sms), &share);
@@ -1137,7 +1199,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     // flags: ready / done counters of every stream
     size_t n_flags = 0;
     size_t f_h[kMaxDepth], f_dz[kMaxDepth], f_dv = 0;
-    if (fused) {
+    if (fused || chains) {
         for (int l = 0; l < depth; ++l) { f_h[l] = n_flags; n_flags += 2 * (size_t)R_h[l]; }
         for (int l = 0; l < depth; ++l) { f_dz[l] = n_flags; n_flags += 2 * (size_t)R_dz[l]; }
         f_dv = n_flags; n_flags += (size_t)nt;
@@ -1160,13 +1222,13 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         FRL_CUDA(cudaMemsetAsync(err, 0, 2 * sizeof(unsigned), st));
         net->train_flags = err;
     }
-    if (fused) {
+    if (fused || chains) {
         FRL_CUDA(cudaMemsetAsync(flags, 0, n_flags * sizeof(unsigned), st));
         FRL_CUDA(cudaMemcpyAsync(err + 1, err, sizeof(unsigned), cudaMemcpyDeviceToDevice, st));
     }
 
     // FRL_FUSED_TRACE=file: per-CTA cycle counters of one launch (synchronises; debugging only)
-    const char* trace_path = fused ? getenv("FRL_FUSED_TRACE") : nullptr;
+    const char* trace_path = (fused || chains) ? getenv("FRL_FUSED_TRACE") : nullptr;
     unsigned long long* trace_dev = nullptr;
     if (trace_path && *trace_path) {
         FRL_CUDA(cudaMalloc(&trace_dev, (size_t)sms * 8 * sizeof(unsigned long long)));
@@ -1188,14 +1250,18 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         e_h[l].bits_words = (uint32_t)bitsW;
         e_h[l].bits_R = nt;
         e_dz[l] = plain(o_dz[l], tileH, R_dz[l]);
-        if (fused) {
-            e_h[l].ready = flags + f_h[l]; e_h[l].done = flags + f_h[l] + R_h[l];
+        if (fused || chains) {
+            e_h[l].ready = flags + f_h[l];
+            e_dz[l].ready = flags + f_dz[l];
+        }
+        if (fused) {   // ring slots are reused: the consumers give them back
+            e_h[l].done = flags + f_h[l] + R_h[l];
             e_h[l].done_per_tile = 2;   // next forward stage (or heads) and wgrad of the next layer (or heads)
-            e_dz[l].ready = flags + f_dz[l]; e_dz[l].done = flags + f_dz[l] + R_dz[l];
+            e_dz[l].done = flags + f_dz[l] + R_dz[l];
             e_dz[l].done_per_tile = l >= 1 ? 2 : 1;   // dgrad through layer l (l >= 1) and wgrad of layer l
         }
     }
-    if (fused) e_dv.ready = flags + f_dv;   // one slot per tile: never reused
+    if (fused || chains) e_dv.ready = flags + f_dv;   // one slot per tile: never reused
 
     // ---- stage parameters ----
     LayerParams LP[kMaxLayerStages] = {};
@@ -1203,13 +1269,13 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
     int n_launch = 0;   // (per-layer launches) the kernels alternate their tile order (see LayerParams::reverse)
     auto finish_layer = [&](LayerParams& p, int epi, int idx) -> int {
         p.n_tiles = nt;
-        p.err = fused ? err : nullptr;
+        p.err = (fused || chains) ? err : nullptr;
         p.trace = trace_dev;
-        p.reverse = fused ? 0 : ((n_launch++) & 1);
+        p.reverse = (fused || chains) ? 0 : ((n_launch++) & 1);
         const size_t base = 2048 + ((size_t)p.K * p.N * 2 + 1023) / 1024 * 1024;
         int stages = (int)(((size_t)di.max_smem - base) / kChunkBytes);
         stages = std::min(stages, kMaxStages);
-        if (fused) stages = std::min(stages, std::max(2, env_int("FRL_FUSED_SMEM_STAGES", kMaxStages)));
+        if (fused || chains) stages = std::min(stages, std::max(2, env_int("FRL_FUSED_SMEM_STAGES", kMaxStages)));
         if (stages < 2) {
             set_error("tensor-core training: layer does not fit in shared memory");
             return FRL_ERR_UNSUPPORTED;
@@ -1280,7 +1346,7 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         else if (l == depth) { jb.Q = e_dv; jb.FQ = NOp; }
         else { jb.Q = e_h[l - 1]; jb.FQ = H; }
         jb.partial = reinterpret_cast<float*>(ws + o_part[l]);
-        jb.err = fused ? err : nullptr;
+        jb.err = (fused || chains) ? err : nullptr;
         jb.trace = trace_dev;
     }
 
@@ -1307,6 +1373,36 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         FRL_CUDA(cudaGetLastError());
     }
 
+    auto stage_name = [&](int i, char* name, size_t n) {
+        if (i < depth) snprintf(name, n, "F%d", i);
+        else if (i == depth) snprintf(name, n, "LOSS");
+        else if (i == depth + 1) snprintf(name, n, "DH");
+        else if (i < n_layer_stages) snprintf(name, n, "D%d", depth - 1 - (i - depth - 2));
+        else snprintf(name, n, "W%d", i - n_layer_stages);
+    };
+    // FRL_FUSED_TRACE: cycle counters of the stages [s0, s1) of the dataflow kernel just launched (synchronises)
+    auto dump_trace = [&](int s0, int s1, const int* first, const char* fmode) -> int {
+        if (!trace_dev) return FRL_OK;
+        std::vector<unsigned long long> h((size_t)sms * 8);
+        FRL_CUDA(cudaStreamSynchronize(st));
+        FRL_CUDA(cudaMemcpy(h.data(), trace_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        FRL_CUDA(cudaMemset(trace_dev, 0, h.size() * sizeof(unsigned long long)));
+        if (FILE* f = fopen(trace_path, fmode)) {
+            fprintf(f, "# tiles %d; stage: F<l> forward, LOSS, DH dgrad heads, D<l> dgrad through layer l, W<l> wgrad (W%d = heads)\n", nt, depth);
+            fprintf(f, "# cta stage rank pool | load thread: total wait_in wait_smem_slot | mma: wait_acc wait_chunks | epilogue warp 0: wait_out_slot wait_acc publish\n");
+            for (int i = s0; i < s1; ++i) {
+                char name[16];
+                stage_name(i, name, sizeof name);
+                for (int r = 0; r < pool[i]; ++r) {
+                    const unsigned long long* t = &h[(size_t)(first[i - s0] + r) * 8];
+                    fprintf(f, "%3d %-4s %2d %2d | %8llu %8llu %8llu | %8llu %8llu | %8llu %8llu %8llu\n", first[i - s0] + r, name, r, pool[i],
+                            t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+                }
+            }
+            fclose(f);
+        }
+        return FRL_OK;
+    };
     if (fused) {
         FusedParams fp{};
         fp.n_layer_stages = n_layer_stages; fp.n_jobs = n_jobs; fp.n_tiles = nt;
@@ -1318,30 +1414,36 @@ int cfm_loss_grad_tc(frl_net* net, const CfmTerm* terms, int n_terms, int accumu
         FRL_CUDA(set_smem_attr(tc_fused_kernel, device, di.max_smem));
         tc_fused_kernel<<<first, kLayerThreads, (size_t)di.max_smem, st>>>(fp);
         FRL_CUDA(cudaGetLastError());
-        if (trace_dev) {
-            std::vector<unsigned long long> h((size_t)sms * 8);
-            FRL_CUDA(cudaStreamSynchronize(st));
-            FRL_CUDA(cudaMemcpy(h.data(), trace_dev, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-            FRL_CUDA(cudaFree(trace_dev));
-            if (FILE* f = fopen(trace_path, "w")) {
-                fprintf(f, "# tiles %d; stage: F<l> forward, LOSS, DH dgrad heads, D<l> dgrad through layer l, W<l> wgrad (W%d = heads)\n", nt, depth);
-                fprintf(f, "# cta stage rank pool | load thread: total wait_in wait_smem_slot | mma: wait_acc wait_chunks | epilogue warp 0: wait_out_slot wait_acc fence\n");
-                for (int i = 0; i < n_stages_total; ++i) {
-                    char name[16];
-                    if (i < depth) snprintf(name, sizeof name, "F%d", i);
-                    else if (i == depth) snprintf(name, sizeof name, "LOSS");
-                    else if (i == depth + 1) snprintf(name, sizeof name, "DH");
-                    else if (i < n_layer_stages) snprintf(name, sizeof name, "D%d", depth - 1 - (i - depth - 2));
-                    else snprintf(name, sizeof name, "W%d", i - n_layer_stages);
-                    for (int r = 0; r < pool[i]; ++r) {
-                        const unsigned long long* t = &h[(size_t)(fp.first[i] + r) * 8];
-                        fprintf(f, "%3d %-4s %2d %2d | %8llu %8llu %8llu | %8llu %8llu | %8llu %8llu %8llu\n", fp.first[i] + r, name, r, pool[i],
-                                t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
-                    }
-                }
-                fclose(f);
+        if ((rc = dump_trace(0, n_stages_total, fp.first, "w")) != FRL_OK) return rc;
+        if (trace_dev) FRL_CUDA(cudaFree(trace_dev));
+    } else if (chains) {
+        auto launch_chain = [&](int s0, int s1) -> int {   // layer stages [s0, s1) as one dataflow kernel on all SMs
+            FusedParams fp{};
+            fp.n_layer_stages = s1 - s0; fp.n_jobs = 0; fp.n_tiles = nt;
+            int first = 0;
+            for (int i = s0; i < s1; ++i) {
+                fp.layer[i - s0] = LP[i];
+                fp.epi[i - s0] = epi_of[i];
+                fp.first[i - s0] = first;
+                first += pool[i];
             }
-        }
+            fp.first[s1 - s0] = first;
+            FRL_CUDA(set_smem_attr(tc_fused_kernel, device, di.max_smem));
+            tc_fused_kernel<<<first, kLayerThreads, (size_t)di.max_smem, st>>>(fp);
+            FRL_CUDA(cudaGetLastError());
+            return dump_trace(s0, s1, fp.first, s0 == 0 ? "w" : "a");
+        };
+        if ((rc = launch_chain(0, depth + 1)) != FRL_OK) return rc;                  // forward chain + heads / loss
+        if ((rc = launch_chain(depth + 1, n_layer_stages)) != FRL_OK) return rc;     // dgrad chain
+        WgradParams wp{};
+        wp.n_jobs = n_jobs; wp.n_tiles = nt;
+        int first = 0;
+        for (int l = 0; l < n_jobs; ++l) { wp.job[l] = WJ[l]; wp.first[l] = first; first += n_splits[l]; }
+        wp.first[n_jobs] = first;
+        FRL_CUDA(set_smem_attr(tc_wgrad_kernel, device, (int)kWgSmemBytes));
+        tc_wgrad_kernel<<<first, kWgradThreads, kWgSmemBytes, st>>>(wp);
+        FRL_CUDA(cudaGetLastError());
+        if (trace_dev) FRL_CUDA(cudaFree(trace_dev));
     } else {
         auto launch = [&](int idx) -> int {
             const LayerParams& p = LP[idx];

@@ -285,15 +285,16 @@ def test_train_step_graph_equals_eager_steps_and_scoring_sees_the_new_weights(pr
 
 
 def test_fused_dataflow_kernel_matches_the_per_layer_launches(monkeypatch):
-    """FRL_TRAIN_FUSED=1 (one persistent kernel, every GEMM stage resident on its own SMs, tiles handed over through L2
-    rings) computes the same stacked-pair gradient as the per-layer launches: identical MMAs per tile, identical fixed-order
-    reduction of per-tile partials -- only the grouping of row tiles into wgrad partial sums differs (fp32 round-off)."""
+    """The dataflow launches -- FRL_TRAIN_FUSED=1: one persistent kernel, every GEMM stage resident on its own SMs, tiles
+    handed over through L2 rings; =2: a forward-chain and a dgrad-chain kernel + the stand-alone wgrad kernel -- compute the
+    same stacked-pair gradient as the per-layer launches (=0): identical MMAs per tile, identical fixed-order reduction of
+    per-tile partials; only the grouping of row tiles into wgrad partial sums may differ (fp32 round-off)."""
     from modril_b200.flowril import FusedAdam, train_step
 
     spec = cf.NetSpec(17, 6, 256, 4, 2)
     flat = cf.make_params(spec, 8, 1.0)
     grads, losses = {}, {}
-    for fused in ("0", "1"):
+    for fused in ("0", "1", "2"):
         monkeypatch.setenv("FRL_TRAIN_FUSED", fused)
         m = build_model(spec, flat)
         opt = FusedAdam([m.net], lr=0.0)   # the weights stay put: three launches on identical weights
@@ -306,5 +307,6 @@ def test_fused_dataflow_kernel_matches_the_per_layer_launches(monkeypatch):
             losses[fused] = [float(x) for x in train_step(terms, opt, 1.0, precision="fp16")]
         grads[fused] = m.net.flat_grad().double().cpu().numpy()
         assert m.net.train_timeouts() == 0
-    assert losses["0"] == pytest.approx(losses["1"], rel=1e-6)
-    assert _rel_l2(grads["1"], grads["0"]) <= 2e-6
+    for mode in ("1", "2"):
+        assert losses["0"] == pytest.approx(losses[mode], rel=1e-6)
+        assert _rel_l2(grads[mode], grads["0"]) <= 2e-6
