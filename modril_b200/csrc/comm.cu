@@ -15,6 +15,7 @@
 // every peer's flag e + 1, which a peer raises only after its reduce of epoch e has been enqueued behind its publish
 // e + 1 ... i.e. after it finished reading slot e & 1), so slot e & 1 is never overwritten while someone reads it.
 // The vector is < 1 MB (the net has 0.2 M parameters): 8 ranks read 7 x 0.8 MB each, ~10 us on NVLink 5.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -334,10 +335,33 @@ __global__ void __launch_bounds__(kCommThreads) comm_ll_kernel(const __grid_cons
         if ((int)(q / per) != rank) return;
         const float4 mine = ld_quad(src, valid, vec);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < world; ++r) {
-            float4 v = mine;
-            if (r != rank && !ld_ll(peer[rank] + off1 + ((size_t)r * per + (size_t)(q - rank * per)) * 32, flag, spin_limit, &v)) timed_out = true;
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        for (int r0 = 0; r0 < world; r0 += 8) {   // up to eight peers' cells polled together (their loads overlap), summed in rank order
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u;
+                v[u] = mine;
+                if (r < world && r != rank) {   // first probe of every cell without waiting on the others
+                    const uint8_t* cell = peer[rank] + off1 + ((size_t)r * per + (size_t)(q - rank * per)) * 32;
+                    uint4 a, b;
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(cell) : "memory");
+                    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(cell + 16) : "memory");
+                    if (a.y == flag && a.w == flag && b.y == flag && b.w == flag)
+                        v[u] = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(b.x), __uint_as_float(b.z));
+                    else
+                        v[u].x = __int_as_float(0x7fc00001);   // marker: not there yet (re-polled below; a real value is overwritten anyway)
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u;
+                if (r >= world) continue;
+                if (r != rank && __float_as_int(v[u].x) == 0x7fc00001) {
+                    // (a genuine payload with exactly this NaN bit pattern is simply re-read once: ld_ll returns it as it is)
+                    if (!ld_ll(peer[rank] + off1 + ((size_t)r * per + (size_t)(q - rank * per)) * 32, flag, spin_limit, &v[u])) timed_out = true;
+                }
+                acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+            }
         }
         st_quad(src, acc, valid, vec);
         for (int r = 0; r < world; ++r)
@@ -492,8 +516,11 @@ extern "C" int frl_comm_allreduce(frl_comm* c, float* const* bufs, const long lo
     FRL_CUDA(cudaSetDevice(c->device));
     const long long spin_limit = 20ll * 1000 * 1000 * 1000;
     if (a != "two_shot") {
-        comm_ll_kernel<<<kCommBlocks, kCommThreads, 0, (cudaStream_t)stream>>>(b, c->peer_dev, c->rank, c->world, c->max_floats, c->state,
-                                                                               spin_limit);
+        // no barrier inside: any grid size is safe; enough threads for one quad per thread and pass (capped at two CTAs per SM)
+        const long long quads = b.first[b.n] / 4;
+        const int blocks = (int)std::max<long long>(1, std::min<long long>((quads + kCommThreads - 1) / kCommThreads, 296));
+        comm_ll_kernel<<<blocks, kCommThreads, 0, (cudaStream_t)stream>>>(b, c->peer_dev, c->rank, c->world, c->max_floats, c->state,
+                                                                         spin_limit);
         FRL_CUDA(cudaGetLastError());
         return FRL_OK;
     }
