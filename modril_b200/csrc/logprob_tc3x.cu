@@ -188,7 +188,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
             mbar_init(w_full(s), cta_rank == 0 ? 2 : 1);   // leader: own producer + the peer's relay
             mbar_init(w_empty(s), 2);                      // one commit per stream
         }
-        for (int kq = 0; kq < 4; ++kq) mbar_init(a_ready(kq), kEpiWarps);   // the 4 warps of that column slice in each of the two CTAs
+        for (int kq = 0; kq < 4; ++kq) mbar_init(a_ready(kq), 2 * kEpiWarps);   // every epilogue warp of both CTAs writes a part of every operand quarter
         for (int h = 0; h < 2; ++h) {
             mbar_init(acc_free(h), 2 * kEpiWarps);   // every epilogue warp of both CTAs
             mbar_init(d_full(h), 2);
@@ -399,13 +399,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
             if (write_t) put_split(x0, lo_off, (t_col >> 3) * kChunk + rowp * 16 + (t_col & 7) * 2, tval);
         };
         // the layer-0 operand is complete and the head accumulators are drained: every barrier the issuers wait on gets one
-        // phase (warp (q, cs) arrives for the operand quarters cs and 2 + cs, so that each collects its 4 + 4 arrivals)
+        // phase
         auto arrive_all = [&]() {
             if (lane == 0) {
                 arrive_leader(acc_free(0));
                 arrive_leader(acc_free(1));
-                arrive_leader(a_ready(cs));
-                arrive_leader(a_ready(2 + cs));
+                for (int kq = 0; kq < 4; ++kq) arrive_leader(a_ready(kq));
             }
         };
 
@@ -461,50 +460,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
                         par_d[h] ^= 1;
                         tc_fence_after();
                         tr.mark(0x200 + l * 2 + h);
-                        // z = main + small accumulator (fp32, round-to-nearest) of both 16-row groups of this warp's lane quarter
-                        float z[2][32];
-                        const uint32_t col0 = (uint32_t)(h * 128 + cs * 64);
+                        // z = main + small accumulator (fp32, round-to-nearest) of both 16-row groups of this warp's lane quarter.
+                        // The 128 columns of the half are the operand quarters 2h and 2h + 1; ALL eight warps take 32 columns of
+                        // quarter 2h first and of quarter 2h + 1 afterwards (slice cs of each), so that the next layer's MMAs over
+                        // quarter 2h start while the second quarter is still being written.
+                        float z[2][2][16];   // [quarter part][row group][4 x (primal c, c+1, tangent c, c+1)]
 #pragma unroll
-                        for (int grp = 0; grp < 2; ++grp) {
-                            uint32_t zm[32], zs[32];
-                            const uint32_t tb = lane_addr + ((uint32_t)(grp * 16) << 16) + col0;
-                            tmem_ld_16x256b_x8(tb, zm);
-                            tmem_ld_16x256b_x8(tb + 256, zs);
-                            tmem_ld_wait_dep(zm);
-                            tmem_ld_wait_dep(zs);
+                        for (int part = 0; part < 2; ++part) {
+                            const uint32_t colp = (uint32_t)(h * 128 + part * 64 + cs * 32);
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) z[grp][i] = __uint_as_float(zm[i]) + __uint_as_float(zs[i]);
+                            for (int grp = 0; grp < 2; ++grp) {
+                                uint32_t zm[16], zs[16];
+                                const uint32_t tb = lane_addr + ((uint32_t)(grp * 16) << 16) + colp;
+                                tmem_ld_16x256b_x4(tb, zm);
+                                tmem_ld_16x256b_x4(tb + 256, zs);
+                                tmem_ld_wait_dep16(zm);
+                                tmem_ld_wait_dep16(zs);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) z[part][grp][i] = __uint_as_float(zm[i]) + __uint_as_float(zs[i]);
+                            }
                         }
                         // the accumulator half is in registers: the next layer's MMAs may overwrite it
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) arrive_leader(acc_free(h));
                         tr.mark(0x500 + l * 2 + h);
-                        if (h == 0) {   // in-place update: wait until half 1's MMAs are past this warp's operand columns
-                            mbar_wait(ka_done(cs), (par_k >> cs) & 1);
-                            par_k ^= 1u << cs;
-                        }
 #pragma unroll
-                        for (int grp = 0; grp < 2; ++grp) {
-                            // lane i addresses row i%8 of matrix i/8: matrices 0/1 = primal/tangent rows of chunk k,
-                            // matrices 2/3 = the same of chunk k+1
-                            const uint32_t rowa = (uint32_t)(q * 32 + grp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8);
-                            uint32_t addr = smem_u32(sA) + (uint32_t)((col0 >> 3) + (lane >> 4)) * kChunk + rowa * 16;
-#pragma unroll
-                            for (int k = 0; k < 8; k += 2) {
-                                uint32_t wh[4], wl[4];
-#pragma unroll
-                                for (int e = 0; e < 2; ++e)
-                                    split4(z[grp][4 * (k + e)], z[grp][4 * (k + e) + 1], z[grp][4 * (k + e) + 2], z[grp][4 * (k + e) + 3],
-                                           wh[2 * e], wh[2 * e + 1], wl[2 * e], wl[2 * e + 1]);
-                                stmatrix_x4(addr, wh[0], wh[1], wh[2], wh[3]);
-                                stmatrix_x4(addr + a_tile_bytes, wl[0], wl[1], wl[2], wl[3]);
-                                addr += 2 * kChunk;
+                        for (int part = 0; part < 2; ++part) {
+                            if (h == 0) {   // in-place update: wait until half 1's MMAs are past this operand quarter
+                                mbar_wait(ka_done(part), (par_k >> part) & 1);
+                                par_k ^= 1u << part;
                             }
+                            const uint32_t colp = (uint32_t)(h * 128 + part * 64 + cs * 32);
+#pragma unroll
+                            for (int grp = 0; grp < 2; ++grp) {
+                                // lane i addresses row i%8 of matrix i/8: matrices 0/1 = primal/tangent rows of chunk k,
+                                // matrices 2/3 = the same of chunk k+1
+                                const uint32_t rowa = (uint32_t)(q * 32 + grp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8);
+                                uint32_t addr = smem_u32(sA) + (uint32_t)((colp >> 3) + (lane >> 4)) * kChunk + rowa * 16;
+#pragma unroll
+                                for (int k = 0; k < 4; k += 2) {
+                                    uint32_t wh[4], wl[4];
+#pragma unroll
+                                    for (int e = 0; e < 2; ++e)
+                                        split4(z[part][grp][4 * (k + e)], z[part][grp][4 * (k + e) + 1], z[part][grp][4 * (k + e) + 2],
+                                               z[part][grp][4 * (k + e) + 3], wh[2 * e], wh[2 * e + 1], wl[2 * e], wl[2 * e + 1]);
+                                    stmatrix_x4(addr, wh[0], wh[1], wh[2], wh[3]);
+                                    stmatrix_x4(addr + a_tile_bytes, wl[0], wl[1], wl[2], wl[3]);
+                                    addr += 2 * kChunk;
+                                }
+                            }
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) arrive_leader(a_ready(2 * h + part));
                         }
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) arrive_leader(a_ready(2 * h + cs));
                         tr.mark(0x300 + l * 2 + h);
                     }
                 }
