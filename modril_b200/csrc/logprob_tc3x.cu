@@ -176,7 +176,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     uint2* sRingRec = reinterpret_cast<uint2*>(smem + p.off_rrec);  // [n_blocks] {offset, bytes} of the producer's loads
     uint8_t* sRing = smem + p.off_ring;
     uint8_t* sTrace = smem + p.off_trace;
-    const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+    const bool tracing = p.trace != nullptr && blockIdx.x < 2;   // cluster 0: the leader's roles, and the peer's epilogue warp 0 (as role 4)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();          // 0 = leader (issues the MMAs of the pair)
@@ -250,7 +250,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            LTracer tr; tr.init(sTrace, 3, tracing);
+            LTracer tr; tr.init(sTrace, 3, tracing && blockIdx.x == 0);
             for (long long duo = cluster_id; duo < n_duos; duo += n_clusters) {
                 const uint8_t* wbase = p.wpack[duo % p.n_roles] + (size_t)cta_rank * p.rank_stride;
                 for (int step = 0; step < p.n_steps; ++step) {
@@ -301,7 +301,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
             uint32_t phase = 0;
             const uint32_t ring_lo = smem_u32(sRing) >> 4;
             constexpr uint32_t kDescHi = (uint32_t)(128 >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
-            LTracer tr; tr.init(sTrace, 1 + st, tracing && x == 0);           // roles 1 / 2: first issuer of stream 0 / 1
+            LTracer tr; tr.init(sTrace, 1 + st, tracing && blockIdx.x == 0 && x == 0);           // roles 1 / 2: first issuer of stream 0 / 1
             for (long long duo = cluster_id; duo < n_duos; duo += n_clusters) {
                 for (int step = 0; step < p.n_steps; ++step) {
                     tr.arm(duo == cluster_id && step == p.trace_step);
@@ -628,7 +628,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) logprob
     if (tracing)
         for (int i = threadIdx.x; i < 4 * kTraceCap; i += kThreads) {
             const uint2 v = reinterpret_cast<const uint2*>(sTrace)[i];
-            p.trace[i] = ((unsigned long long)v.x << 32) | v.y;
+            p.trace[(size_t)blockIdx.x * 4 * kTraceCap + i] = ((unsigned long long)v.x << 32) | v.y;
         }
     cluster_sync_all();   // the leader's last MMAs read the peer's shared memory: nobody leaves or frees TMEM early
     if (warp == 0) {
@@ -925,8 +925,8 @@ int launch_logprob_tc3x(const ScoreArgs& a, cudaStream_t stream) {
             return FRL_ERR_UNSUPPORTED;
         }
         unsigned long long* d = nullptr;
-        FRL_CUDA(cudaMalloc(&d, 4 * kTraceCap * sizeof(unsigned long long)));
-        FRL_CUDA(cudaMemset(d, 0, 4 * kTraceCap * sizeof(unsigned long long)));
+        FRL_CUDA(cudaMalloc(&d, 8 * kTraceCap * sizeof(unsigned long long)));
+        FRL_CUDA(cudaMemset(d, 0, 8 * kTraceCap * sizeof(unsigned long long)));
         p.trace = d;
         p.trace_step = getenv("FRL_TC_TRACE_STEP") ? atoi(getenv("FRL_TC_TRACE_STEP")) : std::min(10, p.n_steps - 1);
         p.off_trace = (uint32_t)smem_bytes;
@@ -934,11 +934,11 @@ int launch_logprob_tc3x(const ScoreArgs& a, cudaStream_t stream) {
         int rc = q_launch(p, smem_bytes + 4 * kTraceCap * 8);
         if (rc != FRL_OK) return rc;
         FRL_CUDA(cudaDeviceSynchronize());
-        std::vector<unsigned long long> h(4 * kTraceCap);
+        std::vector<unsigned long long> h(8 * kTraceCap);
         FRL_CUDA(cudaMemcpy(h.data(), d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         cudaFree(d);
         if (FILE* f = fopen(tp, "w")) {
-            for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < 8; ++r)   // 0-3: leader roles; 4: the peer CTA's epilogue warp 0 (its own SM clock)
                 for (int i = 0; i < kTraceCap && h[(size_t)r * kTraceCap + i]; ++i)
                     fprintf(f, "%d %llx %llu\n", r, h[(size_t)r * kTraceCap + i] >> 32, h[(size_t)r * kTraceCap + i] & 0xFFFFFFFFull);
             fclose(f);

@@ -12,12 +12,14 @@ for line in open(sys.argv[1]):
     r, tag, clk = line.split()
     if 0 < int(tag, 16) < 0x1000:
         rows[int(r)].append((int(tag, 16), int(clk)))
-t0 = min(c for ev in rows.values() for _, c in ev)
-names = {0: "epilogue warp 0 (leader)", 1: "issuer main stream", 2: "issuer small stream", 3: "producer (leader)"}
-for r in (0, 1, 2, 3):
+t0 = min(c for r_, ev in rows.items() if r_ < 4 for _, c in ev)
+t0_peer = min([c for _, c in rows.get(4, [])] or [0])
+names = {0: "epilogue warp 0 (leader)", 1: "issuer main stream", 2: "issuer small stream", 3: "producer (leader)",
+         4: "epilogue warp 0 (PEER CTA: another SM clock -- compare durations, not absolute stamps)"}
+for r in (0, 1, 2, 3, 4):
     print(f"--- {names[r]}")
     prev = None
     for t, c in rows[r]:
-        c = (c - t0) & 0xFFFFFFFF
+        c = (c - (t0_peer if r == 4 else t0)) & 0xFFFFFFFF
         print(f"   {t:#06x} @{c:7d}" + (f"  (+{c - prev})" if prev is not None else ""))
         prev = c
